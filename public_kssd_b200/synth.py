@@ -1,0 +1,190 @@
+"""Deterministic synthetic inputs (genomes, FASTA/FASTQ text, sketches) for tests and bench.py.
+
+Everything is a pure function of integer seeds through a splitmix64 counter hash, so the same bytes
+come out on every box and numpy version (golden fixtures under tests/golden/ depend on that).
+Shapes follow SURVEY.md s8(d): clusters of genomes derived from an ancestor by i.i.d. substitutions
+(mirrors test_fna's seq_mutX), 80-column FASTA, optional N runs / soft-masking / many contigs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = (x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def _stream(seed: int, n: int, salt: int = 0) -> np.ndarray:
+    """n 64-bit pseudo-random words for (seed, salt)."""
+    base = np.uint64((seed * 0x9E3779B97F4A7C15 + salt * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        return splitmix64(np.arange(n, dtype=np.uint64) + base)
+
+
+def make_shuf_table(subk: int, seed: int) -> np.ndarray:
+    """Deterministic permutation of 0..16^subk-1 usable as a .shuf payload."""
+    n = 1 << (4 * subk)
+    h = _stream(seed, n, salt=77)
+    order = np.argsort(h, kind="stable")
+    perm = np.empty(n, dtype=np.int32)
+    perm[order] = np.arange(n, dtype=np.int32)
+    return perm
+
+
+def random_bases(n: int, seed: int) -> np.ndarray:
+    """uint8 codes 0..3."""
+    return (_stream(seed, n, salt=1) >> np.uint64(33)).astype(np.uint8) & 3
+
+
+def mutate(bases: np.ndarray, rate: float, seed: int) -> np.ndarray:
+    """i.i.d. substitutions at `rate` (always to a different base)."""
+    r = _stream(seed, bases.size, salt=2)
+    hit = (r >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53)) < rate
+    shift = ((r & np.uint64(0xFF)) % np.uint64(3)).astype(np.uint8) + 1
+    out = bases.copy()
+    out[hit] = (out[hit] + shift[hit]) & 3
+    return out
+
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def to_fasta(bases: np.ndarray, name: str = "seq", width: int = 80, crlf: bool = False) -> np.ndarray:
+    """One-contig FASTA text as a uint8 array: '>name\\n' + lines of `width` + final newline."""
+    n = bases.size
+    seq = _ACGT[bases]
+    eol = b"\r\n" if crlf else b"\n"
+    nl = len(eol)
+    if width <= 0:
+        body = np.concatenate([seq, np.frombuffer(eol, dtype=np.uint8)])
+    else:
+        nlines = (n + width - 1) // width
+        body = np.empty(n + nlines * nl, dtype=np.uint8)
+        full = n // width
+        if full:
+            blk = body[: full * (width + nl)].reshape(full, width + nl)
+            blk[:, :width] = seq[: full * width].reshape(full, width)
+            blk[:, width:] = np.frombuffer(eol, dtype=np.uint8)
+        rem = n - full * width
+        if rem:
+            tail = body[full * (width + nl):]
+            tail[:rem] = seq[full * width:]
+            tail[rem:] = np.frombuffer(eol, dtype=np.uint8)
+    hdr = np.frombuffer(b">" + name.encode() + eol, dtype=np.uint8)
+    return np.concatenate([hdr, body])
+
+
+def messy_fasta(nbases: int, seed: int, ncontigs: int = 7, width: int = 60, n_rate: float = 0.002,
+                lower_frac: float = 0.2, crlf: bool = False, iupac: bool = True) -> np.ndarray:
+    """Many-contig FASTA with N runs, soft-masked stretches, IUPAC codes, odd bytes and blank lines --
+    the shapes SURVEY.md s8a S1 / A5-A6 list as edge cases."""
+    parts = []
+    per = max(nbases // ncontigs, 50)
+    for c in range(ncontigs):
+        b = random_bases(per + 13 * c, seed * 1000 + c)
+        txt = _ACGT[b].copy()
+        r = _stream(seed * 1000 + c, txt.size, salt=5)
+        u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+        # soft-masked blocks
+        blk = (np.arange(txt.size) // 97) % 5 == (c % 5)
+        if lower_frac > 0:
+            txt[blk] |= 0x20
+        # N runs: start with prob n_rate/8, length 1..16
+        starts = np.nonzero(u < n_rate / 8)[0]
+        for s0 in starts:
+            ln = int(r[s0] & np.uint64(15)) + 1
+            txt[s0:s0 + ln] = ord("N") if (int(r[s0]) >> 8) & 1 else ord("n")
+        if iupac:
+            odd = np.nonzero((u > 0.5) & (u < 0.5 + n_rate / 4))[0]
+            alphabet = np.frombuffer(b"RYKMSWBDHVryk*-.0 9", dtype=np.uint8)
+            txt[odd] = alphabet[(r[odd] >> np.uint64(20)).astype(np.int64) % alphabet.size]
+        eol = b"\r\n" if crlf else b"\n"
+        w = width + (c % 3) * 10
+        lines = [b">contig_%d some description > with gt ACGTACGTACGTACGTACGTACGTACGT len=%d" % (c, txt.size) + eol]
+        tb = txt.tobytes()
+        for i in range(0, len(tb), w):
+            lines.append(tb[i:i + w] + eol)
+        if c % 2 == 1:
+            lines.append(eol)           # blank line between contigs
+        parts.append(b"".join(lines))
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+
+
+def cluster_genomes(n_genomes: int, genome_len: int, seed: int, cluster_size: int = 20,
+                    min_rate: float = 0.001, max_rate: float = 0.1):
+    """Yield (name, bases) for n_genomes genomes arranged as clusters of mutated copies of an ancestor."""
+    n_clusters = (n_genomes + cluster_size - 1) // cluster_size
+    g = 0
+    for c in range(n_clusters):
+        anc = random_bases(genome_len, seed * 7919 + c)
+        for m in range(cluster_size):
+            if g >= n_genomes:
+                return
+            if m == 0:
+                b = anc
+            else:
+                rate = min_rate * (max_rate / min_rate) ** ((m - 1) / max(cluster_size - 2, 1))
+                b = mutate(anc, rate, seed * 104729 + g)
+            yield f"c{c}_m{m}", b
+            g += 1
+
+
+def to_fastq(bases: np.ndarray, n_reads: int, read_len: int, seed: int, err: float = 0.005,
+             n_rate: float = 0.001, qual_lo: int = 35, qual_hi: int = 73, trailing_newline: bool = True) -> np.ndarray:
+    """4-line FASTQ of reads sampled uniformly from `bases` (forward strand only), Phred+33 qualities."""
+    r = _stream(seed, n_reads, salt=9)
+    starts = (r % np.uint64(max(bases.size - read_len, 1))).astype(np.int64)
+    idx = starts[:, None] + np.arange(read_len)[None, :]
+    rb = bases[idx]
+    rr = _stream(seed, n_reads * read_len, salt=10).reshape(n_reads, read_len)
+    u = (rr >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+    sub = u < err
+    rb = np.where(sub, (rb + 1 + ((rr & np.uint64(0xFF)) % np.uint64(3)).astype(np.uint8)) & 3, rb)
+    txt = _ACGT[rb]
+    txt = np.where((u > 0.5) & (u < 0.5 + n_rate), np.uint8(ord("N")), txt)
+    qual = (qual_lo + ((rr >> np.uint64(40)) % np.uint64(qual_hi - qual_lo + 1)).astype(np.int64)).astype(np.uint8)
+    recs = []
+    tb, qb = txt.tobytes(), qual.tobytes()
+    for i in range(n_reads):
+        recs.append(b"@r%d\n" % i + tb[i * read_len:(i + 1) * read_len] + b"\n+\n" + qb[i * read_len:(i + 1) * read_len] + b"\n")
+    out = b"".join(recs)
+    if not trailing_newline:
+        out = out[:-1]
+    return np.frombuffer(out, dtype=np.uint8).copy()
+
+
+def synth_sketches(n_genomes: int, codes_per_genome: int, seed: int, code_bits: int = 28, cluster_size: int = 20,
+                   min_div: float = 0.001, max_div: float = 0.1, klen: int = 20):
+    """Sketches without sequences (SURVEY.md s8d cfg 3): per cluster an ancestor set of codes; each member keeps an
+    ancestor code with probability (1-d)^klen and replaces the rest with fresh random codes.
+    Returns (codes uint32 concatenated, index uint64[n+1]); each genome's codes are sorted unique."""
+    n_clusters = (n_genomes + cluster_size - 1) // cluster_size
+    mask = np.uint64((1 << code_bits) - 1)
+    chunks, counts = [], []
+    g = 0
+    for c in range(n_clusters):
+        anc = np.unique((_stream(seed * 31 + c, codes_per_genome, salt=20) & mask).astype(np.uint32))
+        for m in range(cluster_size):
+            if g >= n_genomes:
+                break
+            if m == 0:
+                s = anc
+            else:
+                d = min_div * (max_div / min_div) ** ((m - 1) / max(cluster_size - 2, 1))
+                keep_p = (1.0 - d) ** klen
+                r = _stream(seed * 1009 + g, anc.size, salt=21)
+                u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+                fresh = (_stream(seed * 2003 + g, anc.size, salt=22) & mask).astype(np.uint32)
+                s = np.unique(np.where(u < keep_p, anc, fresh))
+            chunks.append(s)
+            counts.append(s.size)
+            g += 1
+    index = np.zeros(n_genomes + 1, dtype=np.uint64)
+    np.cumsum(np.asarray(counts, dtype=np.uint64), out=index[1:])
+    return np.concatenate(chunks).astype(np.uint32), index
