@@ -1,0 +1,200 @@
+/*
+ * kssd_b200.h -- C-ABI of libkssd_b200.so: the B200 (sm_100a) implementation of Kssd's
+ * sketch -> index -> compare hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (yhg926/public_kssd) has no FFI or plugin API: its hot path is three in-process
+ * C seams driven by file-scope globals.  Each entry point below names the seam
+ * (reference file:line, paths relative to the reference tree) it replaces; INTEGRATION.md shows
+ * the calls a maintainer would put at those lines.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative KSSD_E_* code; kssd_last_error() gives
+ *     the message for the calling thread.  (The reference calls err(errno, ...) and exits; the
+ *     codes map 1:1 onto those exits so a host can keep that behaviour.)
+ *   - "host" buffers are ordinary (ideally pinned) host memory; "dev" buffers are device memory
+ *     on the context's device.  Caller owns every buffer it passes in; results live in opaque
+ *     handles until copied out and freed.
+ *   - one context = one device = one CUDA stream; contexts are independent (one per GPU rank).
+ *   - there is NO CPU fallback: without a usable sm_100 device kssd_ctx_create fails.
+ */
+#ifndef KSSD_B200_H
+#define KSSD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSSD_OK 0
+#define KSSD_E_INVAL (-1)      /* bad argument                                                   */
+#define KSSD_E_CUDA (-2)       /* CUDA runtime failure / no device                               */
+#define KSSD_E_PRIMER (-3)     /* get_hashsz(): primer_ind out of range  (command_dist.c:221-232) */
+#define KSSD_E_CROWD (-4)      /* "the context space is too crowd"       (iseq2comem.c:262-263)   */
+#define KSSD_E_HEADER_EOF (-5) /* "can not find seqences head start from '>'" (iseq2comem.c:233)  */
+#define KSSD_E_MISMATCH (-6)   /* query args not match ref args          (command_dist.c:701-706) */
+#define KSSD_E_NOMEM (-7)
+#define KSSD_E_NNEIGH (-8)     /* neighborN_max > NREF or > ref_num      (command_dist.c:1196-98) */
+
+const char *kssd_last_error(void);
+const char *kssd_version(void);
+/* number of kernels launched by this library in the calling process since load (bench.py) */
+uint64_t kssd_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Context: replaces read_dim_shuffle_file (command_shuffle.c:192-207), get_hashsz
+ * (command_dist.c:217-236) and seq2co_global_var_initial (iseq2comem.c:54-77) -- the globals
+ * `dim_shuffle`, `hashsize`, `hashlimit`, `component_num` become fields of the context.
+ * shuf_table: the .shuf payload, int32[16^subk] on the host (copied; may be freed afterwards).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kssd_ctx kssd_ctx_t;
+
+typedef struct kssd_ctx_info {
+    int32_t k, subk, drlevel, component_sz;
+    int32_t component_num, comp_code_bits;
+    uint32_t dim_end;              /* max(16^(subk-drlevel), 4096)                              */
+    uint32_t hashsize, hashlimit;  /* primer[...] and hashsize*0.6, as in the reference         */
+    uint32_t n_sampled;            /* |{d : shuf[d] < dim_end}|                                  */
+    int32_t device, sm_count;
+} kssd_ctx_info_t;
+
+int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf_table, int k, int subk,
+                    int drlevel, int component_sz);
+void kssd_ctx_destroy(kssd_ctx_t *ctx);
+int kssd_ctx_info(const kssd_ctx_t *ctx, kssd_ctx_info_t *info);
+/* the CUDA stream (cudaStream_t) all work of this context is issued on, for event timing */
+void *kssd_ctx_stream(const kssd_ctx_t *ctx);
+int kssd_ctx_sync(const kssd_ctx_t *ctx);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Stage I -- sequence -> sketch.  Replaces, per genome, the pair
+ *     co = fasta2co(seqfname, CO[tid], pipecmd)            iseq2comem.c:188   (KSSD_MODE_FASTA)
+ *     co = uniq_fasta2co(...)                              iseq2comem.c:616   (KSSD_MODE_FASTA_UNIQ)
+ *     co = fastq2co(..., Q, M)                             iseq2comem.c:277   (KSSD_MODE_FASTQ)
+ *     co = mt_shortreads2koc(...)                          iseq2comem.c:554   (KSSD_MODE_FASTQ_ABUND)
+ *     n  = wrt_co2cmpn_use_inn_subctx / write_fqco2file / write_fqkoc2files(cofname, co)
+ *                                                          iseq2comem.c:525 / :499 / :435
+ * as called from run_stageI (command_dist.c:277-310), for a whole batch of genomes at once.
+ * Input: the decompressed text of n genomes laid out in one byte buffer; genome g occupies
+ * [goff[g], goff[g]+glen[g]); goff[g] must be a multiple of 16.
+ * Output (per component c, exactly the content of combco.<c> / combco.index.<c> / combco.<c>.a,
+ * command_dist.c:331-354) with each genome's ids in ASCENDING order (the reference emits hash-slot
+ * order; the set is identical, and `ord` lets a host replay slot order byte-for-byte).
+ * ------------------------------------------------------------------------------------------ */
+enum { KSSD_MODE_FASTA = 0, KSSD_MODE_FASTA_UNIQ = 1, KSSD_MODE_FASTQ = 2, KSSD_MODE_FASTQ_ABUND = 3 };
+
+typedef struct kssd_sketch_opts {
+    int32_t mode;        /* KSSD_MODE_*                                                          */
+    int32_t Q;           /* fastq: minimum raw quality byte (-Q), iseq2comem.c:312               */
+    int32_t M;           /* fastq: minimum occurrence (-n, 1..14), iseq2comem.c:336-346          */
+    int32_t want_ord;    /* also return first-occurrence byte offsets (for slot-order replay)    */
+    uint32_t span_bytes; /* 0 = auto; work-unit size the batch is cut into                       */
+    uint32_t reserved;
+} kssd_sketch_opts_t;
+
+typedef struct kssd_sketch kssd_sketch_t; /* result handle */
+
+/* seq on the HOST: copies to the device inside the call (end-to-end path). */
+int kssd_sketch_batch_host(kssd_ctx_t *ctx, const uint8_t *seq, size_t seq_bytes,
+                           const uint64_t *goff, const uint64_t *glen, int n_genomes,
+                           const kssd_sketch_opts_t *opts, kssd_sketch_t **out);
+/* seq already on the DEVICE (kernel-only path; goff/glen stay on the host). */
+int kssd_sketch_batch_dev(kssd_ctx_t *ctx, const uint8_t *seq_dev, size_t seq_bytes,
+                          const uint64_t *goff, const uint64_t *glen, int n_genomes,
+                          const kssd_sketch_opts_t *opts, kssd_sketch_t **out);
+/* total ids in component c, or negative error */
+int64_t kssd_sketch_count(const kssd_sketch_t *s, int comp);
+/* per-genome status: 0 ok, KSSD_E_CROWD, KSSD_E_HEADER_EOF (the reference would have exited) */
+int kssd_sketch_status(const kssd_sketch_t *s, int32_t *status_out /* n_genomes */);
+/* copy component c to host: ids[count], index[n_genomes+1], optional abund[count] (mode 3),
+ * optional ord[count] (want_ord). NULL pointers are skipped. */
+int kssd_sketch_fetch(const kssd_sketch_t *s, int comp, uint32_t *ids, uint64_t *index,
+                      uint16_t *abund, uint64_t *ord);
+/* device pointers of component c (valid until free): ids (u32), per-genome index (u64[n+1]) */
+int kssd_sketch_dev_ptrs(const kssd_sketch_t *s, int comp, const uint32_t **ids_dev,
+                         const uint64_t **index_dev);
+/* k-mers that passed sampling before dedup (all components), and device time of the scan kernel */
+int kssd_sketch_stats(const kssd_sketch_t *s, uint64_t *n_occurrences, float *scan_kernel_ms);
+void kssd_sketch_free(kssd_sketch_t *s);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Stage II -- sketch -> inverted index.  Replaces combco2mco (co2mco.c:25-77) for one component:
+ * input = combco.<c> (u32 codes) + combco.index.<c> (u64[n+1]); output = the postings of mco.<c>
+ * (gids ascending within a code, codes ascending) as a CSR over the codes that occur, plus an
+ * expander that writes the reference's dense inclusive table mco.index.<c> (16^component_sz u64).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kssd_index kssd_index_t;
+
+int kssd_index_build_host(kssd_ctx_t *ctx, const uint32_t *combco, const uint64_t *cbdcoindex,
+                          int n_genomes, kssd_index_t **out);
+int kssd_index_build_dev(kssd_ctx_t *ctx, const uint32_t *combco_dev, const uint64_t *cbdcoindex_dev,
+                         int n_genomes, uint64_t n_codes, kssd_index_t **out);
+int kssd_index_sizes(const kssd_index_t *ix, uint64_t *n_unique, uint64_t *n_postings, int *n_genomes);
+/* CSR to host: ucodes[n_unique], uoff[n_unique+1] (exclusive), gids[n_postings] (= mco.<c>) */
+int kssd_index_fetch(const kssd_index_t *ix, uint32_t *ucodes, uint64_t *uoff, uint32_t *gids);
+/* dense inclusive prefix table exactly as fwrite'n at co2mco.c:57-61; dense_out has 16^component_sz
+ * entries on the host. */
+int kssd_index_fetch_dense(const kssd_index_t *ix, uint64_t *dense_out);
+/* load an index back from the reference's files (mco.<c> postings + dense mco.index.<c>) */
+int kssd_index_from_dense_host(kssd_ctx_t *ctx, const uint64_t *dense_incl, const uint32_t *gids,
+                               uint64_t n_postings, int n_genomes, kssd_index_t **out);
+void kssd_index_free(kssd_index_t *ix);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Stage III -- query x reference shared k-mer counts and statistics.  Replaces the hot loop of
+ * mco_cbdco_nobin_dist (command_dist.c:763-790) and the numeric part of output_ctrl
+ * (command_dist.c:1251-1287) / top-N selection of dist_print_nobin (command_dist.c:1212-1227).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kssd_dist kssd_dist_t; /* a Q x R job: accumulates over components */
+
+/* ref_ctx_ct / qry_ctx_ct: per-genome sketch sizes (cofiles.stat / mcofiles.stat ctx_ct lists) */
+int kssd_dist_create(kssd_ctx_t *ctx, int n_qry, int n_ref, const uint32_t *qry_ctx_ct,
+                     const uint32_t *ref_ctx_ct, kssd_dist_t **out);
+/* add one component: ct[q][r] += |{codes of q} n postings| (command_dist.c:779-784).
+ * Query sketch given as combco.<c>/combco.index.<c> content. */
+int kssd_dist_accumulate_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes,
+                              const uint64_t *qindex);
+int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev,
+                             const uint64_t *qindex_dev, uint64_t n_qcodes);
+/* the sharedk_ct.dat matrix, uint32[Q][R] row-major (command_dist.c:708-748) */
+int kssd_dist_fetch_counts(const kssd_dist_t *d, uint32_t *ct_out);
+const uint32_t *kssd_dist_counts_dev(const kssd_dist_t *d);
+
+enum { KSSD_METRIC_JACCARD = 0, KSSD_METRIC_CONTAINMENT = 1 };
+
+typedef struct kssd_stat_opts {
+    int32_t metric;      /* -M: KSSD_METRIC_*                                                    */
+    int32_t correction;  /* --correction 0/1                                                     */
+    int32_t kmerlen;     /* 2k   (co_dstat.kmerlen)                                              */
+    int32_t dim_rd_len;  /* 2L   (co_dstat.dim_rd_len)                                           */
+    double dthreshold;   /* -D: rows with dist > dthreshold are suppressed                       */
+    int32_t n_neighbors; /* -N: 0 = all refs, else best N per query by raw metric                */
+    int32_t skip_zero;   /* extension: 1 = also suppress rows with shared == 0                   */
+} kssd_stat_opts_t;
+
+/* one output row; the doubles are exactly the values output_ctrl formats with %lf / %E */
+typedef struct kssd_stat_row {
+    uint32_t qry, ref;
+    uint32_t shared, rs_u; /* XnY_size, (unsigned)rs                                             */
+    uint32_t ref_size, qry_size;
+    double metric, dist, pvalue, fdr;
+    double ci_metric_lo, ci_metric_hi, ci_dist_lo, ci_dist_hi;
+} kssd_stat_row_t;
+
+/* Runs the fused statistics kernel over the count matrix.  Rows come out query-major, refs
+ * ascending (or best-first for -N), as dist_print_nobin writes them.  Two-call pattern:
+ * kssd_dist_stats() computes on the device and returns the number of rows; kssd_dist_fetch_stats
+ * copies them out. */
+int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *opts);
+int kssd_dist_fetch_stats(const kssd_dist_t *d, kssd_stat_row_t *rows_out);
+void kssd_dist_free(kssd_dist_t *d);
+
+/* device time (ms, CUDA events on the context stream) of the last scan / index / count / stats
+ * kernel sequence issued through this context; which = 0 sketch scan, 1 sketch total,
+ * 2 index build, 3 dist counts, 4 dist stats */
+float kssd_ctx_last_ms(const kssd_ctx_t *ctx, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSSD_B200_H */

@@ -1,0 +1,305 @@
+// index_dist.cuh -- Stage II (inverted index) and Stage III (shared counts + statistics) kernels.
+#pragma once
+#include "kssd_device.cuh"
+
+namespace kssd {
+
+// ------------------------------------------------------------------------------------------------
+// Stage II helpers.  combco2mco (reference co2mco.c:42-55) appends genome j to the list of every
+// code of genome j, j ascending: postings = gids ordered by (code, gid).  Here: tag each code with
+// its gid, stable LSD radix sort by code (gid order is preserved inside a code), run heads -> CSR.
+// ------------------------------------------------------------------------------------------------
+__global__ void expand_gid_kernel(const uint64_t *__restrict__ index, int n_genomes, uint64_t n, uint32_t *__restrict__ gid)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = n_genomes;          // last j with index[j] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (index[mid] <= i) lo = mid; else hi = mid;
+    }
+    gid[i] = (uint32_t)lo;
+}
+
+__global__ void head_flags_kernel(const uint32_t *__restrict__ codes, uint64_t n, uint32_t *__restrict__ flags)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || codes[i] != codes[i - 1]) ? 1u : 0u;
+}
+
+__global__ void csr_scatter_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ flags,
+                                   const uint32_t *__restrict__ pos, uint64_t n, uint32_t *__restrict__ ucodes,
+                                   uint32_t *__restrict__ uoff)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i]) { ucodes[pos[i]] = codes[i]; uoff[pos[i]] = (uint32_t)i; }
+}
+
+// Dense EXCLUSIVE start table over the whole code space of one component:
+//   dense[c] = #postings with code < c,  c in [0, space]   (space = 16^COMPONENT_SZ)
+// One warp per unique code fills the (coalesced) range that ends at that code.
+__global__ void dense_fill_kernel(const uint32_t *__restrict__ ucodes, const uint32_t *__restrict__ uoff, uint32_t nuniq,
+                                  uint32_t n_postings, uint64_t space, uint32_t *__restrict__ dense)
+{
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w > nuniq) return;
+    uint64_t from, to;     // dense[from..to] = val
+    uint32_t val;
+    if (w < nuniq) {
+        from = w == 0 ? 0 : (uint64_t)ucodes[w - 1] + 1;
+        to = ucodes[w];
+        val = uoff[w];
+    } else {
+        from = nuniq == 0 ? 0 : (uint64_t)ucodes[nuniq - 1] + 1;
+        to = space;
+        val = n_postings;
+    }
+    for (uint64_t c = from + lane; c <= to; c += 32) dense[c] = val;
+}
+
+// mco.index.<c> as the reference writes it (co2mco.c:57-61): inclusive u64 prefix, chunked
+__global__ void dense_incl64_kernel(const uint32_t *__restrict__ dense, uint64_t first, uint64_t count, uint64_t *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = dense[first + i + 1];
+}
+
+__global__ void dense_from_incl64_kernel(const uint64_t *__restrict__ incl, uint64_t first, uint64_t count, uint32_t *__restrict__ dense)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dense[first + i + 1] = (uint32_t)incl[i];
+    if (first == 0 && i == 0) dense[0] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage III.  Reference hot loop (command_dist.c:774-784): for every code of query k, walk its
+// posting list and ++ct[k*R + gid].  Here one CTA owns one (query, reference-tile) strip of the
+// count matrix in shared memory: postings are scattered with shared-memory atomics, and the strip
+// is written to HBM exactly once, coalesced -- no global atomics and no separate memset pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDistThreads = 512;
+
+template <typename CT>   // uint16_t when every query sketch is < 65536 codes, else uint32_t
+__global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
+                                                                  const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                  uint32_t n_ref, uint32_t tile_refs, uint32_t n_tiles,
+                                                                  uint32_t *__restrict__ ct, int accumulate)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CT *tile = reinterpret_cast<CT *>(smem_raw);
+    const uint32_t q = blockIdx.x / n_tiles;
+    const uint32_t t = blockIdx.x - q * n_tiles;
+    const uint32_t r0 = t * tile_refs;
+    const uint32_t r1 = min(r0 + tile_refs, n_ref);
+    const uint32_t width = r1 - r0;
+    // zero the strip (word-wise)
+    {
+        uint32_t *z = reinterpret_cast<uint32_t *>(smem_raw);
+        const uint32_t words = (width * (uint32_t)sizeof(CT) + 3) / 4;
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) z[i] = 0;
+    }
+    __syncthreads();
+    const uint64_t qs = qindex[q], qe = qindex[q + 1];
+    if (sizeof(CT) == 4) {
+        uint32_t *t32 = reinterpret_cast<uint32_t *>(smem_raw);
+        for (uint64_t i = qs + threadIdx.x; i < qe; i += blockDim.x) {
+            const uint32_t c = __ldg(&qcodes[i]);
+            const uint2 se = make_uint2(__ldg(&dense[c]), __ldg(&dense[c + 1]));
+            for (uint32_t g = se.x; g < se.y; g++) {
+                const uint32_t r = __ldg(&mco[g]);
+                if (r >= r0 && r < r1) atomicAdd(&t32[r - r0], 1u);
+            }
+        }
+    } else {
+        // 16-bit counters packed two per word: add 1 or 1<<16; cannot carry across halves because a
+        // count never exceeds the query sketch size (< 65536 on this path)
+        uint32_t *t32 = reinterpret_cast<uint32_t *>(smem_raw);
+        for (uint64_t i = qs + threadIdx.x; i < qe; i += blockDim.x) {
+            const uint32_t c = __ldg(&qcodes[i]);
+            const uint2 se = make_uint2(__ldg(&dense[c]), __ldg(&dense[c + 1]));
+            for (uint32_t g = se.x; g < se.y; g++) {
+                const uint32_t r = __ldg(&mco[g]);
+                if (r >= r0 && r < r1) {
+                    const uint32_t o = r - r0;
+                    atomicAdd(&t32[o >> 1], (o & 1u) ? 0x10000u : 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t *row = ct + (uint64_t)q * n_ref + r0;
+    if (accumulate) {
+        for (uint32_t i = threadIdx.x; i < width; i += blockDim.x) row[i] += (uint32_t)tile[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < width; i += blockDim.x) row[i] = (uint32_t)tile[i];
+    }
+}
+
+// ---- statistics (reference output_ctrl, command_dist.c:1251-1287), double precision ----
+struct StatParams {
+    int metric, correction, kmerlen, dim_rd_len, skip_zero;
+    double dthreshold;
+    double cmprsn_num;    // (double)(llong)(uint32)(ref_num*qry_num), command_dist.c:1186
+};
+
+struct StatRow {   // mirrors kssd_stat_row_t
+    uint32_t qry, ref, shared, rs_u, ref_size, qry_size;
+    double metric, dist, pvalue, fdr, ci_m_lo, ci_m_hi, ci_d_lo, ci_d_hi;
+};
+
+__device__ __forceinline__ double get_matric(int metric_kind, double y)
+{
+    return metric_kind == 0 ? 1.0 / (2.0 * y) + 0.5 : 1.0 / y;
+}
+
+// returns false when the row is suppressed
+__device__ __forceinline__ bool stat_row(const StatParams &S, uint32_t X, uint32_t Y, uint32_t I, StatRow &r)
+{
+    double rs = 0.0;
+    if (S.correction) {
+        const uint32_t xo = X - I, yo = Y - I;
+        const double base = 1.0 - 1.0 / pow(4.0, (double)(S.kmerlen - S.dim_rd_len));
+        const double px = 1.0 - pow(base, (double)xo);
+        const double py = 1.0 - pow(base, (double)yo);
+        rs = px * py * (double)(xo + yo) / (px + py - 2.0 * px * py);
+    }
+    const uint32_t tmp = S.metric == 0 ? X + Y - I : (X < Y ? X : Y);
+    const double m = ((double)I - rs) / (double)tmp;
+    double dist = log(get_matric(S.metric, m)) / (double)S.kmerlen;
+    if (dist > 1.0) dist = 1.0;
+    if (dist > S.dthreshold) return false;
+    if (S.skip_zero && I == 0) return false;
+    const double sd = sqrt(m * (1.0 - m) / (double)tmp);
+    const double pv = 0.5 * erfc(m / sd * 0.70710678118654757);   // pow(0.5,0.5) rounded to double
+    const double c1 = m - 1.96 * sd, c2 = m + 1.96 * sd;
+    r.shared = I; r.rs_u = (uint32_t)rs; r.ref_size = X; r.qry_size = Y;
+    r.metric = m; r.dist = dist; r.pvalue = pv; r.fdr = pv * S.cmprsn_num;
+    r.ci_m_lo = c1; r.ci_m_hi = c2;
+    r.ci_d_lo = log(get_matric(S.metric, c2)) / (double)S.kmerlen;
+    r.ci_d_hi = log(get_matric(S.metric, c1)) / (double)S.kmerlen;
+    return true;
+}
+
+// pass 1: kept rows per (query, block of 1024 refs); pass 2: ordered write.  Query-major, refs
+// ascending, exactly the order dist_print_nobin emits (command_dist.c:1228-1242).
+constexpr int kStatThreads = 256;
+constexpr int kStatRefsPerBlock = 1024;
+
+__global__ void __launch_bounds__(kStatThreads) stats_count_kernel(const StatParams S, const uint32_t *__restrict__ ct,
+                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                                    uint32_t n_ref, uint32_t blocks_per_row, uint32_t *__restrict__ block_counts)
+{
+    const uint32_t q = blockIdx.x / blocks_per_row;
+    const uint32_t b = blockIdx.x - q * blocks_per_row;
+    const uint32_t Y = qsz[q];
+    uint32_t kept = 0;
+    StatRow tmp;
+    for (uint32_t j = threadIdx.x; j < kStatRefsPerBlock; j += kStatThreads) {
+        const uint32_t r = b * kStatRefsPerBlock + j;
+        if (r < n_ref) kept += stat_row(S, rsz[r], Y, ct[(uint64_t)q * n_ref + r], tmp) ? 1u : 0u;
+    }
+    __shared__ uint32_t red[kStatThreads / 32];
+    kept = __reduce_add_sync(kFull, kept);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kept;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < kStatThreads / 32; i++) s += red[i];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads) stats_write_kernel(const StatParams S, const uint32_t *__restrict__ ct,
+                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                                    uint32_t n_ref, uint32_t blocks_per_row,
+                                                                    const uint64_t *__restrict__ block_offsets, StatRow *__restrict__ rows)
+{
+    const uint32_t q = blockIdx.x / blocks_per_row;
+    const uint32_t b = blockIdx.x - q * blocks_per_row;
+    const uint32_t Y = qsz[q];
+    __shared__ uint32_t wsum[kStatThreads / 32];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const uint64_t base = block_offsets[blockIdx.x];
+    for (uint32_t j0 = 0; j0 < kStatRefsPerBlock; j0 += kStatThreads) {
+        const uint32_t r = b * kStatRefsPerBlock + j0 + threadIdx.x;
+        StatRow row;
+        bool keep = false;
+        if (r < n_ref) keep = stat_row(S, rsz[r], Y, ct[(uint64_t)q * n_ref + r], row);
+        const uint32_t bal = __ballot_sync(kFull, keep);
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t before = running;
+        for (uint32_t w = 0; w < wid; w++) before += wsum[w];
+        if (keep) {
+            row.qry = q; row.ref = r;
+            rows[base + before + __popc(bal & ((1u << lane) - 1u))] = row;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t s = 0;
+            for (int w = 0; w < kStatThreads / 32; w++) s += wsum[w];
+            running += s;
+        }
+        __syncthreads();
+    }
+}
+
+// -N: best n refs per query by the raw metric with the reference's insertion rule
+// (command_dist.c:1212-1227): strictly greater than everything it passes, so ties keep the lower
+// rid first and zero-metric refs are never listed.  One CTA per query; n <= 1024.
+__global__ void __launch_bounds__(256) topn_kernel(const StatParams S, const uint32_t *__restrict__ ct, const uint32_t *__restrict__ qsz,
+                                                   const uint32_t *__restrict__ rsz, uint32_t n_ref, int nmax,
+                                                   uint32_t *__restrict__ row_counts, StatRow *__restrict__ rows)
+{
+    const uint32_t q = blockIdx.x;
+    const uint32_t Y = qsz[q];
+    __shared__ double best_m[256];
+    __shared__ int best_r[256];
+    __shared__ double last_m;
+    __shared__ int last_r;
+    __shared__ uint32_t nout;
+    if (threadIdx.x == 0) { last_m = 1e300; last_r = -1; nout = 0; }
+    __syncthreads();
+    for (int it = 0; it < nmax; it++) {
+        // next element in (metric desc, rid asc) order after (last_m, last_r), metric > 0
+        double bm = 0.0;
+        int br = -1;
+        for (uint32_t r = threadIdx.x; r < n_ref; r += blockDim.x) {
+            const uint32_t X = rsz[r], I = ct[(uint64_t)q * n_ref + r];
+            const double m = S.metric == 1 ? (double)I / (double)(X < Y ? X : Y) : (double)I / (double)(X + Y - I);
+            const bool after = (m < last_m) || (m == last_m && (int)r > last_r);
+            if (!(m > 0.0) || !after) continue;
+            if (br < 0 || m > bm || (m == bm && (int)r < br)) { bm = m; br = (int)r; }
+        }
+        best_m[threadIdx.x] = bm;
+        best_r[threadIdx.x] = br;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            int r = -1;
+            for (int i = 0; i < (int)blockDim.x; i++)
+                if (best_r[i] >= 0 && (r < 0 || best_m[i] > m || (best_m[i] == m && best_r[i] < r))) { m = best_m[i]; r = best_r[i]; }
+            last_m = m;
+            last_r = r;
+            if (r >= 0) {
+                StatRow row;
+                if (stat_row(S, rsz[r], Y, ct[(uint64_t)q * n_ref + r], row)) {
+                    row.qry = q; row.ref = (uint32_t)r;
+                    rows[(uint64_t)q * nmax + nout] = row;
+                    nout++;
+                }
+            }
+        }
+        __syncthreads();
+        if (last_r < 0) break;
+    }
+    if (threadIdx.x == 0) row_counts[q] = nout;
+}
+
+}  // namespace kssd

@@ -1,0 +1,903 @@
+// kssd_b200.cu -- host side of libkssd_b200.so: contexts, launch sequences and the C-ABI declared in
+// include/kssd_b200.h.  CUDA runtime only (no torch, no CPU compute path: every entry point needs
+// the device).  Sorting/scans of the (tiny) post-sampling streams use CUB from the CUDA toolkit;
+// the byte scan, the index expansion and the count/statistics kernels are ours.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kssd_b200.h"
+#include "index_dist.cuh"
+#include "sketch_scan.cuh"
+
+using namespace kssd;
+
+// ------------------------------------------------------------------------------------------------
+// errors, bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(KSSD_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCHED(n) g_launches.fetch_add((n), std::memory_order_relaxed)
+
+extern "C" const char *kssd_last_error(void) { return g_err.c_str(); }
+extern "C" const char *kssd_version(void) { return "kssd-b200 0.1 (sm_100a)"; }
+extern "C" uint64_t kssd_kernel_launch_count(void) { return g_launches.load(); }
+
+static const uint32_t kPrimer[25] = {   // reference global_basic.c:74-81
+    251u, 509u, 1021u, 2039u, 4093u, 8191u, 16381u, 32749u, 65521u, 131071u, 262139u, 524287u, 1048573u,
+    2097143u, 4194301u, 8388593u, 16777213u, 33554393u, 67108859u, 134217689u, 268435399u, 536870909u,
+    1073741789u, 2147483647u, 4294967291u};
+
+// grow-only device scratch buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct kssd_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    SketchParams P{};
+    kssd_ctx_info_t info{};
+    uint32_t *d_prefilter = nullptr;
+    uint2 *d_ht = nullptr;
+    // scratch
+    DevBuf seq, meta, keys, ords, keys2, ords2, flags, pos, counts, minord, cubtmp, misc;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[5] = {0, 0, 0, 0, 0};
+};
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+__global__ void count_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t n, uint32_t dim_end, uint32_t *count)
+{
+    uint32_t c = 0;
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+        const int32_t v = shuf[d];
+        c += (v >= 0 && (uint32_t)v < dim_end) ? 1u : 0u;
+    }
+    c = __reduce_add_sync(kFull, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+// S = {d : shuf[d] < dim_end}: exact hash table d -> pf, and the prefilter bitmap of S u RC(S)
+__global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t n, uint32_t dim_end, int s, uint32_t pfmask,
+                                     uint32_t *__restrict__ prefilter, uint2 *__restrict__ ht, uint32_t ht_mask)
+{
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+        const int32_t v = shuf[d];
+        if (v < 0 || (uint32_t)v >= dim_end) continue;
+        const uint32_t a = d & pfmask;
+        const uint32_t b = (uint32_t)revcomp2((uint64_t)d, 2 * s) & pfmask;
+        atomicOr(&prefilter[a >> 5], 1u << (a & 31));
+        atomicOr(&prefilter[b >> 5], 1u << (b & 31));
+        uint32_t h = mix32(d) & ht_mask;
+        for (;;) {
+            const uint32_t old = atomicCAS(&ht[h].x, kHtEmpty, d);
+            if (old == kHtEmpty) { ht[h].y = (uint32_t)v; break; }
+            h = (h + 1) & ht_mask;
+        }
+    }
+}
+
+extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf_table, int k, int subk, int drlevel,
+                               int component_sz)
+{
+    if (!out || !shuf_table) return fail(KSSD_E_INVAL, "kssd_ctx_create: null argument");
+    if (subk < 1 || subk >= 8 || k < subk || k > 16 || drlevel < 0 || drlevel > subk || k - subk > 15 || component_sz < 1 ||
+        component_sz > 7)
+        return fail(KSSD_E_INVAL, "kssd_ctx_create: unsupported (k=%d, subk=%d, drlevel=%d, COMPONENT_SZ=%d)", k, subk, drlevel,
+                    component_sz);
+    const int pi = 4 * (k - drlevel) - 8 - 7;   // CTX_SPC_USE_L = 8, command_dist.c:220
+    if (pi < 0 || pi > 24) return fail(KSSD_E_PRIMER, "get_hashsz(): primer_ind: %d out of range(0 ~ 24)", pi);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(KSSD_E_CUDA, "kssd_ctx_create: no CUDA device %d (found %d); this library has no CPU path", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(KSSD_E_CUDA, "kssd_ctx_create: device %d is sm_%d%d, need sm_100", device, prop.major, prop.minor);
+
+    kssd_ctx *c = new kssd_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CU(cudaEventCreate(&e));
+
+    SketchParams &P = c->P;
+    P.k = k; P.s = subk; P.L = drlevel;
+    P.TL = 2 * k;
+    P.out = k - subk;
+    P.hist_min_n = (P.TL - 1 + 1) / 2;
+    P.tupmask = ~0ull >> (64 - 4 * k);
+    P.undomask = ((1ull << (2 * P.out)) - 1ull) << (2 * (k + subk));
+    P.outmask = (1ull << (2 * P.out)) - 1ull;
+    P.innermask = (uint32_t)((1ull << (4 * subk)) - 1ull);
+    P.pfmask = std::min<uint32_t>(P.innermask, (1u << kPfBits) - 1u);
+    const uint64_t subspace = 1ull << (4 * (subk - drlevel));
+    P.dim_end = (uint32_t)std::max<uint64_t>(subspace, 4096);   // MIN_SUBCTX_DIM_SMP_SZ
+    P.comp_code_bits = (k - drlevel > component_sz) ? 4 * (k - drlevel - component_sz) : 0;
+    P.comp_mask = (1u << P.comp_code_bits) - 1u;
+
+    const uint32_t n = 1u << (4 * subk);
+    int32_t *d_shuf = nullptr;
+    uint32_t *d_cnt = nullptr;
+    CU(cudaMalloc(&d_shuf, (size_t)n * 4));
+    CU(cudaMalloc(&d_cnt, 4));
+    CU(cudaMemcpyAsync(d_shuf, shuf_table, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_cnt, 0, 4, c->stream));
+    count_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, d_cnt);
+    LAUNCHED(1);
+    uint32_t n_sampled = 0;
+    CU(cudaMemcpyAsync(&n_sampled, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint32_t ht_size = 1024;
+    while (ht_size < 2 * (uint64_t)n_sampled + 16) ht_size <<= 1;
+    P.ht_mask = ht_size - 1;
+    CU(cudaMalloc(&c->d_prefilter, kPfWords * 4));
+    CU(cudaMalloc(&c->d_ht, (size_t)ht_size * sizeof(uint2)));
+    CU(cudaMemsetAsync(c->d_prefilter, 0, kPfWords * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_ht, 0xff, (size_t)ht_size * sizeof(uint2), c->stream));
+    build_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, subk, P.pfmask, c->d_prefilter, c->d_ht,
+                                                                P.ht_mask);
+    LAUNCHED(1);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    cudaFree(d_shuf);
+    cudaFree(d_cnt);
+    P.prefilter = c->d_prefilter;
+    P.ht = c->d_ht;
+
+    CU(cudaFuncSetAttribute(sketch_fasta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(kPfWords * 4 + kScanWarps * sizeof(WarpQueue))));
+
+    kssd_ctx_info_t &I = c->info;
+    I.k = k; I.subk = subk; I.drlevel = drlevel; I.component_sz = component_sz;
+    I.component_num = 1 << P.comp_code_bits;
+    I.comp_code_bits = P.comp_code_bits;
+    I.dim_end = P.dim_end;
+    I.hashsize = kPrimer[pi];
+    I.hashlimit = (uint32_t)(I.hashsize * 0.6);   // LD_FCTR
+    I.n_sampled = n_sampled;
+    I.device = device;
+    I.sm_count = c->sm_count;
+    *out = c;
+    return KSSD_OK;
+}
+
+extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf *b : {&c->seq, &c->meta, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->counts, &c->minord,
+                      &c->cubtmp, &c->misc})
+        b->release();
+    cudaFree(c->d_prefilter);
+    cudaFree(c->d_ht);
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int kssd_ctx_info(const kssd_ctx_t *c, kssd_ctx_info_t *info)
+{
+    if (!c || !info) return fail(KSSD_E_INVAL, "kssd_ctx_info: null argument");
+    *info = c->info;
+    return KSSD_OK;
+}
+extern "C" void *kssd_ctx_stream(const kssd_ctx_t *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int kssd_ctx_sync(const kssd_ctx_t *c)
+{
+    if (!c) return fail(KSSD_E_INVAL, "kssd_ctx_sync: null");
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+extern "C" float kssd_ctx_last_ms(const kssd_ctx_t *c, int which) { return (c && which >= 0 && which < 5) ? c->last_ms[which] : -1.f; }
+
+// ------------------------------------------------------------------------------------------------
+// Stage I
+// ------------------------------------------------------------------------------------------------
+struct kssd_sketch {
+    kssd_ctx *ctx = nullptr;
+    int n_genomes = 0, n_comp = 1, mode = 0;
+    uint64_t n_occ = 0, total = 0;
+    float scan_ms = 0;
+    uint32_t *d_ids = nullptr;
+    uint16_t *d_abund = nullptr;
+    uint64_t *d_ord = nullptr;
+    uint64_t *d_index = nullptr;                 // n_comp * (n_genomes+1)
+    std::vector<uint64_t> comp_start;            // n_comp+1 offsets into d_ids
+    std::vector<uint64_t> index;                 // n_comp * (n_genomes+1)
+    std::vector<int32_t> status;
+};
+
+// run heads of the sorted occurrence keys: multiplicity, first-occurrence offset, keep rule per mode
+__global__ void rle_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ ords, uint32_t n, int mode, int M,
+                           uint32_t *__restrict__ flags, uint16_t *__restrict__ counts, uint64_t *__restrict__ minord)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    if (i > 0 && keys[i - 1] == key) { flags[i] = 0; return; }
+    uint32_t cnt = 1;
+    uint64_t mo = ords[i];
+    for (uint32_t j = i + 1; j < n && keys[j] == key; j++) { cnt++; mo = min(mo, ords[j]); }
+    bool keep = true;
+    if (mode == KSSD_MODE_FASTA_UNIQ) keep = cnt == 1;          // iseq2comem.c:694-695 + :540
+    else if (mode == KSSD_MODE_FASTQ) keep = cnt >= (uint32_t)M; // iseq2comem.c:336-346 + :514
+    flags[i] = keep ? 1u : 0u;
+    counts[i] = (uint16_t)min(cnt, 65535u);                      // iseq2comem.c:602-604
+    minord[i] = mo;
+}
+
+__global__ void sketch_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos,
+                                      const uint16_t *__restrict__ counts, const uint64_t *__restrict__ minord, uint32_t n, int n_genomes,
+                                      uint32_t *__restrict__ ids, uint16_t *__restrict__ abund, uint64_t *__restrict__ ord,
+                                      uint32_t *__restrict__ per_cg)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const uint64_t key = keys[i];
+    const uint32_t p = pos[i];
+    ids[p] = (uint32_t)(key & 0x0fffffffu);
+    abund[p] = counts[i];
+    ord[p] = minord[i];
+    const uint32_t comp = (uint32_t)(key >> 56), gid = (uint32_t)(key >> 28) & 0x0fffffffu;
+    atomicAdd(&per_cg[(uint64_t)comp * n_genomes + gid], 1u);
+}
+
+static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const uint64_t *goff, const uint64_t *glen, int n_genomes,
+                      const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
+{
+    const SketchParams &P = c->P;
+    const int mode = opts ? opts->mode : KSSD_MODE_FASTA;
+    if (mode != KSSD_MODE_FASTA && mode != KSSD_MODE_FASTA_UNIQ)
+        return fail(KSSD_E_INVAL, "kssd_sketch_batch: mode %d is not available in this build (FASTA modes only)", mode);
+    if (n_genomes <= 0 || n_genomes >= (1 << 28)) return fail(KSSD_E_INVAL, "kssd_sketch_batch: n_genomes=%d", n_genomes);
+    uint64_t total = 0;
+    for (int g = 0; g < n_genomes; g++) {
+        if (goff[g] % 16 || goff[g] + glen[g] > seq_bytes)
+            return fail(KSSD_E_INVAL, "kssd_sketch_batch: genome %d extent [%llu,+%llu) misaligned or outside the buffer", g,
+                        (unsigned long long)goff[g], (unsigned long long)glen[g]);
+        total += glen[g];
+    }
+    // spans: the unit a warp pulls; sized so that every warp gets several
+    uint32_t span = opts ? opts->span_bytes : 0;
+    if (span == 0) {
+        const uint64_t warps = (uint64_t)c->sm_count * kScanWarps;
+        uint64_t want = total / (warps * 6) + 1;
+        span = 4096;
+        while (span < want && span < (256u << 10)) span <<= 1;
+    }
+    if (span < 512 || (span & (span - 1))) return fail(KSSD_E_INVAL, "kssd_sketch_batch: span_bytes must be a power of two >= 512");
+    std::vector<uint32_t> span_gid;
+    std::vector<uint64_t> span_nom;
+    for (int g = 0; g < n_genomes; g++)
+        for (uint64_t o = 0; o < glen[g]; o += span) { span_gid.push_back((uint32_t)g); span_nom.push_back(goff[g] + o); }
+    const uint32_t n_spans = (uint32_t)span_gid.size();
+
+    // device metadata: goff | glen | span_nom | span_gid | gstatus | ticket | out_count
+    const size_t m_goff = 0, m_glen = m_goff + 8ull * n_genomes, m_nom = m_glen + 8ull * n_genomes,
+                 m_sgid = m_nom + 8ull * n_spans, m_stat = m_sgid + 4ull * n_spans, m_tick = m_stat + 4ull * n_genomes,
+                 m_cnt = m_tick + 4, m_end = m_cnt + 4;
+    CU(c->meta.ensure(m_end));
+    uint8_t *mb = c->meta.as<uint8_t>();
+    CU(cudaMemcpyAsync(mb + m_goff, goff, 8ull * n_genomes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(mb + m_glen, glen, 8ull * n_genomes, cudaMemcpyHostToDevice, c->stream));
+    if (n_spans) {
+        CU(cudaMemcpyAsync(mb + m_nom, span_nom.data(), 8ull * n_spans, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(mb + m_sgid, span_gid.data(), 4ull * n_spans, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemsetAsync(mb + m_stat, 0, 4ull * n_genomes + 8, c->stream));
+
+    // occurrence buffer: expected total/|sampling| ; 4x head-room, retried on overflow
+    const double rate = (double)c->info.n_sampled / (double)(1ull << (4 * P.s));
+    uint64_t cap = (uint64_t)((double)total * rate * 4.0) + (1u << 16);
+    kssd_sketch *S = new kssd_sketch();
+    S->ctx = c; S->n_genomes = n_genomes; S->n_comp = c->info.component_num; S->mode = mode;
+    uint32_t n_occ = 0;
+    for (int attempt = 0;; attempt++) {
+        if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
+        CU(c->keys.ensure(cap * 8));
+        CU(c->ords.ensure(cap * 8));
+        ScanArgs A{};
+        A.seq = d_seq; A.seq_bytes = seq_bytes;
+        A.goff = reinterpret_cast<uint64_t *>(mb + m_goff);
+        A.glen = reinterpret_cast<uint64_t *>(mb + m_glen);
+        A.span_nom = reinterpret_cast<uint64_t *>(mb + m_nom);
+        A.span_gid = reinterpret_cast<uint32_t *>(mb + m_sgid);
+        A.n_spans = n_spans; A.span_bytes = span;
+        A.gstatus = reinterpret_cast<int32_t *>(mb + m_stat);
+        A.ticket = reinterpret_cast<uint32_t *>(mb + m_tick);
+        A.out_count = reinterpret_cast<uint32_t *>(mb + m_cnt);
+        A.out_keys = c->keys.as<uint64_t>(); A.out_ords = c->ords.as<uint64_t>();
+        A.out_cap = (uint32_t)cap;
+        A.drop_zero = 1;
+        CU(cudaMemsetAsync(mb + m_tick, 0, 8, c->stream));
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        if (n_spans) {
+            sketch_fasta_kernel<<<c->sm_count, kScanThreads, kPfWords * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
+            LAUNCHED(1);
+        }
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        CU(cudaMemcpyAsync(&n_occ, mb + m_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        if (n_occ <= cap) break;
+        if (attempt >= 2) { delete S; return fail(KSSD_E_NOMEM, "kssd_sketch_batch: occurrence buffer overflow (%u > %llu)", n_occ, (unsigned long long)cap); }
+        cap = (uint64_t)n_occ + (n_occ >> 3) + 1024;
+    }
+    CU(cudaEventElapsedTime(&S->scan_ms, c->ev[0], c->ev[1]));
+    c->last_ms[0] = S->scan_ms;
+    S->n_occ = n_occ;
+
+    const int n_comp = S->n_comp;
+    S->status.assign(n_genomes, 0);
+    S->comp_start.assign(n_comp + 1, 0);
+    S->index.assign((size_t)n_comp * (n_genomes + 1), 0);
+    std::vector<uint32_t> per_cg((size_t)n_comp * n_genomes, 0);
+    uint32_t kept = 0;
+    if (n_occ) {
+        // sort occurrences by (component, genome, id); carry the offset along
+        CU(c->keys2.ensure((size_t)n_occ * 8));
+        CU(c->ords2.ensure((size_t)n_occ * 8));
+        size_t tmp_bytes = 0;
+        const int end_bit = 56 + std::max(P.comp_code_bits, 1);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->ords.as<uint64_t>(),
+                                        c->ords2.as<uint64_t>(), n_occ, 0, end_bit, c->stream);
+        CU(c->cubtmp.ensure(tmp_bytes));
+        CU(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp_bytes, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->ords.as<uint64_t>(),
+                                           c->ords2.as<uint64_t>(), n_occ, 0, end_bit, c->stream));
+        LAUNCHED(8);
+        CU(c->flags.ensure((size_t)n_occ * 4));
+        CU(c->pos.ensure((size_t)n_occ * 4));
+        CU(c->counts.ensure((size_t)n_occ * 2));
+        CU(c->minord.ensure((size_t)n_occ * 8));
+        const uint32_t nb = (n_occ + 255) / 256;
+        rle_kernel<<<nb, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->ords2.as<uint64_t>(), n_occ, mode, opts ? opts->M : 1,
+                                              c->flags.as<uint32_t>(), c->counts.as<uint16_t>(), c->minord.as<uint64_t>());
+        LAUNCHED(1);
+        size_t tmp2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ, c->stream);
+        CU(c->cubtmp.ensure(tmp2));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp2, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ, c->stream));
+        LAUNCHED(2);
+        uint32_t last_pos = 0, last_flag = 0;
+        CU(cudaMemcpyAsync(&last_pos, c->pos.as<uint32_t>() + (n_occ - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&last_flag, c->flags.as<uint32_t>() + (n_occ - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        kept = last_pos + last_flag;
+    }
+    S->total = kept;
+    CU(cudaMalloc(&S->d_ids, std::max<size_t>(kept, 1) * 4));
+    CU(cudaMalloc(&S->d_abund, std::max<size_t>(kept, 1) * 2));
+    CU(cudaMalloc(&S->d_ord, std::max<size_t>(kept, 1) * 8));
+    CU(cudaMalloc(&S->d_index, S->index.size() * 8));
+    if (n_occ) {
+        CU(c->misc.ensure(per_cg.size() * 4));
+        CU(cudaMemsetAsync(c->misc.p, 0, per_cg.size() * 4, c->stream));
+        sketch_scatter_kernel<<<(n_occ + 255) / 256, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->flags.as<uint32_t>(), c->pos.as<uint32_t>(),
+                                                                          c->counts.as<uint16_t>(), c->minord.as<uint64_t>(), n_occ, n_genomes,
+                                                                          S->d_ids, S->d_abund, S->d_ord, c->misc.as<uint32_t>());
+        LAUNCHED(1);
+        CU(cudaMemcpyAsync(per_cg.data(), c->misc.p, per_cg.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(S->status.data(), mb + m_stat, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    // per-component combco.index (command_dist.c:331-354) and reference error conditions
+    std::vector<uint64_t> per_genome(n_genomes, 0);
+    uint64_t run = 0;
+    for (int cc = 0; cc < n_comp; cc++) {
+        S->comp_start[cc] = run;
+        uint64_t *ix = &S->index[(size_t)cc * (n_genomes + 1)];
+        ix[0] = 0;
+        for (int g = 0; g < n_genomes; g++) {
+            const uint32_t v = per_cg[(size_t)cc * n_genomes + g];
+            ix[g + 1] = ix[g] + v;
+            per_genome[g] += v;
+        }
+        run += ix[n_genomes];
+    }
+    S->comp_start[n_comp] = run;
+    for (int g = 0; g < n_genomes; g++) {
+        if (S->status[g] & 1) S->status[g] = KSSD_E_HEADER_EOF;
+        else if (per_genome[g] > c->info.hashlimit) S->status[g] = KSSD_E_CROWD;
+        else S->status[g] = 0;
+    }
+    CU(cudaMemcpyAsync(S->d_index, S->index.data(), S->index.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[2]));
+    *out = S;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_sketch_batch_dev(kssd_ctx_t *c, const uint8_t *seq_dev, size_t seq_bytes, const uint64_t *goff, const uint64_t *glen,
+                                     int n_genomes, const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
+{
+    if (!c || !seq_dev || !goff || !glen || !out) return fail(KSSD_E_INVAL, "kssd_sketch_batch_dev: null argument");
+    CU(cudaSetDevice(c->device));
+    return sketch_run(c, seq_dev, seq_bytes, goff, glen, n_genomes, opts, out);
+}
+
+extern "C" int kssd_sketch_batch_host(kssd_ctx_t *c, const uint8_t *seq, size_t seq_bytes, const uint64_t *goff, const uint64_t *glen,
+                                      int n_genomes, const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
+{
+    if (!c || !seq || !goff || !glen || !out) return fail(KSSD_E_INVAL, "kssd_sketch_batch_host: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(c->seq.ensure(seq_bytes + 1024));
+    CU(cudaMemcpyAsync(c->seq.p, seq, seq_bytes, cudaMemcpyHostToDevice, c->stream));
+    return sketch_run(c, c->seq.as<uint8_t>(), seq_bytes, goff, glen, n_genomes, opts, out);
+}
+
+extern "C" int64_t kssd_sketch_count(const kssd_sketch_t *s, int comp)
+{
+    if (!s || comp < 0 || comp >= s->n_comp) return fail(KSSD_E_INVAL, "kssd_sketch_count: bad component");
+    return (int64_t)(s->comp_start[comp + 1] - s->comp_start[comp]);
+}
+
+extern "C" int kssd_sketch_status(const kssd_sketch_t *s, int32_t *status_out)
+{
+    if (!s || !status_out) return fail(KSSD_E_INVAL, "kssd_sketch_status: null");
+    memcpy(status_out, s->status.data(), s->status.size() * 4);
+    return KSSD_OK;
+}
+
+extern "C" int kssd_sketch_fetch(const kssd_sketch_t *s, int comp, uint32_t *ids, uint64_t *index, uint16_t *abund, uint64_t *ord)
+{
+    if (!s || comp < 0 || comp >= s->n_comp) return fail(KSSD_E_INVAL, "kssd_sketch_fetch: bad component");
+    kssd_ctx *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint64_t b = s->comp_start[comp], n = s->comp_start[comp + 1] - b;
+    if (ids && n) CU(cudaMemcpyAsync(ids, s->d_ids + b, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (abund && n) CU(cudaMemcpyAsync(abund, s->d_abund + b, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (ord && n) CU(cudaMemcpyAsync(ord, s->d_ord + b, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (index) memcpy(index, &s->index[(size_t)comp * (s->n_genomes + 1)], 8ull * (s->n_genomes + 1));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" int kssd_sketch_dev_ptrs(const kssd_sketch_t *s, int comp, const uint32_t **ids_dev, const uint64_t **index_dev)
+{
+    if (!s || comp < 0 || comp >= s->n_comp) return fail(KSSD_E_INVAL, "kssd_sketch_dev_ptrs: bad component");
+    if (ids_dev) *ids_dev = s->d_ids + s->comp_start[comp];
+    if (index_dev) *index_dev = s->d_index + (size_t)comp * (s->n_genomes + 1);
+    return KSSD_OK;
+}
+
+extern "C" int kssd_sketch_stats(const kssd_sketch_t *s, uint64_t *n_occurrences, float *scan_kernel_ms)
+{
+    if (!s) return fail(KSSD_E_INVAL, "kssd_sketch_stats: null");
+    if (n_occurrences) *n_occurrences = s->n_occ;
+    if (scan_kernel_ms) *scan_kernel_ms = s->scan_ms;
+    return KSSD_OK;
+}
+
+extern "C" void kssd_sketch_free(kssd_sketch_t *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_ids);
+    cudaFree(s->d_abund);
+    cudaFree(s->d_ord);
+    cudaFree(s->d_index);
+    delete s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage II
+// ------------------------------------------------------------------------------------------------
+struct kssd_index {
+    kssd_ctx *ctx = nullptr;
+    int n_genomes = 0;
+    uint64_t n_postings = 0, n_unique = 0, space = 0;
+    uint32_t *d_ucodes = nullptr, *d_uoff = nullptr, *d_gids = nullptr, *d_dense = nullptr;
+};
+
+static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
+{
+    // d_sorted_codes: n_postings codes ascending (scratch), ix->d_gids already in (code, gid) order
+    const uint64_t n = ix->n_postings;
+    uint32_t nuniq = 0;
+    if (n) {
+        CU(c->flags.ensure(n * 4));
+        CU(c->pos.ensure(n * 4));
+        const uint32_t nb = (uint32_t)((n + 255) / 256);
+        head_flags_kernel<<<nb, 256, 0, c->stream>>>(d_sorted_codes, n, c->flags.as<uint32_t>());
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n, c->stream));
+        LAUNCHED(3);
+        uint32_t lp = 0, lf = 0;
+        CU(cudaMemcpyAsync(&lp, c->pos.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&lf, c->flags.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        nuniq = lp + lf;
+    }
+    ix->n_unique = nuniq;
+    CU(cudaMalloc(&ix->d_ucodes, std::max<size_t>(nuniq, 1) * 4));
+    CU(cudaMalloc(&ix->d_uoff, ((size_t)nuniq + 1) * 4));
+    if (n) {
+        csr_scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(d_sorted_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n,
+                                                                               ix->d_ucodes, ix->d_uoff);
+        LAUNCHED(1);
+    }
+    const uint32_t n32 = (uint32_t)n;
+    CU(cudaMemcpyAsync(ix->d_uoff + nuniq, &n32, 4, cudaMemcpyHostToDevice, c->stream));
+    // dense exclusive start table for O(1) query lookups (and for mco.index.<c> export)
+    CU(cudaMalloc(&ix->d_dense, (ix->space + 1) * 4));
+    const uint64_t warps = (uint64_t)nuniq + 1;
+    dense_fill_kernel<<<(uint32_t)((warps * 32 + 255) / 256), 256, 0, c->stream>>>(ix->d_ucodes, ix->d_uoff, nuniq, n32, ix->space, ix->d_dense);
+    LAUNCHED(1);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return KSSD_OK;
+}
+
+extern "C" int kssd_index_build_dev(kssd_ctx_t *c, const uint32_t *combco_dev, const uint64_t *cbdcoindex_dev, int n_genomes, uint64_t n_codes,
+                                    kssd_index_t **out)
+{
+    if (!c || !out || n_genomes <= 0 || (n_codes && (!combco_dev || !cbdcoindex_dev))) return fail(KSSD_E_INVAL, "kssd_index_build_dev: bad argument");
+    if (n_codes >= 0xffffffffull) return fail(KSSD_E_INVAL, "kssd_index_build_dev: more than 2^32 postings in one component");
+    CU(cudaSetDevice(c->device));
+    kssd_index *ix = new kssd_index();
+    ix->ctx = c; ix->n_genomes = n_genomes; ix->n_postings = n_codes;
+    ix->space = 1ull << (4 * c->info.component_sz);   // the reference's dense table always spans 16^COMPONENT_SZ
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    CU(cudaMalloc(&ix->d_gids, std::max<size_t>(n_codes, 1) * 4));
+    uint32_t *d_sorted = nullptr;
+    if (n_codes) {
+        CU(c->keys.ensure(n_codes * 4));     // gid tags (unsorted)
+        CU(c->keys2.ensure(n_codes * 4));    // sorted codes
+        expand_gid_kernel<<<(uint32_t)((n_codes + 255) / 256), 256, 0, c->stream>>>(cbdcoindex_dev, n_genomes, n_codes, c->keys.as<uint32_t>());
+        LAUNCHED(1);
+        size_t tmp = 0;
+        const int bits = 4 * std::min(c->info.component_sz, c->info.k - c->info.drlevel);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, combco_dev, c->keys2.as<uint32_t>(), c->keys.as<uint32_t>(), ix->d_gids, n_codes, 0, bits,
+                                        c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, combco_dev, c->keys2.as<uint32_t>(), c->keys.as<uint32_t>(), ix->d_gids, n_codes, 0,
+                                           bits, c->stream));
+        LAUNCHED(5);
+        d_sorted = c->keys2.as<uint32_t>();
+    }
+    int rc = index_finish(c, ix, d_sorted);
+    if (rc) { kssd_index_free(ix); return rc; }
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[1]));
+    *out = ix;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_index_build_host(kssd_ctx_t *c, const uint32_t *combco, const uint64_t *cbdcoindex, int n_genomes, kssd_index_t **out)
+{
+    if (!c || !cbdcoindex || !out || n_genomes <= 0) return fail(KSSD_E_INVAL, "kssd_index_build_host: bad argument");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = cbdcoindex[n_genomes];
+    if (n && !combco) return fail(KSSD_E_INVAL, "kssd_index_build_host: null combco");
+    CU(c->seq.ensure(n * 4 + 8ull * (n_genomes + 1) + 64));
+    uint64_t *d_index = c->seq.as<uint64_t>();
+    uint32_t *d_codes = reinterpret_cast<uint32_t *>(d_index + n_genomes + 1);
+    CU(cudaMemcpyAsync(d_index, cbdcoindex, 8ull * (n_genomes + 1), cudaMemcpyHostToDevice, c->stream));
+    if (n) CU(cudaMemcpyAsync(d_codes, combco, n * 4, cudaMemcpyHostToDevice, c->stream));
+    return kssd_index_build_dev(c, d_codes, d_index, n_genomes, n, out);
+}
+
+extern "C" int kssd_index_sizes(const kssd_index_t *ix, uint64_t *n_unique, uint64_t *n_postings, int *n_genomes)
+{
+    if (!ix) return fail(KSSD_E_INVAL, "kssd_index_sizes: null");
+    if (n_unique) *n_unique = ix->n_unique;
+    if (n_postings) *n_postings = ix->n_postings;
+    if (n_genomes) *n_genomes = ix->n_genomes;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_index_fetch(const kssd_index_t *ix, uint32_t *ucodes, uint64_t *uoff, uint32_t *gids)
+{
+    if (!ix) return fail(KSSD_E_INVAL, "kssd_index_fetch: null");
+    kssd_ctx *c = ix->ctx;
+    CU(cudaSetDevice(c->device));
+    if (ucodes && ix->n_unique) CU(cudaMemcpyAsync(ucodes, ix->d_ucodes, ix->n_unique * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (gids && ix->n_postings) CU(cudaMemcpyAsync(gids, ix->d_gids, ix->n_postings * 4, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<uint32_t> tmp;
+    if (uoff) {
+        tmp.resize(ix->n_unique + 1);
+        CU(cudaMemcpyAsync(tmp.data(), ix->d_uoff, (ix->n_unique + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (uoff) for (size_t i = 0; i <= ix->n_unique; i++) uoff[i] = tmp[i];
+    return KSSD_OK;
+}
+
+extern "C" int kssd_index_fetch_dense(const kssd_index_t *ix, uint64_t *dense_out)
+{
+    if (!ix || !dense_out) return fail(KSSD_E_INVAL, "kssd_index_fetch_dense: null");
+    kssd_ctx *c = ix->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint64_t chunk = 1ull << 24;   // 128 MiB of u64 per step
+    CU(c->keys.ensure(chunk * 8));
+    for (uint64_t first = 0; first < ix->space; first += chunk) {
+        const uint64_t cnt = std::min(chunk, ix->space - first);
+        dense_incl64_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->stream>>>(ix->d_dense, first, cnt, c->keys.as<uint64_t>());
+        LAUNCHED(1);
+        CU(cudaMemcpyAsync(dense_out + first, c->keys.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return KSSD_OK;
+}
+
+__global__ void codes_from_dense_kernel(const uint32_t *__restrict__ dense, uint64_t space, uint32_t *__restrict__ codes)
+{
+    // every code writes itself over its posting range
+    const uint64_t cidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= space) return;
+    const uint32_t s = dense[cidx], e = dense[cidx + 1];
+    for (uint32_t g = s; g < e; g++) codes[g] = (uint32_t)cidx;
+}
+
+extern "C" int kssd_index_from_dense_host(kssd_ctx_t *c, const uint64_t *dense_incl, const uint32_t *gids, uint64_t n_postings, int n_genomes,
+                                          kssd_index_t **out)
+{
+    if (!c || !dense_incl || !out || n_genomes <= 0 || (n_postings && !gids)) return fail(KSSD_E_INVAL, "kssd_index_from_dense_host: bad argument");
+    if (n_postings >= 0xffffffffull) return fail(KSSD_E_INVAL, "kssd_index_from_dense_host: too many postings");
+    CU(cudaSetDevice(c->device));
+    kssd_index *ix = new kssd_index();
+    ix->ctx = c; ix->n_genomes = n_genomes; ix->n_postings = n_postings;
+    ix->space = 1ull << (4 * c->info.component_sz);   // the reference's dense table always spans 16^COMPONENT_SZ
+    CU(cudaMalloc(&ix->d_gids, std::max<size_t>(n_postings, 1) * 4));
+    if (n_postings) CU(cudaMemcpyAsync(ix->d_gids, gids, n_postings * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t *d_dense_tmp = nullptr;
+    CU(cudaMalloc(&d_dense_tmp, (ix->space + 1) * 4));
+    const uint64_t chunk = 1ull << 24;
+    CU(c->keys.ensure(chunk * 8));
+    for (uint64_t first = 0; first < ix->space; first += chunk) {
+        const uint64_t cnt = std::min(chunk, ix->space - first);
+        CU(cudaMemcpyAsync(c->keys.p, dense_incl + first, cnt * 8, cudaMemcpyHostToDevice, c->stream));
+        dense_from_incl64_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->stream>>>(c->keys.as<uint64_t>(), first, cnt, d_dense_tmp);
+        LAUNCHED(1);
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    CU(c->keys2.ensure(std::max<size_t>(n_postings, 1) * 4));
+    codes_from_dense_kernel<<<(uint32_t)((ix->space + 255) / 256), 256, 0, c->stream>>>(d_dense_tmp, ix->space, c->keys2.as<uint32_t>());
+    LAUNCHED(1);
+    int rc = index_finish(c, ix, n_postings ? c->keys2.as<uint32_t>() : nullptr);
+    cudaFree(d_dense_tmp);
+    if (rc) { kssd_index_free(ix); return rc; }
+    *out = ix;
+    return KSSD_OK;
+}
+
+extern "C" void kssd_index_free(kssd_index_t *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    cudaFree(ix->d_ucodes);
+    cudaFree(ix->d_uoff);
+    cudaFree(ix->d_gids);
+    cudaFree(ix->d_dense);
+    delete ix;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage III
+// ------------------------------------------------------------------------------------------------
+struct kssd_dist {
+    kssd_ctx *ctx = nullptr;
+    int n_qry = 0, n_ref = 0, components_done = 0;
+    uint32_t max_qry_size = 0;
+    uint32_t *d_ct = nullptr, *d_qsz = nullptr, *d_rsz = nullptr;
+    StatRow *d_rows = nullptr;
+    uint64_t n_rows = 0;
+};
+
+extern "C" int kssd_dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, kssd_dist_t **out)
+{
+    if (!c || !out || n_qry <= 0 || n_ref <= 0 || !qry_ctx_ct || !ref_ctx_ct) return fail(KSSD_E_INVAL, "kssd_dist_create: bad argument");
+    CU(cudaSetDevice(c->device));
+    kssd_dist *d = new kssd_dist();
+    d->ctx = c; d->n_qry = n_qry; d->n_ref = n_ref;
+    for (int i = 0; i < n_qry; i++) d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]);
+    CU(cudaMalloc(&d->d_ct, (size_t)n_qry * n_ref * 4));
+    CU(cudaMalloc(&d->d_qsz, (size_t)n_qry * 4));
+    CU(cudaMalloc(&d->d_rsz, (size_t)n_ref * 4));
+    CU(cudaMemcpyAsync(d->d_qsz, qry_ctx_ct, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d->d_rsz, ref_ctx_ct, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = d;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev, const uint64_t *qindex_dev,
+                                        uint64_t n_qcodes)
+{
+    if (!d || !ref_ix || !qindex_dev || (n_qcodes && !qcodes_dev)) return fail(KSSD_E_INVAL, "kssd_dist_accumulate_dev: null argument");
+    if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    const bool small = d->max_qry_size < 65536u;
+    const uint32_t elem = small ? 2 : 4;
+    // strip width: whole row when it fits in ~96 KiB (two CTAs per SM), else equal tiles
+    const uint32_t max_refs = (96u << 10) / elem;
+    const uint32_t n_tiles = ((uint32_t)d->n_ref + max_refs - 1) / max_refs;
+    uint32_t tile = ((uint32_t)d->n_ref + n_tiles - 1) / n_tiles;
+    tile = (tile + 1) & ~1u;
+    const size_t smem = ((size_t)tile * elem + 15) & ~(size_t)15;
+    const uint32_t grid = (uint32_t)d->n_qry * n_tiles;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (small) {
+        CU(cudaFuncSetAttribute(dist_count_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dist_count_kernel<uint16_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
+                                                                           tile, n_tiles, d->d_ct, d->components_done > 0);
+    } else {
+        CU(cudaFuncSetAttribute(dist_count_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dist_count_kernel<uint32_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
+                                                                           tile, n_tiles, d->d_ct, d->components_done > 0);
+    }
+    LAUNCHED(1);
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]));
+    d->components_done++;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_dist_accumulate_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes, const uint64_t *qindex)
+{
+    if (!d || !ref_ix || !qindex) return fail(KSSD_E_INVAL, "kssd_dist_accumulate_host: null argument");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = qindex[d->n_qry];
+    if (n && !qcodes) return fail(KSSD_E_INVAL, "kssd_dist_accumulate_host: null qcodes");
+    CU(c->seq.ensure(n * 4 + 8ull * (d->n_qry + 1) + 64));
+    uint64_t *d_index = c->seq.as<uint64_t>();
+    uint32_t *d_codes = reinterpret_cast<uint32_t *>(d_index + d->n_qry + 1);
+    CU(cudaMemcpyAsync(d_index, qindex, 8ull * (d->n_qry + 1), cudaMemcpyHostToDevice, c->stream));
+    if (n) CU(cudaMemcpyAsync(d_codes, qcodes, n * 4, cudaMemcpyHostToDevice, c->stream));
+    return kssd_dist_accumulate_dev(d, ref_ix, d_codes, d_index, n);
+}
+
+extern "C" int kssd_dist_fetch_counts(const kssd_dist_t *d, uint32_t *ct_out)
+{
+    if (!d || !ct_out) return fail(KSSD_E_INVAL, "kssd_dist_fetch_counts: null");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    if (d->components_done == 0) CU(cudaMemsetAsync(d->d_ct, 0, (size_t)d->n_qry * d->n_ref * 4, c->stream));
+    CU(cudaMemcpyAsync(ct_out, d->d_ct, (size_t)d->n_qry * d->n_ref * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" const uint32_t *kssd_dist_counts_dev(const kssd_dist_t *d) { return d ? d->d_ct : nullptr; }
+
+extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
+{
+    if (!d || !o) return fail(KSSD_E_INVAL, "kssd_dist_stats: null");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    if (o->n_neighbors < 0 || o->n_neighbors > 1024 || o->n_neighbors > d->n_ref)
+        return fail(KSSD_E_NNEIGH, "neighborN_max %d should smaller than NREF 1024 and ref_num %d", o->n_neighbors, d->n_ref);
+    if (d->components_done == 0) CU(cudaMemsetAsync(d->d_ct, 0, (size_t)d->n_qry * d->n_ref * 4, c->stream));
+    StatParams S;
+    S.metric = o->metric; S.correction = o->correction; S.kmerlen = o->kmerlen; S.dim_rd_len = o->dim_rd_len;
+    S.skip_zero = o->skip_zero; S.dthreshold = o->dthreshold;
+    S.cmprsn_num = (double)(uint32_t)((uint32_t)d->n_ref * (uint32_t)d->n_qry);   // 32-bit wrap, command_dist.c:1186
+    if (d->d_rows) { cudaFree(d->d_rows); d->d_rows = nullptr; }
+    d->n_rows = 0;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (o->n_neighbors > 0) {
+        const int N = o->n_neighbors;
+        StatRow *tmp_rows = nullptr;
+        CU(cudaMalloc(&tmp_rows, (size_t)d->n_qry * N * sizeof(StatRow)));
+        CU(c->flags.ensure((size_t)d->n_qry * 4));
+        topn_kernel<<<d->n_qry, 256, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, N, c->flags.as<uint32_t>(), tmp_rows);
+        LAUNCHED(1);
+        std::vector<uint32_t> rc(d->n_qry);
+        CU(cudaMemcpyAsync(rc.data(), c->flags.p, (size_t)d->n_qry * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        uint64_t total = 0;
+        for (auto v : rc) total += v;
+        CU(cudaMalloc(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow)));
+        uint64_t o2 = 0;
+        for (int q = 0; q < d->n_qry; q++) {
+            if (rc[q]) CU(cudaMemcpyAsync(d->d_rows + o2, tmp_rows + (size_t)q * N, (size_t)rc[q] * sizeof(StatRow), cudaMemcpyDeviceToDevice, c->stream));
+            o2 += rc[q];
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp_rows);
+        d->n_rows = total;
+    } else {
+        const uint32_t bpr = ((uint32_t)d->n_ref + kStatRefsPerBlock - 1) / kStatRefsPerBlock;
+        const uint64_t nblocks = (uint64_t)bpr * d->n_qry;
+        CU(c->flags.ensure(nblocks * 4));
+        CU(c->pos.ensure((nblocks + 1) * 8));
+        stats_count_kernel<<<(uint32_t)nblocks, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, c->flags.as<uint32_t>());
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nblocks, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nblocks, c->stream));
+        LAUNCHED(3);
+        uint64_t lastoff = 0;
+        uint32_t lastcnt = 0;
+        CU(cudaMemcpyAsync(&lastoff, c->pos.as<uint64_t>() + (nblocks - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&lastcnt, c->flags.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const uint64_t total = lastoff + lastcnt;
+        CU(cudaMalloc(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow)));
+        stats_write_kernel<<<(uint32_t)nblocks, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, c->pos.as<uint64_t>(),
+                                                                             d->d_rows);
+        LAUNCHED(1);
+        d->n_rows = total;
+    }
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&c->last_ms[4], c->ev[0], c->ev[1]));
+    return (int64_t)d->n_rows;
+}
+
+extern "C" int kssd_dist_fetch_stats(const kssd_dist_t *d, kssd_stat_row_t *rows_out)
+{
+    static_assert(sizeof(kssd_stat_row_t) == sizeof(StatRow), "row layout");
+    if (!d || !rows_out) return fail(KSSD_E_INVAL, "kssd_dist_fetch_stats: null");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    if (d->n_rows) CU(cudaMemcpyAsync(rows_out, d->d_rows, d->n_rows * sizeof(StatRow), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" void kssd_dist_free(kssd_dist_t *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaFree(d->d_ct);
+    cudaFree(d->d_qsz);
+    cudaFree(d->d_rsz);
+    cudaFree(d->d_rows);
+    delete d;
+}

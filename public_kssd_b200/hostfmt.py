@@ -1,0 +1,101 @@
+"""Host-side file formats and ordering helpers of the reference -- no compute kernels.
+
+combco.<c> in the reference is in HASH-SLOT order (iseq2comem.c:538-546).  The GPU returns each
+genome's ids ascending plus the byte offset of every id's first occurrence; `slot_order` replays the
+open-addressing insertion of the distinct keys in first-occurrence order, which reproduces the
+reference file byte for byte.
+"""
+from __future__ import annotations
+
+import struct
+from pathlib import Path
+
+import numpy as np
+
+
+def slot_order(ids: np.ndarray, first_occurrence: np.ndarray, hashsize: int, keys: np.ndarray | None = None) -> np.ndarray:
+    """ids of ONE genome (one component when comp_num == 1) -> the order wrt_co2cmpn_use_inn_subctx writes them.
+    keys: the full drtuple values when they differ from ids (comp_num > 1); default = ids."""
+    keys = ids.astype(np.uint64) if keys is None else keys.astype(np.uint64)
+    order = np.argsort(first_occurrence, kind="stable")
+    H = int(hashsize)
+    table = {}
+    for j in order:
+        key = int(keys[j])
+        h1, h2 = key % H, 1 + key % (H - 1)
+        i = 0
+        while True:
+            n = (h1 + i * h2) % H
+            if n not in table:
+                table[n] = int(ids[j])
+                break
+            i += 1
+    return np.array([table[s] for s in sorted(table)], dtype=np.uint32)
+
+
+def _names_block(names) -> bytes:
+    out = []
+    for nm in names:
+        b = nm.encode()[:255]
+        out.append(b + b"\0" * (256 - len(b)))
+    return b"".join(out)
+
+
+def write_cofiles_stat(d, shuf_id: int, koc: bool, kmerlen: int, dim_rd_len: int, comp_num: int, ctx_ct: np.ndarray, names) -> None:
+    """co_dstat_t (global_basic.h:94-103) + ctx_ct + 256-byte names (command_dist.c:361-377)."""
+    with open(Path(d, "cofiles.stat"), "wb") as f:
+        f.write(struct.pack("<I?xxxiiiiQ", shuf_id & 0xFFFFFFFF, bool(koc), kmerlen, dim_rd_len, comp_num, len(names),
+                            int(np.sum(ctx_ct, dtype=np.uint64))))
+        f.write(np.ascontiguousarray(ctx_ct, dtype="<u4").tobytes())
+        f.write(_names_block(names))
+
+
+def write_mcofiles_stat(d, shuf_id: int, kmerlen: int, dim_rd_len: int, comp_num: int, ctx_ct: np.ndarray, names) -> None:
+    """mco_dstat_t (command_dist.h:57-64) + ctx_ct + names (command_dist.c:397-409)."""
+    with open(Path(d, "mcofiles.stat"), "wb") as f:
+        f.write(struct.pack("<Iiiii", shuf_id & 0xFFFFFFFF, kmerlen, dim_rd_len, comp_num, len(names)))
+        f.write(np.ascontiguousarray(ctx_ct, dtype="<u4").tobytes())
+        f.write(_names_block(names))
+
+
+def read_cofiles_stat(d) -> dict:
+    raw = Path(d, "cofiles.stat").read_bytes()
+    shuf_id, koc, kmerlen, dim_rd_len, comp_num, infile_num, all_ctx_ct = struct.unpack_from("<I?xxxiiiiQ", raw, 0)
+    ct = np.frombuffer(raw, dtype="<u4", count=infile_num, offset=32).copy()
+    base = 32 + 4 * infile_num
+    names = [raw[base + 256 * i: base + 256 * (i + 1)].split(b"\0")[0].decode() for i in range(infile_num)]
+    return dict(shuf_id=shuf_id, koc=koc, kmerlen=kmerlen, dim_rd_len=dim_rd_len, comp_num=comp_num, infile_num=infile_num,
+                all_ctx_ct=all_ctx_ct, ctx_ct=ct, names=names)
+
+
+def read_mcofiles_stat(d) -> dict:
+    raw = Path(d, "mcofiles.stat").read_bytes()
+    shuf_id, kmerlen, dim_rd_len, comp_num, infile_num = struct.unpack_from("<Iiiii", raw, 0)
+    ct = np.frombuffer(raw, dtype="<u4", count=infile_num, offset=20).copy()
+    base = 20 + 4 * infile_num
+    names = [raw[base + 256 * i: base + 256 * (i + 1)].split(b"\0")[0].decode() for i in range(infile_num)]
+    return dict(shuf_id=shuf_id, kmerlen=kmerlen, dim_rd_len=dim_rd_len, comp_num=comp_num, infile_num=infile_num, ctx_ct=ct,
+                names=names)
+
+
+def write_combco(d, comp: int, ids: np.ndarray, index: np.ndarray, abund: np.ndarray | None = None) -> None:
+    np.ascontiguousarray(ids, dtype="<u4").tofile(Path(d, f"combco.{comp}"))
+    np.ascontiguousarray(index, dtype="<u8").tofile(Path(d, f"combco.index.{comp}"))
+    if abund is not None:
+        np.ascontiguousarray(abund, dtype="<u2").tofile(Path(d, f"combco.{comp}.a"))
+
+
+def read_combco(d, comp: int):
+    ids = np.fromfile(Path(d, f"combco.{comp}"), dtype="<u4")
+    index = np.fromfile(Path(d, f"combco.index.{comp}"), dtype="<u8")
+    ap = Path(d, f"combco.{comp}.a")
+    return ids, index, (np.fromfile(ap, dtype="<u2") if ap.exists() else None)
+
+
+def write_mco(d, comp: int, gids: np.ndarray, dense_incl: np.ndarray) -> None:
+    np.ascontiguousarray(gids, dtype="<u4").tofile(Path(d, f"mco.{comp}"))
+    np.ascontiguousarray(dense_incl, dtype="<u8").tofile(Path(d, f"mco.index.{comp}"))
+
+
+def read_mco(d, comp: int):
+    return np.fromfile(Path(d, f"mco.{comp}"), dtype="<u4"), np.fromfile(Path(d, f"mco.index.{comp}"), dtype="<u8")

@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's stage functions on top of the C-ABI (capi.py).
+
+Names follow the reference seams they stand for:
+
+    Context            read_dim_shuffle_file + get_hashsz + seq2co_global_var_initial
+    Context.sketch     fasta2co / uniq_fasta2co (+ the wrt_* writers) for a batch of genomes
+    Context.combco2mco co2mco.c:25 combco2mco for one component
+    DistJob            mco_cbdco_nobin_dist hot loop + output_ctrl numbers
+
+All compute happens in libkssd_b200.so on the GPU; this module only moves buffers and keeps the
+reference's data shapes (combco / combco.index / mco / sharedk_ct matrices).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import KssdError, check, lib, ptr
+
+
+def read_shuf_file(path) -> tuple[dict, np.ndarray]:
+    """.shuf: 16-byte dim_shuffle_stat_t {id,k,subk,drlevel} + int32[16^subk] (command_shuffle.c:192-207)."""
+    path = str(path)
+    if not path.endswith(".shuf"):
+        raise ValueError(f"read_dim_shuffle_file(): input file {path} is not .shuf file")
+    with open(path, "rb") as f:
+        sid, k, subk, drlevel = struct.unpack("<iiii", f.read(16))
+        table = np.fromfile(f, dtype="<i4", count=1 << (4 * subk))
+    return dict(id=sid, k=k, subk=subk, drlevel=drlevel), table
+
+
+def write_shuf_file(path, shuf_id: int, k: int, subk: int, drlevel: int, table: np.ndarray) -> None:
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiii", shuf_id, k, subk, drlevel))
+        f.write(np.ascontiguousarray(table, dtype="<i4").tobytes())
+
+
+def pack_genomes(genomes: Sequence[bytes | np.ndarray], align: int = 128, pinned: bool = False):
+    """Lay genomes out in one byte buffer, each start aligned (>= 16 required by the C-ABI).
+    Returns (buffer uint8, goff uint64[n], glen uint64[n])."""
+    n = len(genomes)
+    glen = np.array([len(g) for g in genomes], dtype=np.uint64)
+    goff = np.zeros(n, dtype=np.uint64)
+    o = 0
+    for i in range(n):
+        goff[i] = o
+        o += (int(glen[i]) + align - 1) // align * align
+    total = max(o, align)
+    if pinned:
+        import torch
+        buf = torch.empty(total, dtype=torch.uint8, pin_memory=True).numpy()
+    else:
+        buf = np.empty(total, dtype=np.uint8)
+    buf[:] = 0x0A
+    for i, g in enumerate(genomes):
+        a = np.frombuffer(g, dtype=np.uint8) if not isinstance(g, np.ndarray) else g
+        buf[int(goff[i]): int(goff[i]) + a.size] = a
+    return buf, goff, glen
+
+
+@dataclass
+class Sketch:
+    """One batch of sketches: per component the content of combco.<c> / combco.index.<c> (ids ascending per genome)."""
+    ids: list          # per component uint32[]
+    index: list        # per component uint64[n+1]
+    abund: list        # per component uint16[] (abundance mode) or None
+    ord: list          # per component uint64[] first-occurrence byte offsets or None
+    status: np.ndarray  # per genome 0 / KSSD_E_*
+    n_occurrences: int
+    scan_ms: float
+    total_ms: float
+
+    def genome_sets(self):
+        n = len(self.index[0]) - 1
+        return [[self.ids[c][int(self.index[c][g]): int(self.index[c][g + 1])] for c in range(len(self.ids))] for g in range(n)]
+
+    def ctx_ct(self) -> np.ndarray:
+        """per-genome sketch size over all components (cofiles.stat ctx_ct list)."""
+        return sum(np.diff(ix).astype(np.uint32) for ix in self.index)
+
+
+class Context:
+    """One GPU + one .shuf: the globals of the reference's Stage I as an object."""
+
+    def __init__(self, k: int, subk: int, drlevel: int, table: np.ndarray, device: int = 0, component_sz: int = 7,
+                 shuf_id: int = 0):
+        self._h = C.c_void_p()
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        if table.size != 1 << (4 * subk):
+            raise ValueError("shuf table must hold 16^subk entries")
+        check(lib().kssd_ctx_create(C.byref(self._h), device, ptr(table, C.c_int32), k, subk, drlevel, component_sz))
+        self.info = capi.CtxInfo()
+        check(lib().kssd_ctx_info(self._h, C.byref(self.info)))
+        self.k, self.subk, self.drlevel, self.shuf_id = k, subk, drlevel, shuf_id
+        self.component_num = self.info.component_num
+        self.device = device
+
+    @classmethod
+    def from_shuf_file(cls, path, device: int = 0, component_sz: int = 7) -> "Context":
+        st, table = read_shuf_file(path)
+        return cls(st["k"], st["subk"], st["drlevel"], table, device=device, component_sz=component_sz, shuf_id=st["id"])
+
+    def close(self):
+        if self._h:
+            lib().kssd_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(lib().kssd_ctx_stream(self._h) or 0)
+
+    def last_ms(self, which: int) -> float:
+        return float(lib().kssd_ctx_last_ms(self._h, which))
+
+    # ---------------- Stage I ----------------
+    def sketch_raw(self, buf, nbytes: int, goff: np.ndarray, glen: np.ndarray, mode: int = capi.MODE_FASTA, Q: int = 0, M: int = 1,
+                   span_bytes: int = 0, device_ptr: int | None = None):
+        """Returns an opaque sketch handle (int).  `buf` numpy uint8 (host) or device_ptr (int) for resident input."""
+        goff = np.ascontiguousarray(goff, dtype=np.uint64)
+        glen = np.ascontiguousarray(glen, dtype=np.uint64)
+        opts = capi.SketchOpts(mode, Q, M, 1, span_bytes, 0)
+        h = C.c_void_p()
+        if device_ptr is not None:
+            check(lib().kssd_sketch_batch_dev(self._h, C.c_void_p(device_ptr), nbytes, ptr(goff, C.c_uint64), ptr(glen, C.c_uint64),
+                                              len(goff), C.byref(opts), C.byref(h)))
+        else:
+            check(lib().kssd_sketch_batch_host(self._h, buf.ctypes.data_as(C.c_void_p), nbytes, ptr(goff, C.c_uint64),
+                                               ptr(glen, C.c_uint64), len(goff), C.byref(opts), C.byref(h)))
+        return h
+
+    def fetch_sketch(self, h, n_genomes: int, free: bool = True, want_ord: bool = True, want_abund: bool = False) -> Sketch:
+        ids, index, abund, ordl = [], [], [], []
+        for c in range(self.component_num):
+            n = check(lib().kssd_sketch_count(h, c))
+            a = np.empty(n, dtype=np.uint32)
+            ix = np.empty(n_genomes + 1, dtype=np.uint64)
+            ab = np.empty(n, dtype=np.uint16) if want_abund else None
+            od = np.empty(n, dtype=np.uint64) if want_ord else None
+            check(lib().kssd_sketch_fetch(h, c, ptr(a, C.c_uint32), ptr(ix, C.c_uint64), ptr(ab, C.c_uint16) if want_abund else None,
+                                          ptr(od, C.c_uint64) if want_ord else None))
+            ids.append(a); index.append(ix); abund.append(ab); ordl.append(od)
+        status = np.zeros(n_genomes, dtype=np.int32)
+        check(lib().kssd_sketch_status(h, ptr(status, C.c_int32)))
+        nocc = C.c_uint64(0)
+        ms = C.c_float(0)
+        check(lib().kssd_sketch_stats(h, C.byref(nocc), C.byref(ms)))
+        total_ms = self.last_ms(1)
+        if free:
+            lib().kssd_sketch_free(h)
+        return Sketch(ids, index, abund, ordl, status, int(nocc.value), float(ms.value), total_ms)
+
+    def sketch(self, genomes: Sequence[bytes | np.ndarray], uniq: bool = False, span_bytes: int = 0, strict: bool = True) -> Sketch:
+        """fasta2co / uniq_fasta2co + writer for each genome of the batch (host buffers in, host arrays out).
+        strict: raise where the reference would have exited (crowded context space, header at EOF)."""
+        buf, goff, glen = pack_genomes(genomes)
+        h = self.sketch_raw(buf, buf.size, goff, glen, capi.MODE_FASTA_UNIQ if uniq else capi.MODE_FASTA, span_bytes=span_bytes)
+        sk = self.fetch_sketch(h, len(genomes))
+        if strict:
+            for g, s in enumerate(sk.status):
+                if s == capi.E_CROWD:
+                    raise KssdError(s, f"the context space is too crowd, try rerun the program using -k{self.k + 1} (genome {g})")
+                if s == capi.E_HEADER_EOF:
+                    raise KssdError(s, f"fasta2co(): can not find seqences head start from '>' (genome {g})")
+        return sk
+
+    # ---------------- Stage II ----------------
+    def combco2mco(self, combco: np.ndarray, cbdcoindex: np.ndarray) -> "Index":
+        combco = np.ascontiguousarray(combco, dtype=np.uint32)
+        cbdcoindex = np.ascontiguousarray(cbdcoindex, dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().kssd_index_build_host(self._h, ptr(combco, C.c_uint32), ptr(cbdcoindex, C.c_uint64), len(cbdcoindex) - 1, C.byref(h)))
+        return Index(self, h)
+
+    def index_from_dense(self, dense_incl: np.ndarray, gids: np.ndarray, n_genomes: int) -> "Index":
+        dense_incl = np.ascontiguousarray(dense_incl, dtype=np.uint64)
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        h = C.c_void_p()
+        check(lib().kssd_index_from_dense_host(self._h, ptr(dense_incl, C.c_uint64), ptr(gids, C.c_uint32), gids.size, n_genomes, C.byref(h)))
+        return Index(self, h)
+
+
+class Index:
+    """Inverted index of one component (mco.<c> + mco.index.<c>), resident on the GPU."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+        nu, npst, ng = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        check(lib().kssd_index_sizes(h, C.byref(nu), C.byref(npst), C.byref(ng)))
+        self.n_unique, self.n_postings, self.n_genomes = int(nu.value), int(npst.value), int(ng.value)
+
+    def csr(self):
+        """(unique codes, exclusive offsets, gids) -- gids is the content of mco.<c>."""
+        uc = np.empty(self.n_unique, dtype=np.uint32)
+        uo = np.empty(self.n_unique + 1, dtype=np.uint64)
+        g = np.empty(self.n_postings, dtype=np.uint32)
+        check(lib().kssd_index_fetch(self._h, ptr(uc, C.c_uint32), ptr(uo, C.c_uint64), ptr(g, C.c_uint32)))
+        return uc, uo, g
+
+    def dense(self) -> np.ndarray:
+        """mco.index.<c>: uint64[16^COMPONENT_SZ] inclusive prefix (co2mco.c:57-61)."""
+        d = np.empty(1 << (4 * self.ctx.info.component_sz), dtype=np.uint64)
+        check(lib().kssd_index_fetch_dense(self._h, ptr(d, C.c_uint64)))
+        return d
+
+    def close(self):
+        if self._h:
+            lib().kssd_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DistJob:
+    """Q x R shared-k-mer count matrix (sharedk_ct.dat) and the statistics of distance.out."""
+
+    def __init__(self, ctx: Context, qry_ctx_ct: np.ndarray, ref_ctx_ct: np.ndarray):
+        self.ctx = ctx
+        q = np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
+        r = np.ascontiguousarray(ref_ctx_ct, dtype=np.uint32)
+        self.n_qry, self.n_ref = q.size, r.size
+        self._h = C.c_void_p()
+        check(lib().kssd_dist_create(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.byref(self._h)))
+
+    def accumulate(self, ref_index: Index, qcodes: np.ndarray, qindex: np.ndarray):
+        qcodes = np.ascontiguousarray(qcodes, dtype=np.uint32)
+        qindex = np.ascontiguousarray(qindex, dtype=np.uint64)
+        check(lib().kssd_dist_accumulate_host(self._h, ref_index._h, ptr(qcodes, C.c_uint32), ptr(qindex, C.c_uint64)))
+
+    def accumulate_dev(self, ref_index: Index, qcodes_ptr: int, qindex_ptr: int, n_qcodes: int):
+        check(lib().kssd_dist_accumulate_dev(self._h, ref_index._h, C.c_void_p(qcodes_ptr), C.c_void_p(qindex_ptr), n_qcodes))
+
+    def counts(self) -> np.ndarray:
+        ct = np.empty((self.n_qry, self.n_ref), dtype=np.uint32)
+        check(lib().kssd_dist_fetch_counts(self._h, ptr(ct, C.c_uint32)))
+        return ct
+
+    def stats(self, metric: int = 0, correction: int = 0, kmerlen: int | None = None, dim_rd_len: int | None = None,
+              dthreshold: float = 1.0, n_neighbors: int = 0, skip_zero: int = 0, fetch: bool = True):
+        o = capi.StatOpts(metric, correction, kmerlen if kmerlen is not None else 2 * self.ctx.k,
+                          dim_rd_len if dim_rd_len is not None else 2 * self.ctx.drlevel, dthreshold, n_neighbors, skip_zero)
+        n = check(lib().kssd_dist_stats(self._h, C.byref(o)))
+        if not fetch:
+            return n
+        rows = np.empty(n, dtype=capi.STAT_ROW_DTYPE)
+        check(lib().kssd_dist_fetch_stats(self._h, rows.ctypes.data_as(C.c_void_p)))
+        return rows
+
+    def close(self):
+        if self._h:
+            lib().kssd_dist_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,160 @@
+"""GPU parity: Stage II (inverted index) and Stage III (shared counts, statistics) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from public_kssd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sketches():
+    rc, ri = synth.synth_sketches(300, 400, seed=5, cluster_size=20)
+    qc, qi = synth.synth_sketches(70, 400, seed=5, cluster_size=7)     # same ancestors -> shared codes
+    return rc, ri, qc, qi
+
+
+def test_index_matches_oracle(gpu_ctx_l3k10, oracle_mod, sketches):
+    rc, ri, _, _ = sketches
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    uc, uo, gids = ix.csr()
+    euc, euo, egids = oracle_mod.csr_from_combco(rc, ri)
+    assert np.array_equal(uc, euc) and np.array_equal(uo, euo) and np.array_equal(gids, egids)
+    # mco.<c> exactly as the reference writes it
+    mco, _ = oracle_mod.combco2mco(rc, ri)
+    assert np.array_equal(gids, mco)
+    ix.close()
+
+
+def test_index_dense_table(gpu_ctx_l3k10, oracle_mod):
+    rc, ri = synth.synth_sketches(40, 300, seed=9)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    dense = ix.dense()
+    mco, edense = oracle_mod.combco2mco(rc, ri, dense=True)
+    assert dense.shape == edense.shape and np.array_equal(dense, edense)
+    # round trip through the reference's file content
+    ix2 = gpu_ctx_l3k10.index_from_dense(dense, mco, 40)
+    a, b = ix.csr(), ix2.csr()
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    ix.close(); ix2.close()
+
+
+def test_index_edge_cases(gpu_ctx_l3k10, oracle_mod):
+    # empty genomes in the middle, code 0 and the largest 28-bit code, one genome only
+    codes = np.array([0, 5, (1 << 28) - 1, 5, 7, (1 << 28) - 1, 0], dtype=np.uint32)
+    index = np.array([0, 3, 3, 6, 6, 7], dtype=np.uint64)
+    ix = gpu_ctx_l3k10.combco2mco(codes, index)
+    uc, uo, gids = ix.csr()
+    euc, euo, egids = oracle_mod.csr_from_combco(codes, index)
+    assert np.array_equal(uc, euc) and np.array_equal(uo, euo) and np.array_equal(gids, egids)
+    ix.close()
+
+
+def test_dist_counts_match_oracle(gpu_ctx_l3k10, oracle_mod, sketches):
+    from public_kssd_b200 import kssd
+    rc, ri, qc, qi = sketches
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    job = kssd.DistJob(gpu_ctx_l3k10, np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32))
+    job.accumulate(ix, qc, qi)
+    ct = job.counts()
+    euc, euo, egids = oracle_mod.csr_from_combco(rc, ri)
+    exp = oracle_mod.dist_counts(qc, qi, euc, euo, egids, len(ri) - 1)
+    assert np.array_equal(ct, exp)
+    assert ct.sum() > 0
+    # brute force on a few pairs
+    for q, r in [(0, 0), (3, 2), (69, 299), (10, 21)]:
+        a = qc[int(qi[q]):int(qi[q + 1])]; b = rc[int(ri[r]):int(ri[r + 1])]
+        assert ct[q, r] == np.intersect1d(a, b).size
+    # a second component accumulates on top (command_dist.c:769-785)
+    job.accumulate(ix, qc, qi)
+    assert np.array_equal(job.counts(), 2 * exp)
+    job.close(); ix.close()
+
+
+def test_dist_counts_wide_and_big_query(gpu_ctx_l3k10, oracle_mod):
+    """More refs than one shared-memory strip holds, and a query sketch >= 65536 codes (32-bit strip path)."""
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(60_000, 24, seed=3, cluster_size=50)
+    qc, qi = synth.synth_sketches(8, 24, seed=3, cluster_size=2)
+    big = np.unique(np.concatenate([rc[:200_000:2], synth.synth_sketches(1, 70_000, seed=77)[0]]))
+    qc2 = np.concatenate([qc, big]).astype(np.uint32)
+    qi2 = np.concatenate([qi, [qi[-1] + big.size]]).astype(np.uint64)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    euc, euo, egids = oracle_mod.csr_from_combco(rc, ri)
+    for codes, index in [(qc, qi), (qc2, qi2)]:
+        job = kssd.DistJob(gpu_ctx_l3k10, np.diff(index).astype(np.uint32), np.diff(ri).astype(np.uint32))
+        job.accumulate(ix, codes, index)
+        exp = oracle_mod.dist_counts(codes, index, euc, euo, egids, len(ri) - 1, nthreads=8)
+        assert np.array_equal(job.counts(), exp)
+        job.close()
+    ix.close()
+
+
+def _check_rows(rows, ct, qsz, rsz, oracle_mod, metric, correction, dthr, kmerlen=20, dim_rd_len=6, skip_zero=0):
+    Q, R = ct.shape
+    cmprsn = (Q * R) & 0xFFFFFFFF
+    exp = []
+    for q in range(Q):
+        for r in range(R):
+            keep, v = oracle_mod.output_ctrl(rsz[r], qsz[q], ct[q, r], metric, correction, kmerlen, dim_rd_len, dthr, cmprsn)
+            if keep and not (skip_zero and ct[q, r] == 0):
+                exp.append((q, r, v))
+    assert len(rows) == len(exp)
+    for row, (q, r, v) in zip(rows, exp):
+        assert row["qry"] == q and row["ref"] == r and row["shared"] == ct[q, r]
+        assert row["ref_size"] == rsz[r] and row["qry_size"] == qsz[q]
+        assert row["rs_u"] == np.uint32(v[8]) if np.isfinite(v[8]) else True
+        got = [row[n] for n in ("metric", "dist", "pvalue", "fdr", "ci_metric_lo", "ci_metric_hi", "ci_dist_lo", "ci_dist_hi")]
+        for g, e in zip(got, v[:8]):
+            if np.isnan(e):
+                assert np.isnan(g)
+            elif np.isinf(e):
+                assert g == e
+            else:
+                assert abs(g - e) <= 1e-6 * max(abs(e), 1e-300), (q, r, g, e)     # north_star: 1e-6 relative
+
+
+@pytest.mark.parametrize("metric,correction,dthr,skip_zero", [(0, 0, 1.0, 0), (1, 0, 1.0, 0), (0, 1, 1.0, 0), (1, 1, 0.2, 0), (0, 0, 0.05, 1)])
+def test_stats_match_output_ctrl(gpu_ctx_l3k10, oracle_mod, metric, correction, dthr, skip_zero):
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(45, 500, seed=5, cluster_size=9)
+    qc, qi = synth.synth_sketches(12, 500, seed=5, cluster_size=4)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    job = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz)
+    job.accumulate(ix, qc, qi)
+    ct = job.counts()
+    rows = job.stats(metric=metric, correction=correction, dthreshold=dthr, skip_zero=skip_zero)
+    _check_rows(rows, ct, qsz, rsz, oracle_mod, metric, correction, dthr, skip_zero=skip_zero)
+    job.close(); ix.close()
+
+
+def test_topn_neighbors(gpu_ctx_l3k10, oracle_mod):
+    """-N: best n refs per query by the raw metric, insertion semantics of command_dist.c:1212-1227."""
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(60, 300, seed=5, cluster_size=12)
+    qc, qi = synth.synth_sketches(9, 300, seed=5, cluster_size=3)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    job = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz)
+    job.accumulate(ix, qc, qi)
+    ct = job.counts()
+    for metric in (0, 1):
+        N = 5
+        rows = job.stats(metric=metric, n_neighbors=N)
+        exp = []
+        for q in range(len(qsz)):
+            best = [(0.0, -1)] * (N + 1)
+            for r in range(len(rsz)):
+                X, Y, I = int(rsz[r]), int(qsz[q]), int(ct[q, r])
+                m = I / min(X, Y) if metric == 1 else I / (X + Y - I)
+                i = N - 1
+                while i >= 0 and m > best[i][0]:
+                    best[i + 1] = best[i]
+                    best[i] = (m, r)
+                    i -= 1
+            exp += [(q, r) for (m, r) in best[:N] if r != -1]
+        assert [(int(a["qry"]), int(a["ref"])) for a in rows] == exp
+    with pytest.raises(kssd.KssdError):
+        job.stats(n_neighbors=61)
+    job.close(); ix.close()
