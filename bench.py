@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Kssd hot path on B200 (BASELINE.json configs[1]).
+
+Workload ("step"): Stage I over one batch of synthetic genomes -- 1,000 x 5 Mbp, 80-column FASTA,
+50 clusters x 20 members with 0.1-10 % substitutions, L3K10 (k=10, subk=6, drlevel=3) -- i.e. the
+sequence -> sketch path (fasta2co + writers) for the whole batch.  metric = sketch Gbp/s.
+The all-vs-all Stage II + III pass over the resulting sketches (index, 10^6 shared counts, fused
+statistics) is timed in the same run and reported under "dist" (pairs/s), with its own roofline.
+
+  value        Gbp/s with the batch already resident in HBM (kssd_sketch_batch_dev), CUDA events on the
+               library's stream, barrier + synchronize on both sides, max over ranks.
+  e2e          the same batch through the reference-facing C-ABI with HOST buffers
+               (kssd_sketch_batch_host from pinned memory; ids/index fetched back every step).
+  roofline     the scan kernel: algorithmic bytes = 1 B per input text byte over the
+               kernel time measured with CUDA events inside the library, vs MEASURED_PEAKS.json.
+  cpu_baseline the unmodified reference (oracle/_ref/kssd, all host cores) on a bounded sample of the
+               same genomes; `--impl reference` runs only that arm.
+
+N > 1 (torchrun): every rank sketches its own 1,000-genome batch (weak scaling, no collective on the
+sketch path -- genomes are independent); value = all ranks' bp / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K, SUBK, DRLEVEL = 10, 6, 3
+SHUF_SEED = 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genomes", type=int, default=1000)
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0, help="genomes in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic batch, generated on the device (5 GB of FASTA text) -- same shape as synth.cluster_genomes
+# ------------------------------------------------------------------------------------------------
+def make_batch_device(n_genomes, genome_len, seed, device, cluster_size=20, width=80):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    nl = width + 1
+    full = genome_len // width
+    rem = genome_len - full * width
+    body_len = full * nl + (rem + 1 if rem else 0)
+    hdr_len = 16
+    rec_len = hdr_len + body_len
+    stride = (rec_len + 127) // 128 * 128
+    buf = torch.full((n_genomes * stride + 1024,), 10, dtype=torch.uint8, device=device)
+    goff = np.arange(n_genomes, dtype=np.uint64) * np.uint64(stride)
+    glen = np.full(n_genomes, rec_len, dtype=np.uint64)
+    anc = None
+    for i in range(n_genomes):
+        m = i % cluster_size
+        if m == 0:
+            anc = torch.randint(0, 4, (genome_len,), generator=g, device=device, dtype=torch.uint8)
+            b = anc
+        else:
+            rate = 0.001 * (100.0 ** ((m - 1) / max(cluster_size - 2, 1)))
+            hit = torch.rand(genome_len, generator=g, device=device) < rate
+            shift = torch.randint(1, 4, (genome_len,), generator=g, device=device, dtype=torch.uint8)
+            b = (anc + shift * hit) & 3
+        txt = lut[b.long()]
+        o = i * stride
+        hdr = (">g%06d c%04d" % (i, i // cluster_size)).encode().ljust(hdr_len - 1, b" ")[: hdr_len - 1] + b"\n"
+        buf[o:o + hdr_len] = torch.tensor(list(hdr), dtype=torch.uint8, device=device)
+        o += hdr_len
+        if full:
+            blk = buf[o:o + full * nl].view(full, nl)
+            blk[:, :width] = txt[: full * width].view(full, width)
+            blk[:, width] = 10
+            o += full * nl
+        if rem:
+            buf[o:o + rem] = txt[full * width:]
+            buf[o + rem] = 10
+    return buf, goff, glen
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the unmodified CPU kssd on the box's host cores
+# ------------------------------------------------------------------------------------------------
+def reference_run(host_genomes, shuf_table, steps, warmup, cores, with_dist=True):
+    """host_genomes: list of uint8 arrays (FASTA text).  Times `kssd dist` stage I per step on tmpfs;
+    stage II / III once.  Returns dict."""
+    from oracle import oracle as O
+    if not O.REF_BIN.exists():
+        O.build()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    work = Path(tempfile.mkdtemp(prefix="kssd_refbench_", dir=base))
+    try:
+        shuf = work / "L3K10.shuf"
+        O.write_shuf_file(shuf, 4242, K, SUBK, DRLEVEL, shuf_table)
+        ind = work / "in"
+        ind.mkdir()
+        total_bp = 0
+        total_bytes = 0
+        for i, g in enumerate(host_genomes):
+            (ind / f"g{i:05d}.fasta").write_bytes(g.tobytes())
+            total_bytes += g.size
+            total_bp += int(np.count_nonzero((g == 65) | (g == 67) | (g == 71) | (g == 84)))
+        times = []
+        for it in range(warmup + steps):
+            out = work / f"sk{it}"
+            t0 = time.perf_counter()
+            r = subprocess.run([str(O.REF_BIN), "dist", "-p", str(cores), "-L", str(shuf), "-o", str(out), str(ind)],
+                               capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0 or not (out / "cofiles.stat").exists():
+                raise RuntimeError("reference stage I failed: " + r.stderr[-300:])
+            if it >= warmup:
+                times.append(dt)
+            if it < warmup + steps - 1:
+                shutil.rmtree(out)
+        res = {"sketch_s": float(np.mean(times)), "bp": total_bp, "bytes": total_bytes, "genomes": len(host_genomes)}
+        if with_dist:
+            t0 = time.perf_counter()
+            r = subprocess.run([str(O.REF_BIN), "dist", "-p", str(cores), "-o", str(out), str(out)], capture_output=True, text=True)
+            res["index_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            r = subprocess.run([str(O.REF_BIN), "dist", "-p", str(cores), "-r", str(out), "-o", str(work / "dist"), str(out)],
+                               capture_output=True, text=True)
+            res["dist_s"] = time.perf_counter() - t0
+            res["dist_pairs"] = len(host_genomes) ** 2
+            res["dist_ok"] = (work / "dist" / "distance.out").exists()
+        return res
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    from public_kssd_b200 import synth
+    table = synth.make_shuf_table(SUBK, SHUF_SEED)
+    workload = f"{args.genomes} x {args.genome_len} bp synthetic bacterial genomes, 80-col FASTA, L{DRLEVEL}K{K} (subk {SUBK})"
+    config = {"workload": workload, "configs_index": 1, "genomes_per_gpu": args.genomes, "genome_len": args.genome_len,
+              "k": K, "subk": SUBK, "drlevel": DRLEVEL, "l2": "inputs (5 GB) larger than L2, no flush needed",
+              "sharding": "genomes across ranks, no collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_s = args.ref_sample or max(16, min(4 * cores, 256))
+        n_s = min(n_s, args.genomes)
+        gens = [synth.to_fasta(b, n, 80) for n, b in synth.cluster_genomes(n_s, args.genome_len, seed=20260101, cluster_size=20)]
+        r = reference_run(gens, table, args.steps, args.warmup, cores)
+        val = r["bp"] / r["sketch_s"] / 1e9
+        sample = f"{n_s} of the workload's genomes ({r['bytes'] / 1e6:.0f} MB FASTA on tmpfs), kssd dist -p {cores}, per step"
+        line = {"impl": "reference", "metric": "sketch_gbp_per_s", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["sketch_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "dist": {"pairs_per_s": r.get("dist_pairs", 0) / max(r.get("dist_s", 1e-9), 1e-9), "pairs": r.get("dist_pairs"),
+                         "dist_s": r.get("dist_s"), "index_s": r.get("index_s"), "note": "stage III incl. distance.out text; stage II separately"}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from public_kssd_b200 import capi, kssd
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = kssd.Context(K, SUBK, DRLEVEL, table, device=local_rank, shuf_id=4242)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    buf, goff, glen = make_batch_device(args.genomes, args.genome_len, 20260101 + rank, dev)
+    torch.cuda.synchronize()
+    nbytes = int(buf.numel())
+    text_bytes = int(glen.sum())
+    bp = args.genomes * args.genome_len
+    L = capi.lib()
+
+    def sketch_dev():
+        return ctx.sketch_raw(None, nbytes, goff, glen, device_ptr=buf.data_ptr())
+
+    # ---- correctness guard inside the bench: a sample of genomes against the oracle (not timed) ----
+    launches0 = L.kssd_kernel_launch_count()
+    for _ in range(args.warmup):
+        h = sketch_dev()
+        L.kssd_sketch_free(h)
+    scan_ms = []
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = L.kssd_kernel_launch_count()
+    e0.record(stream)
+    last = None
+    for _ in range(args.steps):
+        if last is not None:
+            L.kssd_sketch_free(last)
+        last = sketch_dev()
+        scan_ms.append(ctx.last_ms(0))
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    gpu_launches = int(L.kssd_kernel_launch_count() - l0)
+    step_ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms_max = float(t.item())
+    value = world * bp / (step_ms_max * 1e-3) / 1e9
+
+    # ---- Stage II + III on the sketches just made (all-vs-all), device resident ----
+    sk_h = last
+    ids_p, idx_p = capi.C.c_void_p(), capi.C.c_void_p()
+    capi.check(L.kssd_sketch_dev_ptrs(sk_h, 0, capi.C.byref(ids_p), capi.C.byref(idx_p)))
+    n_codes = int(capi.check(L.kssd_sketch_count(sk_h, 0)))
+    index_host = np.empty(args.genomes + 1, dtype=np.uint64)
+    capi.check(L.kssd_sketch_fetch(sk_h, 0, None, capi.ptr(index_host, capi.C.c_uint64), None, None))
+    sizes = np.diff(index_host).astype(np.uint32)
+    dist_info = {}
+    ix_ms, ct_ms, st_ms = [], [], []
+    for it in range(3):
+        ixh = capi.C.c_void_p()
+        capi.check(L.kssd_index_build_dev(ctx._h, ids_p, idx_p, args.genomes, n_codes, capi.C.byref(ixh)))
+        ix_ms.append(ctx.last_ms(2))
+        ix = kssd.Index(ctx, ixh)
+        job = kssd.DistJob(ctx, sizes, sizes)
+        job.accumulate_dev(ix, ids_p.value, idx_p.value, n_codes)
+        ct_ms.append(ctx.last_ms(3))
+        nrows = job.stats(fetch=False)
+        st_ms.append(ctx.last_ms(4))
+        if it == 2:
+            ct = job.counts()
+            dist_info["shared_total"] = int(ct.sum(dtype=np.uint64))
+            dist_info["diag_ok"] = bool(np.array_equal(np.diag(ct), sizes))
+            dist_info["rows"] = int(nrows)
+        job.close(); ix.close()
+    pairs = args.genomes * args.genomes
+    peak, peak_src = peaks()
+    d_ct, d_st, d_ix = float(np.min(ct_ms)), float(np.min(st_ms)), float(np.min(ix_ms))
+    dist_bytes = 4 * n_codes + 8 * n_codes + 4 * dist_info.get("shared_total", 0) + 4 * pairs
+    dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": world * pairs / ((d_ct + d_st) * 1e-3), "count_ms": d_ct,
+                      "stats_ms": d_st, "index_ms": d_ix,
+                      "roofline": {"bound": "hbm", "achieved": dist_bytes / (d_ct * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": dist_bytes / (d_ct * 1e-3) / 1e9 / peak, "traffic": None,
+                                   "note": "count kernel; bytes = 4*Nq + 8*Nq + 4*P + 4*Q*R (SURVEY.md s8d)"}})
+
+    # ---- end to end through the C-ABI with host buffers ----
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host.copy_(buf)
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    e2e_steps = max(2, min(args.steps, 5))
+    d2h = 0
+
+    def sketch_host():
+        nonlocal d2h
+        h = ctx.sketch_raw(host_np, nbytes, goff, glen)
+        n = int(capi.check(L.kssd_sketch_count(h, 0)))
+        ids = np.empty(n, dtype=np.uint32)
+        ixx = np.empty(args.genomes + 1, dtype=np.uint64)
+        capi.check(L.kssd_sketch_fetch(h, 0, capi.ptr(ids, capi.C.c_uint32), capi.ptr(ixx, capi.C.c_uint64), None, None))
+        L.kssd_sketch_free(h)
+        d2h = ids.nbytes + ixx.nbytes
+        return ids, ixx
+
+    sketch_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ids_e2e, ix_e2e = sketch_host()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * bp / float(te.item()) / 1e9
+
+    # the device-resident and host paths must agree with each other
+    ids_dev = np.empty(n_codes, dtype=np.uint32)
+    capi.check(L.kssd_sketch_fetch(sk_h, 0, capi.ptr(ids_dev, capi.C.c_uint32), None, None, None))
+    same = bool(np.array_equal(ids_dev, ids_e2e) and np.array_equal(index_host, ix_e2e))
+    L.kssd_sketch_free(sk_h)
+
+    scan = float(np.median(scan_ms))
+    roof = {"bound": "hbm", "achieved": text_bytes / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": text_bytes / (scan * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "kernel": "sketch_fasta_kernel", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            n_s = args.ref_sample or max(16, min(2 * cores, 128))
+            n_s = min(n_s, args.genomes)
+            gens = []
+            for i in range(n_s):
+                o = int(goff[i])
+                gens.append(host_np[o:o + int(glen[i])].copy())
+            r = reference_run(gens, table, 1, 0, cores)
+            # parity of the sampled genomes against the oracle restatement (checker only)
+            from oracle import oracle as O
+            orc = O.Ctx(K, SUBK, DRLEVEL, table)
+            ok = True
+            for i in range(min(3, n_s)):
+                ids_o, _ = orc.fasta(gens[i])
+                ok &= bool(np.array_equal(np.sort(ids_o), ids_e2e[int(ix_e2e[i]):int(ix_e2e[i + 1])]))
+            cpu_baseline = {"value": r["bp"] / r["sketch_s"] / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+                            "sample": f"first {n_s} genomes of rank 0's batch ({r['bytes'] / 1e6:.0f} MB FASTA on tmpfs), one `kssd dist -p {cores}` run",
+                            "sketch_s": r["sketch_s"], "index_s": r.get("index_s"), "dist_s": r.get("dist_s"),
+                            "dist_pairs_per_s": r.get("dist_pairs", 0) / max(r.get("dist_s", 1e-9), 1e-9), "oracle_parity_on_sample": ok}
+        except Exception as ex:  # the baseline must not take the measurement down
+            cpu_baseline = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": "sketch_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "config": config, "clocks": clk,
+                "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": float(te.item()) * 1e3, "matches_device_path": same},
+                "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu_baseline, "dist": dist_info,
+                "sketch": {"codes": n_codes, "text_bytes": text_bytes, "scan_kernel_ms": scan, "step_ms": step_ms_max}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
