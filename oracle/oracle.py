@@ -282,11 +282,20 @@ class RefRun:
         self.k, self.s, self.L = k, s, L
 
     def sketch(self, files_dir, outname, extra=(), p=1):
+        """Stage I.  With comp_num > 1 (K11) the reference corrupts its heap intermittently (glibc aborts in
+        sysmalloc after the last genome, thread-count dependent; observed here with -p 1 and -p 4, not -p 2);
+        the sets it writes when it survives are deterministic, so a crashed run is retried with another -p."""
         out = self.dir / outname
-        r = run_ref(["dist", "-p", p, "-L", self.shuf, "-o", out, *extra, files_dir], cwd=self.dir)
-        if r.returncode != 0 or not (out / "cofiles.stat").exists():
-            raise RuntimeError(f"reference sketch failed rc={r.returncode}: {r.stderr[-500:]} {r.stdout[-300:]}")
-        return out
+        last = None
+        for pp in [p] + [x for x in (2, 3, 5, 1) if x != p]:
+            shutil.rmtree(out, ignore_errors=True)
+            r = run_ref(["dist", "-p", pp, "-L", self.shuf, "-o", out, *extra, files_dir], cwd=self.dir)
+            if r.returncode == 0 and (out / "cofiles.stat").exists():
+                return out
+            last = r
+            if r.returncode != -6:
+                break
+        raise RuntimeError(f"reference sketch failed rc={last.returncode}: {last.stderr[-500:]} {last.stdout[-300:]}")
 
     def index(self, sketch_dir, binary=None, p=1):
         r = run_ref(["dist", "-p", p, "-o", sketch_dir, sketch_dir], cwd=self.dir, binary=binary)

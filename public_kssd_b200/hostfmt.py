@@ -99,3 +99,41 @@ def write_mco(d, comp: int, gids: np.ndarray, dense_incl: np.ndarray) -> None:
 
 def read_mco(d, comp: int):
     return np.fromfile(Path(d, f"mco.{comp}"), dtype="<u4"), np.fromfile(Path(d, f"mco.index.{comp}"), dtype="<u8")
+
+
+# ------------------------------------------------------------------------------------------------
+# distance.out text (dist_print_nobin / output_ctrl, command_dist.c:1188-1195, :1268-1285)
+# ------------------------------------------------------------------------------------------------
+_HEADER = (("Jaccard\tMashD", "P-value(J)\tFDR(J)", "Jaccard_CI\tMashD_CI"),
+           ("ContainmentM\tAafD", "P-value(C)\tFDR(C)", "ContainmentM_CI\tAafD_CI"))
+
+
+def _c_double(v: float, spec: str) -> str:
+    """glibc printf of a double for '%.6lf' (spec 'f') and '%E' (spec 'E'), including -nan / inf spellings."""
+    import math
+    if math.isnan(v):
+        neg = math.copysign(1.0, v) < 0
+        s = "nan" if spec == "f" else "NAN"
+        return ("-" if neg else "") + s
+    if math.isinf(v):
+        s = "inf" if spec == "f" else "INF"
+        return ("-" if v < 0 else "") + s
+    return ("%.6f" % v) if spec == "f" else ("%E" % v)
+
+
+def distance_out_header(metric: int, outfields: int) -> str:
+    return "Qry\tRef\tShared_k|Ref_s|Qry_s" + "".join("\t" + _HEADER[metric][i] for i in range(outfields + 1)) + "\n"
+
+
+def format_stat_rows(rows, qry_names, ref_names, metric: int = 0, outfields: int = 2) -> str:
+    """rows: numpy structured array from DistJob.stats() -> the body of distance.out (one line per row)."""
+    out = []
+    for r in rows:
+        s = "%s\t%s\t%d-%d|%d|%d\t%s\t%s" % (qry_names[int(r["qry"])], ref_names[int(r["ref"])], r["shared"], r["rs_u"], r["ref_size"],
+                                           r["qry_size"], _c_double(float(r["metric"]), "f"), _c_double(float(r["dist"]), "f"))
+        if outfields >= 1:
+            s += "\t%s\t%s" % (_c_double(float(r["pvalue"]), "E"), _c_double(float(r["fdr"]), "E"))
+        if outfields >= 2:
+            s += "\t[%s,%s]\t[%s,%s]" % tuple(_c_double(float(r[n]), "f") for n in ("ci_metric_lo", "ci_metric_hi", "ci_dist_lo", "ci_dist_hi"))
+        out.append(s + "\n")
+    return "".join(out)

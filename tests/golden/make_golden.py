@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/kssd, built by
+oracle/Makefile from /root/reference) on the seeded inputs of cases.py.  Run here (the container with
+/root/reference); the outputs are committed so the pin travels to boxes without the reference.
+
+    python tests/golden/make_golden.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+from oracle import oracle as O  # noqa: E402
+from public_kssd_b200 import synth  # noqa: E402
+import cases  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def by_name(d):
+    """sketch dir -> {basename without extension: [per component id arrays (file order)]}, plus stat."""
+    st = O.read_cofiles_stat(d)
+    res = {}
+    comps = [O.read_combco(d, c) for c in range(st["comp_num"])]
+    for i, nm in enumerate(st["names"]):
+        key = Path(nm).name.rsplit(".", 1)[0]
+        res[key] = [(codes[int(ix[i]):int(ix[i + 1])], None if ab is None else ab[int(ix[i]):int(ix[i + 1])]) for codes, ix, ab in comps]
+    return st, res
+
+
+def sketch_case(tag, k, s, L, table, inputs, ext, extra=(), store_abund=False):
+    rr = O.RefRun(k, s, L, table, shuf_id=cases.SHUF_ID)
+    d = rr.dir / "in"
+    d.mkdir()
+    for n, b in inputs.items():
+        (d / f"{n}.{ext}").write_bytes(b.tobytes())
+    out = rr.sketch(d, "sk", extra=extra, p=1)
+    st, res = by_name(out)
+    pack = {"comp_num": np.int32(st["comp_num"]), "kmerlen": np.int32(st["kmerlen"]), "dim_rd_len": np.int32(st["dim_rd_len"]),
+            "names": np.array(sorted(res))}
+    for n in sorted(res):
+        for c, (ids, ab) in enumerate(res[n]):
+            pack[f"{n}.{c}"] = ids            # reference order (hash-slot order)
+            if store_abund and ab is not None:
+                pack[f"{n}.{c}.a"] = ab
+    np.savez_compressed(OUT / f"{tag}.npz", **pack)
+    print(tag, {n: [len(x[0]) for x in res[n]] for n in sorted(res)})
+    return rr, out, st
+
+
+def main():
+    O.build()
+    assert O.ref_available(), "reference binary missing: make -C oracle ref"
+    t6 = synth.make_shuf_table(6, cases.SHUF_SEED_S6)
+    t5 = synth.make_shuf_table(5, cases.SHUF_SEED_S5)
+    fa, fq = cases.fasta_inputs(), cases.fastq_inputs()
+
+    # ---- Stage I, FASTA ----
+    rr, out, st = sketch_case("fasta_l3k10", 10, 6, 3, t6, fa, "fasta")
+    # ---- Stage II + III on the same sketches: refs = all, queries = subset ----
+    rr.index(out)
+    mco = np.fromfile(out / "mco.0", dtype="<u4")
+    dense = np.fromfile(out / "mco.index.0", dtype="<u8")
+    nz = np.flatnonzero(np.diff(np.concatenate([[0], dense])))
+    mst = O.read_mcofiles_stat(out)
+    qd = rr.dir / "qin"
+    qd.mkdir()
+    for n in ("h_anc", "i_mut1", "j_mut5", "d_messy"):
+        (qd / f"{n}.fasta").write_bytes(fa[n].tobytes())
+    qout = rr.sketch(qd, "qsk", p=1)
+    qst = O.read_cofiles_stat(qout)
+    pack = {"ref_names": np.array([Path(n).name.rsplit(".", 1)[0] for n in mst["names"]]), "ref_ctx_ct": mst["ctx_ct"],
+            "qry_names": np.array([Path(n).name.rsplit(".", 1)[0] for n in qst["names"]]), "qry_ctx_ct": qst["ctx_ct"],
+            "mco": mco, "dense_nonzero_codes": nz.astype(np.uint32), "dense_values_at_nonzero": dense[nz], "dense_last": dense[-1:],
+            "mcofiles_stat": np.frombuffer((out / "mcofiles.stat").read_bytes(), dtype=np.uint8),
+            "cofiles_stat": np.frombuffer((out / "cofiles.stat").read_bytes(), dtype=np.uint8),
+            "ref_combco": np.fromfile(out / "combco.0", dtype="<u4"), "ref_combco_index": np.fromfile(out / "combco.index.0", dtype="<u8"),
+            "qry_combco": np.fromfile(qout / "combco.0", dtype="<u4"), "qry_combco_index": np.fromfile(qout / "combco.index.0", dtype="<u8")}
+    variants = {"default": [], "M1_O1": ["-M", "1", "-O", "1"], "corr_O2": ["--correction", "1"], "N2_M1": ["-N", "2", "-M", "1"],
+                "D0.1": ["-D", "0.1"], "O0": ["-O", "0"]}
+    for tag, extra in variants.items():
+        dout = rr.dist(out, qout, f"dist_{tag}", extra=["--keepskf"] + extra if tag == "default" else extra)
+        pack[f"distance_out.{tag}"] = np.frombuffer((dout / "distance.out").read_bytes(), dtype=np.uint8)
+        if tag == "default":
+            pack["sharedk_ct"] = np.fromfile(dout / "sharedk_ct.dat", dtype="<u4").reshape(len(qst["names"]), len(mst["names"]))
+    np.savez_compressed(OUT / "index_dist_l3k10.npz", **pack)
+    print("index/dist: postings", mco.size, "unique", nz.size, "ct\n", pack["sharedk_ct"])
+    rr.cleanup()
+
+    # ---- Stage I variants ----
+    rr, _, _ = sketch_case("fasta_uniq_l3k10", 10, 6, 3, t6, {n: fa[n] for n in ("g_dup", "d_messy", "a_plain80")}, "fasta", extra=["-u"])
+    rr.cleanup()
+    rr, _, _ = sketch_case("fasta_l2k8", 8, 5, 2, t5, {n: fa[n] for n in ("a_plain80", "d_messy", "f_short_lines")}, "fasta")
+    rr.cleanup()
+    rr, _, _ = sketch_case("fasta_l3k11", 11, 6, 3, t6, {n: fa[n] for n in ("a_plain80", "d_messy", "h_anc")}, "fasta")
+    rr.cleanup()
+    for tag, extra in {"fastq_l2k8_q0n1": [], "fastq_l2k8_q40n2": ["-Q", "40", "-n", "2"], "fastq_l2k8_q0n3": ["-n", "3"]}.items():
+        rr, _, _ = sketch_case(tag, 8, 5, 2, t5, fq, "fastq", extra=extra)
+        rr.cleanup()
+    rr, _, _ = sketch_case("fastq_l3k11_q0n2", 11, 6, 3, t6, fq, "fastq", extra=["-n", "2"])
+    rr.cleanup()
+    rr, _, _ = sketch_case("fastq_abund_l2k8", 8, 5, 2, t5, fq, "fastq", extra=["-A"], store_abund=True)
+    rr.cleanup()
+
+
+if __name__ == "__main__":
+    main()
