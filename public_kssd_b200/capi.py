@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libkssd_b200.so"
+LIB_PATH = Path(os.environ.get("KSSD_B200_LIB", PKG_DIR / "libkssd_b200.so"))
 
 # every symbol include/kssd_b200.h declares (tests/test_capi_symbols.py checks header <-> this list <-> .so)
 SYMBOLS = [

@@ -109,8 +109,8 @@ __global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t 
         if (v < 0 || (uint32_t)v >= dim_end) continue;
         const uint32_t a = d & pfmask;
         const uint32_t b = (uint32_t)revcomp2((uint64_t)d, 2 * s) & pfmask;
-        atomicOr(&prefilter[a >> 5], 1u << (a & 31));
-        atomicOr(&prefilter[b >> 5], 1u << (b & 31));
+        atomicOr(&prefilter[a >> 5], 0x80000000u >> (a & 31));   // reversed bit order, see pf_test_top()
+        atomicOr(&prefilter[b >> 5], 0x80000000u >> (b & 31));
         uint32_t h = mix32(d) & ht_mask;
         for (;;) {
             const uint32_t old = atomicCAS(&ht[h].x, kHtEmpty, d);
@@ -142,6 +142,12 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // keep stream-ordered allocations cached in the pool instead of returning them at every sync
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (auto &e : c->ev) CU(cudaEventCreate(&e));
 
     SketchParams &P = c->P;
@@ -154,6 +160,7 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.outmask = (1ull << (2 * P.out)) - 1ull;
     P.innermask = (uint32_t)((1ull << (4 * subk)) - 1ull);
     P.pfmask = std::min<uint32_t>(P.innermask, (1u << kPfBits) - 1u);
+    P.pf_amask = (P.pfmask >> 5) << 2;
     const uint64_t subspace = 1ull << (4 * (subk - drlevel));
     P.dim_end = (uint32_t)std::max<uint64_t>(subspace, 4096);   // MIN_SUBCTX_DIM_SMP_SZ
     P.comp_code_bits = (k - drlevel > component_sz) ? 4 * (k - drlevel - component_sz) : 0;
@@ -243,6 +250,8 @@ struct kssd_sketch {
     int n_genomes = 0, n_comp = 1, mode = 0;
     uint64_t n_occ = 0, total = 0;
     float scan_ms = 0;
+    uint8_t *d_blob = nullptr;                   // one stream-ordered allocation: ids | ord | abund | index
+    size_t blob_bytes = 0;
     uint32_t *d_ids = nullptr;
     uint16_t *d_abund = nullptr;
     uint64_t *d_ord = nullptr;
@@ -285,6 +294,12 @@ __global__ void sketch_scatter_kernel(const uint64_t *__restrict__ keys, const u
     ord[p] = minord[i];
     const uint32_t comp = (uint32_t)(key >> 56), gid = (uint32_t)(key >> 28) & 0x0fffffffu;
     atomicAdd(&per_cg[(uint64_t)comp * n_genomes + gid], 1u);
+}
+
+// total kept = pos[n-1] + flags[n-1], left in the slot after the per-(component, genome) counters
+__global__ void sketch_total_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos, uint32_t n, uint32_t *__restrict__ slot)
+{
+    *slot = pos[n - 1] + flags[n - 1];
 }
 
 static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const uint64_t *goff, const uint64_t *glen, int n_genomes,
@@ -376,8 +391,16 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     S->status.assign(n_genomes, 0);
     S->comp_start.assign(n_comp + 1, 0);
     S->index.assign((size_t)n_comp * (n_genomes + 1), 0);
-    std::vector<uint32_t> per_cg((size_t)n_comp * n_genomes, 0);
-    uint32_t kept = 0;
+    std::vector<uint32_t> per_cg((size_t)n_comp * n_genomes + 1, 0);   // [n_comp*n_genomes] = kept total
+    // one stream-ordered allocation holds ids | ord | abund | index for the life of the handle
+    const size_t nmax = std::max<size_t>(n_occ, 1);
+    const size_t o_ids = 0, o_ord = (nmax * 4 + 15) & ~(size_t)15, o_ab = o_ord + nmax * 8, o_idx = (o_ab + nmax * 2 + 15) & ~(size_t)15;
+    S->blob_bytes = o_idx + S->index.size() * 8;
+    CU(cudaMallocAsync(&S->d_blob, S->blob_bytes, c->stream));
+    S->d_ids = reinterpret_cast<uint32_t *>(S->d_blob + o_ids);
+    S->d_ord = reinterpret_cast<uint64_t *>(S->d_blob + o_ord);
+    S->d_abund = reinterpret_cast<uint16_t *>(S->d_blob + o_ab);
+    S->d_index = reinterpret_cast<uint64_t *>(S->d_blob + o_idx);
     if (n_occ) {
         // sort occurrences by (component, genome, id); carry the offset along
         CU(c->keys2.ensure((size_t)n_occ * 8));
@@ -403,29 +426,20 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(c->cubtmp.ensure(tmp2));
         CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp2, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ, c->stream));
         LAUNCHED(2);
-        uint32_t last_pos = 0, last_flag = 0;
-        CU(cudaMemcpyAsync(&last_pos, c->pos.as<uint32_t>() + (n_occ - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(&last_flag, c->flags.as<uint32_t>() + (n_occ - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        kept = last_pos + last_flag;
-    }
-    S->total = kept;
-    CU(cudaMalloc(&S->d_ids, std::max<size_t>(kept, 1) * 4));
-    CU(cudaMalloc(&S->d_abund, std::max<size_t>(kept, 1) * 2));
-    CU(cudaMalloc(&S->d_ord, std::max<size_t>(kept, 1) * 8));
-    CU(cudaMalloc(&S->d_index, S->index.size() * 8));
-    if (n_occ) {
         CU(c->misc.ensure(per_cg.size() * 4));
         CU(cudaMemsetAsync(c->misc.p, 0, per_cg.size() * 4, c->stream));
-        sketch_scatter_kernel<<<(n_occ + 255) / 256, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->flags.as<uint32_t>(), c->pos.as<uint32_t>(),
-                                                                          c->counts.as<uint16_t>(), c->minord.as<uint64_t>(), n_occ, n_genomes,
-                                                                          S->d_ids, S->d_abund, S->d_ord, c->misc.as<uint32_t>());
-        LAUNCHED(1);
+        sketch_scatter_kernel<<<nb, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->flags.as<uint32_t>(), c->pos.as<uint32_t>(),
+                                                         c->counts.as<uint16_t>(), c->minord.as<uint64_t>(), n_occ, n_genomes, S->d_ids,
+                                                         S->d_abund, S->d_ord, c->misc.as<uint32_t>());
+        sketch_total_kernel<<<1, 1, 0, c->stream>>>(c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ,
+                                                    c->misc.as<uint32_t>() + (size_t)n_comp * n_genomes);
+        LAUNCHED(2);
         CU(cudaMemcpyAsync(per_cg.data(), c->misc.p, per_cg.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaMemcpyAsync(S->status.data(), mb + m_stat, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
+    S->total = per_cg[(size_t)n_comp * n_genomes];
     // per-component combco.index (command_dist.c:331-354) and reference error conditions
     std::vector<uint64_t> per_genome(n_genomes, 0);
     uint64_t run = 0;
@@ -448,7 +462,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     }
     CU(cudaMemcpyAsync(S->d_index, S->index.data(), S->index.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev[2], c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventSynchronize(c->ev[2]));
     CU(cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[2]));
     *out = S;
     return KSSD_OK;
@@ -458,6 +472,7 @@ extern "C" int kssd_sketch_batch_dev(kssd_ctx_t *c, const uint8_t *seq_dev, size
                                      int n_genomes, const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
 {
     if (!c || !seq_dev || !goff || !glen || !out) return fail(KSSD_E_INVAL, "kssd_sketch_batch_dev: null argument");
+    if (reinterpret_cast<uintptr_t>(seq_dev) & 15) return fail(KSSD_E_INVAL, "kssd_sketch_batch_dev: seq_dev must be 16-byte aligned");
     CU(cudaSetDevice(c->device));
     return sketch_run(c, seq_dev, seq_bytes, goff, glen, n_genomes, opts, out);
 }
@@ -519,10 +534,7 @@ extern "C" void kssd_sketch_free(kssd_sketch_t *s)
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->d_ids);
-    cudaFree(s->d_abund);
-    cudaFree(s->d_ord);
-    cudaFree(s->d_index);
+    if (s->d_blob) cudaFreeAsync(s->d_blob, s->ctx->stream);
     delete s;
 }
 

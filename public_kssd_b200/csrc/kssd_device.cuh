@@ -31,6 +31,7 @@ struct SketchParams {
     uint64_t outmask;    // right outer bases (low 2*out bits)
     uint32_t innermask;  // low 4s bits
     uint32_t pfmask;     // min(innermask, 2^20-1)
+    uint32_t pf_amask;   // (pfmask >> 5) << 2: byte offset mask of the bitmap word
     uint32_t dim_end;
     int comp_code_bits;
     uint32_t comp_mask;  // component_num - 1

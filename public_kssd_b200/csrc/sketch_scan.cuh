@@ -20,12 +20,39 @@
 //     canonical min, exact lookup in the sampled-set hash table, drtuple) 32 at a time;
 //   * k-mers are OWNED by the span their first base lies in; a warp runs past the end of its span
 //     until 2k-1 valid bases or a break, so spans never exchange state.
+//
+// The kernel is instruction-issue bound (profiles/r1_sketch_*): every choice below is about the
+// number of ALU-pipe instructions per input byte, not about bytes moved.
 #pragma once
 #include "kssd_device.cuh"
 
+// Tuning switches (A/B measured on B200, see profiles/): which constant shifts go through mul.hi (FMA pipe)
+#ifndef KSSD_MULHI_CLS
+#define KSSD_MULHI_CLS 0
+#endif
+#ifndef KSSD_MULHI_T
+#define KSSD_MULHI_T 0
+#endif
+#ifndef KSSD_MULHI_ADDR
+#define KSSD_MULHI_ADDR 0
+#endif
+#ifndef KSSD_MULHI_ACC
+#define KSSD_MULHI_ACC 0
+#endif
+
 namespace kssd {
 
-constexpr int kScanThreads = 512;               // 16 warps per SM
+template <int S> __device__ __forceinline__ uint32_t shr_fma(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
+#if KSSD_MULHI_CLS
+#define KSSD_SHR_CLS(x, s) shr_fma<s>(x)
+#else
+#define KSSD_SHR_CLS(x, s) ((x) >> (s))
+#endif
+
+#ifndef KSSD_SCAN_THREADS
+#define KSSD_SCAN_THREADS 640
+#endif
+constexpr int kScanThreads = KSSD_SCAN_THREADS; // warps per SM = threads / 32 (one CTA per SM)
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kQueueCap = 64;                   // per-warp candidate stack entries
 constexpr uint64_t kNoSpan = ~0ull;
@@ -55,41 +82,43 @@ struct WarpQueue {
     uint32_t ord[kQueueCap];
 };
 
-// ---- byte classification, 4 bytes at a time (verified exhaustively, see tests/test_bittricks.py) ----
-// diff byte == 0  <=>  byte is one of ACGTacgt, '\n', '\r'
-// sc bit 6 of a byte set  <=> byte has bit 6 clear (for a clean byte: it is '\n' or '\r')
-// p8 = the four 2-bit codes, first byte in the top two bits
-__device__ __forceinline__ void classify4(uint32_t w, uint32_t &diff, uint32_t &sc, uint32_t &p8)
+// ---- byte classification, 4 bytes at a time (bit tricks checked exhaustively in tests/test_bittricks.py) ----
+//   dacc |= nonzero byte  <=>  that byte is NOT one of ACGTacgt, '\n', '\r'
+//   t3   : per byte, bits 0-1 = (b >> 1) & 3 (A0 C1 T2 G3), bit 2 = "bit 6 of b is clear" (a skip byte when clean)
+//   m    : top byte = the four 2-bit codes A0 C1 G2 T3, first byte in the top two bits
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &dacc, uint32_t &t3, uint32_t &m)
 {
-    const uint32_t t3 = ((w >> 1) & 0x03030303u) | ((~w >> 4) & 0x04040404u);
-    const uint32_t u = w & ~((w >> 1) & 0x20202020u);           // fold case of letters only
-    const uint32_t a = t3 | (t3 >> 4);
+    // constant right shifts are written as mul.hi by 2^(32-s): they issue on the FMA pipe, the ALU pipe is the bound
+    const uint32_t s1 = KSSD_SHR_CLS(w, 1);
+    const uint32_t t = s1 & 0x03030303u;
+    t3 = t | (~KSSD_SHR_CLS(w, 4) & 0x04040404u);
+    const uint32_t u = w & ~(s1 & 0x20202020u);                   // fold case of letters only
+    const uint32_t a = t3 | KSSD_SHR_CLS(t3, 4);
     const uint32_t sel = prmt(a, 0u, 0x4420u);
-    const uint32_t e = prmt(0x47544341u, 0xFF0D0AFFu, sel);      // A C T G | - \n \r -
-    diff = u ^ e;
-    sc = ~w & 0x40404040u;
-    const uint32_t t = t3 & 0x03030303u;
-    const uint32_t t2 = t ^ ((t >> 1) & 0x01010101u);            // A0 C1 T2 G3 -> A0 C1 G2 T3
-    p8 = (t2 * 0x40100401u) >> 24;
+    const uint32_t e = prmt(0x47544341u, 0xFF0D0AFFu, sel);        // A C T G | - \n \r -
+    dacc |= u ^ e;
+    const uint32_t t2 = t ^ (KSSD_SHR_CLS(t, 1) & 0x01010101u);
+    m = t2 * 0x40100401u;
 }
 
-// 16 bits, bit b = byte b of the lane's 16 bytes has bit 6 clear (natural order)
-__device__ __forceinline__ uint32_t skip_mask16(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3)
+// 8 bits from two t3 words (tOld = the older four bytes): bit (7 - b) = flag (t3 bit 2) of byte b of the eight,
+// i.e. reversed order, newest byte in bit 0.  The multiplier both gathers and reverses the flags.
+__device__ __forceinline__ uint32_t rev_flags8(uint32_t tOld, uint32_t tNew)
 {
-    const uint32_t g01 = (s0 >> 6) | (s1 >> 2);
-    const uint32_t g23 = (s2 >> 6) | (s3 >> 2);
-    return (((g01 * 0x00204081u) >> 21) & 0xffu) | (((g23 * 0x00204081u) >> 13) & 0xff00u);
+    const uint32_t g = ((tNew >> 2) | (tOld << 2)) & 0x11111111u;
+    return (g * 0x08040201u) >> 24;
 }
 
-// remove the 2-bit groups flagged in m (bit b = group of byte b, byte 0 in the top bits);
-// the survivors end up right-aligned
-__device__ __forceinline__ uint32_t squeeze_groups(uint32_t c, uint32_t m)
+// remove the 2-bit groups flagged in rsk (bit p = group at bits [2p, 2p+1]); survivors end up right-aligned.
+// First removal is branch-free (rsk == 0 leaves c untouched); further ones only if some lane of the warp needs them.
+__device__ __forceinline__ uint32_t squeeze_groups(uint32_t c, uint32_t rsk)
 {
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t low = (1u << (30 - 2 * b)) - 1u;
+    for (;;) {
+        const uint32_t iso = rsk & (0u - rsk);
+        const uint32_t low = iso * iso - 1u;
         c = ((c >> 2) & ~low) | (c & low);
+        rsk = (rsk ^ iso) >> 1;
+        if (!__any_sync(kFull, rsk != 0)) break;
     }
     return c;
 }
@@ -101,6 +130,14 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
 __device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d)
 {
     return ((uint64_t)__shfl_up_sync(kFull, (uint32_t)(v >> 32), d) << 32) | __shfl_up_sync(kFull, (uint32_t)v, d);
+}
+
+// (hi:lo) << s for s in [0, 32]: the three result words; clamp-mode funnel shifts make s == 32 exact
+__device__ __forceinline__ void shl96(uint32_t lo, uint32_t hi, uint32_t s, uint32_t &r0, uint32_t &r1, uint32_t &r2)
+{
+    r0 = __funnelshift_lc(0u, lo, s);
+    r1 = __funnelshift_lc(lo, hi, s);
+    r2 = __funnelshift_lc(hi, 0u, s);
 }
 
 // first '\n' at or after nominal-1, searched over at most span_bytes bytes; returns the offset just
@@ -122,6 +159,13 @@ __device__ __forceinline__ uint64_t find_span_start(const uint8_t *seq, uint64_t
         }
     }
     return kNoSpan;
+}
+
+// prefilter bit of a 20-bit index; bit order inside a word is reversed (bit 31 - (idx & 31)) so that a
+// left shift by the low index bits (funnel shift, wrap mode) brings the flag to bit 31
+__device__ __forceinline__ uint32_t pf_test_top(const uint32_t *__restrict__ pf, uint32_t idx)
+{
+    return __funnelshift_l(0u, pf[idx >> 5], idx);
 }
 
 // ---- exact resolution of queued candidates (dense: up to 32 at a time) ----
@@ -171,12 +215,12 @@ __device__ __forceinline__ void push_candidates(const SketchParams &P, const Sca
                                                 uint32_t lane_off, uint32_t vmask, uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
-    while (__any_sync(kFull, cand != 0)) {
+    uint32_t pm = __ballot_sync(kFull, cand != 0);
+    while (pm) {
         const bool has = cand != 0;
-        const int d = has ? (__ffs(cand) - 1) : 0;
-        cand &= cand - 1;
-        const uint32_t pm = __ballot_sync(kFull, has);
         if (has) {
+            const int d = __ffs(cand) - 1;
+            cand &= cand - 1;
             const uint32_t lo = __funnelshift_r(W0, W1, 2 * d);
             const uint32_t hi = __funnelshift_r(W1, W2, 2 * d);
             const uint64_t fwd = (((uint64_t)hi << 32) | lo) & P.tupmask;
@@ -195,10 +239,12 @@ __device__ __forceinline__ void push_candidates(const SketchParams &P, const Sca
             qn -= 32;
             __syncwarp();
         }
+        pm = __ballot_sync(kFull, cand != 0);
     }
 }
 
-__device__ __forceinline__ uint4 load_chunk16(const ScanArgs &A, uint64_t addr)
+// guarded 16-byte load for the first / last chunks of a buffer
+__device__ __forceinline__ uint4 load_chunk16_guarded(const ScanArgs &A, uint64_t addr)
 {
     if (addr + 16 <= A.seq_bytes) return ldg_stream(reinterpret_cast<const uint4 *>(A.seq + addr));
     uint32_t w[4] = {0x0d0d0d0du, 0x0d0d0d0du, 0x0d0d0d0du, 0x0d0d0d0du};
@@ -229,7 +275,7 @@ struct StreamState {
     uint32_t hdr;          // inside a '>' header line
 };
 
-// One span: [start, end) of genome [gs, ge); returns nothing, appends occurrences to the output.
+// One span: [start, end) of genome [gs, ge); appends occurrences to the output.
 __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q,
                           uint32_t gid, uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
 {
@@ -238,62 +284,94 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
     StreamState st = {0ull, 0u, 0u, 0u};
     uint32_t qn = 0;
     const uint64_t chunk0 = start & ~127ull;
-    const uint64_t ord_base = chunk0 - gs + 0;   // chunk0 >= gs - 127 can be below gs: handled by signed add below
-    uint64_t chunk = chunk0;
-    uint4 nxt = load_chunk16(A, chunk + 16 * lane);
+    const uint64_t ord_base = chunk0 - gs;           // may wrap below zero; real occurrences add back past it
+    // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
+    const uint64_t lim = end < ge ? end : ge;
+    const uint64_t full = (lim - chunk0) >> 9;       // iterations [0, full) end at or before lim
+    const uint32_t n_steady = full > 1 ? (uint32_t)(full - 1 < 0x7fffffffull ? full - 1 : 0x7fffffffull) : 0u;
+    const uint8_t *lp = A.seq + chunk0 + 16 * lane;  // this lane's 16 bytes of the current chunk
+    uint4 nxt = load_chunk16_guarded(A, chunk0 + 16 * lane);
+    bool at_eof = false;
 
-    for (;;) {
+    for (uint32_t it = 0;; it++) {
         uint4 cur = nxt;
-        const uint64_t cbase = chunk;
-        const uint64_t laddr = cbase + 16 * lane;
-        chunk += 512;
-        if (chunk < ge) nxt = load_chunk16(A, chunk + 16 * lane);
-        if (cbase < start || cbase + 512 > ge)
-            mask_lane_bytes(cur, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
+        const bool steady = (it - 1u) < n_steady;
+        const uint64_t cbase = chunk0 + ((uint64_t)it << 9);
+        const uint32_t lane_off = (it << 9) + 16 * lane;
+        // prefetch the next chunk: unguarded while the next iteration is steady too
+        if (it < n_steady) nxt = ldg_stream(reinterpret_cast<const uint4 *>(lp + 512));
+        else if (cbase + 512 < ge) nxt = load_chunk16_guarded(A, cbase + 512 + 16 * lane);
+        lp += 512;
 
-        uint32_t d0, d1, d2, d3, s0, s1, s2, s3, p0, p1, p2, p3;
-        classify4(cur.x, d0, s0, p0);
-        classify4(cur.y, d1, s1, p1);
-        classify4(cur.z, d2, s2, p2);
-        classify4(cur.w, d3, s3, p3);
-        const uint32_t codes = (p0 << 24) | (p1 << 16) | (p2 << 8) | p3;   // byte 0 in the top two bits
-        const bool dirty = (d0 | d1 | d2 | d3) != 0;
-        const uint32_t skm = skip_mask16(s0, s1, s2, s3);
-        uint32_t n = 16 - __popc(skm);
-        const bool past_end = cbase + 512 > end;
-        const uint32_t lane_off = (uint32_t)(cbase - chunk0) + 16 * lane;
+        bool past_end = false, cut_lane = false;
+        if (!steady) {
+            const uint64_t laddr = cbase + 16 * lane;
+            if (cbase < start || cbase + 512 > ge)
+                mask_lane_bytes(cur, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
+            past_end = cbase + 512 > end;
+            cut_lane = laddr < start || laddr + 16 > ge;     // text itself is cut here: a short lane is not a defect
+        }
 
-        // a lane may be short of bases only where the text itself is cut (before `start`, after the genome end)
-        const bool lane_ok = !dirty && (n >= (uint32_t)P.hist_min_n || laddr < start || laddr + 16 > ge);
+        uint32_t dacc = 0, t0, t1, t2, t3w, m0, m1, m2, m3;
+        classify4(cur.x, dacc, t0, m0);
+        classify4(cur.y, dacc, t1, m1);
+        classify4(cur.z, dacc, t2, m2);
+        classify4(cur.w, dacc, t3w, m3);
+        const uint32_t codes = prmt(prmt(m3, m2, 0x0073u), prmt(m1, m0, 0x0073u), 0x5410u);   // byte 0 in the top two bits
+        const uint32_t rsk = (rev_flags8(t0, t1) << 8) | rev_flags8(t2, t3w);                 // bit 15-b: byte b has bit 6 clear
+        uint32_t n = 16 - __popc(rsk);
+        const bool lane_ok = dacc == 0 && (n >= (uint32_t)P.hist_min_n || cut_lane);
         const bool clean = __all_sync(kFull, lane_ok) && !st.hdr;
         uint32_t cand = 0, W0, W1, W2, vmask = 0;
 
         if (clean) {
             // ---------------- clean iteration: only bases and line ends, no header pending ----------------
-            const uint32_t Pl = squeeze_groups(codes, skm);
+            const uint32_t Pl = squeeze_groups(codes, rsk);
             const uint32_t A1 = __shfl_up_sync(kFull, Pl, 1);
             const uint32_t B2 = __shfl_up_sync(kFull, Pl, 2);
             const uint32_t nA = __shfl_up_sync(kFull, n, 1);
-            uint64_t H;
-            if (lane == 0) H = st.cw;
-            else {
-                const uint64_t older = lane >= 2 ? (uint64_t)B2 : st.cw;
-                H = (nA >= 16 ? (older << 32) : (older << (2 * nA))) | A1;
+            // H = history before this lane = (lane-2's bases : lane-1's bases), the warp carry for lanes 0/1
+            uint32_t H0, H1;
+            {
+                const uint32_t o0 = lane >= 2 ? B2 : (uint32_t)st.cw;
+                const uint32_t o1 = lane >= 2 ? 0u : (uint32_t)(st.cw >> 32);
+                const uint32_t s = 2 * nA;
+                H0 = __funnelshift_lc(0u, o0, s) | A1;
+                H1 = __funnelshift_lc(o0, o1, s);
+                if (lane == 0) { H0 = (uint32_t)st.cw; H1 = (uint32_t)(st.cw >> 32); }
             }
-            // W = (H << 2n) | Pl, 96 bits
-            const uint64_t x0 = (n >= 16) ? ((uint64_t)(uint32_t)H << 32) : ((uint64_t)(uint32_t)H << (2 * n));
-            const uint64_t x1 = (n >= 16) ? ((uint64_t)(uint32_t)(H >> 32) << 32) : ((uint64_t)(uint32_t)(H >> 32) << (2 * n));
-            W0 = (uint32_t)x0 | Pl;
-            W1 = (uint32_t)(x0 >> 32) | (uint32_t)x1;
-            W2 = (uint32_t)(x1 >> 32);
-            // prefilter on the central 2s-mer of the k-mer ending at each own base
+            shl96(H0, H1, 2 * n, W0, W1, W2);
+            W0 |= Pl;
+            // prefilter on the central 2s-mer of the k-mer ending at each own base (d = distance from the newest)
             const uint32_t Xlo = __funnelshift_r(W0, W1, 2 * P.out);
             const uint32_t Xhi = __funnelshift_r(W1, W2, 2 * P.out);
+#if KSSD_MULHI_T
+            // every 20-bit window lies inside one of three 32-bit views of X, so the per-window shift can be a
+            // mul.hi by a power of two (FMA pipe) instead of a funnel shift (ALU pipe)
+            const uint32_t X1 = __funnelshift_r(Xlo, Xhi, 12);
+            const uint32_t X2 = __funnelshift_r(Xlo, Xhi, 24);
+#endif
 #pragma unroll
-            for (int d = 0; d < 16; d++) {
-                const uint32_t tmp = __funnelshift_r(Xlo, Xhi, 2 * d) & P.pfmask;
-                const uint32_t word = pf[tmp >> 5];
-                cand |= ((word >> (tmp & 31)) & 1u) << d;
+            for (int d = 15; d >= 0; d--) {
+#if KSSD_MULHI_T
+                const uint32_t view = d < 6 ? Xlo : (d < 12 ? X1 : X2);
+                const int off = d < 6 ? 2 * d : (d < 12 ? 2 * d - 12 : 2 * d - 24);
+                const uint32_t t = off ? __umulhi(view, 1u << (32 - off)) : view;
+#else
+                const uint32_t t = __funnelshift_r(Xlo, Xhi, 2 * d);
+#endif
+                // byte offset of the bitmap word: (t >> 3) & amask
+#if KSSD_MULHI_ADDR
+                const uint32_t boff = __umulhi(t, 0x20000000u) & P.pf_amask;
+#else
+                const uint32_t boff = (t >> 3) & P.pf_amask;
+#endif
+                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + boff);
+#if KSSD_MULHI_ACC
+                cand = cand * 2u + __umulhi(__funnelshift_l(0u, word, t), 2u);      // cand = cand << 1 | flag
+#else
+                cand = __funnelshift_l(__funnelshift_l(0u, word, t), cand, 1);      // cand = cand << 1 | flag
+#endif
             }
             cand &= (1u << n) - 1u;
 
@@ -313,20 +391,20 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
                     const int keep = (int)n - need;                   // d <= keep-1
                     cand &= keep <= 0 ? 0u : ((1u << keep) - 1u);
                 }
-                uint32_t E = N;                                      // valid bases of this iteration before `end`
                 if (past_end) {
-                    // lane holding `end` (or lane 0 when the whole iteration is past it)
+                    uint32_t E;                                      // valid bases of this iteration before `end`
                     const int64_t rel = (int64_t)end - (int64_t)cbase;
                     if (rel <= 0) E = 0;
                     else {
                         const int le = (int)(rel >> 4);
                         const int be = (int)(rel & 15);
-                        const uint32_t before = (uint32_t)o_l + (uint32_t)__popc(~skm & ((1u << be) - 1u));
+                        // bytes [0,be) of the lane <-> bits 15 .. 16-be of rsk
+                        const uint32_t before = (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(rsk >> (16 - be));
                         E = __shfl_sync(kFull, before, le);
                     }
                     // ok2: after_end + (t_local - E + 1) <= TL-1   for t_local >= E
-                    const int lim = TL - 2 - (int)st.after_end + (int)E - o_l;   // n-1-d <= lim
-                    const int drop = (int)n - 1 - lim;                            // d >= drop
+                    const int lim2 = TL - 2 - (int)st.after_end + (int)E - o_l;   // n-1-d <= lim2
+                    const int drop = (int)n - 1 - lim2;                           // d >= drop
                     if (drop > 0) cand &= drop >= 16 ? 0u : ~((1u << drop) - 1u);
                     st.after_end += N - E;
                 }
@@ -335,10 +413,11 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
             // carry: the last two lanes hold at least TL-1 bases
             const uint32_t P30 = __shfl_sync(kFull, Pl, 30), P31 = __shfl_sync(kFull, Pl, 31);
             const uint32_t n31 = __shfl_sync(kFull, n, 31);
-            st.cw = (n31 >= 16 ? ((uint64_t)P30 << 32) : ((uint64_t)P30 << (2 * n31))) | P31;
+            st.cw = ((uint64_t)P30 << (2 * n31)) | P31;
         } else {
             // ---------------- general iteration: headers, N, IUPAC, anything ----------------
             const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+            const uint64_t laddr = cbase + 16 * lane;
             uint32_t V = 0, NLm = 0, CRm = 0, GTm = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -423,16 +502,12 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
                     j++;
                     if (run >= (uint32_t)TL && ae <= (uint32_t)(TL - 1)) {
                         const uint32_t tmp = (uint32_t)(fwd >> (2 * P.out)) & P.pfmask;
-                        if ((pf[tmp >> 5] >> (tmp & 31)) & 1u) cand |= 1u << (n - j);
+                        if (pf_test_top(pf, tmp) >> 31) cand |= 1u << (n - j);
                     }
                 } else if ((BRK >> i) & 1u) run = 0;
             }
-            // W = (hist << 2n) | Pl
-            const uint64_t x0 = (n >= 16) ? ((uint64_t)(uint32_t)hist << 32) : ((uint64_t)(uint32_t)hist << (2 * n));
-            const uint64_t x1 = (n >= 16) ? ((uint64_t)(uint32_t)(hist >> 32) << 32) : ((uint64_t)(uint32_t)(hist >> 32) << (2 * n));
-            W0 = (uint32_t)x0 | Pl;
-            W1 = (uint32_t)(x0 >> 32) | (uint32_t)x1;
-            W2 = (uint32_t)(x1 >> 32);
+            shl96((uint32_t)hist, (uint32_t)(hist >> 32), 2 * n, W0, W1, W2);
+            W0 |= Pl;
             // warp carry = inclusive value of lane 31 on top of the old carry
             const uint64_t sb31 = shfl64(sb, 31);
             const uint32_t sn31 = __shfl_sync(kFull, sn, 31), sbrk31 = __shfl_sync(kFull, sbrk, 31);
@@ -443,13 +518,15 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
 
         push_candidates(P, A, q, qn, cand, n, W0, W1, W2, lane_off, vmask, gid, ord_base);
 
-        if (cbase + 512 >= ge) break;                       // genome exhausted
-        if (cbase + 512 >= end) {                           // run-out: stop when no owned k-mer can still end
-            if (st.after_end >= (uint32_t)(TL - 1) || st.since_break <= st.after_end) break;
+        if (!steady) {
+            if (cbase + 512 >= ge) { at_eof = true; break; }    // genome exhausted
+            if (cbase + 512 >= end) {                           // run-out: stop when no owned k-mer can still end
+                if (st.after_end >= (uint32_t)(TL - 1) || st.since_break <= st.after_end) break;
+            }
         }
     }
     if (qn) { resolve_candidates(P, A, q, 0, qn, gid, ord_base); __syncwarp(); }
-    if (st.hdr && chunk >= ge && lane == 0) atomicOr(&A.gstatus[gid], 1);
+    if (st.hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
 }
 
 __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta_kernel(const SketchParams P, const ScanArgs A)
