@@ -35,6 +35,8 @@ extern "C" {
 #define KSSD_E_MISMATCH (-6)   /* query args not match ref args          (command_dist.c:701-706) */
 #define KSSD_E_NOMEM (-7)
 #define KSSD_E_NNEIGH (-8)     /* neighborN_max > NREF or > ref_num      (command_dist.c:1196-98) */
+#define KSSD_E_LONGLINE (-9)   /* a FASTQ line exceeds the reference's fgets buffer (iseq2comem.c:274,553):
+                                  the reference mis-frames every later record; not imitated                */
 
 const char *kssd_last_error(void);
 const char *kssd_version(void);

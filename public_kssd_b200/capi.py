@@ -31,7 +31,7 @@ SYMBOLS = [
 MODE_FASTA, MODE_FASTA_UNIQ, MODE_FASTQ, MODE_FASTQ_ABUND = 0, 1, 2, 3
 METRIC_JACCARD, METRIC_CONTAINMENT = 0, 1
 
-E_CROWD, E_HEADER_EOF = -4, -5
+E_CROWD, E_HEADER_EOF, E_LONGLINE = -4, -5, -9
 
 
 class KssdError(RuntimeError):

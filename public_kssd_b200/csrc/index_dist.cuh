@@ -155,6 +155,14 @@ __device__ __forceinline__ double get_matric(int metric_kind, double y)
     return metric_kind == 0 ? 1.0 / (2.0 * y) + 0.5 : 1.0 / y;
 }
 
+// (unsigned int)rs as gcc/x86-64 evaluates it at command_dist.c:1269 (cvttsd2si to 64 bits, low half kept):
+// NaN and out-of-range doubles give 0x8000000000000000 -> 0
+__device__ __forceinline__ uint32_t x86_double_to_u32(double v)
+{
+    if (!(fabs(v) < 9223372036854775808.0)) return 0u;
+    return (uint32_t)(unsigned long long)(long long)v;
+}
+
 // returns false when the row is suppressed
 __device__ __forceinline__ bool stat_row(const StatParams &S, uint32_t X, uint32_t Y, uint32_t I, StatRow &r)
 {
@@ -175,7 +183,7 @@ __device__ __forceinline__ bool stat_row(const StatParams &S, uint32_t X, uint32
     const double sd = sqrt(m * (1.0 - m) / (double)tmp);
     const double pv = 0.5 * erfc(m / sd * 0.70710678118654757);   // pow(0.5,0.5) rounded to double
     const double c1 = m - 1.96 * sd, c2 = m + 1.96 * sd;
-    r.shared = I; r.rs_u = (uint32_t)rs; r.ref_size = X; r.qry_size = Y;
+    r.shared = I; r.rs_u = x86_double_to_u32(rs); r.ref_size = X; r.qry_size = Y;
     r.metric = m; r.dist = dist; r.pvalue = pv; r.fdr = pv * S.cmprsn_num;
     r.ci_m_lo = c1; r.ci_m_hi = c2;
     r.ci_d_lo = log(get_matric(S.metric, c2)) / (double)S.kmerlen;

@@ -16,6 +16,7 @@
 
 #include "../../include/kssd_b200.h"
 #include "index_dist.cuh"
+#include "sketch_fastq.cuh"
 #include "sketch_scan.cuh"
 
 using namespace kssd;
@@ -302,13 +303,66 @@ __global__ void sketch_total_kernel(const uint32_t *__restrict__ flags, const ui
     *slot = pos[n - 1] + flags[n - 1];
 }
 
+// FASTQ: per genome, index the lines (two streaming passes + a scan), then one thread per record
+static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, const uint64_t *glen, int n_genomes, int mode, int Q,
+                     const ScanArgs &A)
+{
+    const SketchParams &P = c->P;
+    CU(cudaFuncSetAttribute(sketch_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPfWords * 4)));
+    for (int g = 0; g < n_genomes; g++) {
+        const uint64_t gs = goff[g], ge = gs + glen[g];
+        if (ge == gs) continue;
+        const uint64_t a0 = gs & ~15ull;
+        const uint64_t nblk = (ge - a0 + kNlBytesPerBlock - 1) / kNlBytesPerBlock;
+        if (nblk > 0x7fffffffull) return fail(KSSD_E_INVAL, "kssd_sketch_batch: FASTQ text of genome %d too large", g);
+        CU(c->flags.ensure(nblk * 4));
+        CU(c->pos.ensure(nblk * 4));
+        nl_count_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->flags.as<uint32_t>());
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream));
+        LAUNCHED(3);
+        uint32_t lastoff = 0, lastcnt = 0;
+        uint8_t lastbyte = 0;
+        CU(cudaMemcpyAsync(&lastoff, c->pos.as<uint32_t>() + (nblk - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&lastcnt, c->flags.as<uint32_t>() + (nblk - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&lastbyte, d_seq + ge - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const uint64_t n_nl = (uint64_t)lastoff + lastcnt;
+        CU(c->minord.ensure(std::max<uint64_t>(n_nl, 1) * 8));
+        nl_fill_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->pos.as<uint32_t>(), c->minord.as<uint64_t>());
+        LAUNCHED(1);
+        FastqArgs F{};
+        F.seq = d_seq; F.gs = gs; F.ge = ge;
+        F.nlpos = c->minord.as<uint64_t>();
+        F.n_nl = n_nl;
+        F.n_lines = n_nl + (lastbyte != '\n' ? 1 : 0);
+        F.n_records = (F.n_lines + 3) / 4;
+        F.gid = (uint32_t)g;
+        F.abund = mode == KSSD_MODE_FASTQ_ABUND;
+        F.Q = Q;
+        F.line_cap = F.abund ? 4094u : 19998u;     // fgets(…, 4096 / 20000, …) keeps len+1 <= cap-1 in one piece
+        F.out_keys = A.out_keys; F.out_ords = A.out_ords; F.out_cap = A.out_cap; F.out_count = A.out_count; F.gstatus = A.gstatus;
+        if (F.n_records) {
+            const uint64_t want = (F.n_records + kFastqThreads - 1) / kFastqThreads;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)c->sm_count);
+            sketch_fastq_kernel<<<grid, kFastqThreads, kPfWords * 4, c->stream>>>(P, F);
+            LAUNCHED(1);
+        }
+    }
+    return KSSD_OK;
+}
+
 static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const uint64_t *goff, const uint64_t *glen, int n_genomes,
                       const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
 {
     const SketchParams &P = c->P;
     const int mode = opts ? opts->mode : KSSD_MODE_FASTA;
-    if (mode != KSSD_MODE_FASTA && mode != KSSD_MODE_FASTA_UNIQ)
-        return fail(KSSD_E_INVAL, "kssd_sketch_batch: mode %d is not available in this build (FASTA modes only)", mode);
+    if (mode < KSSD_MODE_FASTA || mode > KSSD_MODE_FASTQ_ABUND) return fail(KSSD_E_INVAL, "kssd_sketch_batch: unknown mode %d", mode);
+    const bool is_fastq = mode == KSSD_MODE_FASTQ || mode == KSSD_MODE_FASTQ_ABUND;
+    if (mode == KSSD_MODE_FASTQ && opts && (opts->M < 1 || opts->M >= 15))
+        return fail(KSSD_E_INVAL, "fastq2co(): Occurence num should smaller than 15");   // iseq2comem.c:279
     if (n_genomes <= 0 || n_genomes >= (1 << 28)) return fail(KSSD_E_INVAL, "kssd_sketch_batch: n_genomes=%d", n_genomes);
     uint64_t total = 0;
     for (int g = 0; g < n_genomes; g++) {
@@ -368,12 +422,17 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         A.out_count = reinterpret_cast<uint32_t *>(mb + m_cnt);
         A.out_keys = c->keys.as<uint64_t>(); A.out_ords = c->ords.as<uint64_t>();
         A.out_cap = (uint32_t)cap;
-        A.drop_zero = 1;
+        A.drop_zero = is_fastq ? 0 : 1;
         CU(cudaMemsetAsync(mb + m_tick, 0, 8, c->stream));
         CU(cudaEventRecord(c->ev[0], c->stream));
-        if (n_spans) {
-            sketch_fasta_kernel<<<c->sm_count, kScanThreads, kPfWords * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
-            LAUNCHED(1);
+        if (!is_fastq) {
+            if (n_spans) {
+                sketch_fasta_kernel<<<c->sm_count, kScanThreads, kPfWords * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
+                LAUNCHED(1);
+            }
+        } else {
+            int rc = fastq_run(c, d_seq, goff, glen, n_genomes, mode, opts ? opts->Q : 0, A);
+            if (rc) { delete S; return rc; }
         }
         CU(cudaEventRecord(c->ev[1], c->stream));
         CU(cudaMemcpyAsync(&n_occ, mb + m_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -457,7 +516,8 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     S->comp_start[n_comp] = run;
     for (int g = 0; g < n_genomes; g++) {
         if (S->status[g] & 1) S->status[g] = KSSD_E_HEADER_EOF;
-        else if (per_genome[g] > c->info.hashlimit) S->status[g] = KSSD_E_CROWD;
+        else if (S->status[g] & 2) S->status[g] = KSSD_E_LONGLINE;
+        else if (mode != KSSD_MODE_FASTQ && per_genome[g] > c->info.hashlimit) S->status[g] = KSSD_E_CROWD;   // fastq2co never counts keys (iseq2comem.c:338)
         else S->status[g] = 0;
     }
     CU(cudaMemcpyAsync(S->d_index, S->index.data(), S->index.size() * 8, cudaMemcpyHostToDevice, c->stream));

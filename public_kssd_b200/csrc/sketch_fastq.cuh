@@ -1,0 +1,193 @@
+// sketch_fastq.cuh -- Stage I for FASTQ text: fastq2co (reference iseq2comem.c:277-356) and the abundance
+// variant mt_shortreads2koc (iseq2comem.c:554-615).
+//
+// Record semantics reproduced (oracle/kssd_oracle.c):
+//   * the file is cut in lines at '\n' (fgets); record i = lines 4i..4i+3, bases come from line 4i+1,
+//     qualities from line 4i+3; every record starts a fresh run (base = 1);
+//   * fastq2co: a base counts iff it is ACGTacgt AND (signed char)qual[pos] >= Q (raw ASCII, no -33); anything
+//     else breaks the run; record 0 is always processed, record i >= 1 only if its four lines are all
+//     newline-terminated (the reference notices EOF while reading the record and stops: "last record is dropped
+//     when the file has no trailing newline"); code 0 is kept;
+//   * mt_shortreads2koc: quality ignored, a record is processed iff its four lines exist (the last may be
+//     unterminated), occurrence counts saturate at 65535 (done in rle_kernel).
+// Lines that do not fit the reference's fgets buffers (20000 / 4096 bytes) make the reference mis-frame records;
+// such genomes are flagged (status bit 1) instead of imitated.
+//
+// B200 mapping: a line index (positions of every '\n', two streaming passes at HBM speed) turns the text into
+// independent records; one THREAD walks one read with a rolling forward 2k-mer, 16-byte aligned loads, and the
+// same shared-memory prefilter / exact sampled-set lookup as the FASTA kernel.  Reads are short, so there is no
+// cross-thread state at all.
+#pragma once
+#include "kssd_device.cuh"
+
+namespace kssd {
+
+constexpr int kNlBlock = 256;            // threads per block of the line-index passes
+constexpr int kNlBytesPerBlock = kNlBlock * 16;
+
+__device__ __forceinline__ uint32_t nl_mask16(const uint8_t *seq, uint64_t a, uint64_t gs, uint64_t ge)
+{
+    // bit i = byte a+i is '\n' and lies inside [gs, ge); a is 16-byte aligned
+    if (a + 16 <= gs || a >= ge) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(seq + a));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        m |= (uint32_t)(b == '\n') << i;
+    }
+    if (a < gs) m &= ~((1u << (gs - a)) - 1u);
+    if (a + 16 > ge) m &= (1u << (ge - a)) - 1u;
+    return m;
+}
+
+__global__ void __launch_bounds__(kNlBlock) nl_count_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0,
+                                                             uint32_t *__restrict__ block_counts)
+{
+    const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + 16ull * threadIdx.x;
+    uint32_t c = __popc(nl_mask16(seq, a, gs, ge));
+    c = __reduce_add_sync(kFull, c);
+    __shared__ uint32_t red[kNlBlock / 32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < kNlBlock / 32; i++) s += red[i];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0,
+                                                            const uint32_t *__restrict__ block_offsets, uint64_t *__restrict__ nlpos)
+{
+    const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + 16ull * threadIdx.x;
+    uint32_t m = nl_mask16(seq, a, gs, ge);
+    const uint32_t c = __popc(m);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    __shared__ uint32_t wsum[kNlBlock / 32];
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t base = block_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < wid; w++) base += wsum[w];
+    uint32_t o = base + incl - c;
+    while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        nlpos[o++] = a + i;
+    }
+}
+
+struct FastqArgs {
+    const uint8_t *seq;
+    uint64_t gs, ge;             // genome extent
+    const uint64_t *nlpos;       // positions of the newline-terminated lines' '\n' (ascending)
+    uint64_t n_nl;               // newline-terminated lines
+    uint64_t n_lines;            // n_nl + 1 if an unterminated tail line exists
+    uint64_t n_records;          // ceil(n_lines / 4)
+    uint32_t gid;
+    int abund;                   // 0 = fastq2co rules, 1 = mt_shortreads2koc rules
+    int Q;
+    uint32_t line_cap;           // 19999 / 4095: longest line the reference's fgets keeps in one piece
+    uint64_t *out_keys;
+    uint64_t *out_ords;
+    uint32_t out_cap;
+    uint32_t *out_count;
+    int32_t *gstatus;
+};
+
+__device__ __forceinline__ uint32_t byte_at(const uint8_t *seq, uint64_t p, uint64_t &chunk_addr, uint4 &chunk)
+{
+    const uint64_t a = p & ~15ull;
+    if (a != chunk_addr) { chunk = __ldg(reinterpret_cast<const uint4 *>(seq + a)); chunk_addr = a; }
+    const uint32_t i = (uint32_t)(p - a);
+    const uint32_t w = i < 8 ? (i < 4 ? chunk.x : chunk.y) : (i < 12 ? chunk.z : chunk.w);
+    return (w >> (8 * (i & 3))) & 0xffu;
+}
+
+constexpr int kFastqThreads = 1024;
+
+__global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const SketchParams P, const FastqArgs A)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
+        uint4 *dst = reinterpret_cast<uint4 *>(pf);
+        for (uint32_t i = threadIdx.x; i < kPfWords / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
+    }
+    __syncthreads();
+    const int TL = P.TL;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.n_records; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t l_seq = 4 * r + 1, l_q = 4 * r + 3;
+        if (l_seq >= A.n_lines) continue;                                  // no sequence line at all
+        bool process;
+        if (A.abund) process = 4 * r + 4 <= A.n_lines;                     // four lines exist (iseq2comem.c:567)
+        else process = (r == 0) || (4 * r + 4 <= A.n_nl);                  // read without touching EOF (:300-307)
+        if (!process) continue;
+        const uint64_t s0 = A.nlpos[l_seq - 1] + 1;                        // l_seq >= 1: previous line is terminated
+        const uint64_t s1 = l_seq < A.n_nl ? A.nlpos[l_seq] : A.ge;        // end of bases ('\n' position or text end)
+        uint64_t q0 = 0, qlen = 0;                                          // quality line incl. its '\n'
+        if (l_q < A.n_lines) {
+            q0 = A.nlpos[l_q - 1] + 1;
+            qlen = l_q < A.n_nl ? A.nlpos[l_q] + 1 - q0 : A.ge - q0;
+        }
+        {   // every line of the record must fit the reference's fgets buffer, or its framing (and ours) is off
+            const uint64_t h0 = r == 0 ? A.gs : A.nlpos[4 * r - 1] + 1;
+            const uint64_t hlen = A.nlpos[4 * r] - h0;
+            const uint64_t plen = (l_seq + 1 < A.n_nl) ? A.nlpos[l_seq + 1] - (A.nlpos[l_seq] + 1) : 0;
+            if (s1 - s0 > A.line_cap || hlen > A.line_cap || plen > A.line_cap || qlen > (uint64_t)A.line_cap + 1) {
+                atomicOr(&A.gstatus[A.gid], 2);
+                continue;
+            }
+        }
+        uint64_t fwd = 0, ca = ~0ull, qa = ~0ull;
+        uint4 cc = make_uint4(0, 0, 0, 0), qc = make_uint4(0, 0, 0, 0);
+        uint32_t run = 0;
+        const bool use_q = !A.abund && A.Q > -128;
+        for (uint64_t p = s0; p < s1; p++) {
+            const uint32_t b = byte_at(A.seq, p, ca, cc);
+            const uint32_t l = b | 0x20u;
+            bool ok = (l == 'a' || l == 'c' || l == 'g' || l == 't');
+            if (ok && use_q) {
+                const uint64_t off = p - s0;
+                const int q = off < qlen ? (int)(int8_t)byte_at(A.seq, q0 + off, qa, qc) : 0;
+                ok = q >= A.Q;
+            }
+            if (!ok) { run = 0; continue; }
+            const uint32_t t = (b >> 1) & 3u;
+            fwd = (fwd << 2) | (t ^ (t >> 1));
+            if (++run < (uint32_t)TL) continue;
+            const uint32_t idx = (uint32_t)(fwd >> (2 * P.out)) & P.pfmask;
+            if (!((pf[idx >> 5] << (idx & 31)) >> 31)) continue;
+            // exact resolution (rare)
+            const uint64_t kmer = fwd & P.tupmask;
+            const uint64_t rc = revcomp2(kmer, TL);
+            const uint64_t u = kmer < rc ? kmer : rc;
+            const uint32_t inner = (uint32_t)(u >> (2 * P.out)) & P.innermask;
+            uint32_t h = mix32(inner) & P.ht_mask, pfv = 0;
+            bool found = false;
+            for (;;) {
+                const uint2 e = __ldg(&P.ht[h]);
+                if (e.x == inner) { found = true; pfv = e.y; break; }
+                if (e.x == kHtEmpty) break;
+                h = (h + 1) & P.ht_mask;
+            }
+            if (!found) continue;
+            const uint64_t dr = (((u & P.undomask) + ((u & P.outmask) << (4 * P.s))) >> (4 * P.L)) + pfv;
+            const uint32_t o = atomicAdd(A.out_count, 1u);
+            if (o < A.out_cap) {
+                A.out_keys[o] = ((dr & P.comp_mask) << 56) | ((uint64_t)A.gid << 28) | (dr >> P.comp_code_bits);
+                A.out_ords[o] = p - A.gs;
+            }
+        }
+    }
+}
+
+}  // namespace kssd

@@ -161,6 +161,15 @@ class Context:
             lib().kssd_sketch_free(h)
         return Sketch(ids, index, abund, ordl, status, int(nocc.value), float(ms.value), total_ms)
 
+    def _raise_status(self, sk: Sketch):
+        for g, s in enumerate(sk.status):
+            if s == capi.E_CROWD:
+                raise KssdError(s, f"the context space is too crowd, try rerun the program using -k{self.k + 1} (genome {g})")
+            if s == capi.E_HEADER_EOF:
+                raise KssdError(s, f"fasta2co(): can not find seqences head start from '>' (genome {g})")
+            if s == capi.E_LONGLINE:
+                raise KssdError(s, f"FASTQ line longer than the reference's fgets buffer (genome {g})")
+
     def sketch(self, genomes: Sequence[bytes | np.ndarray], uniq: bool = False, span_bytes: int = 0, strict: bool = True) -> Sketch:
         """fasta2co / uniq_fasta2co + writer for each genome of the batch (host buffers in, host arrays out).
         strict: raise where the reference would have exited (crowded context space, header at EOF)."""
@@ -168,11 +177,16 @@ class Context:
         h = self.sketch_raw(buf, buf.size, goff, glen, capi.MODE_FASTA_UNIQ if uniq else capi.MODE_FASTA, span_bytes=span_bytes)
         sk = self.fetch_sketch(h, len(genomes))
         if strict:
-            for g, s in enumerate(sk.status):
-                if s == capi.E_CROWD:
-                    raise KssdError(s, f"the context space is too crowd, try rerun the program using -k{self.k + 1} (genome {g})")
-                if s == capi.E_HEADER_EOF:
-                    raise KssdError(s, f"fasta2co(): can not find seqences head start from '>' (genome {g})")
+            self._raise_status(sk)
+        return sk
+
+    def sketch_fastq(self, files: Sequence[bytes | np.ndarray], Q: int = 0, M: int = 1, abundance: bool = False, strict: bool = True) -> Sketch:
+        """fastq2co(Q, M) + write_fqco2file, or with abundance=True mt_shortreads2koc + write_fqkoc2files (-A)."""
+        buf, goff, glen = pack_genomes(files)
+        h = self.sketch_raw(buf, buf.size, goff, glen, capi.MODE_FASTQ_ABUND if abundance else capi.MODE_FASTQ, Q=Q, M=M)
+        sk = self.fetch_sketch(h, len(files), want_abund=abundance)
+        if strict:
+            self._raise_status(sk)
         return sk
 
     # ---------------- Stage II ----------------
