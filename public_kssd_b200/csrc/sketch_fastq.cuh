@@ -1,7 +1,7 @@
 // sketch_fastq.cuh -- Stage I for FASTQ text: fastq2co (reference iseq2comem.c:277-356) and the abundance
 // variant mt_shortreads2koc (iseq2comem.c:554-615).
 //
-// Record semantics reproduced (oracle/kssd_oracle.c):
+// Record semantics reproduced:
 //   * the file is cut in lines at '\n' (fgets); record i = lines 4i..4i+3, bases come from line 4i+1,
 //     qualities from line 4i+3; every record starts a fresh run (base = 1);
 //   * fastq2co: a base counts iff it is ACGTacgt AND (signed char)qual[pos] >= Q (raw ASCII, no -33); anything
