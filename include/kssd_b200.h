@@ -152,6 +152,11 @@ typedef struct kssd_dist kssd_dist_t; /* a Q x R job: accumulates over component
 /* ref_ctx_ct / qry_ctx_ct: per-genome sketch sizes (cofiles.stat / mcofiles.stat ctx_ct lists) */
 int kssd_dist_create(kssd_ctx_t *ctx, int n_qry, int n_ref, const uint32_t *qry_ctx_ct,
                      const uint32_t *ref_ctx_ct, kssd_dist_t **out);
+/* Same, but the Q x R uint32 count matrix lives in CALLER-owned device memory (e.g. a buffer that takes part in
+ * an NCCL reduce-scatter when the reference index is sharded by code range across GPUs).  already_filled != 0:
+ * the buffer already holds counts (statistics only / further components accumulate on top). */
+int kssd_dist_create_ext(kssd_ctx_t *ctx, int n_qry, int n_ref, const uint32_t *qry_ctx_ct,
+                         const uint32_t *ref_ctx_ct, uint32_t *ct_dev, int already_filled, kssd_dist_t **out);
 /* add one component: ct[q][r] += |{codes of q} n postings| (command_dist.c:779-784).
  * Query sketch given as combco.<c>/combco.index.<c> content. */
 int kssd_dist_accumulate_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes,
@@ -172,6 +177,8 @@ typedef struct kssd_stat_opts {
     double dthreshold;   /* -D: rows with dist > dthreshold are suppressed                       */
     int32_t n_neighbors; /* -N: 0 = all refs, else best N per query by raw metric                */
     int32_t skip_zero;   /* extension: 1 = also suppress rows with shared == 0                   */
+    uint64_t cmprsn_num; /* 0 = (uint32)(ref_num*qry_num) as at command_dist.c:1186; else this value
+                            (a rank that owns a block of query rows passes the whole job's number)  */
 } kssd_stat_opts_t;
 
 /* one output row; the doubles are exactly the values output_ctrl formats with %lf / %E */

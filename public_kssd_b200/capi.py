@@ -24,7 +24,7 @@ SYMBOLS = [
     "kssd_sketch_dev_ptrs", "kssd_sketch_stats", "kssd_sketch_free",
     "kssd_index_build_host", "kssd_index_build_dev", "kssd_index_sizes", "kssd_index_fetch", "kssd_index_fetch_dense",
     "kssd_index_from_dense_host", "kssd_index_free",
-    "kssd_dist_create", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
+    "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
     "kssd_dist_counts_dev", "kssd_dist_stats", "kssd_dist_fetch_stats", "kssd_dist_free",
 ]
 
@@ -54,7 +54,7 @@ class SketchOpts(C.Structure):
 
 class StatOpts(C.Structure):
     _fields_ = [("metric", C.c_int32), ("correction", C.c_int32), ("kmerlen", C.c_int32), ("dim_rd_len", C.c_int32),
-                ("dthreshold", C.c_double), ("n_neighbors", C.c_int32), ("skip_zero", C.c_int32)]
+                ("dthreshold", C.c_double), ("n_neighbors", C.c_int32), ("skip_zero", C.c_int32), ("cmprsn_num", C.c_uint64)]
 
 
 STAT_ROW_DTYPE = np.dtype([("qry", "<u4"), ("ref", "<u4"), ("shared", "<u4"), ("rs_u", "<u4"), ("ref_size", "<u4"),
@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
     L.kssd_index_free.argtypes = [vp]
     L.kssd_index_free.restype = None
     L.kssd_dist_create.argtypes = [vp, C.c_int, C.c_int, u32p, u32p, C.POINTER(vp)]
+    L.kssd_dist_create_ext.argtypes = [vp, C.c_int, C.c_int, u32p, u32p, vp, C.c_int, C.POINTER(vp)]
     L.kssd_dist_accumulate_host.argtypes = [vp, vp, u32p, u64p]
     L.kssd_dist_accumulate_dev.argtypes = [vp, vp, vp, vp, C.c_uint64]
     L.kssd_dist_fetch_counts.argtypes = [vp, u32p]

@@ -802,18 +802,21 @@ struct kssd_dist {
     int n_qry = 0, n_ref = 0, components_done = 0;
     uint32_t max_qry_size = 0;
     uint32_t *d_ct = nullptr, *d_qsz = nullptr, *d_rsz = nullptr;
+    bool owns_ct = true;
     StatRow *d_rows = nullptr;
     uint64_t n_rows = 0;
 };
 
-extern "C" int kssd_dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, kssd_dist_t **out)
+static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, uint32_t *ct_ext, int filled,
+                       kssd_dist_t **out)
 {
     if (!c || !out || n_qry <= 0 || n_ref <= 0 || !qry_ctx_ct || !ref_ctx_ct) return fail(KSSD_E_INVAL, "kssd_dist_create: bad argument");
     CU(cudaSetDevice(c->device));
     kssd_dist *d = new kssd_dist();
     d->ctx = c; d->n_qry = n_qry; d->n_ref = n_ref;
     for (int i = 0; i < n_qry; i++) d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]);
-    CU(cudaMalloc(&d->d_ct, (size_t)n_qry * n_ref * 4));
+    if (ct_ext) { d->d_ct = ct_ext; d->owns_ct = false; d->components_done = filled ? 1 : 0; }
+    else CU(cudaMalloc(&d->d_ct, (size_t)n_qry * n_ref * 4));
     CU(cudaMalloc(&d->d_qsz, (size_t)n_qry * 4));
     CU(cudaMalloc(&d->d_rsz, (size_t)n_ref * 4));
     CU(cudaMemcpyAsync(d->d_qsz, qry_ctx_ct, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
@@ -821,6 +824,18 @@ extern "C" int kssd_dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint3
     CU(cudaStreamSynchronize(c->stream));
     *out = d;
     return KSSD_OK;
+}
+
+extern "C" int kssd_dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, kssd_dist_t **out)
+{
+    return dist_create(c, n_qry, n_ref, qry_ctx_ct, ref_ctx_ct, nullptr, 0, out);
+}
+
+extern "C" int kssd_dist_create_ext(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct,
+                                    uint32_t *ct_dev, int already_filled, kssd_dist_t **out)
+{
+    if (!ct_dev) return fail(KSSD_E_INVAL, "kssd_dist_create_ext: null count buffer");
+    return dist_create(c, n_qry, n_ref, qry_ctx_ct, ref_ctx_ct, ct_dev, already_filled, out);
 }
 
 extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev, const uint64_t *qindex_dev,
@@ -897,7 +912,8 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
     StatParams S;
     S.metric = o->metric; S.correction = o->correction; S.kmerlen = o->kmerlen; S.dim_rd_len = o->dim_rd_len;
     S.skip_zero = o->skip_zero; S.dthreshold = o->dthreshold;
-    S.cmprsn_num = (double)(uint32_t)((uint32_t)d->n_ref * (uint32_t)d->n_qry);   // 32-bit wrap, command_dist.c:1186
+    S.cmprsn_num = o->cmprsn_num ? (double)o->cmprsn_num
+                                 : (double)(uint32_t)((uint32_t)d->n_ref * (uint32_t)d->n_qry);   // 32-bit wrap, command_dist.c:1186
     if (d->d_rows) { cudaFree(d->d_rows); d->d_rows = nullptr; }
     d->n_rows = 0;
     CU(cudaEventRecord(c->ev[0], c->stream));
@@ -967,7 +983,7 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
 {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
-    cudaFree(d->d_ct);
+    if (d->owns_ct) cudaFree(d->d_ct);
     cudaFree(d->d_qsz);
     cudaFree(d->d_rsz);
     cudaFree(d->d_rows);

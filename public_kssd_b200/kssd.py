@@ -243,13 +243,20 @@ class Index:
 class DistJob:
     """Q x R shared-k-mer count matrix (sharedk_ct.dat) and the statistics of distance.out."""
 
-    def __init__(self, ctx: Context, qry_ctx_ct: np.ndarray, ref_ctx_ct: np.ndarray):
+    def __init__(self, ctx: Context, qry_ctx_ct: np.ndarray, ref_ctx_ct: np.ndarray, ct_dev_ptr: int | None = None,
+                 already_filled: bool = False):
+        """ct_dev_ptr: optional caller-owned device buffer (Q*R uint32) for the count matrix, e.g. a torch tensor that
+        takes part in a reduce-scatter (parallel.py)."""
         self.ctx = ctx
         q = np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
         r = np.ascontiguousarray(ref_ctx_ct, dtype=np.uint32)
         self.n_qry, self.n_ref = q.size, r.size
         self._h = C.c_void_p()
-        check(lib().kssd_dist_create(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.byref(self._h)))
+        if ct_dev_ptr is None:
+            check(lib().kssd_dist_create(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.byref(self._h)))
+        else:
+            check(lib().kssd_dist_create_ext(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.c_void_p(ct_dev_ptr),
+                                             int(already_filled), C.byref(self._h)))
 
     def accumulate(self, ref_index: Index, qcodes: np.ndarray, qindex: np.ndarray):
         qcodes = np.ascontiguousarray(qcodes, dtype=np.uint32)
@@ -265,9 +272,10 @@ class DistJob:
         return ct
 
     def stats(self, metric: int = 0, correction: int = 0, kmerlen: int | None = None, dim_rd_len: int | None = None,
-              dthreshold: float = 1.0, n_neighbors: int = 0, skip_zero: int = 0, fetch: bool = True):
+              dthreshold: float = 1.0, n_neighbors: int = 0, skip_zero: int = 0, fetch: bool = True, cmprsn_num: int = 0):
         o = capi.StatOpts(metric, correction, kmerlen if kmerlen is not None else 2 * self.ctx.k,
-                          dim_rd_len if dim_rd_len is not None else 2 * self.ctx.drlevel, dthreshold, n_neighbors, skip_zero)
+                          dim_rd_len if dim_rd_len is not None else 2 * self.ctx.drlevel, dthreshold, n_neighbors, skip_zero,
+                          cmprsn_num)
         n = check(lib().kssd_dist_stats(self._h, C.byref(o)))
         if not fetch:
             return n

@@ -1,0 +1,143 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL over NVLink on the box, gloo in CPU tests).
+
+SURVEY.md s8(e) / BASELINE.json north_star:
+  * Stage I shards by input GENOME: every rank sketches its own genomes, there is no data-path collective;
+    the (tiny) per-genome code lists are gathered to whoever writes combco.
+  * Stage III shards the REFERENCE INDEX BY CODE RANGE: rank r indexes only the reference codes that fall in
+    its slice of the code space, the query sketches are broadcast, every rank counts into a full Q x R matrix of
+    partial counts, and one reduce-scatter (uint32 sum) leaves rank r with the final counts of its block of
+    query rows; statistics run on the owner.
+
+The planning functions are pure Python (tested with gloo on CPU); the compute they drive is the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# plans (pure functions)
+# ------------------------------------------------------------------------------------------------
+def genome_shard(n_genomes: int, world: int, rank: int) -> range:
+    """Contiguous block of genomes for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_genomes, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def balanced_genome_shards(sizes, world: int):
+    """Size-balanced assignment (longest-processing-time first): list of genome-id lists, one per rank."""
+    order = np.argsort(-np.asarray(sizes, dtype=np.int64), kind="stable")
+    load = [0] * world
+    out = [[] for _ in range(world)]
+    for g in order:
+        r = int(np.argmin(load))
+        out[r].append(int(g))
+        load[r] += int(sizes[g])
+    return [sorted(x) for x in out]
+
+
+def code_range(rank: int, world: int, code_bits: int = 28) -> tuple[int, int]:
+    """[lo, hi) slice of the code space owned by `rank` (equal-width ranges; codes are hash-like, so equal width
+    is equal load)."""
+    space = 1 << code_bits
+    return (space * rank) // world, (space * (rank + 1)) // world
+
+
+def row_block(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Query rows whose final counts land on `rank` after the reduce-scatter (equal blocks, padded at the end)."""
+    per = (n_rows + world - 1) // world
+    lo = min(rank * per, n_rows)
+    return lo, min(lo + per, n_rows)
+
+
+def filter_codes_to_range(codes: np.ndarray, index: np.ndarray, lo: int, hi: int):
+    """Restrict a combco (codes, index) to codes in [lo, hi): the shard of the reference a rank indexes."""
+    codes = np.asarray(codes, dtype=np.uint32)
+    index = np.asarray(index, dtype=np.uint64)
+    keep = (codes >= lo) & (codes < hi)
+    csum = np.concatenate([[0], np.cumsum(keep, dtype=np.uint64)])
+    return codes[keep], csum[index.astype(np.int64)]
+
+
+# ------------------------------------------------------------------------------------------------
+# collectives
+# ------------------------------------------------------------------------------------------------
+def reduce_scatter_rows(partial, world: int, rank: int):
+    """partial: torch int32 tensor [rows_padded, R] with rows_padded % world == 0.  Returns this rank's
+    [rows_padded / world, R] block of the element-wise sum over ranks."""
+    import torch
+    import torch.distributed as dist
+    rows = partial.shape[0] // world
+    if world == 1:
+        return partial
+    out = torch.empty((rows, partial.shape[1]), dtype=partial.dtype, device=partial.device)
+    if dist.get_backend() == "nccl":
+        dist.reduce_scatter_tensor(out, partial, op=dist.ReduceOp.SUM)
+    else:   # gloo (CPU tests): same result through all_reduce + slice
+        tmp = partial.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+        out.copy_(tmp[rank * rows:(rank + 1) * rows])
+    return out
+
+
+class ShardedDist:
+    """Stage III over `world` GPUs: reference index sharded by code range, queries broadcast, partial count
+    matrices combined by reduce-scatter.  Every rank calls the same methods (SPMD)."""
+
+    def __init__(self, ctx, world: int, rank: int, code_bits: int = 28):
+        self.ctx, self.world, self.rank, self.code_bits = ctx, world, rank, code_bits
+        self.index = None
+        self.ref_sizes = None
+
+    def build_reference(self, ref_codes: np.ndarray, ref_index: np.ndarray):
+        """Every rank sees the reference combco (or at least its own code range of it) and indexes its slice."""
+        lo, hi = code_range(self.rank, self.world, self.code_bits)
+        c, ix = filter_codes_to_range(ref_codes, ref_index, lo, hi)
+        self.index = self.ctx.combco2mco(c, ix)
+        self.ref_sizes = np.diff(np.asarray(ref_index, dtype=np.uint64)).astype(np.uint32)
+        return self
+
+    def search(self, qry_codes: np.ndarray | None, qry_index: np.ndarray | None, src: int = 0, stats_opts: dict | None = None):
+        """Broadcast the query sketches from `src`, count, reduce-scatter.  Returns (row_lo, row_hi, counts block
+        as numpy uint32, stats rows or None) for the rows this rank owns."""
+        import torch
+        import torch.distributed as dist
+        from . import kssd
+        dev = torch.device("cuda", self.ctx.device)
+        if self.world > 1:
+            meta = torch.zeros(2, dtype=torch.int64, device=dev)
+            if self.rank == src:
+                meta[0], meta[1] = len(qry_index) - 1, len(qry_codes)
+            dist.broadcast(meta, src)
+            nq, nc = int(meta[0]), int(meta[1])
+            tq = torch.empty(max(nc, 1), dtype=torch.int32, device=dev)
+            ti = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+            if self.rank == src:
+                tq[:nc] = torch.from_numpy(np.ascontiguousarray(qry_codes, dtype=np.uint32).view(np.int32)).to(dev)
+                ti.copy_(torch.from_numpy(np.ascontiguousarray(qry_index, dtype=np.uint64).view(np.int64)).to(dev))
+            dist.broadcast(tq, src)
+            dist.broadcast(ti, src)
+        else:
+            nq, nc = len(qry_index) - 1, len(qry_codes)
+            tq = torch.from_numpy(np.ascontiguousarray(qry_codes, dtype=np.uint32).view(np.int32)).to(dev)
+            ti = torch.from_numpy(np.ascontiguousarray(qry_index, dtype=np.uint64).view(np.int64)).to(dev)
+        qsizes = (ti[1:] - ti[:-1]).to(torch.int64).cpu().numpy().astype(np.uint32)
+        R = int(self.ref_sizes.size)
+        per = (nq + self.world - 1) // self.world
+        rows_padded = per * self.world
+        partial = torch.zeros((rows_padded, R), dtype=torch.int32, device=dev)
+        job = kssd.DistJob(self.ctx, qsizes, self.ref_sizes, ct_dev_ptr=partial.data_ptr())
+        torch.cuda.synchronize()
+        job.accumulate_dev(self.index, tq.data_ptr(), ti.data_ptr(), nc)
+        job.close()
+        mine = reduce_scatter_rows(partial, self.world, self.rank)
+        torch.cuda.synchronize()
+        lo, hi = row_block(nq, self.world, self.rank)
+        rows = None
+        if stats_opts is not None and hi > lo:
+            sj = kssd.DistJob(self.ctx, qsizes[lo:hi], self.ref_sizes, ct_dev_ptr=mine.data_ptr(), already_filled=True)
+            rows = sj.stats(cmprsn_num=(R * nq) & 0xFFFFFFFF, **stats_opts)
+            rows["qry"] += lo
+            sj.close()
+        return lo, hi, mine[: hi - lo].cpu().numpy().view(np.uint32), rows
