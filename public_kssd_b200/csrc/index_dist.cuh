@@ -9,16 +9,14 @@ namespace kssd {
 // code of genome j, j ascending: postings = gids ordered by (code, gid).  Here: tag each code with
 // its gid, stable LSD radix sort by code (gid order is preserved inside a code), run heads -> CSR.
 // ------------------------------------------------------------------------------------------------
-__global__ void expand_gid_kernel(const uint64_t *__restrict__ index, int n_genomes, uint64_t n, uint32_t *__restrict__ gid)
+// gid of every posting position: mark the first position of each non-empty genome with its id, then an inclusive
+// max-scan spreads it (ids ascend with position).  Replaces a per-element binary search.
+__global__ void mark_genome_starts_kernel(const uint64_t *__restrict__ index, int n_genomes, uint32_t *__restrict__ gid)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int lo = 0, hi = n_genomes;          // last j with index[j] <= i
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (index[mid] <= i) lo = mid; else hi = mid;
-    }
-    gid[i] = (uint32_t)lo;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_genomes) return;
+    const uint64_t a = index[j], b = index[j + 1];
+    if (a < b) gid[a] = (uint32_t)j;
 }
 
 __global__ void head_flags_kernel(const uint32_t *__restrict__ codes, uint64_t n, uint32_t *__restrict__ flags)
@@ -39,25 +37,13 @@ __global__ void csr_scatter_kernel(const uint32_t *__restrict__ codes, const uin
 
 // Dense EXCLUSIVE start table over the whole code space of one component:
 //   dense[c] = #postings with code < c,  c in [0, space]   (space = 16^COMPONENT_SZ)
-// One warp per unique code fills the (coalesced) range that ends at that code.
-__global__ void dense_fill_kernel(const uint32_t *__restrict__ ucodes, const uint32_t *__restrict__ uoff, uint32_t nuniq,
-                                  uint32_t n_postings, uint64_t space, uint32_t *__restrict__ dense)
+// Built as: zero, dense[ucode + 1] = end offset of that code's postings, inclusive max-scan (offsets ascend with
+// the code) -- two streaming passes over the table instead of one short uncoalesced range per code.
+__global__ void dense_mark_kernel(const uint32_t *__restrict__ ucodes, const uint32_t *__restrict__ uoff, uint32_t nuniq,
+                                  uint32_t *__restrict__ dense)
 {
-    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (w > nuniq) return;
-    uint64_t from, to;     // dense[from..to] = val
-    uint32_t val;
-    if (w < nuniq) {
-        from = w == 0 ? 0 : (uint64_t)ucodes[w - 1] + 1;
-        to = ucodes[w];
-        val = uoff[w];
-    } else {
-        from = nuniq == 0 ? 0 : (uint64_t)ucodes[nuniq - 1] + 1;
-        to = space;
-        val = n_postings;
-    }
-    for (uint64_t c = from + lane; c <= to; c += 32) dense[c] = val;
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nuniq) dense[(uint64_t)ucodes[u] + 1] = uoff[u + 1];
 }
 
 // mco.index.<c> as the reference writes it (co2mco.c:57-61): inclusive u64 prefix, chunked
@@ -103,28 +89,22 @@ __global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t
     }
     __syncthreads();
     const uint64_t qs = qindex[q], qe = qindex[q + 1];
-    if (sizeof(CT) == 4) {
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(smem_raw);
-        for (uint64_t i = qs + threadIdx.x; i < qe; i += blockDim.x) {
-            const uint32_t c = __ldg(&qcodes[i]);
-            const uint2 se = make_uint2(__ldg(&dense[c]), __ldg(&dense[c + 1]));
-            for (uint32_t g = se.x; g < se.y; g++) {
-                const uint32_t r = __ldg(&mco[g]);
-                if (r >= r0 && r < r1) atomicAdd(&t32[r - r0], 1u);
-            }
-        }
-    } else {
-        // 16-bit counters packed two per word: add 1 or 1<<16; cannot carry across halves because a
-        // count never exceeds the query sketch size (< 65536 on this path)
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(smem_raw);
-        for (uint64_t i = qs + threadIdx.x; i < qe; i += blockDim.x) {
-            const uint32_t c = __ldg(&qcodes[i]);
-            const uint2 se = make_uint2(__ldg(&dense[c]), __ldg(&dense[c + 1]));
-            for (uint32_t g = se.x; g < se.y; g++) {
-                const uint32_t r = __ldg(&mco[g]);
-                if (r >= r0 && r < r1) {
-                    const uint32_t o = r - r0;
-                    atomicAdd(&t32[o >> 1], (o & 1u) ? 0x10000u : 1u);
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(smem_raw);
+    for (uint64_t i = qs + threadIdx.x; i < qe; i += blockDim.x) {
+        const uint32_t c = __ldg(&qcodes[i]);
+        const uint32_t s0 = __ldg(&dense[c]), s1 = __ldg(&dense[c + 1]);
+        // postings are fetched eight at a time before any atomic, so a thread keeps eight loads in flight
+        for (uint32_t g = s0; g < s1; g += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) r[u] = (g + u < s1) ? __ldg(&mco[g + u]) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t o = r[u] - r0;                    // 0xffffffff - r0 >= width: padding never lands
+                if (o < width) {
+                    if (sizeof(CT) == 4) atomicAdd(&t32[o], 1u);
+                    // 16-bit counters packed two per word: a count never exceeds the query sketch size (< 65536 here)
+                    else atomicAdd(&t32[o >> 1], (o & 1u) ? 0x10000u : 1u);
                 }
             }
         }
@@ -163,9 +143,30 @@ __device__ __forceinline__ uint32_t x86_double_to_u32(double v)
     return (uint32_t)(unsigned long long)(long long)v;
 }
 
+// keep / suppress decision only (first pass): no statistics, one log at most
+__device__ __forceinline__ bool stat_keep(const StatParams &S, uint32_t X, uint32_t Y, uint32_t I)
+{
+    if (S.skip_zero && I == 0) return false;
+    if (S.dthreshold >= 1.0) return true;          // dist is clamped to <= 1 (NaN never compares greater)
+    double rs = 0.0;
+    if (S.correction) {
+        const uint32_t xo = X - I, yo = Y - I;
+        const double base = 1.0 - 1.0 / pow(4.0, (double)(S.kmerlen - S.dim_rd_len));
+        const double px = 1.0 - pow(base, (double)xo);
+        const double py = 1.0 - pow(base, (double)yo);
+        rs = px * py * (double)(xo + yo) / (px + py - 2.0 * px * py);
+    }
+    const uint32_t tmp = S.metric == 0 ? X + Y - I : (X < Y ? X : Y);
+    const double m = ((double)I - rs) / (double)tmp;
+    double dist = log(get_matric(S.metric, m)) / (double)S.kmerlen;
+    if (dist > 1.0) dist = 1.0;
+    return !(dist > S.dthreshold);
+}
+
 // returns false when the row is suppressed
 __device__ __forceinline__ bool stat_row(const StatParams &S, uint32_t X, uint32_t Y, uint32_t I, StatRow &r)
 {
+    if (S.skip_zero && I == 0) return false;
     double rs = 0.0;
     if (S.correction) {
         const uint32_t xo = X - I, yo = Y - I;
@@ -191,71 +192,94 @@ __device__ __forceinline__ bool stat_row(const StatParams &S, uint32_t X, uint32
     return true;
 }
 
-// pass 1: kept rows per (query, block of 1024 refs); pass 2: ordered write.  Query-major, refs
-// ascending, exactly the order dist_print_nobin emits (command_dist.c:1228-1242).
+// Statistics in three passes over one WARP per (query, block of 1024 refs):
+//   1. count the rows that will be printed, 2. (after a scan) write their (query, ref) pairs in print order --
+//   query-major, refs ascending, as dist_print_nobin emits them (command_dist.c:1228-1242) -- and
+//   3. one thread per printed row evaluates output_ctrl densely (no lane idles through another lane's erfc/log).
+// TRIVIAL = the keep decision needs no arithmetic (-D >= 1: dist is clamped to <= 1, NaN never compares greater).
 constexpr int kStatThreads = 256;
 constexpr int kStatRefsPerBlock = 1024;
 
+template <bool TRIVIAL>
+__device__ __forceinline__ bool stat_keep_t(const StatParams &S, uint32_t X, uint32_t Y, uint32_t I)
+{
+    if (TRIVIAL) return !(S.skip_zero && I == 0);
+    return stat_keep(S, X, Y, I);
+}
+
+template <bool TRIVIAL>
 __global__ void __launch_bounds__(kStatThreads) stats_count_kernel(const StatParams S, const uint32_t *__restrict__ ct,
                                                                     const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
-                                                                    uint32_t n_ref, uint32_t blocks_per_row, uint32_t *__restrict__ block_counts)
+                                                                    uint32_t n_ref, uint32_t blocks_per_row, uint64_t n_blocks,
+                                                                    uint32_t *__restrict__ block_counts)
 {
-    const uint32_t q = blockIdx.x / blocks_per_row;
-    const uint32_t b = blockIdx.x - q * blocks_per_row;
+    const uint64_t wb = ((uint64_t)blockIdx.x * kStatThreads + threadIdx.x) >> 5;     // this warp's block
+    if (wb >= n_blocks) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = (uint32_t)(wb / blocks_per_row);
+    const uint32_t b = (uint32_t)(wb - (uint64_t)q * blocks_per_row);
     const uint32_t Y = qsz[q];
+    const uint32_t *row = ct + (uint64_t)q * n_ref;
+    const uint32_t r0 = b * kStatRefsPerBlock;
     uint32_t kept = 0;
-    StatRow tmp;
-    for (uint32_t j = threadIdx.x; j < kStatRefsPerBlock; j += kStatThreads) {
-        const uint32_t r = b * kStatRefsPerBlock + j;
-        if (r < n_ref) kept += stat_row(S, rsz[r], Y, ct[(uint64_t)q * n_ref + r], tmp) ? 1u : 0u;
+    if (TRIVIAL && (n_ref & 3u) == 0 && r0 + kStatRefsPerBlock <= n_ref) {
+        // rows are 16-byte aligned: eight 16-byte loads per lane, all in flight together
+        const uint4 *v = reinterpret_cast<const uint4 *>(row + r0);
+        uint4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = __ldg(&v[lane + 32 * i]);
+        if (S.skip_zero) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) kept += (x[i].x != 0) + (x[i].y != 0) + (x[i].z != 0) + (x[i].w != 0);
+        } else kept = 32;
+    } else {
+#pragma unroll 4
+        for (uint32_t j = lane; j < kStatRefsPerBlock; j += 32) {
+            const uint32_t r = r0 + j;
+            if (r < n_ref) kept += stat_keep_t<TRIVIAL>(S, rsz[r], Y, row[r]) ? 1u : 0u;
+        }
     }
-    __shared__ uint32_t red[kStatThreads / 32];
     kept = __reduce_add_sync(kFull, kept);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kept;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t s = 0;
-        for (int i = 0; i < kStatThreads / 32; i++) s += red[i];
-        block_counts[blockIdx.x] = s;
+    if (lane == 0) block_counts[wb] = kept;
+}
+
+template <bool TRIVIAL>
+__global__ void __launch_bounds__(kStatThreads) stats_pairs_kernel(const StatParams S, const uint32_t *__restrict__ ct,
+                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                                    uint32_t n_ref, uint32_t blocks_per_row, uint64_t n_blocks,
+                                                                    const uint32_t *__restrict__ block_counts,
+                                                                    const uint64_t *__restrict__ block_offsets, uint2 *__restrict__ pairs)
+{
+    const uint64_t wb = ((uint64_t)blockIdx.x * kStatThreads + threadIdx.x) >> 5;
+    if (wb >= n_blocks) return;
+    if (block_counts[wb] == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = (uint32_t)(wb / blocks_per_row);
+    const uint32_t b = (uint32_t)(wb - (uint64_t)q * blocks_per_row);
+    const uint32_t Y = qsz[q];
+    const uint32_t *row = ct + (uint64_t)q * n_ref;
+    uint64_t running = block_offsets[wb];
+    for (uint32_t j = lane; j < kStatRefsPerBlock; j += 32) {
+        const uint32_t r = b * kStatRefsPerBlock + j;
+        const bool keep = r < n_ref && stat_keep_t<TRIVIAL>(S, rsz[r], Y, row[r]);
+        const uint32_t bal = __ballot_sync(kFull, keep);
+        if (keep) pairs[running + __popc(bal & ((1u << lane) - 1u))] = make_uint2(q, r);
+        running += __popc(bal);
     }
 }
 
-__global__ void __launch_bounds__(kStatThreads) stats_write_kernel(const StatParams S, const uint32_t *__restrict__ ct,
-                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
-                                                                    uint32_t n_ref, uint32_t blocks_per_row,
-                                                                    const uint64_t *__restrict__ block_offsets, StatRow *__restrict__ rows)
+__global__ void __launch_bounds__(kStatThreads) stats_rows_kernel(const StatParams S, const uint32_t *__restrict__ ct,
+                                                                   const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                                   uint32_t n_ref, const uint2 *__restrict__ pairs, uint64_t n_rows,
+                                                                   StatRow *__restrict__ rows)
 {
-    const uint32_t q = blockIdx.x / blocks_per_row;
-    const uint32_t b = blockIdx.x - q * blocks_per_row;
-    const uint32_t Y = qsz[q];
-    __shared__ uint32_t wsum[kStatThreads / 32];
-    __shared__ uint32_t running;
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    const uint64_t base = block_offsets[blockIdx.x];
-    for (uint32_t j0 = 0; j0 < kStatRefsPerBlock; j0 += kStatThreads) {
-        const uint32_t r = b * kStatRefsPerBlock + j0 + threadIdx.x;
-        StatRow row;
-        bool keep = false;
-        if (r < n_ref) keep = stat_row(S, rsz[r], Y, ct[(uint64_t)q * n_ref + r], row);
-        const uint32_t bal = __ballot_sync(kFull, keep);
-        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (lane == 0) wsum[wid] = __popc(bal);
-        __syncthreads();
-        uint32_t before = running;
-        for (uint32_t w = 0; w < wid; w++) before += wsum[w];
-        if (keep) {
-            row.qry = q; row.ref = r;
-            rows[base + before + __popc(bal & ((1u << lane) - 1u))] = row;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t s = 0;
-            for (int w = 0; w < kStatThreads / 32; w++) s += wsum[w];
-            running += s;
-        }
-        __syncthreads();
-    }
+    const uint64_t i = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
+    if (i >= n_rows) return;
+    const uint2 p = pairs[i];
+    StatRow out;
+    stat_row(S, rsz[p.y], qsz[p.x], ct[(uint64_t)p.x * n_ref + p.y], out);   // kept by construction
+    out.qry = p.x; out.ref = p.y;
+    rows[i] = out;
 }
 
 // -N: best n refs per query by the raw metric with the reference's insertion rule

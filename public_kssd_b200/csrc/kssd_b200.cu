@@ -641,9 +641,15 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
     CU(cudaMemcpyAsync(ix->d_uoff + nuniq, &n32, 4, cudaMemcpyHostToDevice, c->stream));
     // dense exclusive start table for O(1) query lookups (and for mco.index.<c> export)
     CU(cudaMalloc(&ix->d_dense, (ix->space + 1) * 4));
-    const uint64_t warps = (uint64_t)nuniq + 1;
-    dense_fill_kernel<<<(uint32_t)((warps * 32 + 255) / 256), 256, 0, c->stream>>>(ix->d_ucodes, ix->d_uoff, nuniq, n32, ix->space, ix->d_dense);
-    LAUNCHED(1);
+    CU(cudaMemsetAsync(ix->d_dense, 0, (ix->space + 1) * 4, c->stream));
+    if (nuniq) {
+        dense_mark_kernel<<<(nuniq + 255) / 256, 256, 0, c->stream>>>(ix->d_ucodes, ix->d_uoff, nuniq, ix->d_dense);
+        size_t tmpb = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tmpb, ix->d_dense, ix->d_dense, cub::Max(), ix->space + 1, c->stream);
+        CU(c->cubtmp.ensure(tmpb));
+        CU(cub::DeviceScan::InclusiveScan(c->cubtmp.p, tmpb, ix->d_dense, ix->d_dense, cub::Max(), ix->space + 1, c->stream));
+        LAUNCHED(3);
+    }
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     return KSSD_OK;
@@ -664,9 +670,14 @@ extern "C" int kssd_index_build_dev(kssd_ctx_t *c, const uint32_t *combco_dev, c
     if (n_codes) {
         CU(c->keys.ensure(n_codes * 4));     // gid tags (unsorted)
         CU(c->keys2.ensure(n_codes * 4));    // sorted codes
-        expand_gid_kernel<<<(uint32_t)((n_codes + 255) / 256), 256, 0, c->stream>>>(cbdcoindex_dev, n_genomes, n_codes, c->keys.as<uint32_t>());
-        LAUNCHED(1);
+        CU(cudaMemsetAsync(c->keys.p, 0, n_codes * 4, c->stream));
+        mark_genome_starts_kernel<<<(n_genomes + 255) / 256, 256, 0, c->stream>>>(cbdcoindex_dev, n_genomes, c->keys.as<uint32_t>());
         size_t tmp = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tmp, c->keys.as<uint32_t>(), c->keys.as<uint32_t>(), cub::Max(), n_codes, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::InclusiveScan(c->cubtmp.p, tmp, c->keys.as<uint32_t>(), c->keys.as<uint32_t>(), cub::Max(), n_codes, c->stream));
+        LAUNCHED(3);
+        tmp = 0;
         const int bits = 4 * std::min(c->info.component_sz, c->info.k - c->info.drlevel);
         cub::DeviceRadixSort::SortPairs(nullptr, tmp, combco_dev, c->keys2.as<uint32_t>(), c->keys.as<uint32_t>(), ix->d_gids, n_codes, 0, bits,
                                         c->stream);
@@ -847,8 +858,8 @@ extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_
     CU(cudaSetDevice(c->device));
     const bool small = d->max_qry_size < 65536u;
     const uint32_t elem = small ? 2 : 4;
-    // strip width: whole row when it fits in ~96 KiB (two CTAs per SM), else equal tiles
-    const uint32_t max_refs = (96u << 10) / elem;
+    // strip width: whole row when it fits in 112 KiB (two CTAs per SM), else equal tiles
+    const uint32_t max_refs = (112u << 10) / elem;
     const uint32_t n_tiles = ((uint32_t)d->n_ref + max_refs - 1) / max_refs;
     uint32_t tile = ((uint32_t)d->n_ref + n_tiles - 1) / n_tiles;
     tile = (tile + 1) & ~1u;
@@ -914,13 +925,13 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
     S.skip_zero = o->skip_zero; S.dthreshold = o->dthreshold;
     S.cmprsn_num = o->cmprsn_num ? (double)o->cmprsn_num
                                  : (double)(uint32_t)((uint32_t)d->n_ref * (uint32_t)d->n_qry);   // 32-bit wrap, command_dist.c:1186
-    if (d->d_rows) { cudaFree(d->d_rows); d->d_rows = nullptr; }
+    if (d->d_rows) { cudaFreeAsync(d->d_rows, c->stream); d->d_rows = nullptr; }
     d->n_rows = 0;
     CU(cudaEventRecord(c->ev[0], c->stream));
     if (o->n_neighbors > 0) {
         const int N = o->n_neighbors;
         StatRow *tmp_rows = nullptr;
-        CU(cudaMalloc(&tmp_rows, (size_t)d->n_qry * N * sizeof(StatRow)));
+        CU(cudaMallocAsync(&tmp_rows, (size_t)d->n_qry * N * sizeof(StatRow), c->stream));
         CU(c->flags.ensure((size_t)d->n_qry * 4));
         topn_kernel<<<d->n_qry, 256, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, N, c->flags.as<uint32_t>(), tmp_rows);
         LAUNCHED(1);
@@ -929,21 +940,24 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         CU(cudaStreamSynchronize(c->stream));
         uint64_t total = 0;
         for (auto v : rc) total += v;
-        CU(cudaMalloc(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow)));
+        CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
         uint64_t o2 = 0;
         for (int q = 0; q < d->n_qry; q++) {
             if (rc[q]) CU(cudaMemcpyAsync(d->d_rows + o2, tmp_rows + (size_t)q * N, (size_t)rc[q] * sizeof(StatRow), cudaMemcpyDeviceToDevice, c->stream));
             o2 += rc[q];
         }
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(tmp_rows);
+        cudaFreeAsync(tmp_rows, c->stream);
         d->n_rows = total;
     } else {
         const uint32_t bpr = ((uint32_t)d->n_ref + kStatRefsPerBlock - 1) / kStatRefsPerBlock;
         const uint64_t nblocks = (uint64_t)bpr * d->n_qry;
         CU(c->flags.ensure(nblocks * 4));
         CU(c->pos.ensure((nblocks + 1) * 8));
-        stats_count_kernel<<<(uint32_t)nblocks, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, c->flags.as<uint32_t>());
+        const uint32_t grid = (uint32_t)((nblocks * 32 + kStatThreads - 1) / kStatThreads);
+        const bool trivial = S.dthreshold >= 1.0;
+        if (trivial) stats_count_kernel<true><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks, c->flags.as<uint32_t>());
+        else stats_count_kernel<false><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks, c->flags.as<uint32_t>());
         size_t tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nblocks, c->stream);
         CU(c->cubtmp.ensure(tmp));
@@ -955,10 +969,17 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         CU(cudaMemcpyAsync(&lastcnt, c->flags.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         const uint64_t total = lastoff + lastcnt;
-        CU(cudaMalloc(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow)));
-        stats_write_kernel<<<(uint32_t)nblocks, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, c->pos.as<uint64_t>(),
-                                                                             d->d_rows);
-        LAUNCHED(1);
+        CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
+        if (total) {
+            CU(c->keys.ensure(total * sizeof(uint2)));
+            if (trivial) stats_pairs_kernel<true><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks,
+                                                                                      c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), c->keys.as<uint2>());
+            else stats_pairs_kernel<false><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks,
+                                                                               c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), c->keys.as<uint2>());
+            stats_rows_kernel<<<(uint32_t)((total + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
+                S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, c->keys.as<uint2>(), total, d->d_rows);
+            LAUNCHED(2);
+        }
         d->n_rows = total;
     }
     CU(cudaEventRecord(c->ev[1], c->stream));
@@ -986,6 +1007,6 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
     if (d->owns_ct) cudaFree(d->d_ct);
     cudaFree(d->d_qsz);
     cudaFree(d->d_rsz);
-    cudaFree(d->d_rows);
+    if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);
     delete d;
 }
