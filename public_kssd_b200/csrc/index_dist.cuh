@@ -66,26 +66,28 @@ __global__ void dense_from_incl64_kernel(const uint64_t *__restrict__ incl, uint
 // count matrix in shared memory: postings are scattered with shared-memory atomics, and the strip
 // is written to HBM exactly once, coalesced -- no global atomics and no separate memset pass.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDistThreads = 512;
+#ifndef KSSD_DIST_THREADS
+#define KSSD_DIST_THREADS 256
+#endif
+constexpr int kDistThreads = KSSD_DIST_THREADS;
 
 template <typename CT>   // uint16_t when every query sketch is < 65536 codes, else uint32_t
 __global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
-                                                                  const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
-                                                                  uint32_t n_ref, uint32_t tile_refs, uint32_t n_tiles,
-                                                                  uint32_t *__restrict__ ct, int accumulate)
+                                                                     const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                     uint32_t n_ref, uint32_t tile_refs, uint32_t n_tiles,
+                                                                     uint32_t *__restrict__ ct, int accumulate)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    CT *tile = reinterpret_cast<CT *>(smem_raw);
     const uint32_t q = blockIdx.x / n_tiles;
     const uint32_t t = blockIdx.x - q * n_tiles;
-    const uint32_t r0 = t * tile_refs;
+    const uint32_t r0 = t * tile_refs;                      // tile_refs is a multiple of 8
     const uint32_t r1 = min(r0 + tile_refs, n_ref);
     const uint32_t width = r1 - r0;
-    // zero the strip (word-wise)
+    // zero the strip, 16 bytes per store
     {
-        uint32_t *z = reinterpret_cast<uint32_t *>(smem_raw);
-        const uint32_t words = (width * (uint32_t)sizeof(CT) + 3) / 4;
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) z[i] = 0;
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        const uint32_t vecs = (width * (uint32_t)sizeof(CT) + 15) / 16;
+        for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const uint64_t qs = qindex[q], qe = qindex[q + 1];
@@ -110,11 +112,83 @@ __global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t
         }
     }
     __syncthreads();
+    // write the strip once; 16-byte stores when the row slice is 16-byte aligned
     uint32_t *row = ct + (uint64_t)q * n_ref + r0;
-    if (accumulate) {
-        for (uint32_t i = threadIdx.x; i < width; i += blockDim.x) row[i] += (uint32_t)tile[i];
+    const bool vec_ok = ((n_ref & 3u) == 0) && !accumulate;
+    const uint32_t w4 = vec_ok ? (width & ~3u) : 0;
+    if (sizeof(CT) == 2) {
+        const uint2 *src = reinterpret_cast<const uint2 *>(smem_raw);      // four 16-bit counters
+        uint4 *dst = reinterpret_cast<uint4 *>(row);
+        for (uint32_t i = threadIdx.x; i < w4 / 4; i += blockDim.x) {
+            const uint2 v = src[i];
+            dst[i] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+        }
     } else {
-        for (uint32_t i = threadIdx.x; i < width; i += blockDim.x) row[i] = (uint32_t)tile[i];
+        const uint4 *src = reinterpret_cast<const uint4 *>(smem_raw);
+        uint4 *dst = reinterpret_cast<uint4 *>(row);
+        for (uint32_t i = threadIdx.x; i < w4 / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    const CT *tile = reinterpret_cast<const CT *>(smem_raw);
+    for (uint32_t i = w4 + threadIdx.x; i < width; i += blockDim.x) {
+        if (accumulate) row[i] += (uint32_t)tile[i];
+        else row[i] = (uint32_t)tile[i];
+    }
+}
+
+// L2-resident variant: one persistent CTA per SM owns one query ROW at a time.  The row (R x 4 B) is zeroed with
+// 16-byte stores -- it lands in the 126 MB L2, 148 rows in flight are ~59 MB at R = 100k -- and the postings are
+// added with global reductions (RED.ADD) that hit those L2 lines; the row reaches HBM once, by write-back.  No
+// shared-memory strip, no reference tiles (every posting list is walked once), no copy-out phase.
+constexpr int kDistRowThreads = 512;
+
+__global__ void __launch_bounds__(kDistRowThreads) dist_count_rows_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
+                                                                              const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                              uint32_t n_qry, uint32_t n_ref, uint32_t *__restrict__ ct, int accumulate)
+{
+    for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
+        uint32_t *row = ct + (uint64_t)q * n_ref;
+        if (!accumulate) {
+            // head up to a 16-byte boundary, body as uint4, tail
+            const uint32_t mis = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15) / 4;
+            const uint32_t head = min(mis, n_ref);
+            if (threadIdx.x < head) row[threadIdx.x] = 0;
+            uint4 *v = reinterpret_cast<uint4 *>(row + head);
+            const uint32_t nv = (n_ref - head) / 4;
+            for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) v[i] = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = head + nv * 4 + threadIdx.x; i < n_ref; i += blockDim.x) row[i] = 0;
+            __syncthreads();
+        }
+        // a WARP walks 32 query codes at a time: every lane looks one code up, then the warp reads each posting
+        // list with consecutive lanes (coalesced; lists average ~15 gids) -- eight lists in flight before any RED
+        const uint64_t qs = qindex[q], qe = qindex[q + 1];
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (uint64_t base = qs + 32ull * wid; base < qe; base += 32ull * nw) {
+            const uint64_t i = base + lane;
+            uint32_t s0 = 0, s1 = 0;
+            if (i < qe) {
+                const uint32_t c = __ldg(&qcodes[i]);
+                s0 = __ldg(&dense[c]);
+                s1 = __ldg(&dense[c + 1]);
+            }
+            const uint32_t cnt = (uint32_t)min((uint64_t)32, qe - base);
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t a = __shfl_sync(kFull, s0, (j0 + u) & 31), b = __shfl_sync(kFull, s1, (j0 + u) & 31);
+                    r[u] = (j0 + u < cnt && a + lane < b) ? __ldg(&mco[a + lane]) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (r[u] != 0xffffffffu) atomicAdd(&row[r[u]], 1u);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {          // lists longer than a warp (rare)
+                    const uint32_t a = __shfl_sync(kFull, s0, (j0 + u) & 31), b = __shfl_sync(kFull, s1, (j0 + u) & 31);
+                    if (j0 + u < cnt)
+                        for (uint32_t g = a + 32 + lane; g < b; g += 32) atomicAdd(&row[__ldg(&mco[g])], 1u);
+                }
+            }
+        }
     }
 }
 
@@ -192,10 +266,13 @@ __device__ __forceinline__ bool stat_row(const StatParams &S, uint32_t X, uint32
     return true;
 }
 
-// Statistics in three passes over one WARP per (query, block of 1024 refs):
-//   1. count the rows that will be printed, 2. (after a scan) write their (query, ref) pairs in print order --
-//   query-major, refs ascending, as dist_print_nobin emits them (command_dist.c:1228-1242) -- and
-//   3. one thread per printed row evaluates output_ctrl densely (no lane idles through another lane's erfc/log).
+// Statistics.  One WARP owns one chunk of 1024 refs of one query row.
+//   list pass  : read the chunk once (eight 16-byte loads per lane in flight), decide which cells are printed, reserve
+//                room in the pair list with one atomicAdd per chunk and write the (query, ref) pairs, ref ascending;
+//   (scan of the per-chunk counts gives every chunk its place in print order: query-major, refs ascending, exactly
+//    as dist_print_nobin emits rows, command_dist.c:1228-1242)
+//   rows pass  : one thread per printed row evaluates output_ctrl densely -- no lane idles through another lane's
+//                erfc/log -- and stores the row at its final position.
 // TRIVIAL = the keep decision needs no arithmetic (-D >= 1: dist is clamped to <= 1, NaN never compares greater).
 constexpr int kStatThreads = 256;
 constexpr int kStatRefsPerBlock = 1024;
@@ -208,77 +285,135 @@ __device__ __forceinline__ bool stat_keep_t(const StatParams &S, uint32_t X, uin
 }
 
 template <bool TRIVIAL>
-__global__ void __launch_bounds__(kStatThreads) stats_count_kernel(const StatParams S, const uint32_t *__restrict__ ct,
-                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
-                                                                    uint32_t n_ref, uint32_t blocks_per_row, uint64_t n_blocks,
-                                                                    uint32_t *__restrict__ block_counts)
+__global__ void __launch_bounds__(kStatThreads) stats_list_kernel(const StatParams S, const uint32_t *__restrict__ ct,
+                                                                   const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                                   uint32_t n_ref, uint32_t chunks_per_row, uint64_t n_chunks,
+                                                                   uint32_t *__restrict__ chunk_cnt, uint32_t *__restrict__ chunk_pos,
+                                                                   unsigned long long *__restrict__ cursor, uint64_t cap, uint2 *__restrict__ pairs)
 {
-    const uint64_t wb = ((uint64_t)blockIdx.x * kStatThreads + threadIdx.x) >> 5;     // this warp's block
-    if (wb >= n_blocks) return;
+    uint64_t wb = ((uint64_t)blockIdx.x * kStatThreads + threadIdx.x) >> 5;     // this warp's chunk
+    const bool live = wb < n_chunks;                 // dead warps of the last CTA still take part in the barriers
+    if (!live) wb = n_chunks - 1;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t q = (uint32_t)(wb / blocks_per_row);
-    const uint32_t b = (uint32_t)(wb - (uint64_t)q * blocks_per_row);
+    const uint32_t q = (uint32_t)(wb / chunks_per_row);
+    const uint32_t b = (uint32_t)(wb - (uint64_t)q * chunks_per_row);
     const uint32_t Y = qsz[q];
     const uint32_t *row = ct + (uint64_t)q * n_ref;
-    const uint32_t r0 = b * kStatRefsPerBlock;
+    const uint32_t r0 = live ? b * kStatRefsPerBlock : n_ref;     // a dead warp sees an empty chunk
+    // lane l holds refs r0 + 128*i + 4*l + {0..3}, i = 0..7 (vector path) -- ascending in (i, lane, component)
+    uint32_t m[8];
     uint32_t kept = 0;
-    if (TRIVIAL && (n_ref & 3u) == 0 && r0 + kStatRefsPerBlock <= n_ref) {
-        // rows are 16-byte aligned: eight 16-byte loads per lane, all in flight together
+    const bool vec = (n_ref & 3u) == 0 && r0 + kStatRefsPerBlock <= n_ref;
+    if (vec) {
         const uint4 *v = reinterpret_cast<const uint4 *>(row + r0);
         uint4 x[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = __ldg(&v[lane + 32 * i]);
-        if (S.skip_zero) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) kept += (x[i].x != 0) + (x[i].y != 0) + (x[i].z != 0) + (x[i].w != 0);
-        } else kept = 32;
+        for (int i = 0; i < 8; i++) {
+            const uint32_t r = r0 + 128 * i + 4 * lane;
+            if (TRIVIAL) {
+                m[i] = S.skip_zero ? ((x[i].x != 0) | ((x[i].y != 0) << 1) | ((x[i].z != 0) << 2) | ((x[i].w != 0) << 3)) : 15u;
+            } else {
+                m[i] = (uint32_t)stat_keep(S, rsz[r], Y, x[i].x) | ((uint32_t)stat_keep(S, rsz[r + 1], Y, x[i].y) << 1) |
+                       ((uint32_t)stat_keep(S, rsz[r + 2], Y, x[i].z) << 2) | ((uint32_t)stat_keep(S, rsz[r + 3], Y, x[i].w) << 3);
+            }
+            kept += __popc(m[i]);
+        }
     } else {
-#pragma unroll 4
-        for (uint32_t j = lane; j < kStatRefsPerBlock; j += 32) {
-            const uint32_t r = r0 + j;
-            if (r < n_ref) kept += stat_keep_t<TRIVIAL>(S, rsz[r], Y, row[r]) ? 1u : 0u;
+        // ragged tail / unaligned rows: lane l holds refs r0 + 32*j + l, bit j of m[j >> 2 ... ] -- simple scalar layout
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            m[i] = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t r = r0 + 32 * (4 * i + c) + lane;
+                if (r < n_ref && stat_keep_t<TRIVIAL>(S, rsz[r], Y, row[r])) m[i] |= 1u << c;
+            }
+            kept += __popc(m[i]);
         }
     }
-    kept = __reduce_add_sync(kFull, kept);
-    if (lane == 0) block_counts[wb] = kept;
-}
-
-template <bool TRIVIAL>
-__global__ void __launch_bounds__(kStatThreads) stats_pairs_kernel(const StatParams S, const uint32_t *__restrict__ ct,
-                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
-                                                                    uint32_t n_ref, uint32_t blocks_per_row, uint64_t n_blocks,
-                                                                    const uint32_t *__restrict__ block_counts,
-                                                                    const uint64_t *__restrict__ block_offsets, uint2 *__restrict__ pairs)
-{
-    const uint64_t wb = ((uint64_t)blockIdx.x * kStatThreads + threadIdx.x) >> 5;
-    if (wb >= n_blocks) return;
-    if (block_counts[wb] == 0) return;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t q = (uint32_t)(wb / blocks_per_row);
-    const uint32_t b = (uint32_t)(wb - (uint64_t)q * blocks_per_row);
-    const uint32_t Y = qsz[q];
-    const uint32_t *row = ct + (uint64_t)q * n_ref;
-    uint64_t running = block_offsets[wb];
-    for (uint32_t j = lane; j < kStatRefsPerBlock; j += 32) {
-        const uint32_t r = b * kStatRefsPerBlock + j;
-        const bool keep = r < n_ref && stat_keep_t<TRIVIAL>(S, rsz[r], Y, row[r]);
-        const uint32_t bal = __ballot_sync(kFull, keep);
-        if (keep) pairs[running + __popc(bal & ((1u << lane) - 1u))] = make_uint2(q, r);
-        running += __popc(bal);
+    const uint32_t total = __reduce_add_sync(kFull, kept);
+    // one atomicAdd per CTA (eight chunks) reserves the room; warps take their share in chunk order
+    __shared__ uint32_t wtot[kStatThreads / 32];
+    __shared__ unsigned long long cta_base;
+    const uint32_t wid = threadIdx.x >> 5;
+    if (lane == 0) wtot[wid] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t sum = 0;
+        for (int w = 0; w < kStatThreads / 32; w++) sum += wtot[w];
+        cta_base = sum ? atomicAdd(cursor, (unsigned long long)sum) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long base = cta_base;
+    for (uint32_t w = 0; w < wid; w++) base += wtot[w];
+    if (lane == 0 && live) {
+        chunk_cnt[wb] = total;
+        chunk_pos[wb] = (uint32_t)base;
+    }
+    if (total == 0 || base + total > cap) return;
+    uint64_t o = base;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t cnt = __popc(m[i]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
+            }
+            uint64_t w = o + incl - cnt;
+            const uint32_t r = r0 + 128 * i + 4 * lane;
+            if (m[i] & 1u) pairs[w++] = make_uint2(q, r);
+            if (m[i] & 2u) pairs[w++] = make_uint2(q, r + 1);
+            if (m[i] & 4u) pairs[w++] = make_uint2(q, r + 2);
+            if (m[i] & 8u) pairs[w++] = make_uint2(q, r + 3);
+            o += __shfl_sync(kFull, incl, 31);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const bool keep = (m[i] >> c) & 1u;
+                const uint32_t bal = __ballot_sync(kFull, keep);
+                if (keep) pairs[o + __popc(bal & ((1u << lane) - 1u))] = make_uint2(q, r0 + 32 * (4 * i + c) + lane);
+                o += __popc(bal);
+            }
     }
 }
 
+// one thread per listed pair evaluates the statistics and stores the row at its print-order position
+// (chunk of the pair -> where that chunk's rows start + rank of the pair inside its chunk)
 __global__ void __launch_bounds__(kStatThreads) stats_rows_kernel(const StatParams S, const uint32_t *__restrict__ ct,
                                                                    const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
-                                                                   uint32_t n_ref, const uint2 *__restrict__ pairs, uint64_t n_rows,
-                                                                   StatRow *__restrict__ rows)
+                                                                   uint32_t n_ref, uint32_t chunks_per_row, const uint32_t *__restrict__ chunk_pos,
+                                                                   const uint64_t *__restrict__ chunk_out, const uint2 *__restrict__ pairs,
+                                                                   uint64_t n_pairs, StatRow *__restrict__ rows)
 {
     const uint64_t i = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
-    if (i >= n_rows) return;
+    if (i >= n_pairs) return;
     const uint2 p = pairs[i];
+    const uint64_t wb = (uint64_t)p.x * chunks_per_row + p.y / kStatRefsPerBlock;
     StatRow out;
     stat_row(S, rsz[p.y], qsz[p.x], ct[(uint64_t)p.x * n_ref + p.y], out);   // kept by construction
     out.qry = p.x; out.ref = p.y;
+    rows[chunk_out[wb] + (i - chunk_pos[wb])] = out;
+}
+
+// every cell is printed (-D >= 1, no skip_zero): rows land at q * R + r directly
+__global__ void __launch_bounds__(kStatThreads) stats_rows_dense_kernel(const StatParams S, const uint32_t *__restrict__ ct,
+                                                                         const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                                         uint32_t n_ref, uint64_t n_cells, StatRow *__restrict__ rows)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
+    if (i >= n_cells) return;
+    const uint32_t q = (uint32_t)(i / n_ref), r = (uint32_t)(i - (uint64_t)q * n_ref);
+    StatRow out;
+    stat_row(S, rsz[r], qsz[q], ct[i], out);
+    out.qry = q; out.ref = r;
     rows[i] = out;
 }
 

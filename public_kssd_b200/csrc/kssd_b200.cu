@@ -856,24 +856,35 @@ extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_
     if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
     kssd_ctx *c = d->ctx;
     CU(cudaSetDevice(c->device));
-    const bool small = d->max_qry_size < 65536u;
-    const uint32_t elem = small ? 2 : 4;
-    // strip width: whole row when it fits in 112 KiB (two CTAs per SM), else equal tiles
-    const uint32_t max_refs = (112u << 10) / elem;
-    const uint32_t n_tiles = ((uint32_t)d->n_ref + max_refs - 1) / max_refs;
-    uint32_t tile = ((uint32_t)d->n_ref + n_tiles - 1) / n_tiles;
-    tile = (tile + 1) & ~1u;
-    const size_t smem = ((size_t)tile * elem + 15) & ~(size_t)15;
-    const uint32_t grid = (uint32_t)d->n_qry * n_tiles;
     CU(cudaEventRecord(c->ev[0], c->stream));
-    if (small) {
-        CU(cudaFuncSetAttribute(dist_count_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dist_count_kernel<uint16_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
-                                                                           tile, n_tiles, d->d_ct, d->components_done > 0);
+    const char *force = getenv("KSSD_DIST_KERNEL");           // "strip" / "rows": A/B switch for profiling
+    const bool rows_fit_l2 = (uint64_t)d->n_ref * 4 * c->sm_count <= (128ull << 20);   // measured fine up to 4 rows per SM in flight
+    const bool use_rows = force ? (strcmp(force, "rows") == 0) : rows_fit_l2;
+    if (use_rows) {
+        const char *rps = getenv("KSSD_DIST_ROWS_PER_SM");
+        const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * (rps ? atoi(rps) : 4));
+        dist_count_rows_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_qry,
+                                                                       (uint32_t)d->n_ref, d->d_ct, d->components_done > 0);
     } else {
-        CU(cudaFuncSetAttribute(dist_count_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dist_count_kernel<uint32_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
-                                                                           tile, n_tiles, d->d_ct, d->components_done > 0);
+        const bool small = d->max_qry_size < 65536u;
+        const uint32_t elem = small ? 2 : 4;
+        // strip width: whole row when it fits in 112 KiB (two CTAs per SM), else equal tiles
+        const char *skb = getenv("KSSD_DIST_STRIP_KB");
+        const uint32_t max_refs = ((skb ? (uint32_t)atoi(skb) : 112u) << 10) / elem;
+        const uint32_t n_tiles = ((uint32_t)d->n_ref + max_refs - 1) / max_refs;
+        uint32_t tile = ((uint32_t)d->n_ref + n_tiles - 1) / n_tiles;
+        tile = (tile + 7) & ~7u;      // strips start 16-byte aligned in the output row
+        const size_t smem = ((size_t)tile * elem + 15) & ~(size_t)15;
+        const uint32_t grid = (uint32_t)d->n_qry * n_tiles;
+        if (small) {
+            CU(cudaFuncSetAttribute(dist_count_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dist_count_kernel<uint16_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
+                                                                               tile, n_tiles, d->d_ct, d->components_done > 0);
+        } else {
+            CU(cudaFuncSetAttribute(dist_count_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dist_count_kernel<uint32_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
+                                                                               tile, n_tiles, d->d_ct, d->components_done > 0);
+        }
     }
     LAUNCHED(1);
     CU(cudaEventRecord(c->ev[1], c->stream));
@@ -949,36 +960,49 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         CU(cudaStreamSynchronize(c->stream));
         cudaFreeAsync(tmp_rows, c->stream);
         d->n_rows = total;
+    } else if (S.dthreshold >= 1.0 && !o->skip_zero) {
+        const uint64_t cells = (uint64_t)d->n_qry * d->n_ref;
+        CU(cudaMallocAsync(&d->d_rows, cells * sizeof(StatRow), c->stream));
+        stats_rows_dense_kernel<<<(uint32_t)((cells + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
+            S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, cells, d->d_rows);
+        LAUNCHED(1);
+        d->n_rows = cells;
     } else {
-        const uint32_t bpr = ((uint32_t)d->n_ref + kStatRefsPerBlock - 1) / kStatRefsPerBlock;
-        const uint64_t nblocks = (uint64_t)bpr * d->n_qry;
-        CU(c->flags.ensure(nblocks * 4));
-        CU(c->pos.ensure((nblocks + 1) * 8));
-        const uint32_t grid = (uint32_t)((nblocks * 32 + kStatThreads - 1) / kStatThreads);
+        const uint32_t cpr = ((uint32_t)d->n_ref + kStatRefsPerBlock - 1) / kStatRefsPerBlock;
+        const uint64_t nchunks = (uint64_t)cpr * d->n_qry;
+        const uint64_t cells = (uint64_t)d->n_qry * d->n_ref;
+        const uint32_t grid = (uint32_t)((nchunks * 32 + kStatThreads - 1) / kStatThreads);
         const bool trivial = S.dthreshold >= 1.0;
-        if (trivial) stats_count_kernel<true><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks, c->flags.as<uint32_t>());
-        else stats_count_kernel<false><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks, c->flags.as<uint32_t>());
-        size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nblocks, c->stream);
-        CU(c->cubtmp.ensure(tmp));
-        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nblocks, c->stream));
-        LAUNCHED(3);
-        uint64_t lastoff = 0;
-        uint32_t lastcnt = 0;
-        CU(cudaMemcpyAsync(&lastoff, c->pos.as<uint64_t>() + (nblocks - 1), 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(&lastcnt, c->flags.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        const uint64_t total = lastoff + lastcnt;
+        CU(c->flags.ensure(nchunks * 4));            // chunk_cnt
+        CU(c->counts.ensure(nchunks * 4));           // chunk_pos
+        CU(c->pos.ensure((nchunks + 1) * 8));        // chunk_out
+        CU(c->misc.ensure(8));
+        uint64_t total = 0;
+        uint64_t cap = std::min<uint64_t>(cells, std::max<uint64_t>(1ull << 24, (uint64_t)d->n_qry * 4096));
+        for (int attempt = 0;; attempt++) {
+            if (cap > 0xffffffffull) return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D / -N");
+            CU(c->keys.ensure(cap * sizeof(uint2)));
+            CU(cudaMemsetAsync(c->misc.p, 0, 8, c->stream));
+            if (trivial) stats_list_kernel<true><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, cpr, nchunks, c->flags.as<uint32_t>(),
+                                                                                     c->counts.as<uint32_t>(), c->misc.as<unsigned long long>(), cap, c->keys.as<uint2>());
+            else stats_list_kernel<false><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, cpr, nchunks, c->flags.as<uint32_t>(),
+                                                                              c->counts.as<uint32_t>(), c->misc.as<unsigned long long>(), cap, c->keys.as<uint2>());
+            LAUNCHED(1);
+            CU(cudaMemcpyAsync(&total, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (total <= cap) break;
+            if (attempt) return fail(KSSD_E_NOMEM, "kssd_dist_stats: pair list overflow");
+            cap = total;
+        }
         CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
         if (total) {
-            CU(c->keys.ensure(total * sizeof(uint2)));
-            if (trivial) stats_pairs_kernel<true><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks,
-                                                                                      c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), c->keys.as<uint2>());
-            else stats_pairs_kernel<false><<<grid, kStatThreads, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, bpr, nblocks,
-                                                                               c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), c->keys.as<uint2>());
+            size_t tmp = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nchunks, c->stream);
+            CU(c->cubtmp.ensure(tmp));
+            CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), nchunks, c->stream));
             stats_rows_kernel<<<(uint32_t)((total + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
-                S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, c->keys.as<uint2>(), total, d->d_rows);
-            LAUNCHED(2);
+                S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, cpr, c->counts.as<uint32_t>(), c->pos.as<uint64_t>(), c->keys.as<uint2>(), total, d->d_rows);
+            LAUNCHED(3);
         }
         d->n_rows = total;
     }
@@ -1008,5 +1032,6 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
     cudaFree(d->d_qsz);
     cudaFree(d->d_rsz);
     if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);
+
     delete d;
 }
