@@ -119,7 +119,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -261,14 +261,13 @@ def main():
         return ctx.sketch_raw(None, nbytes, goff, glen, device_ptr=buf.data_ptr())
 
     # ---- correctness guard inside the bench: a sample of genomes against the oracle (not timed) ----
-    launches0 = L.kssd_kernel_launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()                      # sampled through both timed regions (resident steps and end-to-end steps)
     for _ in range(args.warmup):
         h = sketch_dev()
         L.kssd_sketch_free(h)
     scan_ms = []
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = L.kssd_kernel_launch_count()
     e0.record(stream)
@@ -280,7 +279,6 @@ def main():
         scan_ms.append(ctx.last_ms(0))
     e1.record(stream)
     barrier()
-    clk = clocks.stop()
     gpu_launches = int(L.kssd_kernel_launch_count() - l0)
     step_ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([step_ms], device=dev, dtype=torch.float64)
@@ -298,32 +296,59 @@ def main():
     capi.check(L.kssd_sketch_fetch(sk_h, 0, None, capi.ptr(index_host, capi.C.c_uint64), None, None))
     sizes = np.diff(index_host).astype(np.uint32)
     dist_info = {}
-    ix_ms, ct_ms, st_ms = [], [], []
-    for it in range(3):
-        ixh = capi.C.c_void_p()
-        capi.check(L.kssd_index_build_dev(ctx._h, ids_p, idx_p, args.genomes, n_codes, capi.C.byref(ixh)))
-        ix_ms.append(ctx.last_ms(2))
-        ix = kssd.Index(ctx, ixh)
-        job = kssd.DistJob(ctx, sizes, sizes)
-        job.accumulate_dev(ix, ids_p.value, idx_p.value, n_codes)
-        ct_ms.append(ctx.last_ms(3))
-        nrows = job.stats(fetch=False)
-        st_ms.append(ctx.last_ms(4))
-        if it == 2:
-            ct = job.counts()
-            dist_info["shared_total"] = int(ct.sum(dtype=np.uint64))
-            dist_info["diag_ok"] = bool(np.array_equal(np.diag(ct), sizes))
-            dist_info["rows"] = int(nrows)
-        job.close(); ix.close()
     pairs = args.genomes * args.genomes
     peak, peak_src = peaks()
-    d_ct, d_st, d_ix = float(np.min(ct_ms)), float(np.min(st_ms)), float(np.min(ix_ms))
-    dist_bytes = 4 * n_codes + 8 * n_codes + 4 * dist_info.get("shared_total", 0) + 4 * pairs
-    dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": world * pairs / ((d_ct + d_st) * 1e-3), "count_ms": d_ct,
-                      "stats_ms": d_st, "index_ms": d_ix,
-                      "roofline": {"bound": "hbm", "achieved": dist_bytes / (d_ct * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                   "frac": dist_bytes / (d_ct * 1e-3) / 1e9 / peak, "traffic": None,
-                                   "note": "count kernel; bytes = 4*Nq + 8*Nq + 4*P + 4*Q*R (SURVEY.md s8d)"}})
+    if world == 1:
+        ix_ms, ct_ms, st_ms = [], [], []
+        for it in range(3):
+            ixh = capi.C.c_void_p()
+            capi.check(L.kssd_index_build_dev(ctx._h, ids_p, idx_p, args.genomes, n_codes, capi.C.byref(ixh)))
+            ix_ms.append(ctx.last_ms(2))
+            ix = kssd.Index(ctx, ixh)
+            job = kssd.DistJob(ctx, sizes, sizes)
+            job.accumulate_dev(ix, ids_p.value, idx_p.value, n_codes)
+            ct_ms.append(ctx.last_ms(3))
+            nrows = job.stats(fetch=False)
+            st_ms.append(ctx.last_ms(4))
+            if it == 2:
+                ct = job.counts()
+                dist_info["shared_total"] = int(ct.sum(dtype=np.uint64))
+                dist_info["diag_ok"] = bool(np.array_equal(np.diag(ct), sizes))
+                dist_info["rows"] = int(nrows)
+            job.close(); ix.close()
+        d_ct, d_st, d_ix = float(np.min(ct_ms)), float(np.min(st_ms)), float(np.min(ix_ms))
+        dist_bytes = 4 * n_codes + 8 * n_codes + 4 * dist_info.get("shared_total", 0) + 4 * pairs
+        dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": pairs / ((d_ct + d_st) * 1e-3), "count_ms": d_ct,
+                          "stats_ms": d_st, "index_ms": d_ix, "stats_rows": "all Q*R rows (Jaccard, MashD, P-value, FDR, CIs), fp64",
+                          "roofline": {"bound": "hbm", "achieved": dist_bytes / (d_ct * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": dist_bytes / (d_ct * 1e-3) / 1e9 / peak, "traffic": None,
+                                       "note": "count kernel; bytes = 4*Nq + 8*Nq + 4*P + 4*Q*R (SURVEY.md s8d); 10^6 cells is launch-latency scale -- "
+                                               "profiles/r1_dist_ncu_summary.md has the 10^9-pair run (0.52 of peak)"}})
+    else:
+        # north-star scheme: reference index sharded by code range, queries broadcast, NCCL reduce-scatter of the
+        # partial count matrices; rank 0's sketches serve as reference and query set for every rank
+        from public_kssd_b200 import parallel
+        ids0 = np.empty(n_codes, dtype=np.uint32)
+        capi.check(L.kssd_sketch_fetch(sk_h, 0, capi.ptr(ids0, capi.C.c_uint32), None, None, None))
+        obj = [ids0 if rank == 0 else None, index_host if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ref_ids, ref_index = obj
+        sd = parallel.ShardedDist(ctx, world, rank, code_bits=4 * min(7, K - DRLEVEL)).build_reference(ref_ids, ref_index)
+        times = []
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            lo, hi, block, rows = sd.search(ref_ids if rank == 0 else None, ref_index if rank == 0 else None, src=0, stats_opts={})
+            barrier()
+            times.append(time.perf_counter() - t0)
+        tt = torch.tensor([min(times)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        own = np.diff(ref_index).astype(np.uint32)
+        dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": pairs / float(tt.item()), "ms": float(tt.item()) * 1e3,
+                          "rows_on_rank0": int(len(rows)) if rows is not None else 0,
+                          "diag_ok": bool(np.array_equal(np.diag(block[:, lo:hi]), own[lo:hi])) if hi > lo else True,
+                          "sharding": "reference index by code range across ranks, query sketches broadcast, NCCL reduce-scatter of partial "
+                                      "count matrices, statistics on the owner of each query block (wall clock incl. collectives)"})
 
     # ---- end to end through the C-ABI with host buffers ----
     host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
@@ -355,6 +380,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * bp / float(te.item()) / 1e9
+    clk = clocks.stop()
 
     # the device-resident and host paths must agree with each other
     ids_dev = np.empty(n_codes, dtype=np.uint32)
