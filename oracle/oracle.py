@@ -298,10 +298,17 @@ class RefRun:
         raise RuntimeError(f"reference sketch failed rc={last.returncode}: {last.stderr[-500:]} {last.stdout[-300:]}")
 
     def index(self, sketch_dir, binary=None, p=1):
-        r = run_ref(["dist", "-p", p, "-o", sketch_dir, sketch_dir], cwd=self.dir, binary=binary)
-        if r.returncode != 0 or not (Path(sketch_dir) / "mcofiles.stat").exists():
-            raise RuntimeError(f"reference index failed rc={r.returncode}: {r.stderr[-500:]}")
-        return sketch_dir
+        """Stage II.  combco2mco frees 16^7 never-initialised pointers (co2mco.c:31,70) and sometimes dies in glibc
+        even with one component; a crashed run is retried, then handed to the calloc-patched build (same output)."""
+        last = None
+        for b in ([binary] if binary else [None, None, REF_BIN_MC]):
+            for f in Path(sketch_dir).glob("mco*"):
+                f.unlink()
+            r = run_ref(["dist", "-p", p, "-o", sketch_dir, sketch_dir], cwd=self.dir, binary=b)
+            if r.returncode == 0 and (Path(sketch_dir) / "mcofiles.stat").exists():
+                return sketch_dir
+            last = r
+        raise RuntimeError(f"reference index failed rc={last.returncode}: {last.stderr[-500:]}")
 
     def dist(self, ref_dir, qry_dir, outname, extra=(), p=1):
         out = self.dir / outname

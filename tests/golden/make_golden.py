@@ -107,5 +107,35 @@ def main():
     rr.cleanup()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def tutorial_golden():
+    """BASELINE.json configs[0]: the README quick tutorial on test_fna (seqs1 = refs, seqs2 = queries), L3K10."""
+    import gzip
+    t6 = synth.make_shuf_table(6, cases.SHUF_SEED_S6)
+    rr = O.RefRun(10, 6, 3, t6, shuf_id=cases.SHUF_ID)
+    src = Path("/root/reference/test_fna")
+    ref = rr.sketch(src / "seqs1", "reference", p=4)
+    rr.index(ref)
+    qry = rr.sketch(src / "seqs2", "query", p=4)
+    out = rr.dist(ref, qry, "distout", extra=["--keepskf"])
+    rst, qst = O.read_mcofiles_stat(ref), O.read_cofiles_stat(qry)
+    rc, ri, _ = O.read_combco(ref, 0)
+    qc, qi, _ = O.read_combco(qry, 0)
+    pack = {"ref_names": np.array([Path(n).name for n in rst["names"]]), "qry_names": np.array([Path(n).name for n in qst["names"]]),
+            "ref_ctx_ct": rst["ctx_ct"], "qry_ctx_ct": qst["ctx_ct"],
+            "sharedk_ct": np.fromfile(out / "sharedk_ct.dat", dtype="<u4").reshape(len(qst["names"]), len(rst["names"])),
+            "distance_out": np.frombuffer((out / "distance.out").read_bytes(), dtype=np.uint8)}
+    for i, n in enumerate(pack["ref_names"]):
+        pack[f"ref.{n}"] = np.sort(rc[int(ri[i]):int(ri[i + 1])])
+    for i, n in enumerate(pack["qry_names"]):
+        pack[f"qry.{n}"] = np.sort(qc[int(qi[i]):int(qi[i + 1])])
+    np.savez_compressed(OUT / "tutorial_test_fna_l3k10.npz", **pack)
+    print("tutorial:", len(rc), "ref codes", len(qc), "query codes; ct sum", int(pack["sharedk_ct"].sum()))
+    rr.cleanup()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tutorial":
+    tutorial_golden()
