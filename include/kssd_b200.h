@@ -100,7 +100,8 @@ typedef struct kssd_sketch kssd_sketch_t; /* result handle */
 int kssd_sketch_batch_host(kssd_ctx_t *ctx, const uint8_t *seq, size_t seq_bytes,
                            const uint64_t *goff, const uint64_t *glen, int n_genomes,
                            const kssd_sketch_opts_t *opts, kssd_sketch_t **out);
-/* seq already on the DEVICE (kernel-only path; goff/glen stay on the host). */
+/* seq already on the DEVICE (kernel-only path; goff/glen stay on the host).  seq_dev must be 32-byte aligned and
+ * readable up to the next 16-byte boundary past seq_bytes (any cudaMalloc'ed buffer is). */
 int kssd_sketch_batch_dev(kssd_ctx_t *ctx, const uint8_t *seq_dev, size_t seq_bytes,
                           const uint64_t *goff, const uint64_t *glen, int n_genomes,
                           const kssd_sketch_opts_t *opts, kssd_sketch_t **out);

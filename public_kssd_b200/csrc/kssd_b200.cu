@@ -17,9 +17,19 @@
 #include "../../include/kssd_b200.h"
 #include "index_dist.cuh"
 #include "sketch_fastq.cuh"
-#include "sketch_scan.cuh"
+#include "sketch_scan32.cuh"
 
 using namespace kssd;
+
+// clean-path granularity of the FASTA scan: 32 bytes per lane (sketch_scan32.cuh) or 16 (sketch_scan.cuh)
+#ifndef KSSD_SCAN_LANE_BYTES
+#define KSSD_SCAN_LANE_BYTES 32
+#endif
+#if KSSD_SCAN_LANE_BYTES == 32
+#define KSSD_FASTA_KERNEL sketch_fasta32_kernel
+#else
+#define KSSD_FASTA_KERNEL sketch_fasta_kernel
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // errors, bookkeeping
@@ -196,7 +206,7 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.prefilter = c->d_prefilter;
     P.ht = c->d_ht;
 
-    CU(cudaFuncSetAttribute(sketch_fasta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(KSSD_FASTA_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(kPfWords * 4 + kScanWarps * sizeof(WarpQueue))));
 
     kssd_ctx_info_t &I = c->info;
@@ -371,19 +381,37 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
                         (unsigned long long)goff[g], (unsigned long long)glen[g]);
         total += glen[g];
     }
-    // spans: the unit a warp pulls; sized so that every warp gets several
+    // Spans: the unit a warp pulls from the ticket.  Guided sizes: big spans for the bulk (the per-span start-up --
+    // boundary search, one masked iteration -- is ~3 us), a quarter of that for the last round and a sixteenth for the
+    // last quarter round, so the tail of the dynamic schedule is short.  opts->span_bytes fixes one size (tests).
+    const uint64_t warps = (uint64_t)c->sm_count * kScanWarps;
     uint32_t span = opts ? opts->span_bytes : 0;
-    if (span == 0) {
-        const uint64_t warps = (uint64_t)c->sm_count * kScanWarps;
-        uint64_t want = total / (warps * 6) + 1;
+    const bool guided = span == 0;
+    if (guided) {
+        uint64_t want = total / (warps * 4) + 1;
         span = 4096;
         while (span < want && span < (256u << 10)) span <<= 1;
     }
     if (span < 512 || (span & (span - 1))) return fail(KSSD_E_INVAL, "kssd_sketch_batch: span_bytes must be a power of two >= 512");
     std::vector<uint32_t> span_gid;
     std::vector<uint64_t> span_nom;
-    for (int g = 0; g < n_genomes; g++)
-        for (uint64_t o = 0; o < glen[g]; o += span) { span_gid.push_back((uint32_t)g); span_nom.push_back(goff[g] + o); }
+    {
+        uint64_t remaining = total;
+        const uint64_t round = warps * span;
+        for (int g = 0; g < n_genomes; g++)
+            for (uint64_t o = 0; o < glen[g];) {
+                uint32_t sz = span;
+                if (guided) {
+                    if (remaining <= round / 4) sz = std::max<uint32_t>(span / 16, 4096);
+                    else if (remaining <= round) sz = std::max<uint32_t>(span / 4, 4096);
+                }
+                span_gid.push_back((uint32_t)g);
+                span_nom.push_back(goff[g] + o);
+                const uint64_t step = std::min<uint64_t>(sz, glen[g] - o);
+                o += step;
+                remaining -= step;
+            }
+    }
     const uint32_t n_spans = (uint32_t)span_gid.size();
 
     // device metadata: goff | glen | span_nom | span_gid | gstatus | ticket | out_count
@@ -427,7 +455,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
             if (n_spans) {
-                sketch_fasta_kernel<<<c->sm_count, kScanThreads, kPfWords * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
+                KSSD_FASTA_KERNEL<<<c->sm_count, kScanThreads, kPfWords * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
                 LAUNCHED(1);
             }
         } else {
@@ -532,7 +560,7 @@ extern "C" int kssd_sketch_batch_dev(kssd_ctx_t *c, const uint8_t *seq_dev, size
                                      int n_genomes, const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
 {
     if (!c || !seq_dev || !goff || !glen || !out) return fail(KSSD_E_INVAL, "kssd_sketch_batch_dev: null argument");
-    if (reinterpret_cast<uintptr_t>(seq_dev) & 15) return fail(KSSD_E_INVAL, "kssd_sketch_batch_dev: seq_dev must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(seq_dev) & 31) return fail(KSSD_E_INVAL, "kssd_sketch_batch_dev: seq_dev must be 32-byte aligned");
     CU(cudaSetDevice(c->device));
     return sketch_run(c, seq_dev, seq_bytes, goff, glen, n_genomes, opts, out);
 }

@@ -140,16 +140,32 @@ __device__ __forceinline__ void shl96(uint32_t lo, uint32_t hi, uint32_t s, uint
     r2 = __funnelshift_lc(hi, 0u, s);
 }
 
-// first '\n' at or after nominal-1, searched over at most span_bytes bytes; returns the offset just
-// after it (a span always starts right after a newline, or at the genome start).
-__device__ __forceinline__ uint64_t find_span_start(const uint8_t *seq, uint64_t gs, uint64_t ge, uint64_t nominal,
-                                                    uint32_t span_bytes)
+// A span starts right after the first '\n' at or after nominal-1 (or at the genome start); the search stops at `lim`
+// (the next span's nominal-1, or the genome end).  First probe: 128 bytes at once, four per lane -- enough for any
+// ordinary line width; longer lines take the 32-bytes-per-round loop.
+__device__ __forceinline__ uint64_t find_span_start(const uint8_t *seq, uint64_t gs, uint64_t ge, uint64_t nominal, uint64_t lim)
 {
     if (nominal <= gs) return gs;
     const uint32_t lane = lane_id();
-    uint64_t lim = nominal - 1 + span_bytes;
     if (lim > ge) lim = ge;
-    for (uint64_t p = nominal - 1; p < lim; p += 32) {
+    uint64_t p = nominal - 1;
+    {
+        uint32_t hit = 0;                       // bit j: byte p + 4*lane + j is a newline inside [p, lim)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t a = p + 4 * lane + j;
+            hit |= (uint32_t)(a < lim && seq[a] == '\n') << j;
+        }
+        const uint32_t m = __ballot_sync(kFull, hit != 0);
+        if (m) {
+            const int l = __ffs(m) - 1;
+            const uint32_t h = __shfl_sync(kFull, hit, l);
+            const uint64_t st = p + 4 * l + (__ffs(h) - 1) + 1;
+            return st < ge ? st : kNoSpan;
+        }
+        p += 128;
+    }
+    for (; p < lim; p += 32) {
         const uint64_t a = p + lane;
         const bool nl = (a < lim) && (seq[a] == '\n');
         const uint32_t m = __ballot_sync(kFull, nl);
@@ -159,6 +175,22 @@ __device__ __forceinline__ uint64_t find_span_start(const uint8_t *seq, uint64_t
         }
     }
     return kNoSpan;
+}
+
+// start and end of span `si` (its end is the start of the next non-empty span of the same genome)
+__device__ __forceinline__ bool span_extent(const ScanArgs &A, uint32_t si, uint32_t gid, uint64_t gs, uint64_t ge, uint64_t &start, uint64_t &end)
+{
+    auto next_nom = [&](uint32_t j) -> uint64_t {      // where span j's search must stop
+        return (j + 1 < A.n_spans && A.span_gid[j + 1] == gid) ? A.span_nom[j + 1] - 1 : ge;
+    };
+    start = find_span_start(A.seq, gs, ge, A.span_nom[si], next_nom(si));
+    if (start == kNoSpan) return false;
+    end = ge;
+    for (uint32_t j = si + 1; j < A.n_spans && A.span_gid[j] == gid; j++) {
+        const uint64_t e = find_span_start(A.seq, gs, ge, A.span_nom[j], next_nom(j));
+        if (e != kNoSpan) { end = e; break; }
+    }
+    return true;
 }
 
 // prefilter bit of a 20-bit index; bit order inside a word is reversed (bit 31 - (idx & 31)) so that a
@@ -208,11 +240,12 @@ __device__ __forceinline__ void resolve_candidates(const SketchParams &P, const 
 }
 
 // push the candidates flagged in `cand` (bit d = k-mer ending d valid bases before the lane's newest
-// base); W2:W1:W0 holds the lane's history + own bases, newest base in the low bits.
-// vmask: 0 for the clean path (ord sub-index = 15-d), else the lane's effective-valid byte mask.
+// base); W3:W2:W1:W0 holds the lane's history + own bases, newest base in the low bits.
+// vmask: 0 for a clean lane (ord sub-index = span-1-d, span = 16 or 32 bytes per lane), else the lane's
+// effective-valid byte mask (16-byte general path).
 __device__ __forceinline__ void push_candidates(const SketchParams &P, const ScanArgs &A, WarpQueue &q, uint32_t &qn,
-                                                uint32_t cand, uint32_t n, uint32_t W0, uint32_t W1, uint32_t W2,
-                                                uint32_t lane_off, uint32_t vmask, uint32_t gid, uint64_t ord_base)
+                                                uint32_t cand, uint32_t n, uint32_t W0, uint32_t W1, uint32_t W2, uint32_t W3,
+                                                uint32_t lane_off, uint32_t vmask, uint32_t span, uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
     uint32_t pm = __ballot_sync(kFull, cand != 0);
@@ -221,11 +254,14 @@ __device__ __forceinline__ void push_candidates(const SketchParams &P, const Sca
         if (has) {
             const int d = __ffs(cand) - 1;
             cand &= cand - 1;
-            const uint32_t lo = __funnelshift_r(W0, W1, 2 * d);
-            const uint32_t hi = __funnelshift_r(W1, W2, 2 * d);
+            const bool up = d >= 16;                       // k-mer starts in the upper three words
+            const uint32_t a0 = up ? W1 : W0, a1 = up ? W2 : W1, a2 = up ? W3 : W2;
+            const uint32_t sh = 2 * (d & 15);
+            const uint32_t lo = __funnelshift_r(a0, a1, sh);
+            const uint32_t hi = __funnelshift_r(a1, a2, sh);
             const uint64_t fwd = (((uint64_t)hi << 32) | lo) & P.tupmask;
             uint32_t sub;
-            if (vmask == 0) sub = 15 - d;
+            if (vmask == 0) sub = span - 1 - d;
             else sub = __fns(vmask, 0, (int)(n - d));          // byte index of the (n-d)-th valid base
             const uint32_t slot = qn + __popc(pm & ((1u << lane) - 1u));
             q.lo[slot] = (uint32_t)fwd;
@@ -275,6 +311,116 @@ struct StreamState {
     uint32_t hdr;          // inside a '>' header line
 };
 
+// One 512-byte GENERAL iteration (16 bytes per lane): headers, N, IUPAC, anything.  `cur` is already masked to the
+// span / genome extent, `codes` are its 2-bit codes (byte 0 in the top two bits).  Rare, so kept out of line.
+__device__ __noinline__ void general_iter16(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q, uint32_t &qn,
+                                            StreamState &st, uint4 cur, uint32_t codes, uint64_t cbase, uint64_t end, bool past_end,
+                                            uint32_t lane_off, uint32_t gid, uint64_t ord_base)
+{
+    const uint32_t lane = lane_id();
+    const int TL = P.TL;
+    uint32_t cand = 0, W0, W1, W2, vmask = 0, n;
+    const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+    const uint64_t laddr = cbase + 16 * lane;
+    uint32_t V = 0, NLm = 0, CRm = 0, GTm = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        const uint32_t l = b | 0x20u;
+        V |= (uint32_t)(l == 'a' || l == 'c' || l == 'g' || l == 't') << i;
+        NLm |= (uint32_t)(b == '\n') << i;
+        CRm |= (uint32_t)(b == '\r') << i;
+        GTm |= (uint32_t)(b == '>') << i;
+    }
+    // header state: '>' sets, '\n' clears; carry-propagate through the lane, then across lanes
+    const uint32_t ev = GTm | NLm;
+    const bool has_ev = ev != 0;
+    const bool last_set = has_ev && ((GTm >> (31 - __clz(ev))) & 1u);
+    const uint32_t evS = __ballot_sync(kFull, last_set);
+    const uint32_t evA = __ballot_sync(kFull, has_ev);
+    const uint32_t prev = evA & ((1u << lane) - 1u);
+    const uint32_t h_in = prev ? ((evS >> (31 - __clz(prev))) & 1u) : st.hdr;
+    const uint32_t Aa = ~NLm & 0xffffu, Bb = GTm;
+    const uint32_t sum = Aa + Bb + h_in;
+    const uint32_t hdrmask = (sum ^ Aa ^ Bb) & 0xffffu;      // bit i: byte i lies inside a header
+    st.hdr = __shfl_sync(kFull, (sum >> 16) & 1u, 31);
+    const uint32_t Veff = V & ~hdrmask;
+    const uint32_t BRK = ~(V | NLm | CRm) & ~hdrmask & 0xffffu;
+    vmask = Veff;
+    n = __popc(Veff);
+    // lane summary: bases after the lane's last break (tail) and all effective bases (Pl)
+    uint32_t tb = 0, tn = 0, Pl = 0;
+    bool hb = false;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t c = (codes >> (30 - 2 * i)) & 3u;
+        if ((Veff >> i) & 1u) { tb = (tb << 2) | c; tn++; Pl = (Pl << 2) | c; }
+        else if ((BRK >> i) & 1u) { tb = 0; tn = 0; hb = true; }
+    }
+    // inclusive scan of (bits, n, broke) under "append unless the right part broke"
+    uint64_t sb = tb;
+    uint32_t sn = tn;
+    uint32_t sbrk = hb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t ob = shfl_up64(sb, o);
+        const uint32_t on = __shfl_up_sync(kFull, sn, o);
+        const uint32_t obrk = __shfl_up_sync(kFull, sbrk, o);
+        if (lane >= (uint32_t)o && !sbrk) {
+            if (sn < 32) sb |= ob << (2 * sn);
+            sn = min(sn + on, 32u);
+            sbrk = obrk;
+        }
+    }
+    uint64_t eb = shfl_up64(sb, 1);
+    uint32_t en = __shfl_up_sync(kFull, sn, 1);
+    uint32_t ebrk = __shfl_up_sync(kFull, sbrk, 1);
+    if (lane == 0) { eb = 0; en = 0; ebrk = 0; }
+    uint64_t hist;
+    uint32_t run;
+    if (ebrk) { hist = eb; run = en; }
+    else { hist = (en < 32 ? (st.cw << (2 * en)) : 0ull) | eb; run = min(st.since_break + en, kRunCap); }
+    // valid bases at offsets >= end (run-out accounting)
+    uint32_t gem = 0;
+    if (past_end) {
+        const int64_t rel = (int64_t)end - (int64_t)laddr;
+        gem = rel <= 0 ? 0xffffu : (rel >= 16 ? 0u : (~((1u << rel) - 1u) & 0xffffu));
+    }
+    const uint32_t cge = __popc(Veff & gem);
+    uint32_t ginc = cge;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, ginc, o);
+        if (lane >= (uint32_t)o) ginc += t;
+    }
+    uint32_t ae = st.after_end + ginc - cge;
+    // walk the lane's bytes
+    uint64_t fwd = hist;
+    uint32_t j = 0;   // valid bases consumed in this lane
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if ((Veff >> i) & 1u) {
+            fwd = (fwd << 2) | ((codes >> (30 - 2 * i)) & 3u);
+            run = min(run + 1, kRunCap);
+            ae += (gem >> i) & 1u;
+            j++;
+            if (run >= (uint32_t)TL && ae <= (uint32_t)(TL - 1)) {
+                const uint32_t tmp = (uint32_t)(fwd >> (2 * P.out)) & P.pfmask;
+                if (pf_test_top(pf, tmp) >> 31) cand |= 1u << (n - j);
+            }
+        } else if ((BRK >> i) & 1u) run = 0;
+    }
+    shl96((uint32_t)hist, (uint32_t)(hist >> 32), 2 * n, W0, W1, W2);
+    W0 |= Pl;
+    // warp carry = inclusive value of lane 31 on top of the old carry
+    const uint64_t sb31 = shfl64(sb, 31);
+    const uint32_t sn31 = __shfl_sync(kFull, sn, 31), sbrk31 = __shfl_sync(kFull, sbrk, 31);
+    if (sbrk31) { st.cw = sb31; st.since_break = sn31; }
+    else { st.cw = (sn31 < 32 ? (st.cw << (2 * sn31)) : 0ull) | sb31; st.since_break = min(st.since_break + sn31, kRunCap); }
+    st.after_end += __shfl_sync(kFull, ginc, 31);
+    push_candidates(P, A, q, qn, cand, n, W0, W1, W2, 0u, lane_off, vmask, 16u, gid, ord_base);
+}
+
 // One span: [start, end) of genome [gs, ge); appends occurrences to the output.
 __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q,
                           uint32_t gid, uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
@@ -322,9 +468,8 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
         uint32_t n = 16 - __popc(rsk);
         const bool lane_ok = dacc == 0 && (n >= (uint32_t)P.hist_min_n || cut_lane);
         const bool clean = __all_sync(kFull, lane_ok) && !st.hdr;
-        uint32_t cand = 0, W0, W1, W2, vmask = 0;
-
         if (clean) {
+            uint32_t cand = 0, W0, W1, W2;
             // ---------------- clean iteration: only bases and line ends, no header pending ----------------
             const uint32_t Pl = squeeze_groups(codes, rsk);
             const uint32_t A1 = __shfl_up_sync(kFull, Pl, 1);
@@ -414,109 +559,10 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
             const uint32_t P30 = __shfl_sync(kFull, Pl, 30), P31 = __shfl_sync(kFull, Pl, 31);
             const uint32_t n31 = __shfl_sync(kFull, n, 31);
             st.cw = ((uint64_t)P30 << (2 * n31)) | P31;
+            push_candidates(P, A, q, qn, cand, n, W0, W1, W2, 0u, lane_off, 0u, 16u, gid, ord_base);
         } else {
-            // ---------------- general iteration: headers, N, IUPAC, anything ----------------
-            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-            const uint64_t laddr = cbase + 16 * lane;
-            uint32_t V = 0, NLm = 0, CRm = 0, GTm = 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                const uint32_t l = b | 0x20u;
-                V |= (uint32_t)(l == 'a' || l == 'c' || l == 'g' || l == 't') << i;
-                NLm |= (uint32_t)(b == '\n') << i;
-                CRm |= (uint32_t)(b == '\r') << i;
-                GTm |= (uint32_t)(b == '>') << i;
-            }
-            // header state: '>' sets, '\n' clears; carry-propagate through the lane, then across lanes
-            const uint32_t ev = GTm | NLm;
-            const bool has_ev = ev != 0;
-            const bool last_set = has_ev && ((GTm >> (31 - __clz(ev))) & 1u);
-            const uint32_t evS = __ballot_sync(kFull, last_set);
-            const uint32_t evA = __ballot_sync(kFull, has_ev);
-            const uint32_t prev = evA & ((1u << lane) - 1u);
-            const uint32_t h_in = prev ? ((evS >> (31 - __clz(prev))) & 1u) : st.hdr;
-            const uint32_t Aa = ~NLm & 0xffffu, Bb = GTm;
-            const uint32_t sum = Aa + Bb + h_in;
-            const uint32_t hdrmask = (sum ^ Aa ^ Bb) & 0xffffu;      // bit i: byte i lies inside a header
-            st.hdr = __shfl_sync(kFull, (sum >> 16) & 1u, 31);
-            const uint32_t Veff = V & ~hdrmask;
-            const uint32_t BRK = ~(V | NLm | CRm) & ~hdrmask & 0xffffu;
-            vmask = Veff;
-            n = __popc(Veff);
-            // lane summary: bases after the lane's last break (tail) and all effective bases (Pl)
-            uint32_t tb = 0, tn = 0, Pl = 0;
-            bool hb = false;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t c = (codes >> (30 - 2 * i)) & 3u;
-                if ((Veff >> i) & 1u) { tb = (tb << 2) | c; tn++; Pl = (Pl << 2) | c; }
-                else if ((BRK >> i) & 1u) { tb = 0; tn = 0; hb = true; }
-            }
-            // inclusive scan of (bits, n, broke) under "append unless the right part broke"
-            uint64_t sb = tb;
-            uint32_t sn = tn;
-            uint32_t sbrk = hb;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t ob = shfl_up64(sb, o);
-                const uint32_t on = __shfl_up_sync(kFull, sn, o);
-                const uint32_t obrk = __shfl_up_sync(kFull, sbrk, o);
-                if (lane >= (uint32_t)o && !sbrk) {
-                    if (sn < 32) sb |= ob << (2 * sn);
-                    sn = min(sn + on, 32u);
-                    sbrk = obrk;
-                }
-            }
-            uint64_t eb = shfl_up64(sb, 1);
-            uint32_t en = __shfl_up_sync(kFull, sn, 1);
-            uint32_t ebrk = __shfl_up_sync(kFull, sbrk, 1);
-            if (lane == 0) { eb = 0; en = 0; ebrk = 0; }
-            uint64_t hist;
-            uint32_t run;
-            if (ebrk) { hist = eb; run = en; }
-            else { hist = (en < 32 ? (st.cw << (2 * en)) : 0ull) | eb; run = min(st.since_break + en, kRunCap); }
-            // valid bases at offsets >= end (run-out accounting)
-            uint32_t gem = 0;
-            if (past_end) {
-                const int64_t rel = (int64_t)end - (int64_t)laddr;
-                gem = rel <= 0 ? 0xffffu : (rel >= 16 ? 0u : (~((1u << rel) - 1u) & 0xffffu));
-            }
-            const uint32_t cge = __popc(Veff & gem);
-            uint32_t ginc = cge;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, ginc, o);
-                if (lane >= (uint32_t)o) ginc += t;
-            }
-            uint32_t ae = st.after_end + ginc - cge;
-            // walk the lane's bytes
-            uint64_t fwd = hist;
-            uint32_t j = 0;   // valid bases consumed in this lane
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if ((Veff >> i) & 1u) {
-                    fwd = (fwd << 2) | ((codes >> (30 - 2 * i)) & 3u);
-                    run = min(run + 1, kRunCap);
-                    ae += (gem >> i) & 1u;
-                    j++;
-                    if (run >= (uint32_t)TL && ae <= (uint32_t)(TL - 1)) {
-                        const uint32_t tmp = (uint32_t)(fwd >> (2 * P.out)) & P.pfmask;
-                        if (pf_test_top(pf, tmp) >> 31) cand |= 1u << (n - j);
-                    }
-                } else if ((BRK >> i) & 1u) run = 0;
-            }
-            shl96((uint32_t)hist, (uint32_t)(hist >> 32), 2 * n, W0, W1, W2);
-            W0 |= Pl;
-            // warp carry = inclusive value of lane 31 on top of the old carry
-            const uint64_t sb31 = shfl64(sb, 31);
-            const uint32_t sn31 = __shfl_sync(kFull, sn, 31), sbrk31 = __shfl_sync(kFull, sbrk, 31);
-            if (sbrk31) { st.cw = sb31; st.since_break = sn31; }
-            else { st.cw = (sn31 < 32 ? (st.cw << (2 * sn31)) : 0ull) | sb31; st.since_break = min(st.since_break + sn31, kRunCap); }
-            st.after_end += __shfl_sync(kFull, ginc, 31);
+            general_iter16(P, A, pf, q, qn, st, cur, codes, cbase, end, past_end, lane_off, gid, ord_base);
         }
-
-        push_candidates(P, A, q, qn, cand, n, W0, W1, W2, lane_off, vmask, gid, ord_base);
 
         if (!steady) {
             if (cbase + 512 >= ge) { at_eof = true; break; }    // genome exhausted
@@ -549,13 +595,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta_kernel(const Ske
         if (si >= A.n_spans) break;
         const uint32_t gid = A.span_gid[si];
         const uint64_t gs = A.goff[gid], ge = gs + A.glen[gid];
-        const uint64_t start = find_span_start(A.seq, gs, ge, A.span_nom[si], A.span_bytes);
-        if (start == kNoSpan) continue;
-        uint64_t end = ge;
-        for (uint32_t j = si + 1; j < A.n_spans && A.span_gid[j] == gid; j++) {
-            const uint64_t e = find_span_start(A.seq, gs, ge, A.span_nom[j], A.span_bytes);
-            if (e != kNoSpan) { end = e; break; }
-        }
+        uint64_t start, end;
+        if (!span_extent(A, si, gid, gs, ge, start, end)) continue;
         scan_span(P, A, pf, q, gid, gs, ge, start, end);
     }
 }
