@@ -112,16 +112,26 @@ __global__ void count_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t 
 }
 
 // S = {d : shuf[d] < dim_end}: exact hash table d -> pf, and the prefilter bitmap of S u RC(S)
-__global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t n, uint32_t dim_end, int s, uint32_t pfmask,
+__global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t n, uint32_t dim_end, int s,
                                      uint32_t *__restrict__ prefilter, uint2 *__restrict__ ht, uint32_t ht_mask)
 {
+    const int wbits = 4 * s;                                   // width of the inner 2s-mer
+    const uint32_t reps = wbits < kPfBitShift + 5 ? 1u << (kPfBitShift + 5 - wbits) : 1u;
     for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
         const int32_t v = shuf[d];
         if (v < 0 || (uint32_t)v >= dim_end) continue;
-        const uint32_t a = d & pfmask;
-        const uint32_t b = (uint32_t)revcomp2((uint64_t)d, 2 * s) & pfmask;
-        atomicOr(&prefilter[a >> 5], 0x80000000u >> (a & 31));   // reversed bit order, see pf_test_top()
-        atomicOr(&prefilter[b >> 5], 0x80000000u >> (b & 31));
+        const uint32_t both[2] = {d, (uint32_t)revcomp2((uint64_t)d, 2 * s)};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            // first level (layout in kssd_device.cuh); probes may carry bases beyond the window in bits >= 4s,
+            // so a narrow window is entered under every value of those bits
+            for (uint32_t hi = 0; hi < reps; hi++) {
+                const uint32_t x = both[k] | (hi << wbits);
+                atomicOr(&prefilter[x & kPfWordMask], 0x80000000u >> ((x >> kPfBitShift) & 31));
+            }
+            const uint32_t i2 = pf2_index(both[k]);
+            atomicOr(&prefilter[kPfWords + (i2 >> 5)], 1u << (i2 & 31));
+        }
         uint32_t h = mix32(d) & ht_mask;
         for (;;) {
             const uint32_t old = atomicCAS(&ht[h].x, kHtEmpty, d);
@@ -170,8 +180,6 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.undomask = ((1ull << (2 * P.out)) - 1ull) << (2 * (k + subk));
     P.outmask = (1ull << (2 * P.out)) - 1ull;
     P.innermask = (uint32_t)((1ull << (4 * subk)) - 1ull);
-    P.pfmask = std::min<uint32_t>(P.innermask, (1u << kPfBits) - 1u);
-    P.pf_amask = (P.pfmask >> 5) << 2;
     const uint64_t subspace = 1ull << (4 * (subk - drlevel));
     P.dim_end = (uint32_t)std::max<uint64_t>(subspace, 4096);   // MIN_SUBCTX_DIM_SMP_SZ
     P.comp_code_bits = (k - drlevel > component_sz) ? 4 * (k - drlevel - component_sz) : 0;
@@ -192,11 +200,11 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     uint32_t ht_size = 1024;
     while (ht_size < 2 * (uint64_t)n_sampled + 16) ht_size <<= 1;
     P.ht_mask = ht_size - 1;
-    CU(cudaMalloc(&c->d_prefilter, kPfWords * 4));
+    CU(cudaMalloc(&c->d_prefilter, (kPfWords + kPf2Words) * 4));
     CU(cudaMalloc(&c->d_ht, (size_t)ht_size * sizeof(uint2)));
-    CU(cudaMemsetAsync(c->d_prefilter, 0, kPfWords * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_prefilter, 0, (kPfWords + kPf2Words) * 4, c->stream));
     CU(cudaMemsetAsync(c->d_ht, 0xff, (size_t)ht_size * sizeof(uint2), c->stream));
-    build_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, subk, P.pfmask, c->d_prefilter, c->d_ht,
+    build_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, subk, c->d_prefilter, c->d_ht,
                                                                 P.ht_mask);
     LAUNCHED(1);
     CU(cudaStreamSynchronize(c->stream));
@@ -207,7 +215,7 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.ht = c->d_ht;
 
     CU(cudaFuncSetAttribute(KSSD_FASTA_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(kPfWords * 4 + kScanWarps * sizeof(WarpQueue))));
+                            (int)((kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue))));
 
     kssd_ctx_info_t &I = c->info;
     I.k = k; I.subk = subk; I.drlevel = drlevel; I.component_sz = component_sz;
@@ -455,7 +463,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
             if (n_spans) {
-                KSSD_FASTA_KERNEL<<<c->sm_count, kScanThreads, kPfWords * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
+                KSSD_FASTA_KERNEL<<<c->sm_count, kScanThreads, (kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
                 LAUNCHED(1);
             }
         } else {

@@ -16,6 +16,17 @@ constexpr uint32_t kFull = 0xffffffffu;
 // 2s-mer.  128 KiB -- it lives in shared memory of the one persistent CTA per SM.
 constexpr int kPfBits = 20;
 constexpr uint32_t kPfWords = 1u << (kPfBits - 5);
+// Bit layout of the prefilter for a window value v (the central 2s-mer in the low bits of v):
+//   word = v & 0x7fff (bits 0..14),  bit = 31 - ((v >> 16) & 31) (bits 16..20, reversed so that a left funnel
+//   shift by v >> 16 brings the flag to bit 31).  Bit 15 is skipped on purpose: with t[e] = X >> 2e the word offset
+//   of window d is t[d-1] & 0x1fffc and its shift amount is t[d+8] -- one funnel shift per window serves both.
+constexpr uint32_t kPfWordMask = 0x7fffu;
+constexpr int kPfBitShift = 16;
+// Second-level filter (same set, independent hash of the whole window): 2^17 bits, consulted only for the ~1/128
+// windows that pass the first level, so that only ~1/2000 reach the exact path.
+constexpr uint32_t kPf2Words = 1u << 12;
+
+__host__ __device__ __forceinline__ uint32_t pf2_index(uint32_t inner) { return (inner * 0x9E3779B1u) >> 15; }
 
 constexpr uint32_t kHtEmpty = 0xffffffffu;
 
@@ -30,13 +41,11 @@ struct SketchParams {
     uint64_t undomask;   // left outer bases of the canonical k-mer
     uint64_t outmask;    // right outer bases (low 2*out bits)
     uint32_t innermask;  // low 4s bits
-    uint32_t pfmask;     // min(innermask, 2^20-1)
-    uint32_t pf_amask;   // (pfmask >> 5) << 2: byte offset mask of the bitmap word
     uint32_t dim_end;
     int comp_code_bits;
     uint32_t comp_mask;  // component_num - 1
     uint32_t ht_mask;    // sampled-set hash table size - 1
-    const uint32_t *prefilter;  // kPfWords words (global copy)
+    const uint32_t *prefilter;  // kPfWords words (global copy), then kPf2Words words of the second level
     const uint2 *ht;            // {inner, pf}
 };
 

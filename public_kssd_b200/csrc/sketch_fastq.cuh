@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
             const uint32_t t = (b >> 1) & 3u;
             fwd = (fwd << 2) | (t ^ (t >> 1));
             if (++run < (uint32_t)TL) continue;
-            const uint32_t idx = (uint32_t)(fwd >> (2 * P.out)) & P.pfmask;
-            if (!((pf[idx >> 5] << (idx & 31)) >> 31)) continue;
+            const uint32_t v = (uint32_t)(fwd >> (2 * P.out));
+            if (!(__funnelshift_l(0u, pf[v & kPfWordMask], v >> kPfBitShift) >> 31)) continue;
             // exact resolution (rare)
             const uint64_t kmer = fwd & P.tupmask;
             const uint64_t rc = revcomp2(kmer, TL);

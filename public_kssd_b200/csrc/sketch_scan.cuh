@@ -193,11 +193,16 @@ __device__ __forceinline__ bool span_extent(const ScanArgs &A, uint32_t si, uint
     return true;
 }
 
-// prefilter bit of a 20-bit index; bit order inside a word is reversed (bit 31 - (idx & 31)) so that a
-// left shift by the low index bits (funnel shift, wrap mode) brings the flag to bit 31
-__device__ __forceinline__ uint32_t pf_test_top(const uint32_t *__restrict__ pf, uint32_t idx)
+// first-level prefilter probe of a window value v (layout in kssd_device.cuh); returns the flag in bit 31
+__device__ __forceinline__ uint32_t pf_probe(const uint32_t *__restrict__ pf, uint32_t v)
 {
-    return __funnelshift_l(0u, pf[idx >> 5], idx);
+    return __funnelshift_l(0u, pf[v & kPfWordMask], v >> kPfBitShift);
+}
+// second-level probe of the exact inner 2s-mer
+__device__ __forceinline__ bool pf2_probe(const uint32_t *__restrict__ pf, uint32_t inner)
+{
+    const uint32_t i = pf2_index(inner);
+    return (pf[kPfWords + (i >> 5)] >> (i & 31)) & 1u;
 }
 
 // ---- exact resolution of queued candidates (dense: up to 32 at a time) ----
@@ -243,22 +248,28 @@ __device__ __forceinline__ void resolve_candidates(const SketchParams &P, const 
 // base); W3:W2:W1:W0 holds the lane's history + own bases, newest base in the low bits.
 // vmask: 0 for a clean lane (ord sub-index = span-1-d, span = 16 or 32 bytes per lane), else the lane's
 // effective-valid byte mask (16-byte general path).
-__device__ __forceinline__ void push_candidates(const SketchParams &P, const ScanArgs &A, WarpQueue &q, uint32_t &qn,
-                                                uint32_t cand, uint32_t n, uint32_t W0, uint32_t W1, uint32_t W2, uint32_t W3,
+__device__ __forceinline__ void push_candidates(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q,
+                                                uint32_t &qn, uint32_t cand, uint32_t n, uint32_t W0, uint32_t W1, uint32_t W2, uint32_t W3,
                                                 uint32_t lane_off, uint32_t vmask, uint32_t span, uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
-    uint32_t pm = __ballot_sync(kFull, cand != 0);
-    while (pm) {
-        const bool has = cand != 0;
+    while (__any_sync(kFull, cand != 0)) {
+        bool has = cand != 0;
+        int d = 0;
+        uint32_t lo = 0, hi = 0;
         if (has) {
-            const int d = __ffs(cand) - 1;
+            d = __ffs(cand) - 1;
             cand &= cand - 1;
             const bool up = d >= 16;                       // k-mer starts in the upper three words
             const uint32_t a0 = up ? W1 : W0, a1 = up ? W2 : W1, a2 = up ? W3 : W2;
             const uint32_t sh = 2 * (d & 15);
-            const uint32_t lo = __funnelshift_r(a0, a1, sh);
-            const uint32_t hi = __funnelshift_r(a1, a2, sh);
+            lo = __funnelshift_r(a0, a1, sh);
+            hi = __funnelshift_r(a1, a2, sh);
+            // second-level filter on the forward inner 2s-mer: 15 of 16 first-level hits stop here
+            has = pf2_probe(pf, __funnelshift_r(lo, hi, 2 * P.out) & P.innermask);
+        }
+        const uint32_t pm = __ballot_sync(kFull, has);
+        if (has) {
             const uint64_t fwd = (((uint64_t)hi << 32) | lo) & P.tupmask;
             uint32_t sub;
             if (vmask == 0) sub = span - 1 - d;
@@ -275,7 +286,6 @@ __device__ __forceinline__ void push_candidates(const SketchParams &P, const Sca
             qn -= 32;
             __syncwarp();
         }
-        pm = __ballot_sync(kFull, cand != 0);
     }
 }
 
@@ -405,8 +415,7 @@ __device__ __noinline__ void general_iter16(const SketchParams &P, const ScanArg
             ae += (gem >> i) & 1u;
             j++;
             if (run >= (uint32_t)TL && ae <= (uint32_t)(TL - 1)) {
-                const uint32_t tmp = (uint32_t)(fwd >> (2 * P.out)) & P.pfmask;
-                if (pf_test_top(pf, tmp) >> 31) cand |= 1u << (n - j);
+                if (pf_probe(pf, (uint32_t)(fwd >> (2 * P.out))) >> 31) cand |= 1u << (n - j);
             }
         } else if ((BRK >> i) & 1u) run = 0;
     }
@@ -418,7 +427,7 @@ __device__ __noinline__ void general_iter16(const SketchParams &P, const ScanArg
     if (sbrk31) { st.cw = sb31; st.since_break = sn31; }
     else { st.cw = (sn31 < 32 ? (st.cw << (2 * sn31)) : 0ull) | sb31; st.since_break = min(st.since_break + sn31, kRunCap); }
     st.after_end += __shfl_sync(kFull, ginc, 31);
-    push_candidates(P, A, q, qn, cand, n, W0, W1, W2, 0u, lane_off, vmask, 16u, gid, ord_base);
+    push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, 0u, lane_off, vmask, 16u, gid, ord_base);
 }
 
 // One span: [start, end) of genome [gs, ge); appends occurrences to the output.
@@ -490,33 +499,14 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
             // prefilter on the central 2s-mer of the k-mer ending at each own base (d = distance from the newest)
             const uint32_t Xlo = __funnelshift_r(W0, W1, 2 * P.out);
             const uint32_t Xhi = __funnelshift_r(W1, W2, 2 * P.out);
-#if KSSD_MULHI_T
-            // every 20-bit window lies inside one of three 32-bit views of X, so the per-window shift can be a
-            // mul.hi by a power of two (FMA pipe) instead of a funnel shift (ALU pipe)
-            const uint32_t X1 = __funnelshift_r(Xlo, Xhi, 12);
-            const uint32_t X2 = __funnelshift_r(Xlo, Xhi, 24);
-#endif
+            // t(e) = X >> 2e; window d reads the word at t(d-1) & 0x1fffc and shifts it by t(d+8) (layout in kssd_device.cuh)
+            auto tsh = [&](int e) -> uint32_t {
+                return e < 0 ? (Xlo << 2) : (e < 16 ? __funnelshift_r(Xlo, Xhi, 2 * e) : (Xhi >> (2 * e - 32)));
+            };
 #pragma unroll
             for (int d = 15; d >= 0; d--) {
-#if KSSD_MULHI_T
-                const uint32_t view = d < 6 ? Xlo : (d < 12 ? X1 : X2);
-                const int off = d < 6 ? 2 * d : (d < 12 ? 2 * d - 12 : 2 * d - 24);
-                const uint32_t t = off ? __umulhi(view, 1u << (32 - off)) : view;
-#else
-                const uint32_t t = __funnelshift_r(Xlo, Xhi, 2 * d);
-#endif
-                // byte offset of the bitmap word: (t >> 3) & amask
-#if KSSD_MULHI_ADDR
-                const uint32_t boff = __umulhi(t, 0x20000000u) & P.pf_amask;
-#else
-                const uint32_t boff = (t >> 3) & P.pf_amask;
-#endif
-                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + boff);
-#if KSSD_MULHI_ACC
-                cand = cand * 2u + __umulhi(__funnelshift_l(0u, word, t), 2u);      // cand = cand << 1 | flag
-#else
-                cand = __funnelshift_l(__funnelshift_l(0u, word, t), cand, 1);      // cand = cand << 1 | flag
-#endif
+                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (tsh(d - 1) & (kPfWordMask << 2)));
+                cand = __funnelshift_l(__funnelshift_l(0u, word, tsh(d + 8)), cand, 1);      // cand = cand << 1 | flag
             }
             cand &= (1u << n) - 1u;
 
@@ -559,7 +549,7 @@ __device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32
             const uint32_t P30 = __shfl_sync(kFull, Pl, 30), P31 = __shfl_sync(kFull, Pl, 31);
             const uint32_t n31 = __shfl_sync(kFull, n, 31);
             st.cw = ((uint64_t)P30 << (2 * n31)) | P31;
-            push_candidates(P, A, q, qn, cand, n, W0, W1, W2, 0u, lane_off, 0u, 16u, gid, ord_base);
+            push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, 0u, lane_off, 0u, 16u, gid, ord_base);
         } else {
             general_iter16(P, A, pf, q, qn, st, cur, codes, cbase, end, past_end, lane_off, gid, ord_base);
         }
@@ -579,11 +569,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta_kernel(const Ske
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
-    WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + kPfWords * 4);
-    {   // stage the prefilter bitmap (L2 -> shared), 16 B per thread per step
+    WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + (kPfWords + kPf2Words) * 4);
+    {   // stage both prefilter levels (L2 -> shared), 16 B per thread per step
         const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);
-        for (uint32_t i = threadIdx.x; i < kPfWords / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        for (uint32_t i = threadIdx.x; i < (kPfWords + kPf2Words) / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
     }
     __syncthreads();
     WarpQueue &q = queues[threadIdx.x >> 5];

@@ -128,12 +128,14 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
             const uint32_t X1 = __funnelshift_r(W1, W2, 2 * P.out);
             const uint32_t X2 = __funnelshift_r(W2, W3, 2 * P.out);
             uint32_t cand = 0;
+            // t(e) = X >> 2e; window d reads the word at t(d-1) & 0x1fffc and shifts it by t(d+8) (layout in kssd_device.cuh)
+            auto tsh = [&](int e) -> uint32_t {
+                return e < 0 ? (X0 << 2) : (e < 16 ? __funnelshift_r(X0, X1, 2 * e) : (e < 32 ? __funnelshift_r(X1, X2, 2 * e - 32) : (X2 >> (2 * e - 64))));
+            };
 #pragma unroll
             for (int d = 31; d >= 0; d--) {
-                const uint32_t t = d < 16 ? __funnelshift_r(X0, X1, 2 * d) : __funnelshift_r(X1, X2, 2 * (d - 16));
-                const uint32_t boff = (t >> 3) & P.pf_amask;
-                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + boff);
-                cand = __funnelshift_l(__funnelshift_l(0u, word, t), cand, 1);      // cand = cand << 1 | flag
+                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (tsh(d - 1) & (kPfWordMask << 2)));
+                cand = __funnelshift_l(__funnelshift_l(0u, word, tsh(d + 8)), cand, 1);      // cand = cand << 1 | flag
             }
             cand &= low_mask((int)n);
 
@@ -174,7 +176,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
             }
             st.since_break = min(st.since_break + N, kRunCap);
             st.cw = ((uint64_t)__shfl_sync(kFull, P1, 31) << 32) | __shfl_sync(kFull, P0, 31);
-            push_candidates(P, A, q, qn, cand, n, W0, W1, W2, W3, lane_off, 0u, 32u, gid, ord_base);
+            push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, W3, lane_off, 0u, 32u, gid, ord_base);
         } else {
             // two general 512-byte iterations with the 16-byte lane mapping (reloaded: L1/L2 hits)
 #pragma unroll 1
@@ -210,11 +212,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta32_kernel(const S
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
-    WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + kPfWords * 4);
+    WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + (kPfWords + kPf2Words) * 4);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);
-        for (uint32_t i = threadIdx.x; i < kPfWords / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        for (uint32_t i = threadIdx.x; i < (kPfWords + kPf2Words) / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
     }
     __syncthreads();
     WarpQueue &q = queues[threadIdx.x >> 5];
