@@ -391,7 +391,7 @@ def main():
     scan = float(np.median(scan_ms))
     roof = {"bound": "hbm", "achieved": text_bytes / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": text_bytes / (scan * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-            "kernel": "sketch_fasta_kernel", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
+            "kernel": "sketch_fasta32_kernel", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -135,7 +135,11 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
 #pragma unroll
             for (int d = 31; d >= 0; d--) {
                 const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (tsh(d - 1) & (kPfWordMask << 2)));
+#if KSSD_MULHI_ACC
+                cand = cand * 2u + __umulhi(__funnelshift_l(0u, word, tsh(d + 8)), 2u);      // same, through the FMA pipe
+#else
                 cand = __funnelshift_l(__funnelshift_l(0u, word, tsh(d + 8)), cand, 1);      // cand = cand << 1 | flag
+#endif
             }
             cand &= low_mask((int)n);
 
