@@ -137,3 +137,59 @@ def format_stat_rows(rows, qry_names, ref_names, metric: int = 0, outfields: int
             s += "\t[%s,%s]\t[%s,%s]" % tuple(_c_double(float(r[n]), "f") for n in ("ci_metric_lo", "ci_metric_hi", "ci_dist_lo", "ci_dist_hi"))
         out.append(s + "\n")
     return "".join(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# sketch directories: what run_stageI leaves behind, and combine_queries (command_dist.c:1323-1475)
+# ------------------------------------------------------------------------------------------------
+def write_sketch_dir(d, shuf_id: int, k: int, drlevel: int, sketch, names, koc: bool = False) -> None:
+    """cofiles.stat + combco.<c> + combco.index.<c> (+ combco.<c>.a) from a kssd.Sketch (run_stageI's output,
+    command_dist.c:314-378).  Genome order is the order of `names` (the reference shuffles its own)."""
+    d = Path(d)
+    d.mkdir(parents=True, exist_ok=True)
+    for c in range(len(sketch.ids)):
+        write_combco(d, c, sketch.ids[c], sketch.index[c], sketch.abund[c] if koc else None)
+    write_cofiles_stat(d, shuf_id, koc, 2 * k, 2 * drlevel, len(sketch.ids), sketch.ctx_ct(), names)
+
+
+def combine_queries(dirs, out) -> dict:
+    """Concatenate sketch directories that share a shuf_id into `out`, as `kssd dist -o out dirA dirB ...` does:
+    combco.<c> appended, combco.index.<c> rebased, ctx_ct lists and names appended, header counts summed.
+    Directories with another shuf_id or with abundances are skipped with a message, like the reference."""
+    out = Path(out)
+    out.mkdir(parents=True, exist_ok=True)
+    first = read_cofiles_stat(dirs[0])
+    if first["koc"]:
+        raise ValueError("combine_queries(): abundance model not supported yet")
+    comp = first["comp_num"]
+    cts, names = [first["ctx_ct"]], list(first["names"])
+    all_ctx = first["all_ctx_ct"]
+    codes = [[read_combco(dirs[0], c)[0]] for c in range(comp)]
+    index = [[read_combco(dirs[0], c)[1]] for c in range(comp)]
+    for i, dq in enumerate(dirs[1:], start=1):
+        try:
+            st = read_cofiles_stat(dq)
+        except FileNotFoundError:
+            print(f"{i}th query {dq} is not a valid query: no cofiles.stat file")
+            continue
+        if st["shuf_id"] != first["shuf_id"]:
+            print(f"combine_queries(): {i}th shuf_id: {st['shuf_id']} not match 0th shuf_id: {first['shuf_id']}")
+            continue
+        if st["koc"]:
+            print(f"combine_queries(): {i}th query abundance model not supported yet ")
+            continue
+        all_ctx += st["all_ctx_ct"]
+        cts.append(st["ctx_ct"])
+        names += st["names"]
+        for c in range(comp):
+            ids, ix, _ = read_combco(dq, c)
+            codes[c].append(ids)
+            index[c].append(ix[1:] + index[c][-1][-1])
+    ct = np.concatenate(cts)
+    for c in range(comp):
+        write_combco(out, c, np.concatenate(codes[c]), np.concatenate(index[c]))
+    with open(out / "cofiles.stat", "wb") as f:
+        f.write(struct.pack("<I?xxxiiiiQ", first["shuf_id"], False, first["kmerlen"], first["dim_rd_len"], comp, len(names), int(all_ctx)))
+        f.write(np.ascontiguousarray(ct, dtype="<u4").tobytes())
+        f.write(_names_block(names))
+    return read_cofiles_stat(out)

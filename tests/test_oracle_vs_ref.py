@@ -51,3 +51,30 @@ def test_fastq_live(ref, shuf_s5):
     inputs = {"a": synth.to_fastq(src, 3000, 100, seed=202), "b": synth.to_fastq(src, 500, 151, seed=203, trailing_newline=False)}
     _run_case(ref, 8, 5, 2, shuf_s5, inputs, "fq", ["-Q", "45", "-n", "2"], lambda c, b: c.fastq(b, 45, 2))
     _run_case(ref, 8, 5, 2, shuf_s5, inputs, "fq", ["-A"], lambda c, b: c.fastq_abund(b))
+
+
+def test_combine_queries_matches_reference(ref, shuf_s5, tmp_path):
+    """hostfmt.combine_queries vs `kssd dist -o combined dirA dirB` (command_dist.c:1323-1475)."""
+    from public_kssd_b200 import hostfmt
+    O = ref
+    rr = O.RefRun(8, 5, 2, shuf_s5, shuf_id=99)
+    try:
+        dirs = []
+        for j, seeds in enumerate([(1, 2, 3), (4, 5)]):
+            d = rr.dir / f"in{j}"
+            d.mkdir()
+            for s in seeds:
+                (d / f"g{s}.fasta").write_bytes(synth.messy_fasta(60_000 + 999 * s, 300 + s).tobytes())
+            dirs.append(rr.sketch(d, f"sk{j}", p=1))
+        comb = rr.dir / "combined"
+        r = O.run_ref(["dist", "-p", 1, "-o", comb, dirs[0], dirs[1]], cwd=rr.dir)
+        assert r.returncode == 0 and (comb / "cofiles.stat").exists(), r.stderr[-300:]
+        mine = tmp_path / "mine"
+        st = hostfmt.combine_queries(dirs, mine)
+        want = hostfmt.read_cofiles_stat(comb)
+        assert st["infile_num"] == want["infile_num"] == 5 and st["all_ctx_ct"] == want["all_ctx_ct"]
+        assert np.array_equal(st["ctx_ct"], want["ctx_ct"]) and st["names"] == want["names"]
+        assert (mine / "combco.0").read_bytes() == (comb / "combco.0").read_bytes()
+        assert (mine / "combco.index.0").read_bytes() == (comb / "combco.index.0").read_bytes()
+    finally:
+        rr.cleanup()
