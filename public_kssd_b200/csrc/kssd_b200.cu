@@ -16,8 +16,8 @@
 
 #include "../../include/kssd_b200.h"
 #include "index_dist.cuh"
-#include "sketch_fastq.cuh"
 #include "sketch_scan32.cuh"
+#include "sketch_fastq.cuh"
 
 using namespace kssd;
 
@@ -326,7 +326,7 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
                      const ScanArgs &A)
 {
     const SketchParams &P = c->P;
-    CU(cudaFuncSetAttribute(sketch_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPfWords * 4)));
+    CU(cudaFuncSetAttribute(sketch_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kPfWords + kPf2Words) * 4)));
     for (int g = 0; g < n_genomes; g++) {
         const uint64_t gs = goff[g], ge = gs + glen[g];
         if (ge == gs) continue;
@@ -352,7 +352,7 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
         nl_fill_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->pos.as<uint32_t>(), c->minord.as<uint64_t>());
         LAUNCHED(1);
         FastqArgs F{};
-        F.seq = d_seq; F.gs = gs; F.ge = ge;
+        F.seq = d_seq; F.seq_bytes = A.seq_bytes; F.gs = gs; F.ge = ge;
         F.nlpos = c->minord.as<uint64_t>();
         F.n_nl = n_nl;
         F.n_lines = n_nl + (lastbyte != '\n' ? 1 : 0);
@@ -365,7 +365,7 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
         if (F.n_records) {
             const uint64_t want = (F.n_records + kFastqThreads - 1) / kFastqThreads;
             const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)c->sm_count);
-            sketch_fastq_kernel<<<grid, kFastqThreads, kPfWords * 4, c->stream>>>(P, F);
+            sketch_fastq_kernel<<<grid, kFastqThreads, (kPfWords + kPf2Words) * 4, c->stream>>>(P, F);
             LAUNCHED(1);
         }
     }

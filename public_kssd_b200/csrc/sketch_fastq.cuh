@@ -18,7 +18,7 @@
 // same shared-memory prefilter / exact sampled-set lookup as the FASTA kernel.  Reads are short, so there is no
 // cross-thread state at all.
 #pragma once
-#include "kssd_device.cuh"
+#include "sketch_scan.cuh"
 
 namespace kssd {
 
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__rest
 
 struct FastqArgs {
     const uint8_t *seq;
+    uint64_t seq_bytes;          // readable bytes of the batch buffer
     uint64_t gs, ge;             // genome extent
     const uint64_t *nlpos;       // positions of the newline-terminated lines' '\n' (ascending)
     uint64_t n_nl;               // newline-terminated lines
@@ -113,6 +114,62 @@ __device__ __forceinline__ uint32_t byte_at(const uint8_t *seq, uint64_t p, uint
 
 constexpr int kFastqThreads = 1024;
 
+// exact test of one forward 2k-mer ending at byte offset `ord` of its genome (the ~1/2000 that pass both filters)
+__device__ __forceinline__ void fastq_resolve(const SketchParams &P, const FastqArgs &A, uint64_t kmer, uint64_t ord)
+{
+    const uint64_t rc = revcomp2(kmer, P.TL);
+    const uint64_t u = kmer < rc ? kmer : rc;
+    const uint32_t inner = (uint32_t)(u >> (2 * P.out)) & P.innermask;
+    uint32_t h = mix32(inner) & P.ht_mask, pfv = 0;
+    bool found = false;
+    for (;;) {
+        const uint2 e = __ldg(&P.ht[h]);
+        if (e.x == inner) { found = true; pfv = e.y; break; }
+        if (e.x == kHtEmpty) break;
+        h = (h + 1) & P.ht_mask;
+    }
+    if (!found) return;
+    const uint64_t dr = (((u & P.undomask) + ((u & P.outmask) << (4 * P.s))) >> (4 * P.L)) + pfv;
+    const uint32_t o = atomicAdd(A.out_count, 1u);
+    if (o < A.out_cap) {
+        A.out_keys[o] = ((dr & P.comp_mask) << 56) | ((uint64_t)A.gid << 28) | (dr >> P.comp_code_bits);
+        A.out_ords[o] = ord;
+    }
+}
+
+// bit i of the result = byte i of the 16 (four words, byte 0 first) is non-zero
+__device__ __forceinline__ uint32_t nonzero_bytes16(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3)
+{
+    auto nib = [](uint32_t b) -> uint32_t {
+        const uint32_t z = (((b & 0x7f7f7f7fu) + 0x7f7f7f7fu) | b) & 0x80808080u;     // 0x80 per non-zero byte, exact
+        return (((z >> 7) * 0x00204081u) >> 21) & 0xfu;
+    };
+    return nib(b0) | (nib(b1) << 4) | (nib(b2) << 8) | (nib(b3) << 12);
+}
+
+// 16 bytes starting at the (unaligned) address p, assembled from two aligned loads
+__device__ __forceinline__ uint4 load_unaligned16(const uint8_t *seq, uint64_t p, uint64_t readable)
+{
+    const uint64_t a = p & ~15ull;
+    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(seq + a));
+    const uint32_t sh = (uint32_t)(p - a);
+    if (sh == 0) return x;
+    uint4 y = make_uint4(0, 0, 0, 0);
+    if (a + 16 < readable) y = __ldg(reinterpret_cast<const uint4 *>(seq + a + 16));
+    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    const uint32_t ws = sh >> 2, bs = 8 * (sh & 3);
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (ws == (uint32_t)j) { lo = w[i + j]; hi = w[i + j + 1]; }
+        r[i] = __funnelshift_r(lo, hi, bs);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const SketchParams P, const FastqArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -120,7 +177,7 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);
-        for (uint32_t i = threadIdx.x; i < kPfWords / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        for (uint32_t i = threadIdx.x; i < (kPfWords + kPf2Words) / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
     }
     __syncthreads();
     const int TL = P.TL;
@@ -147,44 +204,89 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
                 continue;
             }
         }
-        uint64_t fwd = 0, ca = ~0ull, qa = ~0ull;
-        uint4 cc = make_uint4(0, 0, 0, 0), qc = make_uint4(0, 0, 0, 0);
-        uint32_t run = 0;
         const bool use_q = !A.abund && A.Q > -128;
-        for (uint64_t p = s0; p < s1; p++) {
-            const uint32_t b = byte_at(A.seq, p, ca, cc);
-            const uint32_t l = b | 0x20u;
-            bool ok = (l == 'a' || l == 'c' || l == 'g' || l == 't');
-            if (ok && use_q) {
-                const uint64_t off = p - s0;
-                const int q = off < qlen ? (int)(int8_t)byte_at(A.seq, q0 + off, qa, qc) : 0;
-                ok = q >= A.Q;
+        if (TL >= 16) {
+            // ---- vectorised walk: 16 aligned bytes at a time, same classify / pack / probe code as the FASTA kernel ----
+            // With 2k >= 16 no k-mer can both start after an invalid byte of a chunk and end inside that chunk, so the
+            // chunk's valid k-mer ends are the positions before its first invalid byte (given enough run before it).
+            uint32_t hist0 = 0, hist1 = 0, run = 0;        // last 32 bases (newest low), valid bases since the last break
+            const uint32_t qrep = (uint32_t)(A.Q & 0xff) * 0x01010101u;
+            for (uint64_t a = s0 & ~15ull; a < s1; a += 16) {
+                const uint4 c = __ldg(reinterpret_cast<const uint4 *>(A.seq + a));
+                const int lo = a < s0 ? (int)(s0 - a) : 0;
+                const int hi = s1 - a < 16 ? (int)(s1 - a) : 16;
+                uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, t0, t1, t2, t3, m0, m1, m2, m3;
+                classify4(c.x, d0, t0, m0);
+                classify4(c.y, d1, t1, m1);
+                classify4(c.z, d2, t2, m2);
+                classify4(c.w, d3, t3, m3);
+                const uint32_t codes = prmt(prmt(m3, m2, 0x0073u), prmt(m1, m0, 0x0073u), 0x5410u);
+                // invalid: anything but ACGTacgt (line ends included: '\r' breaks a read, iseq2comem.c:311-319)
+                uint32_t inv = nonzero_bytes16(d0 | (t0 & 0x04040404u), d1 | (t1 & 0x04040404u), d2 | (t2 & 0x04040404u), d3 | (t3 & 0x04040404u));
+                inv |= ~(((1u << hi) - 1u) & ~((1u << lo) - 1u)) & 0xffffu;
+                if (use_q) {
+                    // quality byte of sequence byte a+i is q0 + (a - s0) + i; beyond the quality line it counts as 0
+                    const int64_t rel = (int64_t)a - (int64_t)s0;                    // >= -15
+                    const uint4 qv = load_unaligned16(A.seq, (uint64_t)((int64_t)q0 + rel), A.seq_bytes);
+                    const uint32_t f0 = __vcmpges4(qv.x, qrep), f1 = __vcmpges4(qv.y, qrep), f2 = __vcmpges4(qv.z, qrep), f3 = __vcmpges4(qv.w, qrep);
+                    uint32_t pass = nonzero_bytes16(f0, f1, f2, f3);
+                    const int64_t qn = (int64_t)qlen - rel;                          // bytes of this chunk inside the quality line
+                    const uint32_t inq = qn >= 16 ? 0xffffu : (qn <= 0 ? 0u : ((1u << qn) - 1u));
+                    pass = (pass & inq) | (A.Q <= 0 ? (~inq & 0xffffu) : 0u);
+                    inv |= ~pass & 0xffffu;
+                    if (A.Q > 127) inv = 0xffffu;                                    // no signed byte reaches Q
+                }
+                const int fi = inv ? __ffs(inv) - 1 : 16;                             // k-mers may end at bytes [0, fi)
+                const int need = TL - 1 - (int)run;                                   // ... and at byte >= need
+                if (fi > need) {
+                    uint32_t ends = (fi >= 16 ? 0xffffu : ((1u << fi) - 1u)) & ~(need > 0 ? ((1u << need) - 1u) : 0u);
+                    // W = history : this chunk's 16 codes (byte 15 newest, in the low bits)
+                    const uint32_t X0 = __funnelshift_r(codes, hist0, 2 * P.out);
+                    const uint32_t X1 = __funnelshift_r(hist0, hist1, 2 * P.out);
+                    auto tsh = [&](int e) -> uint32_t {
+                        return e < 0 ? (X0 << 2) : (e < 16 ? __funnelshift_r(X0, X1, 2 * e) : (X1 >> (2 * e - 32)));
+                    };
+                    uint32_t cand = 0;
+#pragma unroll
+                    for (int d = 15; d >= 0; d--) {
+                        const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (tsh(d - 1) & (kPfWordMask << 2)));
+                        cand = __funnelshift_l(__funnelshift_l(0u, word, tsh(d + 8)), cand, 1);
+                    }
+                    cand &= __brev(ends) >> 16;                                       // bit d <-> byte 15 - d
+                    while (cand) {
+                        const int d = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        const uint32_t klo = __funnelshift_r(codes, hist0, 2 * d), khi = __funnelshift_r(hist0, hist1, 2 * d);
+                        if (!pf2_probe(pf, __funnelshift_r(klo, khi, 2 * P.out) & P.innermask)) continue;
+                        fastq_resolve(P, A, (((uint64_t)khi << 32) | klo) & P.tupmask, a + (15 - d) - A.gs);
+                    }
+                }
+                // state after the chunk
+                if (inv == 0) run = min(run + 16u, 64u);
+                else run = (uint32_t)__clz(inv << 16);                                // valid bytes after the last invalid one
+                hist1 = hist0;
+                hist0 = codes;
             }
-            if (!ok) { run = 0; continue; }
-            const uint32_t t = (b >> 1) & 3u;
-            fwd = (fwd << 2) | (t ^ (t >> 1));
-            if (++run < (uint32_t)TL) continue;
-            const uint32_t v = (uint32_t)(fwd >> (2 * P.out));
-            if (!(__funnelshift_l(0u, pf[v & kPfWordMask], v >> kPfBitShift) >> 31)) continue;
-            // exact resolution (rare)
-            const uint64_t kmer = fwd & P.tupmask;
-            const uint64_t rc = revcomp2(kmer, TL);
-            const uint64_t u = kmer < rc ? kmer : rc;
-            const uint32_t inner = (uint32_t)(u >> (2 * P.out)) & P.innermask;
-            uint32_t h = mix32(inner) & P.ht_mask, pfv = 0;
-            bool found = false;
-            for (;;) {
-                const uint2 e = __ldg(&P.ht[h]);
-                if (e.x == inner) { found = true; pfv = e.y; break; }
-                if (e.x == kHtEmpty) break;
-                h = (h + 1) & P.ht_mask;
-            }
-            if (!found) continue;
-            const uint64_t dr = (((u & P.undomask) + ((u & P.outmask) << (4 * P.s))) >> (4 * P.L)) + pfv;
-            const uint32_t o = atomicAdd(A.out_count, 1u);
-            if (o < A.out_cap) {
-                A.out_keys[o] = ((dr & P.comp_mask) << 56) | ((uint64_t)A.gid << 28) | (dr >> P.comp_code_bits);
-                A.out_ords[o] = p - A.gs;
+        } else {
+            // ---- scalar walk (2k < 16: a k-mer can start and end inside one chunk) ----
+            uint64_t fwd = 0, ca = ~0ull, qa = ~0ull;
+            uint4 cc = make_uint4(0, 0, 0, 0), qc = make_uint4(0, 0, 0, 0);
+            uint32_t run = 0;
+            for (uint64_t p = s0; p < s1; p++) {
+                const uint32_t b = byte_at(A.seq, p, ca, cc);
+                const uint32_t l = b | 0x20u;
+                bool ok = (l == 'a' || l == 'c' || l == 'g' || l == 't');
+                if (ok && use_q) {
+                    const uint64_t off = p - s0;
+                    const int q = off < qlen ? (int)(int8_t)byte_at(A.seq, q0 + off, qa, qc) : 0;
+                    ok = q >= A.Q;
+                }
+                if (!ok) { run = 0; continue; }
+                const uint32_t t = (b >> 1) & 3u;
+                fwd = (fwd << 2) | (t ^ (t >> 1));
+                if (++run < (uint32_t)TL) continue;
+                if (!(pf_probe(pf, (uint32_t)(fwd >> (2 * P.out))) >> 31)) continue;
+                fastq_resolve(P, A, fwd & P.tupmask, p - A.gs);
             }
         }
     }
