@@ -389,8 +389,17 @@ def main():
     L.kssd_sketch_free(sk_h)
 
     scan = float(np.median(scan_ms))
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "r1_sketch_traffic.json"          # dram bytes of this kernel from one `ncu --set full` capture
+    if tf.exists():
+        try:
+            tj = json.loads(tf.read_text())
+            if int(tj["algorithmic_bytes_per_launch"]) == text_bytes:
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_sketch_traffic.json (ncu dram__bytes_read+write, same launch shape)"
+        except Exception:
+            pass
     roof = {"bound": "hbm", "achieved": text_bytes / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": text_bytes / (scan * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "frac": text_bytes / (scan * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "kernel": "sketch_fasta32_kernel", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
 
     cpu_baseline = None
