@@ -666,8 +666,8 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
         nuniq = lp + lf;
     }
     ix->n_unique = nuniq;
-    CU(cudaMalloc(&ix->d_ucodes, std::max<size_t>(nuniq, 1) * 4));
-    CU(cudaMalloc(&ix->d_uoff, ((size_t)nuniq + 1) * 4));
+    CU(cudaMallocAsync(&ix->d_ucodes, std::max<size_t>(nuniq, 1) * 4, c->stream));
+    CU(cudaMallocAsync(&ix->d_uoff, ((size_t)nuniq + 1) * 4, c->stream));
     if (n) {
         csr_scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(d_sorted_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n,
                                                                                ix->d_ucodes, ix->d_uoff);
@@ -676,7 +676,7 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
     const uint32_t n32 = (uint32_t)n;
     CU(cudaMemcpyAsync(ix->d_uoff + nuniq, &n32, 4, cudaMemcpyHostToDevice, c->stream));
     // dense exclusive start table for O(1) query lookups (and for mco.index.<c> export)
-    CU(cudaMalloc(&ix->d_dense, (ix->space + 1) * 4));
+    CU(cudaMallocAsync(&ix->d_dense, (ix->space + 1) * 4, c->stream));
     CU(cudaMemsetAsync(ix->d_dense, 0, (ix->space + 1) * 4, c->stream));
     if (nuniq) {
         dense_mark_kernel<<<(nuniq + 255) / 256, 256, 0, c->stream>>>(ix->d_ucodes, ix->d_uoff, nuniq, ix->d_dense);
@@ -701,7 +701,7 @@ extern "C" int kssd_index_build_dev(kssd_ctx_t *c, const uint32_t *combco_dev, c
     ix->ctx = c; ix->n_genomes = n_genomes; ix->n_postings = n_codes;
     ix->space = 1ull << (4 * c->info.component_sz);   // the reference's dense table always spans 16^COMPONENT_SZ
     CU(cudaEventRecord(c->ev[0], c->stream));
-    CU(cudaMalloc(&ix->d_gids, std::max<size_t>(n_codes, 1) * 4));
+    CU(cudaMallocAsync(&ix->d_gids, std::max<size_t>(n_codes, 1) * 4, c->stream));
     uint32_t *d_sorted = nullptr;
     if (n_codes) {
         CU(c->keys.ensure(n_codes * 4));     // gid tags (unsorted)
@@ -807,10 +807,10 @@ extern "C" int kssd_index_from_dense_host(kssd_ctx_t *c, const uint64_t *dense_i
     kssd_index *ix = new kssd_index();
     ix->ctx = c; ix->n_genomes = n_genomes; ix->n_postings = n_postings;
     ix->space = 1ull << (4 * c->info.component_sz);   // the reference's dense table always spans 16^COMPONENT_SZ
-    CU(cudaMalloc(&ix->d_gids, std::max<size_t>(n_postings, 1) * 4));
+    CU(cudaMallocAsync(&ix->d_gids, std::max<size_t>(n_postings, 1) * 4, c->stream));
     if (n_postings) CU(cudaMemcpyAsync(ix->d_gids, gids, n_postings * 4, cudaMemcpyHostToDevice, c->stream));
     uint32_t *d_dense_tmp = nullptr;
-    CU(cudaMalloc(&d_dense_tmp, (ix->space + 1) * 4));
+    CU(cudaMallocAsync(&d_dense_tmp, (ix->space + 1) * 4, c->stream));
     const uint64_t chunk = 1ull << 24;
     CU(c->keys.ensure(chunk * 8));
     for (uint64_t first = 0; first < ix->space; first += chunk) {
@@ -824,7 +824,7 @@ extern "C" int kssd_index_from_dense_host(kssd_ctx_t *c, const uint64_t *dense_i
     codes_from_dense_kernel<<<(uint32_t)((ix->space + 255) / 256), 256, 0, c->stream>>>(d_dense_tmp, ix->space, c->keys2.as<uint32_t>());
     LAUNCHED(1);
     int rc = index_finish(c, ix, n_postings ? c->keys2.as<uint32_t>() : nullptr);
-    cudaFree(d_dense_tmp);
+    cudaFreeAsync(d_dense_tmp, c->stream);
     if (rc) { kssd_index_free(ix); return rc; }
     *out = ix;
     return KSSD_OK;
@@ -834,10 +834,11 @@ extern "C" void kssd_index_free(kssd_index_t *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->ctx->device);
-    cudaFree(ix->d_ucodes);
-    cudaFree(ix->d_uoff);
-    cudaFree(ix->d_gids);
-    cudaFree(ix->d_dense);
+    cudaStream_t st = ix->ctx->stream;
+    if (ix->d_ucodes) cudaFreeAsync(ix->d_ucodes, st);
+    if (ix->d_uoff) cudaFreeAsync(ix->d_uoff, st);
+    if (ix->d_gids) cudaFreeAsync(ix->d_gids, st);
+    if (ix->d_dense) cudaFreeAsync(ix->d_dense, st);
     delete ix;
 }
 
@@ -863,9 +864,9 @@ static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_
     d->ctx = c; d->n_qry = n_qry; d->n_ref = n_ref;
     for (int i = 0; i < n_qry; i++) d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]);
     if (ct_ext) { d->d_ct = ct_ext; d->owns_ct = false; d->components_done = filled ? 1 : 0; }
-    else CU(cudaMalloc(&d->d_ct, (size_t)n_qry * n_ref * 4));
-    CU(cudaMalloc(&d->d_qsz, (size_t)n_qry * 4));
-    CU(cudaMalloc(&d->d_rsz, (size_t)n_ref * 4));
+    else CU(cudaMallocAsync(&d->d_ct, (size_t)n_qry * n_ref * 4, c->stream));
+    CU(cudaMallocAsync(&d->d_qsz, (size_t)n_qry * 4, c->stream));
+    CU(cudaMallocAsync(&d->d_rsz, (size_t)n_ref * 4, c->stream));
     CU(cudaMemcpyAsync(d->d_qsz, qry_ctx_ct, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d->d_rsz, ref_ctx_ct, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1064,9 +1065,10 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
 {
     if (!d) return;
     cudaSetDevice(d->ctx->device);
-    if (d->owns_ct) cudaFree(d->d_ct);
-    cudaFree(d->d_qsz);
-    cudaFree(d->d_rsz);
+    cudaStream_t st = d->ctx->stream;
+    if (d->owns_ct) cudaFreeAsync(d->d_ct, st);
+    cudaFreeAsync(d->d_qsz, st);
+    cudaFreeAsync(d->d_rsz, st);
     if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);
 
     delete d;

@@ -81,55 +81,101 @@ def reduce_scatter_rows(partial, world: int, rank: int):
     return out
 
 
-class ShardedDist:
-    """Stage III over `world` GPUs: reference index sharded by code range, queries broadcast, partial count
-    matrices combined by reduce-scatter.  Every rank calls the same methods (SPMD)."""
+def genome_block(codes: np.ndarray, index: np.ndarray, lo: int, hi: int):
+    """combco (codes, index) of the genomes [lo, hi) only, index rebased to start at 0."""
+    index = np.asarray(index, dtype=np.uint64)
+    a, b = int(index[lo]), int(index[hi])
+    return np.asarray(codes, dtype=np.uint32)[a:b], index[lo:hi + 1] - index[lo]
 
-    def __init__(self, ctx, world: int, rank: int, code_bits: int = 28):
-        self.ctx, self.world, self.rank, self.code_bits = ctx, world, rank, code_bits
+
+class ShardedDist:
+    """Stage III over `world` GPUs.  Every rank calls the same methods (SPMD).
+
+    mode "code"   (north star): reference index sharded by code range, queries broadcast, every rank counts a full
+                  Q x R matrix of partial counts, one reduce-scatter leaves each rank the final counts of its block
+                  of query rows.
+    mode "genome" (zero-communication alternative): rank r indexes the reference genomes of its
+                  block; its Q x R/world count columns are final as they are -- no reduction at all."""
+
+    def __init__(self, ctx, world: int, rank: int, code_bits: int = 28, mode: str = "code"):
+        assert mode in ("code", "genome")
+        self.ctx, self.world, self.rank, self.code_bits, self.mode = ctx, world, rank, code_bits, mode
         self.index = None
         self.ref_sizes = None
+        self.col_lo = self.col_hi = 0
+        self._partial = None
 
     def build_reference(self, ref_codes: np.ndarray, ref_index: np.ndarray):
-        """Every rank sees the reference combco (or at least its own code range of it) and indexes its slice."""
-        lo, hi = code_range(self.rank, self.world, self.code_bits)
-        c, ix = filter_codes_to_range(ref_codes, ref_index, lo, hi)
-        self.index = self.ctx.combco2mco(c, ix)
+        """Every rank sees the reference combco (or at least its own shard of it) and indexes its slice."""
         self.ref_sizes = np.diff(np.asarray(ref_index, dtype=np.uint64)).astype(np.uint32)
+        if self.mode == "code":
+            lo, hi = code_range(self.rank, self.world, self.code_bits)
+            c, ix = filter_codes_to_range(ref_codes, ref_index, lo, hi)
+        else:
+            g = genome_shard(len(ref_index) - 1, self.world, self.rank)
+            self.col_lo, self.col_hi = g.start, g.stop
+            c, ix = genome_block(ref_codes, ref_index, g.start, g.stop) if g.stop > g.start else (np.zeros(0, np.uint32), np.zeros(2, np.uint64))
+        self.index = self.ctx.combco2mco(c, ix) if len(ix) > 1 and (self.mode == "code" or self.col_hi > self.col_lo) else None
         return self
 
-    def search(self, qry_codes: np.ndarray | None, qry_index: np.ndarray | None, src: int = 0, stats_opts: dict | None = None):
-        """Broadcast the query sketches from `src`, count, reduce-scatter.  Returns (row_lo, row_hi, counts block
-        as numpy uint32, stats rows or None) for the rows this rank owns."""
+    def search(self, qry_codes=None, qry_index=None, src: int = 0, stats_opts: dict | None = None, fetch_counts: bool = True,
+               fetch_stats: bool = True):
+        """Broadcast the query sketches from `src`, count, (code mode) reduce-scatter, statistics.  qry_codes/qry_index:
+        numpy arrays or CUDA tensors (int32 view of the uint32 codes, int64 index) on `src`, None elsewhere.
+        Returns (lo, hi, counts block as numpy uint32 or None, stats rows / row count / None): in code mode the block is
+        the query ROWS [lo, hi) x all refs, in genome mode all queries x the reference COLUMNS [lo, hi)."""
         import torch
         import torch.distributed as dist
         from . import kssd
         dev = torch.device("cuda", self.ctx.device)
+
+        def to_dev(a, np_dtype, view, tdtype):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return a.to(dev)
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype).view(view)).to(dev)
+
+        tq, ti = to_dev(qry_codes, np.uint32, np.int32, torch.int32), to_dev(qry_index, np.uint64, np.int64, torch.int64)
         if self.world > 1:
             meta = torch.zeros(2, dtype=torch.int64, device=dev)
             if self.rank == src:
-                meta[0], meta[1] = len(qry_index) - 1, len(qry_codes)
+                meta[0], meta[1] = ti.numel() - 1, tq.numel()
             dist.broadcast(meta, src)
             nq, nc = int(meta[0]), int(meta[1])
-            tq = torch.empty(max(nc, 1), dtype=torch.int32, device=dev)
-            ti = torch.empty(nq + 1, dtype=torch.int64, device=dev)
-            if self.rank == src:
-                tq[:nc] = torch.from_numpy(np.ascontiguousarray(qry_codes, dtype=np.uint32).view(np.int32)).to(dev)
-                ti.copy_(torch.from_numpy(np.ascontiguousarray(qry_index, dtype=np.uint64).view(np.int64)).to(dev))
+            if self.rank != src:
+                tq = torch.empty(max(nc, 1), dtype=torch.int32, device=dev)
+                ti = torch.empty(nq + 1, dtype=torch.int64, device=dev)
             dist.broadcast(tq, src)
             dist.broadcast(ti, src)
         else:
-            nq, nc = len(qry_index) - 1, len(qry_codes)
-            tq = torch.from_numpy(np.ascontiguousarray(qry_codes, dtype=np.uint32).view(np.int32)).to(dev)
-            ti = torch.from_numpy(np.ascontiguousarray(qry_index, dtype=np.uint64).view(np.int64)).to(dev)
-        qsizes = (ti[1:] - ti[:-1]).to(torch.int64).cpu().numpy().astype(np.uint32)
+            nq, nc = ti.numel() - 1, tq.numel()
+        qsizes = (ti[1:] - ti[:-1]).cpu().numpy().astype(np.uint32)
         R = int(self.ref_sizes.size)
+        if self.mode == "genome":
+            # this rank's reference columns are final: count, then statistics, no collective
+            lo, hi = self.col_lo, self.col_hi
+            if hi <= lo:
+                return lo, hi, np.zeros((nq, 0), dtype=np.uint32), None
+            job = kssd.DistJob(self.ctx, qsizes, self.ref_sizes[lo:hi])
+            torch.cuda.synchronize()
+            job.accumulate_dev(self.index, tq.data_ptr(), ti.data_ptr(), nc)
+            rows = None
+            if stats_opts is not None:
+                rows = job.stats(cmprsn_num=(R * nq) & 0xFFFFFFFF, fetch=fetch_stats, **stats_opts)
+                if fetch_stats:
+                    rows["ref"] += lo
+            block = job.counts() if fetch_counts else None
+            job.close()
+            return lo, hi, block, rows
         per = (nq + self.world - 1) // self.world
         rows_padded = per * self.world
-        partial = torch.zeros((rows_padded, R), dtype=torch.int32, device=dev)
+        if self._partial is None or tuple(self._partial.shape) != (rows_padded, R):
+            self._partial = torch.zeros((rows_padded, R), dtype=torch.int32, device=dev)     # padding rows stay zero
+        partial = self._partial
         job = kssd.DistJob(self.ctx, qsizes, self.ref_sizes, ct_dev_ptr=partial.data_ptr())
         torch.cuda.synchronize()
-        job.accumulate_dev(self.index, tq.data_ptr(), ti.data_ptr(), nc)
+        job.accumulate_dev(self.index, tq.data_ptr(), ti.data_ptr(), nc)      # the kernel zeroes and fills rows [0, nq)
         job.close()
         mine = reduce_scatter_rows(partial, self.world, self.rank)
         torch.cuda.synchronize()
@@ -137,7 +183,8 @@ class ShardedDist:
         rows = None
         if stats_opts is not None and hi > lo:
             sj = kssd.DistJob(self.ctx, qsizes[lo:hi], self.ref_sizes, ct_dev_ptr=mine.data_ptr(), already_filled=True)
-            rows = sj.stats(cmprsn_num=(R * nq) & 0xFFFFFFFF, **stats_opts)
-            rows["qry"] += lo
+            rows = sj.stats(cmprsn_num=(R * nq) & 0xFFFFFFFF, fetch=fetch_stats, **stats_opts)
+            if fetch_stats:
+                rows["qry"] += lo
             sj.close()
-        return lo, hi, mine[: hi - lo].cpu().numpy().view(np.uint32), rows
+        return lo, hi, (mine[: hi - lo].cpu().numpy().view(np.uint32) if fetch_counts else None), rows
