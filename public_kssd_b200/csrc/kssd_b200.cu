@@ -92,7 +92,12 @@ struct kssd_ctx {
     uint32_t *d_prefilter = nullptr;
     uint2 *d_ht = nullptr;
     // scratch
-    DevBuf seq, meta, keys, ords, keys2, ords2, flags, pos, counts, minord, cubtmp, misc;
+    DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, counts, minord, cubtmp, misc;
+    // cached span plan of the last batch layout
+    bool plan_valid = false;
+    uint64_t plan_key = 0;
+    int plan_genomes = 0;
+    uint32_t plan_spans = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
 };
@@ -236,7 +241,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->seq, &c->meta, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->counts, &c->minord,
+    for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->counts, &c->minord,
                       &c->cubtmp, &c->misc})
         b->release();
     cudaFree(c->d_prefilter);
@@ -401,9 +406,16 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         while (span < want && span < (256u << 10)) span <<= 1;
     }
     if (span < 512 || (span & (span - 1))) return fail(KSSD_E_INVAL, "kssd_sketch_batch: span_bytes must be a power of two >= 512");
-    std::vector<uint32_t> span_gid;
-    std::vector<uint64_t> span_nom;
-    {
+    // The span plan is a function of the batch layout only; a host that sketches batches of the same layout (a
+    // streaming pipeline with fixed-size staging buffers) pays for it once: the plan and its device copy are cached.
+    uint64_t lkey = 1469598103934665603ull;
+    auto mixkey = [&](uint64_t v) { lkey = (lkey ^ v) * 1099511628211ull; };
+    mixkey((uint64_t)n_genomes); mixkey(span); mixkey(guided);
+    for (int g = 0; g < n_genomes; g++) { mixkey(goff[g]); mixkey(glen[g]); }
+    const bool plan_hit = c->plan_valid && c->plan_key == lkey && c->plan_genomes == n_genomes;
+    if (!plan_hit) {
+        std::vector<uint32_t> span_gid;
+        std::vector<uint64_t> span_nom;
         uint64_t remaining = total;
         const uint64_t round = warps * span;
         for (int g = 0; g < n_genomes; g++)
@@ -419,21 +431,29 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
                 o += step;
                 remaining -= step;
             }
+        c->plan_spans = (uint32_t)span_gid.size();
+        // device plan: goff | glen | span_nom | span_gid
+        const size_t p_glen = 8ull * n_genomes, p_nom = p_glen + 8ull * n_genomes, p_sgid = p_nom + 8ull * c->plan_spans,
+                     p_end = p_sgid + 4ull * c->plan_spans;
+        CU(c->plan.ensure(p_end));
+        uint8_t *pb = c->plan.as<uint8_t>();
+        CU(cudaMemcpyAsync(pb, goff, 8ull * n_genomes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(pb + p_glen, glen, 8ull * n_genomes, cudaMemcpyHostToDevice, c->stream));
+        if (c->plan_spans) {
+            CU(cudaMemcpyAsync(pb + p_nom, span_nom.data(), 8ull * c->plan_spans, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(pb + p_sgid, span_gid.data(), 4ull * c->plan_spans, cudaMemcpyHostToDevice, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));      // the vectors die here
+        c->plan_key = lkey; c->plan_genomes = n_genomes; c->plan_valid = true;
     }
-    const uint32_t n_spans = (uint32_t)span_gid.size();
+    const uint32_t n_spans = c->plan_spans;
+    uint8_t *pb = c->plan.as<uint8_t>();
+    const size_t p_glen = 8ull * n_genomes, p_nom = p_glen + 8ull * n_genomes, p_sgid = p_nom + 8ull * n_spans;
 
-    // device metadata: goff | glen | span_nom | span_gid | gstatus | ticket | out_count
-    const size_t m_goff = 0, m_glen = m_goff + 8ull * n_genomes, m_nom = m_glen + 8ull * n_genomes,
-                 m_sgid = m_nom + 8ull * n_spans, m_stat = m_sgid + 4ull * n_spans, m_tick = m_stat + 4ull * n_genomes,
-                 m_cnt = m_tick + 4, m_end = m_cnt + 4;
+    // per-call device scratch: gstatus | ticket | out_count
+    const size_t m_stat = 0, m_tick = m_stat + 4ull * n_genomes, m_cnt = m_tick + 4, m_end = m_cnt + 4;
     CU(c->meta.ensure(m_end));
     uint8_t *mb = c->meta.as<uint8_t>();
-    CU(cudaMemcpyAsync(mb + m_goff, goff, 8ull * n_genomes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(mb + m_glen, glen, 8ull * n_genomes, cudaMemcpyHostToDevice, c->stream));
-    if (n_spans) {
-        CU(cudaMemcpyAsync(mb + m_nom, span_nom.data(), 8ull * n_spans, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(mb + m_sgid, span_gid.data(), 4ull * n_spans, cudaMemcpyHostToDevice, c->stream));
-    }
     CU(cudaMemsetAsync(mb + m_stat, 0, 4ull * n_genomes + 8, c->stream));
 
     // occurrence buffer: expected total/|sampling| ; 4x head-room, retried on overflow
@@ -448,10 +468,10 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(c->ords.ensure(cap * 8));
         ScanArgs A{};
         A.seq = d_seq; A.seq_bytes = seq_bytes;
-        A.goff = reinterpret_cast<uint64_t *>(mb + m_goff);
-        A.glen = reinterpret_cast<uint64_t *>(mb + m_glen);
-        A.span_nom = reinterpret_cast<uint64_t *>(mb + m_nom);
-        A.span_gid = reinterpret_cast<uint32_t *>(mb + m_sgid);
+        A.goff = reinterpret_cast<uint64_t *>(pb);
+        A.glen = reinterpret_cast<uint64_t *>(pb + p_glen);
+        A.span_nom = reinterpret_cast<uint64_t *>(pb + p_nom);
+        A.span_gid = reinterpret_cast<uint32_t *>(pb + p_sgid);
         A.n_spans = n_spans; A.span_bytes = span;
         A.gstatus = reinterpret_cast<int32_t *>(mb + m_stat);
         A.ticket = reinterpret_cast<uint32_t *>(mb + m_tick);
@@ -501,7 +521,10 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(c->keys2.ensure((size_t)n_occ * 8));
         CU(c->ords2.ensure((size_t)n_occ * 8));
         size_t tmp_bytes = 0;
-        const int end_bit = 56 + std::max(P.comp_code_bits, 1);
+        // sort only the bits in use: id (28) + genome id, plus the component field at bit 56 when there is one
+        int gbits = 1;
+        while ((1ll << gbits) < n_genomes) gbits++;
+        const int end_bit = P.comp_code_bits ? 56 + P.comp_code_bits : 28 + gbits;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->keys.as<uint64_t>(), c->keys2.as<uint64_t>(), c->ords.as<uint64_t>(),
                                         c->ords2.as<uint64_t>(), n_occ, 0, end_bit, c->stream);
         CU(c->cubtmp.ensure(tmp_bytes));
