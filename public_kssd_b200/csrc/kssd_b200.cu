@@ -21,16 +21,6 @@
 
 using namespace kssd;
 
-// clean-path granularity of the FASTA scan: 32 bytes per lane (sketch_scan32.cuh) or 16 (sketch_scan.cuh)
-#ifndef KSSD_SCAN_LANE_BYTES
-#define KSSD_SCAN_LANE_BYTES 32
-#endif
-#if KSSD_SCAN_LANE_BYTES == 32
-#define KSSD_FASTA_KERNEL sketch_fasta32_kernel
-#else
-#define KSSD_FASTA_KERNEL sketch_fasta_kernel
-#endif
-
 // ------------------------------------------------------------------------------------------------
 // errors, bookkeeping
 // ------------------------------------------------------------------------------------------------
@@ -219,7 +209,7 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.prefilter = c->d_prefilter;
     P.ht = c->d_ht;
 
-    CU(cudaFuncSetAttribute(KSSD_FASTA_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(sketch_fasta32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)((kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue))));
 
     kssd_ctx_info_t &I = c->info;
@@ -472,7 +462,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         A.glen = reinterpret_cast<uint64_t *>(pb + p_glen);
         A.span_nom = reinterpret_cast<uint64_t *>(pb + p_nom);
         A.span_gid = reinterpret_cast<uint32_t *>(pb + p_sgid);
-        A.n_spans = n_spans; A.span_bytes = span;
+        A.n_spans = n_spans;
         A.gstatus = reinterpret_cast<int32_t *>(mb + m_stat);
         A.ticket = reinterpret_cast<uint32_t *>(mb + m_tick);
         A.out_count = reinterpret_cast<uint32_t *>(mb + m_cnt);
@@ -483,7 +473,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
             if (n_spans) {
-                KSSD_FASTA_KERNEL<<<c->sm_count, kScanThreads, (kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
+                sketch_fasta32_kernel<<<c->sm_count, kScanThreads, (kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
                 LAUNCHED(1);
             }
         } else {

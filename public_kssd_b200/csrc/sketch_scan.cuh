@@ -11,8 +11,8 @@
 // B200 mapping (DESIGN.md "Stage I"):
 //   * one persistent CTA per SM, the 128 KiB prefilter bitmap resident in shared memory;
 //   * a WARP is the unit of streaming: it pulls a span (a run of whole lines of one genome) from an
-//     atomic ticket and walks it 512 B per iteration, 16 B per lane, with the next 512 B already
-//     in flight (register double buffering); no block-level barrier in the steady state;
+//     atomic ticket and walks it 1 KiB per iteration, 32 B per lane (sketch_scan32.cuh), with the next
+//     KiB already in flight (register double buffering); no block-level barrier in the steady state;
 //   * the central 2s-mer of the FORWARD strand is tested against the bitmap of S u RC(S): the
 //     central window of the reverse complement is the reverse complement of the central window,
 //     so the canonical choice cannot create a hit the forward window does not announce.  Only
@@ -21,33 +21,16 @@
 //   * k-mers are OWNED by the span their first base lies in; a warp runs past the end of its span
 //     until 2k-1 valid bases or a break, so spans never exchange state.
 //
-// The kernel is instruction-issue bound (profiles/r1_sketch_*): every choice below is about the
+// The kernel is instruction bound (profiles/r1_sketch_ncu_summary.md): every choice below is about the
 // number of ALU-pipe instructions per input byte, not about bytes moved.
+//
+// This header holds the pieces shared by the scan kernels: byte classification, the squeeze, the prefilter
+// probes, the candidate queue and its exact resolver, span boundaries, and the general (dirty) iteration.
+// The clean-path loop and the kernel live in sketch_scan32.cuh; the FASTQ walk in sketch_fastq.cuh.
 #pragma once
 #include "kssd_device.cuh"
 
-// Tuning switches (A/B measured on B200, see profiles/): which constant shifts go through mul.hi (FMA pipe)
-#ifndef KSSD_MULHI_CLS
-#define KSSD_MULHI_CLS 0
-#endif
-#ifndef KSSD_MULHI_T
-#define KSSD_MULHI_T 0
-#endif
-#ifndef KSSD_MULHI_ADDR
-#define KSSD_MULHI_ADDR 0
-#endif
-#ifndef KSSD_MULHI_ACC
-#define KSSD_MULHI_ACC 0
-#endif
-
 namespace kssd {
-
-template <int S> __device__ __forceinline__ uint32_t shr_fma(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
-#if KSSD_MULHI_CLS
-#define KSSD_SHR_CLS(x, s) shr_fma<s>(x)
-#else
-#define KSSD_SHR_CLS(x, s) ((x) >> (s))
-#endif
 
 #ifndef KSSD_SCAN_THREADS
 #define KSSD_SCAN_THREADS 640
@@ -66,7 +49,6 @@ struct ScanArgs {
     const uint32_t *span_gid;    // per span genome id (device)
     const uint64_t *span_nom;    // per span nominal start (absolute offset)
     uint32_t n_spans;
-    uint32_t span_bytes;
     uint32_t *ticket;            // span dispenser
     uint64_t *out_keys;          // (comp << 56) | (gid << 28) | id
     uint64_t *out_ords;          // byte offset of the occurrence inside its genome (monotone in stream order)
@@ -88,16 +70,15 @@ struct WarpQueue {
 //   m    : top byte = the four 2-bit codes A0 C1 G2 T3, first byte in the top two bits
 __device__ __forceinline__ void classify4(uint32_t w, uint32_t &dacc, uint32_t &t3, uint32_t &m)
 {
-    // constant right shifts are written as mul.hi by 2^(32-s): they issue on the FMA pipe, the ALU pipe is the bound
-    const uint32_t s1 = KSSD_SHR_CLS(w, 1);
+    const uint32_t s1 = (w >> 1);
     const uint32_t t = s1 & 0x03030303u;
-    t3 = t | (~KSSD_SHR_CLS(w, 4) & 0x04040404u);
+    t3 = t | (~(w >> 4) & 0x04040404u);
     const uint32_t u = w & ~(s1 & 0x20202020u);                   // fold case of letters only
-    const uint32_t a = t3 | KSSD_SHR_CLS(t3, 4);
+    const uint32_t a = t3 | (t3 >> 4);
     const uint32_t sel = prmt(a, 0u, 0x4420u);
     const uint32_t e = prmt(0x47544341u, 0xFF0D0AFFu, sel);        // A C T G | - \n \r -
     dacc |= u ^ e;
-    const uint32_t t2 = t ^ (KSSD_SHR_CLS(t, 1) & 0x01010101u);
+    const uint32_t t2 = t ^ ((t >> 1) & 0x01010101u);
     m = t2 * 0x40100401u;
 }
 
@@ -107,20 +88,6 @@ __device__ __forceinline__ uint32_t rev_flags8(uint32_t tOld, uint32_t tNew)
 {
     const uint32_t g = ((tNew >> 2) | (tOld << 2)) & 0x11111111u;
     return (g * 0x08040201u) >> 24;
-}
-
-// remove the 2-bit groups flagged in rsk (bit p = group at bits [2p, 2p+1]); survivors end up right-aligned.
-// First removal is branch-free (rsk == 0 leaves c untouched); further ones only if some lane of the warp needs them.
-__device__ __forceinline__ uint32_t squeeze_groups(uint32_t c, uint32_t rsk)
-{
-    for (;;) {
-        const uint32_t iso = rsk & (0u - rsk);
-        const uint32_t low = iso * iso - 1u;
-        c = ((c >> 2) & ~low) | (c & low);
-        rsk = (rsk ^ iso) >> 1;
-        if (!__any_sync(kFull, rsk != 0)) break;
-    }
-    return c;
 }
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src)
@@ -428,167 +395,6 @@ __device__ __noinline__ void general_iter16(const SketchParams &P, const ScanArg
     else { st.cw = (sn31 < 32 ? (st.cw << (2 * sn31)) : 0ull) | sb31; st.since_break = min(st.since_break + sn31, kRunCap); }
     st.after_end += __shfl_sync(kFull, ginc, 31);
     push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, 0u, lane_off, vmask, 16u, gid, ord_base);
-}
-
-// One span: [start, end) of genome [gs, ge); appends occurrences to the output.
-__device__ void scan_span(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q,
-                          uint32_t gid, uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
-{
-    const uint32_t lane = lane_id();
-    const int TL = P.TL;
-    StreamState st = {0ull, 0u, 0u, 0u};
-    uint32_t qn = 0;
-    const uint64_t chunk0 = start & ~127ull;
-    const uint64_t ord_base = chunk0 - gs;           // may wrap below zero; real occurrences add back past it
-    // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
-    const uint64_t lim = end < ge ? end : ge;
-    const uint64_t full = (lim - chunk0) >> 9;       // iterations [0, full) end at or before lim
-    const uint32_t n_steady = full > 1 ? (uint32_t)(full - 1 < 0x7fffffffull ? full - 1 : 0x7fffffffull) : 0u;
-    const uint8_t *lp = A.seq + chunk0 + 16 * lane;  // this lane's 16 bytes of the current chunk
-    uint4 nxt = load_chunk16_guarded(A, chunk0 + 16 * lane);
-    bool at_eof = false;
-
-    for (uint32_t it = 0;; it++) {
-        uint4 cur = nxt;
-        const bool steady = (it - 1u) < n_steady;
-        const uint64_t cbase = chunk0 + ((uint64_t)it << 9);
-        const uint32_t lane_off = (it << 9) + 16 * lane;
-        // prefetch the next chunk: unguarded while the next iteration is steady too
-        if (it < n_steady) nxt = ldg_stream(reinterpret_cast<const uint4 *>(lp + 512));
-        else if (cbase + 512 < ge) nxt = load_chunk16_guarded(A, cbase + 512 + 16 * lane);
-        lp += 512;
-
-        bool past_end = false, cut_lane = false;
-        if (!steady) {
-            const uint64_t laddr = cbase + 16 * lane;
-            if (cbase < start || cbase + 512 > ge)
-                mask_lane_bytes(cur, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
-            past_end = cbase + 512 > end;
-            cut_lane = laddr < start || laddr + 16 > ge;     // text itself is cut here: a short lane is not a defect
-        }
-
-        uint32_t dacc = 0, t0, t1, t2, t3w, m0, m1, m2, m3;
-        classify4(cur.x, dacc, t0, m0);
-        classify4(cur.y, dacc, t1, m1);
-        classify4(cur.z, dacc, t2, m2);
-        classify4(cur.w, dacc, t3w, m3);
-        const uint32_t codes = prmt(prmt(m3, m2, 0x0073u), prmt(m1, m0, 0x0073u), 0x5410u);   // byte 0 in the top two bits
-        const uint32_t rsk = (rev_flags8(t0, t1) << 8) | rev_flags8(t2, t3w);                 // bit 15-b: byte b has bit 6 clear
-        uint32_t n = 16 - __popc(rsk);
-        const bool lane_ok = dacc == 0 && (n >= (uint32_t)P.hist_min_n || cut_lane);
-        const bool clean = __all_sync(kFull, lane_ok) && !st.hdr;
-        if (clean) {
-            uint32_t cand = 0, W0, W1, W2;
-            // ---------------- clean iteration: only bases and line ends, no header pending ----------------
-            const uint32_t Pl = squeeze_groups(codes, rsk);
-            const uint32_t A1 = __shfl_up_sync(kFull, Pl, 1);
-            const uint32_t B2 = __shfl_up_sync(kFull, Pl, 2);
-            const uint32_t nA = __shfl_up_sync(kFull, n, 1);
-            // H = history before this lane = (lane-2's bases : lane-1's bases), the warp carry for lanes 0/1
-            uint32_t H0, H1;
-            {
-                const uint32_t o0 = lane >= 2 ? B2 : (uint32_t)st.cw;
-                const uint32_t o1 = lane >= 2 ? 0u : (uint32_t)(st.cw >> 32);
-                const uint32_t s = 2 * nA;
-                H0 = __funnelshift_lc(0u, o0, s) | A1;
-                H1 = __funnelshift_lc(o0, o1, s);
-                if (lane == 0) { H0 = (uint32_t)st.cw; H1 = (uint32_t)(st.cw >> 32); }
-            }
-            shl96(H0, H1, 2 * n, W0, W1, W2);
-            W0 |= Pl;
-            // prefilter on the central 2s-mer of the k-mer ending at each own base (d = distance from the newest)
-            const uint32_t Xlo = __funnelshift_r(W0, W1, 2 * P.out);
-            const uint32_t Xhi = __funnelshift_r(W1, W2, 2 * P.out);
-            // t(e) = X >> 2e; window d reads the word at t(d-1) & 0x1fffc and shifts it by t(d+8) (layout in kssd_device.cuh)
-            auto tsh = [&](int e) -> uint32_t {
-                return e < 0 ? (Xlo << 2) : (e < 16 ? __funnelshift_r(Xlo, Xhi, 2 * e) : (Xhi >> (2 * e - 32)));
-            };
-#pragma unroll
-            for (int d = 15; d >= 0; d--) {
-                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (tsh(d - 1) & (kPfWordMask << 2)));
-                cand = __funnelshift_l(__funnelshift_l(0u, word, tsh(d + 8)), cand, 1);      // cand = cand << 1 | flag
-            }
-            cand &= (1u << n) - 1u;
-
-            const uint32_t N = __reduce_add_sync(kFull, n);
-            if (st.since_break < (uint32_t)(TL - 1) || past_end) {
-                // start of a span / run-out past its end: filter by position inside the iteration
-                uint32_t incl = n;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= (uint32_t)o) incl += t;
-                }
-                const int o_l = (int)(incl - n);                     // valid bases before this lane
-                // ok1: since_break + t_local + 1 >= TL  with t_local = o_l + n-1-d
-                const int need = TL - 1 - (int)st.since_break - o_l; // n-1-d >= need
-                if (need > 0) {
-                    const int keep = (int)n - need;                   // d <= keep-1
-                    cand &= keep <= 0 ? 0u : ((1u << keep) - 1u);
-                }
-                if (past_end) {
-                    uint32_t E;                                      // valid bases of this iteration before `end`
-                    const int64_t rel = (int64_t)end - (int64_t)cbase;
-                    if (rel <= 0) E = 0;
-                    else {
-                        const int le = (int)(rel >> 4);
-                        const int be = (int)(rel & 15);
-                        // bytes [0,be) of the lane <-> bits 15 .. 16-be of rsk
-                        const uint32_t before = (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(rsk >> (16 - be));
-                        E = __shfl_sync(kFull, before, le);
-                    }
-                    // ok2: after_end + (t_local - E + 1) <= TL-1   for t_local >= E
-                    const int lim2 = TL - 2 - (int)st.after_end + (int)E - o_l;   // n-1-d <= lim2
-                    const int drop = (int)n - 1 - lim2;                           // d >= drop
-                    if (drop > 0) cand &= drop >= 16 ? 0u : ~((1u << drop) - 1u);
-                    st.after_end += N - E;
-                }
-            }
-            st.since_break = min(st.since_break + N, kRunCap);
-            // carry: the last two lanes hold at least TL-1 bases
-            const uint32_t P30 = __shfl_sync(kFull, Pl, 30), P31 = __shfl_sync(kFull, Pl, 31);
-            const uint32_t n31 = __shfl_sync(kFull, n, 31);
-            st.cw = ((uint64_t)P30 << (2 * n31)) | P31;
-            push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, 0u, lane_off, 0u, 16u, gid, ord_base);
-        } else {
-            general_iter16(P, A, pf, q, qn, st, cur, codes, cbase, end, past_end, lane_off, gid, ord_base);
-        }
-
-        if (!steady) {
-            if (cbase + 512 >= ge) { at_eof = true; break; }    // genome exhausted
-            if (cbase + 512 >= end) {                           // run-out: stop when no owned k-mer can still end
-                if (st.after_end >= (uint32_t)(TL - 1) || st.since_break <= st.after_end) break;
-            }
-        }
-    }
-    if (qn) { resolve_candidates(P, A, q, 0, qn, gid, ord_base); __syncwarp(); }
-    if (st.hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
-}
-
-__global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta_kernel(const SketchParams P, const ScanArgs A)
-{
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
-    WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + (kPfWords + kPf2Words) * 4);
-    {   // stage both prefilter levels (L2 -> shared), 16 B per thread per step
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
-        uint4 *dst = reinterpret_cast<uint4 *>(pf);
-        for (uint32_t i = threadIdx.x; i < (kPfWords + kPf2Words) / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
-    }
-    __syncthreads();
-    WarpQueue &q = queues[threadIdx.x >> 5];
-    const uint32_t lane = lane_id();
-    for (;;) {
-        uint32_t si = 0;
-        if (lane == 0) si = atomicAdd(A.ticket, 1u);
-        si = __shfl_sync(kFull, si, 0);
-        if (si >= A.n_spans) break;
-        const uint32_t gid = A.span_gid[si];
-        const uint64_t gs = A.goff[gid], ge = gs + A.glen[gid];
-        uint64_t start, end;
-        if (!span_extent(A, si, gid, gs, ge, start, end)) continue;
-        scan_span(P, A, pf, q, gid, gs, ge, start, end);
-    }
 }
 
 }  // namespace kssd

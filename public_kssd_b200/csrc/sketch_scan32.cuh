@@ -1,11 +1,11 @@
 // sketch_scan32.cuh -- Stage I scan, 32 bytes per lane (1 KiB per warp iteration).
 //
-// Same algorithm and helpers as sketch_scan.cuh; what changes is the granularity of the clean path: one 256-bit
-// load per lane (LDG.E.256 on sm_100), the lane's 32 bases in a 64-bit word, history from ONE neighbour lane
-// (it holds >= 2k-1 bases), 32 prefilter windows per lane.  The per-iteration coordination (shuffles, votes,
-// carries, loop control, candidate hand-off) is paid once per 1 KiB instead of once per 512 B -- the kernel is
-// instruction-issue bound, so that is where the time goes (profiles/r1_sketch_ncu_summary.md).
-// Dirty iterations fall back to two 512-byte general iterations with the 16-byte lane mapping (general_iter16).
+// The clean-path loop of the FASTA scan (helpers in sketch_scan.cuh): one 256-bit load per lane (LDG.E.256 on
+// sm_100), the lane's 32 bases in a 64-bit word, history from ONE neighbour lane (it holds >= 2k-1 bases), 32
+// prefilter windows per lane.  The per-iteration coordination (shuffles, votes, carries, loop control, candidate
+// hand-off) is paid once per KiB; an earlier 16-bytes-per-lane loop paid it twice as often and ran at 0.17 of the HBM
+// roofline against 0.21 (profiles/r1_sketch_ncu_summary.md).
+// Dirty iterations fall back to two 512-byte general iterations with a 16-byte lane mapping (general_iter16).
 #pragma once
 #include "sketch_scan.cuh"
 
@@ -135,11 +135,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
 #pragma unroll
             for (int d = 31; d >= 0; d--) {
                 const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (tsh(d - 1) & (kPfWordMask << 2)));
-#if KSSD_MULHI_ACC
-                cand = cand * 2u + __umulhi(__funnelshift_l(0u, word, tsh(d + 8)), 2u);      // same, through the FMA pipe
-#else
                 cand = __funnelshift_l(__funnelshift_l(0u, word, tsh(d + 8)), cand, 1);      // cand = cand << 1 | flag
-#endif
             }
             cand &= low_mask((int)n);
 
