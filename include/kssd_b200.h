@@ -164,6 +164,22 @@ int kssd_dist_accumulate_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const 
                               const uint64_t *qindex);
 int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev,
                              const uint64_t *qindex_dev, uint64_t n_qcodes);
+/* Fused count + reduction over peer memory (one process per GPU, reference index sharded by code range): every rank
+ * walks the posting lists of ITS code range for ALL queries and adds straight into the count rows of the rank that
+ * owns each query block -- row_blocks[o] is the device address (local, or a peer mapping opened with kssd_ipc_open)
+ * of owner o's uint32[rows_per_block][n_ref] block.  The NVLink traffic is the non-zero increments only; no partial
+ * matrix exists and no reduce-scatter runs.  Owners zero their block first; callers put a barrier before and after. */
+int kssd_dist_accumulate_peer(kssd_ctx_t *ctx, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev,
+                              const uint64_t *qindex_dev, int n_qry, int n_ref, uint32_t *const *row_blocks,
+                              int rows_per_block, int world);
+/* plain cudaMalloc'ed (IPC-exportable, zeroed) device memory and CUDA IPC plumbing for the call above */
+int kssd_dev_alloc(kssd_ctx_t *ctx, size_t bytes, void **ptr);
+int kssd_dev_zero(kssd_ctx_t *ctx, void *ptr, size_t bytes);
+void kssd_dev_free(kssd_ctx_t *ctx, void *ptr);
+int kssd_ipc_export(kssd_ctx_t *ctx, void *ptr, uint8_t handle[64]);
+int kssd_ipc_open(kssd_ctx_t *ctx, const uint8_t handle[64], void **ptr);
+int kssd_ipc_close(kssd_ctx_t *ctx, void *ptr);
+
 /* the sharedk_ct.dat matrix, uint32[Q][R] row-major (command_dist.c:708-748) */
 int kssd_dist_fetch_counts(const kssd_dist_t *d, uint32_t *ct_out);
 const uint32_t *kssd_dist_counts_dev(const kssd_dist_t *d);

@@ -24,7 +24,7 @@ dev = torch.device("cuda", local)
 tq = torch.from_numpy(qc.view(np.int32)).to(dev) if rank == 0 else None      # queries start resident on rank 0
 ti = torch.from_numpy(qi.view(np.int64)).to(dev) if rank == 0 else None
 out = {}
-for mode in ("code", "genome"):
+for mode in ("code", "code_p2p", "genome"):
     sd = parallel.ShardedDist(ctx, world, rank, code_bits=28, mode=mode).build_reference(rc, ri)
     best = 1e9
     for it in range(3):
@@ -38,10 +38,11 @@ for mode in ("code", "genome"):
     t = torch.tensor([best], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out[mode] = (float(t.item()), int(tot[0]), int(tot[1]))
+    sd.close()
 if rank == 0:
     for mode, (t, shared, nrows) in out.items():
         print(f"world={world} mode={mode}: {Q}x{R} pairs in {t * 1e3:.2f} ms (queries broadcast + count"
-              f"{' + reduce-scatter' if mode == 'code' else ''} + statistics, wall clock, max over ranks) = {Q * R / t:.3e} pairs/s; "
+              f"{' + reduce-scatter' if mode == 'code' else (' fused with the peer-memory reduction' if mode == 'code_p2p' else '')} + statistics, wall clock, max over ranks) = {Q * R / t:.3e} pairs/s; "
               f"shared total {shared}, rows {nrows}")
-    assert out["code"][1:] == out["genome"][1:], "the two sharding schemes disagree"
+    assert out["code"][1:] == out["genome"][1:] == out["code_p2p"][1:], "the sharding schemes disagree"
 dist.destroy_process_group()

@@ -192,6 +192,59 @@ __global__ void __launch_bounds__(kDistRowThreads) dist_count_rows_kernel(const 
     }
 }
 
+// Peer variant of the row kernel (reference index sharded by code range across GPUs): no zeroing here -- the owner of
+// each query block did that -- and the row of query q lives in the memory of rank q / rows_per_block, reached through
+// a peer mapping.  The RED.ADDs of remote rows travel over NVLink as they are issued, overlapped with the posting
+// walk; nothing dense is ever exchanged.
+constexpr int kMaxPeers = 16;
+struct PeerRows { uint32_t *block[kMaxPeers]; };
+
+__global__ void __launch_bounds__(kDistRowThreads) dist_count_peer_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
+                                                                              const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                              uint32_t n_qry, uint32_t n_ref, PeerRows rows, uint32_t rows_per_block)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
+        const uint32_t owner = q / rows_per_block;
+        uint32_t *row = rows.block[owner] + (uint64_t)(q - owner * rows_per_block) * n_ref;
+        const uint64_t qs = qindex[q], qe = qindex[q + 1];
+        for (uint64_t base = qs + 32ull * wid; base < qe; base += 32ull * nw) {
+            const uint64_t i = base + lane;
+            uint32_t s0 = 0, s1 = 0;
+            if (i < qe) {
+                const uint32_t c = __ldg(&qcodes[i]);
+                s0 = __ldg(&dense[c]);
+                s1 = __ldg(&dense[c + 1]);
+            }
+            // most codes of a query fall outside this rank's code range: skip the empty lists without shuffling them
+            uint32_t live = __ballot_sync(kFull, s1 > s0);
+            while (live) {
+                uint32_t r[4];
+                int src[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    src[u] = live ? __ffs(live) - 1 : -1;
+                    if (live) live &= live - 1;
+                    r[u] = 0xffffffffu;
+                    if (src[u] >= 0) {
+                        const uint32_t a = __shfl_sync(kFull, s0, src[u]), b = __shfl_sync(kFull, s1, src[u]);
+                        if (a + lane < b) r[u] = __ldg(&mco[a + lane]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (r[u] != 0xffffffffu) atomicAdd(&row[r[u]], 1u);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (src[u] >= 0) {              // lists longer than a warp (rare)
+                        const uint32_t a = __shfl_sync(kFull, s0, src[u]), b = __shfl_sync(kFull, s1, src[u]);
+                        for (uint32_t g = a + 32 + lane; g < b; g += 32) atomicAdd(&row[__ldg(&mco[g])], 1u);
+                    }
+            }
+        }
+    }
+}
+
 // ---- statistics (reference output_ctrl, command_dist.c:1251-1287), double precision ----
 struct StatParams {
     int metric, correction, kmerlen, dim_rd_len, skip_zero;

@@ -960,6 +960,83 @@ extern "C" int kssd_dist_accumulate_host(kssd_dist_t *d, const kssd_index_t *ref
     return kssd_dist_accumulate_dev(d, ref_ix, d_codes, d_index, n);
 }
 
+extern "C" int kssd_dist_accumulate_peer(kssd_ctx_t *c, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev, const uint64_t *qindex_dev, int n_qry,
+                                         int n_ref, uint32_t *const *row_blocks, int rows_per_block, int world)
+{
+    if (!c || !ref_ix || !qindex_dev || !row_blocks || n_qry <= 0 || n_ref <= 0 || rows_per_block <= 0 || world <= 0 || world > kMaxPeers)
+        return fail(KSSD_E_INVAL, "kssd_dist_accumulate_peer: bad argument");
+    if (ref_ix->n_genomes != n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, n_ref);
+    if ((int64_t)rows_per_block * world < n_qry) return fail(KSSD_E_INVAL, "kssd_dist_accumulate_peer: row blocks do not cover the queries");
+    CU(cudaSetDevice(c->device));
+    PeerRows pr{};
+    for (int i = 0; i < world; i++) pr.block[i] = row_blocks[i];
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    const uint32_t grid = (uint32_t)std::min<int>(n_qry, c->sm_count * 4);
+    dist_count_peer_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)n_qry, (uint32_t)n_ref,
+                                                                   pr, (uint32_t)rows_per_block);
+    LAUNCHED(1);
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]));
+    return KSSD_OK;
+}
+
+extern "C" int kssd_dev_alloc(kssd_ctx_t *c, size_t bytes, void **ptr)
+{
+    if (!c || !ptr || !bytes) return fail(KSSD_E_INVAL, "kssd_dev_alloc: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(ptr, bytes));
+    CU(cudaMemsetAsync(*ptr, 0, bytes, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" int kssd_dev_zero(kssd_ctx_t *c, void *ptr, size_t bytes)
+{
+    if (!c || !ptr) return fail(KSSD_E_INVAL, "kssd_dev_zero: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(ptr, 0, bytes, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" void kssd_dev_free(kssd_ctx_t *c, void *ptr)
+{
+    if (!c || !ptr) return;
+    cudaSetDevice(c->device);
+    cudaFree(ptr);
+}
+
+extern "C" int kssd_ipc_export(kssd_ctx_t *c, void *ptr, uint8_t handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!c || !ptr || !handle) return fail(KSSD_E_INVAL, "kssd_ipc_export: bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return KSSD_OK;
+}
+
+extern "C" int kssd_ipc_open(kssd_ctx_t *c, const uint8_t handle[64], void **ptr)
+{
+    if (!c || !ptr || !handle) return fail(KSSD_E_INVAL, "kssd_ipc_open: bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KSSD_OK;
+}
+
+extern "C" int kssd_ipc_close(kssd_ctx_t *c, void *ptr)
+{
+    if (!c || !ptr) return fail(KSSD_E_INVAL, "kssd_ipc_close: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaIpcCloseMemHandle(ptr));
+    return KSSD_OK;
+}
+
 extern "C" int kssd_dist_fetch_counts(const kssd_dist_t *d, uint32_t *ct_out)
 {
     if (!d || !ct_out) return fail(KSSD_E_INVAL, "kssd_dist_fetch_counts: null");

@@ -94,29 +94,78 @@ class ShardedDist:
     mode "code"   (north star): reference index sharded by code range, queries broadcast, every rank counts a full
                   Q x R matrix of partial counts, one reduce-scatter leaves each rank the final counts of its block
                   of query rows.
+    mode "code_p2p" same placement as "code", but the count kernel adds straight into the owner's rows through peer
+                  mappings (CUDA IPC over NVLink): compute and reduction are one kernel, only the non-zero increments
+                  cross the links, no partial matrix and no NCCL collective on the data path.
     mode "genome" (zero-communication alternative): rank r indexes the reference genomes of its
                   block; its Q x R/world count columns are final as they are -- no reduction at all."""
 
     def __init__(self, ctx, world: int, rank: int, code_bits: int = 28, mode: str = "code"):
-        assert mode in ("code", "genome")
+        assert mode in ("code", "code_p2p", "genome")
         self.ctx, self.world, self.rank, self.code_bits, self.mode = ctx, world, rank, code_bits, mode
         self.index = None
         self.ref_sizes = None
         self.col_lo = self.col_hi = 0
         self._partial = None
+        self._blocks = None
 
     def build_reference(self, ref_codes: np.ndarray, ref_index: np.ndarray):
         """Every rank sees the reference combco (or at least its own shard of it) and indexes its slice."""
         self.ref_sizes = np.diff(np.asarray(ref_index, dtype=np.uint64)).astype(np.uint32)
-        if self.mode == "code":
+        if self.mode in ("code", "code_p2p"):
             lo, hi = code_range(self.rank, self.world, self.code_bits)
             c, ix = filter_codes_to_range(ref_codes, ref_index, lo, hi)
         else:
             g = genome_shard(len(ref_index) - 1, self.world, self.rank)
             self.col_lo, self.col_hi = g.start, g.stop
             c, ix = genome_block(ref_codes, ref_index, g.start, g.stop) if g.stop > g.start else (np.zeros(0, np.uint32), np.zeros(2, np.uint64))
-        self.index = self.ctx.combco2mco(c, ix) if len(ix) > 1 and (self.mode == "code" or self.col_hi > self.col_lo) else None
+        self.index = self.ctx.combco2mco(c, ix) if len(ix) > 1 and (self.mode != "genome" or self.col_hi > self.col_lo) else None
         return self
+
+    # ---- peer-memory row blocks (mode "code_p2p") ----
+    def _peer_blocks(self, per: int, R: int):
+        """Allocate this rank's uint32[per][R] block (plain cudaMalloc, IPC-exportable), exchange the IPC handles and open
+        the peers' blocks.  Cached per shape."""
+        import ctypes as C
+        import torch.distributed as dist
+        from .capi import check, lib
+        if self._blocks is not None and self._blocks[0] == (per, R):
+            return self._blocks[1], self._blocks[2]
+        self._release_blocks()
+        own = C.c_void_p()
+        check(lib().kssd_dev_alloc(self.ctx._h, per * R * 4, C.byref(own)))
+        handle = (C.c_uint8 * 64)()
+        check(lib().kssd_ipc_export(self.ctx._h, own, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        ptrs = (C.c_void_p * self.world)()
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs[r] = own.value
+            else:
+                p = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(h)
+                check(lib().kssd_ipc_open(self.ctx._h, hb, C.byref(p)))
+                ptrs[r] = p.value
+        self._blocks = ((per, R), own, ptrs)
+        return own, ptrs
+
+    def _release_blocks(self):
+        import torch.distributed as dist
+        from .capi import lib
+        if self._blocks is None:
+            return
+        _, own, ptrs = self._blocks
+        for r in range(self.world):
+            if r != self.rank and ptrs[r]:
+                lib().kssd_ipc_close(self.ctx._h, ptrs[r])
+        if dist.is_initialized():
+            dist.barrier()                     # nobody frees a block a peer still maps
+        lib().kssd_dev_free(self.ctx._h, own)
+        self._blocks = None
+
+    def close(self):
+        self._release_blocks()
 
     def search(self, qry_codes=None, qry_index=None, src: int = 0, stats_opts: dict | None = None, fetch_counts: bool = True,
                fetch_stats: bool = True):
@@ -169,6 +218,34 @@ class ShardedDist:
             job.close()
             return lo, hi, block, rows
         per = (nq + self.world - 1) // self.world
+        if self.mode == "code_p2p":
+            import ctypes as C
+            from .capi import check, lib
+            own, ptrs = self._peer_blocks(per, R)
+            check(lib().kssd_dev_zero(self.ctx._h, own, per * R * 4))
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()                 # every owner has zeroed its rows
+            check(lib().kssd_dist_accumulate_peer(self.ctx._h, self.index._h, C.c_void_p(tq.data_ptr()), C.c_void_p(ti.data_ptr()), nq, R,
+                                                  ptrs, per, self.world))
+            if self.world > 1:
+                dist.barrier()                 # every rank's increments have landed
+            lo, hi = row_block(nq, self.world, self.rank)
+            rows = None
+            if stats_opts is not None and hi > lo:
+                sj = kssd.DistJob(self.ctx, qsizes[lo:hi], self.ref_sizes, ct_dev_ptr=own.value, already_filled=True)
+                rows = sj.stats(cmprsn_num=(R * nq) & 0xFFFFFFFF, fetch=fetch_stats, **stats_opts)
+                if fetch_stats:
+                    rows["qry"] += lo
+                block = sj.counts() if fetch_counts else None
+                sj.close()
+            else:
+                block = None
+                if fetch_counts and hi > lo:
+                    sj = kssd.DistJob(self.ctx, qsizes[lo:hi], self.ref_sizes, ct_dev_ptr=own.value, already_filled=True)
+                    block = sj.counts()
+                    sj.close()
+            return lo, hi, block, rows
         rows_padded = per * self.world
         if self._partial is None or tuple(self._partial.shape) != (rows_padded, R):
             self._partial = torch.zeros((rows_padded, R), dtype=torch.int32, device=dev)     # padding rows stay zero

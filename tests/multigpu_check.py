@@ -38,11 +38,16 @@ def main():
     # ---- 2. dist sharded by code range ----
     rc, ri = synth.synth_sketches(3000, 300, seed=5, cluster_size=20, code_bits=20)
     qc, qi = synth.synth_sketches(101, 300, seed=5, cluster_size=4, code_bits=20)
-    sd = parallel.ShardedDist(ctx, world, rank, code_bits=20).build_reference(rc, ri)
     opts = dict(metric=0, correction=0, dthreshold=1.0, skip_zero=1)
-    lo, hi, block, rows = sd.search(qc if rank == 0 else None, qi if rank == 0 else None, src=0, stats_opts=opts)
-    parts = [None] * world
-    dist.all_gather_object(parts, (lo, hi, block, rows))
+    results = {}
+    for mode in ("code", "code_p2p"):
+        sd = parallel.ShardedDist(ctx, world, rank, code_bits=20, mode=mode).build_reference(rc, ri)
+        lo, hi, block, rows = sd.search(qc if rank == 0 else None, qi if rank == 0 else None, src=0, stats_opts=opts)
+        got = [None] * world
+        dist.all_gather_object(got, (lo, hi, block, rows))
+        results[mode] = got
+        sd.close()
+    parts = results["code"]
     ok2 = True
     if rank == 0:
         ix = ctx.combco2mco(rc, ri)
@@ -53,7 +58,11 @@ def main():
         got = np.concatenate([p[2] for p in sorted(parts, key=lambda p: p[0]) if p[1] > p[0]])
         got_rows = np.concatenate([p[3] for p in sorted(parts, key=lambda p: p[0]) if p[3] is not None and len(p[3])])
         ok2 = np.array_equal(got, ct) and got_rows.tobytes() == ref_rows.tobytes() and ct.sum() > 0
-        print(f"multigpu_check world={world}: sketch_sharding={'ok' if ok1 else 'FAIL'} dist_code_range_reduce_scatter="
+        p2p = results["code_p2p"]
+        got2 = np.concatenate([p[2] for p in sorted(p2p, key=lambda p: p[0]) if p[1] > p[0]])
+        rows2 = np.concatenate([p[3] for p in sorted(p2p, key=lambda p: p[0]) if p[3] is not None and len(p[3])])
+        ok2 = ok2 and np.array_equal(got2, ct) and rows2.tobytes() == ref_rows.tobytes()
+        print(f"multigpu_check world={world}: sketch_sharding={'ok' if ok1 else 'FAIL'} dist_code_range_reduce_scatter_and_p2p="
               f"{'ok' if ok2 else 'FAIL'} shared_total={int(ct.sum())} rows={len(ref_rows)}")
     flag = torch.tensor([int(ok1 and ok2)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
