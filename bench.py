@@ -333,22 +333,30 @@ def main():
         obj = [ids0 if rank == 0 else None, index_host if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         ref_ids, ref_index = obj
-        sd = parallel.ShardedDist(ctx, world, rank, code_bits=4 * min(7, K - DRLEVEL)).build_reference(ref_ids, ref_index)
-        times = []
-        for it in range(3):
-            barrier()
-            t0 = time.perf_counter()
-            lo, hi, block, rows = sd.search(ref_ids if rank == 0 else None, ref_index if rank == 0 else None, src=0, stats_opts={})
-            barrier()
-            times.append(time.perf_counter() - t0)
-        tt = torch.tensor([min(times)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        own = np.diff(ref_index).astype(np.uint32)
-        dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": pairs / float(tt.item()), "ms": float(tt.item()) * 1e3,
-                          "rows_on_rank0": int(len(rows)) if rows is not None else 0,
-                          "diag_ok": bool(np.array_equal(np.diag(block[:, lo:hi]), own[lo:hi])) if hi > lo else True,
-                          "sharding": "reference index by code range across ranks, query sketches broadcast, NCCL reduce-scatter of partial "
-                                      "count matrices, statistics on the owner of each query block (wall clock incl. collectives)"})
+        per_mode = {}
+        for mode in ("code", "code_p2p"):
+            sd = parallel.ShardedDist(ctx, world, rank, code_bits=4 * min(7, K - DRLEVEL), mode=mode).build_reference(ref_ids, ref_index)
+            times = []
+            for it in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                lo, hi, block, rows = sd.search(ref_ids if rank == 0 else None, ref_index if rank == 0 else None, src=0, stats_opts={})
+                barrier()
+                times.append(time.perf_counter() - t0)
+            tt = torch.tensor([min(times)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            own = np.diff(ref_index).astype(np.uint32)
+            per_mode[mode] = (float(tt.item()), int(len(rows)) if rows is not None else 0,
+                              bool(np.array_equal(np.diag(block[:, lo:hi]), own[lo:hi])) if hi > lo else True)
+            sd.close()
+        t_best = per_mode["code_p2p"][0]
+        dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": pairs / t_best, "ms": t_best * 1e3,
+                          "ms_nccl_reduce_scatter": per_mode["code"][0] * 1e3,
+                          "rows_on_rank0": per_mode["code_p2p"][1], "diag_ok": per_mode["code_p2p"][2] and per_mode["code"][2],
+                          "rows_agree": per_mode["code_p2p"][1] == per_mode["code"][1],
+                          "sharding": "reference index by code range across ranks, query sketches broadcast; the count kernel adds into the "
+                                      "owning rank's rows over peer memory (ms), or partial matrices + NCCL reduce-scatter "
+                                      "(ms_nccl_reduce_scatter); statistics on the owner of each query block (wall clock incl. barriers)"})
 
     # ---- end to end through the C-ABI with host buffers ----
     host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)

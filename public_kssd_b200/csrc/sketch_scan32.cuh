@@ -52,7 +52,9 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
 {
     const uint32_t lane = lane_id();
     const int TL = P.TL;
-    StreamState st = {0ull, 0u, 0u, 0u};
+    // stream state in registers; it is packed into a StreamState only around the out-of-line general iterations
+    uint64_t cw = 0;
+    uint32_t since_break = 0, after_end = 0, hdr = 0;
     uint32_t qn = 0;
     const uint64_t chunk0 = start & ~127ull;
     const uint64_t ord_base = chunk0 - gs;           // may wrap below zero; real occurrences add back past it
@@ -98,7 +100,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
         const uint32_t nA = 16 - __popc(rskA), nB = 16 - __popc(rskB);
         const uint32_t n = nA + nB;
         const bool lane_ok = dacc == 0 && (n >= (uint32_t)(TL - 1) || cut_lane);
-        const bool clean = __all_sync(kFull, lane_ok) && !st.hdr;
+        const bool clean = __all_sync(kFull, lane_ok) && !hdr;
 
         if (clean) {
             uint32_t PA = prmt(prmt(m3, m2, 0x0073u), prmt(m1, m0, 0x0073u), 0x5410u);
@@ -118,7 +120,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
             P0 |= PB;
             // history = the previous lane's bases (it holds >= 2k-1 of them), the warp carry for lane 0
             uint32_t H0 = __shfl_up_sync(kFull, P0, 1), H1 = __shfl_up_sync(kFull, P1, 1);
-            if (lane == 0) { H0 = (uint32_t)st.cw; H1 = (uint32_t)(st.cw >> 32); }
+            if (lane == 0) { H0 = (uint32_t)cw; H1 = (uint32_t)(cw >> 32); }
             uint32_t W0, W1, W2, W3;
             shl128(H0, H1, 2 * n, W0, W1, W2, W3);
             W0 |= P0;
@@ -140,7 +142,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
             cand &= low_mask((int)n);
 
             const uint32_t N = __reduce_add_sync(kFull, n);
-            if (st.since_break < (uint32_t)(TL - 1) || past_end) {
+            if (since_break < (uint32_t)(TL - 1) || past_end) {
                 // start of a span / run-out past its end: filter by position inside the iteration
                 uint32_t incl = n;
 #pragma unroll
@@ -150,7 +152,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
                 }
                 const int o_l = (int)(incl - n);                     // valid bases before this lane
                 // ok1: since_break + t_local + 1 >= TL  with t_local = o_l + n-1-d
-                const int need = TL - 1 - (int)st.since_break - o_l; // n-1-d >= need
+                const int need = TL - 1 - (int)since_break - o_l; // n-1-d >= need
                 if (need > 0) cand &= low_mask(max((int)n - need, 0));
                 if (past_end) {
                     uint32_t E;                                      // valid bases of this iteration before `end`
@@ -168,17 +170,18 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
                         E = __shfl_sync(kFull, (uint32_t)o_l + vb, le);
                     }
                     // ok2: after_end + (t_local - E + 1) <= TL-1   for t_local >= E
-                    const int lim2 = TL - 2 - (int)st.after_end + (int)E - o_l;   // n-1-d <= lim2
+                    const int lim2 = TL - 2 - (int)after_end + (int)E - o_l;   // n-1-d <= lim2
                     const int drop = (int)n - 1 - lim2;                           // d >= drop
                     if (drop > 0) cand &= ~low_mask(min(drop, 32));
-                    st.after_end += N - E;
+                    after_end += N - E;
                 }
             }
-            st.since_break = min(st.since_break + N, kRunCap);
-            st.cw = ((uint64_t)__shfl_sync(kFull, P1, 31) << 32) | __shfl_sync(kFull, P0, 31);
+            since_break = min(since_break + N, kRunCap);
+            cw = ((uint64_t)__shfl_sync(kFull, P1, 31) << 32) | __shfl_sync(kFull, P0, 31);
             push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, W3, lane_off, 0u, 32u, gid, ord_base);
         } else {
             // two general 512-byte iterations with the 16-byte lane mapping (reloaded: L1/L2 hits)
+            StreamState st = {cw, since_break, after_end, hdr};
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 const uint64_t sbase = cbase + 512ull * h;
@@ -195,17 +198,18 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
                 const uint32_t codes = prmt(prmt(k3, k2, 0x0073u), prmt(k1, k0, 0x0073u), 0x5410u);
                 general_iter16(P, A, pf, q, qn, st, c16, codes, sbase, end, sbase + 512 > end, (it << 10) + 512u * h + 16 * lane, gid, ord_base);
             }
+            cw = st.cw; since_break = st.since_break; after_end = st.after_end; hdr = st.hdr;
         }
 
         if (!steady) {
             if (cbase + 1024 >= ge) { at_eof = true; break; }   // genome exhausted
             if (cbase + 1024 >= end) {                          // run-out: stop when no owned k-mer can still end
-                if (st.after_end >= (uint32_t)(TL - 1) || st.since_break <= st.after_end) break;
+                if (after_end >= (uint32_t)(TL - 1) || since_break <= after_end) break;
             }
         }
     }
     if (qn) { resolve_candidates(P, A, q, 0, qn, gid, ord_base); __syncwarp(); }
-    if (st.hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
+    if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
 }
 
 __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta32_kernel(const SketchParams P, const ScanArgs A)
