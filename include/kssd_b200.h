@@ -215,6 +215,18 @@ int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *opts);
 int kssd_dist_fetch_stats(const kssd_dist_t *d, kssd_stat_row_t *rows_out);
 void kssd_dist_free(kssd_dist_t *d);
 
+/* distance.out text (host side, multi-threaded): the header line dist_print_nobin writes
+ * (command_dist.c:1188-1195) and one line per statistics row exactly as output_ctrl prints it
+ * (command_dist.c:1267-1285: "%s\t%s\t%u-%u|%u|%u\t%.6lf\t%.6lf", then "\t%E\t%E" for
+ * outfields >= 1 and "\t[%.6lf,%.6lf]\t[%.6lf,%.6lf]" for outfields >= 2).  Names are the
+ * name blocks of cofiles.stat / mcofiles.stat: NUL-terminated strings `name_stride` bytes apart
+ * (256 in the reference).  The text is allocated by the library (free with kssd_host_free);
+ * with_header != 0 prepends the header.  n_threads <= 0: all hardware threads. */
+int kssd_format_distance_rows(const kssd_stat_row_t *rows, size_t n_rows, const char *qry_names, const char *ref_names,
+                              size_t name_stride, int metric, int outfields, int with_header, int n_threads,
+                              char **text_out, size_t *text_len);
+void kssd_host_free(void *p);
+
 /* device time (ms, CUDA events on the context stream) of the last scan / index / count / stats
  * kernel sequence issued through this context; which = 0 sketch scan, 1 sketch total,
  * 2 index build, 3 dist counts, 4 dist stats */

@@ -27,6 +27,7 @@ SYMBOLS = [
     "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
     "kssd_dist_counts_dev", "kssd_dist_accumulate_peer", "kssd_dev_alloc", "kssd_dev_zero", "kssd_dev_free",
     "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_fetch_stats", "kssd_dist_free",
+    "kssd_format_distance_rows", "kssd_host_free",
 ]
 
 MODE_FASTA, MODE_FASTA_UNIQ, MODE_FASTQ, MODE_FASTQ_ABUND = 0, 1, 2, 3
@@ -136,6 +137,10 @@ def lib() -> C.CDLL:
     L.kssd_dist_fetch_stats.argtypes = [vp, vp]
     L.kssd_dist_free.argtypes = [vp]
     L.kssd_dist_free.restype = None
+    L.kssd_format_distance_rows.argtypes = [vp, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.kssd_host_free.argtypes = [vp]
+    L.kssd_host_free.restype = None
     _lib = L
     return L
 

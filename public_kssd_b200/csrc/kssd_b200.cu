@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kssd_b200.h"
@@ -1163,3 +1164,68 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
 
     delete d;
 }
+
+
+// ---- distance.out text (reference dist_print_nobin / output_ctrl, command_dist.c:1188-1195, 1267-1285) ----
+namespace {
+const char *const kDistHeader[2][3] = {{"Jaccard\tMashD", "P-value(J)\tFDR(J)", "Jaccard_CI\tMashD_CI"},
+                                       {"ContainmentM\tAafD", "P-value(C)\tFDR(C)", "ContainmentM_CI\tAafD_CI"}};
+
+void format_rows_range(const kssd_stat_row_t *rows, size_t lo, size_t hi, const char *qn, const char *rn, size_t stride, int outfields,
+                       std::string &out)
+{
+    char line[1024];
+    out.reserve((hi - lo) * 160);
+    for (size_t i = lo; i < hi; i++) {
+        const kssd_stat_row_t &r = rows[i];
+        int n = snprintf(line, sizeof line, "%s\t%s\t%u-%u|%u|%u\t%.6lf\t%.6lf", qn + (size_t)r.qry * stride, rn + (size_t)r.ref * stride, r.shared,
+                         r.rs_u, r.ref_size, r.qry_size, r.metric, r.dist);
+        if (n < 0) n = 0;
+        if ((size_t)n >= sizeof line) n = sizeof line - 1;
+        if (outfields >= 1) n += snprintf(line + n, sizeof line - n, "\t%E\t%E", r.pvalue, r.fdr);
+        if (outfields >= 2 && (size_t)n < sizeof line)
+            n += snprintf(line + n, sizeof line - n, "\t[%.6lf,%.6lf]\t[%.6lf,%.6lf]", r.ci_metric_lo, r.ci_metric_hi, r.ci_dist_lo, r.ci_dist_hi);
+        if ((size_t)n >= sizeof line - 1) n = sizeof line - 2;
+        line[n++] = '\n';
+        out.append(line, (size_t)n);
+    }
+}
+}  // namespace
+
+extern "C" int kssd_format_distance_rows(const kssd_stat_row_t *rows, size_t n_rows, const char *qry_names, const char *ref_names,
+                                         size_t name_stride, int metric, int outfields, int with_header, int n_threads, char **text_out,
+                                         size_t *text_len)
+{
+    if (!text_out || !text_len || (n_rows && (!rows || !qry_names || !ref_names)) || metric < 0 || metric > 1 || outfields < 0 || outfields > 2)
+        return fail(KSSD_E_INVAL, "kssd_format_distance_rows: bad argument");
+    unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
+    nt = (unsigned)std::min<size_t>(nt, std::max<size_t>(1, n_rows / 4096));
+    std::vector<std::string> parts(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) {
+        const size_t lo = n_rows * t / nt, hi = n_rows * (t + 1) / nt;
+        if (t + 1 == nt) format_rows_range(rows, lo, hi, qry_names, ref_names, name_stride, outfields, parts[t]);
+        else th.emplace_back(format_rows_range, rows, lo, hi, qry_names, ref_names, name_stride, outfields, std::ref(parts[t]));
+    }
+    for (auto &x : th) x.join();
+    std::string head;
+    if (with_header) {
+        head = "Qry\tRef\tShared_k|Ref_s|Qry_s";
+        for (int i = 0; i <= outfields; i++) { head += "\t"; head += kDistHeader[metric][i]; }
+        head += "\n";
+    }
+    size_t total = head.size();
+    for (auto &p : parts) total += p.size();
+    char *buf = (char *)malloc(total + 1);
+    if (!buf) return fail(KSSD_E_NOMEM, "kssd_format_distance_rows: out of host memory");
+    size_t off = 0;
+    memcpy(buf, head.data(), head.size());
+    off += head.size();
+    for (auto &p : parts) { memcpy(buf + off, p.data(), p.size()); off += p.size(); }
+    buf[off] = 0;
+    *text_out = buf;
+    *text_len = off;
+    return KSSD_OK;
+}
+
+extern "C" void kssd_host_free(void *p) { free(p); }

@@ -139,6 +139,24 @@ def format_stat_rows(rows, qry_names, ref_names, metric: int = 0, outfields: int
     return "".join(out)
 
 
+def format_distance_out(rows, qry_names, ref_names, metric: int = 0, outfields: int = 2, header: bool = True, threads: int = 0) -> bytes:
+    """distance.out through the library's native multi-threaded formatter (kssd_format_distance_rows): header +
+    one line per row, byte-identical to dist_print_nobin / output_ctrl (command_dist.c:1188-1195, 1267-1285).
+    `format_stat_rows` above is the plain-Python statement of the same text, kept for the tests."""
+    import ctypes as C
+    from .capi import check, lib
+    rows = np.ascontiguousarray(rows)
+    assert rows.dtype.itemsize == 88, "rows must be kssd_stat_row_t records"
+    qn, rn = _names_block(qry_names), _names_block(ref_names)
+    text, n = C.c_void_p(), C.c_size_t()
+    check(lib().kssd_format_distance_rows(rows.ctypes.data_as(C.c_void_p), len(rows), qn, rn, 256, metric, outfields, int(header), threads,
+                                          C.byref(text), C.byref(n)))
+    try:
+        return C.string_at(text, n.value)
+    finally:
+        lib().kssd_host_free(text)
+
+
 # ------------------------------------------------------------------------------------------------
 # sketch directories: what run_stageI leaves behind, and combine_queries (command_dist.c:1323-1475)
 # ------------------------------------------------------------------------------------------------

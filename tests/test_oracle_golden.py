@@ -141,6 +141,9 @@ def test_distance_out_text_identical_to_reference(oracle_mod, tag, metric, outfi
             out.append("\t".join(f))
         return out
     assert norm(mine) == norm(ref_txt)
+    # the library's native formatter (host-only entry point of the C-ABI) writes the same bytes
+    native = hostfmt.format_distance_out(rows, qn, rn, metric, outfields, header=True, threads=3).decode()
+    assert native == mine
 
 
 def test_stat_files_roundtrip(tmp_path):
