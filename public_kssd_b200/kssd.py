@@ -197,6 +197,12 @@ class Context:
         check(lib().kssd_index_build_host(self._h, ptr(combco, C.c_uint32), ptr(cbdcoindex, C.c_uint64), len(cbdcoindex) - 1, C.byref(h)))
         return Index(self, h)
 
+    def combco2mco_dev(self, codes_dev_ptr: int, index_dev_ptr: int, n_genomes: int, n_codes: int) -> "Index":
+        """combco2mco on device-resident input: uint32 codes[n_codes], uint64 index[n_genomes + 1] (kssd_index_build_dev)."""
+        h = C.c_void_p()
+        check(lib().kssd_index_build_dev(self._h, C.c_void_p(codes_dev_ptr), C.c_void_p(index_dev_ptr), n_genomes, n_codes, C.byref(h)))
+        return Index(self, h)
+
     def index_from_dense(self, dense_incl: np.ndarray, gids: np.ndarray, n_genomes: int) -> "Index":
         dense_incl = np.ascontiguousarray(dense_incl, dtype=np.uint64)
         gids = np.ascontiguousarray(gids, dtype=np.uint32)

@@ -81,6 +81,43 @@ def reduce_scatter_rows(partial, world: int, rank: int):
     return out
 
 
+def exchange_codes_by_range(codes, index, gid_lo: int, n_genomes: int, world: int, rank: int, code_bits: int = 28, device=None):
+    """The exchange step between Stage I (sharded by genome) and Stage II (sharded by code range), SURVEY.md s8(e):
+    this rank holds the sketches (codes, index) of the contiguous genome block starting at `gid_lo`; after one
+    all-to-all every rank holds, for ALL `n_genomes` genomes, the codes that fall in ITS slice of the code space --
+    a combco (codes, index[n_genomes + 1]) ready for combco2mco.  Genome blocks ascend with the rank, the routing
+    sort is stable, so the received codes arrive grouped by genome id without any re-sort.
+    codes / index: numpy arrays or torch tensors (CUDA tensors stay on the device under NCCL).  Returns torch tensors
+    (codes int32, index int64) on `device`."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device(device) if device is not None else (codes.device if torch.is_tensor(codes) else torch.device("cpu"))
+    c = (codes if torch.is_tensor(codes) else torch.from_numpy(np.ascontiguousarray(codes).view(np.int32))).to(dev).to(torch.int32)
+    ix = (index if torch.is_tensor(index) else torch.from_numpy(np.ascontiguousarray(index).astype(np.int64))).to(dev).to(torch.int64)
+    n_local = ix.numel() - 1
+    counts = ix[1:] - ix[:-1]
+    gids = torch.repeat_interleave(torch.arange(gid_lo, gid_lo + n_local, device=dev, dtype=torch.int32), counts)
+    bounds = torch.tensor([code_range(r, world, code_bits)[0] for r in range(1, world)], device=dev, dtype=torch.int32)
+    dest = torch.bucketize(c, bounds, right=True)                       # owner rank of every code
+    order = torch.sort(dest, stable=True).indices
+    send_counts = torch.bincount(dest, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    if world > 1:
+        dist.all_to_all_single(recv_counts, send_counts)
+    else:
+        recv_counts.copy_(send_counts)
+    ss, rs = send_counts.tolist(), recv_counts.tolist()
+    payload = torch.stack([c[order], gids[order]], dim=1).contiguous()   # (code, gid) pairs, 8 B per posting
+    got = torch.empty((sum(rs), 2), dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_to_all_single(got, payload, output_split_sizes=rs, input_split_sizes=ss)
+    else:
+        got.copy_(payload)
+    new_index = torch.zeros(n_genomes + 1, dtype=torch.int64, device=dev)
+    new_index[1:] = torch.cumsum(torch.bincount(got[:, 1].to(torch.int64), minlength=n_genomes), 0)
+    return got[:, 0].contiguous(), new_index
+
+
 def genome_block(codes: np.ndarray, index: np.ndarray, lo: int, hi: int):
     """combco (codes, index) of the genomes [lo, hi) only, index rebased to start at 0."""
     index = np.asarray(index, dtype=np.uint64)
@@ -120,6 +157,23 @@ class ShardedDist:
             self.col_lo, self.col_hi = g.start, g.stop
             c, ix = genome_block(ref_codes, ref_index, g.start, g.stop) if g.stop > g.start else (np.zeros(0, np.uint32), np.zeros(2, np.uint64))
         self.index = self.ctx.combco2mco(c, ix) if len(ix) > 1 and (self.mode != "genome" or self.col_hi > self.col_lo) else None
+        return self
+
+    def build_reference_exchanged(self, local_codes, local_index, gid_lo: int, n_genomes: int, ref_sizes):
+        """Stage I -> II across ranks without ever gathering the reference: this rank brings the sketches of ITS genome
+        block (as Stage I left them), `exchange_codes_by_range` routes every code to the rank that owns its code range,
+        and the rank indexes what it received.  ref_sizes: sketch sizes of all genomes (a few bytes each, all-gathered
+        by the caller)."""
+        assert self.mode in ("code", "code_p2p")
+        import torch
+        self.ref_sizes = np.asarray(ref_sizes, dtype=np.uint32)
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        c, ix = exchange_codes_by_range(local_codes, local_index, gid_lo, n_genomes, self.world, self.rank, self.code_bits, device=dev)
+        if c.is_cuda:
+            self.index = self.ctx.combco2mco_dev(c.data_ptr(), ix.data_ptr(), n_genomes, int(c.numel()))
+            torch.cuda.synchronize()
+        else:
+            self.index = self.ctx.combco2mco(c.numpy().view(np.uint32), ix.numpy().astype(np.uint64))
         return self
 
     # ---- peer-memory row blocks (mode "code_p2p") ----

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """N-GPU check, launched with torchrun (NCCL):  python -m torch.distributed.run --nproc-per-node N tests/multigpu_check.py
   1. Stage I sharded by genome: every rank sketches its genomes, results gathered on rank 0 == single-GPU result.
-  2. Stage III sharded by code range + reduce-scatter == single-GPU count matrix and statistics, bit for bit.
+  2. Stage III sharded by code range (NCCL reduce-scatter, and the peer-memory count kernel) == single-GPU count
+     matrix and statistics, bit for bit.
+  3. The whole path across ranks: Stage I shards -> all-to-all by code range -> per-rank index -> peer-memory search
+     == single-GPU all-vs-all of the same genomes.
 Not a pytest file: the default GPU tier has one device."""
 import os
 import sys
@@ -64,7 +67,36 @@ def main():
         ok2 = ok2 and np.array_equal(got2, ct) and rows2.tobytes() == ref_rows.tobytes()
         print(f"multigpu_check world={world}: sketch_sharding={'ok' if ok1 else 'FAIL'} dist_code_range_reduce_scatter_and_p2p="
               f"{'ok' if ok2 else 'FAIL'} shared_total={int(ct.sum())} rows={len(ref_rows)}")
-    flag = torch.tensor([int(ok1 and ok2)], device="cuda")
+    # ---- 3. sketch shards -> exchange by code range -> index -> search, nothing gathered on one rank ----
+    code_bits = 4 * (8 - 2)
+    n_g = len(genomes)
+    local_sizes = np.diff(sk.index[0]).astype(np.uint32) if mine else np.zeros(0, np.uint32)
+    all_sizes = [None] * world
+    dist.all_gather_object(all_sizes, local_sizes)
+    ref_sizes = np.concatenate(all_sizes)
+    sd = parallel.ShardedDist(ctx, world, rank, code_bits=code_bits, mode="code_p2p")
+    sd.build_reference_exchanged(sk.ids[0] if mine else np.zeros(0, np.uint32), sk.index[0] if mine else np.zeros(1, np.uint64),
+                                 mine[0] if mine else 0, n_g, ref_sizes)
+    if rank == 0:
+        qc3, qi3 = full.ids[0], full.index[0]
+    lo, hi, block, rows = sd.search(qc3 if rank == 0 else None, qi3 if rank == 0 else None, src=0, stats_opts=opts)
+    got3 = [None] * world
+    dist.all_gather_object(got3, (lo, hi, block, rows))
+    sd.close()
+    ok3 = True
+    if rank == 0:
+        ix = ctx.combco2mco(full.ids[0], full.index[0])
+        sz = np.diff(full.index[0]).astype(np.uint32)
+        job = kssd.DistJob(ctx, sz, sz)
+        job.accumulate(ix, full.ids[0], full.index[0])
+        ct3 = job.counts()
+        rows3 = job.stats(**opts)
+        g3 = np.concatenate([p[2] for p in sorted(got3, key=lambda p: p[0]) if p[1] > p[0]])
+        r3 = np.concatenate([p[3] for p in sorted(got3, key=lambda p: p[0]) if p[3] is not None and len(p[3])])
+        ok3 = np.array_equal(ref_sizes, sz) and np.array_equal(g3, ct3) and r3.tobytes() == rows3.tobytes() and np.array_equal(np.diag(ct3), sz)
+        print(f"multigpu_check world={world}: sketch->exchange->index->search pipeline={'ok' if ok3 else 'FAIL'} "
+              f"shared_total={int(ct3.sum())} rows={len(rows3)}")
+    flag = torch.tensor([int(ok1 and ok2 and ok3)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

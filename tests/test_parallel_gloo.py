@@ -87,3 +87,36 @@ def test_sharded_dist_plan_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert sum(s for _, _, s, _ in res) == res[0][3]        # partial counts add up to the full matrix
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 41                                              # not a multiple of the world size
+        rc, ri = synth.synth_sketches(n, 250, seed=9, cluster_size=7)
+        g = parallel.genome_shard(n, world, rank)
+        lc, li = parallel.genome_block(rc, ri, g.start, g.stop)
+        c, ix = parallel.exchange_codes_by_range(lc, li, g.start, n, world, rank, 28)
+        wc, wi = parallel.filter_codes_to_range(rc, ri, *parallel.code_range(rank, world, 28))
+        ok = np.array_equal(c.numpy().view(np.uint32), wc) and np.array_equal(ix.numpy().astype(np.uint64), wi)
+        q.put((rank, bool(ok), int(c.numel())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_codes_by_range(world):
+    """Stage I shards (by genome) -> Stage II shards (by code range) through one all-to-all: every rank ends up with
+    exactly the slice filter_codes_to_range would cut from the whole reference, genomes in order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(nc for _, _, nc in res) == len(synth.synth_sketches(41, 250, seed=9, cluster_size=7)[0])
