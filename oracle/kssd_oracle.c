@@ -124,6 +124,45 @@ int orc_fasta2co(const orc_ctx_t *c, const uint8_t *buf, size_t len, int uniq, u
     return 0;
 }
 
+/* iseq2comem.c:78-186 reads2mco (--byread): FASTA-formatted reads, one sketch per '>' record, NO hash table --
+ * every sampled k-mer is emitted at once, duplicates and code 0 included (:170-172).  Emission i carries the id
+ * (drtuple >> comp_code_bits), its component (drtuple % component_num) and the record counter `readn` at that
+ * moment (0 = before the first header); the Python side turns read_of into the inclusive per-component index
+ * the reference writes at :175-180.  Returns the number of emissions, -2 on a header that runs into EOF
+ * (:152), -4 if cap is too small. */
+long orc_reads2mco(const orc_ctx_t *c, const uint8_t *buf, size_t len, uint32_t *ids, int32_t *comp,
+                   uint64_t *read_of, size_t cap, uint64_t *n_reads)
+{
+    uint64_t fwd = 0, rc = 0, run = 0, dr, readn = 0;
+    size_t p = 0, n = 0;
+    while (p < len) {
+        uint8_t ch = buf[p++];
+        int b = base_code(ch);
+        if (b < 0) {
+            if (ch == '\n' || ch == '\r') continue;
+            if (ch == '>') {
+                readn++;                                        /* :140 */
+                while (p < len && buf[p] != '\n') p++;
+                if (p >= len) return -2;
+                p++;
+            }
+            run = 0;
+            continue;
+        }
+        fwd = ((fwd << 2) | (uint64_t)b) & c->tupmask;
+        rc = (rc >> 2) + (((uint64_t)b ^ 3ULL) << c->crvsaddmove);
+        if (++run < (uint64_t)c->TL) continue;
+        if (!sample_kmer(c, fwd, rc, &dr)) continue;
+        if (n >= cap) return -4;
+        ids[n] = (uint32_t)(dr >> c->comp_code_bits);
+        comp[n] = (int32_t)(dr % (uint64_t)c->component_num);
+        read_of[n] = readn;
+        n++;
+    }
+    if (n_reads) *n_reads = readn;
+    return (long)n;
+}
+
 /* ---- fgets emulation over a memory buffer (for the fastq readers) ---- */
 typedef struct { const uint8_t *b; size_t n, p; int eof; } memf_t;
 

@@ -50,6 +50,11 @@ int orc_fastq2co(const orc_ctx_t *c, const uint8_t *buf, size_t len, int Q, int 
 /* iseq2comem.c:554-615 with p == 1 (the only deterministic setting). */
 int orc_shortreads2koc(const orc_ctx_t *c, const uint8_t *buf, size_t len, uint64_t *co);
 
+/* iseq2comem.c:78-186 reads2mco (--byread): every sampled k-mer of a FASTA-formatted read file in stream order,
+ * with its component and the '>' record counter at emission.  Returns the count, -2 / -4 on error. */
+long orc_reads2mco(const orc_ctx_t *c, const uint8_t *buf, size_t len, uint32_t *ids, int32_t *comp,
+                   uint64_t *read_of, size_t cap, uint64_t *n_reads);
+
 /* Writers, slot order.  mode 0: wrt_co2cmpn_use_inn_subctx (iseq2comem.c:525-551);
  * mode 1: write_fqco2file (:499-524); mode 2: write_fqkoc2files (:435-471, fills abund).
  * Outputs ids[i], comp[i] (component of entry i), abund[i] (mode 2, may be NULL otherwise).

@@ -46,6 +46,8 @@ def lib() -> C.CDLL:
         L.orc_fasta2co.argtypes = [C.c_void_p, u8p, C.c_size_t, C.c_int, u64p]
         L.orc_fastq2co.argtypes = [C.c_void_p, u8p, C.c_size_t, C.c_int, C.c_int, u64p, C.POINTER(C.c_int)]
         L.orc_shortreads2koc.argtypes = [C.c_void_p, u8p, C.c_size_t, u64p]
+        L.orc_reads2mco.argtypes = [C.c_void_p, u8p, C.c_size_t, u32p, i32p, u64p, C.c_size_t, u64p]
+        L.orc_reads2mco.restype = C.c_long
         L.orc_write_co.argtypes = [C.c_void_p, u64p, C.c_int, u32p, i32p, u16p]
         L.orc_write_co.restype = C.c_size_t
         L.orc_combco2mco.argtypes = [u32p, u64p, C.c_int, C.c_int, u64p, u32p]
@@ -135,6 +137,25 @@ class Ctx:
             raise RuntimeError(f"orc_fasta2co rc={rc}")
         ids, comp, _ = self._emit(0)
         return ids, comp
+
+    def byread(self, data):
+        """reads2mco (--byread): -> (n_reads, {component: (ids in stream order, index)}) with index = the reference's
+        combco.index.<c>: inclusive cumulative counts for record 0 (before the first '>') .. n_reads."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        cap = max(int(a.size), 1)
+        ids, comp, rd = np.empty(cap, np.uint32), np.empty(cap, np.int32), np.empty(cap, np.uint64)
+        nr = C.c_uint64(0)
+        n = lib().orc_reads2mco(self.ptr, _p(a, C.c_uint8), a.size, _p(ids, C.c_uint32), _p(comp, C.c_int32), _p(rd, C.c_uint64), cap,
+                                C.byref(nr))
+        if n < 0:
+            raise RuntimeError(f"orc_reads2mco rc={n}")
+        ids, comp, rd = ids[:n], comp[:n], rd[:n]
+        out = {}
+        for c in range(self.component_num):
+            m = comp == c
+            cnt = np.bincount(rd[m].astype(np.int64), minlength=int(nr.value) + 1)
+            out[c] = (ids[m].copy(), np.cumsum(cnt, dtype=np.uint64))
+        return int(nr.value), out
 
     def fastq(self, data, Q: int = 0, M: int = 1):
         a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data

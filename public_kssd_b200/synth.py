@@ -116,6 +116,45 @@ def messy_fasta(nbases: int, seed: int, ncontigs: int = 7, width: int = 60, n_ra
     return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
 
 
+def to_read_fasta(bases: np.ndarray, n_reads: int, seed: int, min_len: int = 30, max_len: int = 3000, width: int = 70,
+                  messy: bool = False, leading_sequence: bool = False) -> np.ndarray:
+    """FASTA-formatted reads (the input of `--byread`, reference reads2mco): n_reads records cut from `bases` at
+    pseudo-random places, lengths in [min_len, max_len], every third record on a single line.  messy: N / lower-case
+    stretches, a '>' in the middle of a sequence line, CRLF records, blank lines, an empty record.
+    leading_sequence: sequence text before the first header (it lands in record 0 of the reference's index)."""
+    r = _stream(seed, 3 * n_reads + 3, salt=17)
+    parts = []
+    if leading_sequence:
+        parts.append(_ACGT[bases[:200]].tobytes() + b"\n")
+    for i in range(n_reads):
+        ln = min_len + int(r[3 * i] % np.uint64(max_len - min_len + 1))
+        st = int(r[3 * i + 1] % np.uint64(max(bases.size - ln, 1)))
+        txt = _ACGT[bases[st:st + ln]].copy()
+        flags = int(r[3 * i + 2] & np.uint64(0xffff))
+        eol = b"\n"
+        if messy:
+            if flags & 1:
+                txt[ln // 3: ln // 3 + 1 + (flags >> 8) % 40] = ord("N")
+            if flags & 2:
+                txt[ln // 2:] |= 0x20
+            if flags & 4 and ln > 80:
+                txt[ln // 4] = ord(">")                       # header start in the middle of a sequence line
+            if flags & 8:
+                eol = b"\r\n"
+            if (flags & 0xf0) == 0xf0:
+                txt = txt[:0]                                 # empty record
+        parts.append(b">read_%d/1 len=%d" % (i, txt.size) + eol)
+        tb = txt.tobytes()
+        if i % 3 == 0 or width <= 0:
+            parts.append(tb + eol)
+        else:
+            for j in range(0, len(tb), width):
+                parts.append(tb[j:j + width] + eol)
+        if messy and (flags & 0x300) == 0x300:
+            parts.append(eol)
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+
+
 def cluster_genomes(n_genomes: int, genome_len: int, seed: int, cluster_size: int = 20,
                     min_rate: float = 0.001, max_rate: float = 0.1):
     """Yield (name, bases) for n_genomes genomes arranged as clusters of mutated copies of an ancestor."""

@@ -36,3 +36,14 @@ def fastq_inputs():
     g["b_cov5_nonl"] = synth.to_fastq(src, 3300, 150, seed=43, trailing_newline=False)
     g["c_short"] = synth.to_fastq(src, 2000, 36, seed=44)
     return g
+
+
+def byread_inputs():
+    """FASTA-formatted read files for `--byread` (reference reads2mco, iseq2comem.c:78-186)."""
+    src = synth.random_bases(400_000, 51)
+    g = {}
+    g["a_clean"] = synth.to_read_fasta(src, 900, seed=52)
+    g["b_messy"] = synth.to_read_fasta(src, 700, seed=53, messy=True)
+    g["c_leading_short"] = synth.to_read_fasta(src, 400, seed=54, min_len=5, max_len=60, width=0, leading_sequence=True)
+    g["d_contigs"] = synth.messy_fasta(200_000, 6)
+    return g

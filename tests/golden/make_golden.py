@@ -139,3 +139,31 @@ def tutorial_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tutorial":
     tutorial_golden()
+
+
+def byread_golden():
+    """`kssd dist --byread` (reads2mco): one run per input file (each run rewrites combco.* of the output directory)."""
+    O.build()
+    t6 = synth.make_shuf_table(6, cases.SHUF_SEED_S6)
+    t5 = synth.make_shuf_table(5, cases.SHUF_SEED_S5)
+    for tag, (k, s, L, tab) in {"byread_l2k8": (8, 5, 2, t5), "byread_l3k11": (11, 6, 3, t6)}.items():
+        pack = {}
+        for n, b in cases.byread_inputs().items():
+            rr = O.RefRun(k, s, L, tab, shuf_id=cases.SHUF_ID)
+            d = rr.dir / "in"
+            d.mkdir()
+            (d / f"{n}.fasta").write_bytes(b.tobytes())
+            out = rr.sketch(d, "sk", extra=["--byread"], p=1)
+            comp = 0
+            while (out / f"combco.{comp}").exists():
+                pack[f"{n}.{comp}"] = np.fromfile(out / f"combco.{comp}", dtype="<u4")
+                pack[f"{n}.{comp}.index"] = np.fromfile(out / f"combco.index.{comp}", dtype="<u8")
+                comp += 1
+            pack[f"{n}.comp_num"] = np.int32(comp)
+            print(tag, n, "components", comp, "reads", len(pack[f"{n}.0.index"]) - 1, "codes", sum(len(pack[f"{n}.{c}"]) for c in range(comp)))
+            rr.cleanup()
+        np.savez_compressed(OUT / f"{tag}.npz", **pack)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "byread":
+    byread_golden()

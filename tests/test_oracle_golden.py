@@ -47,6 +47,20 @@ def test_fastq_byte_identical_to_reference(oracle_mod, tables, tag, k, s, L, Q, 
             assert np.array_equal(ids[comp == c], g[f"{name}.{c}"]), (tag, name, c)
 
 
+@pytest.mark.parametrize("tag,k,s,L", [("byread_l2k8", 8, 5, 2), ("byread_l3k11", 11, 6, 3)])
+def test_byread_byte_identical_to_reference(oracle_mod, tables, tag, k, s, L):
+    """--byread (reads2mco): combco.<c> in stream order with duplicates, combco.index.<c> inclusive over the records."""
+    g = _load(tag)
+    ctx = oracle_mod.Ctx(k, s, L, tables[s])
+    for name, data in cases.byread_inputs().items():
+        n_reads, out = ctx.byread(data)
+        assert ctx.component_num == int(g[f"{name}.comp_num"])
+        for c in range(ctx.component_num):
+            assert np.array_equal(out[c][0], g[f"{name}.{c}"]), (tag, name, c)
+            assert np.array_equal(out[c][1], g[f"{name}.{c}.index"]), (tag, name, c)
+            assert len(out[c][1]) == n_reads + 1
+
+
 def test_fastq_abundance_identical_to_reference(oracle_mod, tables):
     g = _load("fastq_abund_l2k8")
     fq = cases.fastq_inputs()
