@@ -83,7 +83,7 @@ int kssd_ctx_sync(const kssd_ctx_t *ctx);
  * command_dist.c:331-354) with each genome's ids in ASCENDING order (the reference emits hash-slot
  * order; the set is identical, and `ord` lets a host replay slot order byte-for-byte).
  * ------------------------------------------------------------------------------------------ */
-enum { KSSD_MODE_FASTA = 0, KSSD_MODE_FASTA_UNIQ = 1, KSSD_MODE_FASTQ = 2, KSSD_MODE_FASTQ_ABUND = 3 };
+enum { KSSD_MODE_FASTA = 0, KSSD_MODE_FASTA_UNIQ = 1, KSSD_MODE_FASTQ = 2, KSSD_MODE_FASTQ_ABUND = 3, KSSD_MODE_BYREAD = 4 };
 
 typedef struct kssd_sketch_opts {
     int32_t mode;        /* KSSD_MODE_*                                                          */
@@ -113,6 +113,14 @@ int kssd_sketch_status(const kssd_sketch_t *s, int32_t *status_out /* n_genomes 
  * optional ord[count] (want_ord). NULL pointers are skipped. */
 int kssd_sketch_fetch(const kssd_sketch_t *s, int comp, uint32_t *ids, uint64_t *index,
                       uint16_t *abund, uint64_t *ord);
+/* KSSD_MODE_BYREAD -- replaces reads2mco (iseq2comem.c:78-186, `kssd dist --byread`): every input "genome" is a file
+ * of FASTA-formatted reads; NOTHING is deduplicated and code 0 is kept.  kssd_sketch_fetch() then returns, per
+ * component, every sampled k-mer id in stream order (files concatenated, index[n_files+1] delimiting them) and in `ord`
+ * the record number of each id (0 = before the first '>').  kssd_sketch_read_counts(): '>' records per file (the
+ * reference's readn).  kssd_sketch_fetch_read_index(): the reference's combco.index.<comp> of ONE file -- n_reads+1
+ * inclusive cumulative counts, entry r = ids of records 0..r (:175-180). */
+int kssd_sketch_read_counts(const kssd_sketch_t *s, uint64_t *n_reads_out /* n_genomes */);
+int kssd_sketch_fetch_read_index(const kssd_sketch_t *s, int comp, int file, uint64_t *index_out /* n_reads+1 */);
 /* device pointers of component c (valid until free): ids (u32), per-genome index (u64[n+1]) */
 int kssd_sketch_dev_ptrs(const kssd_sketch_t *s, int comp, const uint32_t **ids_dev,
                          const uint64_t **index_dev);

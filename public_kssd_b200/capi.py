@@ -21,7 +21,7 @@ SYMBOLS = [
     "kssd_last_error", "kssd_version", "kssd_kernel_launch_count",
     "kssd_ctx_create", "kssd_ctx_destroy", "kssd_ctx_info", "kssd_ctx_stream", "kssd_ctx_sync", "kssd_ctx_last_ms",
     "kssd_sketch_batch_host", "kssd_sketch_batch_dev", "kssd_sketch_count", "kssd_sketch_status", "kssd_sketch_fetch",
-    "kssd_sketch_dev_ptrs", "kssd_sketch_stats", "kssd_sketch_free",
+    "kssd_sketch_dev_ptrs", "kssd_sketch_stats", "kssd_sketch_free", "kssd_sketch_read_counts", "kssd_sketch_fetch_read_index",
     "kssd_index_build_host", "kssd_index_build_dev", "kssd_index_sizes", "kssd_index_fetch", "kssd_index_fetch_dense",
     "kssd_index_from_dense_host", "kssd_index_free",
     "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
@@ -30,7 +30,7 @@ SYMBOLS = [
     "kssd_format_distance_rows", "kssd_host_free",
 ]
 
-MODE_FASTA, MODE_FASTA_UNIQ, MODE_FASTQ, MODE_FASTQ_ABUND = 0, 1, 2, 3
+MODE_FASTA, MODE_FASTA_UNIQ, MODE_FASTQ, MODE_FASTQ_ABUND, MODE_BYREAD = 0, 1, 2, 3, 4
 METRIC_JACCARD, METRIC_CONTAINMENT = 0, 1
 
 E_CROWD, E_HEADER_EOF, E_LONGLINE = -4, -5, -9
@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
     L.kssd_sketch_count.restype = C.c_int64
     L.kssd_sketch_status.argtypes = [vp, i32p]
     L.kssd_sketch_fetch.argtypes = [vp, C.c_int, u32p, u64p, u16p, u64p]
+    L.kssd_sketch_read_counts.argtypes = [vp, u64p]
+    L.kssd_sketch_fetch_read_index.argtypes = [vp, C.c_int, C.c_int, u64p]
     L.kssd_sketch_dev_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.kssd_sketch_stats.argtypes = [vp, u64p, C.POINTER(C.c_float)]
     L.kssd_sketch_free.argtypes = [vp]

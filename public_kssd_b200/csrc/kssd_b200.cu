@@ -274,6 +274,7 @@ struct kssd_sketch {
     std::vector<uint64_t> comp_start;            // n_comp+1 offsets into d_ids
     std::vector<uint64_t> index;                 // n_comp * (n_genomes+1)
     std::vector<int32_t> status;
+    std::vector<uint64_t> n_reads;               // KSSD_MODE_BYREAD: '>' records per file
 };
 
 // run heads of the sorted occurrence keys: multiplicity, first-occurrence offset, keep rule per mode
@@ -331,7 +332,7 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
         if (nblk > 0x7fffffffull) return fail(KSSD_E_INVAL, "kssd_sketch_batch: FASTQ text of genome %d too large", g);
         CU(c->flags.ensure(nblk * 4));
         CU(c->pos.ensure(nblk * 4));
-        nl_count_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->flags.as<uint32_t>());
+        nl_count_kernel<false><<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->flags.as<uint32_t>());
         size_t tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream);
         CU(c->cubtmp.ensure(tmp));
@@ -345,7 +346,7 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
         CU(cudaStreamSynchronize(c->stream));
         const uint64_t n_nl = (uint64_t)lastoff + lastcnt;
         CU(c->minord.ensure(std::max<uint64_t>(n_nl, 1) * 8));
-        nl_fill_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->pos.as<uint32_t>(), c->minord.as<uint64_t>());
+        nl_fill_kernel<false><<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, c->pos.as<uint32_t>(), c->minord.as<uint64_t>());
         LAUNCHED(1);
         FastqArgs F{};
         F.seq = d_seq; F.seq_bytes = A.seq_bytes; F.gs = gs; F.ge = ge;
@@ -368,12 +369,116 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
     return KSSD_OK;
 }
 
+// --byread (reference reads2mco, iseq2comem.c:78-186) after the scan: header starts of every file, occurrences in
+// stream order per (component, file), the record number of each, and the per-(component, file) totals.
+static int byread_finish(kssd_ctx *c, kssd_sketch *S, const uint8_t *d_seq, const uint64_t *goff, const uint64_t *glen, int n_genomes,
+                         uint32_t n_occ, const uint64_t *d_goff, const int32_t *d_gstatus)
+{
+    const SketchParams &P = c->P;
+    const int n_comp = S->n_comp;
+    if (n_genomes >= (1 << 20) || n_comp > 256) return fail(KSSD_E_INVAL, "kssd_sketch_batch: --byread takes < 2^20 files and <= 256 components");
+    std::vector<uint64_t> boff(n_genomes + 1, 0);
+    for (int g = 0; g < n_genomes; g++) {
+        if (glen[g] >> 36) return fail(KSSD_E_INVAL, "kssd_sketch_batch: --byread file %d larger than 64 GiB", g);
+        const uint64_t a0 = goff[g] & ~15ull;
+        boff[g + 1] = boff[g] + (glen[g] ? (goff[g] + glen[g] - a0 + kNlBytesPerBlock - 1) / kNlBytesPerBlock : 0);
+    }
+    const uint64_t nblk = boff[n_genomes];
+    if (nblk > 0x7fffffffull) return fail(KSSD_E_INVAL, "kssd_sketch_batch: --byread batch too large");
+    S->n_reads.assign(n_genomes, 0);
+    std::vector<uint64_t> hdr_off(n_genomes + 1, 0);
+    if (nblk) {
+        CU(c->flags.ensure(nblk * 4));
+        CU(c->pos.ensure(nblk * 4));
+        for (int g = 0; g < n_genomes; g++)
+            if (boff[g + 1] > boff[g]) {
+                nl_count_kernel<true><<<(uint32_t)(boff[g + 1] - boff[g]), kNlBlock, 0, c->stream>>>(d_seq, goff[g], goff[g] + glen[g], goff[g] & ~15ull,
+                                                                                                  c->flags.as<uint32_t>() + boff[g]);
+                LAUNCHED(1);
+            }
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream));
+        LAUNCHED(2);
+        std::vector<uint32_t> pos(nblk);
+        uint32_t lastcnt = 0;
+        CU(cudaMemcpyAsync(pos.data(), c->pos.p, nblk * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&lastcnt, c->flags.as<uint32_t>() + (nblk - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const uint64_t total_hdr = (uint64_t)pos[nblk - 1] + lastcnt;
+        for (int g = 0; g <= n_genomes; g++) hdr_off[g] = boff[g] < nblk ? pos[boff[g]] : total_hdr;
+        for (int g = 0; g < n_genomes; g++) S->n_reads[g] = hdr_off[g + 1] - hdr_off[g];
+        CU(c->minord.ensure(std::max<uint64_t>(total_hdr, 1) * 8));
+        for (int g = 0; g < n_genomes; g++)
+            if (boff[g + 1] > boff[g]) {
+                nl_fill_kernel<true><<<(uint32_t)(boff[g + 1] - boff[g]), kNlBlock, 0, c->stream>>>(d_seq, goff[g], goff[g] + glen[g], goff[g] & ~15ull,
+                                                                                                 c->pos.as<uint32_t>() + boff[g], c->minord.as<uint64_t>());
+                LAUNCHED(1);
+            }
+    }
+    S->status.assign(n_genomes, 0);
+    S->comp_start.assign(n_comp + 1, 0);
+    S->index.assign((size_t)n_comp * (n_genomes + 1), 0);
+    std::vector<uint32_t> per_cg((size_t)n_comp * n_genomes, 0);
+    const size_t nmax = std::max<size_t>(n_occ, 1);
+    const size_t o_ids = 0, o_ord = (nmax * 4 + 15) & ~(size_t)15, o_idx = o_ord + nmax * 8;
+    S->blob_bytes = o_idx + S->index.size() * 8;
+    CU(cudaMallocAsync(&S->d_blob, S->blob_bytes, c->stream));
+    S->d_ids = reinterpret_cast<uint32_t *>(S->d_blob + o_ids);
+    S->d_ord = reinterpret_cast<uint64_t *>(S->d_blob + o_ord);     // record number of every occurrence in this mode
+    S->d_abund = nullptr;
+    S->d_index = reinterpret_cast<uint64_t *>(S->d_blob + o_idx);
+    if (n_occ) {
+        CU(c->keys2.ensure((size_t)n_occ * 8));
+        CU(c->ords2.ensure((size_t)n_occ * 8));
+        const uint32_t nb = (n_occ + 255) / 256;
+        byread_rekey_kernel<<<nb, 256, 0, c->stream>>>(c->keys.as<uint64_t>(), c->ords.as<uint64_t>(), n_occ, c->keys2.as<uint64_t>(),
+                                                       c->ords2.as<uint32_t>());
+        int gbits = 1;
+        while ((1ll << gbits) < n_genomes) gbits++;
+        const int end_bit = P.comp_code_bits ? 56 + P.comp_code_bits : 36 + gbits;
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->keys2.as<uint64_t>(), c->keys.as<uint64_t>(), c->ords2.as<uint32_t>(), S->d_ids, n_occ, 0,
+                                        end_bit, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, c->keys2.as<uint64_t>(), c->keys.as<uint64_t>(), c->ords2.as<uint32_t>(), S->d_ids,
+                                           n_occ, 0, end_bit, c->stream));
+        CU(c->misc.ensure(per_cg.size() * 4));
+        CU(cudaMemsetAsync(c->misc.p, 0, per_cg.size() * 4, c->stream));
+        CU(c->counts.ensure(hdr_off.size() * 8));
+        CU(cudaMemcpyAsync(c->counts.p, hdr_off.data(), hdr_off.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        byread_assign_kernel<<<nb, 256, 0, c->stream>>>(c->keys.as<uint64_t>(), n_occ, d_goff, c->minord.as<uint64_t>(), c->counts.as<uint64_t>(),
+                                                        n_genomes, S->d_ord, c->misc.as<uint32_t>());
+        LAUNCHED(10);
+        CU(cudaMemcpyAsync(per_cg.data(), c->misc.p, per_cg.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(S->status.data(), d_gstatus, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    uint64_t run = 0;
+    for (int cc = 0; cc < n_comp; cc++) {
+        S->comp_start[cc] = run;
+        uint64_t *ix = &S->index[(size_t)cc * (n_genomes + 1)];
+        for (int g = 0; g < n_genomes; g++) ix[g + 1] = ix[g] + per_cg[(size_t)cc * n_genomes + g];
+        run += ix[n_genomes];
+    }
+    S->comp_start[n_comp] = run;
+    S->total = run;
+    for (int g = 0; g < n_genomes; g++) S->status[g] = (S->status[g] & 1) ? KSSD_E_HEADER_EOF : 0;
+    CU(cudaMemcpyAsync(S->d_index, S->index.data(), S->index.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(cudaEventSynchronize(c->ev[2]));
+    CU(cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[2]));
+    return KSSD_OK;
+}
+
 static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const uint64_t *goff, const uint64_t *glen, int n_genomes,
                       const kssd_sketch_opts_t *opts, kssd_sketch_t **out)
 {
     const SketchParams &P = c->P;
     const int mode = opts ? opts->mode : KSSD_MODE_FASTA;
-    if (mode < KSSD_MODE_FASTA || mode > KSSD_MODE_FASTQ_ABUND) return fail(KSSD_E_INVAL, "kssd_sketch_batch: unknown mode %d", mode);
+    if (mode < KSSD_MODE_FASTA || mode > KSSD_MODE_BYREAD) return fail(KSSD_E_INVAL, "kssd_sketch_batch: unknown mode %d", mode);
     const bool is_fastq = mode == KSSD_MODE_FASTQ || mode == KSSD_MODE_FASTQ_ABUND;
     if (mode == KSSD_MODE_FASTQ && opts && (opts->M < 1 || opts->M >= 15))
         return fail(KSSD_E_INVAL, "fastq2co(): Occurence num should smaller than 15");   // iseq2comem.c:279
@@ -469,7 +574,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         A.out_count = reinterpret_cast<uint32_t *>(mb + m_cnt);
         A.out_keys = c->keys.as<uint64_t>(); A.out_ords = c->ords.as<uint64_t>();
         A.out_cap = (uint32_t)cap;
-        A.drop_zero = is_fastq ? 0 : 1;
+        A.drop_zero = (is_fastq || mode == KSSD_MODE_BYREAD) ? 0 : 1;      // only fasta2co's hash table loses code 0
         CU(cudaMemsetAsync(mb + m_tick, 0, 8, c->stream));
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
@@ -492,6 +597,13 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     CU(cudaEventElapsedTime(&S->scan_ms, c->ev[0], c->ev[1]));
     c->last_ms[0] = S->scan_ms;
     S->n_occ = n_occ;
+    if (mode == KSSD_MODE_BYREAD) {
+        const int rc = byread_finish(c, S, d_seq, goff, glen, n_genomes, n_occ, reinterpret_cast<const uint64_t *>(pb),
+                                     reinterpret_cast<const int32_t *>(mb + m_stat));
+        if (rc) { if (S->d_blob) cudaFreeAsync(S->d_blob, c->stream); delete S; return rc; }
+        *out = S;
+        return KSSD_OK;
+    }
 
     const int n_comp = S->n_comp;
     S->status.assign(n_genomes, 0);
@@ -621,6 +733,32 @@ extern "C" int kssd_sketch_fetch(const kssd_sketch_t *s, int comp, uint32_t *ids
     if (ord && n) CU(cudaMemcpyAsync(ord, s->d_ord + b, n * 8, cudaMemcpyDeviceToHost, c->stream));
     if (index) memcpy(index, &s->index[(size_t)comp * (s->n_genomes + 1)], 8ull * (s->n_genomes + 1));
     CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" int kssd_sketch_read_counts(const kssd_sketch_t *s, uint64_t *n_reads_out)
+{
+    if (!s || !n_reads_out) return fail(KSSD_E_INVAL, "kssd_sketch_read_counts: null");
+    if (s->mode != KSSD_MODE_BYREAD) return fail(KSSD_E_INVAL, "kssd_sketch_read_counts: not a --byread sketch");
+    memcpy(n_reads_out, s->n_reads.data(), s->n_reads.size() * 8);
+    return KSSD_OK;
+}
+
+extern "C" int kssd_sketch_fetch_read_index(const kssd_sketch_t *s, int comp, int file, uint64_t *index_out)
+{
+    if (!s || !index_out || comp < 0 || comp >= s->n_comp || file < 0 || file >= s->n_genomes)
+        return fail(KSSD_E_INVAL, "kssd_sketch_fetch_read_index: bad argument");
+    if (s->mode != KSSD_MODE_BYREAD) return fail(KSSD_E_INVAL, "kssd_sketch_fetch_read_index: not a --byread sketch");
+    kssd_ctx *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint64_t *ix = &s->index[(size_t)comp * (s->n_genomes + 1)];
+    const uint64_t seg_lo = s->comp_start[comp] + ix[file], seg_n = ix[file + 1] - ix[file], nr = s->n_reads[file];
+    CU(c->minord.ensure((nr + 1) * 8));
+    byread_index_kernel<<<(uint32_t)((nr + 1 + 255) / 256), 256, 0, c->stream>>>(s->d_ord + seg_lo, seg_n, nr, c->minord.as<uint64_t>());
+    LAUNCHED(1);
+    CU(cudaMemcpyAsync(index_out, c->minord.p, (nr + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
     return KSSD_OK;
 }
 

@@ -42,11 +42,49 @@ __device__ __forceinline__ uint32_t nl_mask16(const uint8_t *seq, uint64_t a, ui
     return m;
 }
 
+// Header starts of FASTA-formatted reads (reference reads2mco, iseq2comem.c:127-157): a '>' opens a record unless it
+// lies inside a header line, i.e. unless another '>' precedes it on the same line ('\n' to '\n').  bit i = byte a+i
+// opens a record.  The backward walk stops at the first '\n' or '>' -- one line at most.
+__device__ __forceinline__ uint32_t hdr_mask16(const uint8_t *seq, uint64_t a, uint64_t gs, uint64_t ge)
+{
+    if (a + 16 <= gs || a >= ge) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(seq + a));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t gt = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        gt |= (uint32_t)(b == '>') << i;
+    }
+    if (a < gs) gt &= ~((1u << (gs - a)) - 1u);
+    if (a + 16 > ge) gt &= (1u << (ge - a)) - 1u;
+    uint32_t m = 0;
+    while (gt) {
+        const int i = __ffs(gt) - 1;
+        gt &= gt - 1;
+        bool opens = true;
+        for (uint64_t p = a + i; p > gs;) {
+            const uint8_t b = seq[--p];
+            if (b == '\n') break;
+            if (b == '>') { opens = false; break; }
+        }
+        m |= (uint32_t)opens << i;
+    }
+    return m;
+}
+
+template <bool HDR>
+__device__ __forceinline__ uint32_t line_mask16(const uint8_t *seq, uint64_t a, uint64_t gs, uint64_t ge)
+{
+    return HDR ? hdr_mask16(seq, a, gs, ge) : nl_mask16(seq, a, gs, ge);
+}
+
+template <bool HDR = false>
 __global__ void __launch_bounds__(kNlBlock) nl_count_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0,
                                                              uint32_t *__restrict__ block_counts)
 {
     const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + 16ull * threadIdx.x;
-    uint32_t c = __popc(nl_mask16(seq, a, gs, ge));
+    uint32_t c = __popc(line_mask16<HDR>(seq, a, gs, ge));
     c = __reduce_add_sync(kFull, c);
     __shared__ uint32_t red[kNlBlock / 32];
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
@@ -58,11 +96,12 @@ __global__ void __launch_bounds__(kNlBlock) nl_count_kernel(const uint8_t *__res
     }
 }
 
+template <bool HDR = false>
 __global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0,
                                                             const uint32_t *__restrict__ block_offsets, uint64_t *__restrict__ nlpos)
 {
     const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + 16ull * threadIdx.x;
-    uint32_t m = nl_mask16(seq, a, gs, ge);
+    uint32_t m = line_mask16<HDR>(seq, a, gs, ge);
     const uint32_t c = __popc(m);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = c;
@@ -290,6 +329,53 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
             }
         }
     }
+}
+
+// ---- --byread (reference reads2mco, iseq2comem.c:78-186): every occurrence kept, stream order, per-record index ----
+// occurrence keys from the scan: (comp << 56) | (gid << 28) | id with the byte offset alongside; re-keyed as
+// (comp << 56) | (gid << 36) | offset so that one radix sort yields stream order per (component, file).
+__global__ void byread_rekey_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ ords, uint32_t n,
+                                    uint64_t *__restrict__ keys2, uint32_t *__restrict__ ids)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys[i];
+    const uint64_t gid = (k >> 28) & 0xfffffffull;
+    keys2[i] = (k & 0xff00000000000000ull) | (gid << 36) | (ords[i] & 0xfffffffffull);
+    ids[i] = (uint32_t)(k & 0xfffffffull);
+}
+
+// sorted occurrence i -> its record number (header starts at or before it inside its file) and the (comp, file) tally
+__global__ void byread_assign_kernel(const uint64_t *__restrict__ keys2, uint32_t n, const uint64_t *__restrict__ goff,
+                                     const uint64_t *__restrict__ hpos, const uint64_t *__restrict__ hdr_off, int n_genomes,
+                                     uint64_t *__restrict__ read_of, uint32_t *__restrict__ per_cg)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys2[i];
+    const uint32_t comp = (uint32_t)(k >> 56), gid = (uint32_t)((k >> 36) & 0xfffffu);
+    const uint64_t abs = goff[gid] + (k & 0xfffffffffull);
+    uint64_t lo = hdr_off[gid], hi = hdr_off[gid + 1];
+    const uint64_t base = lo;
+    while (lo < hi) {                                    // first header start > abs
+        const uint64_t mid = (lo + hi) >> 1;
+        if (hpos[mid] <= abs) lo = mid + 1; else hi = mid;
+    }
+    read_of[i] = lo - base;
+    atomicAdd(&per_cg[(size_t)comp * n_genomes + gid], 1u);
+}
+
+// combco.index.<c> of one file as reads2mco writes it (:175-180): out[r] = occurrences of records 0..r, r = 0..n_reads
+__global__ void byread_index_kernel(const uint64_t *__restrict__ read_of, uint64_t seg_n, uint64_t n_reads, uint64_t *__restrict__ out)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    uint64_t lo = 0, hi = seg_n;
+    while (lo < hi) {                                    // first occurrence with record > r
+        const uint64_t mid = (lo + hi) >> 1;
+        if (read_of[mid] <= r) lo = mid + 1; else hi = mid;
+    }
+    out[r] = lo;
 }
 
 }  // namespace kssd

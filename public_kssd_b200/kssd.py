@@ -189,6 +189,35 @@ class Context:
             self._raise_status(sk)
         return sk
 
+    def reads2mco(self, files: Sequence[bytes | np.ndarray], strict: bool = True):
+        """`kssd dist --byread` (reference reads2mco, iseq2comem.c:78-186) for every file of FASTA-formatted reads in the
+        batch.  Returns one dict per file: {"n_reads": readn, "ids": [per component: ids in stream order, duplicates
+        kept], "index": [per component: the reference's combco.index.<c>, n_reads + 1 inclusive cumulative counts],
+        "read_of": [per component: record number of every id]}."""
+        buf, goff, glen = pack_genomes(files)
+        h = self.sketch_raw(buf, buf.size, goff, glen, capi.MODE_BYREAD)
+        try:
+            n = len(files)
+            nr = np.zeros(n, dtype=np.uint64)
+            check(lib().kssd_sketch_read_counts(h, ptr(nr, C.c_uint64)))
+            sk = self.fetch_sketch(h, n, free=False)
+            if strict:
+                self._raise_status(sk)
+            out = []
+            for g in range(n):
+                rec = {"n_reads": int(nr[g]), "ids": [], "index": [], "read_of": []}
+                for c in range(self.component_num):
+                    a, b = int(sk.index[c][g]), int(sk.index[c][g + 1])
+                    ix = np.empty(int(nr[g]) + 1, dtype=np.uint64)
+                    check(lib().kssd_sketch_fetch_read_index(h, c, g, ptr(ix, C.c_uint64)))
+                    rec["ids"].append(sk.ids[c][a:b])
+                    rec["read_of"].append(sk.ord[c][a:b])
+                    rec["index"].append(ix)
+                out.append(rec)
+            return out
+        finally:
+            lib().kssd_sketch_free(h)
+
     # ---------------- Stage II ----------------
     def combco2mco(self, combco: np.ndarray, cbdcoindex: np.ndarray) -> "Index":
         combco = np.ascontiguousarray(combco, dtype=np.uint32)
