@@ -23,20 +23,29 @@
 namespace kssd {
 
 constexpr int kNlBlock = 256;            // threads per block of the line-index passes
-constexpr int kNlBytesPerBlock = kNlBlock * 16;
+constexpr int kNlBytesPerThread = 64;     // four 16-byte chunks in a row: the scans and the block bookkeeping are paid per 64 B
+constexpr int kNlBytesPerBlock = kNlBlock * kNlBytesPerThread;
+
+// 4 bits: bit b = byte b of w equals the byte replicated in `pat` (exact zero-byte test of w ^ pat, then a
+// multiply that gathers the four 0x80 flags into the top nibble)
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t pat)
+{
+    const uint32_t x = w ^ pat;
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    const uint32_t z = ~(t | x) & 0x80808080u;
+    return ((z >> 7) * 0x10204080u) >> 28;
+}
+
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t pat)
+{
+    return eq_mask4(v.x, pat) | (eq_mask4(v.y, pat) << 4) | (eq_mask4(v.z, pat) << 8) | (eq_mask4(v.w, pat) << 12);
+}
 
 __device__ __forceinline__ uint32_t nl_mask16(const uint8_t *seq, uint64_t a, uint64_t gs, uint64_t ge)
 {
     // bit i = byte a+i is '\n' and lies inside [gs, ge); a is 16-byte aligned
     if (a + 16 <= gs || a >= ge) return 0;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(seq + a));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-        m |= (uint32_t)(b == '\n') << i;
-    }
+    uint32_t m = eq_mask16(ldg_stream(reinterpret_cast<const uint4 *>(seq + a)), 0x0a0a0a0au);
     if (a < gs) m &= ~((1u << (gs - a)) - 1u);
     if (a + 16 > ge) m &= (1u << (ge - a)) - 1u;
     return m;
@@ -48,14 +57,7 @@ __device__ __forceinline__ uint32_t nl_mask16(const uint8_t *seq, uint64_t a, ui
 __device__ __forceinline__ uint32_t hdr_mask16(const uint8_t *seq, uint64_t a, uint64_t gs, uint64_t ge)
 {
     if (a + 16 <= gs || a >= ge) return 0;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(seq + a));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t gt = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-        gt |= (uint32_t)(b == '>') << i;
-    }
+    uint32_t gt = eq_mask16(ldg_stream(reinterpret_cast<const uint4 *>(seq + a)), 0x3e3e3e3eu);
     if (a < gs) gt &= ~((1u << (gs - a)) - 1u);
     if (a + 16 > ge) gt &= (1u << (ge - a)) - 1u;
     uint32_t m = 0;
@@ -79,12 +81,21 @@ __device__ __forceinline__ uint32_t line_mask16(const uint8_t *seq, uint64_t a, 
     return HDR ? hdr_mask16(seq, a, gs, ge) : nl_mask16(seq, a, gs, ge);
 }
 
+// 64-bit mask of the thread's 64 bytes (bit i = byte a+i is a line end / a header start inside [gs, ge))
+template <bool HDR>
+__device__ __forceinline__ uint64_t line_mask64(const uint8_t *seq, uint64_t a, uint64_t gs, uint64_t ge)
+{
+    const uint32_t m0 = line_mask16<HDR>(seq, a, gs, ge), m1 = line_mask16<HDR>(seq, a + 16, gs, ge);
+    const uint32_t m2 = line_mask16<HDR>(seq, a + 32, gs, ge), m3 = line_mask16<HDR>(seq, a + 48, gs, ge);
+    return (uint64_t)(m0 | (m1 << 16)) | ((uint64_t)(m2 | (m3 << 16)) << 32);
+}
+
 template <bool HDR = false>
 __global__ void __launch_bounds__(kNlBlock) nl_count_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0,
                                                              uint32_t *__restrict__ block_counts)
 {
-    const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + 16ull * threadIdx.x;
-    uint32_t c = __popc(line_mask16<HDR>(seq, a, gs, ge));
+    const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + (uint64_t)kNlBytesPerThread * threadIdx.x;
+    uint32_t c = __popcll(line_mask64<HDR>(seq, a, gs, ge));
     c = __reduce_add_sync(kFull, c);
     __shared__ uint32_t red[kNlBlock / 32];
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
@@ -100,9 +111,9 @@ template <bool HDR = false>
 __global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0,
                                                             const uint32_t *__restrict__ block_offsets, uint64_t *__restrict__ nlpos)
 {
-    const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + 16ull * threadIdx.x;
-    uint32_t m = line_mask16<HDR>(seq, a, gs, ge);
-    const uint32_t c = __popc(m);
+    const uint64_t a = a0 + (uint64_t)blockIdx.x * kNlBytesPerBlock + (uint64_t)kNlBytesPerThread * threadIdx.x;
+    uint64_t m = line_mask64<HDR>(seq, a, gs, ge);
+    const uint32_t c = __popcll(m);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = c;
 #pragma unroll
@@ -114,10 +125,11 @@ __global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__rest
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
     uint32_t base = block_offsets[blockIdx.x];
-    for (uint32_t w = 0; w < wid; w++) base += wsum[w];
+#pragma unroll
+    for (uint32_t w = 0; w < kNlBlock / 32; w++) base += w < wid ? wsum[w] : 0u;
     uint32_t o = base + incl - c;
     while (m) {
-        const int i = __ffs(m) - 1;
+        const int i = __ffsll((long long)m) - 1;
         m &= m - 1;
         nlpos[o++] = a + i;
     }
@@ -186,29 +198,6 @@ __device__ __forceinline__ uint32_t nonzero_bytes16(uint32_t b0, uint32_t b1, ui
     return nib(b0) | (nib(b1) << 4) | (nib(b2) << 8) | (nib(b3) << 12);
 }
 
-// 16 bytes starting at the (unaligned) address p, assembled from two aligned loads
-__device__ __forceinline__ uint4 load_unaligned16(const uint8_t *seq, uint64_t p, uint64_t readable)
-{
-    const uint64_t a = p & ~15ull;
-    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(seq + a));
-    const uint32_t sh = (uint32_t)(p - a);
-    if (sh == 0) return x;
-    uint4 y = make_uint4(0, 0, 0, 0);
-    if (a + 16 < readable) y = __ldg(reinterpret_cast<const uint4 *>(seq + a + 16));
-    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    const uint32_t ws = sh >> 2, bs = 8 * (sh & 3);
-    uint32_t r[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (ws == (uint32_t)j) { lo = w[i + j]; hi = w[i + j + 1]; }
-        r[i] = __funnelshift_r(lo, hi, bs);
-    }
-    return make_uint4(r[0], r[1], r[2], r[3]);
-}
-
 __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const SketchParams P, const FastqArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -245,15 +234,25 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
         }
         const bool use_q = !A.abund && A.Q > -128;
         if (TL >= 16) {
-            // ---- vectorised walk: 16 aligned bytes at a time, same classify / pack / probe code as the FASTA kernel ----
-            // With 2k >= 16 no k-mer can both start after an invalid byte of a chunk and end inside that chunk, so the
-            // chunk's valid k-mer ends are the positions before its first invalid byte (given enough run before it).
+            // ---- vectorised walk: 16 aligned bytes at a time (one LDG.128 per chunk, the next one requested before this
+            // one is processed), same classify / pack / probe code as the FASTA kernel.  With 2k >= 16 no k-mer can both
+            // start after an invalid byte of a chunk and end inside that chunk, so the chunk's valid k-mer ends are the
+            // positions before its first invalid byte (given enough run before it).
             uint32_t hist0 = 0, hist1 = 0, run = 0;        // last 32 bases (newest low), valid bases since the last break
             const uint32_t qrep = (uint32_t)(A.Q & 0xff) * 0x01010101u;
-            for (uint64_t a = s0 & ~15ull; a < s1; a += 16) {
-                const uint4 c = __ldg(reinterpret_cast<const uint4 *>(A.seq + a));
-                const int lo = a < s0 ? (int)(s0 - a) : 0;
-                const int hi = s1 - a < 16 ? (int)(s1 - a) : 16;
+            const uint64_t last16 = (A.seq_bytes - 1) & ~15ull;                       // last readable aligned chunk
+            auto ld16 = [&](uint64_t addr) -> uint4 { return __ldg(reinterpret_cast<const uint4 *>(A.seq + (addr < last16 ? addr : last16))); };
+            const uint64_t a0 = s0 & ~15ull;
+            const bool have_q = use_q && qlen > 0;
+            // quality bytes of the chunk at a: [q0 + (a - s0), +16) -- unaligned; the two aligned chunks covering it
+            const uint64_t qa0 = have_q ? ((q0 - (s0 - a0)) & ~15ull) : 0;
+            const uint32_t qsh = have_q ? (uint32_t)((q0 - (s0 - a0)) & 15) : 0;     // same for every chunk of the read
+            uint4 cnext = ld16(a0), qx = make_uint4(0, 0, 0, 0), qnext = make_uint4(0, 0, 0, 0);
+            if (have_q) { qx = ld16(qa0); qnext = ld16(qa0 + 16); }
+            for (uint64_t a = a0; a < s1; a += 16) {
+                const uint4 c = cnext;
+                if (a + 16 < s1) cnext = ld16(a + 16);
+                const bool edge = a < s0 || s1 - a < 16;
                 uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, t0, t1, t2, t3, m0, m1, m2, m3;
                 classify4(c.x, d0, t0, m0);
                 classify4(c.y, d1, t1, m1);
@@ -261,19 +260,41 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
                 classify4(c.w, d3, t3, m3);
                 const uint32_t codes = prmt(prmt(m3, m2, 0x0073u), prmt(m1, m0, 0x0073u), 0x5410u);
                 // invalid: anything but ACGTacgt (line ends included: '\r' breaks a read, iseq2comem.c:311-319)
-                uint32_t inv = nonzero_bytes16(d0 | (t0 & 0x04040404u), d1 | (t1 & 0x04040404u), d2 | (t2 & 0x04040404u), d3 | (t3 & 0x04040404u));
-                inv |= ~(((1u << hi) - 1u) & ~((1u << lo) - 1u)) & 0xffffu;
-                if (use_q) {
-                    // quality byte of sequence byte a+i is q0 + (a - s0) + i; beyond the quality line it counts as 0
-                    const int64_t rel = (int64_t)a - (int64_t)s0;                    // >= -15
-                    const uint4 qv = load_unaligned16(A.seq, (uint64_t)((int64_t)q0 + rel), A.seq_bytes);
-                    const uint32_t f0 = __vcmpges4(qv.x, qrep), f1 = __vcmpges4(qv.y, qrep), f2 = __vcmpges4(qv.z, qrep), f3 = __vcmpges4(qv.w, qrep);
-                    uint32_t pass = nonzero_bytes16(f0, f1, f2, f3);
-                    const int64_t qn = (int64_t)qlen - rel;                          // bytes of this chunk inside the quality line
-                    const uint32_t inq = qn >= 16 ? 0xffffu : (qn <= 0 ? 0u : ((1u << qn) - 1u));
-                    pass = (pass & inq) | (A.Q <= 0 ? (~inq & 0xffffu) : 0u);
-                    inv |= ~pass & 0xffffu;
-                    if (A.Q > 127) inv = 0xffffu;                                    // no signed byte reaches Q
+                uint32_t inv = 0;
+                if (((d0 | d1 | d2 | d3) | ((t0 | t1 | t2 | t3) & 0x04040404u)) != 0u || edge) {
+                    const int lo = a < s0 ? (int)(s0 - a) : 0;
+                    const int hi = s1 - a < 16 ? (int)(s1 - a) : 16;
+                    inv = nonzero_bytes16(d0 | (t0 & 0x04040404u), d1 | (t1 & 0x04040404u), d2 | (t2 & 0x04040404u), d3 | (t3 & 0x04040404u));
+                    inv |= ~(((1u << hi) - 1u) & ~((1u << lo) - 1u)) & 0xffffu;
+                }
+                if (have_q) {
+                    const uint4 qy = qnext;
+                    const uint64_t qa = qa0 + (a - a0);
+                    if (a + 16 < s1) qnext = ld16(qa + 32);
+                    // Q <= 0: only bytes with the high bit set (negative as signed char) can fail -- none in ASCII text
+                    if (A.Q > 0 || ((qx.x | qx.y | qx.z | qx.w | qy.x | qy.y | qy.z | qy.w) & 0x80808080u) != 0u) {
+                        const uint32_t w[8] = {qx.x, qx.y, qx.z, qx.w, qy.x, qy.y, qy.z, qy.w};
+                        const uint32_t ws = qsh >> 2, bs = 8 * (qsh & 3);
+                        uint32_t f[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            uint32_t l = 0, h = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (ws == (uint32_t)j) { l = w[i + j]; h = w[i + j + 1 < 8 ? i + j + 1 : 7]; }
+                            f[i] = __vcmpges4(__funnelshift_r(l, h, bs), qrep);          // 0xff / 0x00 per byte
+                        }
+                        auto nib = [](uint32_t v) -> uint32_t { return ((v & 0x08040201u) * 0x01010101u) >> 24; };
+                        uint32_t pass = nib(f[0]) | (nib(f[1]) << 4) | (nib(f[2]) << 8) | (nib(f[3]) << 12);
+                        const int64_t qn = (int64_t)qlen - ((int64_t)a - (int64_t)s0);   // bytes of this chunk inside the quality line
+                        const uint32_t inq = qn >= 16 ? 0xffffu : (qn <= 0 ? 0u : ((1u << qn) - 1u));
+                        pass = (pass & inq) | (A.Q <= 0 ? (~inq & 0xffffu) : 0u);       // beyond the line a quality counts as 0
+                        inv |= ~pass & 0xffffu;
+                        if (A.Q > 127) inv = 0xffffu;                                   // no signed byte reaches Q
+                    }
+                    qx = qy;
+                } else if (use_q && A.Q > 0) {
+                    inv = 0xffffu;                                                       // no quality line: every quality counts as 0
                 }
                 const int fi = inv ? __ffs(inv) - 1 : 16;                             // k-mers may end at bytes [0, fi)
                 const int need = TL - 1 - (int)run;                                   // ... and at byte >= need
