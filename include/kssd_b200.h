@@ -215,6 +215,21 @@ typedef struct kssd_stat_row {
     double ci_metric_lo, ci_metric_hi, ci_dist_lo, ci_dist_hi;
 } kssd_stat_row_t;
 
+/* Sparse job: the same search without the Q x R matrix, for runs that can never print a zero-shared cell (skip_zero,
+ * or -D < 1 without --correction: output_ctrl gives such a cell dist = 1 > D, command_dist.c:1265-1267).  Components
+ * are REGISTERED (the device pointers must stay valid until kssd_dist_stats returns; the host variant keeps its own
+ * copy) and kssd_dist_stats counts, filters and lists in one kernel: shared counts live in a per-query shared-memory
+ * hash table, work is proportional to the postings touched instead of Q x R.  Rows are identical to the dense job's.
+ * If the options do print zero cells (-N, -D >= 1 without skip_zero, --correction, empty sketches whose cells are NaN),
+ * a query touches more than 6144
+ * references, or counts are fetched, the job falls back to the matrix transparently. */
+int kssd_dist_create_sparse(kssd_ctx_t *ctx, int n_qry, int n_ref, const uint32_t *qry_ctx_ct,
+                            const uint32_t *ref_ctx_ct, kssd_dist_t **out);
+int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev,
+                             const uint64_t *qindex_dev, uint64_t n_qcodes);
+int kssd_dist_sparse_add_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes,
+                              const uint64_t *qindex);
+
 /* Runs the fused statistics kernel over the count matrix.  Rows come out query-major, refs
  * ascending (or best-first for -N), as dist_print_nobin writes them.  Two-call pattern:
  * kssd_dist_stats() computes on the device and returns the number of rows; kssd_dist_fetch_stats

@@ -25,7 +25,7 @@ SYMBOLS = [
     "kssd_index_build_host", "kssd_index_build_dev", "kssd_index_sizes", "kssd_index_fetch", "kssd_index_fetch_dense",
     "kssd_index_from_dense_host", "kssd_index_free",
     "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
-    "kssd_dist_counts_dev", "kssd_dist_accumulate_peer", "kssd_dev_alloc", "kssd_dev_zero", "kssd_dev_free",
+    "kssd_dist_counts_dev", "kssd_dist_create_sparse", "kssd_dist_sparse_add_dev", "kssd_dist_sparse_add_host", "kssd_dist_accumulate_peer", "kssd_dev_alloc", "kssd_dev_zero", "kssd_dev_free",
     "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_fetch_stats", "kssd_dist_free",
     "kssd_format_distance_rows", "kssd_host_free",
 ]
@@ -131,6 +131,9 @@ def lib() -> C.CDLL:
     L.kssd_ipc_export.argtypes = [vp, vp, u8p]
     L.kssd_ipc_open.argtypes = [vp, u8p, C.POINTER(vp)]
     L.kssd_ipc_close.argtypes = [vp, vp]
+    L.kssd_dist_create_sparse.argtypes = [vp, C.c_int, C.c_int, u32p, u32p, C.POINTER(vp)]
+    L.kssd_dist_sparse_add_dev.argtypes = [vp, vp, vp, vp, C.c_uint64]
+    L.kssd_dist_sparse_add_host.argtypes = [vp, vp, u32p, u64p]
     L.kssd_dist_fetch_counts.argtypes = [vp, u32p]
     L.kssd_dist_counts_dev.argtypes = [vp]
     L.kssd_dist_counts_dev.restype = vp

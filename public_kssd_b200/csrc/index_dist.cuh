@@ -470,6 +470,217 @@ __global__ void __launch_bounds__(kStatThreads) stats_rows_dense_kernel(const St
     rows[i] = out;
 }
 
+// ---- fused sparse Stage III: counts + filter + listing without the Q x R matrix ----
+// For searches that can never print a zero-shared cell (skip_zero, or -D < 1 without --correction: I = 0 gives
+// dist = 1 > D) only the cells some posting touches matter -- P increments instead of Q x R cells.  One CTA owns one
+// query at a time: the gids of its postings are counted in a shared-memory hash table (CAS insert + ATOMS add), a
+// shared bitmap of the touched refs gives the ascending-ref order dist_print_nobin needs without a sort, the keep
+// rule of output_ctrl is applied in place, and the (query, ref, shared) hits are appended to one list; the rows pass
+// then evaluates the statistics densely, one thread per hit.  All components of the index add into the same table.
+struct SparseComp { const uint32_t *qcodes; const uint64_t *qindex; const uint32_t *dense; const uint32_t *mco; };
+struct SparseHit { uint32_t q, r, shared; };
+constexpr int kSparseThreads = 512;
+constexpr uint32_t kSparseSlots = 8192;                       // hash slots per CTA: 64 KiB of keys + counts
+constexpr uint32_t kSparseMaxDistinct = kSparseSlots / 4 * 3; // refs one query may touch before the dense path takes over
+constexpr uint32_t kSparseEmpty = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t sparse_hash(uint32_t g) { return (g * 0x9E3779B1u) >> 19; }   // 13 bits
+
+__device__ __forceinline__ void sparse_insert(uint32_t *keys, uint32_t *vals, uint32_t *bitmap, uint32_t *distinct, uint32_t g)
+{
+    uint32_t h = sparse_hash(g);
+    for (uint32_t probes = 0; probes < kSparseSlots; probes++) {
+        // a ref shared with the query is hit once per shared code: most inserts find their key already there
+        if (*reinterpret_cast<volatile uint32_t *>(&keys[h]) == g) { atomicAdd(&vals[h], 1u); return; }
+        const uint32_t old = atomicCAS(&keys[h], kSparseEmpty, g);
+        if (old == kSparseEmpty) {
+            atomicAdd(distinct, 1u);
+            atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+            atomicAdd(&vals[h], 1u);
+            return;
+        }
+        if (old == g) { atomicAdd(&vals[h], 1u); return; }
+        h = (h + 1) & (kSparseSlots - 1);
+    }
+    atomicAdd(distinct, kSparseSlots);                        // table full: poison the tally, the query goes dense
+}
+
+constexpr uint32_t kSparseTile = 2048;                        // query codes per pass of the walk
+
+// block-wide exclusive prefix of one value per thread; returns the prefix, *total = the block sum (2 barriers)
+__device__ __forceinline__ uint32_t sparse_block_scan(uint32_t v, uint32_t *wsum, uint32_t *total)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();                                          // wsum may still be read from the previous scan
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t off = incl - v, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kSparseThreads / 32; w++) {
+        off += w < wid ? wsum[w] : 0u;
+        tot += wsum[w];
+    }
+    *total = tot;
+    return off;
+}
+
+template <bool TRIVIAL>
+__global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const SparseComp *__restrict__ comps, int n_comp, uint32_t n_qry, uint32_t n_ref,
+                                                                     const StatParams S, const uint32_t *__restrict__ qsz,
+                                                                     const uint32_t *__restrict__ rsz, uint32_t *__restrict__ q_cnt,
+                                                                     unsigned long long *__restrict__ q_pos, unsigned long long *__restrict__ cursor,
+                                                                     uint64_t cap, SparseHit *__restrict__ hits, int *__restrict__ overflow)
+{
+    extern __shared__ __align__(16) uint32_t sparse_sm[];
+    uint32_t *keys = sparse_sm, *vals = keys + kSparseSlots, *lstart = vals + kSparseSlots, *lpre = lstart + kSparseTile,
+             *bitmap = lpre + kSparseTile + 1;
+    __shared__ uint32_t distinct, wsum[kSparseThreads / 32], tbase[kSparseThreads];
+    __shared__ unsigned long long base_s;
+    const uint32_t bw = (n_ref + 31) / 32;
+    for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < kSparseSlots; i += kSparseThreads) { keys[i] = kSparseEmpty; vals[i] = 0; }
+        for (uint32_t i = threadIdx.x; i < bw; i += kSparseThreads) bitmap[i] = 0;
+        if (threadIdx.x == 0) distinct = 0;
+        // ---- walk: per tile of query codes, (A) every thread looks its codes up -- all the random reads of the tile are
+        // in flight at once -- and leaves (list start, length) in shared memory; (B) the tile's postings, numbered through
+        // a prefix sum of the lengths, are split evenly: every thread adds the same number of gids to the table,
+        // whatever the list lengths (the next gid is requested before the current one is inserted).
+        for (int cc = 0; cc < n_comp; cc++) {
+            const SparseComp C = comps[cc];
+            const uint64_t qs = C.qindex[q], qe = C.qindex[q + 1];
+            for (uint64_t t0 = qs; t0 < qe; t0 += kSparseTile) {
+                const uint32_t nt = (uint32_t)min((uint64_t)kSparseTile, qe - t0);
+                constexpr uint32_t kPer = kSparseTile / kSparseThreads;           // consecutive codes per thread
+                uint32_t len[kPer], sum = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < kPer; j++) {
+                    const uint32_t i = threadIdx.x * kPer + j;
+                    uint32_t s0 = 0, s1 = 0;
+                    if (i < nt) {
+                        const uint32_t c = __ldg(&C.qcodes[t0 + i]);
+                        s0 = __ldg(&C.dense[c]);
+                        s1 = __ldg(&C.dense[c + 1]);
+                    }
+                    lstart[i] = s0;
+                    len[j] = s1 - s0;
+                    sum += len[j];
+                }
+                uint32_t T;
+                uint32_t pre = sparse_block_scan(sum, wsum, &T);
+#pragma unroll
+                for (uint32_t j = 0; j < kPer; j++) {
+                    lpre[threadIdx.x * kPer + j] = pre;
+                    pre += len[j];
+                }
+                if (threadIdx.x == kSparseThreads - 1) lpre[kSparseTile] = pre;
+                __syncthreads();
+                // every WARP takes an equal run of the tile's postings, 32 consecutive ones per step: lane l finds the
+                // list of posting pb + l by walking forward from the list of the step's first posting (a step spans two or
+                // three lists), so the gid loads of a step fall into a few contiguous pieces
+                constexpr uint32_t nw = kSparseThreads / 32;
+                const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+                const uint32_t wchunk = ((T + nw - 1) / nw + 31) & ~31u;
+                const uint32_t pw0 = min(wid * wchunk, T), pw1 = min(pw0 + wchunk, T);
+                if (pw0 < pw1) {
+                    uint32_t lo = 0, hi = kSparseTile;                            // list holding posting pw0 (warp-uniform search)
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (lpre[mid] <= pw0) lo = mid; else hi = mid;
+                    }
+                    uint32_t j0 = lo;
+                    auto fetch = [&](uint32_t pb, uint32_t &jl) -> uint32_t {
+                        const uint32_t p = pb + lane;
+                        uint32_t j = j0;
+                        uint32_t g = 0xffffffffu;
+                        if (p < pw1) {
+                            while (lpre[j + 1] <= p) j++;
+                            g = __ldg(&C.mco[lstart[j] + (p - lpre[j])]);
+                        }
+                        jl = j;
+                        return g;
+                    };
+                    uint32_t jl;
+                    uint32_t g = fetch(pw0, jl);
+                    for (uint32_t pb = pw0; pb < pw1; pb += 32) {
+                        const uint32_t cur = g;
+                        j0 = __shfl_sync(kFull, jl, 31);                          // lane 31 is live in every step but the last
+                        if (pb + 32 < pw1) g = fetch(pb + 32, jl);
+                        if (cur != 0xffffffffu) sparse_insert(keys, vals, bitmap, &distinct, cur);
+                    }
+                }
+                __syncthreads();                                                  // lstart / lpre are rewritten by the next tile
+            }
+        }
+        __syncthreads();
+        if (distinct > kSparseMaxDistinct) {                 // uniform: every thread reads the same shared word
+            if (threadIdx.x == 0) { atomicExch(overflow, 1); q_cnt[q] = 0; q_pos[q] = 0; }
+            __syncthreads();
+            continue;
+        }
+        // ---- emission in ascending ref order without a sort: a hit's place is the number of touched refs below it,
+        // read off the bitmap; the threads go over the TABLE slots (hashing spreads the hits evenly over them)
+        const uint32_t Y = qsz[q];
+        constexpr uint32_t kSlotsPer = kSparseSlots / kSparseThreads;
+        if (!TRIVIAL) {                                       // output_ctrl's keep rule, applied per touched cell
+            for (uint32_t i = 0; i < kSlotsPer; i++) {
+                const uint32_t sidx = threadIdx.x + i * kSparseThreads, r = keys[sidx];
+                if (r != kSparseEmpty && !stat_keep(S, rsz[r], Y, vals[sidx])) {
+                    atomicAnd(&bitmap[r >> 5], ~(1u << (r & 31)));
+                    keys[sidx] = kSparseEmpty;
+                }
+            }
+            __syncthreads();
+        }
+        const uint32_t per = (bw + kSparseThreads - 1) / kSparseThreads;         // consecutive bitmap words per thread
+        const uint32_t w0 = min(threadIdx.x * per, bw), w1 = min(w0 + per, bw);
+        uint32_t cnt = 0;
+        for (uint32_t w = w0; w < w1; w++) cnt += __popc(bitmap[w]);
+        uint32_t total;
+        const uint32_t off = sparse_block_scan(cnt, wsum, &total);
+        tbase[threadIdx.x] = off;
+        if (threadIdx.x == 0) {
+            base_s = total ? atomicAdd(cursor, (unsigned long long)total) : 0ull;
+            q_cnt[q] = total;
+            q_pos[q] = base_s;
+        }
+        __syncthreads();
+        const unsigned long long base = base_s;
+        if (total && base + total <= cap) {
+            for (uint32_t i = 0; i < kSlotsPer; i++) {
+                const uint32_t sidx = threadIdx.x + i * kSparseThreads, r = keys[sidx];
+                if (r == kSparseEmpty) continue;
+                const uint32_t w = r >> 5, owner = w / per;
+                uint32_t rank = tbase[owner] + __popc(bitmap[w] & ((1u << (r & 31)) - 1u));
+                for (uint32_t x = owner * per; x < w; x++) rank += __popc(bitmap[x]);
+                SparseHit h;
+                h.q = q; h.r = r; h.shared = vals[sidx];
+                hits[base + rank] = h;
+            }
+        }
+        __syncthreads();                                      // the table is cleared for the next query
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads) stats_rows_sparse_kernel(const StatParams S, const uint32_t *__restrict__ qsz,
+                                                                          const uint32_t *__restrict__ rsz, const SparseHit *__restrict__ hits,
+                                                                          uint64_t n_hits, const unsigned long long *__restrict__ q_pos,
+                                                                          const uint64_t *__restrict__ q_out, StatRow *__restrict__ rows)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
+    if (i >= n_hits) return;
+    const SparseHit h = hits[i];
+    StatRow out;
+    stat_row(S, rsz[h.r], qsz[h.q], h.shared, out);          // kept by construction
+    out.qry = h.q; out.ref = h.r;
+    rows[q_out[h.q] + (i - q_pos[h.q])] = out;
+}
+
 // -N: best n refs per query by the raw metric with the reference's insertion rule
 // (command_dist.c:1212-1227): strictly greater than everything it passes, so ties keep the lower
 // rid first and zero-metric refs are never listed.  One CTA per query; n <= 1024.

@@ -1001,10 +1001,17 @@ struct kssd_dist {
     kssd_ctx *ctx = nullptr;
     int n_qry = 0, n_ref = 0, components_done = 0;
     uint32_t max_qry_size = 0;
+    bool empty_qry = false, empty_ref = false;   // some sketch has no k-mer (its cells give NaN statistics)
     uint32_t *d_ct = nullptr, *d_qsz = nullptr, *d_rsz = nullptr;
     bool owns_ct = true;
     StatRow *d_rows = nullptr;
     uint64_t n_rows = 0;
+    // sparse job (kssd_dist_create_sparse): no Q x R matrix; the components are registered and counted inside kssd_dist_stats
+    bool sparse = false;
+    std::vector<SparseComp> comps;
+    std::vector<const kssd_index_t *> comp_ix;
+    std::vector<uint64_t> comp_ncodes;
+    std::vector<void *> owned;                   // device copies of host query sketches
 };
 
 static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, uint32_t *ct_ext, int filled,
@@ -1014,8 +1021,10 @@ static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_
     CU(cudaSetDevice(c->device));
     kssd_dist *d = new kssd_dist();
     d->ctx = c; d->n_qry = n_qry; d->n_ref = n_ref;
-    for (int i = 0; i < n_qry; i++) d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]);
+    for (int i = 0; i < n_qry; i++) { d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]); d->empty_qry |= qry_ctx_ct[i] == 0; }
+    for (int i = 0; i < n_ref; i++) d->empty_ref |= ref_ctx_ct[i] == 0;
     if (ct_ext) { d->d_ct = ct_ext; d->owns_ct = false; d->components_done = filled ? 1 : 0; }
+    else if (filled < 0) d->sparse = true;       // sparse job: the matrix is allocated only if a query overflows the sparse path
     else CU(cudaMallocAsync(&d->d_ct, (size_t)n_qry * n_ref * 4, c->stream));
     CU(cudaMallocAsync(&d->d_qsz, (size_t)n_qry * 4, c->stream));
     CU(cudaMallocAsync(&d->d_rsz, (size_t)n_ref * 4, c->stream));
@@ -1038,10 +1047,61 @@ extern "C" int kssd_dist_create_ext(kssd_ctx_t *c, int n_qry, int n_ref, const u
     return dist_create(c, n_qry, n_ref, qry_ctx_ct, ref_ctx_ct, ct_dev, already_filled, out);
 }
 
+extern "C" int kssd_dist_create_sparse(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, kssd_dist_t **out)
+{
+    return dist_create(c, n_qry, n_ref, qry_ctx_ct, ref_ctx_ct, nullptr, -1, out);
+}
+
+extern "C" int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev, const uint64_t *qindex_dev,
+                                        uint64_t n_qcodes)
+{
+    if (!d || !ref_ix || !qindex_dev || (n_qcodes && !qcodes_dev)) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: null argument");
+    if (!d->sparse) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: not a sparse job");
+    if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
+    if (d->comps.size() >= 256) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: more than 256 components");
+    d->comps.push_back(SparseComp{qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids});
+    d->comp_ix.push_back(ref_ix);
+    d->comp_ncodes.push_back(n_qcodes);
+    return KSSD_OK;
+}
+
+extern "C" int kssd_dist_sparse_add_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes, const uint64_t *qindex)
+{
+    if (!d || !ref_ix || !qindex) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_host: null argument");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = qindex[d->n_qry];
+    if (n && !qcodes) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_host: null qcodes");
+    uint8_t *buf = nullptr;
+    const size_t ib = 8ull * (d->n_qry + 1);
+    CU(cudaMallocAsync(&buf, ib + n * 4 + 16, c->stream));
+    d->owned.push_back(buf);
+    CU(cudaMemcpyAsync(buf, qindex, ib, cudaMemcpyHostToDevice, c->stream));
+    if (n) CU(cudaMemcpyAsync(buf + ib, qcodes, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return kssd_dist_sparse_add_dev(d, ref_ix, reinterpret_cast<const uint32_t *>(buf + ib), reinterpret_cast<const uint64_t *>(buf), n);
+}
+
+// sparse job -> ordinary job: allocate the matrix and count every registered component into it
+static int dist_densify(kssd_dist *d)
+{
+    kssd_ctx *c = d->ctx;
+    CU(cudaMallocAsync(&d->d_ct, (size_t)d->n_qry * d->n_ref * 4, c->stream));
+    d->owns_ct = true;
+    d->sparse = false;
+    d->components_done = 0;
+    for (size_t i = 0; i < d->comps.size(); i++) {
+        const int rc = kssd_dist_accumulate_dev(d, d->comp_ix[i], d->comps[i].qcodes, d->comps[i].qindex, d->comp_ncodes[i]);
+        if (rc) return rc;
+    }
+    return KSSD_OK;
+}
+
 extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev, const uint64_t *qindex_dev,
                                         uint64_t n_qcodes)
 {
     if (!d || !ref_ix || !qindex_dev || (n_qcodes && !qcodes_dev)) return fail(KSSD_E_INVAL, "kssd_dist_accumulate_dev: null argument");
+    if (d->sparse) return fail(KSSD_E_INVAL, "kssd_dist_accumulate_dev: sparse job, register components with kssd_dist_sparse_add_*");
     if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
     kssd_ctx *c = d->ctx;
     CU(cudaSetDevice(c->device));
@@ -1181,6 +1241,10 @@ extern "C" int kssd_dist_fetch_counts(const kssd_dist_t *d, uint32_t *ct_out)
     if (!d || !ct_out) return fail(KSSD_E_INVAL, "kssd_dist_fetch_counts: null");
     kssd_ctx *c = d->ctx;
     CU(cudaSetDevice(c->device));
+    if (d->sparse) {                              // the matrix was never built: build it now
+        const int rc = dist_densify(const_cast<kssd_dist *>(d));
+        if (rc) return rc;
+    }
     if (d->components_done == 0) CU(cudaMemsetAsync(d->d_ct, 0, (size_t)d->n_qry * d->n_ref * 4, c->stream));
     CU(cudaMemcpyAsync(ct_out, d->d_ct, (size_t)d->n_qry * d->n_ref * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1196,7 +1260,6 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
     CU(cudaSetDevice(c->device));
     if (o->n_neighbors < 0 || o->n_neighbors > 1024 || o->n_neighbors > d->n_ref)
         return fail(KSSD_E_NNEIGH, "neighborN_max %d should smaller than NREF 1024 and ref_num %d", o->n_neighbors, d->n_ref);
-    if (d->components_done == 0) CU(cudaMemsetAsync(d->d_ct, 0, (size_t)d->n_qry * d->n_ref * 4, c->stream));
     StatParams S;
     S.metric = o->metric; S.correction = o->correction; S.kmerlen = o->kmerlen; S.dim_rd_len = o->dim_rd_len;
     S.skip_zero = o->skip_zero; S.dthreshold = o->dthreshold;
@@ -1204,6 +1267,77 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
                                  : (double)(uint32_t)((uint32_t)d->n_ref * (uint32_t)d->n_qry);   // 32-bit wrap, command_dist.c:1186
     if (d->d_rows) { cudaFreeAsync(d->d_rows, c->stream); d->d_rows = nullptr; }
     d->n_rows = 0;
+    if (d->sparse) {
+        // only searches that cannot print a zero-shared cell run sparse; the others need the matrix
+        // (a cell with I = 0 has metric 0 -> dist 1 > D, unless its denominator is 0 too: NaN is never "> D" and prints --
+        //  Jaccard X + Y - I = 0 needs both sketches empty, containment min(X, Y) = 0 needs one of them empty)
+        const bool nan_cells = o->metric == 0 ? (d->empty_qry && d->empty_ref) : (d->empty_qry || d->empty_ref);
+        const bool no_zero_rows = o->n_neighbors == 0 && (o->skip_zero || (o->dthreshold < 1.0 && !o->correction && !nan_cells));
+        const uint32_t bw = ((uint32_t)d->n_ref + 31) / 32;
+        const size_t smem = (2ull * kSparseSlots + 2ull * kSparseTile + 1 + bw) * 4;
+        if (no_zero_rows && smem <= 200u * 1024u) {
+            const bool trivial = S.dthreshold >= 1.0;
+            const int nc = (int)d->comps.size();
+            CU(cudaEventRecord(c->ev[0], c->stream));
+            CU(c->flags.ensure((size_t)d->n_qry * 4));                 // q_cnt
+            CU(c->counts.ensure((size_t)d->n_qry * 8));                // q_pos
+            CU(c->pos.ensure(((size_t)d->n_qry + 1) * 8));             // q_out
+            CU(c->misc.ensure(16 + sizeof(SparseComp) * 256));
+            uint8_t *mb = c->misc.as<uint8_t>();
+            if (nc) CU(cudaMemcpyAsync(mb + 16, d->comps.data(), sizeof(SparseComp) * nc, cudaMemcpyHostToDevice, c->stream));
+            if (trivial) CU(cudaFuncSetAttribute(dist_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CU(cudaFuncSetAttribute(dist_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int per_sm = smem + 1024 <= 100u * 1024u ? 2 : 1;
+            const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
+            uint64_t total = 0, cap = std::max<uint64_t>(1ull << 22, (uint64_t)d->n_qry * 1024);
+            int over = 0;
+            for (int attempt = 0;; attempt++) {
+                if (cap > 0xffffffffull) return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D");
+                CU(c->keys.ensure(cap * sizeof(SparseHit)));
+                CU(cudaMemsetAsync(mb, 0, 16, c->stream));
+                if (trivial)
+                    dist_sparse_kernel<true><<<grid, kSparseThreads, smem, c->stream>>>(
+                        reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, S, d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(),
+                        c->counts.as<unsigned long long>(), reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(), reinterpret_cast<int *>(mb + 8));
+                else
+                    dist_sparse_kernel<false><<<grid, kSparseThreads, smem, c->stream>>>(
+                        reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, S, d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(),
+                        c->counts.as<unsigned long long>(), reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(), reinterpret_cast<int *>(mb + 8));
+                LAUNCHED(1);
+                CU(cudaEventRecord(c->ev[2], c->stream));
+                CU(cudaMemcpyAsync(&total, mb, 8, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaMemcpyAsync(&over, mb + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaGetLastError());
+                if (over || total <= cap) break;
+                if (attempt) return fail(KSSD_E_NOMEM, "kssd_dist_stats: hit list overflow");
+                cap = total;
+            }
+            if (!over) {
+                CU(cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[2]));       // counting + listing
+                CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
+                if (total) {
+                    size_t tmp = 0;
+                    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream);
+                    CU(c->cubtmp.ensure(tmp));
+                    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream));
+                    stats_rows_sparse_kernel<<<(uint32_t)((total + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
+                        S, d->d_qsz, d->d_rsz, c->keys.as<SparseHit>(), total, c->counts.as<unsigned long long>(), c->pos.as<uint64_t>(), d->d_rows);
+                    LAUNCHED(3);
+                }
+                d->n_rows = total;
+                CU(cudaEventRecord(c->ev[1], c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaGetLastError());
+                CU(cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]));
+                return (int64_t)d->n_rows;
+            }
+        }
+        // some query touches too many references, or zero cells are wanted: go through the matrix after all
+        const int rc = dist_densify(d);
+        if (rc) return rc;
+    }
+    if (d->components_done == 0) CU(cudaMemsetAsync(d->d_ct, 0, (size_t)d->n_qry * d->n_ref * 4, c->stream));
     CU(cudaEventRecord(c->ev[0], c->stream));
     if (o->n_neighbors > 0) {
         const int N = o->n_neighbors;
@@ -1295,7 +1429,8 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
     if (!d) return;
     cudaSetDevice(d->ctx->device);
     cudaStream_t st = d->ctx->stream;
-    if (d->owns_ct) cudaFreeAsync(d->d_ct, st);
+    if (d->owns_ct && d->d_ct) cudaFreeAsync(d->d_ct, st);
+    for (void *p : d->owned) cudaFreeAsync(p, st);
     cudaFreeAsync(d->d_qsz, st);
     cudaFreeAsync(d->d_rsz, st);
     if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);

@@ -279,15 +279,21 @@ class DistJob:
     """Q x R shared-k-mer count matrix (sharedk_ct.dat) and the statistics of distance.out."""
 
     def __init__(self, ctx: Context, qry_ctx_ct: np.ndarray, ref_ctx_ct: np.ndarray, ct_dev_ptr: int | None = None,
-                 already_filled: bool = False):
+                 already_filled: bool = False, sparse: bool = False):
         """ct_dev_ptr: optional caller-owned device buffer (Q*R uint32) for the count matrix, e.g. a torch tensor that
-        takes part in a reduce-scatter (parallel.py)."""
+        takes part in a reduce-scatter (parallel.py).
+        sparse: no count matrix -- accumulate() only registers the component and stats() counts, filters and lists in
+        one kernel (kssd_dist_create_sparse); same rows, work proportional to the postings touched."""
         self.ctx = ctx
+        self.sparse = sparse
         q = np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
         r = np.ascontiguousarray(ref_ctx_ct, dtype=np.uint32)
         self.n_qry, self.n_ref = q.size, r.size
         self._h = C.c_void_p()
-        if ct_dev_ptr is None:
+        if sparse:
+            assert ct_dev_ptr is None
+            check(lib().kssd_dist_create_sparse(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.byref(self._h)))
+        elif ct_dev_ptr is None:
             check(lib().kssd_dist_create(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.byref(self._h)))
         else:
             check(lib().kssd_dist_create_ext(ctx._h, q.size, r.size, ptr(q, C.c_uint32), ptr(r, C.c_uint32), C.c_void_p(ct_dev_ptr),
@@ -296,9 +302,13 @@ class DistJob:
     def accumulate(self, ref_index: Index, qcodes: np.ndarray, qindex: np.ndarray):
         qcodes = np.ascontiguousarray(qcodes, dtype=np.uint32)
         qindex = np.ascontiguousarray(qindex, dtype=np.uint64)
-        check(lib().kssd_dist_accumulate_host(self._h, ref_index._h, ptr(qcodes, C.c_uint32), ptr(qindex, C.c_uint64)))
+        f = lib().kssd_dist_sparse_add_host if self.sparse else lib().kssd_dist_accumulate_host
+        check(f(self._h, ref_index._h, ptr(qcodes, C.c_uint32), ptr(qindex, C.c_uint64)))
 
     def accumulate_dev(self, ref_index: Index, qcodes_ptr: int, qindex_ptr: int, n_qcodes: int):
+        if self.sparse:      # the pointers must stay valid until stats() returns
+            check(lib().kssd_dist_sparse_add_dev(self._h, ref_index._h, C.c_void_p(qcodes_ptr), C.c_void_p(qindex_ptr), n_qcodes))
+            return
         check(lib().kssd_dist_accumulate_dev(self._h, ref_index._h, C.c_void_p(qcodes_ptr), C.c_void_p(qindex_ptr), n_qcodes))
 
     def counts(self) -> np.ndarray:

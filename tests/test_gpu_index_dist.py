@@ -158,3 +158,73 @@ def test_topn_neighbors(gpu_ctx_l3k10, oracle_mod):
     with pytest.raises(kssd.KssdError):
         job.stats(n_neighbors=61)
     job.close(); ix.close()
+
+
+@pytest.mark.parametrize("opts", [dict(skip_zero=1), dict(dthreshold=0.05), dict(metric=1, dthreshold=0.2), dict(metric=1, skip_zero=1, correction=1),
+                                  dict(dthreshold=1.0), dict(n_neighbors=3), dict(dthreshold=0.3, correction=1)])
+def test_sparse_job_rows_identical_to_dense(gpu_ctx_l3k10, opts):
+    """kssd_dist_create_sparse: fused count + filter + listing without the Q x R matrix gives byte-identical rows; options
+    that print zero-shared cells (-D >= 1, -N, --correction with -D) fall back to the matrix transparently."""
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(700, 400, seed=8, cluster_size=25)
+    qc, qi = synth.synth_sketches(67, 400, seed=8, cluster_size=5)
+    # an empty query and an empty reference in the middle
+    qi = np.concatenate([qi[:10], qi[10:11], qi[10:]])
+    ri = np.concatenate([ri[:100], ri[100:101], ri[100:]])
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    dense = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz)
+    dense.accumulate(ix, qc, qi)
+    want = dense.stats(**opts)
+    sp = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz, sparse=True)
+    sp.accumulate(ix, qc, qi)
+    got = sp.stats(**opts)
+    assert len(want) > 0 and got.tobytes() == want.tobytes()
+    assert np.array_equal(sp.counts(), dense.counts())          # counts on request: the matrix is built then
+    dense.close(); sp.close(); ix.close()
+
+
+def test_sparse_job_many_refs_per_query_falls_back(gpu_ctx_l3k10):
+    """A query that touches more references than the shared-memory table holds sends the job through the matrix."""
+    from public_kssd_b200 import kssd
+    n_ref = 9000
+    base = np.arange(50, dtype=np.uint32) * 7919 + 13
+    rc = np.concatenate([np.sort(np.concatenate([base[:3], np.array([100000 + g], dtype=np.uint32)])) for g in range(n_ref)])
+    ri = np.arange(n_ref + 1, dtype=np.uint64) * 4
+    qc = np.sort(np.concatenate([base, np.array([100000 + 5, 100000 + 77], dtype=np.uint32)]))
+    qi = np.array([0, len(qc)], dtype=np.uint64)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    dense = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz)
+    dense.accumulate(ix, qc, qi)
+    want = dense.stats(skip_zero=1)
+    sp = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz, sparse=True)
+    sp.accumulate(ix, qc, qi)
+    got = sp.stats(skip_zero=1)
+    assert len(want) == n_ref and got.tobytes() == want.tobytes()
+    dense.close(); sp.close(); ix.close()
+
+
+def test_sparse_job_multi_component(shuf_l3k10):
+    """K11: 16 components add into the same per-query table."""
+    from public_kssd_b200 import kssd
+    ctx = kssd.Context(11, 6, 3, shuf_l3k10)
+    try:
+        parts_r = [synth.synth_sketches(120, 90, seed=20 + c, cluster_size=10) for c in range(16)]
+        parts_q = [synth.synth_sketches(15, 90, seed=20 + c, cluster_size=3) for c in range(16)]
+        rsz = sum(np.diff(ri).astype(np.uint32) for _, ri in parts_r)
+        qsz = sum(np.diff(qi).astype(np.uint32) for _, qi in parts_q)
+        idx = [ctx.combco2mco(rc, ri) for rc, ri in parts_r]
+        dense = kssd.DistJob(ctx, qsz, rsz)
+        sp = kssd.DistJob(ctx, qsz, rsz, sparse=True)
+        for ix, (qc, qi) in zip(idx, parts_q):
+            dense.accumulate(ix, qc, qi)
+            sp.accumulate(ix, qc, qi)
+        want = dense.stats(metric=1, dthreshold=0.5)
+        got = sp.stats(metric=1, dthreshold=0.5)
+        assert len(want) > 0 and got.tobytes() == want.tobytes()
+        dense.close(); sp.close()
+        for ix in idx:
+            ix.close()
+    finally:
+        ctx.close()
