@@ -507,24 +507,27 @@ __device__ __forceinline__ void sparse_insert(uint32_t *keys, uint32_t *vals, ui
 
 constexpr uint32_t kSparseTile = 2048;                        // query codes per pass of the walk
 
-// block-wide exclusive prefix of one value per thread; returns the prefix, *total = the block sum (2 barriers)
-__device__ __forceinline__ uint32_t sparse_block_scan(uint32_t v, uint32_t *wsum, uint32_t *total)
+// block-wide exclusive prefix of two values per thread (x, y); returns the prefixes, *total = the block sums (2 barriers)
+__device__ __forceinline__ uint2 sparse_block_scan(uint2 v, uint2 *wsum, uint2 *total)
 {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = v;
+    uint2 incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= (uint32_t)o) incl += t;
+        const uint32_t tx = __shfl_up_sync(kFull, incl.x, o), ty = __shfl_up_sync(kFull, incl.y, o);
+        if (lane >= (uint32_t)o) { incl.x += tx; incl.y += ty; }
     }
     __syncthreads();                                          // wsum may still be read from the previous scan
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
-    uint32_t off = incl - v, tot = 0;
+    uint2 off = make_uint2(incl.x - v.x, incl.y - v.y), tot = make_uint2(0, 0);
 #pragma unroll
     for (uint32_t w = 0; w < kSparseThreads / 32; w++) {
-        off += w < wid ? wsum[w] : 0u;
-        tot += wsum[w];
+        const uint2 s = wsum[w];
+        off.x += w < wid ? s.x : 0u;
+        off.y += w < wid ? s.y : 0u;
+        tot.x += s.x;
+        tot.y += s.y;
     }
     *total = tot;
     return off;
@@ -540,7 +543,8 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
     extern __shared__ __align__(16) uint32_t sparse_sm[];
     uint32_t *keys = sparse_sm, *vals = keys + kSparseSlots, *lstart = vals + kSparseSlots, *lpre = lstart + kSparseTile,
              *bitmap = lpre + kSparseTile + 1;
-    __shared__ uint32_t distinct, wsum[kSparseThreads / 32], tbase[kSparseThreads];
+    __shared__ uint32_t distinct, tbase[kSparseThreads];
+    __shared__ uint2 wsum[kSparseThreads / 32];
     __shared__ unsigned long long base_s;
     const uint32_t bw = (n_ref + 31) / 32;
     for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
             for (uint64_t t0 = qs; t0 < qe; t0 += kSparseTile) {
                 const uint32_t nt = (uint32_t)min((uint64_t)kSparseTile, qe - t0);
                 constexpr uint32_t kPer = kSparseTile / kSparseThreads;           // consecutive codes per thread
-                uint32_t len[kPer], sum = 0;
+                uint32_t st[kPer], len[kPer], sum = 0, live = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < kPer; j++) {
                     const uint32_t i = threadIdx.x * kPer + j;
@@ -567,18 +571,27 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
                         s0 = __ldg(&C.dense[c]);
                         s1 = __ldg(&C.dense[c + 1]);
                     }
-                    lstart[i] = s0;
+                    st[j] = s0;
                     len[j] = s1 - s0;
                     sum += len[j];
+                    live += len[j] != 0;
                 }
-                uint32_t T;
-                uint32_t pre = sparse_block_scan(sum, wsum, &T);
+                // only the non-empty lists get a descriptor (a query code no reference holds has an empty list)
+                uint2 tot;
+                const uint2 pre = sparse_block_scan(make_uint2(live, sum), wsum, &tot);
+                const uint32_t T = tot.y, nl = tot.x;
+                {
+                    uint32_t slot = pre.x, p = pre.y;
 #pragma unroll
-                for (uint32_t j = 0; j < kPer; j++) {
-                    lpre[threadIdx.x * kPer + j] = pre;
-                    pre += len[j];
+                    for (uint32_t j = 0; j < kPer; j++)
+                        if (len[j]) {
+                            lstart[slot] = st[j];
+                            lpre[slot] = p;
+                            slot++;
+                            p += len[j];
+                        }
                 }
-                if (threadIdx.x == kSparseThreads - 1) lpre[kSparseTile] = pre;
+                if (threadIdx.x == 0) lpre[nl] = T;
                 __syncthreads();
                 // every WARP takes an equal run of the tile's postings, 32 consecutive ones per step: lane l finds the
                 // list of posting pb + l by walking forward from the list of the step's first posting (a step spans two or
@@ -588,7 +601,7 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
                 const uint32_t wchunk = ((T + nw - 1) / nw + 31) & ~31u;
                 const uint32_t pw0 = min(wid * wchunk, T), pw1 = min(pw0 + wchunk, T);
                 if (pw0 < pw1) {
-                    uint32_t lo = 0, hi = kSparseTile;                            // list holding posting pw0 (warp-uniform search)
+                    uint32_t lo = 0, hi = nl;                                     // list holding posting pw0 (warp-uniform search)
                     while (hi - lo > 1) {
                         const uint32_t mid = (lo + hi) >> 1;
                         if (lpre[mid] <= pw0) lo = mid; else hi = mid;
@@ -605,13 +618,29 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
                         jl = j;
                         return g;
                     };
-                    uint32_t jl;
-                    uint32_t g = fetch(pw0, jl);
-                    for (uint32_t pb = pw0; pb < pw1; pb += 32) {
-                        const uint32_t cur = g;
-                        j0 = __shfl_sync(kFull, jl, 31);                          // lane 31 is live in every step but the last
-                        if (pb + 32 < pw1) g = fetch(pb + 32, jl);
-                        if (cur != 0xffffffffu) sparse_insert(keys, vals, bitmap, &distinct, cur);
+                    // four steps of gid loads stay in flight ahead of the inserts (a first touch of a list is a DRAM miss)
+                    constexpr int kAhead = 4;
+                    uint32_t g[kAhead], jl;
+#pragma unroll
+                    for (int u = 0; u < kAhead; u++) {
+                        g[u] = 0xffffffffu;
+                        if (pw0 + 32u * u < pw1) {
+                            g[u] = fetch(pw0 + 32u * u, jl);
+                            j0 = __shfl_sync(kFull, jl, 31);                      // lane 31 is live in every step but the last
+                        }
+                    }
+                    for (uint32_t pb = pw0; pb < pw1; pb += 32u * kAhead) {
+#pragma unroll
+                        for (int u = 0; u < kAhead; u++) {
+                            const uint32_t cur = g[u];
+                            g[u] = 0xffffffffu;
+                            const uint32_t nxt = pb + 32u * (u + kAhead);
+                            if (nxt < pw1) {
+                                g[u] = fetch(nxt, jl);
+                                j0 = __shfl_sync(kFull, jl, 31);
+                            }
+                            if (cur != 0xffffffffu) sparse_insert(keys, vals, bitmap, &distinct, cur);
+                        }
                     }
                 }
                 __syncthreads();                                                  // lstart / lpre are rewritten by the next tile
@@ -637,12 +666,14 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
             }
             __syncthreads();
         }
-        const uint32_t per = (bw + kSparseThreads - 1) / kSparseThreads;         // consecutive bitmap words per thread
-        const uint32_t w0 = min(threadIdx.x * per, bw), w1 = min(w0 + per, bw);
+        uint32_t per_log = 0;                                 // consecutive bitmap words per thread: a power of two
+        while (((uint32_t)kSparseThreads << per_log) < bw) per_log++;
+        const uint32_t w0 = min(threadIdx.x << per_log, bw), w1 = min(w0 + (1u << per_log), bw);
         uint32_t cnt = 0;
         for (uint32_t w = w0; w < w1; w++) cnt += __popc(bitmap[w]);
-        uint32_t total;
-        const uint32_t off = sparse_block_scan(cnt, wsum, &total);
+        uint2 tot2;
+        const uint32_t off = sparse_block_scan(make_uint2(cnt, 0u), wsum, &tot2).x;
+        const uint32_t total = tot2.x;
         tbase[threadIdx.x] = off;
         if (threadIdx.x == 0) {
             base_s = total ? atomicAdd(cursor, (unsigned long long)total) : 0ull;
@@ -655,9 +686,9 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
             for (uint32_t i = 0; i < kSlotsPer; i++) {
                 const uint32_t sidx = threadIdx.x + i * kSparseThreads, r = keys[sidx];
                 if (r == kSparseEmpty) continue;
-                const uint32_t w = r >> 5, owner = w / per;
+                const uint32_t w = r >> 5, owner = w >> per_log;
                 uint32_t rank = tbase[owner] + __popc(bitmap[w] & ((1u << (r & 31)) - 1u));
-                for (uint32_t x = owner * per; x < w; x++) rank += __popc(bitmap[x]);
+                for (uint32_t x = owner << per_log; x < w; x++) rank += __popc(bitmap[x]);
                 SparseHit h;
                 h.q = q; h.r = r; h.shared = vals[sidx];
                 hits[base + rank] = h;
