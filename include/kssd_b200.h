@@ -128,6 +128,22 @@ int kssd_sketch_dev_ptrs(const kssd_sketch_t *s, int comp, const uint32_t **ids_
 int kssd_sketch_stats(const kssd_sketch_t *s, uint64_t *n_occurrences, float *scan_kernel_ms);
 void kssd_sketch_free(kssd_sketch_t *s);
 
+/* Stage I straight from files -- replaces the file loop of run_stageI (command_dist.c:277-312) together with the
+ * popen("zcat -fc") decode inside fasta2co / fastq2co (iseq2comem.c:187-200, :283-290).  n_threads host threads read
+ * plain files straight into pinned staging memory and inflate .gz files with zlib; batches of about batch_bytes are
+ * copied and sketched on the context stream while the readers fill the second staging buffer.  The result is what
+ * kssd_sketch_fetch would give for all files in input order (combco.<c>, combco.index.<c>, combco.<c>.a).
+ * n_threads <= 0: all hardware threads; batch_bytes 0: 1 GiB.  Modes: every KSSD_MODE_* but BYREAD. */
+typedef struct kssd_stage1 kssd_stage1_t;
+int kssd_stage1_files(kssd_ctx_t *ctx, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts,
+                      int n_threads, size_t batch_bytes, kssd_stage1_t **out);
+int64_t kssd_stage1_count(const kssd_stage1_t *s, int comp);
+int kssd_stage1_fetch(const kssd_stage1_t *s, int comp, uint32_t *ids, uint64_t *index /* n_files+1 */, uint16_t *abund);
+int kssd_stage1_status(const kssd_stage1_t *s, int32_t *status_out /* n_files */);
+/* average busy seconds per reader thread, seconds inside GPU calls, wall seconds, decoded bytes, batches */
+int kssd_stage1_timing(const kssd_stage1_t *s, double *read_s, double *gpu_s, double *total_s, uint64_t *bytes, int *batches);
+void kssd_stage1_free(kssd_stage1_t *s);
+
 /* ------------------------------------------------------------------------------------------ *
  * Stage II -- sketch -> inverted index.  Replaces combco2mco (co2mco.c:25-77) for one component:
  * input = combco.<c> (u32 codes) + combco.index.<c> (u64[n+1]); output = the postings of mco.<c>

@@ -84,6 +84,8 @@ struct kssd_ctx {
     uint2 *d_ht = nullptr;
     // scratch
     DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, counts, minord, cubtmp, misc;
+    uint8_t *stag[2] = {nullptr, nullptr};       // pinned staging buffers of kssd_stage1_files
+    uint64_t stag_cap[2] = {0, 0};
     // cached span plan of the last batch layout
     bool plan_valid = false;
     uint64_t plan_key = 0;
@@ -235,6 +237,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->counts, &c->minord,
                       &c->cubtmp, &c->misc})
         b->release();
+    for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
     cudaFree(c->d_prefilter);
     cudaFree(c->d_ht);
     for (auto &e : c->ev) cudaEventDestroy(e);
@@ -785,6 +788,8 @@ extern "C" void kssd_sketch_free(kssd_sketch_t *s)
     if (s->d_blob) cudaFreeAsync(s->d_blob, s->ctx->stream);
     delete s;
 }
+
+#include "stage1_files.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Stage II

@@ -189,6 +189,35 @@ class Context:
             self._raise_status(sk)
         return sk
 
+    def sketch_files(self, paths: Sequence[str], mode: int = capi.MODE_FASTA, Q: int = 0, M: int = 1, threads: int = 0,
+                     batch_bytes: int = 0, strict: bool = True):
+        """Stage I from files (run_stageI's file loop + the zcat decode): plain or .gz FASTA / FASTQ files, read and
+        inflated by host threads into pinned staging buffers and sketched batch by batch (kssd_stage1_files).
+        Returns (Sketch over all files in input order, timing dict)."""
+        arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+        opts = capi.SketchOpts(mode, Q, M, 0, 0, 0)
+        h = C.c_void_p()
+        check(lib().kssd_stage1_files(self._h, arr, len(paths), C.byref(opts), threads, batch_bytes, C.byref(h)))
+        try:
+            ids, index, abund = [], [], []
+            for c in range(self.component_num):
+                n = check(lib().kssd_stage1_count(h, c))
+                a = np.empty(n, dtype=np.uint32)
+                ix = np.empty(len(paths) + 1, dtype=np.uint64)
+                ab = np.empty(n, dtype=np.uint16) if mode == capi.MODE_FASTQ_ABUND else None
+                check(lib().kssd_stage1_fetch(h, c, ptr(a, C.c_uint32), ptr(ix, C.c_uint64), ptr(ab, C.c_uint16) if ab is not None else None))
+                ids.append(a); index.append(ix); abund.append(ab)
+            status = np.zeros(len(paths), dtype=np.int32)
+            check(lib().kssd_stage1_status(h, ptr(status, C.c_int32)))
+            rs, gs, ts, nb, nbat = C.c_double(), C.c_double(), C.c_double(), C.c_uint64(), C.c_int()
+            check(lib().kssd_stage1_timing(h, C.byref(rs), C.byref(gs), C.byref(ts), C.byref(nb), C.byref(nbat)))
+        finally:
+            lib().kssd_stage1_free(h)
+        sk = Sketch(ids, index, abund, [None] * self.component_num, status, 0, 0.0, 0.0)
+        if strict:
+            self._raise_status(sk)
+        return sk, dict(read_s=rs.value, gpu_s=gs.value, total_s=ts.value, bytes=int(nb.value), batches=int(nbat.value))
+
     def reads2mco(self, files: Sequence[bytes | np.ndarray], strict: bool = True):
         """`kssd dist --byread` (reference reads2mco, iseq2comem.c:78-186) for every file of FASTA-formatted reads in the
         batch.  Returns one dict per file: {"n_reads": readn, "ids": [per component: ids in stream order, duplicates

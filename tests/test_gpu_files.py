@@ -1,0 +1,74 @@
+"""GPU parity: Stage I straight from files (kssd_stage1_files) == the batch API on the same bytes, for plain and .gz
+inputs, many small batches, one file larger than a batch, FASTQ modes; and against the reference goldens."""
+import gzip
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from public_kssd_b200 import capi, synth
+
+GOLD = Path(__file__).resolve().parent / "golden"
+sys.path.insert(0, str(GOLD))
+import cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _write(tmp, files, gz_every=2):
+    paths = []
+    for i, (name, data) in enumerate(sorted(files.items())):
+        raw = data.tobytes()
+        if gz_every and i % gz_every == 1:
+            p = tmp / f"{name}.fa.gz"
+            with gzip.open(p, "wb", compresslevel=1) as f:
+                f.write(raw)
+        else:
+            p = tmp / f"{name}.fa"
+            p.write_bytes(raw)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("batch_bytes,threads", [(0, 0), (300_000, 3), (1 << 20, 1)])
+def test_files_match_batch_api_and_reference(gpu_ctx_l3k10, tmp_path, batch_bytes, threads):
+    files = cases.fasta_inputs()
+    paths = _write(tmp_path, files)
+    sk, t = gpu_ctx_l3k10.sketch_files(paths, threads=threads, batch_bytes=batch_bytes)
+    want = gpu_ctx_l3k10.sketch([files[n] for n in sorted(files)])
+    assert np.array_equal(sk.index[0], want.index[0]) and np.array_equal(sk.ids[0], want.ids[0])
+    assert t["bytes"] == sum(v.size for v in files.values()) and t["batches"] >= (1 if batch_bytes == 0 else 3)
+    g = np.load(GOLD / "fasta_l3k10.npz", allow_pickle=False)
+    for i, n in enumerate(sorted(files)):
+        a, b = int(sk.index[0][i]), int(sk.index[0][i + 1])
+        assert np.array_equal(sk.ids[0][a:b], np.sort(g[f"{n}.0"]))       # same set as the reference wrote
+
+
+def test_files_fastq_modes(shuf_s5, tmp_path):
+    from public_kssd_b200 import kssd
+    ctx = kssd.Context(8, 5, 2, shuf_s5)
+    try:
+        files = cases.fastq_inputs()
+        paths = _write(tmp_path, files)
+        names = sorted(files)
+        sk, _ = ctx.sketch_files(paths, mode=capi.MODE_FASTQ, Q=40, M=2, batch_bytes=2_000_000, threads=2)
+        want = ctx.sketch_fastq([files[n] for n in names], Q=40, M=2)
+        assert np.array_equal(sk.index[0], want.index[0]) and np.array_equal(sk.ids[0], want.ids[0])
+        sk, _ = ctx.sketch_files(paths, mode=capi.MODE_FASTQ_ABUND, threads=2)
+        want = ctx.sketch_fastq([files[n] for n in names], abundance=True)
+        assert np.array_equal(sk.ids[0], want.ids[0]) and np.array_equal(sk.abund[0], want.abund[0])
+    finally:
+        ctx.close()
+
+
+def test_files_errors(gpu_ctx_l3k10, tmp_path):
+    from public_kssd_b200 import kssd
+    with pytest.raises(kssd.KssdError):
+        gpu_ctx_l3k10.sketch_files([tmp_path / "missing.fa"])
+    bad = tmp_path / "trunc.fa"
+    bad.write_bytes(b">h\nACGTACGTACGTACGTACGTACGTACGTACGT\n>header without end")
+    with pytest.raises(kssd.KssdError):
+        gpu_ctx_l3k10.sketch_files([bad])                                    # the reference exits on this file too
+    sk, _ = gpu_ctx_l3k10.sketch_files([bad], strict=False)
+    assert sk.status[0] == capi.E_HEADER_EOF
