@@ -266,6 +266,24 @@ int kssd_format_distance_rows(const kssd_stat_row_t *rows, size_t n_rows, const 
                               char **text_out, size_t *text_len);
 void kssd_host_free(void *p);
 
+/* ------------------------------------------------------------------------------------------ *
+ * kssd set (reference command_set.c), one component per call (the caller loops over combco.<c>):
+ *   union      -u  sketch_union      (:226-293)  pan.<c>      = every code that occurs, ascending
+ *   uniq union -q  uniq_sketch_union (:374-443)  uniq_pan.<c> = codes that occur exactly once in combco.<c>
+ *   operate    -i / -s <pan>  sketch_operate (:294-373): every genome keeps, in order, the codes whose membership in
+ *              the pan sketch equals `intersect`; index_out is the rebuilt combco.index.<c>, the per-genome counts
+ *              (cofiles.stat ctx_ct) are its differences summed over the components.
+ * pan_out / combco_out need room for n_codes entries.
+ * ------------------------------------------------------------------------------------------ */
+int kssd_set_union_host(kssd_ctx_t *ctx, const uint32_t *combco, uint64_t n_codes, int uniq, uint32_t *pan_out, uint64_t *n_out);
+int kssd_set_union_dev(kssd_ctx_t *ctx, const uint32_t *combco_dev, uint64_t n_codes, int uniq, uint32_t *pan_dev,
+                       uint64_t pan_cap, uint64_t *n_out);
+int kssd_set_operate_host(kssd_ctx_t *ctx, const uint32_t *combco, const uint64_t *index, int n_genomes,
+                          const uint32_t *pan, uint64_t n_pan, int intersect, uint32_t *combco_out, uint64_t *index_out);
+int kssd_set_operate_dev(kssd_ctx_t *ctx, const uint32_t *combco_dev, const uint64_t *index_dev, int n_genomes,
+                         uint64_t n_codes, const uint32_t *pan_dev, uint64_t n_pan, int intersect,
+                         uint32_t *combco_out_dev, uint64_t *index_out_dev);
+
 /* device time (ms, CUDA events on the context stream) of the last scan / index / count / stats
  * kernel sequence issued through this context; which = 0 sketch scan, 1 sketch total,
  * 2 index build, 3 dist counts, 4 dist stats */

@@ -386,3 +386,48 @@ int orc_output_ctrl(uint32_t X, uint32_t Y, uint32_t I, int metric_kind, int cor
     out[7] = log(ORC_GM(c1)) / kmerlen;
     return 1;
 }
+
+
+/* ---- kssd set (command_set.c) ---- */
+/* sketch_union (:226-293) / uniq_sketch_union (:374-443) for ONE component: the codes of combco.<c> that occur
+ * (uniq: that occur exactly once in the whole file), ascending.  code_bits = 4*COMPONENT_SZ.  Returns the count. */
+size_t orc_set_union(const uint32_t *combco, size_t n, int uniq, int code_bits, uint32_t *out)
+{
+    const size_t words = ((size_t)1 << code_bits) / 64;
+    uint64_t *seen = (uint64_t *)calloc(words, 8), *once = NULL;
+    if (uniq) { once = (uint64_t *)malloc(words * 8); memset(once, 0xff, words * 8); }
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t bit = 0x8000000000000000ULL >> (combco[i] % 64);
+        if (uniq && (seen[combco[i] / 64] & bit)) once[combco[i] / 64] &= ~bit;
+        seen[combco[i] / 64] |= bit;
+    }
+    size_t k = 0;
+    for (size_t w = 0; w < words; w++) {
+        const uint64_t v = uniq ? (seen[w] & once[w]) : seen[w];
+        if (!v) continue;
+        for (int b = 0; b < 64; b++)
+            if ((0x8000000000000000ULL >> b) & v) out[k++] = (uint32_t)(64 * w + b);
+    }
+    free(seen);
+    free(once);
+    return k;
+}
+
+/* sketch_operate (:294-373) for ONE component: every genome keeps, in order, the codes whose membership in the pan
+ * sketch equals `intersect` (1 = -i, 0 = -s); out_index is the rebuilt combco.index (n_genomes + 1). */
+void orc_set_operate(const uint32_t *combco, const uint64_t *index, int n_genomes, const uint32_t *pan, size_t n_pan,
+                     int intersect, int code_bits, uint32_t *out, uint64_t *out_index)
+{
+    const size_t words = ((size_t)1 << code_bits) / 64;
+    uint64_t *dict = (uint64_t *)calloc(words, 8);
+    for (size_t i = 0; i < n_pan; i++) dict[pan[i] / 64] |= 0x8000000000000000ULL >> (pan[i] % 64);
+    out_index[0] = 0;
+    for (int g = 0; g < n_genomes; g++) {
+        out_index[g + 1] = out_index[g];
+        for (uint64_t i = index[g]; i < index[g + 1]; i++) {
+            const int in = (dict[combco[i] / 64] & (0x8000000000000000ULL >> (combco[i] % 64))) != 0;
+            if (in == intersect) out[out_index[g + 1]++] = combco[i];
+        }
+    }
+    free(dict);
+}

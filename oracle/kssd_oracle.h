@@ -84,6 +84,11 @@ int orc_output_ctrl(uint32_t X, uint32_t Y, uint32_t I, int metric_kind, int cor
                     int kmerlen, int dim_reduct_len, double dthreshold, uint64_t cmprsn_num,
                     double out[9]);
 
+/* kssd set, one component (command_set.c:226-293 union, :374-443 uniq union, :294-373 intersect / subtract) */
+size_t orc_set_union(const uint32_t *combco, size_t n, int uniq, int code_bits, uint32_t *out);
+void orc_set_operate(const uint32_t *combco, const uint64_t *index, int n_genomes, const uint32_t *pan, size_t n_pan,
+                     int intersect, int code_bits, uint32_t *out, uint64_t *out_index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,10 @@ def lib() -> C.CDLL:
         L.orc_shortreads2koc.argtypes = [C.c_void_p, u8p, C.c_size_t, u64p]
         L.orc_reads2mco.argtypes = [C.c_void_p, u8p, C.c_size_t, u32p, i32p, u64p, C.c_size_t, u64p]
         L.orc_reads2mco.restype = C.c_long
+        L.orc_set_union.argtypes = [u32p, C.c_size_t, C.c_int, C.c_int, u32p]
+        L.orc_set_union.restype = C.c_size_t
+        L.orc_set_operate.argtypes = [u32p, u64p, C.c_int, u32p, C.c_size_t, C.c_int, C.c_int, u32p, u64p]
+        L.orc_set_operate.restype = None
         L.orc_write_co.argtypes = [C.c_void_p, u64p, C.c_int, u32p, i32p, u16p]
         L.orc_write_co.restype = C.c_size_t
         L.orc_combco2mco.argtypes = [u32p, u64p, C.c_int, C.c_int, u64p, u32p]
@@ -250,6 +254,26 @@ def output_ctrl(X, Y, I, metric=0, correction=0, kmerlen=20, dim_rd_len=6, dthre
 # ----------------------------------------------------------------------------------------------
 def ref_available() -> bool:
     return REF_BIN.exists()
+
+
+def set_union(combco: np.ndarray, uniq: bool = False, code_bits: int = 28) -> np.ndarray:
+    """kssd set -u / -q for one component: pan.<c> / uniq_pan.<c>."""
+    a = np.ascontiguousarray(combco, dtype=np.uint32)
+    out = np.empty(max(a.size, 1), dtype=np.uint32)
+    n = lib().orc_set_union(_p(a, C.c_uint32), a.size, int(uniq), code_bits, _p(out, C.c_uint32))
+    return out[:n].copy()
+
+
+def set_operate(combco: np.ndarray, index: np.ndarray, pan: np.ndarray, intersect: bool, code_bits: int = 28):
+    """kssd set -i / -s <pan> for one component: (combco.<c>, combco.index.<c>) after the filter."""
+    a = np.ascontiguousarray(combco, dtype=np.uint32)
+    ix = np.ascontiguousarray(index, dtype=np.uint64)
+    pn = np.ascontiguousarray(pan, dtype=np.uint32)
+    out = np.empty(max(a.size, 1), dtype=np.uint32)
+    oix = np.empty(ix.size, dtype=np.uint64)
+    lib().orc_set_operate(_p(a, C.c_uint32), _p(ix, C.c_uint64), ix.size - 1, _p(pn, C.c_uint32), pn.size, int(intersect), code_bits,
+                          _p(out, C.c_uint32), _p(oix, C.c_uint64))
+    return out[:int(oix[-1])].copy(), oix
 
 
 def run_ref(args, cwd=None, binary=None, timeout=3600) -> subprocess.CompletedProcess:

@@ -19,6 +19,7 @@
 #include "index_dist.cuh"
 #include "sketch_scan32.cuh"
 #include "sketch_fastq.cuh"
+#include "set_ops.cuh"
 
 using namespace kssd;
 
@@ -1507,3 +1508,133 @@ extern "C" int kssd_format_distance_rows(const kssd_stat_row_t *rows, size_t n_r
 }
 
 extern "C" void kssd_host_free(void *p) { free(p); }
+
+
+// ------------------------------------------------------------------------------------------------
+// kssd set (reference command_set.c): union / uniq union, intersect / subtract
+// ------------------------------------------------------------------------------------------------
+static int set_code_words(kssd_ctx *c, uint64_t *n_words)
+{
+    const int bits = 4 * std::min(c->P.k - c->P.L, c->info.component_sz > 0 ? c->info.component_sz : 7);
+    *n_words = (1ull << bits) / 32;
+    return bits;
+}
+
+// members of (seen & ~twice) ascending into out (device, capacity cap); returns the count through *n_out
+static int set_emit(kssd_ctx *c, const uint32_t *seen, const uint32_t *twice, uint64_t n_words, uint32_t *out, uint64_t cap, uint64_t *n_out)
+{
+    const uint32_t nblk = (uint32_t)((n_words + kSetWordsPerBlock - 1) / kSetWordsPerBlock);
+    CU(c->flags.ensure((size_t)nblk * 4));
+    CU(c->pos.ensure((size_t)nblk * 4));
+    set_count_kernel<<<nblk, kSetThreads, 0, c->stream>>>(seen, twice, n_words, c->flags.as<uint32_t>());
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), nblk, c->stream));
+    uint32_t lastoff = 0, lastcnt = 0;
+    CU(cudaMemcpyAsync(&lastoff, c->pos.as<uint32_t>() + (nblk - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&lastcnt, c->flags.as<uint32_t>() + (nblk - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t total = (uint64_t)lastoff + lastcnt;
+    if (total > cap) return fail(KSSD_E_INVAL, "kssd_set_union: output buffer too small (%llu > %llu)", (unsigned long long)total, (unsigned long long)cap);
+    if (total) set_fill_kernel<<<nblk, kSetThreads, 0, c->stream>>>(seen, twice, n_words, c->pos.as<uint32_t>(), out);
+    LAUNCHED(4);
+    *n_out = total;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_set_union_dev(kssd_ctx_t *c, const uint32_t *combco_dev, uint64_t n_codes, int uniq, uint32_t *pan_dev, uint64_t pan_cap,
+                                  uint64_t *n_out)
+{
+    if (!c || !n_out || (n_codes && (!combco_dev || !pan_dev))) return fail(KSSD_E_INVAL, "kssd_set_union_dev: null argument");
+    CU(cudaSetDevice(c->device));
+    uint64_t n_words;
+    set_code_words(c, &n_words);
+    CU(c->keys.ensure(n_words * 4));
+    CU(cudaMemsetAsync(c->keys.p, 0, n_words * 4, c->stream));
+    uint32_t *twice = nullptr;
+    if (uniq) {
+        CU(c->keys2.ensure(n_words * 4));
+        CU(cudaMemsetAsync(c->keys2.p, 0, n_words * 4, c->stream));
+        twice = c->keys2.as<uint32_t>();
+    }
+    if (n_codes) {
+        set_mark_kernel<<<(uint32_t)((n_codes + 255) / 256), 256, 0, c->stream>>>(combco_dev, n_codes, c->keys.as<uint32_t>(), twice);
+        LAUNCHED(1);
+    }
+    const int rc = set_emit(c, c->keys.as<uint32_t>(), twice, n_words, pan_dev, pan_cap, n_out);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return KSSD_OK;
+}
+
+extern "C" int kssd_set_union_host(kssd_ctx_t *c, const uint32_t *combco, uint64_t n_codes, int uniq, uint32_t *pan_out, uint64_t *n_out)
+{
+    if (!c || !n_out || (n_codes && (!combco || !pan_out))) return fail(KSSD_E_INVAL, "kssd_set_union_host: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(c->seq.ensure(std::max<uint64_t>(n_codes, 1) * 8));
+    uint32_t *d_in = c->seq.as<uint32_t>(), *d_out = d_in + n_codes;
+    if (n_codes) CU(cudaMemcpyAsync(d_in, combco, n_codes * 4, cudaMemcpyHostToDevice, c->stream));
+    const int rc = kssd_set_union_dev(c, d_in, n_codes, uniq, d_out, n_codes, n_out);
+    if (rc) return rc;
+    if (*n_out) CU(cudaMemcpyAsync(pan_out, d_out, *n_out * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+extern "C" int kssd_set_operate_dev(kssd_ctx_t *c, const uint32_t *combco_dev, const uint64_t *index_dev, int n_genomes, uint64_t n_codes,
+                                    const uint32_t *pan_dev, uint64_t n_pan, int intersect, uint32_t *combco_out_dev, uint64_t *index_out_dev)
+{
+    if (!c || !index_dev || !index_out_dev || n_genomes < 0 || (n_codes && (!combco_dev || !combco_out_dev)) || (n_pan && !pan_dev))
+        return fail(KSSD_E_INVAL, "kssd_set_operate_dev: bad argument");
+    if (n_codes >= 0xffffffffull) return fail(KSSD_E_INVAL, "kssd_set_operate_dev: more than 2^32 codes in one component");
+    CU(cudaSetDevice(c->device));
+    uint64_t n_words;
+    set_code_words(c, &n_words);
+    CU(c->keys.ensure(n_words * 4));
+    CU(cudaMemsetAsync(c->keys.p, 0, n_words * 4, c->stream));
+    if (n_pan) set_mark_kernel<<<(uint32_t)((n_pan + 255) / 256), 256, 0, c->stream>>>(pan_dev, n_pan, c->keys.as<uint32_t>(), nullptr);
+    const uint64_t nn = std::max<uint64_t>(n_codes, 1);
+    CU(c->flags.ensure(nn * 4));
+    CU(c->pos.ensure(nn * 4));
+    if (n_codes) {
+        const uint32_t nb = (uint32_t)((n_codes + 255) / 256);
+        set_flag_kernel<<<nb, 256, 0, c->stream>>>(combco_dev, n_codes, c->keys.as<uint32_t>(), intersect ? 1 : 0, c->flags.as<uint32_t>());
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_codes, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_codes, c->stream));
+        set_scatter_kernel<<<nb, 256, 0, c->stream>>>(combco_dev, n_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), combco_out_dev);
+    }
+    set_index_kernel<<<(n_genomes + 1 + 255) / 256, 256, 0, c->stream>>>(index_dev, n_genomes, n_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(),
+                                                                        index_out_dev);
+    LAUNCHED(6);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return KSSD_OK;
+}
+
+extern "C" int kssd_set_operate_host(kssd_ctx_t *c, const uint32_t *combco, const uint64_t *index, int n_genomes, const uint32_t *pan, uint64_t n_pan,
+                                     int intersect, uint32_t *combco_out, uint64_t *index_out)
+{
+    if (!c || !index || !index_out || n_genomes < 0) return fail(KSSD_E_INVAL, "kssd_set_operate_host: bad argument");
+    const uint64_t n = index[n_genomes];
+    if ((n && (!combco || !combco_out)) || (n_pan && !pan)) return fail(KSSD_E_INVAL, "kssd_set_operate_host: null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t ib = 8ull * (n_genomes + 1);
+    CU(c->seq.ensure(2 * ib + (2 * n + n_pan) * 4 + 64));
+    uint64_t *d_ix = c->seq.as<uint64_t>(), *d_ox = d_ix + n_genomes + 1;
+    uint32_t *d_in = reinterpret_cast<uint32_t *>(d_ox + n_genomes + 1), *d_out = d_in + n, *d_pan = d_out + n;
+    CU(cudaMemcpyAsync(d_ix, index, ib, cudaMemcpyHostToDevice, c->stream));
+    if (n) CU(cudaMemcpyAsync(d_in, combco, n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n_pan) CU(cudaMemcpyAsync(d_pan, pan, n_pan * 4, cudaMemcpyHostToDevice, c->stream));
+    const int rc = kssd_set_operate_dev(c, d_in, d_ix, n_genomes, n, d_pan, n_pan, intersect, d_out, d_ox);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(index_out, d_ox, ib, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t kept = index_out[n_genomes];
+    if (kept) CU(cudaMemcpyAsync(combco_out, d_out, kept * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}

@@ -247,6 +247,27 @@ class Context:
         finally:
             lib().kssd_sketch_free(h)
 
+    # ---------------- kssd set ----------------
+    def set_union(self, combco: np.ndarray, uniq: bool = False) -> np.ndarray:
+        """`kssd set -u` / `-q` for one component (sketch_union / uniq_sketch_union): pan.<c> / uniq_pan.<c>."""
+        a = np.ascontiguousarray(combco, dtype=np.uint32)
+        out = np.empty(max(a.size, 1), dtype=np.uint32)
+        n = C.c_uint64(0)
+        check(lib().kssd_set_union_host(self._h, ptr(a, C.c_uint32), a.size, int(uniq), ptr(out, C.c_uint32), C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_operate(self, combco: np.ndarray, index: np.ndarray, pan: np.ndarray, intersect: bool):
+        """`kssd set -i <pan>` (intersect=True) / `-s <pan>` for one component (sketch_operate): the filtered
+        (combco.<c>, combco.index.<c>)."""
+        a = np.ascontiguousarray(combco, dtype=np.uint32)
+        ix = np.ascontiguousarray(index, dtype=np.uint64)
+        pn = np.ascontiguousarray(pan, dtype=np.uint32)
+        out = np.empty(max(a.size, 1), dtype=np.uint32)
+        oix = np.empty(ix.size, dtype=np.uint64)
+        check(lib().kssd_set_operate_host(self._h, ptr(a, C.c_uint32), ptr(ix, C.c_uint64), ix.size - 1, ptr(pn, C.c_uint32), pn.size,
+                                          int(intersect), ptr(out, C.c_uint32), ptr(oix, C.c_uint64)))
+        return out[:int(oix[-1])].copy(), oix
+
     # ---------------- Stage II ----------------
     def combco2mco(self, combco: np.ndarray, cbdcoindex: np.ndarray) -> "Index":
         combco = np.ascontiguousarray(combco, dtype=np.uint32)

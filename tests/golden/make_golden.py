@@ -167,3 +167,58 @@ def byread_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "byread":
     byread_golden()
+
+
+def set_golden():
+    """`kssd set` on a Stage-I directory: -u (pan), -q (uniq_pan), -i / -s <pan> (filters), L3K10 and L3K11 (16 components)."""
+    O.build()
+    t6 = synth.make_shuf_table(6, cases.SHUF_SEED_S6)
+    fa = cases.fasta_inputs()
+    for tag, (k, s, L) in {"set_l3k10": (10, 6, 3), "set_l3k11": (11, 6, 3)}.items():
+        rr = O.RefRun(k, s, L, t6, shuf_id=cases.SHUF_ID)
+        d = rr.dir / "in"
+        d.mkdir()
+        for n in ("g_dup", "h_anc", "i_mut1", "j_mut5", "a_plain80"):
+            (d / f"{n}.fasta").write_bytes(fa[n].tobytes())
+        sk = rr.sketch(d, "sk", p=1)
+        # the pan sketch is built from a SUBSET (another directory), so that intersect / subtract are both non-trivial
+        d2 = rr.dir / "in2"
+        d2.mkdir()
+        for n in ("h_anc", "g_dup"):
+            (d2 / f"{n}.fasta").write_bytes(fa[n].tobytes())
+        sk2 = rr.sketch(d2, "sk2", p=1)
+        st = O.read_cofiles_stat(sk)
+        comp = st["comp_num"]
+        pack = {"comp_num": np.int32(comp), "names": np.array([Path(n).name.rsplit(".", 1)[0] for n in st["names"]])}
+        for c in range(comp):
+            codes, ix, _ = O.read_combco(sk, c)
+            pack[f"in.{c}"] = codes
+            pack[f"in.index.{c}"] = ix
+            c2, _, _ = O.read_combco(sk2, c)
+            pack[f"in2.{c}"] = c2
+        runs = {"u": (["-u"], sk2, "pan"), "q": (["-q"], sk, "uniq_pan")}
+        for key, (flags, src, prefix) in runs.items():
+            out = rr.dir / f"set_{key}"
+            r = O.run_ref(["set", *flags, "-o", out, src], cwd=rr.dir)
+            assert r.returncode == 0, r.stderr
+            for c in range(comp):
+                pack[f"{key}.{c}"] = np.fromfile(out / f"{prefix}.{c}", dtype="<u4")
+        for key, flag in {"i": "-i", "s": "-s"}.items():
+            out = rr.dir / f"set_{key}"
+            r = O.run_ref(["set", flag, rr.dir / "set_u", "-o", out, sk], cwd=rr.dir)
+            assert r.returncode == 0, r.stderr
+            for c in range(comp):
+                pack[f"{key}.{c}"] = np.fromfile(out / f"combco.{c}", dtype="<u4")
+                pack[f"{key}.index.{c}"] = np.fromfile(out / f"combco.index.{c}", dtype="<u8")
+            pack[f"{key}.ctx_ct"] = O.read_cofiles_stat(out)["ctx_ct"]
+            pack[f"{key}.all_ctx_ct"] = np.uint64(O.read_cofiles_stat(out)["all_ctx_ct"])
+        pack["in.all_ctx_ct"] = np.uint64(st["all_ctx_ct"])
+        np.savez_compressed(OUT / f"{tag}.npz", **pack)
+        print(tag, "components", comp, "input codes", sum(len(pack[f'in.{c}']) for c in range(comp)),
+              "pan", sum(len(pack[f'u.{c}']) for c in range(comp)), "uniq", sum(len(pack[f'q.{c}']) for c in range(comp)),
+              "intersect", sum(len(pack[f'i.{c}']) for c in range(comp)), "subtract", sum(len(pack[f's.{c}']) for c in range(comp)))
+        rr.cleanup()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "set":
+    set_golden()

@@ -61,6 +61,26 @@ def test_byread_byte_identical_to_reference(oracle_mod, tables, tag, k, s, L):
             assert len(out[c][1]) == n_reads + 1
 
 
+@pytest.mark.parametrize("tag", ["set_l3k10", "set_l3k11"])
+def test_set_operations_identical_to_reference(oracle_mod, tag):
+    """kssd set -u / -q / -i / -s: pan, uniq_pan and the filtered combco + index + per-genome counts, per component."""
+    g = _load(tag)
+    comp = int(g["comp_num"])
+    n = len(g["names"])
+    ct_i, ct_s = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    for c in range(comp):
+        pan = oracle_mod.set_union(g[f"in2.{c}"])
+        assert np.array_equal(pan, g[f"u.{c}"])
+        assert np.array_equal(oracle_mod.set_union(g[f"in.{c}"], uniq=True), g[f"q.{c}"])
+        for key, inter, ct in (("i", True, ct_i), ("s", False, ct_s)):
+            codes, ix = oracle_mod.set_operate(g[f"in.{c}"], g[f"in.index.{c}"], pan, inter)
+            assert np.array_equal(codes, g[f"{key}.{c}"]) and np.array_equal(ix, g[f"{key}.index.{c}"])
+            ct += np.diff(ix).astype(np.uint32)
+    assert np.array_equal(ct_i, g["i.ctx_ct"]) and np.array_equal(ct_s, g["s.ctx_ct"])
+    # the reference leaves all_ctx_ct in the header stale (command_set.c:314-315, 365-367)
+    assert int(g["i.all_ctx_ct"]) == int(g["in.all_ctx_ct"]) == int(g["s.all_ctx_ct"])
+
+
 def test_fastq_abundance_identical_to_reference(oracle_mod, tables):
     g = _load("fastq_abund_l2k8")
     fq = cases.fastq_inputs()
