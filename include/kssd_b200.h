@@ -137,6 +137,9 @@ void kssd_sketch_free(kssd_sketch_t *s);
 typedef struct kssd_stage1 kssd_stage1_t;
 int kssd_stage1_files(kssd_ctx_t *ctx, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts,
                       int n_threads, size_t batch_bytes, kssd_stage1_t **out);
+/* same with the reference's -P <cmd> (iseq2comem.c:195-199): every file is read from the stdout of "<cmd> <file>" */
+int kssd_stage1_files_ex(kssd_ctx_t *ctx, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts,
+                         int n_threads, size_t batch_bytes, const char *pipecmd, kssd_stage1_t **out);
 int64_t kssd_stage1_count(const kssd_stage1_t *s, int comp);
 int kssd_stage1_fetch(const kssd_stage1_t *s, int comp, uint32_t *ids, uint64_t *index /* n_files+1 */, uint16_t *abund);
 int kssd_stage1_status(const kssd_stage1_t *s, int32_t *status_out /* n_files */);

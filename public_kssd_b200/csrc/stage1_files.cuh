@@ -123,6 +123,33 @@ static bool read_plain(const char *path, uint8_t *dst, uint64_t size)
     return got == size;
 }
 
+// `-P <cmd>` of the reference (popen("<cmd> <file>"), iseq2comem.c:195-199): the command's stdout is the file content
+static bool pipe_file(const char *cmd, const char *path, uint8_t **out, uint64_t *size)
+{
+    std::string line = std::string(cmd) + " " + path;
+    FILE *fp = popen(line.c_str(), "r");
+    if (!fp) return false;
+    uint64_t cap = 1ull << 24, n = 0;
+    uint8_t *buf = (uint8_t *)malloc(cap);
+    if (!buf) { pclose(fp); return false; }
+    for (;;) {
+        if (cap - n < (1u << 20)) {
+            cap *= 2;
+            uint8_t *nb = (uint8_t *)realloc(buf, cap);
+            if (!nb) { free(buf); pclose(fp); return false; }
+            buf = nb;
+        }
+        const size_t r = fread(buf + n, 1, cap - n, fp);
+        if (r == 0) break;
+        n += r;
+    }
+    const int st = pclose(fp);
+    if (st != 0) { free(buf); return false; }
+    *out = buf;
+    *size = n;
+    return true;
+}
+
 static bool inflate_file(const char *path, uint8_t **out, uint64_t *size)
 {
     gzFile g = gzopen(path, "rb");
@@ -151,8 +178,17 @@ static bool inflate_file(const char *path, uint8_t **out, uint64_t *size)
 
 }  // namespace stage1
 
+extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts, int n_threads,
+                                    size_t batch_bytes, const char *pipecmd, kssd_stage1_t **out);
+
 extern "C" int kssd_stage1_files(kssd_ctx_t *c, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts, int n_threads,
                                  size_t batch_bytes, kssd_stage1_t **out)
+{
+    return kssd_stage1_files_ex(c, paths, n_files, opts, n_threads, batch_bytes, nullptr, out);
+}
+
+extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts, int n_threads,
+                                    size_t batch_bytes, const char *pipecmd, kssd_stage1_t **out)
 {
     using namespace stage1;
     if (!c || !paths || !out || n_files <= 0) return fail(KSSD_E_INVAL, "kssd_stage1_files: bad argument");
@@ -169,7 +205,7 @@ extern "C" int kssd_stage1_files(kssd_ctx_t *c, const char *const *paths, int n_
         tasks[i].file = i;
         struct stat st;
         if (!paths[i] || stat(paths[i], &st) != 0) return fail(KSSD_E_INVAL, "kssd_stage1_files: cannot stat %s", paths[i] ? paths[i] : "(null)");
-        tasks[i].gz = has_gz_magic(paths[i]);
+        tasks[i].gz = (pipecmd && pipecmd[0]) || has_gz_magic(paths[i]);     // "gz" = size unknown until decoded
         if (!tasks[i].gz) { tasks[i].size = (uint64_t)st.st_size; biggest_plain = std::max(biggest_plain, tasks[i].size); }
     }
     // two pinned staging buffers, kept in the context between calls (pinning a GiB costs about as much as reading it);
@@ -280,7 +316,7 @@ extern "C" int kssd_stage1_files(kssd_ctx_t *c, const char *const *paths, int n_
                     const auto t0 = clk::now();
                     uint8_t *buf = nullptr;
                     uint64_t sz = 0;
-                    const bool ok = inflate_file(paths[i], &buf, &sz);
+                    const bool ok = (pipecmd && pipecmd[0]) ? pipe_file(pipecmd, paths[i], &buf, &sz) : inflate_file(paths[i], &buf, &sz);
                     std::lock_guard<std::mutex> l(m);
                     tasks[i].priv = buf; tasks[i].size = sz; tasks[i].failed = !ok; tasks[i].decoded = true;
                     inflight_priv += sz;

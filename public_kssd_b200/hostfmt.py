@@ -33,6 +33,11 @@ def slot_order(ids: np.ndarray, first_occurrence: np.ndarray, hashsize: int, key
     return np.array([table[s] for s in sorted(table)], dtype=np.uint32)
 
 
+def read_list_file(path) -> list:
+    """The reference's `-l <list>`: one input path per line (command_dist.c organize step); blank lines ignored."""
+    return [ln.strip() for ln in Path(path).read_text().splitlines() if ln.strip()]
+
+
 def _names_block(names) -> bytes:
     out = []
     for nm in names:

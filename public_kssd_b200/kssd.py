@@ -190,14 +190,16 @@ class Context:
         return sk
 
     def sketch_files(self, paths: Sequence[str], mode: int = capi.MODE_FASTA, Q: int = 0, M: int = 1, threads: int = 0,
-                     batch_bytes: int = 0, strict: bool = True):
+                     batch_bytes: int = 0, strict: bool = True, pipecmd: str | None = None):
         """Stage I from files (run_stageI's file loop + the zcat decode): plain or .gz FASTA / FASTQ files, read and
         inflated by host threads into pinned staging buffers and sketched batch by batch (kssd_stage1_files).
+        pipecmd: the reference's -P <cmd> -- every file is read from the stdout of "<cmd> <file>".
         Returns (Sketch over all files in input order, timing dict)."""
         arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
         opts = capi.SketchOpts(mode, Q, M, 0, 0, 0)
         h = C.c_void_p()
-        check(lib().kssd_stage1_files(self._h, arr, len(paths), C.byref(opts), threads, batch_bytes, C.byref(h)))
+        check(lib().kssd_stage1_files_ex(self._h, arr, len(paths), C.byref(opts), threads, batch_bytes,
+                                         pipecmd.encode() if pipecmd else None, C.byref(h)))
         try:
             ids, index, abund = [], [], []
             for c in range(self.component_num):

@@ -20,7 +20,7 @@ def _write(tmp, files, gz_every=2):
     paths = []
     for i, (name, data) in enumerate(sorted(files.items())):
         raw = data.tobytes()
-        if gz_every and i % gz_every == 1:
+        if gz_every and i % gz_every == gz_every - 1:
             p = tmp / f"{name}.fa.gz"
             with gzip.open(p, "wb", compresslevel=1) as f:
                 f.write(raw)
@@ -72,3 +72,22 @@ def test_files_errors(gpu_ctx_l3k10, tmp_path):
         gpu_ctx_l3k10.sketch_files([bad])                                    # the reference exits on this file too
     sk, _ = gpu_ctx_l3k10.sketch_files([bad], strict=False)
     assert sk.status[0] == capi.E_HEADER_EOF
+
+
+def test_files_through_pipe_command_and_list_file(gpu_ctx_l3k10, tmp_path):
+    """-P <cmd>: the files are read from the stdout of "<cmd> <file>" (here xz-like: `gzip -dc`); -l list file."""
+    from public_kssd_b200 import hostfmt
+    files = {n: v for n, v in cases.fasta_inputs().items() if n in ("a_plain80", "d_messy", "f_short_lines")}
+    paths = _write(tmp_path, files, gz_every=1)           # every file compressed
+    paths = [p if p.suffix == ".gz" else p for p in paths]
+    gz_only = [p for p in paths if p.suffix == ".gz"]
+    lst = tmp_path / "inputs.list"
+    lst.write_text("\n".join(str(p) for p in gz_only) + "\n\n")
+    listed = hostfmt.read_list_file(lst)
+    assert listed == [str(p) for p in gz_only]
+    sk, _ = gpu_ctx_l3k10.sketch_files(listed, pipecmd="gzip -dc", threads=2)
+    want, _ = gpu_ctx_l3k10.sketch_files(listed)
+    assert np.array_equal(sk.ids[0], want.ids[0]) and np.array_equal(sk.index[0], want.index[0]) and len(sk.ids[0]) > 0
+    from public_kssd_b200 import kssd
+    with pytest.raises(kssd.KssdError):
+        gpu_ctx_l3k10.sketch_files(listed, pipecmd="false")
