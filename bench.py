@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--genomes", type=int, default=1000)
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dist-scale", action="store_true", help="skip the 10,000 x 100,000 Stage III measurement (N = 1 only)")
     ap.add_argument("--ref-sample", type=int, default=0, help="genomes in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -427,6 +428,41 @@ def main():
     roof = {"bound": "hbm", "achieved": text_bytes / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": text_bytes / (scan * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "kernel": "sketch_fasta32_kernel", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
+
+    # (after the end-to-end leg: the host-side generation below must not disturb where its pinned buffer lives)
+    if world == 1 and not args.no_dist_scale and args.genomes >= 1000:
+        # the second headline metric at BASELINE.json configs[2] size: 100,000 reference sketches x ~1,220 codes (cluster /
+        # mutation model of SURVEY.md s8d), 10,000 queries, 10^9 pairs; skip_zero listing (the cells a search prints)
+        try:
+            rc, ri = synth.synth_sketches(100_000, 1220, seed=5, cluster_size=20)
+            qc, qi = synth.synth_sketches(10_000, 1220, seed=5, cluster_size=2)
+            ixb = ctx.combco2mco(rc, ri)
+            tq = torch.from_numpy(qc.view(np.int32)).to(dev)
+            ti = torch.from_numpy(qi.view(np.int64)).to(dev)
+            qs_, rs_ = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+            best = {}
+            for sparse in (False, True):
+                for it in range(3):
+                    jb = kssd.DistJob(ctx, qs_, rs_, sparse=sparse)
+                    jb.accumulate_dev(ixb, tq.data_ptr(), ti.data_ptr(), len(qc))
+                    c_ms = 0.0 if sparse else ctx.last_ms(3)
+                    nr = jb.stats(skip_zero=1, fetch=False)
+                    tot = c_ms + ctx.last_ms(4) + (ctx.last_ms(3) if sparse else 0.0)
+                    if sparse not in best or tot < best[sparse][0]:
+                        best[sparse] = (tot, c_ms if not sparse else ctx.last_ms(3), int(nr))
+                    jb.close()
+            ixb.close()
+            big_pairs = 10_000 * 100_000
+            dist_info["configs2_scale"] = {
+                "pairs": big_pairs, "ref_postings": int(len(rc)), "query_codes": int(len(qc)), "printed_rows": best[True][2],
+                "dense_job_ms": best[False][0], "dense_count_ms": best[False][1], "sparse_job_ms": best[True][0],
+                "pairs_per_s": big_pairs / (best[True][0] * 1e-3), "pairs_per_s_dense": big_pairs / (best[False][0] * 1e-3),
+                "rows_agree": best[True][2] == best[False][2],
+                "note": "device time (CUDA events in the library), sketches synthetic and resident; sparse job = no Q x R matrix "
+                        "(kssd_dist_create_sparse), dense job = count matrix + listing + statistics"}
+            del tq, ti
+        except Exception as ex:  # must not take the headline measurement down
+            dist_info["configs2_scale"] = {"failed": str(ex)}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
