@@ -135,7 +135,9 @@ class ShardedDist:
                   mappings (CUDA IPC over NVLink): compute and reduction are one kernel, only the non-zero increments
                   cross the links, no partial matrix and no NCCL collective on the data path.
     mode "genome" (zero-communication alternative): rank r indexes the reference genomes of its
-                  block; its Q x R/world count columns are final as they are -- no reduction at all."""
+                  block; its Q x R/world count columns are final as they are -- no reduction at all.  When the counts are
+                  not fetched the rank runs a SPARSE job (no Q x R/world matrix; kssd_dist_create_sparse) -- it falls
+                  back to the matrix by itself if the options print zero-shared cells."""
 
     def __init__(self, ctx, world: int, rank: int, code_bits: int = 28, mode: str = "code"):
         assert mode in ("code", "code_p2p", "genome")
@@ -260,7 +262,7 @@ class ShardedDist:
             lo, hi = self.col_lo, self.col_hi
             if hi <= lo:
                 return lo, hi, np.zeros((nq, 0), dtype=np.uint32), None
-            job = kssd.DistJob(self.ctx, qsizes, self.ref_sizes[lo:hi])
+            job = kssd.DistJob(self.ctx, qsizes, self.ref_sizes[lo:hi], sparse=(stats_opts is not None and not fetch_counts))
             torch.cuda.synchronize()
             job.accumulate_dev(self.index, tq.data_ptr(), ti.data_ptr(), nc)
             rows = None
