@@ -486,20 +486,32 @@ constexpr uint32_t kSparseEmpty = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t sparse_hash(uint32_t g) { return (g * 0x9E3779B1u) >> 19; }   // 13 bits
 
-__device__ __forceinline__ void sparse_insert(uint32_t *keys, uint32_t *vals, uint32_t *bitmap, uint32_t *distinct, uint32_t g)
+// PACKED: one 32-bit word per slot, gid in the high bits and the count in the low `cb` bits (the host picks it when
+// R and the largest query sketch leave room) -- the table is 32 KiB instead of 64 and a third CTA fits on the SM.
+template <bool PACKED>
+__device__ __forceinline__ void sparse_insert(uint32_t *keys, uint32_t *vals, uint32_t cb, uint32_t *bitmap, uint32_t *distinct, uint32_t g)
 {
     uint32_t h = sparse_hash(g);
     for (uint32_t probes = 0; probes < kSparseSlots; probes++) {
         // a ref shared with the query is hit once per shared code: most inserts find their key already there
-        if (*reinterpret_cast<volatile uint32_t *>(&keys[h]) == g) { atomicAdd(&vals[h], 1u); return; }
-        const uint32_t old = atomicCAS(&keys[h], kSparseEmpty, g);
+        const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&keys[h]);
+        if (PACKED) {
+            if ((cur >> cb) == g) { atomicAdd(&keys[h], 1u); return; }          // (the empty pattern never decodes to a gid)
+        } else {
+            if (cur == g) { atomicAdd(&vals[h], 1u); return; }
+        }
+        const uint32_t old = atomicCAS(&keys[h], kSparseEmpty, PACKED ? ((g << cb) | 1u) : g);
         if (old == kSparseEmpty) {
             atomicAdd(distinct, 1u);
             atomicOr(&bitmap[g >> 5], 1u << (g & 31));
-            atomicAdd(&vals[h], 1u);
+            if (!PACKED) atomicAdd(&vals[h], 1u);
             return;
         }
-        if (old == g) { atomicAdd(&vals[h], 1u); return; }
+        if (PACKED) {
+            if ((old >> cb) == g) { atomicAdd(&keys[h], 1u); return; }
+        } else {
+            if (old == g) { atomicAdd(&vals[h], 1u); return; }
+        }
         h = (h + 1) & (kSparseSlots - 1);
     }
     atomicAdd(distinct, kSparseSlots);                        // table full: poison the tally, the query goes dense
@@ -634,29 +646,33 @@ __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__
     }
 }
 
-template <bool TRIVIAL>
-__global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const SparseComp *__restrict__ comps, int n_comp, uint32_t n_qry, uint32_t n_ref,
+template <bool TRIVIAL, bool PACKED>
+__global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const SparseComp *__restrict__ comps, int n_comp, uint32_t n_qry, uint32_t n_ref, uint32_t cb,
                                                                      const StatParams S, const uint32_t *__restrict__ qsz,
                                                                      const uint32_t *__restrict__ rsz, uint32_t *__restrict__ q_cnt,
                                                                      unsigned long long *__restrict__ q_pos, unsigned long long *__restrict__ cursor,
                                                                      uint64_t cap, SparseHit *__restrict__ hits, int *__restrict__ overflow)
 {
     extern __shared__ __align__(16) uint32_t sparse_sm[];
-    uint32_t *keys = sparse_sm, *vals = keys + kSparseSlots, *lstart = vals + kSparseSlots, *lpre = lstart + kSparseTile,
-             *bitmap = lpre + kSparseTile + 1;
+    uint32_t *keys = sparse_sm, *vals = keys + kSparseSlots, *lstart = vals + (PACKED ? 0 : kSparseSlots), *lpre = lstart + kSparseTile,
+             *bitmap = lpre + kSparseTile + 1;                  // PACKED: no vals array, the descriptors start right after the keys
+    const uint32_t cmask = PACKED ? ((1u << cb) - 1u) : 0u;
     __shared__ uint32_t distinct, tbase[kSparseThreads];
     __shared__ uint2 wsum[kSparseThreads / 32];
     __shared__ unsigned long long base_s;
     const uint32_t bw = (n_ref + 31) / 32;
     for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < kSparseSlots; i += kSparseThreads) { keys[i] = kSparseEmpty; vals[i] = 0; }
+        for (uint32_t i = threadIdx.x; i < kSparseSlots; i += kSparseThreads) {
+            keys[i] = kSparseEmpty;
+            if (!PACKED) vals[i] = 0;
+        }
         for (uint32_t i = threadIdx.x; i < bw; i += kSparseThreads) bitmap[i] = 0;
         if (threadIdx.x == 0) distinct = 0;
         // ---- walk (walk_query_postings): every gid of every posting list of the query's codes goes into the table
         for (int cc = 0; cc < n_comp; cc++) {
             const SparseComp C = comps[cc];
             walk_query_postings(C.qcodes, C.qindex, C.dense, C.mco, q, lstart, lpre, wsum,
-                                [&](uint32_t g) { sparse_insert(keys, vals, bitmap, &distinct, g); });
+                                [&](uint32_t g) { sparse_insert<PACKED>(keys, vals, cb, bitmap, &distinct, g); });
         }
         __syncthreads();
         if (distinct > kSparseMaxDistinct) {                 // uniform: every thread reads the same shared word
@@ -670,8 +686,9 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         constexpr uint32_t kSlotsPer = kSparseSlots / kSparseThreads;
         if (!TRIVIAL) {                                       // output_ctrl's keep rule, applied per touched cell
             for (uint32_t i = 0; i < kSlotsPer; i++) {
-                const uint32_t sidx = threadIdx.x + i * kSparseThreads, r = keys[sidx];
-                if (r != kSparseEmpty && !stat_keep(S, rsz[r], Y, vals[sidx])) {
+                const uint32_t sidx = threadIdx.x + i * kSparseThreads, e = keys[sidx];
+                const uint32_t r = PACKED ? e >> cb : e, cnt_r = PACKED ? e & cmask : vals[sidx];
+                if (e != kSparseEmpty && !stat_keep(S, rsz[r], Y, cnt_r)) {
                     atomicAnd(&bitmap[r >> 5], ~(1u << (r & 31)));
                     keys[sidx] = kSparseEmpty;
                 }
@@ -696,13 +713,14 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         const unsigned long long base = base_s;
         if (total && base + total <= cap) {
             for (uint32_t i = 0; i < kSlotsPer; i++) {
-                const uint32_t sidx = threadIdx.x + i * kSparseThreads, r = keys[sidx];
-                if (r == kSparseEmpty) continue;
+                const uint32_t sidx = threadIdx.x + i * kSparseThreads, e = keys[sidx];
+                if (e == kSparseEmpty) continue;
+                const uint32_t r = PACKED ? e >> cb : e;
                 const uint32_t w = r >> 5, owner = w >> per_log;
                 uint32_t rank = tbase[owner] + __popc(bitmap[w] & ((1u << (r & 31)) - 1u));
                 for (uint32_t x = owner << per_log; x < w; x++) rank += __popc(bitmap[x]);
                 SparseHit h;
-                h.q = q; h.r = r; h.shared = vals[sidx];
+                h.q = q; h.r = r; h.shared = PACKED ? e & cmask : vals[sidx];
                 hits[base + rank] = h;
             }
         }

@@ -1280,7 +1280,12 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         const bool nan_cells = o->metric == 0 ? (d->empty_qry && d->empty_ref) : (d->empty_qry || d->empty_ref);
         const bool no_zero_rows = o->n_neighbors == 0 && (o->skip_zero || (o->dthreshold < 1.0 && !o->correction && !nan_cells));
         const uint32_t bw = ((uint32_t)d->n_ref + 31) / 32;
-        const size_t smem = (2ull * kSparseSlots + 2ull * kSparseTile + 1 + bw) * 4;
+        // packed table (gid | count in one word) when the ref ids and the largest possible count leave room in 32 bits
+        uint32_t gbits = 1;
+        while ((1ull << gbits) - 1 < (uint64_t)d->n_ref) gbits++;                // n_ref <= 2^gbits - 1: no gid is all ones
+        const uint32_t cb = 32 - gbits;
+        const bool packed = gbits <= 24 && (uint64_t)d->max_qry_size + 1 < (1ull << cb) - 1 && !getenv("KSSD_SPARSE_UNPACKED");   // env: A/B and tests
+        const size_t smem = ((packed ? 1ull : 2ull) * kSparseSlots + 2ull * kSparseTile + 1 + bw) * 4;
         if (no_zero_rows && smem <= 200u * 1024u) {
             const bool trivial = S.dthreshold >= 1.0;
             const int nc = (int)d->comps.size();
@@ -1291,9 +1296,11 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
             CU(c->misc.ensure(16 + sizeof(SparseComp) * 256));
             uint8_t *mb = c->misc.as<uint8_t>();
             if (nc) CU(cudaMemcpyAsync(mb + 16, d->comps.data(), sizeof(SparseComp) * nc, cudaMemcpyHostToDevice, c->stream));
-            if (trivial) CU(cudaFuncSetAttribute(dist_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else CU(cudaFuncSetAttribute(dist_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int per_sm = smem + 1024 <= 100u * 1024u ? 2 : 1;
+            auto kern = trivial ? (packed ? dist_sparse_kernel<true, true> : dist_sparse_kernel<true, false>)
+                                : (packed ? dist_sparse_kernel<false, true> : dist_sparse_kernel<false, false>);
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // (the variant that evaluates the keep rule in place needs more registers: two CTAs per SM measured faster than three)
+            const int per_sm = std::max(1, std::min(trivial ? 3 : 2, (int)((227u * 1024u) / (smem + 3400))));
             const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
             uint64_t total = 0, cap = std::max<uint64_t>(1ull << 22, (uint64_t)d->n_qry * 1024);
             int over = 0;
@@ -1301,14 +1308,10 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
                 if (cap > 0xffffffffull) return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D");
                 CU(c->keys.ensure(cap * sizeof(SparseHit)));
                 CU(cudaMemsetAsync(mb, 0, 16, c->stream));
-                if (trivial)
-                    dist_sparse_kernel<true><<<grid, kSparseThreads, smem, c->stream>>>(
-                        reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, S, d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(),
-                        c->counts.as<unsigned long long>(), reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(), reinterpret_cast<int *>(mb + 8));
-                else
-                    dist_sparse_kernel<false><<<grid, kSparseThreads, smem, c->stream>>>(
-                        reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, S, d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(),
-                        c->counts.as<unsigned long long>(), reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(), reinterpret_cast<int *>(mb + 8));
+                kern<<<grid, kSparseThreads, smem, c->stream>>>(reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, cb, S,
+                                                                d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(), c->counts.as<unsigned long long>(),
+                                                                reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(),
+                                                                reinterpret_cast<int *>(mb + 8));
                 LAUNCHED(1);
                 CU(cudaEventRecord(c->ev[2], c->stream));
                 CU(cudaMemcpyAsync(&total, mb, 8, cudaMemcpyDeviceToHost, c->stream));

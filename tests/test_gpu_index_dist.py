@@ -184,6 +184,25 @@ def test_sparse_job_rows_identical_to_dense(gpu_ctx_l3k10, opts):
     dense.close(); sp.close(); ix.close()
 
 
+def test_sparse_job_unpacked_table(gpu_ctx_l3k10, monkeypatch):
+    """The two-array table (used when ref ids and counts do not fit one 32-bit word) gives the same rows as the packed one."""
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(900, 300, seed=9, cluster_size=30)
+    qc, qi = synth.synth_sketches(40, 300, seed=9, cluster_size=4)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    out = []
+    for unpacked in (False, True):
+        if unpacked:
+            monkeypatch.setenv("KSSD_SPARSE_UNPACKED", "1")
+        sp = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz, sparse=True)
+        sp.accumulate(ix, qc, qi)
+        out.append(sp.stats(dthreshold=0.2).tobytes() + sp.stats(skip_zero=1).tobytes())
+        sp.close()
+    assert out[0] == out[1] and len(out[0]) > 0
+    ix.close()
+
+
 def test_sparse_job_many_refs_per_query_falls_back(gpu_ctx_l3k10):
     """A query that touches more references than the shared-memory table holds sends the job through the matrix."""
     from public_kssd_b200 import kssd
