@@ -66,19 +66,20 @@ struct WarpQueue {
 
 // ---- byte classification, 4 bytes at a time (bit tricks checked exhaustively in tests/test_bittricks.py) ----
 //   dacc |= nonzero byte  <=>  that byte is NOT one of ACGTacgt, '\n', '\r'
-//   t3   : per byte, bits 0-1 = (b >> 1) & 3 (A0 C1 T2 G3), bit 2 = "bit 6 of b is clear" (a skip byte when clean)
+//   t3   : per byte, bits 0-1 = (b >> 1) & 3 (A0 C1 T2 G3), bit 2 = bit 3 of b -- clear in every letter, set in '\n' and
+//          '\r' (a skip byte when clean); the three bits are adjacent in b, so one AND of w >> 1 yields them and they
+//          index the eight-entry PRMT table of the bytes a clean byte must equal
 //   m    : top byte = the four 2-bit codes A0 C1 G2 T3, first byte in the top two bits
 __device__ __forceinline__ void classify4(uint32_t w, uint32_t &dacc, uint32_t &t3, uint32_t &m)
 {
-    const uint32_t s1 = (w >> 1);
-    const uint32_t t = s1 & 0x03030303u;
-    t3 = t | (~(w >> 4) & 0x04040404u);
+    const uint32_t s1 = w >> 1, s2 = w >> 2;
+    t3 = s1 & 0x07070707u;
     const uint32_t u = w & ~(s1 & 0x20202020u);                   // fold case of letters only
     const uint32_t a = t3 | (t3 >> 4);
     const uint32_t sel = prmt(a, 0u, 0x4420u);
     const uint32_t e = prmt(0x47544341u, 0xFF0D0AFFu, sel);        // A C T G | - \n \r -
     dacc |= u ^ e;
-    const uint32_t t2 = t ^ ((t >> 1) & 0x01010101u);
+    const uint32_t t2 = (s1 ^ s2) & 0x03030303u;                  // bit 0 = b1 ^ b2, bit 1 = b2 ^ b3 = b2 for letters
     m = t2 * 0x40100401u;
 }
 

@@ -19,13 +19,13 @@ def prmt(x, y, sel):
 def classify4(w):
     """mirror of classify4(): returns (diff, t3, m)"""
     s1 = w >> 1
-    t = s1 & 0x03030303
-    t3 = t | ((~(w >> 4)) & 0x04040404)
+    s2 = w >> 2
+    t3 = s1 & 0x07070707                      # bits 0-1 = (b >> 1) & 3, bit 2 = bit 3 of b (set for \n and \r only)
     u = w & ~(s1 & 0x20202020) & M32
     a = (t3 | (t3 >> 4)) & M32
     sel = prmt(a, 0, 0x4420) & 0xFFFF
     e = prmt(0x47544341, 0xFF0D0AFF, sel)
-    t2 = t ^ ((t >> 1) & 0x01010101)
+    t2 = (s1 ^ s2) & 0x03030303               # A0 C1 G2 T3 for letters (their bit 3 is clear)
     return u ^ e, t3, (t2 * 0x40100401) & M32
 
 
@@ -44,7 +44,7 @@ def test_classification_is_exact_for_every_byte_in_every_position():
                 if o != pos:
                     assert (diff >> (8 * o)) & 0xFF == 0
             if clean:
-                assert bool((t3 >> (8 * pos)) & 4) == (b in (10, 13))       # skip flag = bit 6 clear
+                assert bool((t3 >> (8 * pos)) & 4) == (b in (10, 13))       # skip flag = bit 3 of the byte
 
 
 def test_multiply_gather_packs_codes_oldest_first():
