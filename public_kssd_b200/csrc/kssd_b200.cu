@@ -214,7 +214,7 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.ht = c->d_ht;
 
     CU(cudaFuncSetAttribute(sketch_fasta32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)((kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue))));
+                            (int)kScanSmemBytes));
 
     kssd_ctx_info_t &I = c->info;
     I.k = k; I.subk = subk; I.drlevel = drlevel; I.component_sz = component_sz;
@@ -583,7 +583,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
             if (n_spans) {
-                sketch_fasta32_kernel<<<c->sm_count, kScanThreads, (kPfWords + kPf2Words) * 4 + kScanWarps * sizeof(WarpQueue), c->stream>>>(P, A);
+                sketch_fasta32_kernel<<<c->sm_count, kScanThreads, kScanSmemBytes, c->stream>>>(P, A);
                 LAUNCHED(1);
             }
         } else {

@@ -64,6 +64,14 @@ struct WarpQueue {
     uint32_t ord[kQueueCap];
 };
 
+// Lanes of a clean iteration whose first-level probe hit something park here -- their four base words, the hit mask and
+// their offset -- until 32 of them are waiting; the second-level probe and the hand-over to the exact queue then run
+// with every lane busy instead of once per iteration for the few lanes that hit.
+struct LaneQueue {
+    uint32_t w0[kQueueCap], w1[kQueueCap], w2[kQueueCap], w3[kQueueCap], cand[kQueueCap], off[kQueueCap];
+};
+constexpr size_t kScanSmemBytes = (size_t)(kPfWords + kPf2Words) * 4 + (size_t)kScanWarps * (sizeof(WarpQueue) + sizeof(LaneQueue));
+
 // ---- byte classification, 4 bytes at a time (bit tricks checked exhaustively in tests/test_bittricks.py) ----
 //   dacc |= nonzero byte  <=>  that byte is NOT one of ACGTacgt, '\n', '\r'
 //   t3   : per byte, bits 0-1 = (b >> 1) & 3 (A0 C1 T2 G3), bit 2 = bit 3 of b -- clear in every letter, set in '\n' and

@@ -47,7 +47,20 @@ __device__ __forceinline__ uint32_t low_mask(int bits)     // bits in [0, 32]
     return bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
 }
 
-__device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q,
+// second-level probe + hand-over of `m` parked lanes (entries first .. first+m-1), one per lane
+__device__ __forceinline__ void drain_lanes(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q, uint32_t &qn,
+                                            const LaneQueue &lq, uint32_t first, uint32_t m, uint32_t gid, uint64_t ord_base)
+{
+    const uint32_t lane = lane_id();
+    uint32_t c = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0, off = 0;
+    if (lane < m) {
+        const uint32_t i = first + lane;
+        c = lq.cand[i]; w0 = lq.w0[i]; w1 = lq.w1[i]; w2 = lq.w2[i]; w3 = lq.w3[i]; off = lq.off[i];
+    }
+    push_candidates(P, A, pf, q, qn, c, 32u, w0, w1, w2, w3, off, 0u, 32u, gid, ord_base);
+}
+
+__device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q, LaneQueue &lq,
                             uint32_t gid, uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
 {
     const uint32_t lane = lane_id();
@@ -55,7 +68,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
     // stream state in registers; it is packed into a StreamState only around the out-of-line general iterations
     uint64_t cw = 0;
     uint32_t since_break = 0, after_end = 0, hdr = 0;
-    uint32_t qn = 0;
+    uint32_t qn = 0, ln = 0;
     const uint64_t chunk0 = start & ~127ull;
     const uint64_t ord_base = chunk0 - gs;           // may wrap below zero; real occurrences add back past it
     // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
@@ -178,7 +191,20 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
             }
             since_break = min(since_break + N, kRunCap);
             cw = ((uint64_t)__shfl_sync(kFull, P1, 31) << 32) | __shfl_sync(kFull, P0, 31);
-            push_candidates(P, A, pf, q, qn, cand, n, W0, W1, W2, W3, lane_off, 0u, 32u, gid, ord_base);
+            const uint32_t hit = __ballot_sync(kFull, cand != 0);
+            if (hit) {
+                if (cand) {
+                    const uint32_t i = ln + __popc(hit & ((1u << lane) - 1u));
+                    lq.w0[i] = W0; lq.w1[i] = W1; lq.w2[i] = W2; lq.w3[i] = W3; lq.cand[i] = cand; lq.off[i] = lane_off;
+                }
+                ln += __popc(hit);
+                __syncwarp();
+                if (ln >= 32) {
+                    drain_lanes(P, A, pf, q, qn, lq, ln - 32, 32, gid, ord_base);
+                    ln -= 32;
+                    __syncwarp();
+                }
+            }
         } else {
             // two general 512-byte iterations with the 16-byte lane mapping (reloaded: L1/L2 hits)
             StreamState st = {cw, since_break, after_end, hdr};
@@ -208,6 +234,7 @@ __device__ void scan_span32(const SketchParams &P, const ScanArgs &A, const uint
             }
         }
     }
+    if (ln) { drain_lanes(P, A, pf, q, qn, lq, 0, ln, gid, ord_base); __syncwarp(); }
     if (qn) { resolve_candidates(P, A, q, 0, qn, gid, ord_base); __syncwarp(); }
     if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
 }
@@ -217,6 +244,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta32_kernel(const S
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
     WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + (kPfWords + kPf2Words) * 4);
+    LaneQueue *lqueues = reinterpret_cast<LaneQueue *>(queues + kScanWarps);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);
@@ -234,7 +262,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta32_kernel(const S
         const uint64_t gs = A.goff[gid], ge = gs + A.glen[gid];
         uint64_t start, end;
         if (!span_extent(A, si, gid, gs, ge, start, end)) continue;
-        scan_span32(P, A, pf, q, gid, gs, ge, start, end);
+        scan_span32(P, A, pf, q, lqueues[threadIdx.x >> 5], gid, gs, ge, start, end);
     }
 }
 
