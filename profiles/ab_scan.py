@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Kernel-only A/B harness: times sketch_fasta_kernel (CUDA events inside the library) on a resident batch.
+"""Kernel-only A/B harness: times sketch_fasta32_kernel (CUDA events inside the library) on a resident batch.
 usage: KSSD_B200_LIB=path/to/variant.so python profiles/ab_scan.py [genomes]"""
 import sys
 from pathlib import Path
