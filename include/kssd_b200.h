@@ -239,9 +239,10 @@ typedef struct kssd_stat_row {
  * are REGISTERED (the device pointers must stay valid until kssd_dist_stats returns; the host variant keeps its own
  * copy) and kssd_dist_stats counts, filters and lists in one kernel: shared counts live in a per-query shared-memory
  * hash table, work is proportional to the postings touched instead of Q x R.  Rows are identical to the dense job's.
- * If the options do print zero cells (-N, -D >= 1 without skip_zero, --correction, empty sketches whose cells are NaN),
- * a query touches more than 6144
- * references, or counts are fetched, the job falls back to the matrix transparently. */
+ * Queries that touch more than 6144 references do not fit the shared-memory table: they are counted through a small
+ * dense sub-job (n_over x R) and merged back in print order.  If the options do print zero cells (-N, -D >= 1 without
+ * skip_zero, --correction, empty sketches whose cells are NaN), most queries overflow, or counts are fetched, the whole
+ * job falls back to the matrix transparently. */
 int kssd_dist_create_sparse(kssd_ctx_t *ctx, int n_qry, int n_ref, const uint32_t *qry_ctx_ct,
                             const uint32_t *ref_ctx_ct, kssd_dist_t **out);
 int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev,

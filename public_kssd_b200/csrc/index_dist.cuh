@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
                                                                      const StatParams S, const uint32_t *__restrict__ qsz,
                                                                      const uint32_t *__restrict__ rsz, uint32_t *__restrict__ q_cnt,
                                                                      unsigned long long *__restrict__ q_pos, unsigned long long *__restrict__ cursor,
-                                                                     uint64_t cap, SparseHit *__restrict__ hits, int *__restrict__ overflow)
+                                                                     uint64_t cap, SparseHit *__restrict__ hits, uint32_t *__restrict__ over_n,
+                                                                     uint32_t *__restrict__ over_list)
 {
     extern __shared__ __align__(16) uint32_t sparse_sm[];
     uint32_t *keys = sparse_sm, *vals = keys + kSparseSlots, *lstart = vals + (PACKED ? 0 : kSparseSlots), *lpre = lstart + kSparseTile,
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         }
         __syncthreads();
         if (distinct > kSparseMaxDistinct) {                 // uniform: every thread reads the same shared word
-            if (threadIdx.x == 0) { atomicExch(overflow, 1); q_cnt[q] = 0; q_pos[q] = 0; }
+            if (threadIdx.x == 0) { over_list[atomicAdd(over_n, 1u)] = q; q_cnt[q] = 0; q_pos[q] = 0; }   // handled densely by the host
             __syncthreads();
             continue;
         }
@@ -726,6 +727,34 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         }
         __syncthreads();                                      // the table is cleared for the next query
     }
+}
+
+// ---- queries that overflowed the sparse table go through a small dense sub-job; these kernels move data in and out ----
+// codes of the listed queries, compacted: out[sub_index[i] ..] = qcodes[qindex[list[i]] ..]
+__global__ void gather_query_codes_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex, const uint32_t *__restrict__ list,
+                                          const uint64_t *__restrict__ sub_index, uint32_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x;
+    const uint64_t a = qindex[list[i]], n = qindex[list[i] + 1] - a, o = sub_index[i];
+    for (uint64_t j = threadIdx.x; j < n; j += blockDim.x) out[o + j] = qcodes[a + j];
+}
+
+__global__ void count_rows_by_query_kernel(const StatRow *__restrict__ rows, uint64_t n, uint32_t *__restrict__ cnt)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) atomicAdd(&cnt[rows[j].qry], 1u);
+}
+
+// rows of the sub-job (query-major, local query numbers) -> their place in the print order of the whole job
+__global__ void place_sub_rows_kernel(const StatRow *__restrict__ sub_rows, uint64_t n, const uint32_t *__restrict__ list,
+                                      const uint64_t *__restrict__ first, const uint64_t *__restrict__ q_out, StatRow *__restrict__ rows)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    StatRow r = sub_rows[j];
+    const uint32_t lq = r.qry, q = list[lq];
+    r.qry = q;
+    rows[q_out[q] + (j - first[lq])] = r;
 }
 
 __global__ void __launch_bounds__(kStatThreads) stats_rows_sparse_kernel(const StatParams S, const uint32_t *__restrict__ qsz,

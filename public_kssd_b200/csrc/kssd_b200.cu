@@ -1018,6 +1018,7 @@ struct kssd_dist {
     std::vector<const kssd_index_t *> comp_ix;
     std::vector<uint64_t> comp_ncodes;
     std::vector<void *> owned;                   // device copies of host query sketches
+    std::vector<uint32_t> h_qsz, h_rsz;          // host copies of the sketch sizes (sub-jobs of the sparse path)
 };
 
 static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, uint32_t *ct_ext, int filled,
@@ -1029,6 +1030,8 @@ static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_
     d->ctx = c; d->n_qry = n_qry; d->n_ref = n_ref;
     for (int i = 0; i < n_qry; i++) { d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]); d->empty_qry |= qry_ctx_ct[i] == 0; }
     for (int i = 0; i < n_ref; i++) d->empty_ref |= ref_ctx_ct[i] == 0;
+    d->h_qsz.assign(qry_ctx_ct, qry_ctx_ct + n_qry);
+    d->h_rsz.assign(ref_ctx_ct, ref_ctx_ct + n_ref);
     if (ct_ext) { d->d_ct = ct_ext; d->owns_ct = false; d->components_done = filled ? 1 : 0; }
     else if (filled < 0) d->sparse = true;       // sparse job: the matrix is allocated only if a query overflows the sparse path
     else CU(cudaMallocAsync(&d->d_ct, (size_t)n_qry * n_ref * 4, c->stream));
@@ -1303,7 +1306,8 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
             const int per_sm = std::max(1, std::min(trivial ? 3 : 2, (int)((227u * 1024u) / (smem + 3400))));
             const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
             uint64_t total = 0, cap = std::max<uint64_t>(1ull << 22, (uint64_t)d->n_qry * 1024);
-            int over = 0;
+            uint32_t n_over = 0;
+            CU(c->ords2.ensure((size_t)d->n_qry * 4));                 // queries that overflow the table
             for (int attempt = 0;; attempt++) {
                 if (cap > 0xffffffffull) return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D");
                 CU(c->keys.ensure(cap * sizeof(SparseHit)));
@@ -1311,38 +1315,125 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
                 kern<<<grid, kSparseThreads, smem, c->stream>>>(reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, cb, S,
                                                                 d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(), c->counts.as<unsigned long long>(),
                                                                 reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(),
-                                                                reinterpret_cast<int *>(mb + 8));
+                                                                reinterpret_cast<uint32_t *>(mb + 8), c->ords2.as<uint32_t>());
                 LAUNCHED(1);
                 CU(cudaEventRecord(c->ev[2], c->stream));
                 CU(cudaMemcpyAsync(&total, mb, 8, cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaMemcpyAsync(&over, mb + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaMemcpyAsync(&n_over, mb + 8, 4, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 CU(cudaGetLastError());
-                if (over || total <= cap) break;
+                if (total <= cap) break;
                 if (attempt) return fail(KSSD_E_NOMEM, "kssd_dist_stats: hit list overflow");
                 cap = total;
             }
-            if (!over) {
-                CU(cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[2]));       // counting + listing
-                CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
-                if (total) {
-                    size_t tmp = 0;
-                    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream);
-                    CU(c->cubtmp.ensure(tmp));
-                    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream));
-                    stats_rows_sparse_kernel<<<(uint32_t)((total + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
-                        S, d->d_qsz, d->d_rsz, c->keys.as<SparseHit>(), total, c->counts.as<unsigned long long>(), c->pos.as<uint64_t>(), d->d_rows);
-                    LAUNCHED(3);
+            if ((uint64_t)n_over * 2 <= (uint64_t)d->n_qry) {
+                float count_ms = 0;
+                CU(cudaEventElapsedTime(&count_ms, c->ev[0], c->ev[2]));             // counting + listing
+                c->last_ms[3] = count_ms;
+                uint32_t *p_cnt = c->flags.as<uint32_t>();
+                unsigned long long *p_pos = c->counts.as<unsigned long long>();
+                SparseHit *p_hits = c->keys.as<SparseHit>();
+                // queries whose refs did not fit the table: a small dense sub-job (n_over x R matrix), merged in print order
+                kssd_dist *sub = nullptr;
+                uint64_t sub_rows = 0;
+                std::vector<uint32_t> over(n_over);
+                std::vector<uint64_t> first(n_over + 1, 0);
+                std::vector<void *> scratch;
+                uint32_t *d_list = nullptr;
+                auto cleanup = [&] { for (void *p : scratch) cudaFreeAsync(p, c->stream); if (sub) kssd_dist_free(sub); };
+                if (n_over) {
+                    // the sub-job below goes through the context's scratch buffers: keep what the sparse kernel left there
+                    void *keep[3] = {nullptr, nullptr, nullptr};
+                    const size_t kb[3] = {(size_t)d->n_qry * 4, (size_t)d->n_qry * 8, std::max<uint64_t>(total, 1) * sizeof(SparseHit)};
+                    const void *src[3] = {p_cnt, p_pos, p_hits};
+                    for (int i = 0; i < 3; i++) {
+                        CU(cudaMallocAsync(&keep[i], kb[i], c->stream));
+                        scratch.push_back(keep[i]);
+                        CU(cudaMemcpyAsync(keep[i], src[i], kb[i], cudaMemcpyDeviceToDevice, c->stream));
+                    }
+                    p_cnt = static_cast<uint32_t *>(keep[0]);
+                    p_pos = static_cast<unsigned long long *>(keep[1]);
+                    p_hits = static_cast<SparseHit *>(keep[2]);
+                    CU(cudaMemcpyAsync(over.data(), c->ords2.p, (size_t)n_over * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));
+                    std::sort(over.begin(), over.end());
+                    std::vector<uint32_t> sub_qsz(n_over);
+                    for (uint32_t i = 0; i < n_over; i++) sub_qsz[i] = d->h_qsz[over[i]];
+                    int rc = dist_create(c, (int)n_over, d->n_ref, sub_qsz.data(), d->h_rsz.data(), nullptr, 0, &sub);
+                    if (rc) return rc;
+                    CU(cudaMallocAsync(&d_list, (size_t)n_over * 4, c->stream));
+                    scratch.push_back(d_list);
+                    CU(cudaMemcpyAsync(d_list, over.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, c->stream));
+                    std::vector<uint64_t> qix((size_t)d->n_qry + 1), six((size_t)n_over + 1);
+                    for (int cc = 0; cc < nc; cc++) {
+                        CU(cudaMemcpyAsync(qix.data(), d->comps[cc].qindex, qix.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+                        CU(cudaStreamSynchronize(c->stream));
+                        six[0] = 0;
+                        for (uint32_t i = 0; i < n_over; i++) six[i + 1] = six[i] + (qix[over[i] + 1] - qix[over[i]]);
+                        uint64_t *d_six = nullptr;
+                        uint32_t *d_codes = nullptr;
+                        CU(cudaMallocAsync(&d_six, six.size() * 8, c->stream));
+                        scratch.push_back(d_six);
+                        CU(cudaMallocAsync(&d_codes, std::max<uint64_t>(six[n_over], 1) * 4, c->stream));
+                        scratch.push_back(d_codes);
+                        CU(cudaMemcpyAsync(d_six, six.data(), six.size() * 8, cudaMemcpyHostToDevice, c->stream));
+                        gather_query_codes_kernel<<<n_over, 256, 0, c->stream>>>(d->comps[cc].qcodes, d->comps[cc].qindex, d_list, d_six, d_codes);
+                        LAUNCHED(1);
+                        rc = kssd_dist_accumulate_dev(sub, d->comp_ix[cc], d_codes, d_six, six[n_over]);
+                        if (rc) { cleanup(); return rc; }
+                    }
+                    kssd_stat_opts_t o2 = *o;
+                    o2.cmprsn_num = (uint64_t)S.cmprsn_num;                        // the whole job's comparison count
+                    const int64_t nr = kssd_dist_stats(sub, &o2);
+                    if (nr < 0) { cleanup(); return (int)nr; }
+                    sub_rows = (uint64_t)nr;
+                    // per-query row counts of the sub-job -> q_cnt of the whole job
+                    uint32_t *d_cnt = nullptr;
+                    CU(cudaMallocAsync(&d_cnt, (size_t)n_over * 4, c->stream));
+                    scratch.push_back(d_cnt);
+                    CU(cudaMemsetAsync(d_cnt, 0, (size_t)n_over * 4, c->stream));
+                    if (sub_rows) count_rows_by_query_kernel<<<(uint32_t)((sub_rows + 255) / 256), 256, 0, c->stream>>>(sub->d_rows, sub_rows, d_cnt);
+                    std::vector<uint32_t> cnt(n_over), qc((size_t)d->n_qry);
+                    CU(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)n_over * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaMemcpyAsync(qc.data(), p_cnt, (size_t)d->n_qry * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));
+                    for (uint32_t i = 0; i < n_over; i++) { qc[over[i]] = cnt[i]; first[i + 1] = first[i] + cnt[i]; }
+                    CU(cudaMemcpyAsync(p_cnt, qc.data(), (size_t)d->n_qry * 4, cudaMemcpyHostToDevice, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));                          // qc dies here
+                    c->last_ms[3] = count_ms;
                 }
-                d->n_rows = total;
+                const uint64_t all_rows = total + sub_rows;
+                if (all_rows > 0xffffffffull) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D"); }
+                CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(all_rows, 1) * sizeof(StatRow), c->stream));
+                if (all_rows) {
+                    size_t tmp = 0;
+                    CU(c->pos.ensure(((size_t)d->n_qry + 1) * 8));
+                    cub::DeviceScan::ExclusiveSum(nullptr, tmp, p_cnt, c->pos.as<uint64_t>(), d->n_qry, c->stream);
+                    CU(c->cubtmp.ensure(tmp));
+                    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, p_cnt, c->pos.as<uint64_t>(), d->n_qry, c->stream));
+                    if (total)
+                        stats_rows_sparse_kernel<<<(uint32_t)((total + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
+                            S, d->d_qsz, d->d_rsz, p_hits, total, p_pos, c->pos.as<uint64_t>(), d->d_rows);
+                    if (sub_rows) {
+                        uint64_t *d_first = nullptr;
+                        CU(cudaMallocAsync(&d_first, first.size() * 8, c->stream));
+                        scratch.push_back(d_first);
+                        CU(cudaMemcpyAsync(d_first, first.data(), first.size() * 8, cudaMemcpyHostToDevice, c->stream));
+                        place_sub_rows_kernel<<<(uint32_t)((sub_rows + 255) / 256), 256, 0, c->stream>>>(
+                            sub->d_rows, sub_rows, d_list, d_first, c->pos.as<uint64_t>(), d->d_rows);
+                    }
+                    LAUNCHED(4);
+                }
+                d->n_rows = all_rows;
                 CU(cudaEventRecord(c->ev[1], c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 CU(cudaGetLastError());
                 CU(cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]));
+                cleanup();
                 return (int64_t)d->n_rows;
             }
         }
-        // some query touches too many references, or zero cells are wanted: go through the matrix after all
+        // most queries touch too many references, or zero cells are wanted: go through the matrix after all
         const int rc = dist_densify(d);
         if (rc) return rc;
     }

@@ -224,6 +224,35 @@ def test_sparse_job_many_refs_per_query_falls_back(gpu_ctx_l3k10):
     dense.close(); sp.close(); ix.close()
 
 
+@pytest.mark.parametrize("opts", [dict(skip_zero=1), dict(dthreshold=0.4), dict(metric=1, dthreshold=0.3)])
+def test_sparse_job_heavy_queries_take_the_dense_sub_job(gpu_ctx_l3k10, opts):
+    """Queries that touch more references than the shared-memory table holds are counted through a small dense sub-job
+    and merged back in print order; the others stay sparse.  Rows identical to the all-dense job."""
+    from public_kssd_b200 import kssd
+    n_ref = 9000
+    base = np.arange(50, dtype=np.uint32) * 7919 + 13
+    rc = np.concatenate([np.sort(np.concatenate([base[:3], np.array([100000 + g, 200000 + g // 7], dtype=np.uint32)])) for g in range(n_ref)])
+    ri = np.arange(n_ref + 1, dtype=np.uint64) * 5
+    light = [np.sort(np.array([100000 + 11 * i, 100000 + 11 * i + 1, 200000 + i, 777 + i], dtype=np.uint32)) for i in range(9)]
+    heavy = np.sort(np.concatenate([base, np.array([100000 + 5, 200000 + 3], dtype=np.uint32)]))
+    queries = light[:3] + [heavy] + light[3:6] + [np.zeros(0, np.uint32), heavy[:40]] + light[6:]
+    qc = np.concatenate(queries)
+    qi = np.concatenate([[0], np.cumsum([len(q) for q in queries])]).astype(np.uint64)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    dense = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz)
+    dense.accumulate(ix, qc, qi)
+    want = dense.stats(**opts)
+    sp = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz, sparse=True)
+    sp.accumulate(ix, qc, qi)
+    got = sp.stats(**opts)
+    assert len(want) > 2 * n_ref - 100 or "dthreshold" in opts
+    assert got.tobytes() == want.tobytes()
+    got2 = sp.stats(**opts)                                   # the job is reusable
+    assert got2.tobytes() == want.tobytes()
+    dense.close(); sp.close(); ix.close()
+
+
 def test_sparse_job_multi_component(shuf_l3k10):
     """K11: 16 components add into the same per-query table."""
     from public_kssd_b200 import kssd
