@@ -37,3 +37,10 @@ def test_native_formatter_matches_python(metric, outfields, threads):
     got = hostfmt.format_distance_out(rows, qn, rn, metric, outfields, header=True, threads=threads).decode()
     assert got == want
     assert hostfmt.format_distance_out(rows[:0], qn, rn, metric, outfields, header=False) == b""
+
+
+def test_list_file_reader(tmp_path):
+    """-l <list>: one path per line, blank lines ignored."""
+    lst = tmp_path / "in.list"
+    lst.write_text("a/b.fna\n\n  c d/e.fa.gz  \nlast.fq")
+    assert hostfmt.read_list_file(lst) == ["a/b.fna", "c d/e.fa.gz", "last.fq"]
