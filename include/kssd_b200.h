@@ -288,6 +288,23 @@ int kssd_set_operate_dev(kssd_ctx_t *ctx, const uint32_t *combco_dev, const uint
                          uint64_t n_codes, const uint32_t *pan_dev, uint64_t n_pan, int intersect,
                          uint32_t *combco_out_dev, uint64_t *index_out_dev);
 
+/* ------------------------------------------------------------------------------------------ *
+ * kssd composite -- replaces get_species_abundance (command_composite.c:389-547): for every query sketch with
+ * abundances (`-A`: combco.<c> + combco.<c>.a) and every reference, the abundances of the k-mers they share, summarised
+ * as the reference prints them (:531): kmer_num, mean = (float)sum/kmer_num, pct = mean of the sorted abundances
+ * a[floor(0.98 k)] .. a[n <= 0.99 k] (1-based), median = a[k/2], max = a[k].  Rows come in print order: queries
+ * ascending, references with >= min_kmers (MIN_KM_S = 6 when <= 0) shared k-mers, most shared first, ties in reference
+ * order.  The reference side is the inverted index of the reference sketches, one per component (kssd_index_build_*).
+ * Rows are allocated by the library (kssd_host_free). */
+typedef struct kssd_comp_row {
+    uint32_t qry, ref, kmer_num, median, max;
+    float mean, pct;
+    uint32_t reserved;
+} kssd_comp_row_t;
+int kssd_composite_host(kssd_ctx_t *ctx, int n_comp, const kssd_index_t *const *ref_ix, const uint32_t *const *qcodes,
+                        const uint64_t *const *qindex, const uint16_t *const *qabund, int n_qry, int min_kmers,
+                        kssd_comp_row_t **rows_out, uint64_t *n_rows);
+
 /* device time (ms, CUDA events on the context stream) of the last scan / index / count / stats
  * kernel sequence issued through this context; which = 0 sketch scan, 1 sketch total,
  * 2 index build, 3 dist counts, 4 dist stats */

@@ -276,6 +276,48 @@ def set_operate(combco: np.ndarray, index: np.ndarray, pan: np.ndarray, intersec
     return out[:int(oix[-1])].copy(), oix
 
 
+def composite(ref_codes, ref_index, qry_codes, qry_index, qry_abund, min_kmers: int = 6):
+    """get_species_abundance (command_composite.c:389-547), numbers only.  Arguments are per-component lists (combco.<c>,
+    combco.index.<c>, combco.<c>.a).  For every query, the references that share >= MIN_KM_S (6) k-mers with it, most
+    shared first (glibc qsort is a stable merge sort here: ties keep reference order): rows
+    (qry, ref, kmer_num, mean, pct, median, max) with mean = (float)sum/kmer_num, pct = mean of the sorted abundances
+    a[floor(0.98 k)] .. a[n <= 0.99 k] (1-based), median = a[k/2], max = a[k] (:512-531)."""
+    ncomp = len(ref_codes)
+    nr, nq = len(ref_index[0]) - 1, len(qry_index[0]) - 1
+    rows = []
+    for qn in range(nq):
+        lists = [[] for _ in range(nr)]
+        for c in range(ncomp):
+            a, b = int(qry_index[c][qn]), int(qry_index[c][qn + 1])
+            km = dict(zip(qry_codes[c][a:b].tolist(), qry_abund[c][a:b].tolist()))
+            rc, ri = ref_codes[c], ref_index[c]
+            for rn in range(nr):
+                for code in rc[int(ri[rn]):int(ri[rn + 1])].tolist():
+                    v = km.get(code)
+                    if v is not None:
+                        lists[rn].append(v)
+        for rn in sorted(range(nr), key=lambda i: -len(lists[i])):
+            k = len(lists[rn])
+            if k < min_kmers:
+                break
+            a = [0] + sorted(lists[rn])                     # 1-based like ref_abund[rn][1..k]
+            total = sum(a)
+            lastsum = lastn = 0
+            n = int(k * 0.98)
+            while n <= k * 0.99:
+                lastsum += a[n]
+                lastn += 1
+                n += 1
+            rows.append((qn, rn, k, np.float32(total) / np.float32(k), np.float32(lastsum) / np.float32(lastn), a[k // 2], a[k]))
+    return rows
+
+
+def composite_text(rows, qry_names, ref_names) -> str:
+    """the printf at command_composite.c:531"""
+    return "".join("%s\t%s\t%d\t%f\t%f\t%d\t%d\n" % (qry_names[q], ref_names[r], k, float(m), float(p), med, mx)
+                   for q, r, k, m, p, med, mx in rows)
+
+
 def run_ref(args, cwd=None, binary=None, timeout=3600) -> subprocess.CompletedProcess:
     return subprocess.run([str(binary or REF_BIN)] + [str(a) for a in args], cwd=cwd, capture_output=True,
                           text=True, timeout=timeout)

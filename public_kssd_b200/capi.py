@@ -30,12 +30,16 @@ SYMBOLS = [
     "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_fetch_stats", "kssd_dist_free",
     "kssd_format_distance_rows", "kssd_host_free",
     "kssd_set_union_host", "kssd_set_union_dev", "kssd_set_operate_host", "kssd_set_operate_dev",
+    "kssd_composite_host",
 ]
 
 MODE_FASTA, MODE_FASTA_UNIQ, MODE_FASTQ, MODE_FASTQ_ABUND, MODE_BYREAD = 0, 1, 2, 3, 4
 METRIC_JACCARD, METRIC_CONTAINMENT = 0, 1
 
 E_CROWD, E_HEADER_EOF, E_LONGLINE = -4, -5, -9
+
+COMP_ROW_DTYPE = np.dtype([("qry", "<u4"), ("ref", "<u4"), ("kmer_num", "<u4"), ("median", "<u4"), ("max", "<u4"), ("mean", "<f4"),
+                           ("pct", "<f4"), ("reserved", "<u4")])
 
 
 class KssdError(RuntimeError):
@@ -159,6 +163,8 @@ def lib() -> C.CDLL:
     L.kssd_set_union_dev.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, C.c_uint64, u64p]
     L.kssd_set_operate_host.argtypes = [vp, u32p, u64p, C.c_int, u32p, C.c_uint64, C.c_int, u32p, u64p]
     L.kssd_set_operate_dev.argtypes = [vp, vp, vp, C.c_int, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]
+    L.kssd_composite_host.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int,
+                                      C.POINTER(vp), u64p]
     L.kssd_host_free.argtypes = [vp]
     L.kssd_host_free.restype = None
     _lib = L

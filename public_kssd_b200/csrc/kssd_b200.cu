@@ -20,6 +20,7 @@
 #include "sketch_scan32.cuh"
 #include "sketch_fastq.cuh"
 #include "set_ops.cuh"
+#include "composite.cuh"
 
 using namespace kssd;
 
@@ -1730,5 +1731,122 @@ extern "C" int kssd_set_operate_host(kssd_ctx_t *c, const uint32_t *combco, cons
     const uint64_t kept = index_out[n_genomes];
     if (kept) CU(cudaMemcpyAsync(combco_out, d_out, kept * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// kssd composite (reference get_species_abundance, command_composite.c:389-547)
+// ------------------------------------------------------------------------------------------------
+extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t *const *ref_ix, const uint32_t *const *qcodes,
+                                   const uint64_t *const *qindex, const uint16_t *const *qabund, int n_qry, int min_kmers,
+                                   kssd_comp_row_t **rows_out, uint64_t *n_rows)
+{
+    static_assert(sizeof(kssd_comp_row_t) == sizeof(CompRow), "row layout");
+    if (!c || n_comp <= 0 || !ref_ix || !qcodes || !qindex || !qabund || n_qry <= 0 || !rows_out || !n_rows)
+        return fail(KSSD_E_INVAL, "kssd_composite_host: bad argument");
+    if (n_qry >= (1 << 20)) return fail(KSSD_E_INVAL, "kssd_composite_host: at most 2^20 - 1 queries per call");
+    for (int cc = 0; cc < n_comp; cc++) {
+        if (!ref_ix[cc] || !qindex[cc]) return fail(KSSD_E_INVAL, "kssd_composite_host: null component %d", cc);
+        if (ref_ix[cc]->n_genomes != ref_ix[0]->n_genomes || ref_ix[cc]->n_genomes >= (1 << 24))
+            return fail(KSSD_E_MISMATCH, "kssd_composite_host: component %d has %d references", cc, ref_ix[cc]->n_genomes);
+    }
+    CU(cudaSetDevice(c->device));
+    if (min_kmers < 1) min_kmers = 6;                                   // MIN_KM_S
+    *rows_out = nullptr;
+    *n_rows = 0;
+    std::vector<void *> scratch;
+    auto cleanup = [&] { for (void *p : scratch) cudaFreeAsync(p, c->stream); };
+    auto dalloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, std::max<size_t>(bytes, 16), c->stream) != cudaSuccess) return nullptr;
+        scratch.push_back(p);
+        return p;
+    };
+    struct Comp { uint32_t *codes; uint16_t *ab; uint64_t *index, *off; uint64_t n, pairs; };
+    std::vector<Comp> comps(n_comp);
+    uint64_t P = 0;
+    size_t tmp = 0;
+    for (int cc = 0; cc < n_comp; cc++) {
+        Comp &C = comps[cc];
+        C.n = qindex[cc][n_qry];
+        if (C.n && (!qcodes[cc] || !qabund[cc])) { cleanup(); return fail(KSSD_E_INVAL, "kssd_composite_host: null codes in component %d", cc); }
+        C.codes = (uint32_t *)dalloc(C.n * 4); C.ab = (uint16_t *)dalloc(C.n * 2); C.index = (uint64_t *)dalloc(8ull * (n_qry + 1));
+        C.off = (uint64_t *)dalloc(C.n * 8);
+        uint32_t *len = (uint32_t *)dalloc(C.n * 4);
+        if (!C.codes || !C.ab || !C.index || !C.off || !len) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
+        CU(cudaMemcpyAsync(C.index, qindex[cc], 8ull * (n_qry + 1), cudaMemcpyHostToDevice, c->stream));
+        C.pairs = 0;
+        if (C.n) {
+            CU(cudaMemcpyAsync(C.codes, qcodes[cc], C.n * 4, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(C.ab, qabund[cc], C.n * 2, cudaMemcpyHostToDevice, c->stream));
+            comp_count_kernel<<<(uint32_t)((C.n + 255) / 256), 256, 0, c->stream>>>(C.codes, C.n, ref_ix[cc]->d_dense, len);
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, C.off, C.n, c->stream);
+            CU(c->cubtmp.ensure(tmp));
+            CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, len, C.off, C.n, c->stream));
+            uint64_t lo = 0;
+            uint32_t ll = 0;
+            CU(cudaMemcpyAsync(&lo, C.off + (C.n - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(&ll, len + (C.n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            C.pairs = lo + ll;
+            LAUNCHED(3);
+        }
+        P += C.pairs;
+    }
+    if (P == 0) { CU(cudaStreamSynchronize(c->stream)); cleanup(); return KSSD_OK; }
+    if (P >= 0x7fffffffull) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: more than 2^31 shared k-mer pairs in one call; split the queries"); }
+    uint64_t *keys = (uint64_t *)dalloc(P * 8), *sorted = (uint64_t *)dalloc(P * 8), *groups = (uint64_t *)dalloc(P * 8);
+    uint64_t *run_key = (uint64_t *)dalloc(P * 8), *run_off = (uint64_t *)dalloc(P * 8);
+    uint32_t *run_len = (uint32_t *)dalloc(P * 4), *d_meta = (uint32_t *)dalloc(16);
+    if (!keys || !sorted || !groups || !run_key || !run_off || !run_len || !d_meta) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
+    uint64_t base = 0;
+    for (int cc = 0; cc < n_comp; cc++) {
+        const Comp &C = comps[cc];
+        if (C.n) comp_emit_kernel<<<(uint32_t)((C.n + 255) / 256), 256, 0, c->stream>>>(C.codes, C.ab, C.index, n_qry, C.n, ref_ix[cc]->d_dense,
+                                                                                       ref_ix[cc]->d_gids, C.off, keys + base);
+        base += C.pairs;
+    }
+    int qbits = 1;
+    while ((1ll << qbits) < n_qry) qbits++;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, sorted, P, 0, kCompQryShift + qbits, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(c->cubtmp.p, tmp, keys, sorted, P, 0, kCompQryShift + qbits, c->stream));
+    comp_group_kernel<<<(uint32_t)((P + 255) / 256), 256, 0, c->stream>>>(sorted, P, groups);
+    cub::DeviceRunLengthEncode::Encode(nullptr, tmp, groups, run_key, run_len, d_meta, (int)P, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cub::DeviceRunLengthEncode::Encode(c->cubtmp.p, tmp, groups, run_key, run_len, d_meta, (int)P, c->stream));
+    uint32_t n_runs = 0;
+    CU(cudaMemcpyAsync(&n_runs, d_meta, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, run_len, run_off, n_runs, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, run_len, run_off, n_runs, c->stream));
+    CompRow *rows = (CompRow *)dalloc((size_t)n_runs * sizeof(CompRow)), *rows_sorted = (CompRow *)dalloc((size_t)n_runs * sizeof(CompRow));
+    uint64_t *okey = (uint64_t *)dalloc((size_t)n_runs * 8), *okey2 = (uint64_t *)dalloc((size_t)n_runs * 8);
+    uint32_t *perm = (uint32_t *)dalloc((size_t)n_runs * 4), *perm2 = (uint32_t *)dalloc((size_t)n_runs * 4);
+    if (!rows || !rows_sorted || !okey || !okey2 || !perm || !perm2) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
+    CU(cudaMemsetAsync(d_meta + 1, 0, 4, c->stream));
+    const uint32_t nb = (n_runs + 255) / 256;
+    comp_rows_kernel<<<nb, 256, 0, c->stream>>>(sorted, run_key, run_len, run_off, n_runs, (uint32_t)min_kmers, rows, okey, d_meta + 1);
+    comp_iota_kernel<<<nb, 256, 0, c->stream>>>(perm, n_runs);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, okey, okey2, perm, perm2, n_runs, 0, 64, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, okey, okey2, perm, perm2, n_runs, 0, 64, c->stream));
+    comp_gather_kernel<<<nb, 256, 0, c->stream>>>(rows, perm2, n_runs, rows_sorted);
+    LAUNCHED(20);
+    uint32_t kept = 0;
+    CU(cudaMemcpyAsync(&kept, d_meta + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    if (kept) {
+        kssd_comp_row_t *h = (kssd_comp_row_t *)malloc((size_t)kept * sizeof(kssd_comp_row_t));
+        if (!h) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of host memory"); }
+        CU(cudaMemcpyAsync(h, rows_sorted, (size_t)kept * sizeof(CompRow), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *rows_out = h;
+        *n_rows = kept;
+    }
+    cleanup();
     return KSSD_OK;
 }

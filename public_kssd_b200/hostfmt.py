@@ -33,6 +33,12 @@ def slot_order(ids: np.ndarray, first_occurrence: np.ndarray, hashsize: int, key
     return np.array([table[s] for s in sorted(table)], dtype=np.uint32)
 
 
+def format_composite_rows(rows, qry_names, ref_names) -> str:
+    """The text `kssd composite` prints (command_composite.c:531): qry, ref, kmer_num, mean, 98-99 % band mean, median, max."""
+    return "".join("%s\t%s\t%d\t%f\t%f\t%d\t%d\n" % (qry_names[int(r["qry"])], ref_names[int(r["ref"])], r["kmer_num"], float(r["mean"]),
+                                                     float(r["pct"]), r["median"], r["max"]) for r in rows)
+
+
 def read_list_file(path) -> list:
     """The reference's `-l <list>`: one input path per line (command_dist.c organize step); blank lines ignored."""
     return [ln.strip() for ln in Path(path).read_text().splitlines() if ln.strip()]

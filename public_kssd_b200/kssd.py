@@ -270,6 +270,28 @@ class Context:
                                           int(intersect), ptr(out, C.c_uint32), ptr(oix, C.c_uint64)))
         return out[:int(oix[-1])].copy(), oix
 
+    # ---------------- kssd composite ----------------
+    def composite(self, ref_indexes, qry_codes, qry_index, qry_abund, min_kmers: int = 0) -> np.ndarray:
+        """`kssd composite -r <refs> -q <-A queries>` (get_species_abundance): per-component lists of the reference
+        inverted indexes (combco2mco of the reference sketches) and of the query combco.<c> / combco.index.<c> /
+        combco.<c>.a.  Returns the rows in the reference's print order (capi.COMP_ROW_DTYPE)."""
+        nc = len(ref_indexes)
+        qc = [np.ascontiguousarray(a, dtype=np.uint32) for a in qry_codes]
+        qi = [np.ascontiguousarray(a, dtype=np.uint64) for a in qry_index]
+        qa = [np.ascontiguousarray(a, dtype=np.uint16) for a in qry_abund]
+        VP = C.c_void_p * nc
+        rows, n = C.c_void_p(), C.c_uint64(0)
+        check(lib().kssd_composite_host(self._h, nc, VP(*[ix._h for ix in ref_indexes]), VP(*[a.ctypes.data for a in qc]),
+                                        VP(*[a.ctypes.data for a in qi]), VP(*[a.ctypes.data for a in qa]), len(qi[0]) - 1, min_kmers,
+                                        C.byref(rows), C.byref(n)))
+        try:
+            if not n.value:
+                return np.zeros(0, dtype=capi.COMP_ROW_DTYPE)
+            return np.frombuffer(C.string_at(rows, n.value * capi.COMP_ROW_DTYPE.itemsize), dtype=capi.COMP_ROW_DTYPE).copy()
+        finally:
+            if rows:
+                lib().kssd_host_free(rows)
+
     # ---------------- Stage II ----------------
     def combco2mco(self, combco: np.ndarray, cbdcoindex: np.ndarray) -> "Index":
         combco = np.ascontiguousarray(combco, dtype=np.uint32)

@@ -222,3 +222,46 @@ def set_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "set":
     set_golden()
+
+
+def composite_golden():
+    """`kssd composite -r <ref sketches> -q <-A query sketches>` (get_species_abundance, command_composite.c:389-547): the
+    text it prints plus the sketch files it read, L2K8 and L3K10 (the reference aborts in -A sketching at K11)."""
+    O.build()
+    t6 = synth.make_shuf_table(6, cases.SHUF_SEED_S6)
+    t5 = synth.make_shuf_table(5, cases.SHUF_SEED_S5)
+    src = synth.random_bases(100_000, 41)            # the genome cases.fastq_inputs() draws its reads from
+    refs = {"r0_src": synth.to_fasta(src, "src", 80), "r1_mut": synth.to_fasta(synth.mutate(src, 0.05, 7), "mut", 80),
+            "r2_other": synth.to_fasta(synth.random_bases(100_000, 99), "oth", 80), "r3_half": synth.to_fasta(src[:50_000], "half", 80),
+            "r4_half_again": synth.to_fasta(src[:50_000], "half2", 70), "r5_tail": synth.to_fasta(src[90_000:], "tail", 80)}
+    fq = cases.fastq_inputs()
+    for tag, (k, s, L, tab) in {"composite_l2k8": (8, 5, 2, t5), "composite_l3k10": (10, 6, 3, t6)}.items():
+        rr = O.RefRun(k, s, L, tab, shuf_id=cases.SHUF_ID)
+        d = rr.dir / "refs"
+        d.mkdir()
+        for n, b in refs.items():
+            (d / f"{n}.fasta").write_bytes(b.tobytes())
+        rs = rr.sketch(d, "rsk", p=1)
+        q = rr.dir / "q"
+        q.mkdir()
+        for n, b in fq.items():
+            (q / f"{n}.fastq").write_bytes(b.tobytes())
+        qs = rr.sketch(q, "qsk", extra=["-A"], p=1)
+        r = O.run_ref(["composite", "-r", rs, "-q", qs], cwd=rr.dir)
+        assert r.returncode == 0, r.stderr
+        rst, qst = O.read_cofiles_stat(rs), O.read_cofiles_stat(qs)
+        pack = {"comp_num": np.int32(rst["comp_num"]), "ref_names": np.array([Path(n).name for n in rst["names"]]),
+                "qry_names": np.array([Path(n).name for n in qst["names"]]),
+                "stdout": np.frombuffer(r.stdout.encode(), dtype=np.uint8)}
+        for c in range(rst["comp_num"]):
+            rc, ri, _ = O.read_combco(rs, c)
+            qc, qi, qa = O.read_combco(qs, c)
+            pack[f"ref.{c}"], pack[f"ref.index.{c}"] = rc, ri
+            pack[f"qry.{c}"], pack[f"qry.index.{c}"], pack[f"qry.a.{c}"] = qc, qi, qa
+        np.savez_compressed(OUT / f"{tag}.npz", **pack)
+        print(tag, "\n" + r.stdout[:900].replace(str(rr.dir), ""))
+        rr.cleanup()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "composite":
+    composite_golden()

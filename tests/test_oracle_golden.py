@@ -81,6 +81,20 @@ def test_set_operations_identical_to_reference(oracle_mod, tag):
     assert int(g["i.all_ctx_ct"]) == int(g["in.all_ctx_ct"]) == int(g["s.all_ctx_ct"])
 
 
+@pytest.mark.parametrize("tag", ["composite_l2k8", "composite_l3k10"])
+def test_composite_text_identical_to_reference(oracle_mod, tag):
+    """kssd composite (get_species_abundance): shared-k-mer abundance statistics per (query, reference), text identical."""
+    g = _load(tag)
+    nc = int(g["comp_num"])
+    rows = oracle_mod.composite([g[f"ref.{c}"] for c in range(nc)], [g[f"ref.index.{c}"] for c in range(nc)],
+                                [g[f"qry.{c}"] for c in range(nc)], [g[f"qry.index.{c}"] for c in range(nc)],
+                                [g[f"qry.a.{c}"] for c in range(nc)])
+    ref_txt = g["stdout"].tobytes().decode()
+    norm = ["\t".join([Path(f[0]).name, Path(f[1]).name] + f[2:]) for f in (ln.split("\t") for ln in ref_txt.splitlines())]
+    mine = oracle_mod.composite_text(rows, [str(n) for n in g["qry_names"]], [str(n) for n in g["ref_names"]]).splitlines()
+    assert mine == norm and len(mine) > 5
+
+
 def test_fastq_abundance_identical_to_reference(oracle_mod, tables):
     g = _load("fastq_abund_l2k8")
     fq = cases.fastq_inputs()
