@@ -77,6 +77,23 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// stream-ordered scratch allocations of one call, released on every exit path
+struct StreamScratch {
+    cudaStream_t stream;
+    std::vector<void *> ptrs;
+    explicit StreamScratch(cudaStream_t s) : stream(s) {}
+    ~StreamScratch() { for (void *p : ptrs) cudaFreeAsync(p, stream); }
+    void *alloc(size_t bytes)
+    {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return p;
+    }
+    StreamScratch(const StreamScratch &) = delete;
+    StreamScratch &operator=(const StreamScratch &) = delete;
+};
+
 struct kssd_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -1755,14 +1772,8 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
     if (min_kmers < 1) min_kmers = 6;                                   // MIN_KM_S
     *rows_out = nullptr;
     *n_rows = 0;
-    std::vector<void *> scratch;
-    auto cleanup = [&] { for (void *p : scratch) cudaFreeAsync(p, c->stream); };
-    auto dalloc = [&](size_t bytes) -> void * {
-        void *p = nullptr;
-        if (cudaMallocAsync(&p, std::max<size_t>(bytes, 16), c->stream) != cudaSuccess) return nullptr;
-        scratch.push_back(p);
-        return p;
-    };
+    StreamScratch scratch(c->stream);
+    auto dalloc = [&](size_t bytes) -> void * { return scratch.alloc(bytes); };
     struct Comp { uint32_t *codes; uint16_t *ab; uint64_t *index, *off; uint64_t n, pairs; };
     std::vector<Comp> comps(n_comp);
     uint64_t P = 0;
@@ -1770,11 +1781,11 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
     for (int cc = 0; cc < n_comp; cc++) {
         Comp &C = comps[cc];
         C.n = qindex[cc][n_qry];
-        if (C.n && (!qcodes[cc] || !qabund[cc])) { cleanup(); return fail(KSSD_E_INVAL, "kssd_composite_host: null codes in component %d", cc); }
+        if (C.n && (!qcodes[cc] || !qabund[cc])) { return fail(KSSD_E_INVAL, "kssd_composite_host: null codes in component %d", cc); }
         C.codes = (uint32_t *)dalloc(C.n * 4); C.ab = (uint16_t *)dalloc(C.n * 2); C.index = (uint64_t *)dalloc(8ull * (n_qry + 1));
         C.off = (uint64_t *)dalloc(C.n * 8);
         uint32_t *len = (uint32_t *)dalloc(C.n * 4);
-        if (!C.codes || !C.ab || !C.index || !C.off || !len) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
+        if (!C.codes || !C.ab || !C.index || !C.off || !len) { return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
         CU(cudaMemcpyAsync(C.index, qindex[cc], 8ull * (n_qry + 1), cudaMemcpyHostToDevice, c->stream));
         C.pairs = 0;
         if (C.n) {
@@ -1794,12 +1805,12 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
         }
         P += C.pairs;
     }
-    if (P == 0) { CU(cudaStreamSynchronize(c->stream)); cleanup(); return KSSD_OK; }
-    if (P >= 0x7fffffffull) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: more than 2^31 shared k-mer pairs in one call; split the queries"); }
+    if (P == 0) { CU(cudaStreamSynchronize(c->stream)); return KSSD_OK; }
+    if (P >= 0x7fffffffull) { return fail(KSSD_E_NOMEM, "kssd_composite_host: more than 2^31 shared k-mer pairs in one call; split the queries"); }
     uint64_t *keys = (uint64_t *)dalloc(P * 8), *sorted = (uint64_t *)dalloc(P * 8), *groups = (uint64_t *)dalloc(P * 8);
     uint64_t *run_key = (uint64_t *)dalloc(P * 8), *run_off = (uint64_t *)dalloc(P * 8);
     uint32_t *run_len = (uint32_t *)dalloc(P * 4), *d_meta = (uint32_t *)dalloc(16);
-    if (!keys || !sorted || !groups || !run_key || !run_off || !run_len || !d_meta) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
+    if (!keys || !sorted || !groups || !run_key || !run_off || !run_len || !d_meta) { return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
     uint64_t base = 0;
     for (int cc = 0; cc < n_comp; cc++) {
         const Comp &C = comps[cc];
@@ -1825,7 +1836,7 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
     CompRow *rows = (CompRow *)dalloc((size_t)n_runs * sizeof(CompRow)), *rows_sorted = (CompRow *)dalloc((size_t)n_runs * sizeof(CompRow));
     uint64_t *okey = (uint64_t *)dalloc((size_t)n_runs * 8), *okey2 = (uint64_t *)dalloc((size_t)n_runs * 8);
     uint32_t *perm = (uint32_t *)dalloc((size_t)n_runs * 4), *perm2 = (uint32_t *)dalloc((size_t)n_runs * 4);
-    if (!rows || !rows_sorted || !okey || !okey2 || !perm || !perm2) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
+    if (!rows || !rows_sorted || !okey || !okey2 || !perm || !perm2) { return fail(KSSD_E_NOMEM, "kssd_composite_host: out of device memory"); }
     CU(cudaMemsetAsync(d_meta + 1, 0, 4, c->stream));
     const uint32_t nb = (n_runs + 255) / 256;
     comp_rows_kernel<<<nb, 256, 0, c->stream>>>(sorted, run_key, run_len, run_off, n_runs, (uint32_t)min_kmers, rows, okey, d_meta + 1);
@@ -1841,12 +1852,11 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
     CU(cudaGetLastError());
     if (kept) {
         kssd_comp_row_t *h = (kssd_comp_row_t *)malloc((size_t)kept * sizeof(kssd_comp_row_t));
-        if (!h) { cleanup(); return fail(KSSD_E_NOMEM, "kssd_composite_host: out of host memory"); }
+        if (!h) { return fail(KSSD_E_NOMEM, "kssd_composite_host: out of host memory"); }
         CU(cudaMemcpyAsync(h, rows_sorted, (size_t)kept * sizeof(CompRow), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         *rows_out = h;
         *n_rows = kept;
     }
-    cleanup();
     return KSSD_OK;
 }
