@@ -37,3 +37,17 @@ def test_header_is_c_and_links(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "sm_100a" in out.stdout
+
+
+def test_c_host_program_builds(tmp_path):
+    """host/kssd_b200_dist.c -- the Stage I / II / III driver in the reference's language -- compiles warning-free and
+    links against the library; without arguments it prints its usage (no GPU touched)."""
+    from public_kssd_b200 import capi
+    capi.build_library()
+    exe = tmp_path / "kssd_b200_dist"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "include"),
+                        str(ROOT / "host" / "kssd_b200_dist.c"), "-o", str(exe), "-L", str(capi.PKG_DIR), "-lkssd_b200",
+                        f"-Wl,-rpath,{capi.PKG_DIR}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: kssd_b200_dist sketch" in r.stderr
