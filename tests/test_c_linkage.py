@@ -51,3 +51,17 @@ def test_c_host_program_builds(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 2 and "usage: kssd_b200_dist sketch" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        # no device: the host must stop with the library's error, there is no CPU path to fall back to
+        import struct
+        import numpy as np
+        shuf = tmp_path / "t.shuf"
+        with open(shuf, "wb") as f:
+            f.write(struct.pack("<iiii", 7, 8, 5, 2))
+            f.write(np.arange(1 << 20, dtype="<i4").tobytes())
+        fa = tmp_path / "a.fa"
+        fa.write_text(">a\nACGTACGTACGTACGTACGTACGT\n")
+        r = subprocess.run([str(exe), "sketch", str(shuf), str(tmp_path / "out"), str(fa)], capture_output=True, text=True)
+        assert r.returncode == 1 and "kssd_ctx_create" in r.stderr
+        assert not (tmp_path / "out" / "cofiles.stat").exists()
