@@ -17,7 +17,7 @@
 
 #include "../../include/kssd_b200.h"
 #include "index_dist.cuh"
-#include "sketch_scan32.cuh"
+#include "sketch_scan3.cuh"
 #include "sketch_fastq.cuh"
 #include "set_ops.cuh"
 #include "composite.cuh"
@@ -100,6 +100,9 @@ struct kssd_ctx {
     SketchParams P{};
     kssd_ctx_info_t info{};
     uint32_t *d_prefilter = nullptr;
+    uint32_t *d_prefilter3 = nullptr;            // block bitmap + second level of the lazy scan (sketch_scan3.cuh)
+    int scan_stride = 3;                         // bases per first-level probe of that scan (3 when 2*subk >= 12, else 1)
+    int scan_impl = 3;                           // KSSD_SCAN_IMPL=2 selects the previous formulation (A/B runs)
     uint2 *d_ht = nullptr;
     // scratch
     DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, counts, minord, cubtmp, misc;
@@ -130,10 +133,12 @@ __global__ void count_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t 
 
 // S = {d : shuf[d] < dim_end}: exact hash table d -> pf, and the prefilter bitmap of S u RC(S)
 __global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t n, uint32_t dim_end, int s,
-                                     uint32_t *__restrict__ prefilter, uint2 *__restrict__ ht, uint32_t ht_mask)
+                                     uint32_t *__restrict__ prefilter, uint32_t *__restrict__ prefilter3, int stride, uint2 *__restrict__ ht,
+                                     uint32_t ht_mask)
 {
     const int wbits = 4 * s;                                   // width of the inner 2s-mer
     const uint32_t reps = wbits < kPfBitShift + 5 ? 1u << (kPfBitShift + 5 - wbits) : 1u;
+    const uint32_t reps3 = wbits < 20 ? 1u << (20 - wbits) : 1u;
     for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
         const int32_t v = shuf[d];
         if (v < 0 || (uint32_t)v >= dim_end) continue;
@@ -148,6 +153,16 @@ __global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t 
             }
             const uint32_t i2 = pf2_index(both[k]);
             atomicOr(&prefilter[kPfWords + (i2 >> 5)], 1u << (i2 & 31));
+            // lazy scan (sketch_scan3.cuh): the window in the scan representation; its 10-base blocks at offsets
+            // 0 .. stride-1 (word = bits 0-14, flag = 0x80000000 >> bits 15-19), and the hashed whole window
+            const uint32_t y = (uint32_t)to_scan_repr(both[k], 2 * s);
+            for (int r = 0; r < stride; r++)
+                for (uint32_t hi = 0; hi < reps3; hi++) {
+                    const uint32_t b = ((y >> (2 * r)) | (hi << wbits)) & 0xfffffu;
+                    atomicOr(&prefilter3[b & 0x7fffu], 0x80000000u >> (b >> 15));
+                }
+            const uint32_t i3 = pf3b_index(y);
+            atomicOr(&prefilter3[kPf3Words + (i3 >> 5)], 1u << (i3 & 31));
         }
         uint32_t h = mix32(d) & ht_mask;
         for (;;) {
@@ -221,8 +236,12 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     CU(cudaMalloc(&c->d_ht, (size_t)ht_size * sizeof(uint2)));
     CU(cudaMemsetAsync(c->d_prefilter, 0, (kPfWords + kPf2Words) * 4, c->stream));
     CU(cudaMemsetAsync(c->d_ht, 0xff, (size_t)ht_size * sizeof(uint2), c->stream));
-    build_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, subk, c->d_prefilter, c->d_ht,
-                                                                P.ht_mask);
+    CU(cudaMalloc(&c->d_prefilter3, (kPf3Words + kPf3bWords) * 4));
+    CU(cudaMemsetAsync(c->d_prefilter3, 0, (kPf3Words + kPf3bWords) * 4, c->stream));
+    c->scan_stride = 2 * subk >= 12 ? 3 : 1;
+    if (const char *e = getenv("KSSD_SCAN_IMPL")) c->scan_impl = atoi(e) == 2 ? 2 : 3;
+    build_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, subk, c->d_prefilter, c->d_prefilter3,
+                                                                c->scan_stride, c->d_ht, P.ht_mask);
     LAUNCHED(1);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -233,6 +252,10 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
 
     CU(cudaFuncSetAttribute(sketch_fasta32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kScanSmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fasta3_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScan3SmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fasta3_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScan3SmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fasta3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScan3SmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fasta3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScan3SmemBytes));
 
     kssd_ctx_info_t &I = c->info;
     I.k = k; I.subk = subk; I.drlevel = drlevel; I.component_sz = component_sz;
@@ -258,6 +281,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
         b->release();
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
     cudaFree(c->d_prefilter);
+    cudaFree(c->d_prefilter3);
     cudaFree(c->d_ht);
     for (auto &e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -601,7 +625,12 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
             if (n_spans) {
-                sketch_fasta32_kernel<<<c->sm_count, kScanThreads, kScanSmemBytes, c->stream>>>(P, A);
+                const bool big = 2 * (P.TL - 1) >= 32;
+                if (c->scan_impl == 2) sketch_fasta32_kernel<<<c->sm_count, kScanThreads, kScanSmemBytes, c->stream>>>(P, A);
+                else if (c->scan_stride == 3 && big) sketch_fasta3_kernel<3, true><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+                else if (c->scan_stride == 3) sketch_fasta3_kernel<3, false><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+                else if (big) sketch_fasta3_kernel<1, true><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+                else sketch_fasta3_kernel<1, false><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
                 LAUNCHED(1);
             }
         } else {
