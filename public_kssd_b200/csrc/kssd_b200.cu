@@ -105,7 +105,7 @@ struct kssd_ctx {
     int scan_impl = 3;                           // KSSD_SCAN_IMPL=2 selects the previous formulation (A/B runs)
     uint2 *d_ht = nullptr;
     // scratch
-    DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, counts, minord, cubtmp, misc;
+    DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, runs, keep, counts, minord, cubtmp, misc;
     uint8_t *stag[2] = {nullptr, nullptr};       // pinned staging buffers of kssd_stage1_files
     uint64_t stag_cap[2] = {0, 0};
     // cached span plan of the last batch layout
@@ -276,7 +276,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->counts, &c->minord,
+    for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->runs, &c->keep, &c->counts, &c->minord,
                       &c->cubtmp, &c->misc})
         b->release();
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
@@ -323,34 +323,66 @@ struct kssd_sketch {
     std::vector<uint64_t> n_reads;               // KSSD_MODE_BYREAD: '>' records per file
 };
 
-// run heads of the sorted occurrence keys: multiplicity, first-occurrence offset, keep rule per mode
-__global__ void rle_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ ords, uint32_t n, int mode, int M,
-                           uint32_t *__restrict__ flags, uint16_t *__restrict__ counts, uint64_t *__restrict__ minord)
+// Post-pass over the sorted occurrence keys, run by run (a run = one distinct (component, genome, id)).  Nothing here
+// walks a run serially: a k-mer repeated a million times costs what a million distinct ones cost.
+//   run_heads_kernel    flags[i] = key i opens a run                      -> exclusive scan -> run number of every key
+//   run_reduce_kernel   first position of every run; first occurrence (min offset) by a segmented warp reduction
+//   run_keep_kernel     multiplicity = distance to the next run, keep rule per mode, per-genome distinct-key tally
+//   sketch_scatter_kernel  kept runs -> ids / abundances / first-occurrence offsets, per (component, genome) tally
+__global__ void run_heads_kernel(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i - 1] != keys[i]) ? 1u : 0u;
+}
+
+__global__ void run_reduce_kernel(const uint64_t *__restrict__ ords, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos, uint32_t n,
+                                  uint32_t *__restrict__ runstart, unsigned long long *__restrict__ minord)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    const uint32_t f = valid ? flags[i] : 0u;
+    const uint32_t r = valid ? pos[i] + f - 1u : 0xffffffffu;
+    unsigned long long v = valid ? ords[i] : ~0ull;
+    if (f) runstart[r] = i;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {      // segmented min: runs are contiguous, so equal run numbers o lanes apart bound a whole segment
+        const unsigned long long ov = __shfl_down_sync(kFull, v, o);
+        const uint32_t orr = __shfl_down_sync(kFull, r, o);
+        if (lane + o < 32 && orr == r && ov < v) v = ov;
+    }
+    const uint32_t pr = __shfl_up_sync(kFull, r, 1);
+    if (valid && (lane == 0 || pr != r)) atomicMin(&minord[r], v);
+}
+
+__global__ void run_keep_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos,
+                                const uint32_t *__restrict__ runstart, uint32_t n, int mode, int M, uint32_t *__restrict__ keep,
+                                uint16_t *__restrict__ counts, uint32_t *__restrict__ distinct_pg)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t key = keys[i];
-    if (i > 0 && keys[i - 1] == key) { flags[i] = 0; return; }
-    uint32_t cnt = 1;
-    uint64_t mo = ords[i];
-    for (uint32_t j = i + 1; j < n && keys[j] == key; j++) { cnt++; mo = min(mo, ords[j]); }
-    bool keep = true;
-    if (mode == KSSD_MODE_FASTA_UNIQ) keep = cnt == 1;          // iseq2comem.c:694-695 + :540
-    else if (mode == KSSD_MODE_FASTQ) keep = cnt >= (uint32_t)M; // iseq2comem.c:336-346 + :514
-    flags[i] = keep ? 1u : 0u;
-    counts[i] = (uint16_t)min(cnt, 65535u);                      // iseq2comem.c:602-604
-    minord[i] = mo;
+    const uint32_t nruns = pos[n - 1] + flags[n - 1];
+    if (i >= nruns) { keep[i] = 0; return; }
+    const uint32_t s = runstart[i], e = i + 1 < nruns ? runstart[i + 1] : n, cnt = e - s;
+    bool k = true;
+    if (mode == KSSD_MODE_FASTA_UNIQ) k = cnt == 1;          // iseq2comem.c:694-695 + :540
+    else if (mode == KSSD_MODE_FASTQ) k = cnt >= (uint32_t)M; // iseq2comem.c:336-346 + :514
+    keep[i] = k ? 1u : 0u;
+    counts[i] = (uint16_t)min(cnt, 65535u);                   // iseq2comem.c:602-604
+    atomicAdd(&distinct_pg[(uint32_t)(keys[s] >> 28) & 0x0fffffffu], 1u);   // every distinct key took a slot (keycount, :262 / :689)
 }
 
 __global__ void sketch_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos,
-                                      const uint16_t *__restrict__ counts, const uint64_t *__restrict__ minord, uint32_t n, int n_genomes,
+                                      const uint32_t *__restrict__ runstart, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ outpos,
+                                      const uint16_t *__restrict__ counts, const unsigned long long *__restrict__ minord, uint32_t n, int n_genomes,
                                       uint32_t *__restrict__ ids, uint16_t *__restrict__ abund, uint64_t *__restrict__ ord,
                                       uint32_t *__restrict__ per_cg)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !flags[i]) return;
-    const uint64_t key = keys[i];
-    const uint32_t p = pos[i];
+    if (i >= n) return;
+    const uint32_t nruns = pos[n - 1] + flags[n - 1];
+    if (i >= nruns || !keep[i]) return;
+    const uint64_t key = keys[runstart[i]];
+    const uint32_t p = outpos[i];
     ids[p] = (uint32_t)(key & 0x0fffffffu);
     abund[p] = counts[i];
     ord[p] = minord[i];
@@ -358,10 +390,10 @@ __global__ void sketch_scatter_kernel(const uint64_t *__restrict__ keys, const u
     atomicAdd(&per_cg[(uint64_t)comp * n_genomes + gid], 1u);
 }
 
-// total kept = pos[n-1] + flags[n-1], left in the slot after the per-(component, genome) counters
-__global__ void sketch_total_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos, uint32_t n, uint32_t *__restrict__ slot)
+// total kept = outpos[n-1] + keep[n-1], left in the slot after the per-(component, genome) counters
+__global__ void sketch_total_kernel(const uint32_t *__restrict__ keep, const uint32_t *__restrict__ outpos, uint32_t n, uint32_t *__restrict__ slot)
 {
-    *slot = pos[n - 1] + flags[n - 1];
+    *slot = outpos[n - 1] + keep[n - 1];
 }
 
 // FASTQ: per genome, index the lines (two streaming passes + a scan), then one thread per record
@@ -592,11 +624,11 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     uint8_t *pb = c->plan.as<uint8_t>();
     const size_t p_glen = 8ull * n_genomes, p_nom = p_glen + 8ull * n_genomes, p_sgid = p_nom + 8ull * n_spans;
 
-    // per-call device scratch: gstatus | ticket | out_count
-    const size_t m_stat = 0, m_tick = m_stat + 4ull * n_genomes, m_cnt = m_tick + 4, m_end = m_cnt + 4;
+    // per-call device scratch: gstatus | occurrences of code 0 dropped per genome | ticket | out_count
+    const size_t m_stat = 0, m_zero = m_stat + 4ull * n_genomes, m_tick = m_zero + 4ull * n_genomes, m_cnt = m_tick + 4, m_end = m_cnt + 4;
     CU(c->meta.ensure(m_end));
     uint8_t *mb = c->meta.as<uint8_t>();
-    CU(cudaMemsetAsync(mb + m_stat, 0, 4ull * n_genomes + 8, c->stream));
+    CU(cudaMemsetAsync(mb + m_stat, 0, m_end, c->stream));
 
     // occurrence buffer: expected total/|sampling| ; 4x head-room, retried on overflow
     const double rate = (double)c->info.n_sampled / (double)(1ull << (4 * P.s));
@@ -616,12 +648,13 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         A.span_gid = reinterpret_cast<uint32_t *>(pb + p_sgid);
         A.n_spans = n_spans;
         A.gstatus = reinterpret_cast<int32_t *>(mb + m_stat);
+        A.zero_count = reinterpret_cast<uint32_t *>(mb + m_zero);
         A.ticket = reinterpret_cast<uint32_t *>(mb + m_tick);
         A.out_count = reinterpret_cast<uint32_t *>(mb + m_cnt);
         A.out_keys = c->keys.as<uint64_t>(); A.out_ords = c->ords.as<uint64_t>();
         A.out_cap = (uint32_t)cap;
         A.drop_zero = (is_fastq || mode == KSSD_MODE_BYREAD) ? 0 : 1;      // only fasta2co's hash table loses code 0
-        CU(cudaMemsetAsync(mb + m_tick, 0, 8, c->stream));
+        CU(cudaMemsetAsync(mb + m_zero, 0, m_end - m_zero, c->stream));
         CU(cudaEventRecord(c->ev[0], c->stream));
         if (!is_fastq) {
             if (n_spans) {
@@ -660,7 +693,10 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     S->status.assign(n_genomes, 0);
     S->comp_start.assign(n_comp + 1, 0);
     S->index.assign((size_t)n_comp * (n_genomes + 1), 0);
-    std::vector<uint32_t> per_cg((size_t)n_comp * n_genomes + 1, 0);   // [n_comp*n_genomes] = kept total
+    // per_cg: kept ids per (component, genome) | kept total | distinct keys per genome (before the keep rule)
+    const size_t cg_total = (size_t)n_comp * n_genomes, cg_distinct = cg_total + 1;
+    std::vector<uint32_t> per_cg(cg_distinct + n_genomes, 0);
+    std::vector<uint32_t> zeros(n_genomes, 0);
     // one stream-ordered allocation holds ids | ord | abund | index for the life of the handle
     const size_t nmax = std::max<size_t>(n_occ, 1);
     const size_t o_ids = 0, o_ord = (nmax * 4 + 15) & ~(size_t)15, o_ab = o_ord + nmax * 8, o_idx = (o_ab + nmax * 2 + 15) & ~(size_t)15;
@@ -687,31 +723,39 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
         LAUNCHED(8);
         CU(c->flags.ensure((size_t)n_occ * 4));
         CU(c->pos.ensure((size_t)n_occ * 4));
+        CU(c->runs.ensure((size_t)n_occ * 4));
+        CU(c->keep.ensure((size_t)n_occ * 8));          // keep flags | their exclusive scan
         CU(c->counts.ensure((size_t)n_occ * 2));
         CU(c->minord.ensure((size_t)n_occ * 8));
+        uint32_t *d_keep = c->keep.as<uint32_t>(), *d_outpos = d_keep + n_occ;
         const uint32_t nb = (n_occ + 255) / 256;
-        rle_kernel<<<nb, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->ords2.as<uint64_t>(), n_occ, mode, opts ? opts->M : 1,
-                                              c->flags.as<uint32_t>(), c->counts.as<uint16_t>(), c->minord.as<uint64_t>());
-        LAUNCHED(1);
         size_t tmp2 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ, c->stream);
         CU(c->cubtmp.ensure(tmp2));
-        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp2, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ, c->stream));
-        LAUNCHED(2);
         CU(c->misc.ensure(per_cg.size() * 4));
         CU(cudaMemsetAsync(c->misc.p, 0, per_cg.size() * 4, c->stream));
+        CU(cudaMemsetAsync(c->minord.p, 0xff, (size_t)n_occ * 8, c->stream));
+        run_heads_kernel<<<nb, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), n_occ, c->flags.as<uint32_t>());
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp2, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ, c->stream));
+        run_reduce_kernel<<<nb, 256, 0, c->stream>>>(c->ords2.as<uint64_t>(), c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ,
+                                                     c->runs.as<uint32_t>(), c->minord.as<unsigned long long>());
+        run_keep_kernel<<<nb, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), c->runs.as<uint32_t>(),
+                                                   n_occ, mode, opts ? opts->M : 1, d_keep, c->counts.as<uint16_t>(),
+                                                   c->misc.as<uint32_t>() + cg_distinct);
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp2, d_keep, d_outpos, n_occ, c->stream));
         sketch_scatter_kernel<<<nb, 256, 0, c->stream>>>(c->keys2.as<uint64_t>(), c->flags.as<uint32_t>(), c->pos.as<uint32_t>(),
-                                                         c->counts.as<uint16_t>(), c->minord.as<uint64_t>(), n_occ, n_genomes, S->d_ids,
-                                                         S->d_abund, S->d_ord, c->misc.as<uint32_t>());
-        sketch_total_kernel<<<1, 1, 0, c->stream>>>(c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n_occ,
-                                                    c->misc.as<uint32_t>() + (size_t)n_comp * n_genomes);
-        LAUNCHED(2);
+                                                         c->runs.as<uint32_t>(), d_keep, d_outpos, c->counts.as<uint16_t>(),
+                                                         c->minord.as<unsigned long long>(), n_occ, n_genomes, S->d_ids, S->d_abund, S->d_ord,
+                                                         c->misc.as<uint32_t>());
+        sketch_total_kernel<<<1, 1, 0, c->stream>>>(d_keep, d_outpos, n_occ, c->misc.as<uint32_t>() + cg_total);
+        LAUNCHED(9);
         CU(cudaMemcpyAsync(per_cg.data(), c->misc.p, per_cg.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaMemcpyAsync(S->status.data(), mb + m_stat, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(zeros.data(), mb + m_zero, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
-    S->total = per_cg[(size_t)n_comp * n_genomes];
+    S->total = per_cg[cg_total];
     // per-component combco.index (command_dist.c:331-354) and reference error conditions
     std::vector<uint64_t> per_genome(n_genomes, 0);
     uint64_t run = 0;
@@ -730,7 +774,10 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     for (int g = 0; g < n_genomes; g++) {
         if (S->status[g] & 1) S->status[g] = KSSD_E_HEADER_EOF;
         else if (S->status[g] & 2) S->status[g] = KSSD_E_LONGLINE;
-        else if (mode != KSSD_MODE_FASTQ && per_genome[g] > c->info.hashlimit) S->status[g] = KSSD_E_CROWD;   // fastq2co never counts keys (iseq2comem.c:338)
+        // "the context space is too crowd": the reference counts every slot it takes -- every distinct key, kept later or
+        // not, and in the FASTA modes once more for every occurrence of code 0, whose slot never looks taken
+        // (iseq2comem.c:258-263, :685-691; -A: :595-599); fastq2co never counts (:338)
+        else if (mode != KSSD_MODE_FASTQ && (uint64_t)per_cg[cg_distinct + g] + zeros[g] > c->info.hashlimit) S->status[g] = KSSD_E_CROWD;
         else S->status[g] = 0;
     }
     CU(cudaMemcpyAsync(S->d_index, S->index.data(), S->index.size() * 8, cudaMemcpyHostToDevice, c->stream));

@@ -55,6 +55,7 @@ struct ScanArgs {
     uint32_t out_cap;
     uint32_t *out_count;
     int32_t *gstatus;            // per genome flags (bit 0: header ran into EOF)
+    uint32_t *zero_count;        // per genome: occurrences of code 0 dropped by the FASTA quirk (they still count as keys)
     int drop_zero;               // FASTA quirk: drtuple == 0 is never stored (iseq2comem.c:258)
 };
 
@@ -204,7 +205,7 @@ __device__ __forceinline__ void resolve_candidates(const SketchParams &P, const 
         }
         if (found) {
             const uint64_t dr = (((u & P.undomask) + ((u & P.outmask) << (4 * P.s))) >> (4 * P.L)) + pf;
-            if (A.drop_zero && dr == 0) found = false;
+            if (A.drop_zero && dr == 0) { found = false; atomicAdd(&A.zero_count[gid], 1u); }
             key = ((dr & P.comp_mask) << 56) | ((uint64_t)gid << 28) | (dr >> P.comp_code_bits);
         }
     }

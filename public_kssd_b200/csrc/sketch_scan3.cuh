@@ -118,10 +118,10 @@ __device__ __forceinline__ void resolve3(const SketchParams &P, const ScanArgs &
         }
         if (found) {
             const uint64_t dr = (((u & P.undomask) + ((u & P.outmask) << (4 * P.s))) >> (4 * P.L)) + pf;
-            if (A.drop_zero && dr == 0) found = false;
             key = ((dr & P.comp_mask) << 56) | ((uint64_t)gid << 28) | (dr >> P.comp_code_bits);
+            found = verify_window(A.seq, gs, gs + ordv, P.TL);
+            if (found && A.drop_zero && dr == 0) { found = false; atomicAdd(&A.zero_count[gid], 1u); }
         }
-        if (found) found = verify_window(A.seq, gs, gs + ordv, P.TL);
     }
     const uint32_t fm = __ballot_sync(kFull, found);
     if (fm) {

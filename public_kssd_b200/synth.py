@@ -227,3 +227,66 @@ def synth_sketches(n_genomes: int, codes_per_genome: int, seed: int, code_bits: 
     index = np.zeros(n_genomes + 1, dtype=np.uint64)
     np.cumsum(np.asarray(counts, dtype=np.uint64), out=index[1:])
     return np.concatenate(chunks).astype(np.uint32), index
+
+
+def make_shuf_table_affine(subk: int, seed: int) -> np.ndarray:
+    """A permutation of 0..16^subk-1 built from bijective steps (odd multiply, xor-shift, add) instead of an argsort:
+    seconds for the 1 GiB subk = 7 table of `-L 4 -k 10` (reference auto rule, command_shuffle.c:154-160).  The
+    reference accepts any permutation as .shuf payload."""
+    bits = 4 * subk
+    mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
+    a = np.uint32(((0x9E3779B1 + 2 * seed * 0x632BE5AB) | 1) & 0xFFFFFFFF)
+    b = np.uint32((0x85EBCA6B * (seed + 1)) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = np.arange(1 << bits, dtype=np.uint32)
+        x = (x * a) & mask
+        x ^= x >> np.uint32(bits // 2 + 1)
+        x = (x * np.uint32(0xC2B2AE3D | 1)) & mask
+        x ^= x >> np.uint32(bits // 3 + 1)
+        x = (x + b) & mask
+    return x.view(np.int32)
+
+
+def contig_genome(nbases: int, seed: int, contig_len: int = 100_000, width: int = 60, n_frac: float = 0.01,
+                  lower_frac: float = 0.2, crlf: bool = False) -> np.ndarray:
+    """BASELINE configs[3]-shaped FASTA text, vectorised: many contigs (lengths spread around contig_len, one header
+    each), runs of N summing to ~n_frac of the bases (run lengths 1 .. 5000), soft-masked (lower-case) stretches,
+    fixed-width lines."""
+    bases = random_bases(nbases, seed)
+    txt = _ACGT[bases].copy()
+    r = _stream(seed, nbases // 512 + 16, salt=31)
+    if lower_frac > 0:                                    # soft-masked blocks of 512 bases
+        blk = ((r[: (nbases + 511) // 512] >> np.uint64(20)).astype(np.float64) * (1.0 / (1 << 44))) < lower_frac
+        m = np.repeat(blk, 512)[:nbases]
+        txt[m] |= 0x20
+    target, done, i = int(nbases * n_frac), 0, 0
+    rn = _stream(seed, 4096, salt=32)
+    while done < target and i + 1 < rn.size:
+        ln = 1 + int(rn[i] % np.uint64(5000)) if (int(rn[i]) >> 40) & 3 else 1 + int(rn[i] % np.uint64(40))
+        st = int(rn[i + 1] % np.uint64(max(nbases - ln, 1)))
+        txt[st:st + ln] = ord("N") if (int(rn[i]) >> 50) & 1 else ord("n")
+        done += ln
+        i += 2
+    parts, pos, c = [], 0, 0
+    rc = _stream(seed, nbases // max(contig_len // 4, 1) + 8, salt=33)
+    eol = np.frombuffer(b"\r\n" if crlf else b"\n", dtype=np.uint8)
+    while pos < nbases:
+        ln = int(contig_len // 4 + rc[c] % np.uint64(max(contig_len * 3 // 2, 1)))
+        ln = min(ln, nbases - pos)
+        seg = txt[pos:pos + ln]
+        full = ln // width
+        body = np.empty(ln + ((ln + width - 1) // width) * eol.size, dtype=np.uint8)
+        if full:
+            v = body[: full * (width + eol.size)].reshape(full, width + eol.size)
+            v[:, :width] = seg[: full * width].reshape(full, width)
+            v[:, width:] = eol
+        rem = ln - full * width
+        if rem:
+            t = body[full * (width + eol.size):]
+            t[:rem] = seg[full * width:]
+            t[rem:] = eol
+        parts.append(np.frombuffer(b">ctg%06d len=%d ACGTACGTTGCATGCATGCAAGCT\n" % (c, ln), dtype=np.uint8))
+        parts.append(body)
+        pos += ln
+        c += 1
+    return np.concatenate(parts)
