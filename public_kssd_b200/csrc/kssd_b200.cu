@@ -100,7 +100,8 @@ struct kssd_ctx {
     SketchParams P{};
     kssd_ctx_info_t info{};
     uint32_t *d_prefilter = nullptr;
-    uint32_t *d_prefilter3 = nullptr;            // block bitmap + second level of the lazy scan (sketch_scan3.cuh)
+    uint32_t *d_prefilter3 = nullptr;            // block bitmap of the lazy scan (sketch_scan3.cuh)
+    unsigned long long *d_gtab = nullptr;        // its second level: per block, the members among the three windows around it
     int scan_stride = 3;                         // bases per first-level probe of that scan (3 when 2*subk >= 12, else 1)
     int scan_impl = 3;                           // KSSD_SCAN_IMPL=2 selects the previous formulation (A/B runs)
     uint2 *d_ht = nullptr;
@@ -133,8 +134,8 @@ __global__ void count_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t 
 
 // S = {d : shuf[d] < dim_end}: exact hash table d -> pf, and the prefilter bitmap of S u RC(S)
 __global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t n, uint32_t dim_end, int s,
-                                     uint32_t *__restrict__ prefilter, uint32_t *__restrict__ prefilter3, int stride, uint2 *__restrict__ ht,
-                                     uint32_t ht_mask)
+                                     uint32_t *__restrict__ prefilter, uint32_t *__restrict__ prefilter3, unsigned long long *__restrict__ gtab,
+                                     int stride, uint2 *__restrict__ ht, uint32_t ht_mask)
 {
     const int wbits = 4 * s;                                   // width of the inner 2s-mer
     const uint32_t reps = wbits < kPfBitShift + 5 ? 1u << (kPfBitShift + 5 - wbits) : 1u;
@@ -154,15 +155,14 @@ __global__ void build_sampled_kernel(const int32_t *__restrict__ shuf, uint32_t 
             const uint32_t i2 = pf2_index(both[k]);
             atomicOr(&prefilter[kPfWords + (i2 >> 5)], 1u << (i2 & 31));
             // lazy scan (sketch_scan3.cuh): the window in the scan representation; its 10-base blocks at offsets
-            // 0 .. stride-1 (word = bits 0-14, flag = 0x80000000 >> bits 15-19), and the hashed whole window
+            // 0 .. stride-1 (word = bits 0-14, flag = 0x80000000 >> bits 15-19), and per block and offset the folded rest
             const uint32_t y = (uint32_t)to_scan_repr(both[k], 2 * s);
             for (int r = 0; r < stride; r++)
                 for (uint32_t hi = 0; hi < reps3; hi++) {
                     const uint32_t b = ((y >> (2 * r)) | (hi << wbits)) & 0xfffffu;
                     atomicOr(&prefilter3[b & 0x7fffu], 0x80000000u >> (b >> 15));
+                    if (gtab) atomicOr(&gtab[b], 1ull << (16 * r + gtab_ext(y, r)));
                 }
-            const uint32_t i3 = pf3b_index(y);
-            atomicOr(&prefilter3[kPf3Words + (i3 >> 5)], 1u << (i3 & 31));
         }
         uint32_t h = mix32(d) & ht_mask;
         for (;;) {
@@ -236,12 +236,16 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     CU(cudaMalloc(&c->d_ht, (size_t)ht_size * sizeof(uint2)));
     CU(cudaMemsetAsync(c->d_prefilter, 0, (kPfWords + kPf2Words) * 4, c->stream));
     CU(cudaMemsetAsync(c->d_ht, 0xff, (size_t)ht_size * sizeof(uint2), c->stream));
-    CU(cudaMalloc(&c->d_prefilter3, (kPf3Words + kPf3bWords) * 4));
-    CU(cudaMemsetAsync(c->d_prefilter3, 0, (kPf3Words + kPf3bWords) * 4, c->stream));
+    CU(cudaMalloc(&c->d_prefilter3, kPf3Words * 4));
+    CU(cudaMemsetAsync(c->d_prefilter3, 0, kPf3Words * 4, c->stream));
     c->scan_stride = 2 * subk >= 12 ? 3 : 1;
+    if (c->scan_stride == 3) {
+        CU(cudaMalloc(&c->d_gtab, (size_t)kGtabEntries * 8));
+        CU(cudaMemsetAsync(c->d_gtab, 0, (size_t)kGtabEntries * 8, c->stream));
+    }
     if (const char *e = getenv("KSSD_SCAN_IMPL")) c->scan_impl = atoi(e) == 2 ? 2 : 3;
     build_sampled_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_shuf, n, P.dim_end, subk, c->d_prefilter, c->d_prefilter3,
-                                                                c->scan_stride, c->d_ht, P.ht_mask);
+                                                                c->d_gtab, c->scan_stride, c->d_ht, P.ht_mask);
     LAUNCHED(1);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -249,6 +253,7 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     cudaFree(d_cnt);
     P.prefilter = c->d_prefilter;
     P.ht = c->d_ht;
+    P.gtab = c->d_gtab;
 
     CU(cudaFuncSetAttribute(sketch_fasta32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kScanSmemBytes));
@@ -282,6 +287,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
     cudaFree(c->d_prefilter);
     cudaFree(c->d_prefilter3);
+    cudaFree(c->d_gtab);
     cudaFree(c->d_ht);
     for (auto &e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);

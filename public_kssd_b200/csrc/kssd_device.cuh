@@ -47,6 +47,7 @@ struct SketchParams {
     uint32_t ht_mask;    // sampled-set hash table size - 1
     const uint32_t *prefilter;  // kPfWords words (global copy), then kPf2Words words of the second level
     const uint2 *ht;            // {inner, pf}
+    const unsigned long long *gtab;   // lazy scan, 2s >= 12: per 10-base block, members among the three windows around it (else null)
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

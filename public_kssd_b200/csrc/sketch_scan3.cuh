@@ -19,9 +19,11 @@
 //  * GROUP PREFILTER.  Every window of 2s >= 12 bases (the central 2s-mer that decides sampling) contains exactly one
 //    10-base block that starts at a multiple of three bases, so ONE probe of a 2^20-bit shared-memory bitmap, holding
 //    the blocks at offsets 0, 1, 2 of every member of S u RC(S) (24 576 entries, 2.3 % full), stands for three windows:
-//    12 probes per 32 bases instead of 32.  Lanes with a block hit park in a per-warp queue and are expanded to their
-//    three windows 32 lanes at a time against a second-level filter (2^18 bits on a hash of the whole window).
-//    For 2s < 12 (subk <= 5) the same code runs with one probe per window.
+//    12 probes per 32 bases instead of 32.  Lanes with a block hit park in a per-warp queue; 32 lanes at a time, each
+//    block hit is settled by ONE 8-byte read of an L2-resident table indexed by the block (8 MiB): per offset the
+//    sixteen possible values of the window's remaining bases, i.e. exact membership of the three windows (for 2s = 14 the
+//    remaining 8 bits are folded to 4).  For 2s < 12 (subk <= 5) the same code runs with one probe per window and the
+//    bitmap itself is exact.
 //
 //  * Bases are packed OLDEST-LOWEST with raw codes: the multiply that gathers a word's four codes needs no prior shift
 //    in that order, and S u RC(S) is closed under the change of representation at table-build time.  The exact
@@ -35,11 +37,15 @@
 
 namespace kssd {
 
-constexpr uint32_t kPf3Words = 1u << 15;        // first level: 2^20 bits on a 10-base block
-constexpr int kPf3bBits = 18;                   // second level: 2^18 bits on a hash of the whole window
-constexpr uint32_t kPf3bWords = 1u << (kPf3bBits - 5);
+constexpr uint32_t kPf3Words = 1u << 15;        // first level: 2^20 bits on a 10-base block (shared memory)
+constexpr uint32_t kGtabEntries = 1u << 20;     // second level: per block, 3 offsets x 16 values of the rest of the window (global, L2)
 
-__host__ __device__ __forceinline__ uint32_t pf3b_index(uint32_t win) { return (win * 0x9E3779B1u) >> (32 - kPf3bBits); }
+// window (4s bits, scan representation) at block offset r: the bits outside the 10-base block, folded to 4
+__host__ __device__ __forceinline__ uint32_t gtab_ext(uint32_t win, int r)
+{
+    const uint32_t x = (win & ((1u << (2 * r)) - 1u)) | ((win >> (2 * r + 20)) << (2 * r));
+    return (x ^ (x >> 4)) & 15u;
+}
 
 // reverse the order of the low nb 2-bit groups of x (1 <= nb <= 32)
 __host__ __device__ __forceinline__ uint64_t rev_groups64(uint64_t x, int nb)
@@ -65,16 +71,18 @@ struct LaneQ3 {
     uint32_t y[4][kQueueCap];
     uint32_t flags[kQueueCap], wmask[kQueueCap], cand[kQueueCap], off[kQueueCap];
 };
-constexpr size_t kScan3SmemBytes = (size_t)(kPf3Words + kPf3bWords) * 4 + (size_t)kScanWarps * (sizeof(WarpQueue) + sizeof(LaneQ3));
+// candidates on their way to the exact resolver: the k-mer (scan representation), lane offset | own-base number, the lane's skip flags
+struct WarpQ3 { uint32_t lo[kQueueCap], hi[kQueueCap], ord[kQueueCap], f[kQueueCap]; };
+constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3));
 
 __device__ __forceinline__ bool pf3_probe(const uint32_t *__restrict__ pf, uint32_t v)
 {
     return (__funnelshift_l(0u, pf[v & 0x7fffu], v >> 15) >> 31) != 0u;
 }
-__device__ __forceinline__ bool pf3b_probe(const uint32_t *__restrict__ pf, uint32_t win)
+// second level for one window whose block sits at offset 0 (the general path): exact for 2s = 12
+__device__ __forceinline__ bool gtab_probe0(const unsigned long long *__restrict__ gtab, uint32_t win)
 {
-    const uint32_t i = pf3b_index(win);
-    return (pf[kPf3Words + (i >> 5)] >> (i & 31)) & 1u;
+    return (__ldg(&gtab[win & 0xfffffu]) >> gtab_ext(win, 0)) & 1ull;
 }
 
 // The text itself decides: walking back from the window's last base, 2k letters of ACGTacgt with nothing but '\n' and
@@ -93,16 +101,19 @@ __device__ __forceinline__ bool verify_window(const uint8_t *__restrict__ seq, u
     }
 }
 
-// exact resolution of queued candidates (scan representation), up to 32 at a time
-__device__ __forceinline__ void resolve3(const SketchParams &P, const ScanArgs &A, WarpQueue &q, uint32_t first, uint32_t m, uint32_t gid,
-                                         uint64_t ord_base, uint64_t gs)
+// exact resolution of queued candidates (scan representation), up to 32 at a time.  Out of line: three call sites,
+// a few thousand calls per launch -- the clean loop should not carry this code in its instruction-cache footprint.
+__device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, const WarpQ3 &q, uint32_t first, uint32_t m, uint32_t gid,
+                                      uint64_t ord_base, uint64_t gs)
 {
     const uint32_t lane = lane_id();
     bool found = false;
     uint64_t key = 0, ordv = 0;
     if (lane < m) {
         const uint64_t y = ((uint64_t)q.hi[first + lane] << 32) | q.lo[first + lane];
-        ordv = ord_base + q.ord[first + lane];
+        // byte of the occurrence's last base: the lane's offset plus the (j+1)-th byte of the lane without a skip flag
+        const uint32_t o = q.ord[first + lane];
+        ordv = ord_base + (o & ~31u) + __fns(~q.f[first + lane], 0, (int)(o & 31u) + 1);
         const uint64_t yf = y ^ ((y >> 1) & 0x5555555555555555ull);       // raw -> A0 C1 G2 T3
         const uint64_t fwd = rev_groups64(yf, P.TL);                      // the reference's tuple (newest base lowest)
         const uint64_t rc = ~yf & P.tupmask;                              // its crvstuple: complement, oldest base lowest
@@ -135,9 +146,10 @@ __device__ __forceinline__ void resolve3(const SketchParams &P, const ScanArgs &
     }
 }
 
-// append the lanes flagged `has` to the warp's candidate queue; resolve when 32 are waiting
-__device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArgs &A, WarpQueue &q, uint32_t &qn, bool has, uint64_t kmer,
-                                            uint32_t ord, uint32_t gid, uint64_t ord_base, uint64_t gs)
+// append the lanes flagged `has` to the warp's candidate queue; resolve when 32 are waiting.
+// ord = 32-byte-aligned lane offset | own-base number j, f = the lane's skip flags (general path: exact offset, f = 0).
+__device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, bool has, uint64_t kmer,
+                                            uint32_t ord, uint32_t f, uint32_t gid, uint64_t ord_base, uint64_t gs)
 {
     const uint32_t pm = __ballot_sync(kFull, has);
     if (!pm) return;
@@ -146,6 +158,7 @@ __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArg
         q.lo[slot] = (uint32_t)kmer;
         q.hi[slot] = (uint32_t)(kmer >> 32);
         q.ord[slot] = ord;
+        q.f[slot] = f;
     }
     qn += __popc(pm);
     __syncwarp();
@@ -156,51 +169,63 @@ __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArg
     }
 }
 
-// Parked lanes first .. first+m-1, one per lane: block hits -> windows -> second-level filter -> candidate queue.
-// ST = bases per first-level probe (3: a block hit stands for the windows 3i-2 .. 3i; 1: one window per probe).
+// Parked lanes first .. first+m-1, one per lane.  ST = 3: every block hit i (windows 3i-2 .. 3i) is settled by one read
+// of the block's table entry; ST = 1: the bitmap was exact, every hit is a member.  Members go to the candidate queue.
 template <int ST>
-__device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q, uint32_t &qn,
-                                       const LaneQ3 &lq, uint32_t first, uint32_t m, uint32_t gid, uint64_t ord_base, uint64_t gs)
+__device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, const LaneQ3 &lq, uint32_t first,
+                                       uint32_t m, uint32_t gid, uint64_t ord_base, uint64_t gs)
 {
     const uint32_t lane = lane_id();
     const uint32_t e = first + (lane < m ? lane : 0u);
-    uint32_t wc = 0, F = 0, off = 0;
-    if (lane < m) {
-        const uint32_t cand = lq.cand[e];
-        F = lq.flags[e];
-        off = lq.off[e];
-        if (ST == 1) wc = cand;
-        else
-            for (uint32_t c = cand; c; c &= c - 1) wc |= (uint32_t)((7ull << (3 * (__ffs(c) - 1))) >> 2);
-        wc &= lq.wmask[e];
-    }
+    uint32_t cand = 0, wm = 0, F = 0, off = 0;
+    if (lane < m) { cand = lq.cand[e]; wm = lq.wmask[e]; F = lq.flags[e]; off = lq.off[e]; }
+    if (ST == 1) cand &= wm;
     const uint32_t *ye = &lq.y[0][e];                     // word a of the entry: ye[a * kQueueCap]
-    while (__any_sync(kFull, wc != 0)) {
-        bool has = wc != 0;
-        int j = 0;
-        uint64_t kmer = 0;
-        if (has) {
-            j = __ffs(wc) - 1;
-            wc &= wc - 1;
-            // central window of the k-mer that ends at own base j: Y bits [2 (out + j), + 4s)
-            const uint32_t o = 2u * (uint32_t)(P.out + j), a = o >> 5;
-            const uint32_t w0 = ye[a * kQueueCap], w1 = a < 3 ? ye[(a + 1) * kQueueCap] : 0u;
-            has = pf3b_probe(pf, __funnelshift_r(w0, w1, o) & P.innermask);
+    while (__any_sync(kFull, cand != 0)) {
+        uint32_t hits = 0;                                // ST = 3: bit r <-> window 3i - r is a member
+        int i = 0;
+        if (cand) {
+            i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (ST == 1) hits = 1u;
+            else {
+                // S = the 16 bases from X position 3i-2 on: the three windows start at its bases 2, 1, 0
+                const int o = 2 * (P.out + 3 * i) - 4;
+                uint32_t S;
+                if (o >= 0) {
+                    const uint32_t a = (uint32_t)o >> 5;
+                    S = __funnelshift_r(ye[a * kQueueCap], a < 3 ? ye[(a + 1) * kQueueCap] : 0u, (uint32_t)o);
+                } else S = ye[0] << (-o);
+                const unsigned long long mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]);
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const int j = 3 * i - r;
+                    const uint32_t ee = gtab_ext((S >> (2 * (2 - r))) & P.innermask, r);
+                    if (j >= 0 && j < 32 && ((wm >> j) & 1u) && ((mm >> (16 * r + ee)) & 1ull)) hits |= 1u << r;
+                }
+            }
         }
-        if (has) {                                        // the k-mer itself: Y bits [2j, 2j + 4k)
-            const uint32_t a = (2u * j) >> 5;             // 0 or 1
-            const uint32_t w0 = ye[a * kQueueCap], w1 = ye[(a + 1) * kQueueCap], w2 = ye[(a + 2) * kQueueCap];
-            kmer = ((((uint64_t)__funnelshift_r(w1, w2, 2u * j)) << 32) | __funnelshift_r(w0, w1, 2u * j)) & P.tupmask;
+        while (__any_sync(kFull, hits != 0)) {
+            const bool has = hits != 0;
+            uint32_t j = 0;
+            uint64_t kmer = 0;
+            if (has) {
+                const int r = __ffs(hits) - 1;
+                hits &= hits - 1;
+                j = (uint32_t)(ST == 1 ? i : 3 * i - r);
+                const uint32_t a = (2u * j) >> 5;         // 0 or 1: the k-mer is Y bits [2j, 2j + 4k)
+                const uint32_t w0 = ye[a * kQueueCap], w1 = ye[(a + 1) * kQueueCap], w2 = ye[(a + 2) * kQueueCap];
+                kmer = ((((uint64_t)__funnelshift_r(w1, w2, 2u * j)) << 32) | __funnelshift_r(w0, w1, 2u * j)) & P.tupmask;
+            }
+            queue_push3(P, A, q, qn, has, kmer, off | j, F, gid, ord_base, gs);
         }
-        // byte of the lane that holds own base j: the (j+1)-th byte without a skip flag
-        queue_push3(P, A, q, qn, has, kmer, off + (has ? __fns(~F, 0, j + 1) : 0u), gid, ord_base, gs);
     }
 }
 
 // One 512-byte GENERAL iteration (16 bytes per lane): headers, N, IUPAC, anything -- exact per byte.  `cur` is already
 // masked to the span / genome extent.  Same state machine as general_iter16 (sketch_scan.cuh); the k-mer rolls in the
 // scan representation and hits go straight to the candidate queue.
-__device__ __noinline__ void general_iter3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q, uint32_t &qn,
+__device__ __noinline__ void general_iter3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, uint32_t &qn,
                                            StreamState &st, uint4 cur, uint64_t cbase, uint64_t end, bool past_end, uint32_t lane_off,
                                            uint32_t gid, uint64_t ord_base, uint64_t gs)
 {
@@ -292,10 +317,10 @@ __device__ __noinline__ void general_iter3(const SketchParams &P, const ScanArgs
             ae += (gem >> i) & 1u;
             if (run >= (uint32_t)TL && ae <= (uint32_t)(TL - 1)) {
                 const uint32_t v = (uint32_t)(fr >> (2 * P.out));
-                if (pf3_probe(pf, v)) hit = pf3b_probe(pf, v & P.innermask);
+                if (pf3_probe(pf, v)) hit = P.gtab ? gtab_probe0(P.gtab, v & P.innermask) : true;
             }
         } else if ((BRK >> i) & 1u) run = 0;
-        queue_push3(P, A, q, qn, hit, fr, lane_off + i, gid, ord_base, gs);
+        queue_push3(P, A, q, qn, hit, fr, lane_off + i, 0u, gid, ord_base, gs);
     }
     // warp carry = inclusive value of lane 31 on top of the old carry
     const uint64_t sb31 = shfl64(sb, 31);
@@ -325,7 +350,7 @@ __device__ __forceinline__ uint32_t top_bytes4(uint32_t a, uint32_t b, uint32_t 
 
 // ST: bases per first-level probe (3 or 1); BIG: 2k-1 history bases need more than 32 bits (k >= 9)
 template <int ST, bool BIG>
-__device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQueue &q, LaneQ3 &lq, uint32_t gid,
+__device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, LaneQ3 &lq, uint32_t gid,
                            uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
 {
     constexpr int NPROBE = ST == 3 ? 12 : 32;
@@ -343,17 +368,13 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     const uint64_t full = (lim - chunk0) >> 10;
     const uint32_t n_steady = full > 1 ? (uint32_t)(full - 1 < 0x3fffffffull ? full - 1 : 0x3fffffffull) : 0u;
     const uint8_t *lp = A.seq + chunk0 + 32 * lane;
-    Bytes32 nxt = load_chunk32_guarded(A, chunk0 + 32 * lane);
+    Bytes32 cur = load_chunk32_guarded(A, chunk0 + 32 * lane);
     bool at_eof = false;
 
     for (uint32_t it = 0;; it++) {
-        Bytes32 cur = nxt;
         const bool steady = (it - 1u) < n_steady;
         const uint64_t cbase = chunk0 + ((uint64_t)it << 10);
         const uint32_t lane_off = (it << 10) + 32 * lane;
-        if (it < n_steady) nxt = ldg_stream256(lp + 1024);
-        else if (cbase + 1024 < ge) nxt = load_chunk32_guarded(A, cbase + 1024 + 32 * lane);
-        lp += 1024;
 
         bool past_end = false, cut_lane = false;
         if (!steady) {
@@ -366,20 +387,31 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             cut_lane = laddr < start || laddr + 32 > ge;
         }
 
-        uint32_t dacc = 0, c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
-        classify_lazy8(cur.lo.x, cur.lo.y, dacc, c0, c1, g0);
-        classify_lazy8(cur.lo.z, cur.lo.w, dacc, c2, c3, g1);
-        classify_lazy8(cur.hi.x, cur.hi.y, dacc, c4, c5, g2);
-        classify_lazy8(cur.hi.z, cur.hi.w, dacc, c6, c7, g3);
-        const uint32_t F = top_bytes4(g0, g1, g2, g3);            // bit b: byte b of the lane is skipped
+        uint32_t dacc = 0, PA, PB, F;
+        {
+            uint32_t c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
+            classify_lazy8(cur.lo.x, cur.lo.y, dacc, c0, c1, g0);
+            classify_lazy8(cur.lo.z, cur.lo.w, dacc, c2, c3, g1);
+            classify_lazy8(cur.hi.x, cur.hi.y, dacc, c4, c5, g2);
+            classify_lazy8(cur.hi.z, cur.hi.w, dacc, c6, c7, g3);
+            F = top_bytes4(g0, g1, g2, g3);                       // bit b: byte b of the lane is skipped
+            PA = top_bytes4(c0, c1, c2, c3);
+            PB = top_bytes4(c4, c5, c6, c7);
+        }
+        // the 32 bytes are now three words: request the next KiB into the same registers (one buffer, no copies); the
+        // rest of the iteration and the other warps cover its latency.  A dirty iteration re-reads its text itself.
+        if (it < n_steady) cur = ldg_stream256(lp + 1024);
+        else if (cbase + 1024 < ge) cur = load_chunk32_guarded(A, cbase + 1024 + 32 * lane);
+        lp += 1024;
         const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
         const bool lane_ok = dacc == 0 && (n >= (uint32_t)(TL - 1) || cut_lane);
         const bool clean = __all_sync(kFull, lane_ok) && !hdr;
 
         if (clean) {
-            uint32_t PA = top_bytes4(c0, c1, c2, c3), PB = top_bytes4(c4, c5, c6, c7);
             {
                 uint32_t fa = F & 0xffffu, fb = F >> 16;
+                if (fa == 0xffffu) { fa = 0; PA = 0; }           // a half masked out whole (span start, genome end)
+                if (fb == 0xffffu) { fb = 0; PB = 0; }
                 for (;;) {      // squeeze the skipped bytes out of both halves; first round is branch-free
                     const uint32_t ia = fa & (0u - fa), ib = fb & (0u - fb);
                     const uint32_t la = ia * ia - 1u, lb = ib * ib - 1u;
@@ -471,7 +503,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 ln += __popc(hit);
                 __syncwarp();
                 if (ln >= 32) {
-                    drain3<ST>(P, A, pf, q, qn, lq, ln - 32, 32, gid, ord_base, gs);
+                    drain3<ST>(P, A, q, qn, lq, ln - 32, 32, gid, ord_base, gs);
                     ln -= 32;
                     __syncwarp();
                 }
@@ -503,7 +535,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             }
         }
     }
-    if (ln) { drain3<ST>(P, A, pf, q, qn, lq, 0, ln, gid, ord_base, gs); __syncwarp(); }
+    if (ln) { drain3<ST>(P, A, q, qn, lq, 0, ln, gid, ord_base, gs); __syncwarp(); }
     if (qn) { resolve3(P, A, q, 0, qn, gid, ord_base, gs); __syncwarp(); }
     if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
 }
@@ -513,15 +545,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
-    WarpQueue *queues = reinterpret_cast<WarpQueue *>(smem_raw + (kPf3Words + kPf3bWords) * 4);
+    WarpQ3 *queues = reinterpret_cast<WarpQ3 *>(smem_raw + kPf3Words * 4);
     LaneQ3 *lqueues = reinterpret_cast<LaneQ3 *>(queues + kScanWarps);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(pf_global);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);
-        for (uint32_t i = threadIdx.x; i < (kPf3Words + kPf3bWords) / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        for (uint32_t i = threadIdx.x; i < kPf3Words / 4; i += blockDim.x) dst[i] = __ldg(&src[i]);
     }
     __syncthreads();
-    WarpQueue &q = queues[threadIdx.x >> 5];
+    WarpQ3 &q = queues[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
     for (;;) {
         uint32_t si = 0;

@@ -77,7 +77,7 @@ def test_lazy_validation_never_accepts_a_fake(gpu_ctx_l3k10, shuf_l3k10, oracle_
         genomes.append(np.concatenate([body[:8], _sprinkle(body[8:], alphabet, every, 7 * i + 1)]))
     sk = gpu_ctx_l3k10.sketch(genomes, strict=False)
     _compare_sets(sk, orc, genomes)
-    if every >= 300:
+    if every >= 300 and b">" not in alphabet:          # (a '>' swallows the rest of its line: the one-line genome ends there)
         assert all(len(s[0]) > 50 for s in sk.genome_sets())
 
 
