@@ -9,7 +9,7 @@
 // sorted keys.  A second small sort puts the rows in the reference's print order (most shared k-mers first, ties in
 // reference order -- glibc's qsort is a stable merge sort at these sizes).
 #pragma once
-#include "kssd_device.cuh"
+#include "index_dist.cuh"
 
 namespace kssd {
 
@@ -22,17 +22,19 @@ struct CompRow {            // mirrors kssd_comp_row_t
 constexpr int kCompQryShift = 40, kCompRefShift = 16;     // key = qry << 40 | ref << 16 | abundance
 
 // number of (query code, posting) pairs of every query code (one component)
-__global__ void comp_count_kernel(const uint32_t *__restrict__ qcodes, uint64_t n, const uint32_t *__restrict__ dense, uint32_t *__restrict__ len)
+__global__ void comp_count_kernel(const uint32_t *__restrict__ qcodes, uint64_t n, const CodeLookup L, uint32_t *__restrict__ len)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = qcodes[i];
-    len[i] = dense[c + 1] - dense[c];
+    uint32_t s0, s1;
+    code_lookup(L, c, s0, s1);
+    len[i] = s1 - s0;
 }
 
 // query number of every query code (binary search in the per-query index), then its pairs at off[i]..
 __global__ void comp_emit_kernel(const uint32_t *__restrict__ qcodes, const uint16_t *__restrict__ qabund, const uint64_t *__restrict__ qindex,
-                                 int n_qry, uint64_t n, const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                 int n_qry, uint64_t n, const CodeLookup L, const uint32_t *__restrict__ mco,
                                  const uint64_t *__restrict__ off, uint64_t *__restrict__ keys)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,7 +47,9 @@ __global__ void comp_emit_kernel(const uint32_t *__restrict__ qcodes, const uint
     const uint32_t c = qcodes[i];
     const uint64_t base = ((uint64_t)lo << kCompQryShift) | qabund[i];
     uint64_t o = off[i];
-    for (uint32_t p = dense[c]; p < dense[c + 1]; p++) keys[o++] = base | ((uint64_t)mco[p] << kCompRefShift);
+    uint32_t s0, s1;
+    code_lookup(L, c, s0, s1);
+    for (uint32_t p = s0; p < s1; p++) keys[o++] = base | ((uint64_t)mco[p] << kCompRefShift);
 }
 
 // one thread per (query, ref) group: statistics out of the sorted abundances (low 16 bits of the keys)

@@ -35,7 +35,40 @@ __global__ void csr_scatter_kernel(const uint32_t *__restrict__ codes, const uin
     if (flags[i]) { ucodes[pos[i]] = codes[i]; uoff[pos[i]] = (uint32_t)i; }
 }
 
-// Dense EXCLUSIVE start table over the whole code space of one component:
+// Code -> posting list on the device: a rank bitmap over the component's code space.
+//   rb[w] = { bits of the codes 32w .. 32w+31 that occur, number of occurring codes below 32w }
+// 64 MiB for the 2^28 codes of a component -- it stays in the 126 MB L2 -- next to uoff[U+1], the list starts of the U
+// occurring codes.  An absent code costs one 8-byte L2 read and nothing else; an occurring one adds one HBM read of two
+// adjacent offsets.  (The reference's dense 2 GiB mco.index -- one offset per code of the space -- is a file format:
+// it is produced on export and consumed on import, never looked up.)  Codes beyond the space have no list.
+struct CodeLookup { const uint2 *rb; const uint32_t *uoff; uint32_t n_words; };
+
+__device__ __forceinline__ void code_lookup(const CodeLookup &L, uint32_t c, uint32_t &s0, uint32_t &s1)
+{
+    s0 = 0; s1 = 0;
+    const uint32_t w = c >> 5;
+    if (w >= L.n_words) return;
+    const uint2 e = __ldg(&L.rb[w]);
+    const uint32_t bit = 1u << (c & 31);
+    if (e.x & bit) {
+        const uint32_t i = e.y + __popc(e.x & (bit - 1u));
+        s0 = __ldg(&L.uoff[i]);
+        s1 = __ldg(&L.uoff[i + 1]);
+    }
+}
+
+// ucodes ascending: set the bit of every occurring code; the first code of a word leaves its rank (words without
+// a bit are never asked for theirs)
+__global__ void rb_build_kernel(const uint32_t *__restrict__ ucodes, uint32_t nuniq, uint2 *__restrict__ rb)
+{
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nuniq) return;
+    const uint32_t c = ucodes[u], w = c >> 5;
+    atomicOr(&rb[w].x, 1u << (c & 31));
+    if (u == 0 || (ucodes[u - 1] >> 5) != w) rb[w].y = u;
+}
+
+// Dense EXCLUSIVE start table over the whole code space of one component (export / import of mco.index only):
 //   dense[c] = #postings with code < c,  c in [0, space]   (space = 16^COMPONENT_SZ)
 // Built as: zero, dense[ucode + 1] = end offset of that code's postings, inclusive max-scan (offsets ascend with
 // the code) -- two streaming passes over the table instead of one short uncoalesced range per code.
@@ -73,7 +106,7 @@ constexpr int kDistThreads = KSSD_DIST_THREADS;
 
 template <typename CT>   // uint16_t when every query sketch is < 65536 codes, else uint32_t
 __global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
-                                                                     const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                     const CodeLookup L, const uint32_t *__restrict__ mco,
                                                                      uint32_t n_ref, uint32_t tile_refs, uint32_t n_tiles,
                                                                      uint32_t *__restrict__ ct, int accumulate)
 {
@@ -94,7 +127,8 @@ __global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t
     uint32_t *t32 = reinterpret_cast<uint32_t *>(smem_raw);
     for (uint64_t i = qs + threadIdx.x; i < qe; i += blockDim.x) {
         const uint32_t c = __ldg(&qcodes[i]);
-        const uint32_t s0 = __ldg(&dense[c]), s1 = __ldg(&dense[c + 1]);
+        uint32_t s0, s1;
+        code_lookup(L, c, s0, s1);
         // postings are fetched eight at a time before any atomic, so a thread keeps eight loads in flight
         for (uint32_t g = s0; g < s1; g += 8) {
             uint32_t r[8];
@@ -142,7 +176,7 @@ __global__ void __launch_bounds__(kDistThreads) dist_count_kernel(const uint32_t
 constexpr int kDistRowThreads = 512;
 
 __global__ void __launch_bounds__(kDistRowThreads) dist_count_rows_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
-                                                                              const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                              const CodeLookup L, const uint32_t *__restrict__ mco,
                                                                               uint32_t n_qry, uint32_t n_ref, uint32_t *__restrict__ ct, int accumulate)
 {
     for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
@@ -167,8 +201,7 @@ __global__ void __launch_bounds__(kDistRowThreads) dist_count_rows_kernel(const 
             uint32_t s0 = 0, s1 = 0;
             if (i < qe) {
                 const uint32_t c = __ldg(&qcodes[i]);
-                s0 = __ldg(&dense[c]);
-                s1 = __ldg(&dense[c + 1]);
+                code_lookup(L, c, s0, s1);
             }
             const uint32_t cnt = (uint32_t)min((uint64_t)32, qe - base);
             for (uint32_t j0 = 0; j0 < cnt; j0 += 8) {
@@ -200,7 +233,7 @@ constexpr int kMaxPeers = 16;
 struct PeerRows { uint32_t *block[kMaxPeers]; };
 
 __global__ void __launch_bounds__(kDistRowThreads) dist_count_peer_kernel(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
-                                                                              const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco,
+                                                                              const CodeLookup L, const uint32_t *__restrict__ mco,
                                                                               uint32_t n_qry, uint32_t n_ref, PeerRows rows, uint32_t rows_per_block)
 {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -213,8 +246,7 @@ __global__ void __launch_bounds__(kDistRowThreads) dist_count_peer_kernel(const 
             uint32_t s0 = 0, s1 = 0;
             if (i < qe) {
                 const uint32_t c = __ldg(&qcodes[i]);
-                s0 = __ldg(&dense[c]);
-                s1 = __ldg(&dense[c + 1]);
+                code_lookup(L, c, s0, s1);
             }
             // most codes of a query fall outside this rank's code range: skip the empty lists without shuffling them
             uint32_t live = __ballot_sync(kFull, s1 > s0);
@@ -477,7 +509,7 @@ __global__ void __launch_bounds__(kStatThreads) stats_rows_dense_kernel(const St
 // shared bitmap of the touched refs gives the ascending-ref order dist_print_nobin needs without a sort, the keep
 // rule of output_ctrl is applied in place, and the (query, ref, shared) hits are appended to one list; the rows pass
 // then evaluates the statistics densely, one thread per hit.  All components of the index add into the same table.
-struct SparseComp { const uint32_t *qcodes; const uint64_t *qindex; const uint32_t *dense; const uint32_t *mco; };
+struct SparseComp { const uint32_t *qcodes; const uint64_t *qindex; CodeLookup L; const uint32_t *mco; };
 struct SparseHit { uint32_t q, r, shared; };
 constexpr int kSparseThreads = 512;
 constexpr uint32_t kSparseSlots = 8192;                       // hash slots per CTA: 64 KiB of keys + counts
@@ -553,7 +585,7 @@ __device__ __forceinline__ uint2 sparse_block_scan(uint2 v, uint2 *wsum, uint2 *
 // (coalesced pieces of two or three lists), four steps of gid loads in flight ahead of emit(gid).
 template <typename F>
 __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
-                                                    const uint32_t *__restrict__ dense, const uint32_t *__restrict__ mco, uint32_t q,
+                                                    const CodeLookup L, const uint32_t *__restrict__ mco, uint32_t q,
                                                     uint32_t *lstart, uint32_t *lpre, uint2 *wsum, F emit)
 {
     const uint64_t qs = qindex[q], qe = qindex[q + 1];
@@ -567,8 +599,7 @@ __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__
             uint32_t s0 = 0, s1 = 0;
             if (i < nt) {
                 const uint32_t c = __ldg(&qcodes[t0 + i]);
-                s0 = __ldg(&dense[c]);
-                s1 = __ldg(&dense[c + 1]);
+                code_lookup(L, c, s0, s1);
             }
             st[j] = s0;
             len[j] = s1 - s0;
@@ -672,7 +703,7 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         // ---- walk (walk_query_postings): every gid of every posting list of the query's codes goes into the table
         for (int cc = 0; cc < n_comp; cc++) {
             const SparseComp C = comps[cc];
-            walk_query_postings(C.qcodes, C.qindex, C.dense, C.mco, q, lstart, lpre, wsum,
+            walk_query_postings(C.qcodes, C.qindex, C.L, C.mco, q, lstart, lpre, wsum,
                                 [&](uint32_t g) { sparse_insert<PACKED>(keys, vals, cb, bitmap, &distinct, g); });
         }
         __syncthreads();

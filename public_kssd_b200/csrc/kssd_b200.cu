@@ -583,7 +583,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     if (guided) {
         uint64_t want = total / (warps * 4) + 1;
         span = 4096;
-        while (span < want && span < (256u << 10)) span <<= 1;
+        while (span < want && span < (1u << 20)) span <<= 1;
     }
     if (span < 512 || (span & (span - 1))) return fail(KSSD_E_INVAL, "kssd_sketch_batch: span_bytes must be a power of two >= 512");
     // The span plan is a function of the batch layout only; a host that sketches batches of the same layout (a
@@ -899,7 +899,9 @@ struct kssd_index {
     kssd_ctx *ctx = nullptr;
     int n_genomes = 0;
     uint64_t n_postings = 0, n_unique = 0, space = 0;
-    uint32_t *d_ucodes = nullptr, *d_uoff = nullptr, *d_gids = nullptr, *d_dense = nullptr;
+    uint32_t *d_ucodes = nullptr, *d_uoff = nullptr, *d_gids = nullptr;
+    uint2 *d_rb = nullptr;                       // rank bitmap over the code space (index_dist.cuh)
+    CodeLookup lookup() const { return CodeLookup{d_rb, d_uoff, (uint32_t)(space >> 5)}; }
 };
 
 static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
@@ -933,16 +935,12 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
     }
     const uint32_t n32 = (uint32_t)n;
     CU(cudaMemcpyAsync(ix->d_uoff + nuniq, &n32, 4, cudaMemcpyHostToDevice, c->stream));
-    // dense exclusive start table for O(1) query lookups (and for mco.index.<c> export)
-    CU(cudaMallocAsync(&ix->d_dense, (ix->space + 1) * 4, c->stream));
-    CU(cudaMemsetAsync(ix->d_dense, 0, (ix->space + 1) * 4, c->stream));
+    // rank bitmap for O(1) query lookups
+    CU(cudaMallocAsync(&ix->d_rb, (ix->space >> 5) * sizeof(uint2), c->stream));
+    CU(cudaMemsetAsync(ix->d_rb, 0, (ix->space >> 5) * sizeof(uint2), c->stream));
     if (nuniq) {
-        dense_mark_kernel<<<(nuniq + 255) / 256, 256, 0, c->stream>>>(ix->d_ucodes, ix->d_uoff, nuniq, ix->d_dense);
-        size_t tmpb = 0;
-        cub::DeviceScan::InclusiveScan(nullptr, tmpb, ix->d_dense, ix->d_dense, cub::Max(), ix->space + 1, c->stream);
-        CU(c->cubtmp.ensure(tmpb));
-        CU(cub::DeviceScan::InclusiveScan(c->cubtmp.p, tmpb, ix->d_dense, ix->d_dense, cub::Max(), ix->space + 1, c->stream));
-        LAUNCHED(3);
+        rb_build_kernel<<<(nuniq + 255) / 256, 256, 0, c->stream>>>(ix->d_ucodes, nuniq, ix->d_rb);
+        LAUNCHED(1);
     }
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -1035,15 +1033,30 @@ extern "C" int kssd_index_fetch_dense(const kssd_index_t *ix, uint64_t *dense_ou
     if (!ix || !dense_out) return fail(KSSD_E_INVAL, "kssd_index_fetch_dense: null");
     kssd_ctx *c = ix->ctx;
     CU(cudaSetDevice(c->device));
+    // the reference's dense table is a file format: built here for the export only (zero, mark list ends, max-scan)
+    uint32_t *d_dense = nullptr;
+    CU(cudaMallocAsync(&d_dense, (ix->space + 1) * 4, c->stream));
+    CU(cudaMemsetAsync(d_dense, 0, (ix->space + 1) * 4, c->stream));
+    if (ix->n_unique) {
+        dense_mark_kernel<<<(uint32_t)((ix->n_unique + 255) / 256), 256, 0, c->stream>>>(ix->d_ucodes, ix->d_uoff, (uint32_t)ix->n_unique, d_dense);
+        size_t tmpb = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tmpb, d_dense, d_dense, cub::Max(), ix->space + 1, c->stream);
+        if (c->cubtmp.ensure(tmpb) != cudaSuccess) { cudaFreeAsync(d_dense, c->stream); return fail(KSSD_E_CUDA, "kssd_index_fetch_dense: out of memory"); }
+        cub::DeviceScan::InclusiveScan(c->cubtmp.p, tmpb, d_dense, d_dense, cub::Max(), ix->space + 1, c->stream);
+        LAUNCHED(3);
+    }
     const uint64_t chunk = 1ull << 24;   // 128 MiB of u64 per step
-    CU(c->keys.ensure(chunk * 8));
+    if (c->keys.ensure(chunk * 8) != cudaSuccess) { cudaFreeAsync(d_dense, c->stream); return fail(KSSD_E_CUDA, "kssd_index_fetch_dense: out of memory"); }
     for (uint64_t first = 0; first < ix->space; first += chunk) {
         const uint64_t cnt = std::min(chunk, ix->space - first);
-        dense_incl64_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->stream>>>(ix->d_dense, first, cnt, c->keys.as<uint64_t>());
+        dense_incl64_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->stream>>>(d_dense, first, cnt, c->keys.as<uint64_t>());
         LAUNCHED(1);
-        CU(cudaMemcpyAsync(dense_out + first, c->keys.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        cudaMemcpyAsync(dense_out + first, c->keys.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
     }
+    cudaFreeAsync(d_dense, c->stream);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
     return KSSD_OK;
 }
 
@@ -1096,7 +1109,7 @@ extern "C" void kssd_index_free(kssd_index_t *ix)
     if (ix->d_ucodes) cudaFreeAsync(ix->d_ucodes, st);
     if (ix->d_uoff) cudaFreeAsync(ix->d_uoff, st);
     if (ix->d_gids) cudaFreeAsync(ix->d_gids, st);
-    if (ix->d_dense) cudaFreeAsync(ix->d_dense, st);
+    if (ix->d_rb) cudaFreeAsync(ix->d_rb, st);
     delete ix;
 }
 
@@ -1168,7 +1181,7 @@ extern "C" int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_
     if (!d->sparse) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: not a sparse job");
     if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
     if (d->comps.size() >= 256) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: more than 256 components");
-    d->comps.push_back(SparseComp{qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids});
+    d->comps.push_back(SparseComp{qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids});
     d->comp_ix.push_back(ref_ix);
     d->comp_ncodes.push_back(n_qcodes);
     return KSSD_OK;
@@ -1221,7 +1234,7 @@ extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_
     if (use_rows) {
         const char *rps = getenv("KSSD_DIST_ROWS_PER_SM");
         const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * (rps ? atoi(rps) : 4));
-        dist_count_rows_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_qry,
+        dist_count_rows_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids, (uint32_t)d->n_qry,
                                                                        (uint32_t)d->n_ref, d->d_ct, d->components_done > 0);
     } else {
         const bool small = d->max_qry_size < 65536u;
@@ -1236,11 +1249,11 @@ extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_
         const uint32_t grid = (uint32_t)d->n_qry * n_tiles;
         if (small) {
             CU(cudaFuncSetAttribute(dist_count_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dist_count_kernel<uint16_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
+            dist_count_kernel<uint16_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids, (uint32_t)d->n_ref,
                                                                                tile, n_tiles, d->d_ct, d->components_done > 0);
         } else {
             CU(cudaFuncSetAttribute(dist_count_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dist_count_kernel<uint32_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)d->n_ref,
+            dist_count_kernel<uint32_t><<<grid, kDistThreads, smem, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids, (uint32_t)d->n_ref,
                                                                                tile, n_tiles, d->d_ct, d->components_done > 0);
         }
     }
@@ -1280,7 +1293,7 @@ extern "C" int kssd_dist_accumulate_peer(kssd_ctx_t *c, const kssd_index_t *ref_
     for (int i = 0; i < world; i++) pr.block[i] = row_blocks[i];
     CU(cudaEventRecord(c->ev[0], c->stream));
     const uint32_t grid = (uint32_t)std::min<int>(n_qry, c->sm_count * 4);
-    dist_count_peer_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->d_dense, ref_ix->d_gids, (uint32_t)n_qry, (uint32_t)n_ref,
+    dist_count_peer_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids, (uint32_t)n_qry, (uint32_t)n_ref,
                                                                    pr, (uint32_t)rows_per_block);
     LAUNCHED(1);
     CU(cudaEventRecord(c->ev[1], c->stream));
@@ -1873,7 +1886,7 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
         if (C.n) {
             CU(cudaMemcpyAsync(C.codes, qcodes[cc], C.n * 4, cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemcpyAsync(C.ab, qabund[cc], C.n * 2, cudaMemcpyHostToDevice, c->stream));
-            comp_count_kernel<<<(uint32_t)((C.n + 255) / 256), 256, 0, c->stream>>>(C.codes, C.n, ref_ix[cc]->d_dense, len);
+            comp_count_kernel<<<(uint32_t)((C.n + 255) / 256), 256, 0, c->stream>>>(C.codes, C.n, ref_ix[cc]->lookup(), len);
             cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, C.off, C.n, c->stream);
             CU(c->cubtmp.ensure(tmp));
             CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, len, C.off, C.n, c->stream));
@@ -1896,7 +1909,7 @@ extern "C" int kssd_composite_host(kssd_ctx_t *c, int n_comp, const kssd_index_t
     uint64_t base = 0;
     for (int cc = 0; cc < n_comp; cc++) {
         const Comp &C = comps[cc];
-        if (C.n) comp_emit_kernel<<<(uint32_t)((C.n + 255) / 256), 256, 0, c->stream>>>(C.codes, C.ab, C.index, n_qry, C.n, ref_ix[cc]->d_dense,
+        if (C.n) comp_emit_kernel<<<(uint32_t)((C.n + 255) / 256), 256, 0, c->stream>>>(C.codes, C.ab, C.index, n_qry, C.n, ref_ix[cc]->lookup(),
                                                                                        ref_ix[cc]->d_gids, C.off, keys + base);
         base += C.pairs;
     }

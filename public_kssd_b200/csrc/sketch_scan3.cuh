@@ -71,8 +71,9 @@ struct LaneQ3 {
     uint32_t y[4][kQueueCap];
     uint32_t flags[kQueueCap], wmask[kQueueCap], cand[kQueueCap], off[kQueueCap];
 };
-// candidates on their way to the exact resolver: the k-mer (scan representation), lane offset | own-base number, the lane's skip flags
-struct WarpQ3 { uint32_t lo[kQueueCap], hi[kQueueCap], ord[kQueueCap], f[kQueueCap]; };
+// candidates on their way to the exact resolver: the k-mer (scan representation), the lane's offset in its genome (own-base
+// number in the top five bits), the lane's skip flags, the genome.  The queue outlives spans: entries carry all they need.
+struct WarpQ3 { uint32_t lo[kQueueCap], hi[kQueueCap], ordlo[kQueueCap], ordhi[kQueueCap], f[kQueueCap], gid[kQueueCap]; };
 constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3));
 
 __device__ __forceinline__ bool pf3_probe(const uint32_t *__restrict__ pf, uint32_t v)
@@ -103,17 +104,19 @@ __device__ __forceinline__ bool verify_window(const uint8_t *__restrict__ seq, u
 
 // exact resolution of queued candidates (scan representation), up to 32 at a time.  Out of line: three call sites,
 // a few thousand calls per launch -- the clean loop should not carry this code in its instruction-cache footprint.
-__device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, const WarpQ3 &q, uint32_t first, uint32_t m, uint32_t gid,
-                                      uint64_t ord_base, uint64_t gs)
+__device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, const WarpQ3 &q, uint32_t first, uint32_t m)
 {
     const uint32_t lane = lane_id();
     bool found = false;
     uint64_t key = 0, ordv = 0;
+    uint32_t gid = 0;
     if (lane < m) {
         const uint64_t y = ((uint64_t)q.hi[first + lane] << 32) | q.lo[first + lane];
         // byte of the occurrence's last base: the lane's offset plus the (j+1)-th byte of the lane without a skip flag
-        const uint32_t o = q.ord[first + lane];
-        ordv = ord_base + (o & ~31u) + __fns(~q.f[first + lane], 0, (int)(o & 31u) + 1);
+        const uint32_t oh = q.ordhi[first + lane];
+        ordv = (((uint64_t)(oh & 0x07ffffffu) << 32) | q.ordlo[first + lane]) + __fns(~q.f[first + lane], 0, (int)(oh >> 27) + 1);
+        gid = q.gid[first + lane];
+        const uint64_t gs = A.goff[gid];
         const uint64_t yf = y ^ ((y >> 1) & 0x5555555555555555ull);       // raw -> A0 C1 G2 T3
         const uint64_t fwd = rev_groups64(yf, P.TL);                      // the reference's tuple (newest base lowest)
         const uint64_t rc = ~yf & P.tupmask;                              // its crvstuple: complement, oldest base lowest
@@ -147,9 +150,9 @@ __device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, 
 }
 
 // append the lanes flagged `has` to the warp's candidate queue; resolve when 32 are waiting.
-// ord = 32-byte-aligned lane offset | own-base number j, f = the lane's skip flags (general path: exact offset, f = 0).
+// lane_ord = offset of the lane's first byte in its genome (general path: of the byte itself, j = 0, f = 0).
 __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, bool has, uint64_t kmer,
-                                            uint32_t ord, uint32_t f, uint32_t gid, uint64_t ord_base, uint64_t gs)
+                                            uint64_t lane_ord, uint32_t j, uint32_t f, uint32_t gid)
 {
     const uint32_t pm = __ballot_sync(kFull, has);
     if (!pm) return;
@@ -157,13 +160,15 @@ __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArg
         const uint32_t slot = qn + __popc(pm & ((1u << lane_id()) - 1u));
         q.lo[slot] = (uint32_t)kmer;
         q.hi[slot] = (uint32_t)(kmer >> 32);
-        q.ord[slot] = ord;
+        q.ordlo[slot] = (uint32_t)lane_ord;
+        q.ordhi[slot] = ((uint32_t)(lane_ord >> 32) & 0x07ffffffu) | (j << 27);
         q.f[slot] = f;
+        q.gid[slot] = gid;
     }
     qn += __popc(pm);
     __syncwarp();
     if (qn >= 32) {
-        resolve3(P, A, q, qn - 32, 32, gid, ord_base, gs);
+        resolve3(P, A, q, qn - 32, 32);
         qn -= 32;
         __syncwarp();
     }
@@ -173,7 +178,7 @@ __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArg
 // of the block's table entry; ST = 1: the bitmap was exact, every hit is a member.  Members go to the candidate queue.
 template <int ST>
 __device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, const LaneQ3 &lq, uint32_t first,
-                                       uint32_t m, uint32_t gid, uint64_t ord_base, uint64_t gs)
+                                       uint32_t m, uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
     const uint32_t e = first + (lane < m ? lane : 0u);
@@ -197,12 +202,15 @@ __device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A,
                     S = __funnelshift_r(ye[a * kQueueCap], a < 3 ? ye[(a + 1) * kQueueCap] : 0u, (uint32_t)o);
                 } else S = ye[0] << (-o);
                 const unsigned long long mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]);
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    const int j = 3 * i - r;
-                    const uint32_t ee = gtab_ext((S >> (2 * (2 - r))) & P.innermask, r);
-                    if (j >= 0 && j < 32 && ((wm >> j) & 1u) && ((mm >> (16 * r + ee)) & 1ull)) hits |= 1u << r;
-                }
+                const uint32_t m01 = (uint32_t)mm, m2 = (uint32_t)(mm >> 32);
+                uint32_t e0, e1, e2;                      // what each window holds outside the block, folded to 4 bits
+                if (P.s == 6) { e0 = (S >> 24) & 15u; e1 = ((S >> 2) & 3u) | ((S >> 22) & 12u); e2 = S & 15u; }
+                else { e0 = gtab_ext((S >> 4) & P.innermask, 0); e1 = gtab_ext((S >> 2) & P.innermask, 1); e2 = gtab_ext(S & P.innermask, 2); }
+                const int j0 = 3 * i;                     // windows j0, j0 - 1, j0 - 2 (own bases 0 .. 31 only)
+                const uint32_t okm = j0 < 32 ? (wm >> j0) & 1u : 0u;
+                const uint32_t ok1 = (j0 >= 1 && j0 < 33) ? (wm >> (j0 - 1)) & 1u : 0u;
+                const uint32_t ok2 = j0 >= 2 ? (wm >> (j0 - 2)) & 1u : 0u;
+                hits = (okm & (m01 >> e0)) | ((ok1 & (m01 >> (16 + e1))) << 1) | ((ok2 & (m2 >> e2)) << 2);
             }
         }
         while (__any_sync(kFull, hits != 0)) {
@@ -217,7 +225,7 @@ __device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A,
                 const uint32_t w0 = ye[a * kQueueCap], w1 = ye[(a + 1) * kQueueCap], w2 = ye[(a + 2) * kQueueCap];
                 kmer = ((((uint64_t)__funnelshift_r(w1, w2, 2u * j)) << 32) | __funnelshift_r(w0, w1, 2u * j)) & P.tupmask;
             }
-            queue_push3(P, A, q, qn, has, kmer, off | j, F, gid, ord_base, gs);
+            queue_push3(P, A, q, qn, has, kmer, ord_base + off, j, F, gid);
         }
     }
 }
@@ -227,7 +235,7 @@ __device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A,
 // scan representation and hits go straight to the candidate queue.
 __device__ __noinline__ void general_iter3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, uint32_t &qn,
                                            StreamState &st, uint4 cur, uint64_t cbase, uint64_t end, bool past_end, uint32_t lane_off,
-                                           uint32_t gid, uint64_t ord_base, uint64_t gs)
+                                           uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
     const int TL = P.TL;
@@ -320,7 +328,7 @@ __device__ __noinline__ void general_iter3(const SketchParams &P, const ScanArgs
                 if (pf3_probe(pf, v)) hit = P.gtab ? gtab_probe0(P.gtab, v & P.innermask) : true;
             }
         } else if ((BRK >> i) & 1u) run = 0;
-        queue_push3(P, A, q, qn, hit, fr, lane_off + i, 0u, gid, ord_base, gs);
+        queue_push3(P, A, q, qn, hit, fr, ord_base + lane_off + i, 0u, 0u, gid);
     }
     // warp carry = inclusive value of lane 31 on top of the old carry
     const uint64_t sb31 = shfl64(sb, 31);
@@ -350,8 +358,8 @@ __device__ __forceinline__ uint32_t top_bytes4(uint32_t a, uint32_t b, uint32_t 
 
 // ST: bases per first-level probe (3 or 1); BIG: 2k-1 history bases need more than 32 bits (k >= 9)
 template <int ST, bool BIG>
-__device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, LaneQ3 &lq, uint32_t gid,
-                           uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
+__device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, uint32_t &qn, LaneQ3 &lq,
+                           uint32_t gid, uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
 {
     constexpr int NPROBE = ST == 3 ? 12 : 32;
     const uint32_t lane = lane_id();
@@ -360,7 +368,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     // stream state in registers; packed into a StreamState only around the out-of-line general iterations
     uint32_t cw0 = 0, cw1 = 0;                                   // the last 2k-1 bases of the stream, oldest lowest
     uint32_t since_break = 0, after_end = 0, hdr = 0;
-    uint32_t qn = 0, ln = 0;
+    uint32_t ln = 0;
     const uint64_t chunk0 = start & ~127ull;
     const uint64_t ord_base = chunk0 - gs;           // may wrap below zero; real occurrences add back past it
     // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
@@ -463,34 +471,36 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 cand = __funnelshift_l(__funnelshift_l(0u, word, xsh(2 * ST * i + 15)), cand, 1);      // cand = cand << 1 | flag
             }
 
-            const uint32_t N = __reduce_add_sync(kFull, n);
             uint32_t wm = low_mask((int)n);                          // windows (own bases) the stream position allows
-            if (since_break < (uint32_t)(TL - 1) || past_end) {
-                // start of a span / run-out past its end: filter by position inside the iteration
-                uint32_t incl = n;
+            if (since_break < kRunCap || past_end) {
+                const uint32_t N = __reduce_add_sync(kFull, n);
+                if (since_break < (uint32_t)(TL - 1) || past_end) {
+                    // start of a span / run-out past its end: filter by position inside the iteration
+                    uint32_t incl = n;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= (uint32_t)o) incl += t;
-                }
-                const int o_l = (int)(incl - n);                     // bases before this lane
-                const int need = TL - 1 - (int)since_break - o_l;    // own base j ends a k-mer of this span iff j >= need
-                if (need > 0) wm &= ~low_mask(min(need, 32));
-                if (past_end) {
-                    uint32_t E;                                      // bases of this iteration before `end`
-                    const int64_t rel = (int64_t)end - (int64_t)cbase;
-                    if (rel <= 0) E = 0;
-                    else {
-                        const int le = (int)(rel >> 5), be = (int)(rel & 31);      // bytes [0, be) of lane `le` lie before `end`
-                        E = __shfl_sync(kFull, (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(F & low_mask(be)), le);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= (uint32_t)o) incl += t;
                     }
-                    // the k-mer's first base lies before `end` iff after_end + (o_l + j - E + 1) <= 2k-1
-                    const int keep = TL - 1 - (int)after_end + (int)E - o_l;      // j < keep
-                    if (keep < 32) wm &= low_mask(max(keep, 0));
-                    after_end += N - E;
+                    const int o_l = (int)(incl - n);                     // bases before this lane
+                    const int need = TL - 1 - (int)since_break - o_l;    // own base j ends a k-mer of this span iff j >= need
+                    if (need > 0) wm &= ~low_mask(min(need, 32));
+                    if (past_end) {
+                        uint32_t E;                                      // bases of this iteration before `end`
+                        const int64_t rel = (int64_t)end - (int64_t)cbase;
+                        if (rel <= 0) E = 0;
+                        else {
+                            const int le = (int)(rel >> 5), be = (int)(rel & 31);      // bytes [0, be) of lane `le` lie before `end`
+                            E = __shfl_sync(kFull, (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(F & low_mask(be)), le);
+                        }
+                        // the k-mer's first base lies before `end` iff after_end + (o_l + j - E + 1) <= 2k-1
+                        const int keep = TL - 1 - (int)after_end + (int)E - o_l;      // j < keep
+                        if (keep < 32) wm &= low_mask(max(keep, 0));
+                        after_end += N - E;
+                    }
                 }
+                since_break = min(since_break + N, kRunCap);
             }
-            since_break = min(since_break + N, kRunCap);
             cw0 = __shfl_sync(kFull, S0, 31);
             if (BIG) cw1 = __shfl_sync(kFull, S1, 31);
             const uint32_t hit = __ballot_sync(kFull, cand != 0);
@@ -503,7 +513,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 ln += __popc(hit);
                 __syncwarp();
                 if (ln >= 32) {
-                    drain3<ST>(P, A, q, qn, lq, ln - 32, 32, gid, ord_base, gs);
+                    drain3<ST>(P, A, q, qn, lq, ln - 32, 32, gid, ord_base);
                     ln -= 32;
                     __syncwarp();
                 }
@@ -521,7 +531,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 uint4 c16 = load_chunk16_guarded(A, laddr);
                 if (sbase < start || sbase + 512 > ge)
                     mask_lane_bytes(c16, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
-                general_iter3(P, A, pf, q, qn, st, c16, sbase, end, sbase + 512 > end, (it << 10) + 512u * h + 16 * lane, gid, ord_base, gs);
+                general_iter3(P, A, pf, q, qn, st, c16, sbase, end, sbase + 512 > end, (it << 10) + 512u * h + 16 * lane, gid, ord_base);
             }
             const uint64_t cwr = rev_groups64(st.cw & (P.tupmask >> 2), TL - 1);
             cw0 = (uint32_t)cwr; cw1 = (uint32_t)(cwr >> 32);
@@ -535,8 +545,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             }
         }
     }
-    if (ln) { drain3<ST>(P, A, q, qn, lq, 0, ln, gid, ord_base, gs); __syncwarp(); }
-    if (qn) { resolve3(P, A, q, 0, qn, gid, ord_base, gs); __syncwarp(); }
+    if (ln) { drain3<ST>(P, A, q, qn, lq, 0, ln, gid, ord_base); __syncwarp(); }
     if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
 }
 
@@ -555,6 +564,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
     __syncthreads();
     WarpQ3 &q = queues[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
+    uint32_t qn = 0;                                      // candidates waiting in the warp's queue (it outlives spans)
     for (;;) {
         uint32_t si = 0;
         if (lane == 0) si = atomicAdd(A.ticket, 1u);
@@ -564,8 +574,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
         const uint64_t gs = A.goff[gid], ge = gs + A.glen[gid];
         uint64_t start, end;
         if (!span_extent(A, si, gid, gs, ge, start, end)) continue;
-        scan_span3<ST, BIG>(P, A, pf, q, lqueues[threadIdx.x >> 5], gid, gs, ge, start, end);
+        scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], gid, gs, ge, start, end);
     }
+    if (qn) resolve3(P, A, q, 0, qn);
 }
 
 }  // namespace kssd
