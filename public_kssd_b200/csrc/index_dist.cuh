@@ -86,10 +86,17 @@ __global__ void dense_incl64_kernel(const uint32_t *__restrict__ dense, uint64_t
     if (i < count) out[i] = dense[first + i + 1];
 }
 
-__global__ void dense_from_incl64_kernel(const uint64_t *__restrict__ incl, uint64_t first, uint64_t count, uint32_t *__restrict__ dense)
+// import of a reference-written mco.index chunk: exclusive starts, and the checks that make it safe to use as offsets
+// (non-decreasing, never beyond the posting count); `prev` = the entry before the chunk
+__global__ void dense_from_incl64_kernel(const uint64_t *__restrict__ incl, uint64_t first, uint64_t count, uint64_t prev, uint64_t n_postings,
+                                         uint32_t *__restrict__ dense, uint32_t *__restrict__ flag)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) dense[first + i + 1] = (uint32_t)incl[i];
+    if (i < count) {
+        const uint64_t v = incl[i], before = i ? incl[i - 1] : prev;
+        if (v < before || v > n_postings) atomicOr(flag, 1u);
+        dense[first + i + 1] = (uint32_t)(v > n_postings ? n_postings : v);
+    }
     if (first == 0 && i == 0) dense[0] = 0;
 }
 

@@ -105,6 +105,7 @@ struct kssd_ctx {
     int scan_stride = 3;                         // bases per first-level probe of that scan (3 when 2*subk >= 12, else 1)
     int scan_impl = 3;                           // KSSD_SCAN_IMPL=2 selects the previous formulation (A/B runs)
     uint2 *d_ht = nullptr;
+    uint32_t *d_flag = nullptr;                  // set by the validation kernels: data taken from disk is never trusted as an index
     // scratch
     DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, runs, keep, counts, minord, cubtmp, misc;
     uint8_t *stag[2] = {nullptr, nullptr};       // pinned staging buffers of kssd_stage1_files
@@ -234,6 +235,8 @@ extern "C" int kssd_ctx_create(kssd_ctx_t **out, int device, const int32_t *shuf
     P.ht_mask = ht_size - 1;
     CU(cudaMalloc(&c->d_prefilter, (kPfWords + kPf2Words) * 4));
     CU(cudaMalloc(&c->d_ht, (size_t)ht_size * sizeof(uint2)));
+    CU(cudaMalloc(&c->d_flag, 16));
+    CU(cudaMemsetAsync(c->d_flag, 0, 16, c->stream));
     CU(cudaMemsetAsync(c->d_prefilter, 0, (kPfWords + kPf2Words) * 4, c->stream));
     CU(cudaMemsetAsync(c->d_ht, 0xff, (size_t)ht_size * sizeof(uint2), c->stream));
     CU(cudaMalloc(&c->d_prefilter3, kPf3Words * 4));
@@ -289,6 +292,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     cudaFree(c->d_prefilter3);
     cudaFree(c->d_gtab);
     cudaFree(c->d_ht);
+    cudaFree(c->d_flag);
     for (auto &e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -893,6 +897,56 @@ extern "C" void kssd_sketch_free(kssd_sketch_t *s)
 #include "stage1_files.cuh"
 
 // ------------------------------------------------------------------------------------------------
+// validation of caller / on-disk data that is about to be used as device indices (a stale or mismatched sketch, index
+// or pan file must end in KSSD_E_INVAL, not in an out-of-bounds write): one streaming pass, one flag
+// ------------------------------------------------------------------------------------------------
+__global__ void validate_below_kernel(const uint32_t *__restrict__ v, uint64_t n, uint32_t limit, uint32_t *__restrict__ flag)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && v[i] >= limit;
+    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+static int validate_below(kssd_ctx *c, const uint32_t *d_v, uint64_t n, uint64_t limit)
+{
+    if (!n || limit > 0xffffffffull) return KSSD_OK;
+    validate_below_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(d_v, n, (uint32_t)limit, c->d_flag);
+    LAUNCHED(1);
+    return KSSD_OK;
+}
+
+// reads and clears the flag (synchronises the stream)
+static int validation_failed(kssd_ctx *c, bool *failed)
+{
+    uint32_t f = 0;
+    CU(cudaMemcpyAsync(&f, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (f) CU(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
+    *failed = f != 0;
+    return KSSD_OK;
+}
+
+// largest per-query code count of one component, from the data (counts are bounded by it, whatever sizes the caller declared)
+__global__ void max_extent_kernel(const uint64_t *__restrict__ qindex, uint32_t n_qry, uint32_t *__restrict__ out)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = 0;
+    if (q < n_qry) { const uint64_t e = qindex[q + 1] - qindex[q]; v = e > 0xffffffffull ? 0xffffffffu : (uint32_t)e; }
+    v = __reduce_max_sync(kFull, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
+static int max_query_extent(kssd_ctx *c, const uint64_t *qindex_dev, int n_qry, uint32_t *out)
+{
+    CU(cudaMemsetAsync(c->d_flag + 1, 0, 4, c->stream));
+    max_extent_kernel<<<(n_qry + 255) / 256, 256, 0, c->stream>>>(qindex_dev, (uint32_t)n_qry, c->d_flag + 1);
+    LAUNCHED(1);
+    CU(cudaMemcpyAsync(out, c->d_flag + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KSSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stage II
 // ------------------------------------------------------------------------------------------------
 struct kssd_index {
@@ -922,7 +976,10 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
         uint32_t lp = 0, lf = 0;
         CU(cudaMemcpyAsync(&lp, c->pos.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(&lf, c->flags.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        bool bad = false;
+        const int vrc = validation_failed(c, &bad);               // (synchronises)
+        if (vrc) return vrc;
+        if (bad) return fail(KSSD_E_INVAL, "index: a code or genome id lies outside the component's space / the genome count (mismatched or corrupt input)");
         nuniq = lp + lf;
     }
     ix->n_unique = nuniq;
@@ -960,6 +1017,7 @@ extern "C" int kssd_index_build_dev(kssd_ctx_t *c, const uint32_t *combco_dev, c
     CU(cudaMallocAsync(&ix->d_gids, std::max<size_t>(n_codes, 1) * 4, c->stream));
     uint32_t *d_sorted = nullptr;
     if (n_codes) {
+        validate_below(c, combco_dev, n_codes, ix->space);        // a code outside 16^COMPONENT_SZ has no place in the index
         CU(c->keys.ensure(n_codes * 4));     // gid tags (unsorted)
         CU(c->keys2.ensure(n_codes * 4));    // sorted codes
         CU(cudaMemsetAsync(c->keys.p, 0, n_codes * 4, c->stream));
@@ -1080,6 +1138,12 @@ extern "C" int kssd_index_from_dense_host(kssd_ctx_t *c, const uint64_t *dense_i
     ix->space = 1ull << (4 * c->info.component_sz);   // the reference's dense table always spans 16^COMPONENT_SZ
     CU(cudaMallocAsync(&ix->d_gids, std::max<size_t>(n_postings, 1) * 4, c->stream));
     if (n_postings) CU(cudaMemcpyAsync(ix->d_gids, gids, n_postings * 4, cudaMemcpyHostToDevice, c->stream));
+    validate_below(c, ix->d_gids, n_postings, (uint64_t)n_genomes);
+    if (dense_incl[ix->space - 1] != n_postings) {
+        kssd_index_free(ix);
+        return fail(KSSD_E_MISMATCH, "kssd_index_from_dense_host: mco.index ends at %llu, mco holds %llu postings", (unsigned long long)dense_incl[ix->space - 1],
+                    (unsigned long long)n_postings);
+    }
     uint32_t *d_dense_tmp = nullptr;
     CU(cudaMallocAsync(&d_dense_tmp, (ix->space + 1) * 4, c->stream));
     const uint64_t chunk = 1ull << 24;
@@ -1087,7 +1151,8 @@ extern "C" int kssd_index_from_dense_host(kssd_ctx_t *c, const uint64_t *dense_i
     for (uint64_t first = 0; first < ix->space; first += chunk) {
         const uint64_t cnt = std::min(chunk, ix->space - first);
         CU(cudaMemcpyAsync(c->keys.p, dense_incl + first, cnt * 8, cudaMemcpyHostToDevice, c->stream));
-        dense_from_incl64_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->stream>>>(c->keys.as<uint64_t>(), first, cnt, d_dense_tmp);
+        dense_from_incl64_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, c->stream>>>(c->keys.as<uint64_t>(), first, cnt, first ? dense_incl[first - 1] : 0ull,
+                                                                                       n_postings, d_dense_tmp, c->d_flag);
         LAUNCHED(1);
         CU(cudaStreamSynchronize(c->stream));
     }
@@ -1120,6 +1185,7 @@ struct kssd_dist {
     kssd_ctx *ctx = nullptr;
     int n_qry = 0, n_ref = 0, components_done = 0;
     uint32_t max_qry_size = 0;
+    uint64_t max_count = 0;                      // bound of any cell from the DATA: sum over components of the largest query extent
     bool empty_qry = false, empty_ref = false;   // some sketch has no k-mer (its cells give NaN statistics)
     uint32_t *d_ct = nullptr, *d_qsz = nullptr, *d_rsz = nullptr;
     bool owns_ct = true;
@@ -1181,6 +1247,9 @@ extern "C" int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_
     if (!d->sparse) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: not a sparse job");
     if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
     if (d->comps.size() >= 256) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: more than 256 components");
+    uint32_t ext = 0;
+    { const int rc = max_query_extent(d->ctx, qindex_dev, d->n_qry, &ext); if (rc) return rc; }
+    d->max_count += ext;
     d->comps.push_back(SparseComp{qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids});
     d->comp_ix.push_back(ref_ix);
     d->comp_ncodes.push_back(n_qcodes);
@@ -1237,7 +1306,10 @@ extern "C" int kssd_dist_accumulate_dev(kssd_dist_t *d, const kssd_index_t *ref_
         dist_count_rows_kernel<<<grid, kDistRowThreads, 0, c->stream>>>(qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids, (uint32_t)d->n_qry,
                                                                        (uint32_t)d->n_ref, d->d_ct, d->components_done > 0);
     } else {
-        const bool small = d->max_qry_size < 65536u;
+        // 16-bit strip counters only if the DATA cannot overflow them (the declared sketch sizes may be per shard)
+        uint32_t ext = 0;
+        { const int rc = max_query_extent(c, qindex_dev, d->n_qry, &ext); if (rc) return rc; }
+        const bool small = d->max_qry_size < 65536u && ext < 65536u;
         const uint32_t elem = small ? 2 : 4;
         // strip width: whole row when it fits in 112 KiB (two CTAs per SM), else equal tiles
         const char *skb = getenv("KSSD_DIST_STRIP_KB");
@@ -1400,7 +1472,7 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         uint32_t gbits = 1;
         while ((1ull << gbits) - 1 < (uint64_t)d->n_ref) gbits++;                // n_ref <= 2^gbits - 1: no gid is all ones
         const uint32_t cb = 32 - gbits;
-        const bool packed = gbits <= 24 && (uint64_t)d->max_qry_size + 1 < (1ull << cb) - 1 && !getenv("KSSD_SPARSE_UNPACKED");   // env: A/B and tests
+        const bool packed = gbits <= 24 && std::max<uint64_t>(d->max_qry_size, d->max_count) + 1 < (1ull << cb) - 1 && !getenv("KSSD_SPARSE_UNPACKED");   // env: A/B and tests
         const size_t smem = ((packed ? 1ull : 2ull) * kSparseSlots + 2ull * kSparseTile + 1 + bw) * 4;
         if (no_zero_rows && smem <= 200u * 1024u) {
             const bool trivial = S.dthreshold >= 1.0;
@@ -1766,6 +1838,11 @@ extern "C" int kssd_set_union_dev(kssd_ctx_t *c, const uint32_t *combco_dev, uin
         twice = c->keys2.as<uint32_t>();
     }
     if (n_codes) {
+        validate_below(c, combco_dev, n_codes, n_words * 32);
+        bool bad = false;
+        const int vrc = validation_failed(c, &bad);
+        if (vrc) return vrc;
+        if (bad) return fail(KSSD_E_INVAL, "kssd_set_union: a code lies outside the component's code space (mismatched or corrupt sketch)");
         set_mark_kernel<<<(uint32_t)((n_codes + 255) / 256), 256, 0, c->stream>>>(combco_dev, n_codes, c->keys.as<uint32_t>(), twice);
         LAUNCHED(1);
     }
@@ -1801,6 +1878,14 @@ extern "C" int kssd_set_operate_dev(kssd_ctx_t *c, const uint32_t *combco_dev, c
     set_code_words(c, &n_words);
     CU(c->keys.ensure(n_words * 4));
     CU(cudaMemsetAsync(c->keys.p, 0, n_words * 4, c->stream));
+    {
+        validate_below(c, pan_dev, n_pan, n_words * 32);
+        validate_below(c, combco_dev, n_codes, n_words * 32);
+        bool bad = false;
+        const int vrc = validation_failed(c, &bad);
+        if (vrc) return vrc;
+        if (bad) return fail(KSSD_E_INVAL, "kssd_set_operate: a code lies outside the component's code space (mismatched or corrupt sketch / pan file)");
+    }
     if (n_pan) set_mark_kernel<<<(uint32_t)((n_pan + 255) / 256), 256, 0, c->stream>>>(pan_dev, n_pan, c->keys.as<uint32_t>(), nullptr);
     const uint64_t nn = std::max<uint64_t>(n_codes, 1);
     CU(c->flags.ensure(nn * 4));

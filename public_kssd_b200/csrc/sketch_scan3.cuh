@@ -90,6 +90,17 @@ __device__ __forceinline__ bool gtab_probe0(const unsigned long long *__restrict
 // '\r' between them, all inside the genome.  Runs for the few positions that passed every filter and the exact lookup.
 __device__ __forceinline__ bool verify_window(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t p, int TL)
 {
+    // most windows lie inside one line: the 2k bytes ending at p are all letters -- independent loads, one latency
+    if (p - gs + 1 >= (uint64_t)TL) {
+        uint32_t other = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+            if (i < TL) {
+                const uint32_t l = __ldg(seq + p - i) | 0x20u;
+                other |= (uint32_t)!(l == 'a' || l == 'c' || l == 'g' || l == 't');
+            }
+        if (!other) return true;
+    }
     int cnt = 0;
     for (;;) {
         const uint32_t b = __ldg(seq + p);
@@ -375,29 +386,20 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     const uint64_t lim = end < ge ? end : ge;
     const uint64_t full = (lim - chunk0) >> 10;
     const uint32_t n_steady = full > 1 ? (uint32_t)(full - 1 < 0x3fffffffull ? full - 1 : 0x3fffffffull) : 0u;
-    const uint8_t *lp = A.seq + chunk0 + 32 * lane;
-    Bytes32 cur = load_chunk32_guarded(A, chunk0 + 32 * lane);
+    const uint8_t *lp = A.seq + chunk0 + 32 * lane;               // the lane's 32 bytes of iteration `it`
+    Bytes32 cur = {};                                              // ... of the next steady iteration, once requested
     bool at_eof = false;
 
-    for (uint32_t it = 0;; it++) {
+    for (uint32_t it = 0;; it++, lp += 1024) {
+        // Only STEADY iterations take the clean path below: no masking, no span-end accounting there.  The first and the
+        // last one or two iterations of a span go through the exact general path, which knows about both.
         const bool steady = (it - 1u) < n_steady;
         const uint64_t cbase = chunk0 + ((uint64_t)it << 10);
         const uint32_t lane_off = (it << 10) + 32 * lane;
-
-        bool past_end = false, cut_lane = false;
-        if (!steady) {
-            const uint64_t laddr = cbase + 32 * lane;
-            if (cbase < start || cbase + 1024 > ge) {
-                mask_lane_bytes(cur.lo, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
-                mask_lane_bytes(cur.hi, clamp16((int64_t)start - (int64_t)(laddr + 16)), clamp16((int64_t)ge - (int64_t)(laddr + 16)));
-            }
-            past_end = cbase + 1024 > end;
-            cut_lane = laddr < start || laddr + 32 > ge;
-        }
-
-        uint32_t dacc = 0, PA, PB, F;
-        {
-            uint32_t c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
+        uint32_t PA = 0, PB = 0, F = 0;
+        bool clean = false;
+        if (steady) {
+            uint32_t dacc = 0, c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
             classify_lazy8(cur.lo.x, cur.lo.y, dacc, c0, c1, g0);
             classify_lazy8(cur.lo.z, cur.lo.w, dacc, c2, c3, g1);
             classify_lazy8(cur.hi.x, cur.hi.y, dacc, c4, c5, g2);
@@ -405,21 +407,19 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             F = top_bytes4(g0, g1, g2, g3);                       // bit b: byte b of the lane is skipped
             PA = top_bytes4(c0, c1, c2, c3);
             PB = top_bytes4(c4, c5, c6, c7);
+            clean = __all_sync(kFull, dacc == 0 && __popc(F) <= 33 - TL) && !hdr;      // every lane: n >= 2k-1 bases
         }
-        // the 32 bytes are now three words: request the next KiB into the same registers (one buffer, no copies); the
-        // rest of the iteration and the other warps cover its latency.  A dirty iteration re-reads its text itself.
-        if (it < n_steady) cur = ldg_stream256(lp + 1024);
-        else if (cbase + 1024 < ge) cur = load_chunk32_guarded(A, cbase + 1024 + 32 * lane);
-        lp += 1024;
-        const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
-        const bool lane_ok = dacc == 0 && (n >= (uint32_t)(TL - 1) || cut_lane);
-        const bool clean = __all_sync(kFull, lane_ok) && !hdr;
+        // the 32 bytes are now three words: request the next steady KiB into the same registers (one buffer, no
+        // copies; the rest of the iteration and the other warps cover the latency), and pull the one after it into L2
+        if (it < n_steady) {
+            cur = ldg_stream256(lp + 1024);
+            if (it + 1 < n_steady) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 2048));
+        }
 
         if (clean) {
+            const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
             {
                 uint32_t fa = F & 0xffffu, fb = F >> 16;
-                if (fa == 0xffffu) { fa = 0; PA = 0; }           // a half masked out whole (span start, genome end)
-                if (fb == 0xffffu) { fb = 0; PB = 0; }
                 for (;;) {      // squeeze the skipped bytes out of both halves; first round is branch-free
                     const uint32_t ia = fa & (0u - fa), ib = fb & (0u - fb);
                     const uint32_t la = ia * ia - 1u, lb = ib * ib - 1u;
@@ -435,14 +435,9 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             // what the next lane needs of them: the last 2k-1, again oldest lowest
             uint32_t S0, S1;
             {
-                const int d = 2 * ((int)n - (TL - 1));
-                if (steady || d >= 0) {
-                    if (BIG) { S0 = __funnelshift_rc(Q0, Q1, d); S1 = __funnelshift_rc(Q1, 0u, d); }      // d <= 32
-                    else { S0 = (uint32_t)((((uint64_t)Q1 << 32) | Q0) >> d); S1 = 0u; }                  // d <= 62, 2k-1 <= 15 bases left
-                } else {                                                                                  // a cut lane with fewer bases: they end at group 2k-2
-                    const uint64_t s = (((uint64_t)Q1 << 32) | Q0) << (-d);
-                    S0 = (uint32_t)s; S1 = (uint32_t)(s >> 32);
-                }
+                const uint32_t d = 2 * (n - (uint32_t)(TL - 1));
+                if (BIG) { S0 = __funnelshift_rc(Q0, Q1, d); S1 = __funnelshift_rc(Q1, 0u, d); }      // d <= 32
+                else { S0 = (uint32_t)((((uint64_t)Q1 << 32) | Q0) >> d); S1 = 0u; }                  // d <= 62, 2k-1 <= 15 bases left
             }
             uint32_t H0 = __shfl_up_sync(kFull, S0, 1), H1 = BIG ? __shfl_up_sync(kFull, S1, 1) : 0u;
             if (lane == 0) { H0 = cw0; H1 = cw1; }
@@ -472,34 +467,16 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             }
 
             uint32_t wm = low_mask((int)n);                          // windows (own bases) the stream position allows
-            if (since_break < kRunCap || past_end) {
-                const uint32_t N = __reduce_add_sync(kFull, n);
-                if (since_break < (uint32_t)(TL - 1) || past_end) {
-                    // start of a span / run-out past its end: filter by position inside the iteration
-                    uint32_t incl = n;
+            if (since_break < kRunCap) {                              // right after a break (a general iteration left it so)
+                uint32_t incl = n;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                        if (lane >= (uint32_t)o) incl += t;
-                    }
-                    const int o_l = (int)(incl - n);                     // bases before this lane
-                    const int need = TL - 1 - (int)since_break - o_l;    // own base j ends a k-mer of this span iff j >= need
-                    if (need > 0) wm &= ~low_mask(min(need, 32));
-                    if (past_end) {
-                        uint32_t E;                                      // bases of this iteration before `end`
-                        const int64_t rel = (int64_t)end - (int64_t)cbase;
-                        if (rel <= 0) E = 0;
-                        else {
-                            const int le = (int)(rel >> 5), be = (int)(rel & 31);      // bytes [0, be) of lane `le` lie before `end`
-                            E = __shfl_sync(kFull, (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(F & low_mask(be)), le);
-                        }
-                        // the k-mer's first base lies before `end` iff after_end + (o_l + j - E + 1) <= 2k-1
-                        const int keep = TL - 1 - (int)after_end + (int)E - o_l;      // j < keep
-                        if (keep < 32) wm &= low_mask(max(keep, 0));
-                        after_end += N - E;
-                    }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= (uint32_t)o) incl += t;
                 }
-                since_break = min(since_break + N, kRunCap);
+                const int need = TL - 1 - (int)since_break - (int)(incl - n);      // own base j ends a k-mer iff j >= need
+                if (need > 0) wm &= ~low_mask(min(need, 32));
+                since_break = min(since_break + __shfl_sync(kFull, incl, 31), kRunCap);
             }
             cw0 = __shfl_sync(kFull, S0, 31);
             if (BIG) cw1 = __shfl_sync(kFull, S1, 31);

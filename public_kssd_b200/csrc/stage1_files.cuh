@@ -336,12 +336,19 @@ extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int
             B = Batch();
             B.staging = cur;
         };
+        // A batch goes to the GPU only if every file of it landed in the staging buffer: a file that stat() accepted but
+        // open() / read() rejected (permissions, truncation after stat, EIO) must fail the call like the reference's
+        // "eof or fread error" does -- never be sketched from whatever the buffer held.
         auto close_batch = [&] {
+            bool bad = false;
             {
                 std::unique_lock<std::mutex> l(m);
                 cv.wait(l, [&] { return outstanding == 0; });
-                gpu_q.push_back(std::move(B));
+                for (int f : B.files) bad |= tasks[f].failed;
+                if (!bad) gpu_q.push_back(std::move(B));
+                else staging_free[cur] = true;
             }
+            if (bad) failed = true;
             cv.notify_all();
             cur = -1;
         };
@@ -404,7 +411,10 @@ extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int
     }
     for (auto &t : tasks) {
         if (t.priv) free(t.priv);
-        if (t.failed && gpu_err.empty()) gpu_err = std::string("cannot read ") + paths[t.file];
+        if (t.failed) {
+            if (gpu_err.empty()) gpu_err = std::string("cannot read ") + paths[t.file];
+            if (gpu_rc == KSSD_OK) gpu_rc = KSSD_E_INVAL;     // no read failure is ever silent
+        }
     }
     R->read_s = read_busy / nt;
     R->total_s = secs(t_start, clk::now());

@@ -91,3 +91,19 @@ def test_files_through_pipe_command_and_list_file(gpu_ctx_l3k10, tmp_path):
     from public_kssd_b200 import kssd
     with pytest.raises(kssd.KssdError):
         gpu_ctx_l3k10.sketch_files(listed, pipecmd="false")
+
+
+def test_unreadable_file_fails_loudly(gpu_ctx_l3k10, tmp_path):
+    """A path stat() accepts but read() rejects (here: a directory -> EISDIR) must fail the call, as the reference's
+    'eof or fread error' does -- never return sketches made from whatever the staging buffer held."""
+    from public_kssd_b200 import kssd
+    good = tmp_path / "a.fa"
+    good.write_bytes(synth.to_fasta(synth.random_bases(200_000, 5), "a", 80).tobytes())
+    bad = tmp_path / "b.fa"
+    bad.mkdir()
+    (bad / "x").write_bytes(b"y" * 10)
+    for order in ([good, bad, good], [bad], [good, good, bad]):
+        with pytest.raises(kssd.KssdError):
+            gpu_ctx_l3k10.sketch_files(order, batch_bytes=150_000)
+    sk, _ = gpu_ctx_l3k10.sketch_files([good, good])          # the context is still usable
+    assert len(sk.ids[0]) > 0
