@@ -74,7 +74,7 @@ struct LaneQ3 {
 // candidates on their way to the exact resolver: the k-mer (scan representation), the lane's offset in its genome (own-base
 // number in the top five bits), the lane's skip flags, the genome.  The queue outlives spans: entries carry all they need.
 struct WarpQ3 { uint32_t lo[kQueueCap], hi[kQueueCap], ordlo[kQueueCap], ordhi[kQueueCap], f[kQueueCap], gid[kQueueCap]; };
-constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3));
+constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 48);   // + SpanCtx
 
 __device__ __forceinline__ bool pf3_probe(const uint32_t *__restrict__ pf, uint32_t v)
 {
@@ -367,10 +367,14 @@ __device__ __forceinline__ uint32_t top_bytes4(uint32_t a, uint32_t b, uint32_t 
     return prmt(prmt(a, b, 0x0073u), prmt(c, d, 0x0073u), 0x5410u);
 }
 
+// Cold per-span state lives in shared memory (one record per warp): the span's byte extents are 64-bit and only the
+// first and last iterations of a span look at them -- in registers they pushed the loop counters out to local memory.
+struct SpanCtx { uint64_t gs, ge, start, end, chunk0; uint32_t gid, after_end; };
+
 // ST: bases per first-level probe (3 or 1); BIG: 2k-1 history bases need more than 32 bits (k >= 9)
 template <int ST, bool BIG>
 __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, uint32_t &qn, LaneQ3 &lq,
-                           uint32_t gid, uint64_t gs, uint64_t ge, uint64_t start, uint64_t end)
+                           volatile SpanCtx &sc)
 {
     constexpr int NPROBE = ST == 3 ? 12 : 32;
     const uint32_t lane = lane_id();
@@ -378,28 +382,43 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     const uint32_t hsh = (2u * (uint32_t)(TL - 1)) & 31u;      // own bases sit above the 2k-1 history bases: bit 32*BIG + hsh
     // stream state in registers; packed into a StreamState only around the out-of-line general iterations
     uint32_t cw0 = 0, cw1 = 0;                                   // the last 2k-1 bases of the stream, oldest lowest
-    uint32_t since_break = 0, after_end = 0, hdr = 0;
+    uint32_t since_break = 0, hdr = 0;
     uint32_t ln = 0;
-    const uint64_t chunk0 = start & ~127ull;
-    const uint64_t ord_base = chunk0 - gs;           // may wrap below zero; real occurrences add back past it
-    // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
-    const uint64_t lim = end < ge ? end : ge;
-    const uint64_t full = (lim - chunk0) >> 10;
-    const uint32_t n_steady = full > 1 ? (uint32_t)(full - 1 < 0x3fffffffull ? full - 1 : 0x3fffffffull) : 0u;
-    const uint8_t *lp = A.seq + chunk0 + 32 * lane;               // the lane's 32 bytes of iteration `it`
-    Bytes32 cur = {};                                              // ... of the next steady iteration, once requested
+    uint32_t n_steady;
+    const uint8_t *lp;
+    Bytes32 cur;
+    {
+        const uint64_t start = sc.start, end = sc.end, ge = sc.ge, chunk0 = start & ~127ull;
+        if (lane == 0) { sc.chunk0 = chunk0; sc.after_end = 0; }
+        __syncwarp();
+        // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
+        const uint64_t lim = end < ge ? end : ge;
+        const uint64_t full = (lim - chunk0) >> 10;
+        n_steady = full > 1 ? (uint32_t)(full - 1 < 0x3fffffffull ? full - 1 : 0x3fffffffull) : 0u;
+        lp = A.seq + chunk0 + 32 * lane;
+        cur = load_chunk32_guarded(A, chunk0 + 32 * lane);
+    }
     bool at_eof = false;
 
-    for (uint32_t it = 0;; it++, lp += 1024) {
-        // Only STEADY iterations take the clean path below: no masking, no span-end accounting there.  The first and the
-        // last one or two iterations of a span go through the exact general path, which knows about both.
+    for (uint32_t it = 0;; it++) {
         const bool steady = (it - 1u) < n_steady;
-        const uint64_t cbase = chunk0 + ((uint64_t)it << 10);
         const uint32_t lane_off = (it << 10) + 32 * lane;
-        uint32_t PA = 0, PB = 0, F = 0;
-        bool clean = false;
-        if (steady) {
-            uint32_t dacc = 0, c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
+
+        bool past_end = false, cut_lane = false;
+        if (!steady) {
+            const uint64_t start = sc.start, ge = sc.ge, end = sc.end, cbase = sc.chunk0 + ((uint64_t)it << 10);
+            const uint64_t laddr = cbase + 32 * lane;
+            if (cbase < start || cbase + 1024 > ge) {
+                mask_lane_bytes(cur.lo, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
+                mask_lane_bytes(cur.hi, clamp16((int64_t)start - (int64_t)(laddr + 16)), clamp16((int64_t)ge - (int64_t)(laddr + 16)));
+            }
+            past_end = cbase + 1024 > end;
+            cut_lane = laddr < start || laddr + 32 > ge;
+        }
+
+        uint32_t dacc = 0, PA, PB, F;
+        {
+            uint32_t c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
             classify_lazy8(cur.lo.x, cur.lo.y, dacc, c0, c1, g0);
             classify_lazy8(cur.lo.z, cur.lo.w, dacc, c2, c3, g1);
             classify_lazy8(cur.hi.x, cur.hi.y, dacc, c4, c5, g2);
@@ -407,19 +426,28 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             F = top_bytes4(g0, g1, g2, g3);                       // bit b: byte b of the lane is skipped
             PA = top_bytes4(c0, c1, c2, c3);
             PB = top_bytes4(c4, c5, c6, c7);
-            clean = __all_sync(kFull, dacc == 0 && __popc(F) <= 33 - TL) && !hdr;      // every lane: n >= 2k-1 bases
         }
-        // the 32 bytes are now three words: request the next steady KiB into the same registers (one buffer, no
-        // copies; the rest of the iteration and the other warps cover the latency), and pull the one after it into L2
+        // the 32 bytes are now three words: request the next KiB into the same registers (one buffer, no copies); the
+        // rest of the iteration and the other warps cover its latency.  A dirty iteration re-reads its text itself.
         if (it < n_steady) {
             cur = ldg_stream256(lp + 1024);
+#ifdef KSSD_SCAN_PF2
             if (it + 1 < n_steady) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 2048));
+#endif
+        } else {
+            const uint64_t nb = sc.chunk0 + ((uint64_t)(it + 1) << 10);
+            if (nb < sc.ge) cur = load_chunk32_guarded(A, nb + 32 * lane);
         }
+        lp += 1024;
+        const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
+        const bool lane_ok = dacc == 0 && (n >= (uint32_t)(TL - 1) || cut_lane);
+        const bool clean = __all_sync(kFull, lane_ok) && !hdr;
 
         if (clean) {
-            const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
             {
                 uint32_t fa = F & 0xffffu, fb = F >> 16;
+                if (fa == 0xffffu) { fa = 0; PA = 0; }           // a half masked out whole (span start, genome end)
+                if (fb == 0xffffu) { fb = 0; PB = 0; }
                 for (;;) {      // squeeze the skipped bytes out of both halves; first round is branch-free
                     const uint32_t ia = fa & (0u - fa), ib = fb & (0u - fb);
                     const uint32_t la = ia * ia - 1u, lb = ib * ib - 1u;
@@ -435,9 +463,14 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             // what the next lane needs of them: the last 2k-1, again oldest lowest
             uint32_t S0, S1;
             {
-                const uint32_t d = 2 * (n - (uint32_t)(TL - 1));
-                if (BIG) { S0 = __funnelshift_rc(Q0, Q1, d); S1 = __funnelshift_rc(Q1, 0u, d); }      // d <= 32
-                else { S0 = (uint32_t)((((uint64_t)Q1 << 32) | Q0) >> d); S1 = 0u; }                  // d <= 62, 2k-1 <= 15 bases left
+                const int d = 2 * ((int)n - (TL - 1));
+                if (steady || d >= 0) {
+                    if (BIG) { S0 = __funnelshift_rc(Q0, Q1, d); S1 = __funnelshift_rc(Q1, 0u, d); }      // d <= 32
+                    else { S0 = (uint32_t)((((uint64_t)Q1 << 32) | Q0) >> d); S1 = 0u; }                  // d <= 62, 2k-1 <= 15 bases left
+                } else {                                                                                  // a cut lane with fewer bases: they end at group 2k-2
+                    const uint64_t s = (((uint64_t)Q1 << 32) | Q0) << (-d);
+                    S0 = (uint32_t)s; S1 = (uint32_t)(s >> 32);
+                }
             }
             uint32_t H0 = __shfl_up_sync(kFull, S0, 1), H1 = BIG ? __shfl_up_sync(kFull, S1, 1) : 0u;
             if (lane == 0) { H0 = cw0; H1 = cw1; }
@@ -467,16 +500,37 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             }
 
             uint32_t wm = low_mask((int)n);                          // windows (own bases) the stream position allows
-            if (since_break < kRunCap) {                              // right after a break (a general iteration left it so)
-                uint32_t incl = n;
+            if (since_break < kRunCap || past_end) {
+                const uint32_t N = __reduce_add_sync(kFull, n);
+                if (since_break < (uint32_t)(TL - 1) || past_end) {
+                    // start of a span / run-out past its end: filter by position inside the iteration
+                    uint32_t incl = n;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= (uint32_t)o) incl += t;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= (uint32_t)o) incl += t;
+                    }
+                    const int o_l = (int)(incl - n);                     // bases before this lane
+                    const int need = TL - 1 - (int)since_break - o_l;    // own base j ends a k-mer of this span iff j >= need
+                    if (need > 0) wm &= ~low_mask(min(need, 32));
+                    if (past_end) {
+                        uint32_t E;                                      // bases of this iteration before `end`
+                        const uint32_t after_end = sc.after_end;
+                        const int64_t rel = (int64_t)sc.end - (int64_t)(sc.chunk0 + ((uint64_t)it << 10));
+                        if (rel <= 0) E = 0;
+                        else {
+                            const int le = (int)(rel >> 5), be = (int)(rel & 31);      // bytes [0, be) of lane `le` lie before `end`
+                            E = __shfl_sync(kFull, (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(F & low_mask(be)), le);
+                        }
+                        // the k-mer's first base lies before `end` iff after_end + (o_l + j - E + 1) <= 2k-1
+                        const int keep = TL - 1 - (int)after_end + (int)E - o_l;      // j < keep
+                        if (keep < 32) wm &= low_mask(max(keep, 0));
+                        __syncwarp();
+                        if (lane == 0) sc.after_end = after_end + N - E;
+                        __syncwarp();
+                    }
                 }
-                const int need = TL - 1 - (int)since_break - (int)(incl - n);      // own base j ends a k-mer iff j >= need
-                if (need > 0) wm &= ~low_mask(min(need, 32));
-                since_break = min(since_break + __shfl_sync(kFull, incl, 31), kRunCap);
+                since_break = min(since_break + N, kRunCap);
             }
             cw0 = __shfl_sync(kFull, S0, 31);
             if (BIG) cw1 = __shfl_sync(kFull, S1, 31);
@@ -490,7 +544,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 ln += __popc(hit);
                 __syncwarp();
                 if (ln >= 32) {
-                    drain3<ST>(P, A, q, qn, lq, ln - 32, 32, gid, ord_base);
+                    drain3<ST>(P, A, q, qn, lq, ln - 32, 32, sc.gid, sc.chunk0 - sc.gs);
                     ln -= 32;
                     __syncwarp();
                 }
@@ -499,7 +553,8 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             // two general 512-byte iterations with a 16-byte lane mapping (reloaded: L2 hits); the carry changes
             // representation on the way in and out
             const uint64_t cw = ((uint64_t)cw1 << 32) | cw0;
-            StreamState st = {rev_groups64(cw, TL - 1), since_break, after_end, hdr};
+            const uint64_t start = sc.start, ge = sc.ge, end = sc.end, cbase = sc.chunk0 + ((uint64_t)it << 10);
+            StreamState st = {rev_groups64(cw, TL - 1), since_break, sc.after_end, hdr};
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 const uint64_t sbase = cbase + 512ull * h;
@@ -508,22 +563,27 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 uint4 c16 = load_chunk16_guarded(A, laddr);
                 if (sbase < start || sbase + 512 > ge)
                     mask_lane_bytes(c16, clamp16((int64_t)start - (int64_t)laddr), clamp16((int64_t)ge - (int64_t)laddr));
-                general_iter3(P, A, pf, q, qn, st, c16, sbase, end, sbase + 512 > end, (it << 10) + 512u * h + 16 * lane, gid, ord_base);
+                general_iter3(P, A, pf, q, qn, st, c16, sbase, end, sbase + 512 > end, (it << 10) + 512u * h + 16 * lane, sc.gid, sc.chunk0 - sc.gs);
             }
             const uint64_t cwr = rev_groups64(st.cw & (P.tupmask >> 2), TL - 1);
             cw0 = (uint32_t)cwr; cw1 = (uint32_t)(cwr >> 32);
-            since_break = st.since_break; after_end = st.after_end; hdr = st.hdr;
+            since_break = st.since_break; hdr = st.hdr;
+            __syncwarp();
+            if (lane == 0) sc.after_end = st.after_end;
+            __syncwarp();
         }
 
         if (!steady) {
-            if (cbase + 1024 >= ge) { at_eof = true; break; }   // genome exhausted
-            if (cbase + 1024 >= end) {                          // run-out: stop when no owned k-mer can still end
+            const uint64_t nb = sc.chunk0 + ((uint64_t)(it + 1) << 10);
+            if (nb >= sc.ge) { at_eof = true; break; }          // genome exhausted
+            if (nb >= sc.end) {                                 // run-out: stop when no owned k-mer can still end
+                const uint32_t after_end = sc.after_end;
                 if (after_end >= (uint32_t)(TL - 1) || since_break <= after_end) break;
             }
         }
     }
-    if (ln) { drain3<ST>(P, A, q, qn, lq, 0, ln, gid, ord_base); __syncwarp(); }
-    if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[gid], 1);   // the text ended inside a '>' line
+    if (ln) { drain3<ST>(P, A, q, qn, lq, 0, ln, sc.gid, sc.chunk0 - sc.gs); __syncwarp(); }
+    if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[sc.gid], 1);   // the text ended inside a '>' line
 }
 
 template <int ST, bool BIG>
@@ -533,6 +593,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
     WarpQ3 *queues = reinterpret_cast<WarpQ3 *>(smem_raw + kPf3Words * 4);
     LaneQ3 *lqueues = reinterpret_cast<LaneQ3 *>(queues + kScanWarps);
+    SpanCtx *spans = reinterpret_cast<SpanCtx *>(lqueues + kScanWarps);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(pf_global);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);
@@ -551,7 +612,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
         const uint64_t gs = A.goff[gid], ge = gs + A.glen[gid];
         uint64_t start, end;
         if (!span_extent(A, si, gid, gs, ge, start, end)) continue;
-        scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], gid, gs, ge, start, end);
+        SpanCtx &sc = spans[threadIdx.x >> 5];
+        __syncwarp();
+        if (lane == 0) { sc.gs = gs; sc.ge = ge; sc.start = start; sc.end = end; sc.gid = gid; }
+        __syncwarp();
+        scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], sc);
     }
     if (qn) resolve3(P, A, q, 0, qn);
 }
