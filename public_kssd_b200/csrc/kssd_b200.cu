@@ -19,6 +19,7 @@
 #include "index_dist.cuh"
 #include "sketch_scan3.cuh"
 #include "sketch_fastq.cuh"
+#include "sketch_buckets.cuh"
 #include "set_ops.cuh"
 #include "composite.cuh"
 
@@ -115,8 +116,13 @@ struct kssd_ctx {
     uint64_t plan_key = 0;
     int plan_genomes = 0;
     uint32_t plan_spans = 0;
+    // bucket layout of the same batch layout (sketch_buckets.cuh): capacities from the genome lengths
+    bool plan_buckets = false;
+    uint32_t plan_bucket_total = 0, plan_bucket_maxcap = 0;
+    DevBuf bplan, bwork;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
+    bool total_ms_pending = false;               // last_ms[1] of a bucket-mode sketch: read off ev[0] .. ev[2] on demand
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -284,7 +290,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->runs, &c->keep, &c->counts, &c->minord,
+    for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->runs, &c->keep, &c->bplan, &c->bwork, &c->counts, &c->minord,
                       &c->cubtmp, &c->misc})
         b->release();
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
@@ -311,7 +317,17 @@ extern "C" int kssd_ctx_sync(const kssd_ctx_t *c)
     CU(cudaStreamSynchronize(c->stream));
     return KSSD_OK;
 }
-extern "C" float kssd_ctx_last_ms(const kssd_ctx_t *c, int which) { return (c && which >= 0 && which < 5) ? c->last_ms[which] : -1.f; }
+extern "C" float kssd_ctx_last_ms(const kssd_ctx_t *cc, int which)
+{
+    kssd_ctx *c = const_cast<kssd_ctx *>(cc);
+    if (!c || which < 0 || which >= 5) return -1.f;
+    if (which == 1 && c->total_ms_pending) {
+        cudaSetDevice(c->device);
+        if (cudaEventSynchronize(c->ev[2]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[2]);
+        c->total_ms_pending = false;
+    }
+    return c->last_ms[which];
+}
 
 // ------------------------------------------------------------------------------------------------
 // Stage I
@@ -627,6 +643,33 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
             CU(cudaMemcpyAsync(pb + p_nom, span_nom.data(), 8ull * c->plan_spans, cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemcpyAsync(pb + p_sgid, span_gid.data(), 4ull * c->plan_spans, cudaMemcpyHostToDevice, c->stream));
         }
+        {   // bucket capacities: twice the expected occurrences of a (component, genome) plus slack (sketch_buckets.cuh)
+            const int n_comp_b = c->info.component_num;
+            const double rate_b = (double)c->info.n_sampled / (double)(1ull << (4 * P.s)) / n_comp_b;
+            const uint64_t NB = (uint64_t)n_comp_b * n_genomes;
+            std::vector<uint32_t> boff(NB + 1, 0);
+            uint64_t run = 0;
+            uint32_t maxcap = 0;
+            bool ok = NB < (1u << 24);
+            for (int cc = 0; cc < n_comp_b && ok; cc++)
+                for (int g = 0; g < n_genomes; g++) {
+                    const double e = (double)glen[g] * rate_b;
+                    const uint64_t cap = ((uint64_t)(2.0 * e + 8.0 * sqrt(e)) + 64 + 1) & ~1ull;
+                    boff[(size_t)cc * n_genomes + g] = (uint32_t)run;
+                    run += cap;
+                    maxcap = (uint32_t)std::max<uint64_t>(maxcap, cap);
+                    if (cap > kBucketMaxCap || run > 0xfffffff0ull) { ok = false; break; }
+                }
+            boff[NB] = (uint32_t)run;
+            c->plan_buckets = ok;
+            c->plan_bucket_total = (uint32_t)run;
+            c->plan_bucket_maxcap = maxcap;
+            if (ok) {
+                CU(c->bplan.ensure((NB + 1) * 4));
+                CU(cudaMemcpyAsync(c->bplan.p, boff.data(), (NB + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+            }
+            CU(cudaStreamSynchronize(c->stream));
+        }
         CU(cudaStreamSynchronize(c->stream));      // the vectors die here
         c->plan_key = lkey; c->plan_genomes = n_genomes; c->plan_valid = true;
     }
@@ -639,6 +682,114 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     CU(c->meta.ensure(m_end));
     uint8_t *mb = c->meta.as<uint8_t>();
     CU(cudaMemsetAsync(mb + m_stat, 0, m_end, c->stream));
+
+    // ---- bucket mode (sketch_buckets.cuh): no global sort, one host round trip.  FASTA modes of the lazy scan, when every
+    // (component, genome) bucket fits one CTA's shared memory; an overflowing bucket sends the batch to the list mode below.
+    if (!is_fastq && mode != KSSD_MODE_BYREAD && c->scan_impl == 3 && c->plan_buckets && n_spans && !getenv("KSSD_NO_BUCKETS")) {
+        const int n_comp = c->info.component_num;
+        const uint32_t NB = (uint32_t)n_comp * (uint32_t)n_genomes;
+        // work area: bcnt[NB] | kept[NB + 1] | foff[NB + 1] | distinct[G] | overflow | n_occ
+        const size_t w_cnt = 0, w_kept = w_cnt + 4ull * NB, w_foff = w_kept + 4ull * (NB + 1), w_dist = w_foff + 4ull * (NB + 1),
+                     w_ovf = w_dist + 4ull * n_genomes, w_end = w_ovf + 8;
+        CU(c->bwork.ensure(w_end));
+        uint8_t *wb = c->bwork.as<uint8_t>();
+        CU(cudaMemsetAsync(wb, 0, w_end, c->stream));
+        CU(c->keys.ensure((size_t)c->plan_bucket_total * 8));
+        CU(c->flags.ensure((size_t)c->plan_bucket_total * 4));
+        CU(c->counts.ensure((size_t)c->plan_bucket_total * 2));
+        CU(c->minord.ensure((size_t)c->plan_bucket_total * 8));
+        ScanArgs A{};
+        A.seq = d_seq; A.seq_bytes = seq_bytes;
+        A.goff = reinterpret_cast<uint64_t *>(pb);
+        A.glen = reinterpret_cast<uint64_t *>(pb + p_glen);
+        A.span_nom = reinterpret_cast<uint64_t *>(pb + p_nom);
+        A.span_gid = reinterpret_cast<uint32_t *>(pb + p_sgid);
+        A.n_spans = n_spans;
+        A.gstatus = reinterpret_cast<int32_t *>(mb + m_stat);
+        A.zero_count = reinterpret_cast<uint32_t *>(mb + m_zero);
+        A.ticket = reinterpret_cast<uint32_t *>(mb + m_tick);
+        A.out_count = reinterpret_cast<uint32_t *>(mb + m_cnt);
+        A.drop_zero = 1;
+        A.bkeys = c->keys.as<uint64_t>();
+        A.boff = c->bplan.as<uint32_t>();
+        A.bcnt = reinterpret_cast<uint32_t *>(wb + w_cnt);
+        A.boverflow = reinterpret_cast<uint32_t *>(wb + w_ovf);
+        A.n_genomes = (uint32_t)n_genomes;
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        const bool big = 2 * (P.TL - 1) >= 32;
+        if (c->scan_stride == 3 && big) sketch_fasta3_kernel<3, true><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+        else if (c->scan_stride == 3) sketch_fasta3_kernel<3, false><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+        else if (big) sketch_fasta3_kernel<1, true><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+        else sketch_fasta3_kernel<1, false><<<c->sm_count, kScanThreads, kScan3SmemBytes, c->stream>>>(P, A, c->d_prefilter3);
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        uint32_t P2 = 32;
+        while (P2 < c->plan_bucket_maxcap) P2 <<= 1;
+        const size_t bsm = (size_t)P2 * 10;
+        CU(cudaFuncSetAttribute(bucket_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        uint32_t *d_kept = reinterpret_cast<uint32_t *>(wb + w_kept), *d_foff = reinterpret_cast<uint32_t *>(wb + w_foff);
+        bucket_finish_kernel<<<NB, kBucketThreads, bsm, c->stream>>>(A.bkeys, A.boff, A.bcnt, A.boverflow, (uint32_t)n_genomes, mode, opts ? opts->M : 1,
+                                                                   c->flags.as<uint32_t>(), c->counts.as<uint16_t>(), c->minord.as<uint64_t>(), d_kept,
+                                                                   reinterpret_cast<uint32_t *>(wb + w_dist), reinterpret_cast<uint32_t *>(wb + w_ovf) + 1);
+        size_t tmpb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpb, d_kept, d_foff, NB + 1, c->stream);
+        CU(c->cubtmp.ensure(tmpb));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpb, d_kept, d_foff, NB + 1, c->stream));
+        LAUNCHED(4);
+        std::vector<uint32_t> foff(NB + 1), distinct(n_genomes), zeros(n_genomes);
+        uint32_t ovf[2] = {0, 0};
+        kssd_sketch *S = new kssd_sketch();
+        S->ctx = c; S->n_genomes = n_genomes; S->n_comp = n_comp; S->mode = mode;
+        S->status.assign(n_genomes, 0);
+        CU(cudaMemcpyAsync(foff.data(), d_foff, 4ull * (NB + 1), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(distinct.data(), wb + w_dist, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(ovf, wb + w_ovf, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(S->status.data(), mb + m_stat, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(zeros.data(), mb + m_zero, 4ull * n_genomes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        if (ovf[0]) {
+            delete S;                                     // a bucket overflowed: list mode redoes the batch (counters are reset there)
+            CU(cudaMemsetAsync(mb + m_stat, 0, m_end, c->stream));
+        } else {
+            CU(cudaEventElapsedTime(&S->scan_ms, c->ev[0], c->ev[1]));
+            c->last_ms[0] = S->scan_ms;
+            const uint32_t total = foff[NB];
+            S->total = total;
+            S->comp_start.assign(n_comp + 1, 0);
+            S->index.assign((size_t)n_comp * (n_genomes + 1), 0);
+            const size_t nmax = std::max<size_t>(total, 1);
+            const size_t o_ids = 0, o_ord = (nmax * 4 + 15) & ~(size_t)15, o_ab = o_ord + nmax * 8, o_idx = (o_ab + nmax * 2 + 15) & ~(size_t)15;
+            S->blob_bytes = o_idx + S->index.size() * 8;
+            CU(cudaMallocAsync(&S->d_blob, S->blob_bytes, c->stream));
+            S->d_ids = reinterpret_cast<uint32_t *>(S->d_blob + o_ids);
+            S->d_ord = reinterpret_cast<uint64_t *>(S->d_blob + o_ord);
+            S->d_abund = reinterpret_cast<uint16_t *>(S->d_blob + o_ab);
+            S->d_index = reinterpret_cast<uint64_t *>(S->d_blob + o_idx);
+            if (total) {
+                bucket_move_kernel<<<NB, 128, 0, c->stream>>>(A.boff, d_foff, c->flags.as<uint32_t>(), c->counts.as<uint16_t>(), c->minord.as<uint64_t>(),
+                                                             S->d_ids, S->d_abund, S->d_ord);
+                LAUNCHED(1);
+            }
+            for (int cc = 0; cc < n_comp; cc++) {
+                const uint32_t *f = &foff[(size_t)cc * n_genomes];
+                S->comp_start[cc] = f[0];
+                uint64_t *ix = &S->index[(size_t)cc * (n_genomes + 1)];
+                for (int g = 0; g <= n_genomes; g++) ix[g] = (uint64_t)(f[g] - f[0]);
+            }
+            S->comp_start[n_comp] = total;
+            for (int g = 0; g < n_genomes; g++) {
+                if (S->status[g] & 1) S->status[g] = KSSD_E_HEADER_EOF;
+                else if ((uint64_t)distinct[g] + zeros[g] > c->info.hashlimit) S->status[g] = KSSD_E_CROWD;      // keycount (see the list mode below)
+                else S->status[g] = 0;
+            }
+            S->n_occ = ovf[1];
+            CU(cudaMemcpyAsync(S->d_index, S->index.data(), S->index.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaEventRecord(c->ev[2], c->stream));      // (kssd_ctx_last_ms(1) waits for it; the call itself does not)
+            c->total_ms_pending = true;
+            *out = S;
+            return KSSD_OK;
+        }
+    }
 
     // occurrence buffer: expected total/|sampling| ; 4x head-room, retried on overflow
     const double rate = (double)c->info.n_sampled / (double)(1ull << (4 * P.s));
@@ -794,6 +945,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     CU(cudaEventRecord(c->ev[2], c->stream));
     CU(cudaEventSynchronize(c->ev[2]));
     CU(cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[2]));
+    c->total_ms_pending = false;
     *out = S;
     return KSSD_OK;
 }

@@ -57,6 +57,13 @@ struct ScanArgs {
     int32_t *gstatus;            // per genome flags (bit 0: header ran into EOF)
     uint32_t *zero_count;        // per genome: occurrences of code 0 dropped by the FASTA quirk (they still count as keys)
     int drop_zero;               // FASTA quirk: drtuple == 0 is never stored (iseq2comem.c:258)
+    // bucket mode (sketch_scan3.cuh resolver, csrc/sketch_buckets.cuh): occurrences go straight to the (component, genome)
+    // bucket they belong to -- bkeys[boff[b] + n] = id << 36 | offset -- instead of one list that needs a global sort
+    uint64_t *bkeys;             // null = list mode
+    const uint32_t *boff;        // bucket starts (n_buckets + 1), capacities from the genome lengths
+    uint32_t *bcnt;              // occurrences per bucket (may exceed the capacity: then *boverflow is set)
+    uint32_t *boverflow;
+    uint32_t n_genomes;
 };
 
 struct WarpQueue {

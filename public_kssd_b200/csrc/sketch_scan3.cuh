@@ -90,18 +90,32 @@ __device__ __forceinline__ bool gtab_probe0(const unsigned long long *__restrict
 // '\r' between them, all inside the genome.  Runs for the few positions that passed every filter and the exact lookup.
 __device__ __forceinline__ bool verify_window(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t p, int TL)
 {
-    // most windows lie inside one line: the 2k bytes ending at p are all letters -- independent loads, one latency
-    if (p - gs + 1 >= (uint64_t)TL) {
-        uint32_t other = 0;
+    // The 40 bytes ending at p, all requested at once (one latency): bit i of `letter` / `skip` describes byte p - i.
+    // The window is the first 2k letters walking back; it is genuine iff every byte up to its 2k-th letter is a letter
+    // or a line end.  Windows with more than 40 - 2k line-end bytes inside (very short lines) take the byte loop.
+    const uint32_t avail = (uint32_t)min((uint64_t)40, p - gs + 1);
+    uint64_t letter = 0, skip = 0;
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-            if (i < TL) {
-                const uint32_t l = __ldg(seq + p - i) | 0x20u;
-                other |= (uint32_t)!(l == 'a' || l == 'c' || l == 'g' || l == 't');
-            }
-        if (!other) return true;
+    for (int i = 0; i < 40; i++)
+        if ((uint32_t)i < avail) {
+            const uint32_t b = __ldg(seq + p - i), l = b | 0x20u;
+            letter |= (uint64_t)(l == 'a' || l == 'c' || l == 'g' || l == 't') << i;
+            skip |= (uint64_t)(b == '\n' || b == '\r') << i;
+        }
+    const uint64_t bad = ~(letter | skip);                        // (bytes beyond `avail` count as bad)
+    const uint32_t lo_l = (uint32_t)letter, n_lo = __popc(lo_l);
+    int t;                                                         // position of the 2k-th letter
+    if (n_lo >= (uint32_t)TL) t = (int)__fns(lo_l, 0, TL);
+    else {
+        const uint32_t hi_l = (uint32_t)(letter >> 32);
+        t = __popc(hi_l) >= (uint32_t)TL - n_lo ? 32 + (int)__fns(hi_l, 0, TL - (int)n_lo) : -1;
     }
-    int cnt = 0;
+    if (t >= 0) return (bad & ((2ull << t) - 1ull)) == 0;
+    if (bad & ((1ull << avail) - 1ull)) return false;             // something else before 2k letters were seen
+    if (avail < 40) return false;                                 // the genome starts before them
+    if (p - gs < 40) return false;
+    int cnt = __popcll(letter);
+    p -= 40;
     for (;;) {
         const uint32_t b = __ldg(seq + p);
         const uint32_t l = b | 0x20u;
@@ -148,6 +162,15 @@ __device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, 
             if (found && A.drop_zero && dr == 0) { found = false; atomicAdd(&A.zero_count[gid], 1u); }
         }
     }
+    if (A.bkeys) {                                        // bucket mode: straight to the (component, genome) bucket
+        if (found) {
+            const uint32_t b = (uint32_t)(key >> 56) * A.n_genomes + gid, lo = A.boff[b], cap = A.boff[b + 1] - lo;
+            const uint32_t n = atomicAdd(&A.bcnt[b], 1u);
+            if (n < cap) A.bkeys[lo + n] = ((key & 0x0fffffffull) << 36) | (ordv & 0xfffffffffull);
+            else *A.boverflow = 1u;
+        }
+        return;
+    }
     const uint32_t fm = __ballot_sync(kFull, found);
     if (fm) {
         uint32_t base = 0;
@@ -187,8 +210,13 @@ __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArg
 
 // Parked lanes first .. first+m-1, one per lane.  ST = 3: every block hit i (windows 3i-2 .. 3i) is settled by one read
 // of the block's table entry; ST = 1: the bitmap was exact, every hit is a member.  Members go to the candidate queue.
+#ifdef KSSD_DRAIN_NOINLINE
+#define KSSD_DRAIN_ATTR __noinline__
+#else
+#define KSSD_DRAIN_ATTR __forceinline__
+#endif
 template <int ST>
-__device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, const LaneQ3 &lq, uint32_t first,
+__device__ KSSD_DRAIN_ATTR void drain3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, const LaneQ3 &lq, uint32_t first,
                                        uint32_t m, uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
@@ -197,22 +225,37 @@ __device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A,
     if (lane < m) { cand = lq.cand[e]; wm = lq.wmask[e]; F = lq.flags[e]; off = lq.off[e]; }
     if (ST == 1) cand &= wm;
     const uint32_t *ye = &lq.y[0][e];                     // word a of the entry: ye[a * kQueueCap]
-    while (__any_sync(kFull, cand != 0)) {
-        uint32_t hits = 0;                                // ST = 3: bit r <-> window 3i - r is a member
-        int i = 0;
-        if (cand) {
-            i = __ffs(cand) - 1;
+    // S(i) = the 16 bases from X position 3i-2 on (the three windows of block hit i start at its bases 2, 1, 0); the
+    // table entry of the NEXT hit is requested before the current one is looked at
+    auto span16 = [&](int i) -> uint32_t {
+        const int o = 2 * (P.out + 3 * i) - 4;
+        if (o < 0) return ye[0] << (-o);
+        const uint32_t a = (uint32_t)o >> 5;
+        return __funnelshift_r(ye[a * kQueueCap], a < 3 ? ye[(a + 1) * kQueueCap] : 0u, (uint32_t)o);
+    };
+    int i = 0;
+    uint32_t S = 0;
+    unsigned long long mm = 0;
+    bool act = cand != 0;
+    if (act) {
+        i = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (ST == 3) { S = span16(i); mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]); }
+    }
+    while (__any_sync(kFull, act)) {
+        const bool act_n = cand != 0;
+        int i_n = 0;
+        uint32_t S_n = 0;
+        unsigned long long mm_n = 0;
+        if (act_n) {
+            i_n = __ffs(cand) - 1;
             cand &= cand - 1;
+            if (ST == 3) { S_n = span16(i_n); mm_n = __ldg(&P.gtab[(S_n >> 4) & 0xfffffu]); }
+        }
+        uint32_t hits = 0;                                // ST = 3: bit r <-> window 3i - r is a member
+        if (act) {
             if (ST == 1) hits = 1u;
             else {
-                // S = the 16 bases from X position 3i-2 on: the three windows start at its bases 2, 1, 0
-                const int o = 2 * (P.out + 3 * i) - 4;
-                uint32_t S;
-                if (o >= 0) {
-                    const uint32_t a = (uint32_t)o >> 5;
-                    S = __funnelshift_r(ye[a * kQueueCap], a < 3 ? ye[(a + 1) * kQueueCap] : 0u, (uint32_t)o);
-                } else S = ye[0] << (-o);
-                const unsigned long long mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]);
                 const uint32_t m01 = (uint32_t)mm, m2 = (uint32_t)(mm >> 32);
                 uint32_t e0, e1, e2;                      // what each window holds outside the block, folded to 4 bits
                 if (P.s == 6) { e0 = (S >> 24) & 15u; e1 = ((S >> 2) & 3u) | ((S >> 22) & 12u); e2 = S & 15u; }
@@ -238,6 +281,7 @@ __device__ __forceinline__ void drain3(const SketchParams &P, const ScanArgs &A,
             }
             queue_push3(P, A, q, qn, has, kmer, ord_base + off, j, F, gid);
         }
+        act = act_n; i = i_n; S = S_n; mm = mm_n;
     }
 }
 
