@@ -33,7 +33,7 @@
 namespace kssd {
 
 #ifndef KSSD_SCAN_THREADS
-#define KSSD_SCAN_THREADS 640
+#define KSSD_SCAN_THREADS 512
 #endif
 constexpr int kScanThreads = KSSD_SCAN_THREADS; // warps per SM = threads / 32 (one CTA per SM)
 constexpr int kScanWarps = kScanThreads / 32;
