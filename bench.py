@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dist-scale", action="store_true", help="skip the 10,000 x 100,000 Stage III measurement (N = 1 only)")
+    ap.add_argument("--dist-batches", type=int, default=8, help="query batches of the configs[2]-size search")
     ap.add_argument("--ref-sample", type=int, default=0, help="genomes in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -224,7 +225,23 @@ def main():
             return
         n_s = args.ref_sample or max(16, min(4 * cores, 256))
         n_s = min(n_s, args.genomes)
-        gens = [synth.to_fasta(b, n, 80) for n, b in synth.cluster_genomes(n_s, args.genome_len, seed=20260101, cluster_size=20)]
+        # the same bytes as the b200 arm's first n_s genomes: its device generator is sequential per genome, so a batch of n_s
+        # genomes with the same seed is a prefix of the 1000-genome batch (host generator only where there is no GPU at all)
+        same_bytes = False
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dev0 = torch.device("cuda", 0)
+                buf0, goff0, glen0 = make_batch_device(n_s, args.genome_len, 20260101, dev0)
+                hb = buf0.cpu().numpy()
+                gens = [hb[int(goff0[i]):int(goff0[i]) + int(glen0[i])].copy() for i in range(n_s)]
+                del buf0, hb
+                same_bytes = True
+        except Exception:
+            same_bytes = False
+        if not same_bytes:
+            gens = [synth.to_fasta(b, n, 80) for n, b in synth.cluster_genomes(n_s, args.genome_len, seed=20260101, cluster_size=20)]
+        config["reference_sample_is_prefix_of_b200_batch"] = same_bytes
         r = reference_run(gens, table, args.steps, args.warmup, cores)
         val = r["bp"] / r["sketch_s"] / 1e9
         sample = f"{n_s} of the workload's genomes ({r['bytes'] / 1e6:.0f} MB FASTA on tmpfs), kssd dist -p {cores}, per step"
@@ -339,43 +356,7 @@ def main():
                                        "note": "count kernel; bytes = 4*Nq + 8*Nq + 4*P + 4*Q*R (SURVEY.md s8d); 10^6 cells is launch-latency scale -- "
                                                "profiles/r1_dist_ncu_summary.md has the 10^9-pair run (0.52 of peak)"}})
     else:
-        # north-star scheme: reference index sharded by code range, queries broadcast, NCCL reduce-scatter of the
-        # partial count matrices; rank 0's sketches serve as reference and query set for every rank
-        from public_kssd_b200 import parallel
-        ids0 = np.empty(n_codes, dtype=np.uint32)
-        capi.check(L.kssd_sketch_fetch(sk_h, 0, capi.ptr(ids0, capi.C.c_uint32), None, None, None))
-        obj = [ids0 if rank == 0 else None, index_host if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        ref_ids, ref_index = obj
-        per_mode = {}
-        for mode in ("code", "code_p2p"):
-            sd = parallel.ShardedDist(ctx, world, rank, code_bits=4 * min(7, K - DRLEVEL), mode=mode).build_reference(ref_ids, ref_index)
-            times = []
-            for it in range(4):
-                # timed: queries broadcast -> counts -> statistics left on the device (what the N = 1 line times as kernels);
-                # the last, untimed pass fetches counts and rows for the checks below
-                check_pass = it == 3
-                barrier()
-                t0 = time.perf_counter()
-                lo, hi, block, rows = sd.search(ref_ids if rank == 0 else None, ref_index if rank == 0 else None, src=0, stats_opts={},
-                                                fetch_counts=check_pass, fetch_stats=check_pass)
-                barrier()
-                if not check_pass:
-                    times.append(time.perf_counter() - t0)
-            tt = torch.tensor([min(times)], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            own = np.diff(ref_index).astype(np.uint32)
-            per_mode[mode] = (float(tt.item()), int(len(rows)) if rows is not None else 0,
-                              bool(np.array_equal(np.diag(block[:, lo:hi]), own[lo:hi])) if hi > lo else True)
-            sd.close()
-        t_best = per_mode["code_p2p"][0]
-        dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": pairs / t_best, "ms": t_best * 1e3,
-                          "ms_nccl_reduce_scatter": per_mode["code"][0] * 1e3,
-                          "rows_on_rank0": per_mode["code_p2p"][1], "diag_ok": per_mode["code_p2p"][2] and per_mode["code"][2],
-                          "rows_agree": per_mode["code_p2p"][1] == per_mode["code"][1],
-                          "sharding": "reference index by code range across ranks, query sketches broadcast; the count kernel adds into the "
-                                      "owning rank's rows over peer memory (ms), or partial matrices + NCCL reduce-scatter "
-                                      "(ms_nccl_reduce_scatter); statistics on the owner of each query block (wall clock incl. barriers)"})
+        dist_info.update({"metric": "dist_pairs_per_s", "note": "at N > 1 the search is measured at configs[2] size only (configs2_scale below)"})
 
     # ---- end to end through the C-ABI with host buffers ----
     host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
@@ -417,52 +398,31 @@ def main():
 
     scan = float(np.median(scan_ms))
     traffic, traffic_src = None, None
-    tf = ROOT / "profiles" / "r1_sketch_traffic.json"          # dram bytes of this kernel from one `ncu --set full` capture
+    tf = ROOT / "profiles" / "r2_sketch_traffic.json"          # dram bytes of this kernel from one `ncu --set full` capture
     if tf.exists():
         try:
             tj = json.loads(tf.read_text())
-            if int(tj["algorithmic_bytes_per_launch"]) == text_bytes:
-                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_sketch_traffic.json (ncu dram__bytes_read+write, same launch shape)"
+            if tj.get("kernel", "").startswith("sketch_fasta3"):
+                traffic, traffic_src = tj["traffic_bytes_per_launch"] / tj["algorithmic_bytes_per_launch"] * text_bytes, "profiles/r2_sketch_traffic.json (ncu dram__bytes_read+write per algorithmic byte, 200-genome launch, scaled to this launch)"
         except Exception:
             pass
     roof = {"bound": "hbm", "achieved": text_bytes / (scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": text_bytes / (scan * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "kernel": "sketch_fasta32_kernel", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
+            "kernel": "sketch_fasta3_kernel<3, true>", "kernel_ms": scan, "algorithmic_bytes": text_bytes}
 
     # (after the end-to-end leg: the host-side generation below must not disturb where its pinned buffer lives)
-    if world == 1 and not args.no_dist_scale and args.genomes >= 1000:
-        # the second headline metric at BASELINE.json configs[2] size: 100,000 reference sketches x ~1,220 codes (cluster /
-        # mutation model of SURVEY.md s8d), 10,000 queries, 10^9 pairs; skip_zero listing (the cells a search prints)
+    if not args.no_dist_scale and args.genomes >= 1000:
+        # the second headline metric at BASELINE.json configs[2] size, at every N: 100,000 reference sketches sharded over the
+        # ranks, batches of 10,000 queries (10^9 pairs each), content checked against one GPU and the oracle (bench_dist.py)
         try:
-            rc, ri = synth.synth_sketches(100_000, 1220, seed=5, cluster_size=20)
-            qc, qi = synth.synth_sketches(10_000, 1220, seed=5, cluster_size=2)
-            ixb = ctx.combco2mco(rc, ri)
-            tq = torch.from_numpy(qc.view(np.int32)).to(dev)
-            ti = torch.from_numpy(qi.view(np.int64)).to(dev)
-            qs_, rs_ = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
-            best = {}
-            for sparse in (False, True):
-                for it in range(3):
-                    jb = kssd.DistJob(ctx, qs_, rs_, sparse=sparse)
-                    jb.accumulate_dev(ixb, tq.data_ptr(), ti.data_ptr(), len(qc))
-                    c_ms = 0.0 if sparse else ctx.last_ms(3)
-                    nr = jb.stats(skip_zero=1, fetch=False)
-                    tot = c_ms + ctx.last_ms(4) + (ctx.last_ms(3) if sparse else 0.0)
-                    if sparse not in best or tot < best[sparse][0]:
-                        best[sparse] = (tot, c_ms if not sparse else ctx.last_ms(3), int(nr))
-                    jb.close()
-            ixb.close()
-            big_pairs = 10_000 * 100_000
-            dist_info["configs2_scale"] = {
-                "pairs": big_pairs, "ref_postings": int(len(rc)), "query_codes": int(len(qc)), "printed_rows": best[True][2],
-                "dense_job_ms": best[False][0], "dense_count_ms": best[False][1], "sparse_job_ms": best[True][0],
-                "pairs_per_s": big_pairs / (best[True][0] * 1e-3), "pairs_per_s_dense": big_pairs / (best[False][0] * 1e-3),
-                "rows_agree": best[True][2] == best[False][2],
-                "note": "device time (CUDA events in the library), sketches synthetic and resident; sparse job = no Q x R matrix "
-                        "(kssd_dist_create_sparse), dense job = count matrix + listing + statistics"}
-            del tq, ti
+            import bench_dist
+            dist_info["configs2_scale"] = bench_dist.run(ctx, world, rank, dev, peak, batches=args.dist_batches)
+            if world > 1:
+                dist_info["pairs_per_s"] = dist_info["configs2_scale"]["pairs_per_s"]
+                dist_info["pairs"] = dist_info["configs2_scale"]["pairs_per_batch"] * dist_info["configs2_scale"]["batches"]
         except Exception as ex:  # must not take the headline measurement down
-            dist_info["configs2_scale"] = {"failed": str(ex)}
+            import traceback
+            dist_info["configs2_scale"] = {"failed": str(ex), "trace": traceback.format_exc()[-800:]}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -485,13 +445,14 @@ def main():
             from oracle import oracle as O
             orc = O.Ctx(K, SUBK, DRLEVEL, table)
             ok = True
-            for i in range(min(3, n_s)):
+            n_par = min(32, n_s)
+            for i in range(n_par):
                 ids_o, _ = orc.fasta(gens[i])
                 ok &= bool(np.array_equal(np.sort(ids_o), ids_e2e[int(ix_e2e[i]):int(ix_e2e[i + 1])]))
             cpu_baseline = {"value": r["bp"] / r["sketch_s"] / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
                             "sample": f"first {n_s} genomes of rank 0's batch ({r['bytes'] / 1e6:.0f} MB FASTA on tmpfs), one `kssd dist -p {cores}` run",
                             "sketch_s": r["sketch_s"], "index_s": r.get("index_s"), "dist_s": r.get("dist_s"),
-                            "dist_pairs_per_s": r.get("dist_pairs", 0) / max(r.get("dist_s", 1e-9), 1e-9), "oracle_parity_on_sample": ok,
+                            "dist_pairs_per_s": r.get("dist_pairs", 0) / max(r.get("dist_s", 1e-9), 1e-9), "oracle_parity_on_sample": ok, "oracle_parity_genomes": n_par,
                             "gpu_same_files": {"value": r["bp"] / r["files"]["total_s"] / 1e9, "unit": "Gbp/s", "total_s": r["files"]["total_s"],
                                                "matches_device_path": r["files"]["matches_device_path"],
                                                "note": "kssd_stage1_files on the same tmpfs files the reference just read: host threads read into "

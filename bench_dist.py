@@ -1,0 +1,286 @@
+"""bench.py's second metric at BASELINE.json configs[2] size: 100,000 reference sketches x ~1,220 codes searched with batches of
+10,000 queries (10^9 pairs per batch), at every N.
+
+Sharding: the reference index is sharded by GENOME range -- rank r indexes references [r R/N, (r+1) R/N) -- the
+query sketches are broadcast (NCCL, one batch ahead of the compute), every rank runs the sparse Stage III job on its columns
+(count + filter + list + statistics, no Q x R matrix), and its rows are final as they are: no reduction.  The north-star
+variant (index sharded by code range + NCCL reduce-scatter of dense partial matrices) and the peer-memory variant are timed
+next to it on one batch as the baselines they are.  Times are CUDA events on the library stream, max over ranks.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+N_REF, N_QRY, CODES, BATCHES = 100_000, 10_000, 1220, 8
+
+
+def _checksum(rows) -> tuple[int, int]:
+    """order-independent digest of (qry, ref, shared) rows"""
+    if len(rows) == 0:
+        return 0, 0
+    q = rows["qry"].astype(np.uint64)
+    r = rows["ref"].astype(np.uint64)
+    s = rows["shared"].astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = (q * np.uint64(0x9E3779B97F4A7C15)) ^ (r * np.uint64(0xC2B2AE3D27D4EB4F)) ^ (s * np.uint64(0x165667B19E3779F9))
+        h ^= h >> np.uint64(29)
+        h *= np.uint64(0xBF58476D1CE4E5B9)
+    return int(h.sum(dtype=np.uint64)), int(len(rows))
+
+
+def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_qry: int = N_QRY, batches: int = BATCHES,
+        baselines: bool = True) -> dict:
+    import torch
+    import torch.distributed as dist
+    from public_kssd_b200 import kssd, parallel, synth
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- data: rank 0 generates (cluster / mutation model of SURVEY.md s8d), everybody gets the references; the query
+    # batches stay on rank 0 until they are broadcast inside the timed loop
+    t0 = time.perf_counter()
+    meta = torch.zeros(2 + 2 * batches, dtype=torch.int64, device=dev)
+    q_host = []
+    if rank == 0:
+        rc, ri = synth.synth_sketches(n_ref, CODES, seed=5, cluster_size=20)
+        for b in range(batches):
+            q_host.append(synth.synth_sketches(n_qry, CODES, seed=5, cluster_size=2, member_seed=None if b == 0 else 1000 + b))
+        meta[0], meta[1] = len(rc), n_ref
+        for b, (qc, qi) in enumerate(q_host):
+            meta[2 + 2 * b], meta[3 + 2 * b] = len(qc), len(qi)
+    if world > 1:
+        dist.broadcast(meta, 0)
+    m = meta.cpu().numpy()
+    n_codes = int(m[0])
+    if rank == 0:
+        t_rc = torch.from_numpy(rc.view(np.int32)).to(dev)
+        t_ri = torch.from_numpy(ri.view(np.int64)).to(dev)
+    else:
+        t_rc = torch.empty(n_codes, dtype=torch.int32, device=dev)
+        t_ri = torch.empty(n_ref + 1, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(t_rc, 0)
+        dist.broadcast(t_ri, 0)
+    ref_index_host = t_ri.cpu().numpy().view(np.uint64)
+    ref_sizes = np.diff(ref_index_host).astype(np.uint32)
+    q_dev = []
+    for b in range(batches):
+        if rank == 0:
+            qc, qi = q_host[b]
+            q_dev.append((torch.from_numpy(qc.view(np.int32)).to(dev), torch.from_numpy(qi.view(np.int64)).to(dev)))
+        else:
+            q_dev.append((torch.empty(int(m[2 + 2 * b]), dtype=torch.int32, device=dev), torch.empty(int(m[3 + 2 * b]), dtype=torch.int64, device=dev)))
+    gen_s = time.perf_counter() - t0
+
+    # ---- this rank's shard of the index: references [lo, hi)
+    g = parallel.genome_shard(n_ref, world, rank)
+    lo, hi = g.start, g.stop
+    a, bnd = int(ref_index_host[lo]), int(ref_index_host[hi])
+    shard_codes = t_rc[a:bnd]
+    shard_index = (t_ri[lo:hi + 1] - t_ri[lo]).contiguous()
+    ix_ms = []
+    index = None
+    for _ in range(2):
+        if index is not None:
+            index.close()
+        torch.cuda.synchronize()
+        index = ctx.combco2mco_dev(shard_codes.data_ptr(), shard_index.data_ptr(), hi - lo, bnd - a)
+        ix_ms.append(ctx.last_ms(2))
+    shard_sizes = ref_sizes[lo:hi]
+    cm = (n_ref * n_qry) & 0xFFFFFFFF
+
+    qsizes = {}
+
+    def search(b, fetch=False):
+        tq, ti = q_dev[b]
+        if b not in qsizes:                                         # sketch sizes are metadata (cofiles.stat): read once, untimed
+            qsizes[b] = (ti[1:] - ti[:-1]).cpu().numpy().astype(np.uint32)
+        qsz = qsizes[b]
+        job = kssd.DistJob(ctx, qsz, shard_sizes, sparse=True)
+        job.accumulate_dev(index, tq.data_ptr(), ti.data_ptr(), int(tq.numel()))
+        rows = job.stats(skip_zero=1, fetch=fetch, cmprsn_num=cm)
+        t = (ctx.last_ms(3), ctx.last_ms(4))
+        job.close()
+        return rows, t
+
+    def bcast(b):
+        if world == 1:
+            return None
+        return [dist.broadcast(q_dev[b][0], 0, async_op=True), dist.broadcast(q_dev[b][1], 0, async_op=True)]
+
+    def wait(w):
+        if w is not None:
+            for x in w:
+                x.wait()
+            torch.cuda.current_stream().synchronize()
+
+    # warm-up (also fills the non-zero ranks' copies once; the timed loop broadcasts them again)
+    for b in range(batches):
+        wait(bcast(b))
+        search(b)
+    best = None
+    for rep in range(2):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nrows, phases = 0, []
+        nxt = bcast(0)
+        for b in range(batches):
+            wait(nxt)
+            nxt = bcast(b + 1) if b + 1 < batches else None          # the next batch travels while this one is searched
+            n, t = search(b)
+            nrows += int(n)
+            phases.append(t)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        if best is None or ms < best[0]:
+            best = (ms, nrows, phases)
+    total_ms, nrows, phases = best
+    tr = torch.tensor([nrows], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tr)
+    pairs = batches * n_qry * n_ref
+    out = {"pairs_per_batch": n_qry * n_ref, "batches": batches, "refs": n_ref, "queries_per_batch": n_qry, "ref_postings": n_codes,
+           "sharding": f"reference index by genome range over {world} rank(s), query batches broadcast one ahead (NCCL), sparse job per rank, no reduction",
+           "ms_total": total_ms, "ms_per_batch": total_ms / batches, "pairs_per_s": pairs / (total_ms * 1e-3),
+           "printed_rows": int(tr.item()), "index_ms_per_rank": float(min(ix_ms)),
+           "rank0_kernel_ms_per_batch": {"count_list": float(np.mean([p[0] for p in phases])), "rows": float(np.mean([p[1] for p in phases]))},
+           "timing": "CUDA events on the library stream around all batches (host gaps included), max over ranks", "generation_s": gen_s}
+
+    # ---- content: batch 0's rows over all ranks against one GPU holding the whole index (rank 0), and against the oracle
+    rows0, _ = search(0, fetch=True)
+    rows0["ref"] += lo
+    h, n = _checksum(rows0)
+    agg = torch.tensor([h & 0x7FFFFFFFFFFFFFFF, n], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(agg)
+    if rank == 0:
+        tq, ti = q_dev[0]
+        qsz0 = (ti[1:] - ti[:-1]).cpu().numpy().astype(np.uint32)
+        full = index if world == 1 else ctx.combco2mco_dev(t_rc.data_ptr(), t_ri.data_ptr(), n_ref, n_codes)
+        dj = kssd.DistJob(ctx, qsz0, ref_sizes)                    # dense job on one GPU: another kernel, the whole matrix
+        dj.accumulate_dev(full, tq.data_ptr(), ti.data_ptr(), int(tq.numel()))
+        dense_count_ms = ctx.last_ms(3)
+        want = dj.stats(skip_zero=1, cmprsn_num=cm)
+        dense_stats_ms = ctx.last_ms(4)
+        hw, nw = _checksum(want)
+        if world > 1:
+            # per-rank digests were summed modulo 2^63 each: recompute the one-GPU digest the same way
+            parts = [want[(want["ref"] >= parallel.genome_shard(n_ref, world, r).start) & (want["ref"] < parallel.genome_shard(n_ref, world, r).stop)]
+                     for r in range(world)]
+            hw = sum(_checksum(p)[0] & 0x7FFFFFFFFFFFFFFF for p in parts) & 0xFFFFFFFFFFFFFFFF
+            got = int(agg[0].item()) & 0xFFFFFFFFFFFFFFFF
+        else:
+            hw &= 0x7FFFFFFFFFFFFFFF
+            got = int(agg[0].item())
+        out["content_ok"] = bool(got == hw and int(agg[1].item()) == nw)
+        out["content_check"] = "batch 0: digest + count of (qry, ref, shared) rows over all ranks == the dense job of one GPU holding the whole index"
+        # oracle (checker): brute force through the CPU restatement on the first 16 queries x first 2000 references
+        try:
+            from oracle import oracle as O
+            O.build()
+            nq_o, nr_o = 16, 2000
+            rch, rih = t_rc[: int(ref_index_host[nr_o])].cpu().numpy().view(np.uint32), ref_index_host[: nr_o + 1]
+            qih = ti[: nq_o + 1].cpu().numpy().view(np.uint64)
+            qch = tq[: int(qih[nq_o])].cpu().numpy().view(np.uint32)
+            uc, uo, gids = O.csr_from_combco(rch, rih)
+            exp = O.dist_counts(qch, qih, uc, uo, gids, nr_o)
+            sel = want[(want["qry"] < nq_o) & (want["ref"] < nr_o)]
+            got_m = np.zeros((nq_o, nr_o), dtype=np.uint32)
+            got_m[sel["qry"], sel["ref"]] = sel["shared"]
+            ok = bool(np.array_equal(got_m, exp))
+            for row in sel[:: max(1, len(sel) // 64)]:
+                keep, v = O.output_ctrl(ref_sizes[row["ref"]], qsz0[row["qry"]], row["shared"], 0, 0, 20, 6, 1.0, cm)
+                ok &= bool(keep and abs(row["dist"] - v[1]) <= 1e-6 * abs(v[1]) and abs(row["metric"] - v[0]) <= 1e-6 * abs(v[0]))
+            out["oracle_ok"] = ok
+            out["oracle_check"] = f"shared counts of the first {nq_o} queries x {nr_o} references and 64 of their statistics rows against the CPU oracle"
+        except Exception as ex:      # the checker must not take the measurement down
+            out["oracle_ok"] = None
+            out["oracle_check"] = f"failed: {ex}"
+        # ---- one GPU, whole index: the dense job's count kernel against the HBM roofline, atomics/s, end to end from host buffers
+        if world == 1:
+            P = int(want["shared"].sum(dtype=np.uint64))
+            nq_codes = int(tq.numel())
+            alg = 4 * nq_codes + 16 * nq_codes + 4 * P + 4 * n_qry * n_ref
+            cts, sts = [dense_count_ms], [dense_stats_ms]
+            for _ in range(2):
+                dj2 = kssd.DistJob(ctx, qsz0, ref_sizes)
+                dj2.accumulate_dev(full, tq.data_ptr(), ti.data_ptr(), nq_codes)
+                cts.append(ctx.last_ms(3))
+                dj2.stats(skip_zero=1, fetch=False, cmprsn_num=cm)
+                sts.append(ctx.last_ms(4))
+                dj2.close()
+            c_ms, s_ms = float(min(cts)), float(min(sts))
+            out["dense_job"] = {"count_ms": c_ms, "stats_ms": s_ms, "pairs_per_s": n_qry * n_ref / ((c_ms + s_ms) * 1e-3), "increments": P,
+                                "atomics_per_s": P / (c_ms * 1e-3)}
+            traffic = None
+            try:
+                import json
+                from pathlib import Path
+                tj = json.loads((Path(__file__).resolve().parent / "profiles" / "r2_dist_traffic.json").read_text())
+                traffic = tj.get("traffic_bytes_per_launch")
+            except Exception:
+                pass
+            out["roofline"] = {"bound": "hbm", "kernel": "dist_count_rows_kernel", "achieved": alg / (c_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                               "frac": alg / (c_ms * 1e-3) / 1e9 / peak_gbs, "traffic": traffic, "algorithmic_bytes": alg,
+                               "note": "bytes = 4 Nq (codes) + 16 Nq (two offsets per lookup) + 4 P (postings) + 4 Q R (matrix written once), SURVEY.md s8d"}
+            # end to end: host query buffers in, statistics rows on the host out (sparse job)
+            qc_h, qi_h = q_host[0]
+            e2e = []
+            for _ in range(3):
+                t1 = time.perf_counter()
+                sj = kssd.DistJob(ctx, qsz0, ref_sizes, sparse=True)
+                sj.accumulate(full, qc_h, qi_h)
+                rows_h = sj.stats(skip_zero=1, cmprsn_num=cm)
+                sj.close()
+                e2e.append(time.perf_counter() - t1)
+            out["e2e"] = {"value": n_qry * n_ref / min(e2e), "unit": "pairs/s", "ms": min(e2e) * 1e3, "h2d_bytes": int(qc_h.nbytes + qi_h.nbytes + qsz0.nbytes),
+                          "d2h_bytes": int(rows_h.nbytes), "note": "kssd_dist_create_sparse + add_host + stats + fetch_stats: query sketches from host memory, rows back"}
+        dj.close()
+        if world > 1:
+            full.close()
+    if world > 1:
+        ok = torch.tensor([1 if out.get("content_ok", True) else 0], device=dev, dtype=torch.int64)
+        dist.broadcast(ok, 0)
+
+    # ---- the baselines at N > 1, one batch: index by CODE range + NCCL reduce-scatter of dense partial matrices (north
+    # star), and the same placement with the count kernel adding into the owner's rows over peer memory
+    if world > 1 and baselines:
+        rc_h = t_rc.cpu().numpy().view(np.uint32)
+        tq, ti = q_dev[0]
+        for mode in ("code", "code_p2p"):
+            try:
+                sd = parallel.ShardedDist(ctx, world, rank, code_bits=28, mode=mode).build_reference(rc_h, ref_index_host)
+                ts = []
+                for it in range(3):
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    torch.cuda.current_stream().synchronize()
+                    sd.search(tq if rank == 0 else None, ti if rank == 0 else None, src=0, stats_opts={"skip_zero": 1}, fetch_counts=False, fetch_stats=False)
+                    e1.record(stream)
+                    barrier()
+                    if it:
+                        ts.append(e0.elapsed_time(e1))
+                tt = torch.tensor([min(ts)], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                out[f"baseline_{mode}_ms_per_batch"] = float(tt.item())
+                sd.close()
+            except Exception as ex:
+                out[f"baseline_{mode}_ms_per_batch"] = f"failed: {ex}"
+        out["baseline_note"] = ("code = reference index sharded by code range, queries broadcast, dense partial Q x R matrices combined by ncclReduceScatter "
+                                "(north star); code_p2p = same placement, RED.ADD into the owner's rows over NVLink peer mappings; both one batch, "
+                                "library-stream events incl. broadcast and barriers")
+    index.close()
+    return out

@@ -90,32 +90,36 @@ __device__ __forceinline__ bool gtab_probe0(const unsigned long long *__restrict
 // '\r' between them, all inside the genome.  Runs for the few positions that passed every filter and the exact lookup.
 __device__ __forceinline__ bool verify_window(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t p, int TL)
 {
-    // The 40 bytes ending at p, all requested at once (one latency): bit i of `letter` / `skip` describes byte p - i.
+    // The 32 bytes ending at p as nine aligned words, requested together (one latency) and classified four bytes at a
+    // time with the exact table of the second formulation (classify4): bit i of `letter` / `bad` describes byte p - i.
     // The window is the first 2k letters walking back; it is genuine iff every byte up to its 2k-th letter is a letter
-    // or a line end.  Windows with more than 40 - 2k line-end bytes inside (very short lines) take the byte loop.
-    const uint32_t avail = (uint32_t)min((uint64_t)40, p - gs + 1);
-    uint64_t letter = 0, skip = 0;
+    // or a line end.  What 32 bytes cannot decide (line ends inside a window of k > 10, very short lines) takes the byte loop.
+    int cnt = 0;
+    if (p - gs >= 31) {
+        const uint64_t first = p - 31, base = first & ~3ull;
+        const uint32_t sh = (uint32_t)(first - base);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(seq + base);
+        uint32_t w[9];
 #pragma unroll
-    for (int i = 0; i < 40; i++)
-        if ((uint32_t)i < avail) {
-            const uint32_t b = __ldg(seq + p - i), l = b | 0x20u;
-            letter |= (uint64_t)(l == 'a' || l == 'c' || l == 'g' || l == 't') << i;
-            skip |= (uint64_t)(b == '\n' || b == '\r') << i;
+        for (int k = 0; k < 9; k++) w[k] = (k < 8 || sh) ? __ldg(wp + k) : 0u;       // the ninth word exists iff the range is unaligned
+        uint64_t clean = 0, skip = 0;                              // bit b <-> byte base + b
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            uint32_t d = 0, t3, m;
+            classify4(w[k], d, t3, m);
+            const uint32_t z = ~((((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d)) & 0x80808080u;      // 0x80 per CLEAN byte
+            clean |= (uint64_t)((((z >> 7) * 0x00204081u) >> 21) & 15u) << (4 * k);
+            skip |= (uint64_t)(((((t3 >> 2) & 0x01010101u) * 0x00204081u) >> 21) & 15u) << (4 * k);
         }
-    const uint64_t bad = ~(letter | skip);                        // (bytes beyond `avail` count as bad)
-    const uint32_t lo_l = (uint32_t)letter, n_lo = __popc(lo_l);
-    int t;                                                         // position of the 2k-th letter
-    if (n_lo >= (uint32_t)TL) t = (int)__fns(lo_l, 0, TL);
-    else {
-        const uint32_t hi_l = (uint32_t)(letter >> 32);
-        t = __popc(hi_l) >= (uint32_t)TL - n_lo ? 32 + (int)__fns(hi_l, 0, TL - (int)n_lo) : -1;
+        const uint32_t rc = __brev((uint32_t)(clean >> sh)), rs = __brev((uint32_t)(skip >> sh));     // bit i <-> byte p - i
+        const uint32_t letter = rc & ~rs, bad = ~rc;
+        const uint32_t t = __fns(letter, 0, TL);                  // position of the 2k-th letter, or none
+        if (t != 0xffffffffu) return (bad & (0xffffffffu >> (31 - t))) == 0;
+        if (bad) return false;                                    // something else before 2k letters were seen
+        if (p - gs < 32) return false;                            // the genome starts before them
+        cnt = __popc(letter);
+        p -= 32;
     }
-    if (t >= 0) return (bad & ((2ull << t) - 1ull)) == 0;
-    if (bad & ((1ull << avail) - 1ull)) return false;             // something else before 2k letters were seen
-    if (avail < 40) return false;                                 // the genome starts before them
-    if (p - gs < 40) return false;
-    int cnt = __popcll(letter);
-    p -= 40;
     for (;;) {
         const uint32_t b = __ldg(seq + p);
         const uint32_t l = b | 0x20u;
@@ -429,7 +433,6 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     uint32_t since_break = 0, hdr = 0;
     uint32_t ln = 0;
     uint32_t n_steady;
-    const uint8_t *lp;
     Bytes32 cur;
     {
         const uint64_t start = sc.start, end = sc.end, ge = sc.ge, chunk0 = start & ~127ull;
@@ -439,7 +442,6 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         const uint64_t lim = end < ge ? end : ge;
         const uint64_t full = (lim - chunk0) >> 10;
         n_steady = full > 1 ? (uint32_t)(full - 1 < 0x3fffffffull ? full - 1 : 0x3fffffffull) : 0u;
-        lp = A.seq + chunk0 + 32 * lane;
         cur = load_chunk32_guarded(A, chunk0 + 32 * lane);
     }
     bool at_eof = false;
@@ -473,16 +475,12 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         }
         // the 32 bytes are now three words: request the next KiB into the same registers (one buffer, no copies); the
         // rest of the iteration and the other warps cover its latency.  A dirty iteration re-reads its text itself.
-        if (it < n_steady) {
-            cur = ldg_stream256(lp + 1024);
-#ifdef KSSD_SCAN_PF2
-            if (it + 1 < n_steady) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + 2048));
-#endif
+        if (it < n_steady) {       // (the address is rebuilt from the span record: a live 64-bit pointer costs two registers all loop long)
+            cur = ldg_stream256(A.seq + sc.chunk0 + ((uint64_t)(it + 1) << 10) + 32 * lane);
         } else {
             const uint64_t nb = sc.chunk0 + ((uint64_t)(it + 1) << 10);
             if (nb < sc.ge) cur = load_chunk32_guarded(A, nb + 32 * lane);
         }
-        lp += 1024;
         const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
         const bool lane_ok = dacc == 0 && (n >= (uint32_t)(TL - 1) || cut_lane);
         const bool clean = __all_sync(kFull, lane_ok) && !hdr;

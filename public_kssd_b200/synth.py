@@ -199,10 +199,13 @@ def to_fastq(bases: np.ndarray, n_reads: int, read_len: int, seed: int, err: flo
 
 
 def synth_sketches(n_genomes: int, codes_per_genome: int, seed: int, code_bits: int = 28, cluster_size: int = 20,
-                   min_div: float = 0.001, max_div: float = 0.1, klen: int = 20):
+                   min_div: float = 0.001, max_div: float = 0.1, klen: int = 20, member_seed: int | None = None):
     """Sketches without sequences (SURVEY.md s8d cfg 3): per cluster an ancestor set of codes; each member keeps an
     ancestor code with probability (1-d)^klen and replaces the rest with fresh random codes.
-    Returns (codes uint32 concatenated, index uint64[n+1]); each genome's codes are sorted unique."""
+    Returns (codes uint32 concatenated, index uint64[n+1]); each genome's codes are sorted unique.
+    member_seed: same ancestors (they depend on `seed` only), different members -- independent query batches against one
+    reference set."""
+    ms = seed if member_seed is None else member_seed
     n_clusters = (n_genomes + cluster_size - 1) // cluster_size
     mask = np.uint64((1 << code_bits) - 1)
     chunks, counts = [], []
@@ -217,9 +220,9 @@ def synth_sketches(n_genomes: int, codes_per_genome: int, seed: int, code_bits: 
             else:
                 d = min_div * (max_div / min_div) ** ((m - 1) / max(cluster_size - 2, 1))
                 keep_p = (1.0 - d) ** klen
-                r = _stream(seed * 1009 + g, anc.size, salt=21)
+                r = _stream(ms * 1009 + g, anc.size, salt=21)
                 u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
-                fresh = (_stream(seed * 2003 + g, anc.size, salt=22) & mask).astype(np.uint32)
+                fresh = (_stream(ms * 2003 + g, anc.size, salt=22) & mask).astype(np.uint32)
                 s = np.unique(np.where(u < keep_p, anc, fresh))
             chunks.append(s)
             counts.append(s.size)
