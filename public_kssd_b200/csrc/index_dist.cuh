@@ -518,20 +518,29 @@ __global__ void __launch_bounds__(kStatThreads) stats_rows_dense_kernel(const St
 // then evaluates the statistics densely, one thread per hit.  All components of the index add into the same table.
 struct SparseComp { const uint32_t *qcodes; const uint64_t *qindex; CodeLookup L; const uint32_t *mco; };
 struct SparseHit { uint32_t q, r, shared; };
-constexpr int kSparseThreads = 512;
-constexpr uint32_t kSparseSlots = 8192;                       // hash slots per CTA: 64 KiB of keys + counts
-constexpr uint32_t kSparseMaxDistinct = kSparseSlots / 4 * 3; // refs one query may touch before the dense path takes over
+// Two shapes of the per-query CTA.  Wide: 512 threads, 8192 hash slots, 2048 query codes per pass -- queries that touch
+// thousands of references.  Narrow: 128 threads, 2048 slots, 512 codes per pass -- the usual search (a query touches its
+// relatives and a few chance hits), and every shard of a reference set split over GPUs: four times as many queries in
+// flight per SM hide the dependent lookup -> posting chain, and the per-query fixed work (clearing and walking the table)
+// is a quarter.
+template <int THREADS_, uint32_t SLOTS_, uint32_t TILE_, int HBITS_>
+struct SparseCfg {
+    static constexpr int kThreads = THREADS_;
+    static constexpr uint32_t kSlots = SLOTS_, kTile = TILE_;
+    static constexpr uint32_t kMaxDistinct = SLOTS_ / 4 * 3;   // refs one query may touch before the dense path takes over
+    static constexpr int kHashShift = 32 - HBITS_;
+};
+using SparseWide = SparseCfg<512, 8192, 2048, 13>;
+using SparseNarrow = SparseCfg<128, 2048, 512, 11>;
 constexpr uint32_t kSparseEmpty = 0xffffffffu;
-
-__device__ __forceinline__ uint32_t sparse_hash(uint32_t g) { return (g * 0x9E3779B1u) >> 19; }   // 13 bits
 
 // PACKED: one 32-bit word per slot, gid in the high bits and the count in the low `cb` bits (the host picks it when
 // R and the largest query sketch leave room) -- the table is 32 KiB instead of 64 and a third CTA fits on the SM.
-template <bool PACKED>
+template <class C, bool PACKED>
 __device__ __forceinline__ void sparse_insert(uint32_t *keys, uint32_t *vals, uint32_t cb, uint32_t *bitmap, uint32_t *distinct, uint32_t g)
 {
-    uint32_t h = sparse_hash(g);
-    for (uint32_t probes = 0; probes < kSparseSlots; probes++) {
+    uint32_t h = (g * 0x9E3779B1u) >> C::kHashShift;
+    for (uint32_t probes = 0; probes < C::kSlots; probes++) {
         // a ref shared with the query is hit once per shared code: most inserts find their key already there
         const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&keys[h]);
         if (PACKED) {
@@ -551,14 +560,14 @@ __device__ __forceinline__ void sparse_insert(uint32_t *keys, uint32_t *vals, ui
         } else {
             if (old == g) { atomicAdd(&vals[h], 1u); return; }
         }
-        h = (h + 1) & (kSparseSlots - 1);
+        h = (h + 1) & (C::kSlots - 1);
     }
-    atomicAdd(distinct, kSparseSlots);                        // table full: poison the tally, the query goes dense
+    atomicAdd(distinct, C::kSlots);                        // table full: poison the tally, the query goes dense
 }
 
-constexpr uint32_t kSparseTile = 2048;                        // query codes per pass of the walk
 
 // block-wide exclusive prefix of two values per thread (x, y); returns the prefixes, *total = the block sums (2 barriers)
+template <class C>
 __device__ __forceinline__ uint2 sparse_block_scan(uint2 v, uint2 *wsum, uint2 *total)
 {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -573,7 +582,7 @@ __device__ __forceinline__ uint2 sparse_block_scan(uint2 v, uint2 *wsum, uint2 *
     __syncthreads();
     uint2 off = make_uint2(incl.x - v.x, incl.y - v.y), tot = make_uint2(0, 0);
 #pragma unroll
-    for (uint32_t w = 0; w < kSparseThreads / 32; w++) {
+    for (uint32_t w = 0; w < C::kThreads / 32; w++) {
         const uint2 s = wsum[w];
         off.x += w < wid ? s.x : 0u;
         off.y += w < wid ? s.y : 0u;
@@ -584,21 +593,21 @@ __device__ __forceinline__ uint2 sparse_block_scan(uint2 v, uint2 *wsum, uint2 *
     return off;
 }
 
-// The posting walk of one query (kSparseThreads threads).  The dense row kernel keeps its warp-per-list walk: with the
+// The posting walk of one query (C::kThreads threads).  The dense row kernel keeps its warp-per-list walk: with the
 // row zeroing and RED traffic in the way this one measured 1.55 ms against 1.43 ms there.
 // Per tile of query codes: (A) every thread looks its codes up -- all the random reads of the tile are in flight at
 // once -- and leaves (list start, prefix) descriptors of the non-empty lists in shared memory; (B) the tile's postings,
 // numbered through a prefix sum of the list lengths, are split evenly over the warps, 32 consecutive postings per step
 // (coalesced pieces of two or three lists), four steps of gid loads in flight ahead of emit(gid).
-template <typename F>
+template <class C, typename F>
 __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__ qcodes, const uint64_t *__restrict__ qindex,
                                                     const CodeLookup L, const uint32_t *__restrict__ mco, uint32_t q,
                                                     uint32_t *lstart, uint32_t *lpre, uint2 *wsum, F emit)
 {
     const uint64_t qs = qindex[q], qe = qindex[q + 1];
-    for (uint64_t t0 = qs; t0 < qe; t0 += kSparseTile) {
-        const uint32_t nt = (uint32_t)min((uint64_t)kSparseTile, qe - t0);
-        constexpr uint32_t kPer = kSparseTile / kSparseThreads;           // consecutive codes per thread
+    for (uint64_t t0 = qs; t0 < qe; t0 += C::kTile) {
+        const uint32_t nt = (uint32_t)min((uint64_t)C::kTile, qe - t0);
+        constexpr uint32_t kPer = C::kTile / C::kThreads;           // consecutive codes per thread
         uint32_t st[kPer], len[kPer], sum = 0, live = 0;
 #pragma unroll
         for (uint32_t j = 0; j < kPer; j++) {
@@ -615,7 +624,7 @@ __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__
         }
         // only the non-empty lists get a descriptor (a query code no reference holds has an empty list)
         uint2 tot;
-        const uint2 pre = sparse_block_scan(make_uint2(live, sum), wsum, &tot);
+        const uint2 pre = sparse_block_scan<C>(make_uint2(live, sum), wsum, &tot);
         const uint32_t T = tot.y, nl = tot.x;
         {
             uint32_t slot = pre.x, p = pre.y;
@@ -633,7 +642,7 @@ __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__
         // every WARP takes an equal run of the tile's postings, 32 consecutive ones per step: lane l finds the
         // list of posting pb + l by walking forward from the list of the step's first posting (a step spans two or
         // three lists), so the gid loads of a step fall into a few contiguous pieces
-        constexpr uint32_t nw = kSparseThreads / 32;
+        constexpr uint32_t nw = C::kThreads / 32;
         const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const uint32_t wchunk = ((T + nw - 1) / nw + 31) & ~31u;
         const uint32_t pw0 = min(wid * wchunk, T), pw1 = min(pw0 + wchunk, T);
@@ -684,37 +693,44 @@ __device__ __forceinline__ void walk_query_postings(const uint32_t *__restrict__
     }
 }
 
-template <bool TRIVIAL, bool PACKED>
-__global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const SparseComp *__restrict__ comps, int n_comp, uint32_t n_qry, uint32_t n_ref, uint32_t cb,
+template <class C, bool TRIVIAL, bool PACKED>
+__global__ void __launch_bounds__(C::kThreads) dist_sparse_kernel(const SparseComp *__restrict__ comps, int n_comp, uint32_t n_qry, uint32_t n_ref, uint32_t cb,
                                                                      const StatParams S, const uint32_t *__restrict__ qsz,
                                                                      const uint32_t *__restrict__ rsz, uint32_t *__restrict__ q_cnt,
                                                                      unsigned long long *__restrict__ q_pos, unsigned long long *__restrict__ cursor,
                                                                      uint64_t cap, SparseHit *__restrict__ hits, uint32_t *__restrict__ over_n,
-                                                                     uint32_t *__restrict__ over_list)
+                                                                     uint32_t *__restrict__ over_list, uint32_t *__restrict__ err_flag)
 {
     extern __shared__ __align__(16) uint32_t sparse_sm[];
-    uint32_t *keys = sparse_sm, *vals = keys + kSparseSlots, *lstart = vals + (PACKED ? 0 : kSparseSlots), *lpre = lstart + kSparseTile,
-             *bitmap = lpre + kSparseTile + 1;                  // PACKED: no vals array, the descriptors start right after the keys
+    uint32_t *keys = sparse_sm, *vals = keys + C::kSlots, *lstart = vals + (PACKED ? 0 : C::kSlots), *lpre = lstart + C::kTile,
+             *bitmap = lpre + C::kTile + 1;                  // PACKED: no vals array, the descriptors start right after the keys
     const uint32_t cmask = PACKED ? ((1u << cb) - 1u) : 0u;
-    __shared__ uint32_t distinct, tbase[kSparseThreads];
-    __shared__ uint2 wsum[kSparseThreads / 32];
+    __shared__ uint32_t distinct, tbase[C::kThreads];
+    __shared__ uint2 wsum[C::kThreads / 32];
     __shared__ unsigned long long base_s;
     const uint32_t bw = (n_ref + 31) / 32;
     for (uint32_t q = blockIdx.x; q < n_qry; q += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < kSparseSlots; i += kSparseThreads) {
+        for (uint32_t i = threadIdx.x; i < C::kSlots; i += C::kThreads) {
             keys[i] = kSparseEmpty;
             if (!PACKED) vals[i] = 0;
         }
-        for (uint32_t i = threadIdx.x; i < bw; i += kSparseThreads) bitmap[i] = 0;
-        if (threadIdx.x == 0) distinct = 0;
+        for (uint32_t i = threadIdx.x; i < bw; i += C::kThreads) bitmap[i] = 0;
+        if (threadIdx.x == 0) {
+            distinct = 0;
+            if (PACKED) {      // a count shares its word with the ref id: the query must be as small as the host was told
+                uint64_t codes = 0;
+                for (int cc = 0; cc < n_comp; cc++) codes += comps[cc].qindex[q + 1] - comps[cc].qindex[q];
+                if (codes + 1 >= (1ull << cb) - 1) atomicOr(err_flag, 1u);
+            }
+        }
         // ---- walk (walk_query_postings): every gid of every posting list of the query's codes goes into the table
         for (int cc = 0; cc < n_comp; cc++) {
-            const SparseComp C = comps[cc];
-            walk_query_postings(C.qcodes, C.qindex, C.L, C.mco, q, lstart, lpre, wsum,
-                                [&](uint32_t g) { sparse_insert<PACKED>(keys, vals, cb, bitmap, &distinct, g); });
+            const SparseComp Cm = comps[cc];
+            walk_query_postings<C>(Cm.qcodes, Cm.qindex, Cm.L, Cm.mco, q, lstart, lpre, wsum,
+                                   [&](uint32_t g) { sparse_insert<C, PACKED>(keys, vals, cb, bitmap, &distinct, g); });
         }
         __syncthreads();
-        if (distinct > kSparseMaxDistinct) {                 // uniform: every thread reads the same shared word
+        if (distinct > C::kMaxDistinct) {                 // uniform: every thread reads the same shared word
             if (threadIdx.x == 0) { over_list[atomicAdd(over_n, 1u)] = q; q_cnt[q] = 0; q_pos[q] = 0; }   // handled densely by the host
             __syncthreads();
             continue;
@@ -722,10 +738,10 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         // ---- emission in ascending ref order without a sort: a hit's place is the number of touched refs below it,
         // read off the bitmap; the threads go over the TABLE slots (hashing spreads the hits evenly over them)
         const uint32_t Y = qsz[q];
-        constexpr uint32_t kSlotsPer = kSparseSlots / kSparseThreads;
+        constexpr uint32_t kSlotsPer = C::kSlots / C::kThreads;
         if (!TRIVIAL) {                                       // output_ctrl's keep rule, applied per touched cell
             for (uint32_t i = 0; i < kSlotsPer; i++) {
-                const uint32_t sidx = threadIdx.x + i * kSparseThreads, e = keys[sidx];
+                const uint32_t sidx = threadIdx.x + i * C::kThreads, e = keys[sidx];
                 const uint32_t r = PACKED ? e >> cb : e, cnt_r = PACKED ? e & cmask : vals[sidx];
                 if (e != kSparseEmpty && !stat_keep(S, rsz[r], Y, cnt_r)) {
                     atomicAnd(&bitmap[r >> 5], ~(1u << (r & 31)));
@@ -735,12 +751,12 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
             __syncthreads();
         }
         uint32_t per_log = 0;                                 // consecutive bitmap words per thread: a power of two
-        while (((uint32_t)kSparseThreads << per_log) < bw) per_log++;
+        while (((uint32_t)C::kThreads << per_log) < bw) per_log++;
         const uint32_t w0 = min(threadIdx.x << per_log, bw), w1 = min(w0 + (1u << per_log), bw);
         uint32_t cnt = 0;
         for (uint32_t w = w0; w < w1; w++) cnt += __popc(bitmap[w]);
         uint2 tot2;
-        const uint32_t off = sparse_block_scan(make_uint2(cnt, 0u), wsum, &tot2).x;
+        const uint32_t off = sparse_block_scan<C>(make_uint2(cnt, 0u), wsum, &tot2).x;
         const uint32_t total = tot2.x;
         tbase[threadIdx.x] = off;
         if (threadIdx.x == 0) {
@@ -752,7 +768,7 @@ __global__ void __launch_bounds__(kSparseThreads) dist_sparse_kernel(const Spars
         const unsigned long long base = base_s;
         if (total && base + total <= cap) {
             for (uint32_t i = 0; i < kSlotsPer; i++) {
-                const uint32_t sidx = threadIdx.x + i * kSparseThreads, e = keys[sidx];
+                const uint32_t sidx = threadIdx.x + i * C::kThreads, e = keys[sidx];
                 if (e == kSparseEmpty) continue;
                 const uint32_t r = PACKED ? e >> cb : e;
                 const uint32_t w = r >> 5, owner = w >> per_log;

@@ -122,6 +122,7 @@ struct kssd_ctx {
     DevBuf bplan, bwork;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[5] = {0, 0, 0, 0, 0};
+    bool stats_ms_pending = false;               // last_ms[4] of a sparse search: read off ev[2] .. ev[1] on demand
     bool total_ms_pending = false;               // last_ms[1] of a bucket-mode sketch: read off ev[0] .. ev[2] on demand
 };
 
@@ -321,6 +322,11 @@ extern "C" float kssd_ctx_last_ms(const kssd_ctx_t *cc, int which)
 {
     kssd_ctx *c = const_cast<kssd_ctx *>(cc);
     if (!c || which < 0 || which >= 5) return -1.f;
+    if (which == 4 && c->stats_ms_pending) {
+        cudaSetDevice(c->device);
+        if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]);
+        c->stats_ms_pending = false;
+    }
     if (which == 1 && c->total_ms_pending) {
         cudaSetDevice(c->device);
         if (cudaEventSynchronize(c->ev[2]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[2]);
@@ -1368,9 +1374,8 @@ static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_
     else CU(cudaMallocAsync(&d->d_ct, (size_t)n_qry * n_ref * 4, c->stream));
     CU(cudaMallocAsync(&d->d_qsz, (size_t)n_qry * 4, c->stream));
     CU(cudaMallocAsync(&d->d_rsz, (size_t)n_ref * 4, c->stream));
-    CU(cudaMemcpyAsync(d->d_qsz, qry_ctx_ct, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d->d_rsz, ref_ctx_ct, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(d->d_qsz, d->h_qsz.data(), (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));     // (the job's own copies: no wait)
+    CU(cudaMemcpyAsync(d->d_rsz, d->h_rsz.data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
     *out = d;
     return KSSD_OK;
 }
@@ -1399,9 +1404,6 @@ extern "C" int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_
     if (!d->sparse) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: not a sparse job");
     if (ref_ix->n_genomes != d->n_ref) return fail(KSSD_E_MISMATCH, "query args not match ref args: index has %d genomes, job has %d", ref_ix->n_genomes, d->n_ref);
     if (d->comps.size() >= 256) return fail(KSSD_E_INVAL, "kssd_dist_sparse_add_dev: more than 256 components");
-    uint32_t ext = 0;
-    { const int rc = max_query_extent(d->ctx, qindex_dev, d->n_qry, &ext); if (rc) return rc; }
-    d->max_count += ext;
     d->comps.push_back(SparseComp{qcodes_dev, qindex_dev, ref_ix->lookup(), ref_ix->d_gids});
     d->comp_ix.push_back(ref_ix);
     d->comp_ncodes.push_back(n_qcodes);
@@ -1624,9 +1626,21 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         uint32_t gbits = 1;
         while ((1ull << gbits) - 1 < (uint64_t)d->n_ref) gbits++;                // n_ref <= 2^gbits - 1: no gid is all ones
         const uint32_t cb = 32 - gbits;
-        const bool packed = gbits <= 24 && std::max<uint64_t>(d->max_qry_size, d->max_count) + 1 < (1ull << cb) - 1 && !getenv("KSSD_SPARSE_UNPACKED");   // env: A/B and tests
-        const size_t smem = ((packed ? 1ull : 2ull) * kSparseSlots + 2ull * kSparseTile + 1 + bw) * 4;
-        if (no_zero_rows && smem <= 200u * 1024u) {
+        // (the declared sizes pick the packed table; the kernel itself checks every query's real extent against the count bits)
+        const bool packed = gbits <= 24 && (uint64_t)d->max_qry_size + 1 < (1ull << cb) - 1 && !getenv("KSSD_SPARSE_UNPACKED");   // env: A/B and tests
+        // CTA shape (index_dist.cuh): narrow unless the largest query could touch more references than its table holds --
+        // chance hits of max_qry_size random codes in an index of this density, with head-room; a narrow run in which some
+        // query overflowed after all is repeated wide
+        uint64_t postings = 0, spaces = 0;
+        for (const kssd_index_t *ix : d->comp_ix) { postings += ix->n_postings; spaces += ix->space; }
+        const double est_touch = spaces ? (double)d->max_qry_size * (double)postings / (double)spaces : 0.0;
+        const char *shape = getenv("KSSD_SPARSE_SHAPE");             // "wide" / "narrow": A/B and tests
+        bool narrow = shape ? strcmp(shape, "narrow") == 0 : (est_touch * 1.5 + 64 < (double)SparseNarrow::kMaxDistinct);
+        auto smem_of = [&](bool nar) -> size_t {
+            const size_t slots = nar ? SparseNarrow::kSlots : SparseWide::kSlots, tile = nar ? SparseNarrow::kTile : SparseWide::kTile;
+            return ((packed ? 1ull : 2ull) * slots + 2ull * tile + 1 + bw) * 4;
+        };
+        if (no_zero_rows && smem_of(false) <= 200u * 1024u) {
             const bool trivial = S.dthreshold >= 1.0;
             const int nc = (int)d->comps.size();
             CU(cudaEventRecord(c->ev[0], c->stream));
@@ -1636,31 +1650,45 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
             CU(c->misc.ensure(16 + sizeof(SparseComp) * 256));
             uint8_t *mb = c->misc.as<uint8_t>();
             if (nc) CU(cudaMemcpyAsync(mb + 16, d->comps.data(), sizeof(SparseComp) * nc, cudaMemcpyHostToDevice, c->stream));
-            auto kern = trivial ? (packed ? dist_sparse_kernel<true, true> : dist_sparse_kernel<true, false>)
-                                : (packed ? dist_sparse_kernel<false, true> : dist_sparse_kernel<false, false>);
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // (the variant that evaluates the keep rule in place needs more registers: two CTAs per SM measured faster than three)
-            const int per_sm = std::max(1, std::min(trivial ? 3 : 2, (int)((227u * 1024u) / (smem + 3400))));
-            const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
             uint64_t total = 0, cap = std::max<uint64_t>(1ull << 22, (uint64_t)d->n_qry * 1024);
-            uint32_t n_over = 0;
+            uint32_t n_over = 0, bad_extent = 0;
             CU(c->ords2.ensure((size_t)d->n_qry * 4));                 // queries that overflow the table
             for (int attempt = 0;; attempt++) {
                 if (cap > 0xffffffffull) return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D");
                 CU(c->keys.ensure(cap * sizeof(SparseHit)));
                 CU(cudaMemsetAsync(mb, 0, 16, c->stream));
-                kern<<<grid, kSparseThreads, smem, c->stream>>>(reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, cb, S,
-                                                                d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(), c->counts.as<unsigned long long>(),
-                                                                reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(),
-                                                                reinterpret_cast<uint32_t *>(mb + 8), c->ords2.as<uint32_t>());
+                const size_t smem = smem_of(narrow);
+                auto launch = [&](auto kern, int threads, int max_per_sm) -> int {
+                    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const int per_sm = std::max(1, std::min(max_per_sm, (int)((227u * 1024u) / (smem + 3400))));
+                    const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
+                    kern<<<grid, threads, smem, c->stream>>>(reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, cb, S,
+                                                             d->d_qsz, d->d_rsz, c->flags.as<uint32_t>(), c->counts.as<unsigned long long>(),
+                                                             reinterpret_cast<unsigned long long *>(mb), cap, c->keys.as<SparseHit>(),
+                                                             reinterpret_cast<uint32_t *>(mb + 8), c->ords2.as<uint32_t>(), reinterpret_cast<uint32_t *>(mb + 12));
+                    return KSSD_OK;
+                };
+                int lrc;
+                // (wide: the variant that evaluates the keep rule in place needs more registers -- two CTAs per SM measured faster than three)
+                if (narrow) {
+                    if (trivial) lrc = packed ? launch(dist_sparse_kernel<SparseNarrow, true, true>, 128, 12) : launch(dist_sparse_kernel<SparseNarrow, true, false>, 128, 12);
+                    else lrc = packed ? launch(dist_sparse_kernel<SparseNarrow, false, true>, 128, 12) : launch(dist_sparse_kernel<SparseNarrow, false, false>, 128, 12);
+                } else {
+                    if (trivial) lrc = packed ? launch(dist_sparse_kernel<SparseWide, true, true>, 512, 3) : launch(dist_sparse_kernel<SparseWide, true, false>, 512, 3);
+                    else lrc = packed ? launch(dist_sparse_kernel<SparseWide, false, true>, 512, 2) : launch(dist_sparse_kernel<SparseWide, false, false>, 512, 2);
+                }
+                if (lrc) return lrc;
                 LAUNCHED(1);
                 CU(cudaEventRecord(c->ev[2], c->stream));
                 CU(cudaMemcpyAsync(&total, mb, 8, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaMemcpyAsync(&n_over, mb + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaMemcpyAsync(&bad_extent, mb + 12, 4, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 CU(cudaGetLastError());
+                if (bad_extent) return fail(KSSD_E_INVAL, "kssd_dist_stats: a query sketch holds more codes than its declared size allows for");
+                if (narrow && n_over && !shape) { narrow = false; attempt = -1; continue; }      // some query needs the big table
                 if (total <= cap) break;
-                if (attempt) return fail(KSSD_E_NOMEM, "kssd_dist_stats: hit list overflow");
+                if (attempt > 0) return fail(KSSD_E_NOMEM, "kssd_dist_stats: hit list overflow");
                 cap = total;
             }
             if ((uint64_t)n_over * 2 <= (uint64_t)d->n_qry) {
@@ -1763,9 +1791,11 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
                 }
                 d->n_rows = all_rows;
                 CU(cudaEventRecord(c->ev[1], c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                CU(cudaGetLastError());
-                CU(cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]));
+                if (n_over) {
+                    CU(cudaStreamSynchronize(c->stream));
+                    CU(cudaGetLastError());
+                    CU(cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]));
+                } else c->stats_ms_pending = true;      // the rows kernel runs on; kssd_ctx_last_ms(4) / the next fetch wait for it
                 cleanup();
                 return (int64_t)d->n_rows;
             }

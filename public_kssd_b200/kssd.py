@@ -412,3 +412,38 @@ class DistJob:
             self.close()
         except Exception:
             pass
+
+
+def num_cof_batch(mem_limit_bytes: int, n_ref: int, page_sz: int = 4096) -> int:
+    """Query rows per batch of the reference's Stage III (command_dist.c:731-734): as many whole pages of uint32[n_ref] rows as
+    `-m` allows.  Raises where the reference exits ("at least %fG memory needed")."""
+    unit = mem_limit_bytes // (n_ref * 4 * page_sz)
+    if unit < 1:
+        raise KssdError(-1, f"at least {n_ref * 4 * page_sz / 1073741824:f}G memory needed to map ./onedist, specify more memory use -m")
+    return unit * page_sz
+
+
+def batched_search(ctx: Context, ref_indexes: Sequence[Index], qcodes: Sequence[np.ndarray], qindex: Sequence[np.ndarray], qry_ctx_ct: np.ndarray,
+                   ref_ctx_ct: np.ndarray, rows_per_batch: int, sparse: bool = False, fetch_counts: bool = False, **stats_opts):
+    """mco_cbdco_nobin_dist's batch loop (command_dist.c:763-790) on the GPU: the queries are searched `rows_per_batch` at a time,
+    so neither the Q x R count matrix nor the row list of one job ever has to hold the whole search (a 100k x 100k all-vs-all
+    is 40 GB of counts and 10^10 rows at -D 1).  Yields (first_query, counts block or None, statistics rows) per batch, in query
+    order -- concatenated, the rows are those of one unbatched job; `cmprsn_num` is that of the whole search (:1186).
+    qcodes / qindex: per component, as for DistJob.accumulate."""
+    q_sz = np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
+    r_sz = np.ascontiguousarray(ref_ctx_ct, dtype=np.uint32)
+    n_qry, n_ref = q_sz.size, r_sz.size
+    stats_opts.setdefault("cmprsn_num", (n_ref * n_qry) & 0xFFFFFFFF)
+    for lo in range(0, n_qry, rows_per_batch):
+        hi = min(lo + rows_per_batch, n_qry)
+        job = DistJob(ctx, q_sz[lo:hi], r_sz, sparse=sparse)
+        try:
+            for ix, qc, qi in zip(ref_indexes, qcodes, qindex):
+                qi = np.ascontiguousarray(qi, dtype=np.uint64)
+                a, b = int(qi[lo]), int(qi[hi])
+                job.accumulate(ix, np.ascontiguousarray(qc, dtype=np.uint32)[a:b], qi[lo:hi + 1] - qi[lo])
+            rows = job.stats(**stats_opts)
+            rows["qry"] += lo
+            yield lo, (job.counts() if fetch_counts else None), rows
+        finally:
+            job.close()

@@ -276,3 +276,29 @@ def test_sparse_job_multi_component(shuf_l3k10):
             ix.close()
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("sparse,opts", [(False, dict()), (False, dict(metric=1, dthreshold=0.3)), (True, dict(skip_zero=1)), (False, dict(n_neighbors=4))])
+def test_query_batches_equal_one_job(gpu_ctx_l3k10, sparse, opts):
+    """The reference's num_cof_batch loop (command_dist.c:731-734, :763-790): searching the queries a batch at a time gives the
+    rows and the counts of one job, FDR column included (cmprsn_num is the whole search's)."""
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(500, 200, seed=3, cluster_size=10)
+    qc, qi = synth.synth_sketches(77, 200, seed=3, cluster_size=7)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    qsz, rsz = np.diff(qi).astype(np.uint32), np.diff(ri).astype(np.uint32)
+    one = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz, sparse=sparse)
+    one.accumulate(ix, qc, qi)
+    want = one.stats(**opts)
+    want_ct = one.counts()
+    got, cts = [], []
+    for lo, ct, rows in kssd.batched_search(gpu_ctx_l3k10, [ix], [qc], [qi], qsz, rsz, rows_per_batch=16, sparse=sparse, fetch_counts=True, **opts):
+        assert lo % 16 == 0
+        got.append(rows)
+        cts.append(ct)
+    assert np.concatenate(got).tobytes() == want.tobytes()
+    assert np.array_equal(np.concatenate(cts), want_ct)
+    assert kssd.num_cof_batch(8 << 30, 100_000) == 5 * 4096       # -m 8 with 100k references: 20480 query rows per batch
+    with pytest.raises(kssd.KssdError):
+        kssd.num_cof_batch(1 << 20, 100_000)
+    one.close(); ix.close()
