@@ -1635,7 +1635,9 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         for (const kssd_index_t *ix : d->comp_ix) { postings += ix->n_postings; spaces += ix->space; }
         const double est_touch = spaces ? (double)d->max_qry_size * (double)postings / (double)spaces : 0.0;
         const char *shape = getenv("KSSD_SPARSE_SHAPE");             // "wide" / "narrow": A/B and tests
-        bool narrow = shape ? strcmp(shape, "narrow") == 0 : (est_touch * 1.5 + 64 < (double)SparseNarrow::kMaxDistinct);
+        // (measured at 10,000 x 100,000: with ~550 chance references per query the wide shape's 512 threads walk the ~18,000
+        //  postings of a query faster; the narrow one pays off when a shard leaves a query a few thousand postings)
+        bool narrow = shape ? strcmp(shape, "narrow") == 0 : est_touch < 200.0;
         auto smem_of = [&](bool nar) -> size_t {
             const size_t slots = nar ? SparseNarrow::kSlots : SparseWide::kSlots, tile = nar ? SparseNarrow::kTile : SparseWide::kTile;
             return ((packed ? 1ull : 2ull) * slots + 2ull * tile + 1 + bw) * 4;

@@ -74,7 +74,11 @@ struct LaneQ3 {
 // candidates on their way to the exact resolver: the k-mer (scan representation), the lane's offset in its genome (own-base
 // number in the top five bits), the lane's skip flags, the genome.  The queue outlives spans: entries carry all they need.
 struct WarpQ3 { uint32_t lo[kQueueCap], hi[kQueueCap], ordlo[kQueueCap], ordhi[kQueueCap], f[kQueueCap], gid[kQueueCap]; };
+#ifdef KSSD_SCAN_TMA
+constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 48 + 2064);   // + SpanCtx + TmaRing
+#else
 constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 48);   // + SpanCtx
+#endif
 
 __device__ __forceinline__ bool pf3_probe(const uint32_t *__restrict__ pf, uint32_t v)
 {
@@ -415,6 +419,27 @@ __device__ __forceinline__ uint32_t top_bytes4(uint32_t a, uint32_t b, uint32_t 
     return prmt(prmt(a, b, 0x0073u), prmt(c, d, 0x0073u), 0x5410u);
 }
 
+#ifdef KSSD_SCAN_TMA
+// A/B variant (profiles/r2_sketch_ncu_summary.md): the steady iterations' text arrives by 1-D bulk copies (TMA,
+// cp.async.bulk + mbarrier complete_tx) into a two-stage, 1 KiB-per-stage ring per warp, two iterations ahead, and the
+// lanes read their 32 bytes back with two LDS.128 -- instead of one LDG.E.256 per lane into registers.
+struct TmaRing { alignas(16) uint8_t buf[2][1024]; alignas(8) unsigned long long bar[2]; };
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_issue(TmaRing &r, int stage, const uint8_t *src)
+{
+    const uint32_t bar = smem_u32(&r.bar[stage]), dst = smem_u32(r.buf[stage]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 1024;" ::"r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 1024, [%2];" ::"r"(dst), "l"(src), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_wait(TmaRing &r, int stage, uint32_t parity)
+{
+    const uint32_t bar = smem_u32(&r.bar[stage]);
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+#endif
+
 // Cold per-span state lives in shared memory (one record per warp): the span's byte extents are 64-bit and only the
 // first and last iterations of a span look at them -- in registers they pushed the loop counters out to local memory.
 struct SpanCtx { uint64_t gs, ge, start, end, chunk0; uint32_t gid, after_end; };
@@ -422,7 +447,11 @@ struct SpanCtx { uint64_t gs, ge, start, end, chunk0; uint32_t gid, after_end; }
 // ST: bases per first-level probe (3 or 1); BIG: 2k-1 history bases need more than 32 bits (k >= 9)
 template <int ST, bool BIG>
 __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, uint32_t &qn, LaneQ3 &lq,
-                           volatile SpanCtx &sc)
+                           volatile SpanCtx &sc
+#ifdef KSSD_SCAN_TMA
+                           , TmaRing &ring
+#endif
+                           )
 {
     constexpr int NPROBE = ST == 3 ? 12 : 32;
     const uint32_t lane = lane_id();
@@ -443,6 +472,17 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         const uint64_t full = (lim - chunk0) >> 10;
         n_steady = full > 1 ? (uint32_t)(full - 1 < 0x3fffffffull ? full - 1 : 0x3fffffffull) : 0u;
         cur = load_chunk32_guarded(A, chunk0 + 32 * lane);
+#ifdef KSSD_SCAN_TMA
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring.bar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring.bar[1])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (n_steady >= 1) tma_issue(ring, 1, A.seq + chunk0 + 1024);          // iteration j lives in stage j & 1
+            if (n_steady >= 2) tma_issue(ring, 0, A.seq + chunk0 + 2048);
+        }
+        __syncwarp();
+#endif
     }
     bool at_eof = false;
 
@@ -476,7 +516,20 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         // the 32 bytes are now three words: request the next KiB into the same registers (one buffer, no copies); the
         // rest of the iteration and the other warps cover its latency.  A dirty iteration re-reads its text itself.
         if (it < n_steady) {       // (the address is rebuilt from the span record: a live 64-bit pointer costs two registers all loop long)
+#ifdef KSSD_SCAN_TMA
+            const uint32_t j = it + 1;                                // the iteration whose text is due now
+            tma_wait(ring, j & 1, ((j - 1) >> 1) & 1);
+            const uint4 *sp = reinterpret_cast<const uint4 *>(ring.buf[j & 1] + 32 * lane);
+            cur.lo = sp[0];
+            cur.hi = sp[1];
+            __syncwarp();
+            if (lane == 0 && j + 2 <= n_steady) {                     // its stage is free again: two iterations ahead
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_issue(ring, j & 1, A.seq + sc.chunk0 + ((uint64_t)(j + 2) << 10));
+            }
+#else
             cur = ldg_stream256(A.seq + sc.chunk0 + ((uint64_t)(it + 1) << 10) + 32 * lane);
+#endif
         } else {
             const uint64_t nb = sc.chunk0 + ((uint64_t)(it + 1) << 10);
             if (nb < sc.ge) cur = load_chunk32_guarded(A, nb + 32 * lane);
@@ -658,7 +711,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
         __syncwarp();
         if (lane == 0) { sc.gs = gs; sc.ge = ge; sc.start = start; sc.end = end; sc.gid = gid; }
         __syncwarp();
+#ifdef KSSD_SCAN_TMA
+        scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], sc, reinterpret_cast<TmaRing *>(spans + kScanWarps)[threadIdx.x >> 5]);
+#else
         scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], sc);
+#endif
     }
     if (qn) resolve3(P, A, q, 0, qn);
 }
