@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dist-scale", action="store_true", help="skip the 10,000 x 100,000 Stage III measurement (N = 1 only)")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ Stage I leg (N = 1 only)")
     ap.add_argument("--dist-batches", type=int, default=8, help="query batches of the configs[2]-size search")
     ap.add_argument("--ref-sample", type=int, default=0, help="genomes in the CPU sample (0 = auto)")
     return ap.parse_args()
@@ -108,6 +109,63 @@ def make_batch_device(n_genomes, genome_len, seed, device, cluster_size=20, widt
             buf[o:o + rem] = txt[full * width:]
             buf[o + rem] = 10
     return buf, goff, glen
+
+
+def fastq_leg(device, peak, n_reads=4_000_000, rl=150):
+    """Stage I on FASTQ text at a scaled-down BASELINE.json configs[4] shape: n_reads x 150 bp, Phred+33 qualities, L3K11 (16
+    components), -n 2.  Device resident, CUDA events inside the library; a slice of the reads is checked against the oracle."""
+    import torch
+    from public_kssd_b200 import capi, kssd, synth
+    g = torch.Generator(device=device)
+    g.manual_seed(5)
+    src = torch.randint(0, 4, (2_000_000,), generator=g, device=device, dtype=torch.uint8)
+    starts = torch.randint(0, src.numel() - rl, (n_reads,), generator=g, device=device)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    bases = lut[src[starts[:, None] + torch.arange(rl, device=device)[None, :]].long()]
+    err = torch.rand((n_reads, rl), generator=g, device=device) < 0.005
+    bases = torch.where(err, lut[torch.randint(0, 4, (n_reads, rl), generator=g, device=device)], bases)
+    qual = torch.randint(35, 74, (n_reads, rl), generator=g, device=device, dtype=torch.uint8)
+    hdr = torch.full((n_reads, 12), ord("x"), dtype=torch.uint8, device=device)
+    hdr[:, 0] = ord("@")
+    hdr[:, 11] = 10
+    num = torch.arange(n_reads, device=device)
+    for d in range(10):
+        hdr[:, 10 - d] = (48 + (num // (10 ** d)) % 10).to(torch.uint8)
+    plus = torch.tensor([43, 10], dtype=torch.uint8, device=device).expand(n_reads, 2)
+    nl = torch.full((n_reads, 1), 10, dtype=torch.uint8, device=device)
+    rec = torch.cat([hdr, bases, nl, plus, qual, nl], dim=1).contiguous().view(-1)
+    buf = torch.cat([rec, torch.full((1024,), 10, dtype=torch.uint8, device=device)])
+    nbytes = int(rec.numel())
+    del bases, qual, err, hdr
+    torch.cuda.synchronize()
+    tab6 = synth.make_shuf_table(6, 1)
+    ctx = kssd.Context(11, 6, 3, tab6, device=device.index or 0)
+    goff = np.zeros(1, dtype=np.uint64)
+    glen = np.array([nbytes], dtype=np.uint64)
+    ms = []
+    for it in range(5):
+        h = ctx.sketch_raw(None, nbytes, goff, glen, mode=capi.MODE_FASTQ, Q=0, M=2, device_ptr=buf.data_ptr())
+        ms.append((ctx.last_ms(0), ctx.last_ms(1)))
+        sk = ctx.fetch_sketch(h, 1)
+    k, w = min(m[0] for m in ms[1:]), min(m[1] for m in ms[1:])
+    alg = nbytes - n_reads * (rl + 1)          # -Q 0: the quality lines are not part of the algorithm's input (SURVEY.md s8d)
+    ok = None
+    try:
+        from oracle import oracle as O
+        orc = O.Ctx(11, 6, 3, tab6)
+        small = rec[: 20000 * (12 + rl + 1 + 2 + rl + 1)].cpu().numpy()
+        ids, comp = orc.fastq(small, 0, 2)
+        sks = ctx.sketch_fastq([small], Q=0, M=2)
+        ok = bool(all(np.array_equal(sks.genome_sets()[0][c], np.sort(ids[comp == c])) for c in range(16)))
+    except Exception:
+        pass
+    ctx.close()
+    return {"workload": f"{n_reads} reads x {rl} bp, 4-line FASTQ, Phred+33, L3K11 (16 components), -n 2", "text_bytes": nbytes, "bases": n_reads * rl,
+            "scan_ms": k, "call_ms": w, "gbp_per_s": n_reads * rl / (w * 1e-3) / 1e9, "text_gb_per_s": nbytes / (k * 1e-3) / 1e9,
+            "codes": int(sum(len(x) for x in sk.ids)), "oracle_parity_first_20000_reads": ok,
+            "roofline": {"bound": "hbm", "kernel": "nl_count + nl_fill + sketch_fastq kernels", "achieved": alg / (k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
+                         "note": "header, sequence and '+' lines (the quality lines only count with -Q > 0); whole text incl. quality: text_gb_per_s"}}
 
 
 class ClockSampler:
@@ -424,6 +482,13 @@ def main():
             import traceback
             dist_info["configs2_scale"] = {"failed": str(ex), "trace": traceback.format_exc()[-800:]}
 
+    fastq_info = None
+    if world == 1 and not args.no_fastq:
+        try:
+            fastq_info = fastq_leg(dev, peak)
+        except Exception as ex:  # must not take the headline measurement down
+            fastq_info = {"failed": str(ex)}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
@@ -467,6 +532,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": float(te.item()) * 1e3, "matches_device_path": same},
                 "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu_baseline, "dist": dist_info,
+                "fastq": fastq_info,
                 "sketch": {"codes": n_codes, "text_bytes": text_bytes, "scan_kernel_ms": scan, "step_ms": step_ms_max}}
         print(json.dumps(line))
     if world > 1:

@@ -1,11 +1,13 @@
 """bench.py's second metric at BASELINE.json configs[2] size: 100,000 reference sketches x ~1,220 codes searched with batches of
 10,000 queries (10^9 pairs per batch), at every N.
 
-Sharding: the reference index is sharded by GENOME range -- rank r indexes references [r R/N, (r+1) R/N) -- the
-query sketches are broadcast (NCCL, one batch ahead of the compute), every rank runs the sparse Stage III job on its columns
-(count + filter + list + statistics, no Q x R matrix), and its rows are final as they are: no reduction.  The north-star
-variant (index sharded by code range + NCCL reduce-scatter of dense partial matrices) and the peer-memory variant are timed
-next to it on one batch as the baselines they are.  Times are CUDA events on the library stream, max over ranks.
+Sharding: the reference index is sharded by GENOME range and each rank's rows are final as they are -- no
+reduction.  The per-query part of the search (code lookups, clearing and reading out the query's table) does not shrink when
+only the references are split, so from four ranks on the ranks form a 2 x N/2 grid: two reference shards, N/2 query groups.
+Rank 0 holds each query batch and sends every rank the codes of its group point to point (NCCL), one batch ahead of the
+compute; every rank runs the sparse Stage III job (count + filter + list + statistics, no Q x R matrix).  The references-only
+sharding (N x 1), the north-star variant (index sharded by code range + NCCL reduce-scatter of dense partial matrices) and the
+peer-memory variant are timed next to it as the baselines they are.  Times are CUDA events on the library stream, max over ranks.
 """
 from __future__ import annotations
 
@@ -79,115 +81,139 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
             q_dev.append((torch.empty(int(m[2 + 2 * b]), dtype=torch.int32, device=dev), torch.empty(int(m[3 + 2 * b]), dtype=torch.int64, device=dev)))
     gen_s = time.perf_counter() - t0
 
-    # ---- this rank's shard of the index: references [lo, hi)
-    g = parallel.genome_shard(n_ref, world, rank)
-    lo, hi = g.start, g.stop
-    a, bnd = int(ref_index_host[lo]), int(ref_index_host[hi])
-    shard_codes = t_rc[a:bnd]
-    shard_index = (t_ri[lo:hi + 1] - t_ri[lo]).contiguous()
-    ix_ms = []
-    index = None
-    for _ in range(2):
-        if index is not None:
-            index.close()
-        torch.cuda.synchronize()
-        index = ctx.combco2mco_dev(shard_codes.data_ptr(), shard_index.data_ptr(), hi - lo, bnd - a)
-        ix_ms.append(ctx.last_ms(2))
-    shard_sizes = ref_sizes[lo:hi]
     cm = (n_ref * n_qry) & 0xFFFFFFFF
-
-    qsizes = {}
-    phases_wanted = True
-
-    def search(b, fetch=False):
-        tq, ti = q_dev[b]
-        if b not in qsizes:                                         # sketch sizes are metadata (cofiles.stat): read once, untimed
-            qsizes[b] = (ti[1:] - ti[:-1]).cpu().numpy().astype(np.uint32)
-        qsz = qsizes[b]
-        job = kssd.DistJob(ctx, qsz, shard_sizes, sparse=True)
-        job.accumulate_dev(index, tq.data_ptr(), ti.data_ptr(), int(tq.numel()))
-        rows = job.stats(skip_zero=1, fetch=fetch, cmprsn_num=cm)
-        t = (ctx.last_ms(3), ctx.last_ms(4)) if phases_wanted else None      # (reading the second one waits for the rows kernel)
-        job.close()
-        return rows, t
-
-    def bcast(b):
-        if world == 1:
-            return None
-        return [dist.broadcast(q_dev[b][0], 0, async_op=True), dist.broadcast(q_dev[b][1], 0, async_op=True)]
-
-    def wait(w):
-        if w is not None:
-            for x in w:
-                x.wait()
-            torch.cuda.current_stream().synchronize()
-
-    # warm-up (also fills the non-zero ranks' copies once; the timed loop broadcasts them again)
-    phases = []
+    # sketch sizes and per-genome extents are metadata (cofiles.stat / combco.index): everybody has them before the search;
+    # only the query CODES travel inside the timed loop
+    q_index_host = []
     for b in range(batches):
-        wait(bcast(b))
-        phases.append(search(b)[1])
-    phases_wanted = False
-    best = None
-    for rep in range(2):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        nrows = 0
-        nxt = bcast(0)
-        for b in range(batches):
-            wait(nxt)
-            nxt = bcast(b + 1) if b + 1 < batches else None          # the next batch travels while this one is searched
-            n, _ = search(b)
-            nrows += int(n)
-        e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
-        if best is None or ms < best[0]:
-            best = (ms, nrows)
-    total_ms, nrows = best
-    tr = torch.tensor([nrows], device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(tr)
-    pairs = batches * n_qry * n_ref
-    out = {"pairs_per_batch": n_qry * n_ref, "batches": batches, "refs": n_ref, "queries_per_batch": n_qry, "ref_postings": n_codes,
-           "sharding": f"reference index by genome range over {world} rank(s), query batches broadcast one ahead (NCCL), sparse job per rank, no reduction",
-           "ms_total": total_ms, "ms_per_batch": total_ms / batches, "pairs_per_s": pairs / (total_ms * 1e-3),
-           "printed_rows": int(tr.item()), "index_ms_per_rank": float(min(ix_ms)),
-           "rank0_kernel_ms_per_batch_untimed_pass": {"count_list": float(np.mean([p[0] for p in phases])), "rows": float(np.mean([p[1] for p in phases]))},
+            dist.broadcast(q_dev[b][1], 0)
+        q_index_host.append(q_dev[b][1].cpu().numpy().view(np.uint64).copy())
+
+    def measure(Gr: int, nb: int) -> dict:
+        """ranks as a Gr x Gq grid: rank r holds reference shard r % Gr (genome range) and searches query group r // Gr"""
+        Gq = world // Gr
+        gr, gq = rank % Gr, rank // Gr
+        g = parallel.genome_shard(n_ref, Gr, gr)
+        lo, hi = g.start, g.stop
+        a, bnd = int(ref_index_host[lo]), int(ref_index_host[hi])
+        shard_codes = t_rc[a:bnd]
+        shard_index = (t_ri[lo:hi + 1] - t_ri[lo]).contiguous()
+        ix_ms, index = [], None
+        for _ in range(2):
+            if index is not None:
+                index.close()
+            torch.cuda.synchronize()
+            index = ctx.combco2mco_dev(shard_codes.data_ptr(), shard_index.data_ptr(), hi - lo, bnd - a)
+            ix_ms.append(ctx.last_ms(2))
+        shard_sizes = ref_sizes[lo:hi]
+        qg = parallel.genome_shard(n_qry, Gq, gq)
+        qlo, qhi = qg.start, qg.stop
+        # per batch: this rank's query rows, their local index (device), sizes (host), and where their codes sit in the batch
+        plan = []
+        for b in range(nb):
+            qi = q_index_host[b]
+            c0, c1 = int(qi[qlo]), int(qi[qhi])
+            li = torch.from_numpy((qi[qlo:qhi + 1] - qi[qlo]).astype(np.int64)).to(dev)
+            buf = q_dev[b][0][c0:c1] if rank == 0 else torch.empty(c1 - c0, dtype=torch.int32, device=dev)
+            plan.append({"li": li, "qsz": np.diff(qi[qlo:qhi + 1]).astype(np.uint32), "buf": buf, "c0": c0, "c1": c1})
+
+        def send(b):
+            """rank 0 holds batch b: every rank gets the codes of ITS query group (point to point over NVLink)"""
+            if world == 1:
+                return None
+            ops = []
+            if rank == 0:
+                qi = q_index_host[b]
+                for r in range(1, world):
+                    rg = parallel.genome_shard(n_qry, Gq, r // Gr)
+                    ops.append(dist.P2POp(dist.isend, q_dev[b][0][int(qi[rg.start]):int(qi[rg.stop])], r))
+            else:
+                ops.append(dist.P2POp(dist.irecv, plan[b]["buf"], 0))
+            return dist.batch_isend_irecv(ops) if ops else None
+
+        def wait(w):
+            if w is not None:
+                for x in w:
+                    x.wait()
+                torch.cuda.current_stream().synchronize()
+
+        def search(b, fetch=False, phases=False):
+            pl = plan[b]
+            job = kssd.DistJob(ctx, pl["qsz"], shard_sizes, sparse=True)
+            job.accumulate_dev(index, pl["buf"].data_ptr(), pl["li"].data_ptr(), int(pl["buf"].numel()))
+            rows = job.stats(skip_zero=1, fetch=fetch, cmprsn_num=cm)
+            t = (ctx.last_ms(3), ctx.last_ms(4)) if phases else None        # (reading the second one waits for the rows kernel)
+            job.close()
+            return rows, t
+
+        ph = []
+        for b in range(nb):                                          # warm-up, and the kernel times of an unpipelined pass
+            wait(send(b))
+            ph.append(search(b, phases=True)[1])
+        best = None
+        for rep in range(2):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            nrows = 0
+            nxt = send(0)
+            for b in range(nb):
+                wait(nxt)
+                nxt = send(b + 1) if b + 1 < nb else None            # the next batch travels while this one is searched
+                nrows += int(search(b)[0])
+            e1.record(stream)
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if best is None or float(ms.item()) < best[0]:
+                best = (float(ms.item()), nrows)
+        total_ms, nrows = best
+        tr = torch.tensor([nrows], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tr)
+        # content of batch 0 over all ranks: additive digest (mod 2^64) + row count
+        rows0, _ = search(0, fetch=True)
+        rows0["ref"] += lo
+        rows0["qry"] += qlo
+        h, n = _checksum(rows0)
+        agg = torch.tensor([int(np.uint64(h).astype(np.int64)), n], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(agg)
+        index.close()
+        return {"grid": {"ref_shards": Gr, "query_groups": Gq}, "batches": nb, "ms_total": total_ms, "ms_per_batch": total_ms / nb,
+                "pairs_per_s": nb * n_qry * n_ref / (total_ms * 1e-3), "printed_rows": int(tr.item()), "index_ms_per_rank": float(min(ix_ms)),
+                "rank0_kernel_ms_per_batch_unpipelined": {"count_list": float(np.mean([p[0] for p in ph])), "rows": float(np.mean([p[1] for p in ph]))},
+                "digest": int(agg[0].item()) & 0xFFFFFFFFFFFFFFFF, "rows_batch0": int(agg[1].item())}
+
+    # The per-query part of the search (code lookups, clearing and reading out the query's table) does not shrink when only the
+    # references are sharded, so beyond two reference shards the ranks split the QUERIES: a 2 x N/2 grid.  The references-only
+    # sharding (N x 1) is measured next to it on fewer batches.
+    Gr = 1 if world == 1 else 2
+    main = measure(Gr, batches)
+    out = {"pairs_per_batch": n_qry * n_ref, "refs": n_ref, "queries_per_batch": n_qry, "ref_postings": n_codes,
+           "sharding": (f"ranks as a {Gr} x {world // Gr} grid: reference index sharded by genome range over {Gr} rank(s), each batch's queries split over "
+                        f"{world // Gr} group(s); query codes sent point to point one batch ahead (NCCL), sparse job per rank, no reduction"),
            "timing": "CUDA events on the library stream around all batches (host gaps included), max over ranks", "generation_s": gen_s}
+    out.update({k: v for k, v in main.items() if k not in ("digest", "rows_batch0")})
+    if world > 2:
+        alt = measure(world, min(batches, 4))
+        out["refs_only_sharding"] = {k: v for k, v in alt.items() if k not in ("digest", "rows_batch0", "printed_rows")}
+        out["refs_only_sharding"]["content_same_as_grid"] = bool(alt["digest"] == main["digest"] and alt["rows_batch0"] == main["rows_batch0"])
 
     # ---- content: batch 0's rows over all ranks against one GPU holding the whole index (rank 0), and against the oracle
-    phases_wanted = True
-    rows0, _ = search(0, fetch=True)
-    rows0["ref"] += lo
-    h, n = _checksum(rows0)
-    agg = torch.tensor([h & 0x7FFFFFFFFFFFFFFF, n], device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(agg)
     if rank == 0:
         tq, ti = q_dev[0]
-        qsz0 = (ti[1:] - ti[:-1]).cpu().numpy().astype(np.uint32)
-        full = index if world == 1 else ctx.combco2mco_dev(t_rc.data_ptr(), t_ri.data_ptr(), n_ref, n_codes)
+        qsz0 = np.diff(q_index_host[0]).astype(np.uint32)
+        full = ctx.combco2mco_dev(t_rc.data_ptr(), t_ri.data_ptr(), n_ref, n_codes)
         dj = kssd.DistJob(ctx, qsz0, ref_sizes)                    # dense job on one GPU: another kernel, the whole matrix
         dj.accumulate_dev(full, tq.data_ptr(), ti.data_ptr(), int(tq.numel()))
         dense_count_ms = ctx.last_ms(3)
         want = dj.stats(skip_zero=1, cmprsn_num=cm)
         dense_stats_ms = ctx.last_ms(4)
         hw, nw = _checksum(want)
-        if world > 1:
-            # per-rank digests were summed modulo 2^63 each: recompute the one-GPU digest the same way
-            parts = [want[(want["ref"] >= parallel.genome_shard(n_ref, world, r).start) & (want["ref"] < parallel.genome_shard(n_ref, world, r).stop)]
-                     for r in range(world)]
-            hw = sum(_checksum(p)[0] & 0x7FFFFFFFFFFFFFFF for p in parts) & 0xFFFFFFFFFFFFFFFF
-            got = int(agg[0].item()) & 0xFFFFFFFFFFFFFFFF
-        else:
-            hw &= 0x7FFFFFFFFFFFFFFF
-            got = int(agg[0].item())
-        out["content_ok"] = bool(got == hw and int(agg[1].item()) == nw)
+        out["content_ok"] = bool(main["digest"] == (hw & 0xFFFFFFFFFFFFFFFF) and main["rows_batch0"] == nw)
         out["content_check"] = "batch 0: digest + count of (qry, ref, shared) rows over all ranks == the dense job of one GPU holding the whole index"
         # oracle (checker): brute force through the CPU restatement on the first 16 queries x first 2000 references
         try:
@@ -251,8 +277,7 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
             out["e2e"] = {"value": n_qry * n_ref / min(e2e), "unit": "pairs/s", "ms": min(e2e) * 1e3, "h2d_bytes": int(qc_h.nbytes + qi_h.nbytes + qsz0.nbytes),
                           "d2h_bytes": int(rows_h.nbytes), "note": "kssd_dist_create_sparse + add_host + stats + fetch_stats: query sketches from host memory, rows back"}
         dj.close()
-        if world > 1:
-            full.close()
+        full.close()
     if world > 1:
         ok = torch.tensor([1 if out.get("content_ok", True) else 0], device=dev, dtype=torch.int64)
         dist.broadcast(ok, 0)
@@ -285,5 +310,4 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
         out["baseline_note"] = ("code = reference index sharded by code range, queries broadcast, dense partial Q x R matrices combined by ncclReduceScatter "
                                 "(north star); code_p2p = same placement, RED.ADD into the owner's rows over NVLink peer mappings; both one batch, "
                                 "library-stream events incl. broadcast and barriers")
-    index.close()
     return out
