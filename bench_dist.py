@@ -156,14 +156,23 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            nrows = 0
             nxt = send(0)
+            jobs = []
             for b in range(nb):
                 wait(nxt)
                 nxt = send(b + 1) if b + 1 < nb else None            # the next batch travels while this one is searched
-                nrows += int(search(b)[0])
+                pl = plan[b]
+                job = kssd.DistJob(ctx, pl["qsz"], shard_sizes, sparse=True)
+                job.accumulate_dev(index, pl["buf"].data_ptr(), pl["li"].data_ptr(), int(pl["buf"].numel()))
+                job.stats_async(skip_zero=1, cmprsn_num=cm)           # queued: the host runs ahead of the GPU
+                jobs.append(job)
+            nrows = 0
+            for job in jobs:                                         # every batch's rows are on the device when this returns
+                nrows += int(job.stats_wait())
             e1.record(stream)
             barrier()
+            for job in jobs:
+                job.close()
             ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -256,6 +256,12 @@ int kssd_dist_sparse_add_host(kssd_dist_t *d, const kssd_index_t *ref_ix, const 
  * copies them out. */
 int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *opts);
 int kssd_dist_fetch_stats(const kssd_dist_t *d, kssd_stat_row_t *rows_out);
+/* The same search without a host round trip in the middle (sparse jobs): kssd_dist_stats_async() queues count + list +
+ * statistics and returns; kssd_dist_stats_wait() returns the number of rows (and redoes through kssd_dist_stats() whatever
+ * the fast path could not finish).  Several jobs of one context may be in flight: a host that feeds query batch after query
+ * batch -- the loop of mco_cbdco_nobin_dist, command_dist.c:763-790 -- keeps the GPU busy without waiting on it. */
+int kssd_dist_stats_async(kssd_dist_t *d, const kssd_stat_opts_t *opts);
+int64_t kssd_dist_stats_wait(kssd_dist_t *d);
 void kssd_dist_free(kssd_dist_t *d);
 
 /* distance.out text (host side, multi-threaded): the header line dist_print_nobin writes

@@ -27,7 +27,7 @@ SYMBOLS = [
     "kssd_index_from_dense_host", "kssd_index_free",
     "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
     "kssd_dist_counts_dev", "kssd_dist_create_sparse", "kssd_dist_sparse_add_dev", "kssd_dist_sparse_add_host", "kssd_dist_accumulate_peer", "kssd_dev_alloc", "kssd_dev_zero", "kssd_dev_free",
-    "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_fetch_stats", "kssd_dist_free",
+    "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_stats_async", "kssd_dist_stats_wait", "kssd_dist_fetch_stats", "kssd_dist_free",
     "kssd_format_distance_rows", "kssd_host_free",
     "kssd_set_union_host", "kssd_set_union_dev", "kssd_set_operate_host", "kssd_set_operate_dev",
     "kssd_composite_host",
@@ -154,6 +154,9 @@ def lib() -> C.CDLL:
     L.kssd_dist_counts_dev.restype = vp
     L.kssd_dist_stats.argtypes = [vp, C.POINTER(StatOpts)]
     L.kssd_dist_stats.restype = C.c_int64
+    L.kssd_dist_stats_async.argtypes = [vp, C.POINTER(StatOpts)]
+    L.kssd_dist_stats_wait.argtypes = [vp]
+    L.kssd_dist_stats_wait.restype = C.c_int64
     L.kssd_dist_fetch_stats.argtypes = [vp, vp]
     L.kssd_dist_free.argtypes = [vp]
     L.kssd_dist_free.restype = None

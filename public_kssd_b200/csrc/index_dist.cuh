@@ -811,6 +811,24 @@ __global__ void place_sub_rows_kernel(const StatRow *__restrict__ sub_rows, uint
     rows[q_out[q] + (j - first[lq])] = r;
 }
 
+// same, launched before the host knows how many hits there are: the grid covers the hit list's capacity and the count is
+// read from where the count kernel left it (kssd_dist_stats_async)
+__global__ void __launch_bounds__(kStatThreads) stats_rows_sparse_dev_kernel(const StatParams S, const uint32_t *__restrict__ qsz,
+                                                                              const uint32_t *__restrict__ rsz, const SparseHit *__restrict__ hits,
+                                                                              const unsigned long long *__restrict__ n_hits_dev, uint64_t cap,
+                                                                              const unsigned long long *__restrict__ q_pos, const uint64_t *__restrict__ q_out,
+                                                                              StatRow *__restrict__ rows)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
+    const uint64_t n_hits = *n_hits_dev;
+    if (i >= n_hits || n_hits > cap) return;
+    const SparseHit h = hits[i];
+    StatRow out;
+    stat_row(S, rsz[h.r], qsz[h.q], h.shared, out);
+    out.qry = h.q; out.ref = h.r;
+    rows[q_out[h.q] + (i - q_pos[h.q])] = out;
+}
+
 __global__ void __launch_bounds__(kStatThreads) stats_rows_sparse_kernel(const StatParams S, const uint32_t *__restrict__ qsz,
                                                                           const uint32_t *__restrict__ rsz, const SparseHit *__restrict__ hits,
                                                                           uint64_t n_hits, const unsigned long long *__restrict__ q_pos,

@@ -1356,6 +1356,12 @@ struct kssd_dist {
     std::vector<uint64_t> comp_ncodes;
     std::vector<void *> owned;                   // device copies of host query sketches
     std::vector<uint32_t> h_qsz, h_rsz;          // host copies of the sketch sizes (sub-jobs of the sparse path)
+    // kssd_dist_stats_async: the search is in flight; its outcome lands in pinned memory behind `done`
+    bool async_pending = false;
+    uint64_t *h_async = nullptr;                 // pinned: total hits | n_over (low 32) , bad extent (high 32)
+    cudaEvent_t done = nullptr;
+    uint64_t async_cap = 0;
+    kssd_stat_opts_t async_opts{};
 };
 
 static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_ctx_ct, const uint32_t *ref_ctx_ct, uint32_t *ct_ext, int filled,
@@ -1882,6 +1888,106 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
     return (int64_t)d->n_rows;
 }
 
+// Sparse search without a host round trip: count + list kernel, scan of the per-query row counts and the rows kernel are all
+// queued at once -- the rows kernel covers the hit list's capacity and reads the hit count on the device -- and the outcome
+// (hits, overflowing queries) is copied to pinned memory behind an event.  A host that feeds batch after batch never waits for
+// the GPU, and the GPU never waits for a host that was descheduled for a moment (one process per GPU, eight on a box).
+extern "C" int kssd_dist_stats_async(kssd_dist_t *d, const kssd_stat_opts_t *o)
+{
+    if (!d || !o) return fail(KSSD_E_INVAL, "kssd_dist_stats_async: null");
+    if (!d->sparse) return fail(KSSD_E_INVAL, "kssd_dist_stats_async: sparse jobs only (kssd_dist_create_sparse)");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    const bool nan_cells = o->metric == 0 ? (d->empty_qry && d->empty_ref) : (d->empty_qry || d->empty_ref);
+    const bool no_zero_rows = o->n_neighbors == 0 && (o->skip_zero || (o->dthreshold < 1.0 && !o->correction && !nan_cells));
+    d->async_opts = *o;
+    d->async_pending = false;
+    if (!no_zero_rows) return KSSD_OK;                       // needs the matrix: kssd_dist_stats_wait runs the ordinary path
+    StatParams S;
+    S.metric = o->metric; S.correction = o->correction; S.kmerlen = o->kmerlen; S.dim_rd_len = o->dim_rd_len;
+    S.skip_zero = o->skip_zero; S.dthreshold = o->dthreshold;
+    S.cmprsn_num = o->cmprsn_num ? (double)o->cmprsn_num : (double)(uint32_t)((uint32_t)d->n_ref * (uint32_t)d->n_qry);
+    const uint32_t bw = ((uint32_t)d->n_ref + 31) / 32;
+    uint32_t gbits = 1;
+    while ((1ull << gbits) - 1 < (uint64_t)d->n_ref) gbits++;
+    const uint32_t cb = 32 - gbits;
+    const bool packed = gbits <= 24 && (uint64_t)d->max_qry_size + 1 < (1ull << cb) - 1 && !getenv("KSSD_SPARSE_UNPACKED");
+    uint64_t postings = 0, spaces = 0;
+    for (const kssd_index_t *ix : d->comp_ix) { postings += ix->n_postings; spaces += ix->space; }
+    const double est_touch = spaces ? (double)d->max_qry_size * (double)postings / (double)spaces : 0.0;
+    const char *shape = getenv("KSSD_SPARSE_SHAPE");
+    const bool narrow = shape ? strcmp(shape, "narrow") == 0 : est_touch < 200.0;
+    const size_t slots = narrow ? SparseNarrow::kSlots : SparseWide::kSlots, tile = narrow ? SparseNarrow::kTile : SparseWide::kTile;
+    const size_t smem = ((packed ? 1ull : 2ull) * slots + 2ull * tile + 1 + bw) * 4;
+    if (smem > 200u * 1024u) return KSSD_OK;
+    const bool trivial = S.dthreshold >= 1.0;
+    const int nc = (int)d->comps.size();
+    if (!d->h_async) { CU(cudaMallocHost(&d->h_async, 16)); CU(cudaEventCreateWithFlags(&d->done, cudaEventDisableTiming)); }
+    const uint64_t cap = std::max<uint64_t>(1ull << 20, (uint64_t)d->n_qry * 1024);
+    d->async_cap = cap;
+    CU(c->flags.ensure((size_t)d->n_qry * 4));
+    CU(c->counts.ensure((size_t)d->n_qry * 8));
+    CU(c->pos.ensure(((size_t)d->n_qry + 1) * 8));
+    CU(c->misc.ensure(16 + sizeof(SparseComp) * 256));
+    CU(c->ords2.ensure((size_t)d->n_qry * 4));
+    CU(c->keys.ensure(cap * sizeof(SparseHit)));
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    if (d->d_rows) { cudaFreeAsync(d->d_rows, c->stream); d->d_rows = nullptr; }
+    CU(cudaMallocAsync(&d->d_rows, cap * sizeof(StatRow), c->stream));
+    uint8_t *mb = c->misc.as<uint8_t>();
+    if (nc) CU(cudaMemcpyAsync(mb + 16, d->comps.data(), sizeof(SparseComp) * nc, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(mb, 0, 16, c->stream));
+    auto launch = [&](auto kern, int threads, int max_per_sm) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = std::max(1, std::min(max_per_sm, (int)((227u * 1024u) / (smem + 3400))));
+        const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
+        kern<<<grid, threads, smem, c->stream>>>(reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, cb, S, d->d_qsz,
+                                                 d->d_rsz, c->flags.as<uint32_t>(), c->counts.as<unsigned long long>(), reinterpret_cast<unsigned long long *>(mb),
+                                                 cap, c->keys.as<SparseHit>(), reinterpret_cast<uint32_t *>(mb + 8), c->ords2.as<uint32_t>(),
+                                                 reinterpret_cast<uint32_t *>(mb + 12));
+        return KSSD_OK;
+    };
+    int lrc;
+    if (narrow) {
+        if (trivial) lrc = packed ? launch(dist_sparse_kernel<SparseNarrow, true, true>, 128, 12) : launch(dist_sparse_kernel<SparseNarrow, true, false>, 128, 12);
+        else lrc = packed ? launch(dist_sparse_kernel<SparseNarrow, false, true>, 128, 12) : launch(dist_sparse_kernel<SparseNarrow, false, false>, 128, 12);
+    } else {
+        if (trivial) lrc = packed ? launch(dist_sparse_kernel<SparseWide, true, true>, 512, 3) : launch(dist_sparse_kernel<SparseWide, true, false>, 512, 3);
+        else lrc = packed ? launch(dist_sparse_kernel<SparseWide, false, true>, 512, 2) : launch(dist_sparse_kernel<SparseWide, false, false>, 512, 2);
+    }
+    if (lrc) return lrc;
+    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream));
+    stats_rows_sparse_dev_kernel<<<(uint32_t)((cap + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
+        S, d->d_qsz, d->d_rsz, c->keys.as<SparseHit>(), reinterpret_cast<const unsigned long long *>(mb), cap, c->counts.as<unsigned long long>(),
+        c->pos.as<uint64_t>(), d->d_rows);
+    LAUNCHED(4);
+    CU(cudaMemcpyAsync(d->h_async, mb, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(d->done, c->stream));
+    d->async_pending = true;
+    return KSSD_OK;
+}
+
+// waits for kssd_dist_stats_async and returns the number of rows; anything the fast path could not finish (a query that
+// overflowed its table, more hits than the list holds, options that print zero cells) is redone by kssd_dist_stats here
+extern "C" int64_t kssd_dist_stats_wait(kssd_dist_t *d)
+{
+    if (!d) return fail(KSSD_E_INVAL, "kssd_dist_stats_wait: null");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    if (d->async_pending) {
+        d->async_pending = false;
+        CU(cudaEventSynchronize(d->done));
+        CU(cudaGetLastError());
+        const uint64_t total = d->h_async[0];
+        const uint32_t n_over = (uint32_t)d->h_async[1], bad_extent = (uint32_t)(d->h_async[1] >> 32);
+        if (bad_extent) return fail(KSSD_E_INVAL, "kssd_dist_stats: a query sketch holds more codes than its declared size allows for");
+        if (n_over == 0 && total <= d->async_cap) { d->n_rows = total; return (int64_t)total; }
+    }
+    return kssd_dist_stats(d, &d->async_opts);
+}
+
 extern "C" int kssd_dist_fetch_stats(const kssd_dist_t *d, kssd_stat_row_t *rows_out)
 {
     static_assert(sizeof(kssd_stat_row_t) == sizeof(StatRow), "row layout");
@@ -1903,7 +2009,8 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
     cudaFreeAsync(d->d_qsz, st);
     cudaFreeAsync(d->d_rsz, st);
     if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);
-
+    if (d->h_async) cudaFreeHost(d->h_async);
+    if (d->done) cudaEventDestroy(d->done);
     delete d;
 }
 

@@ -402,6 +402,22 @@ class DistJob:
         check(lib().kssd_dist_fetch_stats(self._h, rows.ctypes.data_as(C.c_void_p)))
         return rows
 
+    def stats_async(self, metric: int = 0, correction: int = 0, kmerlen: int | None = None, dim_rd_len: int | None = None,
+                    dthreshold: float = 1.0, n_neighbors: int = 0, skip_zero: int = 0, cmprsn_num: int = 0):
+        """Queue the whole sparse search (count + list + statistics) without waiting for the GPU; stats_wait() returns the row
+        count.  Several jobs of one context may be in flight (kssd_dist_stats_async)."""
+        o = capi.StatOpts(metric, correction, kmerlen if kmerlen is not None else 2 * self.ctx.k,
+                          dim_rd_len if dim_rd_len is not None else 2 * self.ctx.drlevel, dthreshold, n_neighbors, skip_zero, cmprsn_num)
+        check(lib().kssd_dist_stats_async(self._h, C.byref(o)))
+
+    def stats_wait(self, fetch: bool = False):
+        n = check(lib().kssd_dist_stats_wait(self._h))
+        if not fetch:
+            return n
+        rows = np.empty(n, dtype=capi.STAT_ROW_DTYPE)
+        check(lib().kssd_dist_fetch_stats(self._h, rows.ctypes.data_as(C.c_void_p)))
+        return rows
+
     def close(self):
         if self._h:
             lib().kssd_dist_free(self._h)

@@ -302,3 +302,31 @@ def test_query_batches_equal_one_job(gpu_ctx_l3k10, sparse, opts):
     with pytest.raises(kssd.KssdError):
         kssd.num_cof_batch(1 << 20, 100_000)
     one.close(); ix.close()
+
+
+@pytest.mark.parametrize("opts", [dict(skip_zero=1), dict(dthreshold=0.3), dict(metric=1, dthreshold=0.2), dict(dthreshold=1.0)])
+def test_async_sparse_search_equals_sync(gpu_ctx_l3k10, opts):
+    """kssd_dist_stats_async / _wait: several searches in flight on one context give the rows of the synchronous call;
+    options the fast path cannot serve (zero cells print) fall back inside _wait."""
+    from public_kssd_b200 import kssd
+    rc, ri = synth.synth_sketches(800, 300, seed=4, cluster_size=20)
+    ix = gpu_ctx_l3k10.combco2mco(rc, ri)
+    rsz = np.diff(ri).astype(np.uint32)
+    batches = [synth.synth_sketches(60, 300, seed=4, cluster_size=5, member_seed=50 + b) for b in range(4)]
+    want = []
+    for qc, qi in batches:
+        j = kssd.DistJob(gpu_ctx_l3k10, np.diff(qi).astype(np.uint32), rsz, sparse=True)
+        j.accumulate(ix, qc, qi)
+        want.append(j.stats(**opts).tobytes())
+        j.close()
+    jobs = []
+    for qc, qi in batches:
+        j = kssd.DistJob(gpu_ctx_l3k10, np.diff(qi).astype(np.uint32), rsz, sparse=True)
+        j.accumulate(ix, qc, qi)
+        j.stats_async(**opts)
+        jobs.append(j)
+    got = [j.stats_wait(fetch=True).tobytes() for j in jobs]
+    assert got == want and len(want[0]) > 0
+    for j in jobs:
+        j.close()
+    ix.close()
