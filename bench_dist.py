@@ -1,12 +1,13 @@
 """bench.py's second metric at BASELINE.json configs[2] size: 100,000 reference sketches x ~1,220 codes searched with batches of
 10,000 queries (10^9 pairs per batch), at every N.
 
-Sharding: the reference index is sharded by GENOME range and each rank's rows are final as they are -- no
-reduction.  The per-query part of the search (code lookups, clearing and reading out the query's table) does not shrink when
-only the references are split, so from four ranks on the ranks form a 2 x N/2 grid: two reference shards, N/2 query groups.
-Rank 0 holds each query batch and sends every rank the codes of its group point to point (NCCL), one batch ahead of the
-compute; every rank runs the sparse Stage III job (count + filter + list + statistics, no Q x R matrix).  The references-only
-sharding (N x 1), the north-star variant (index sharded by code range + NCCL reduce-scatter of dense partial matrices) and the
+Sharding: the ranks form a Gr x Gq grid -- Gr reference shards by GENOME range (each rank's rows are final as
+they are, no reduction) times Gq query groups.  The per-query part of the search (code lookups, clearing and reading out the
+query's table) does not shrink when only the references are split, and a 100 000-genome index is 0.5 GB, so the main line is
+1 x N: every rank holds the whole index and searches its share of each batch's queries.  Rank 0 holds each query batch and
+sends every rank the codes of its group point to point (NCCL), one batch ahead of the compute; every rank runs the sparse
+Stage III job (count + filter + list + statistics, no Q x R matrix).  The grids with reference shards (2 x N/2, N x 1 -- what an
+index beyond one GPU's memory needs), the north-star variant (index sharded by code range + NCCL reduce-scatter of dense partial matrices) and the
 peer-memory variant are timed next to it as the baselines they are.  Times are CUDA events on the library stream, max over ranks.
 """
 from __future__ import annotations
@@ -49,22 +50,19 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
     # batches stay on rank 0 until they are broadcast inside the timed loop
     t0 = time.perf_counter()
     meta = torch.zeros(2 + 2 * batches, dtype=torch.int64, device=dev)
-    q_host = []
-    if rank == 0:
-        rc, ri = synth.synth_sketches(n_ref, CODES, seed=5, cluster_size=20)
+    q_gen = []
+    if rank == 0:      # (synth_sketches_torch: the numpy generator's sketches element for element, made on the GPU)
+        t_rc, t_ri = synth.synth_sketches_torch(n_ref, CODES, seed=5, device=dev, cluster_size=20)
         for b in range(batches):
-            q_host.append(synth.synth_sketches(n_qry, CODES, seed=5, cluster_size=2, member_seed=None if b == 0 else 1000 + b))
-        meta[0], meta[1] = len(rc), n_ref
-        for b, (qc, qi) in enumerate(q_host):
-            meta[2 + 2 * b], meta[3 + 2 * b] = len(qc), len(qi)
+            q_gen.append(synth.synth_sketches_torch(n_qry, CODES, seed=5, device=dev, cluster_size=2, member_seed=None if b == 0 else 1000 + b))
+        meta[0], meta[1] = int(t_rc.numel()), n_ref
+        for b, (qc, qi) in enumerate(q_gen):
+            meta[2 + 2 * b], meta[3 + 2 * b] = int(qc.numel()), int(qi.numel())
     if world > 1:
         dist.broadcast(meta, 0)
     m = meta.cpu().numpy()
     n_codes = int(m[0])
-    if rank == 0:
-        t_rc = torch.from_numpy(rc.view(np.int32)).to(dev)
-        t_ri = torch.from_numpy(ri.view(np.int64)).to(dev)
-    else:
+    if rank != 0:
         t_rc = torch.empty(n_codes, dtype=torch.int32, device=dev)
         t_ri = torch.empty(n_ref + 1, dtype=torch.int64, device=dev)
     if world > 1:
@@ -75,10 +73,10 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
     q_dev = []
     for b in range(batches):
         if rank == 0:
-            qc, qi = q_host[b]
-            q_dev.append((torch.from_numpy(qc.view(np.int32)).to(dev), torch.from_numpy(qi.view(np.int64)).to(dev)))
+            q_dev.append(q_gen[b])
         else:
             q_dev.append((torch.empty(int(m[2 + 2 * b]), dtype=torch.int32, device=dev), torch.empty(int(m[3 + 2 * b]), dtype=torch.int64, device=dev)))
+    torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
 
     cm = (n_ref * n_qry) & 0xFFFFFFFF
@@ -196,20 +194,27 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
                 "rank0_kernel_ms_per_batch_unpipelined": {"count_list": float(np.mean([p[0] for p in ph])), "rows": float(np.mean([p[1] for p in ph]))},
                 "digest": int(agg[0].item()) & 0xFFFFFFFFFFFFFFFF, "rows_batch0": int(agg[1].item())}
 
-    # The per-query part of the search (code lookups, clearing and reading out the query's table) does not shrink when only the
-    # references are sharded, so beyond two reference shards the ranks split the QUERIES: a 2 x N/2 grid.  The references-only
-    # sharding (N x 1) is measured next to it on fewer batches.
-    Gr = 1 if world == 1 else 2
-    main = measure(Gr, batches)
+    # Which grid?  The per-query part of the search (code lookups, clearing and reading out the query's table) does not shrink
+    # when only the references are sharded, so the ranks split the QUERIES first: a 100 000-genome index is 0.5 GB of the
+    # 180 GB a rank has, every rank holds all of it (1 x N) and no rank repeats another's lookups.  Reference shards (2 x N/2,
+    # N x 1) are what an index beyond one GPU's memory needs; they are timed next to it on fewer batches.
+    grids = [1] if world == 1 else sorted({1, 2, world} & {g for g in (1, 2, world) if world % g == 0})
+    res = {1: measure(1, batches)}
+    for g in grids[1:]:
+        res[g] = measure(g, min(batches, 4))
+    Gr = 1
+    main = res[Gr]
     out = {"pairs_per_batch": n_qry * n_ref, "refs": n_ref, "queries_per_batch": n_qry, "ref_postings": n_codes,
-           "sharding": (f"ranks as a {Gr} x {world // Gr} grid: reference index sharded by genome range over {Gr} rank(s), each batch's queries split over "
+           "sharding": (f"ranks as a {Gr} x {world // Gr} grid: every rank holds the whole reference index, each batch's queries are split over "
                         f"{world // Gr} group(s); query codes sent point to point one batch ahead (NCCL), sparse job per rank, no reduction"),
            "timing": "CUDA events on the library stream around all batches (host gaps included), max over ranks", "generation_s": gen_s}
     out.update({k: v for k, v in main.items() if k not in ("digest", "rows_batch0")})
-    if world > 2:
-        alt = measure(world, min(batches, 4))
-        out["refs_only_sharding"] = {k: v for k, v in alt.items() if k not in ("digest", "rows_batch0", "printed_rows")}
-        out["refs_only_sharding"]["content_same_as_grid"] = bool(alt["digest"] == main["digest"] and alt["rows_batch0"] == main["rows_batch0"])
+    if world > 1:
+        out["other_grids"] = []
+        for g in grids[1:]:
+            alt = {k: v for k, v in res[g].items() if k not in ("digest", "rows_batch0", "printed_rows")}
+            alt["content_same_as_main"] = bool(res[g]["digest"] == main["digest"] and res[g]["rows_batch0"] == main["rows_batch0"])
+            out["other_grids"].append(alt)
 
     # ---- content: batch 0's rows over all ranks against one GPU holding the whole index (rank 0), and against the oracle
     if rank == 0:
@@ -274,7 +279,7 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
                                "frac": alg / (c_ms * 1e-3) / 1e9 / peak_gbs, "traffic": traffic, "algorithmic_bytes": alg,
                                "note": "bytes = 4 Nq (codes) + 16 Nq (two offsets per lookup) + 4 P (postings) + 4 Q R (matrix written once), SURVEY.md s8d"}
             # end to end: host query buffers in, statistics rows on the host out (sparse job)
-            qc_h, qi_h = q_host[0]
+            qc_h, qi_h = tq.cpu().numpy().view(np.uint32), ti.cpu().numpy().view(np.uint64)
             e2e = []
             for _ in range(3):
                 t1 = time.perf_counter()

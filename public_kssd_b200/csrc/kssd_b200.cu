@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -124,6 +125,15 @@ struct kssd_ctx {
     float last_ms[5] = {0, 0, 0, 0, 0};
     bool stats_ms_pending = false;               // last_ms[4] of a sparse search: read off ev[2] .. ev[1] on demand
     bool total_ms_pending = false;               // last_ms[1] of a bucket-mode sketch: read off ev[0] .. ev[2] on demand
+    // Sketch-size arrays of reference sets already on the device (Stage III): the reference's query-batch loop
+    // (command_dist.c:763-790) searches the same references batch after batch, and a pageable 400 KB upload per batch
+    // would make the host wait for the stream.  Keyed by content (memcmp); an entry lives while a job uses it.
+    struct SizeSet { uint32_t refs = 0; bool any_empty = false; uint32_t *dev = nullptr; std::shared_ptr<std::vector<uint32_t>> host; };
+    std::vector<SizeSet> size_sets;
+    // pinned result slots + events of kssd_dist_stats_async (cudaMallocHost / cudaFreeHost synchronise the device: never per job)
+    uint64_t *async_page = nullptr;
+    std::vector<int> async_free;
+    std::vector<cudaEvent_t> async_events;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -295,6 +305,9 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
                       &c->cubtmp, &c->misc})
         b->release();
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
+    for (auto &e : c->size_sets) cudaFree(e.dev);
+    if (c->async_page) cudaFreeHost(c->async_page);
+    for (cudaEvent_t e : c->async_events) if (e) cudaEventDestroy(e);
     cudaFree(c->d_prefilter);
     cudaFree(c->d_prefilter3);
     cudaFree(c->d_gtab);
@@ -1355,7 +1368,9 @@ struct kssd_dist {
     std::vector<const kssd_index_t *> comp_ix;
     std::vector<uint64_t> comp_ncodes;
     std::vector<void *> owned;                   // device copies of host query sketches
-    std::vector<uint32_t> h_qsz, h_rsz;          // host copies of the sketch sizes (sub-jobs of the sparse path)
+    std::vector<uint32_t> h_qsz;                 // host copies of the sketch sizes (sub-jobs of the sparse path)
+    std::shared_ptr<std::vector<uint32_t>> h_rsz;   // shared with the context's cache of reference sets (d_rsz is its device copy)
+    int async_slot = -1;                         // pinned slot + event of kssd_dist_stats_async (from the context's pool)
     // kssd_dist_stats_async: the search is in flight; its outcome lands in pinned memory behind `done`
     bool async_pending = false;
     uint64_t *h_async = nullptr;                 // pinned: total hits | n_over (low 32) , bad extent (high 32)
@@ -1372,16 +1387,34 @@ static int dist_create(kssd_ctx_t *c, int n_qry, int n_ref, const uint32_t *qry_
     kssd_dist *d = new kssd_dist();
     d->ctx = c; d->n_qry = n_qry; d->n_ref = n_ref;
     for (int i = 0; i < n_qry; i++) { d->max_qry_size = std::max(d->max_qry_size, qry_ctx_ct[i]); d->empty_qry |= qry_ctx_ct[i] == 0; }
-    for (int i = 0; i < n_ref; i++) d->empty_ref |= ref_ctx_ct[i] == 0;
     d->h_qsz.assign(qry_ctx_ct, qry_ctx_ct + n_qry);
-    d->h_rsz.assign(ref_ctx_ct, ref_ctx_ct + n_ref);
+    // the reference sizes: on the device already if an earlier job of this context searched the same reference set
+    {
+        kssd_ctx::SizeSet *hit = nullptr;
+        for (auto &e : c->size_sets)                                   // (exact: one memcmp of the array, ~30 us per 100 000 references)
+            if (e.refs == (uint32_t)n_ref && memcmp(e.host->data(), ref_ctx_ct, (size_t)n_ref * 4) == 0) { hit = &e; break; }
+        if (!hit) {
+            for (size_t i = 0; i < c->size_sets.size() && c->size_sets.size() >= 4;)      // keep a few; never drop one a job still uses
+                if (c->size_sets[i].host.use_count() == 1) { cudaFreeAsync(c->size_sets[i].dev, c->stream); c->size_sets.erase(c->size_sets.begin() + i); }
+                else i++;
+            kssd_ctx::SizeSet e;
+            e.refs = (uint32_t)n_ref;
+            for (int i = 0; i < n_ref; i++) e.any_empty |= ref_ctx_ct[i] == 0;
+            e.host = std::make_shared<std::vector<uint32_t>>(ref_ctx_ct, ref_ctx_ct + n_ref);
+            if (cudaMallocAsync(&e.dev, (size_t)n_ref * 4, c->stream) != cudaSuccess) { delete d; return fail(KSSD_E_CUDA, "kssd_dist_create: out of device memory"); }
+            CU(cudaMemcpyAsync(e.dev, e.host->data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
+            c->size_sets.push_back(std::move(e));
+            hit = &c->size_sets.back();
+        }
+        d->h_rsz = hit->host;
+        d->d_rsz = hit->dev;
+        d->empty_ref = hit->any_empty;
+    }
     if (ct_ext) { d->d_ct = ct_ext; d->owns_ct = false; d->components_done = filled ? 1 : 0; }
     else if (filled < 0) d->sparse = true;       // sparse job: the matrix is allocated only if a query overflows the sparse path
     else CU(cudaMallocAsync(&d->d_ct, (size_t)n_qry * n_ref * 4, c->stream));
     CU(cudaMallocAsync(&d->d_qsz, (size_t)n_qry * 4, c->stream));
-    CU(cudaMallocAsync(&d->d_rsz, (size_t)n_ref * 4, c->stream));
-    CU(cudaMemcpyAsync(d->d_qsz, d->h_qsz.data(), (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));     // (the job's own copies: no wait)
-    CU(cudaMemcpyAsync(d->d_rsz, d->h_rsz.data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d->d_qsz, d->h_qsz.data(), (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));     // (the job's own copy: no wait)
     *out = d;
     return KSSD_OK;
 }
@@ -1732,7 +1765,7 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
                     std::sort(over.begin(), over.end());
                     std::vector<uint32_t> sub_qsz(n_over);
                     for (uint32_t i = 0; i < n_over; i++) sub_qsz[i] = d->h_qsz[over[i]];
-                    int rc = dist_create(c, (int)n_over, d->n_ref, sub_qsz.data(), d->h_rsz.data(), nullptr, 0, &sub);
+                    int rc = dist_create(c, (int)n_over, d->n_ref, sub_qsz.data(), d->h_rsz->data(), nullptr, 0, &sub);
                     if (rc) return rc;
                     CU(cudaMallocAsync(&d_list, (size_t)n_over * 4, c->stream));
                     scratch.push_back(d_list);
@@ -1922,7 +1955,19 @@ extern "C" int kssd_dist_stats_async(kssd_dist_t *d, const kssd_stat_opts_t *o)
     if (smem > 200u * 1024u) return KSSD_OK;
     const bool trivial = S.dthreshold >= 1.0;
     const int nc = (int)d->comps.size();
-    if (!d->h_async) { CU(cudaMallocHost(&d->h_async, 16)); CU(cudaEventCreateWithFlags(&d->done, cudaEventDisableTiming)); }
+    if (d->async_slot < 0) {                                 // a pinned 16-byte slot and an event from the context's pool
+        if (!c->async_page) {
+            CU(cudaMallocHost(&c->async_page, 4096));
+            for (int i = 255; i >= 0; i--) c->async_free.push_back(i);
+            c->async_events.assign(256, nullptr);
+        }
+        if (c->async_free.empty()) return KSSD_OK;           // 256 searches in flight: this one takes the ordinary path in _wait
+        d->async_slot = c->async_free.back();
+        c->async_free.pop_back();
+        if (!c->async_events[d->async_slot]) CU(cudaEventCreateWithFlags(&c->async_events[d->async_slot], cudaEventDisableTiming));
+        d->h_async = c->async_page + 2 * d->async_slot;
+        d->done = c->async_events[d->async_slot];
+    }
     const uint64_t cap = std::max<uint64_t>(1ull << 20, (uint64_t)d->n_qry * 1024);
     d->async_cap = cap;
     CU(c->flags.ensure((size_t)d->n_qry * 4));
@@ -2007,10 +2052,12 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
     if (d->owns_ct && d->d_ct) cudaFreeAsync(d->d_ct, st);
     for (void *p : d->owned) cudaFreeAsync(p, st);
     cudaFreeAsync(d->d_qsz, st);
-    cudaFreeAsync(d->d_rsz, st);
+    d->h_rsz.reset();                                        // (d_rsz belongs to the context's cache of reference sets)
     if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);
-    if (d->h_async) cudaFreeHost(d->h_async);
-    if (d->done) cudaEventDestroy(d->done);
+    if (d->async_slot >= 0) {
+        if (d->async_pending) cudaEventSynchronize(d->done);   // the slot must not be reused while a copy into it is queued
+        d->ctx->async_free.push_back(d->async_slot);
+    }
     delete d;
 }
 

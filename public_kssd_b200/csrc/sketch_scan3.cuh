@@ -75,9 +75,9 @@ struct LaneQ3 {
 // number in the top five bits), the lane's skip flags, the genome.  The queue outlives spans: entries carry all they need.
 struct WarpQ3 { uint32_t lo[kQueueCap], hi[kQueueCap], ordlo[kQueueCap], ordhi[kQueueCap], f[kQueueCap], gid[kQueueCap]; };
 #ifdef KSSD_SCAN_TMA
-constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 48 + 2064);   // + SpanCtx + TmaRing
+constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 56 + 2072);   // + SpanCtx + TmaRing
 #else
-constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 48);   // + SpanCtx
+constexpr size_t kScan3SmemBytes = (size_t)kPf3Words * 4 + (size_t)kScanWarps * (sizeof(WarpQ3) + sizeof(LaneQ3) + 56);   // + SpanCtx
 #endif
 
 __device__ __forceinline__ bool pf3_probe(const uint32_t *__restrict__ pf, uint32_t v)
@@ -442,11 +442,11 @@ __device__ __forceinline__ void tma_wait(TmaRing &r, int stage, uint32_t parity)
 
 // Cold per-span state lives in shared memory (one record per warp): the span's byte extents are 64-bit and only the
 // first and last iterations of a span look at them -- in registers they pushed the loop counters out to local memory.
-struct SpanCtx { uint64_t gs, ge, start, end, chunk0; uint32_t gid, after_end; };
+struct SpanCtx { uint64_t gs, ge, start, end, chunk0; uint32_t gid, after_end, ln, qn; };
 
 // ST: bases per first-level probe (3 or 1); BIG: 2k-1 history bases need more than 32 bits (k >= 9)
 template <int ST, bool BIG>
-__device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, uint32_t &qn, LaneQ3 &lq,
+__device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint32_t *__restrict__ pf, WarpQ3 &q, LaneQ3 &lq,
                            volatile SpanCtx &sc
 #ifdef KSSD_SCAN_TMA
                            , TmaRing &ring
@@ -460,12 +460,11 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     // stream state in registers; packed into a StreamState only around the out-of-line general iterations
     uint32_t cw0 = 0, cw1 = 0;                                   // the last 2k-1 bases of the stream, oldest lowest
     uint32_t since_break = 0, hdr = 0;
-    uint32_t ln = 0;
     uint32_t n_steady;
     Bytes32 cur;
     {
         const uint64_t start = sc.start, end = sc.end, ge = sc.ge, chunk0 = start & ~127ull;
-        if (lane == 0) { sc.chunk0 = chunk0; sc.after_end = 0; }
+        if (lane == 0) { sc.chunk0 = chunk0; sc.after_end = 0; sc.ln = 0; }
         __syncwarp();
         // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
         const uint64_t lim = end < ge ? end : ge;
@@ -631,6 +630,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             if (BIG) cw1 = __shfl_sync(kFull, S1, 31);
             const uint32_t hit = __ballot_sync(kFull, cand != 0);
             if (hit) {
+                uint32_t ln = sc.ln;                                  // parked lanes of this warp (cold state: shared memory)
                 if (cand) {
                     const uint32_t i = ln + __popc(hit & ((1u << lane) - 1u));
                     lq.y[0][i] = Y0; lq.y[1][i] = Y1; lq.y[2][i] = Y2; lq.y[3][i] = Y3;
@@ -639,10 +639,13 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 ln += __popc(hit);
                 __syncwarp();
                 if (ln >= 32) {
+                    uint32_t qn = sc.qn;                              // candidates waiting in the warp's queue (cold state too)
                     drain3<ST>(P, A, q, qn, lq, ln - 32, 32, sc.gid, sc.chunk0 - sc.gs);
+                    if (lane == 0) sc.qn = qn;
                     ln -= 32;
-                    __syncwarp();
                 }
+                if (lane == 0) sc.ln = ln;
+                __syncwarp();
             }
         } else {
             // two general 512-byte iterations with a 16-byte lane mapping (reloaded: L2 hits); the carry changes
@@ -650,6 +653,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             const uint64_t cw = ((uint64_t)cw1 << 32) | cw0;
             const uint64_t start = sc.start, ge = sc.ge, end = sc.end, cbase = sc.chunk0 + ((uint64_t)it << 10);
             StreamState st = {rev_groups64(cw, TL - 1), since_break, sc.after_end, hdr};
+            uint32_t qn = sc.qn;
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 const uint64_t sbase = cbase + 512ull * h;
@@ -664,7 +668,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             cw0 = (uint32_t)cwr; cw1 = (uint32_t)(cwr >> 32);
             since_break = st.since_break; hdr = st.hdr;
             __syncwarp();
-            if (lane == 0) sc.after_end = st.after_end;
+            if (lane == 0) { sc.after_end = st.after_end; sc.qn = qn; }
             __syncwarp();
         }
 
@@ -677,7 +681,16 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
             }
         }
     }
-    if (ln) { drain3<ST>(P, A, q, qn, lq, 0, ln, sc.gid, sc.chunk0 - sc.gs); __syncwarp(); }
+    {
+        const uint32_t ln = sc.ln;
+        if (ln) {
+            uint32_t qn = sc.qn;
+            drain3<ST>(P, A, q, qn, lq, 0, ln, sc.gid, sc.chunk0 - sc.gs);
+            __syncwarp();
+            if (lane == 0) sc.qn = qn;
+            __syncwarp();
+        }
+    }
     if (hdr && at_eof && lane == 0) atomicOr(&A.gstatus[sc.gid], 1);   // the text ended inside a '>' line
 }
 
@@ -697,7 +710,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
     __syncthreads();
     WarpQ3 &q = queues[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
-    uint32_t qn = 0;                                      // candidates waiting in the warp's queue (it outlives spans)
+    if (lane == 0) spans[threadIdx.x >> 5].qn = 0;       // candidates waiting in the warp's queue (it outlives spans)
+    __syncwarp();
     for (;;) {
         uint32_t si = 0;
         if (lane == 0) si = atomicAdd(A.ticket, 1u);
@@ -712,12 +726,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __
         if (lane == 0) { sc.gs = gs; sc.ge = ge; sc.start = start; sc.end = end; sc.gid = gid; }
         __syncwarp();
 #ifdef KSSD_SCAN_TMA
-        scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], sc, reinterpret_cast<TmaRing *>(spans + kScanWarps)[threadIdx.x >> 5]);
+        scan_span3<ST, BIG>(P, A, pf, q, lqueues[threadIdx.x >> 5], sc, reinterpret_cast<TmaRing *>(spans + kScanWarps)[threadIdx.x >> 5]);
 #else
-        scan_span3<ST, BIG>(P, A, pf, q, qn, lqueues[threadIdx.x >> 5], sc);
+        scan_span3<ST, BIG>(P, A, pf, q, lqueues[threadIdx.x >> 5], sc);
 #endif
     }
-    if (qn) resolve3(P, A, q, 0, qn);
+    {
+        __syncwarp();
+        const uint32_t qn = reinterpret_cast<volatile SpanCtx *>(spans)[threadIdx.x >> 5].qn;
+        if (qn) resolve3(P, A, q, 0, qn);
+    }
 }
 
 }  // namespace kssd

@@ -293,3 +293,79 @@ def contig_genome(nbases: int, seed: int, contig_len: int = 100_000, width: int 
         pos += ln
         c += 1
     return np.concatenate(parts)
+
+
+def synth_sketches_torch(n_genomes: int, codes_per_genome: int, seed: int, device, code_bits: int = 28, cluster_size: int = 20,
+                         min_div: float = 0.001, max_div: float = 0.1, klen: int = 20, member_seed: int | None = None,
+                         block_clusters: int = 512):
+    """synth_sketches, evaluated with torch on `device` (bench data at configs[2] size in a second instead of 20 s of
+    numpy calls per genome): the SAME codes and index, element for element (tests/test_synth_torch.py).
+    Returns (codes int32 tensor [bit pattern of the uint32 codes], index int64 tensor[n+1])."""
+    import torch
+
+    M64 = 0xFFFFFFFFFFFFFFFF
+
+    def s64(v: int) -> int:                      # python int -> the int64 with the same bit pattern
+        v &= M64
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(x, s):                               # logical shift right of int64 bit patterns
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    def mix(x):
+        z = x + s64(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+        return z ^ lsr(z, 31)
+
+    def streams(seeds, n, salt):                 # rows: _stream(seed, n, salt) for every seed (python ints)
+        base = torch.tensor([s64(sd * 0x9E3779B97F4A7C15 + salt * 0xD1B54A32D192ED03) for sd in seeds], dtype=torch.int64, device=device)
+        return mix(base[:, None] + torch.arange(n, dtype=torch.int64, device=device)[None, :])
+
+    ms = seed if member_seed is None else member_seed
+    n_clusters = (n_genomes + cluster_size - 1) // cluster_size
+    mask = (1 << code_bits) - 1
+    SENT = 1 << 40                               # sorts after every code
+    n = codes_per_genome
+
+    def sort_unique_rows(v):                     # rows sorted, repeats pushed to the end as SENT
+        v, _ = torch.sort(v, dim=1)
+        dup = torch.zeros_like(v, dtype=torch.bool)
+        dup[:, 1:] = (v[:, 1:] == v[:, :-1]) & (v[:, 1:] != SENT)
+        v = torch.where(dup, torch.full_like(v, SENT), v)
+        v, _ = torch.sort(v, dim=1)
+        return v
+
+    keep_ps = []
+    for m in range(cluster_size):
+        if m == 0:
+            keep_ps.append(2.0)
+        else:
+            d = min_div * (max_div / min_div) ** ((m - 1) / max(cluster_size - 2, 1))
+            keep_ps.append((1.0 - d) ** klen)
+    keep_row = torch.tensor(keep_ps, dtype=torch.float64, device=device)
+
+    out_codes, out_counts = [], []
+    for c0 in range(0, n_clusters, block_clusters):
+        c1 = min(c0 + block_clusters, n_clusters)
+        nc = c1 - c0
+        anc = sort_unique_rows(streams([seed * 31 + c for c in range(c0, c1)], n, 20) & mask)          # [nc, n], SENT-padded
+        gids = [c * cluster_size + m for c in range(c0, c1) for m in range(cluster_size)]
+        r = streams([ms * 1009 + g for g in gids], n, 21)
+        u = lsr(r, 11).to(torch.float64) * (1.0 / (1 << 53))
+        fresh = streams([ms * 2003 + g for g in gids], n, 22) & mask
+        ancm = anc[:, None, :].expand(nc, cluster_size, n).reshape(nc * cluster_size, n)
+        kp = keep_row[None, :].expand(nc, cluster_size).reshape(nc * cluster_size, 1)
+        s = torch.where(u < kp, ancm, fresh)
+        s = torch.where(ancm == SENT, ancm, s)                                                       # streams are cut at anc.size
+        s = sort_unique_rows(s)
+        live = torch.tensor([g < n_genomes for g in gids], dtype=torch.bool, device=device)
+        s = s[live]
+        valid = s != SENT
+        out_codes.append(s[valid].to(torch.int32))                                                    # codes < 2^28: same bits
+        out_counts.append(valid.sum(dim=1))
+    codes = torch.cat(out_codes)
+    counts = torch.cat(out_counts)
+    index = torch.zeros(n_genomes + 1, dtype=torch.int64, device=device)
+    index[1:] = torch.cumsum(counts, dim=0)
+    return codes, index
