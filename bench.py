@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dist-scale", action="store_true", help="skip the 10,000 x 100,000 Stage III measurement (N = 1 only)")
     ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ Stage I leg (N = 1 only)")
+    ap.add_argument("--no-files", action="store_true", help="skip the end-to-end-from-files leg (N = 1 only)")
     ap.add_argument("--dist-batches", type=int, default=8, help="query batches of the configs[2]-size search")
     ap.add_argument("--ref-sample", type=int, default=0, help="genomes in the CPU sample (0 = auto)")
     return ap.parse_args()
@@ -215,6 +216,47 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the reference arm: the unmodified CPU kssd on the box's host cores
 # ------------------------------------------------------------------------------------------------
+def files_leg(ctx, host_np, goff, glen, genome_len, ids_e2e, ix_e2e, n_plain=200, n_gz=48):
+    """End to end the way a user runs it: Stage I from FILES (kssd_stage1_files: host threads read / inflate into pinned staging,
+    H2D, scan, results back).  Plain FASTA and gzip (level 1, the format of the reference's own fixtures) on tmpfs; the ids must
+    equal the resident path's."""
+    import gzip
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    work = Path(tempfile.mkdtemp(prefix="kssd_filesleg_", dir=base))
+    out = {}
+    try:
+        n_plain = min(n_plain, len(glen))
+        n_gz = min(n_gz, n_plain)
+        plain, gz = [], []
+        for i in range(n_plain):
+            g = host_np[int(goff[i]):int(goff[i]) + int(glen[i])]
+            f = work / f"g{i:05d}.fasta"
+            f.write_bytes(g.tobytes())
+            plain.append(f)
+            if i < n_gz:
+                fz = work / f"g{i:05d}.fasta.gz"
+                with gzip.open(fz, "wb", compresslevel=1) as z:
+                    z.write(g.tobytes())
+                gz.append(fz)
+        for name, paths in (("plain", plain), ("gz", gz)):
+            best, sk = None, None
+            for _ in range(3):                                       # the first call pins the staging buffers
+                sk, t = ctx.sketch_files(paths)
+                best = t if best is None or t["total_s"] < best["total_s"] else best
+            n = len(paths)
+            bp = n * genome_len
+            same = bool(np.array_equal(sk.ids[0], ids_e2e[:int(ix_e2e[n])]))
+            on_disk = int(sum(f.stat().st_size for f in paths))
+            out[name] = {"value": bp / best["total_s"] / 1e9, "unit": "Gbp/s", "files": n, "text_bytes": best["bytes"], "bytes_on_disk": on_disk,
+                         "total_s": best["total_s"], "read_s": best["read_s"], "gpu_s": best["gpu_s"], "text_gb_per_s": best["bytes"] / best["total_s"] / 1e9,
+                         "matches_device_path": same}
+        out["note"] = ("kssd_stage1_files on tmpfs files, best of 3 calls, every host core reading / inflating (zlib); gz = gzip -1; "
+                       "ids compared with the resident path's")
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
 def reference_run(host_genomes, shuf_table, steps, warmup, cores, with_dist=True, files_fn=None):
     """host_genomes: list of uint8 arrays (FASTA text).  Times `kssd dist` stage I per step on tmpfs;
     stage II / III once.  Returns dict."""
@@ -447,6 +489,18 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * bp / float(te.item()) / 1e9
     clk = clocks.stop()
+    # what the box's host -> device path alone does with the same bytes (every rank copies its pinned batch at the same time):
+    # the ceiling of any end-to-end number from host memory
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    buf.copy_(host, non_blocking=True)
+    h1.record()
+    barrier()
+    th = torch.tensor([h0.elapsed_time(h1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    h2d_ms = float(th.item())
 
     # the device-resident and host paths must agree with each other
     ids_dev = np.empty(n_codes, dtype=np.uint32)
@@ -489,6 +543,13 @@ def main():
         except Exception as ex:  # must not take the headline measurement down
             fastq_info = {"failed": str(ex)}
 
+    files_info = None
+    if world == 1 and not args.no_files:
+        try:
+            files_info = files_leg(ctx, host_np, goff, glen, args.genome_len, ids_e2e, ix_e2e)
+        except Exception as ex:  # must not take the headline measurement down
+            files_info = {"failed": str(ex)}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
@@ -530,7 +591,10 @@ def main():
                 "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic", "config": config, "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": float(te.item()) * 1e3, "matches_device_path": same},
+                        "ms_per_step": float(te.item()) * 1e3, "matches_device_path": same,
+                        "h2d_copy_alone_ms": h2d_ms, "h2d_aggregate_gb_per_s": world * nbytes / (h2d_ms * 1e-3) / 1e9,
+                        "h2d_share_of_step": h2d_ms / (float(te.item()) * 1e3),
+                        "from_files": files_info},
                 "gpu_launches": gpu_launches, "roofline": roof, "cpu_baseline": cpu_baseline, "dist": dist_info,
                 "fastq": fastq_info,
                 "sketch": {"codes": n_codes, "text_bytes": text_bytes, "scan_kernel_ms": scan, "step_ms": step_ms_max}}

@@ -78,7 +78,7 @@ __global__ void comp_rows_kernel(const uint64_t *__restrict__ keys, const uint64
     for (uint32_t n = 1; n <= k; n++) sum += (long long)(a[n] & 0xffffu);
     int lastsum = 0, lastn = 0;
     for (int n = (int)((double)k * 0.98); (double)n <= (double)k * 0.99; n++) {
-        lastsum += (int)(a[n] & 0xffffu);
+        lastsum += n == 0 ? (int)k : (int)(a[n] & 0xffffu);     // (k == 1: the reference reads ref_abund[rn][0], the count itself)
         lastn++;
     }
     row.median = (uint32_t)(a[k / 2] & 0xffffu);

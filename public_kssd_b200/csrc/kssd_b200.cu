@@ -133,7 +133,8 @@ struct kssd_ctx {
     // pinned result slots + events of kssd_dist_stats_async (cudaMallocHost / cudaFreeHost synchronise the device: never per job)
     uint64_t *async_page = nullptr;
     std::vector<int> async_free;
-    std::vector<cudaEvent_t> async_events;
+    std::vector<cudaEvent_t> async_events, async_counted;
+    cudaStream_t stream2 = nullptr;              // the rows pass of search b runs here while the count kernel of search b + 1 runs on `stream`
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +309,8 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     for (auto &e : c->size_sets) cudaFree(e.dev);
     if (c->async_page) cudaFreeHost(c->async_page);
     for (cudaEvent_t e : c->async_events) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->async_counted) if (e) cudaEventDestroy(e);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     cudaFree(c->d_prefilter);
     cudaFree(c->d_prefilter3);
     cudaFree(c->d_gtab);
@@ -441,9 +444,12 @@ __global__ void sketch_total_kernel(const uint32_t *__restrict__ keep, const uin
     *slot = outpos[n - 1] + keep[n - 1];
 }
 
-// FASTQ: per genome, index the lines (two streaming passes + a scan), then one thread per record
+// FASTQ: per genome, index the lines, then one thread per record.  The index is built in ONE pass over the text
+// (nl_index_kernel: decoupled look-back, 32-bit offsets, counts left on the device -- no host round trip before the walk);
+// files of 4 GiB and more, or with lines so short that the index outgrows its buffer (`single_pass` false after the retry),
+// take the two-pass index (count, scan, fill) with 64-bit positions.
 static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, const uint64_t *glen, int n_genomes, int mode, int Q,
-                     const ScanArgs &A)
+                     const ScanArgs &A, bool single_pass)
 {
     const SketchParams &P = c->P;
     CU(cudaFuncSetAttribute(sketch_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kPfWords + kPf2Words) * 4)));
@@ -451,6 +457,29 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
         const uint64_t gs = goff[g], ge = gs + glen[g];
         if (ge == gs) continue;
         const uint64_t a0 = gs & ~15ull;
+        if (single_pass && ge - a0 < 0xffffffffull) {
+            const uint64_t nblk = (ge - a0 + kNlBytesPerBlock - 1) / kNlBytesPerBlock;
+            const uint64_t lines_cap = std::max<uint64_t>((ge - a0) / 8, 4096);          // lines of 8 bytes on average: 10x the usual read
+            CU(c->flags.ensure(nblk * 8 + 64));
+            CU(c->minord.ensure(lines_cap * 4));
+            unsigned long long *state = c->flags.as<unsigned long long>();
+            NlIndexOut *io = reinterpret_cast<NlIndexOut *>(state + nblk);
+            CU(cudaMemsetAsync(state, 0, nblk * 8 + sizeof(NlIndexOut), c->stream));
+            nl_index_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, (uint32_t)nblk, state, io, c->minord.as<uint32_t>(), (uint32_t)lines_cap,
+                                                                          A.ticket);
+            FastqArgs F{};
+            F.seq = d_seq; F.seq_bytes = A.seq_bytes; F.gs = gs; F.ge = ge;
+            F.nlpos32 = c->minord.as<uint32_t>(); F.pos_base = a0; F.idx = io;
+            F.gid = (uint32_t)g;
+            F.abund = mode == KSSD_MODE_FASTQ_ABUND;
+            F.Q = Q;
+            F.line_cap = F.abund ? 4094u : 19998u;
+            F.out_keys = A.out_keys; F.out_ords = A.out_ords; F.out_cap = A.out_cap; F.out_count = A.out_count; F.gstatus = A.gstatus;
+            const uint64_t want = ((ge - gs) / 64 + kFastqThreads - 1) / kFastqThreads;   // records are not counted yet: >= 64 bytes each as a guess
+            sketch_fastq_kernel<<<(uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)c->sm_count), kFastqThreads, (kPfWords + kPf2Words) * 4, c->stream>>>(P, F);
+            LAUNCHED(2);
+            continue;
+        }
         const uint64_t nblk = (ge - a0 + kNlBytesPerBlock - 1) / kNlBytesPerBlock;
         if (nblk > 0x7fffffffull) return fail(KSSD_E_INVAL, "kssd_sketch_batch: FASTQ text of genome %d too large", g);
         CU(c->flags.ensure(nblk * 4));
@@ -816,6 +845,7 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
     kssd_sketch *S = new kssd_sketch();
     S->ctx = c; S->n_genomes = n_genomes; S->n_comp = c->info.component_num; S->mode = mode;
     uint32_t n_occ = 0;
+    bool fq_single_pass = !getenv("KSSD_FASTQ_TWO_PASS");
     for (int attempt = 0;; attempt++) {
         if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
         CU(c->keys.ensure(cap * 8));
@@ -847,13 +877,16 @@ static int sketch_run(kssd_ctx *c, const uint8_t *d_seq, size_t seq_bytes, const
                 LAUNCHED(1);
             }
         } else {
-            int rc = fastq_run(c, d_seq, goff, glen, n_genomes, mode, opts ? opts->Q : 0, A);
+            int rc = fastq_run(c, d_seq, goff, glen, n_genomes, mode, opts ? opts->Q : 0, A, fq_single_pass);
             if (rc) { delete S; return rc; }
         }
         CU(cudaEventRecord(c->ev[1], c->stream));
-        CU(cudaMemcpyAsync(&n_occ, mb + m_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+        uint32_t tick_cnt[2] = {0, 0};                          // m_tick (FASTQ: "a line index overflowed") | m_cnt
+        CU(cudaMemcpyAsync(tick_cnt, mb + m_tick, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaGetLastError());
+        n_occ = tick_cnt[1];
+        if (is_fastq && fq_single_pass && tick_cnt[0]) { fq_single_pass = false; attempt--; continue; }      // once more with the two-pass index
         if (n_occ <= cap) break;
         if (attempt >= 2) { delete S; return fail(KSSD_E_NOMEM, "kssd_sketch_batch: occurrence buffer overflow (%u > %llu)", n_occ, (unsigned long long)cap); }
         cap = (uint64_t)n_occ + (n_occ >> 3) + 1024;
@@ -1370,7 +1403,9 @@ struct kssd_dist {
     std::vector<void *> owned;                   // device copies of host query sketches
     std::vector<uint32_t> h_qsz;                 // host copies of the sketch sizes (sub-jobs of the sparse path)
     std::shared_ptr<std::vector<uint32_t>> h_rsz;   // shared with the context's cache of reference sets (d_rsz is its device copy)
-    int async_slot = -1;                         // pinned slot + event of kssd_dist_stats_async (from the context's pool)
+    int async_slot = -1;                         // pinned slot + events of kssd_dist_stats_async (from the context's pool)
+    uint8_t *d_async = nullptr;                  // its per-job scratch: hit list, per-query tallies (several searches are in flight)
+    cudaEvent_t counted = nullptr;
     // kssd_dist_stats_async: the search is in flight; its outcome lands in pinned memory behind `done`
     bool async_pending = false;
     uint64_t *h_async = nullptr;                 // pinned: total hits | n_over (low 32) , bad extent (high 32)
@@ -1955,33 +1990,44 @@ extern "C" int kssd_dist_stats_async(kssd_dist_t *d, const kssd_stat_opts_t *o)
     if (smem > 200u * 1024u) return KSSD_OK;
     const bool trivial = S.dthreshold >= 1.0;
     const int nc = (int)d->comps.size();
-    if (d->async_slot < 0) {                                 // a pinned 16-byte slot and an event from the context's pool
+    if (d->async_slot < 0) {                                 // a pinned 16-byte slot and two events from the context's pool
         if (!c->async_page) {
             CU(cudaMallocHost(&c->async_page, 4096));
             for (int i = 255; i >= 0; i--) c->async_free.push_back(i);
             c->async_events.assign(256, nullptr);
+            c->async_counted.assign(256, nullptr);
+            CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         }
         if (c->async_free.empty()) return KSSD_OK;           // 256 searches in flight: this one takes the ordinary path in _wait
         d->async_slot = c->async_free.back();
         c->async_free.pop_back();
-        if (!c->async_events[d->async_slot]) CU(cudaEventCreateWithFlags(&c->async_events[d->async_slot], cudaEventDisableTiming));
+        if (!c->async_events[d->async_slot]) {
+            CU(cudaEventCreateWithFlags(&c->async_events[d->async_slot], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->async_counted[d->async_slot], cudaEventDisableTiming));
+        }
         d->h_async = c->async_page + 2 * d->async_slot;
         d->done = c->async_events[d->async_slot];
+        d->counted = c->async_counted[d->async_slot];
     }
     const uint64_t cap = std::max<uint64_t>(1ull << 20, (uint64_t)d->n_qry * 1024);
     d->async_cap = cap;
-    CU(c->flags.ensure((size_t)d->n_qry * 4));
-    CU(c->counts.ensure((size_t)d->n_qry * 8));
-    CU(c->pos.ensure(((size_t)d->n_qry + 1) * 8));
-    CU(c->misc.ensure(16 + sizeof(SparseComp) * 256));
-    CU(c->ords2.ensure((size_t)d->n_qry * 4));
-    CU(c->keys.ensure(cap * sizeof(SparseHit)));
+    // per-job scratch (stream-ordered): misc | q_cnt u32[Q] | q_pos u64[Q] | q_out u64[Q+1] | over_list u32[Q] | hits[cap] | scan temp
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_misc = 0, o_cnt = up(16 + sizeof(SparseComp) * std::max(nc, 1)), o_pos = o_cnt + up((size_t)d->n_qry * 4),
+                 o_out = o_pos + up((size_t)d->n_qry * 8), o_over = o_out + up(((size_t)d->n_qry + 1) * 8), o_hits = o_over + up((size_t)d->n_qry * 4),
+                 o_tmp = o_hits + up(cap * sizeof(SparseHit));
     size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream);
-    CU(c->cubtmp.ensure(tmp));
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t *)nullptr, (uint64_t *)nullptr, d->n_qry, c->stream2);
+    const size_t total_b = o_tmp + up(tmp);
+    if (d->d_async) { cudaFreeAsync(d->d_async, c->stream); d->d_async = nullptr; }
+    CU(cudaMallocAsync(&d->d_async, total_b, c->stream));
+    uint8_t *mb = d->d_async + o_misc;
+    uint32_t *q_cnt = reinterpret_cast<uint32_t *>(d->d_async + o_cnt), *over_list = reinterpret_cast<uint32_t *>(d->d_async + o_over);
+    unsigned long long *q_pos = reinterpret_cast<unsigned long long *>(d->d_async + o_pos);
+    uint64_t *q_out = reinterpret_cast<uint64_t *>(d->d_async + o_out);
+    SparseHit *hits = reinterpret_cast<SparseHit *>(d->d_async + o_hits);
     if (d->d_rows) { cudaFreeAsync(d->d_rows, c->stream); d->d_rows = nullptr; }
     CU(cudaMallocAsync(&d->d_rows, cap * sizeof(StatRow), c->stream));
-    uint8_t *mb = c->misc.as<uint8_t>();
     if (nc) CU(cudaMemcpyAsync(mb + 16, d->comps.data(), sizeof(SparseComp) * nc, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(mb, 0, 16, c->stream));
     auto launch = [&](auto kern, int threads, int max_per_sm) -> int {
@@ -1989,8 +2035,8 @@ extern "C" int kssd_dist_stats_async(kssd_dist_t *d, const kssd_stat_opts_t *o)
         const int per_sm = std::max(1, std::min(max_per_sm, (int)((227u * 1024u) / (smem + 3400))));
         const uint32_t grid = (uint32_t)std::min<int>(d->n_qry, c->sm_count * per_sm);
         kern<<<grid, threads, smem, c->stream>>>(reinterpret_cast<const SparseComp *>(mb + 16), nc, (uint32_t)d->n_qry, (uint32_t)d->n_ref, cb, S, d->d_qsz,
-                                                 d->d_rsz, c->flags.as<uint32_t>(), c->counts.as<unsigned long long>(), reinterpret_cast<unsigned long long *>(mb),
-                                                 cap, c->keys.as<SparseHit>(), reinterpret_cast<uint32_t *>(mb + 8), c->ords2.as<uint32_t>(),
+                                                 d->d_rsz, q_cnt, q_pos, reinterpret_cast<unsigned long long *>(mb),
+                                                 cap, hits, reinterpret_cast<uint32_t *>(mb + 8), over_list,
                                                  reinterpret_cast<uint32_t *>(mb + 12));
         return KSSD_OK;
     };
@@ -2003,13 +2049,16 @@ extern "C" int kssd_dist_stats_async(kssd_dist_t *d, const kssd_stat_opts_t *o)
         else lrc = packed ? launch(dist_sparse_kernel<SparseWide, false, true>, 512, 2) : launch(dist_sparse_kernel<SparseWide, false, false>, 512, 2);
     }
     if (lrc) return lrc;
-    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->flags.as<uint32_t>(), c->pos.as<uint64_t>(), d->n_qry, c->stream));
-    stats_rows_sparse_dev_kernel<<<(uint32_t)((cap + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream>>>(
-        S, d->d_qsz, d->d_rsz, c->keys.as<SparseHit>(), reinterpret_cast<const unsigned long long *>(mb), cap, c->counts.as<unsigned long long>(),
-        c->pos.as<uint64_t>(), d->d_rows);
+    // the rows pass (print order by a scan of the per-query tallies, then one thread per hit) goes to the side stream: it is
+    // memory bound, the count kernel is latency bound, and the next search's count kernel starts right behind this one
+    CU(cudaEventRecord(d->counted, c->stream));
+    CU(cudaStreamWaitEvent(c->stream2, d->counted, 0));
+    CU(cub::DeviceScan::ExclusiveSum(d->d_async + o_tmp, tmp, q_cnt, q_out, d->n_qry, c->stream2));
+    stats_rows_sparse_dev_kernel<<<(uint32_t)((cap + kStatThreads - 1) / kStatThreads), kStatThreads, 0, c->stream2>>>(
+        S, d->d_qsz, d->d_rsz, hits, reinterpret_cast<const unsigned long long *>(mb), cap, q_pos, q_out, d->d_rows);
     LAUNCHED(4);
-    CU(cudaMemcpyAsync(d->h_async, mb, 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaEventRecord(d->done, c->stream));
+    CU(cudaMemcpyAsync(d->h_async, mb, 16, cudaMemcpyDeviceToHost, c->stream2));
+    CU(cudaEventRecord(d->done, c->stream2));
     d->async_pending = true;
     return KSSD_OK;
 }
@@ -2049,15 +2098,17 @@ extern "C" void kssd_dist_free(kssd_dist_t *d)
     if (!d) return;
     cudaSetDevice(d->ctx->device);
     cudaStream_t st = d->ctx->stream;
+    if (d->async_slot >= 0) {
+        if (d->async_pending) cudaEventSynchronize(d->done);   // the slot must not be reused while a copy into it is queued
+        cudaStreamWaitEvent(st, d->done, 0);                   // the rows pass ran on the side stream: the frees below come after it
+        d->ctx->async_free.push_back(d->async_slot);
+    }
     if (d->owns_ct && d->d_ct) cudaFreeAsync(d->d_ct, st);
     for (void *p : d->owned) cudaFreeAsync(p, st);
     cudaFreeAsync(d->d_qsz, st);
     d->h_rsz.reset();                                        // (d_rsz belongs to the context's cache of reference sets)
-    if (d->d_rows) cudaFreeAsync(d->d_rows, d->ctx->stream);
-    if (d->async_slot >= 0) {
-        if (d->async_pending) cudaEventSynchronize(d->done);   // the slot must not be reused while a copy into it is queued
-        d->ctx->async_free.push_back(d->async_slot);
-    }
+    if (d->d_rows) cudaFreeAsync(d->d_rows, st);
+    if (d->d_async) cudaFreeAsync(d->d_async, st);
     delete d;
 }
 

@@ -135,11 +135,83 @@ __global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__rest
     }
 }
 
+// ---- single-pass line index (decoupled look-back): ONE read of the text gives the position of every line end ----
+// The two passes above read the text twice (count, then fill) with a scan between them.  Here a block takes a ticket (so
+// that blocks start in text order), finds its line ends, publishes their number, adds up what the blocks before it
+// published (aggregates, or an inclusive prefix as soon as one is there) and writes its positions -- 32-bit offsets
+// from a0, which is all a file below 4 GiB needs.  state[b]: bits 62-63 = 0 nothing yet / 1 aggregate / 2 inclusive
+// prefix, low 32 bits = the count.  If the index does not fit `cap` entries the overflow flag is raised and the host
+// falls back to the two-pass index.
+constexpr unsigned long long kNlAgg = 1ull << 62, kNlPrefix = 2ull << 62;
+struct NlIndexOut { unsigned long long n_nl; uint32_t overflow; uint32_t ticket; };
+
+__global__ void __launch_bounds__(kNlBlock) nl_index_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0, uint32_t nblk,
+                                                             unsigned long long *__restrict__ state, NlIndexOut *__restrict__ out,
+                                                             uint32_t *__restrict__ nlpos32, uint32_t cap, uint32_t *__restrict__ any_overflow)
+{
+    __shared__ uint32_t s_blk, s_prefix, wsum[kNlBlock / 32];
+    if (threadIdx.x == 0) s_blk = atomicAdd(&out->ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_blk;
+    const uint64_t a = a0 + (uint64_t)b * kNlBytesPerBlock + (uint64_t)kNlBytesPerThread * threadIdx.x;
+    uint64_t m = line_mask64<false>(seq, a, gs, ge);
+    const uint32_t c = __popcll(m);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kNlBlock / 32; w++) { base += w < wid ? wsum[w] : 0u; total += wsum[w]; }
+    if (wid == 0) {
+        volatile unsigned long long *st = state;
+        if (lane == 0) { st[b] = (b == 0 ? kNlPrefix : kNlAgg) | total; __threadfence(); }
+        uint32_t excl = 0;
+        if (b > 0) {
+            int64_t j = (int64_t)b - 1;                      // lane l looks at block j - l
+            for (;;) {
+                const int64_t mine = j - lane;
+                unsigned long long v = kNlPrefix;            // before the first block: an empty prefix
+                if (mine >= 0) { do { v = st[mine]; } while ((v >> 62) == 0); }
+                const uint32_t pm = __ballot_sync(kFull, (v >> 62) == 2);
+                const uint32_t upto = pm ? (uint32_t)__ffs(pm) : 32u;             // lanes 0 .. upto-1 count (the first prefix included)
+                uint32_t val = lane < upto ? (uint32_t)v : 0u;
+                val = __reduce_add_sync(kFull, val);
+                excl += val;
+                if (pm) break;
+                j -= 32;
+            }
+            if (lane == 0) { __threadfence(); st[b] = kNlPrefix | (unsigned long long)(excl + total); }
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            if (b == nblk - 1) out->n_nl = (unsigned long long)excl + total;
+            if ((unsigned long long)excl + total > cap) { out->overflow = 1u; *any_overflow = 1u; }
+        }
+    }
+    __syncthreads();
+    uint32_t o = s_prefix + base + incl - c;
+    while (m) {
+        const int i = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (o < cap) nlpos32[o] = (uint32_t)(a + i - a0);
+        o++;
+    }
+}
+
 struct FastqArgs {
     const uint8_t *seq;
     uint64_t seq_bytes;          // readable bytes of the batch buffer
     uint64_t gs, ge;             // genome extent
     const uint64_t *nlpos;       // positions of the newline-terminated lines' '\n' (ascending)
+    const uint32_t *nlpos32;     // or (single-pass index): 32-bit offsets from pos_base, the counts read from *idx on the device
+    uint64_t pos_base;
+    const NlIndexOut *idx;
     uint64_t n_nl;               // newline-terminated lines
     uint64_t n_lines;            // n_nl + 1 if an unterminated tail line exists
     uint64_t n_records;          // ceil(n_lines / 4)
@@ -209,24 +281,32 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
     }
     __syncthreads();
     const int TL = P.TL;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.n_records; r += (uint64_t)gridDim.x * blockDim.x) {
+    // the line index: 64-bit positions and host-known counts (two-pass index), or 32-bit offsets with the counts left on
+    // the device by nl_index_kernel (no host round trip between the index and this walk)
+    const bool idx32 = A.nlpos32 != nullptr;
+    if (idx32 && A.idx->overflow) return;                                  // the host redoes this file with the two-pass index
+    const uint64_t n_nl = idx32 ? (uint64_t)A.idx->n_nl : A.n_nl;
+    const uint64_t n_lines = idx32 ? n_nl + (A.seq[A.ge - 1] != '\n' ? 1u : 0u) : A.n_lines;
+    const uint64_t n_records = idx32 ? (n_lines + 3) / 4 : A.n_records;
+    auto NLP = [&](uint64_t i) -> uint64_t { return idx32 ? A.pos_base + A.nlpos32[i] : A.nlpos[i]; };
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records; r += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t l_seq = 4 * r + 1, l_q = 4 * r + 3;
-        if (l_seq >= A.n_lines) continue;                                  // no sequence line at all
+        if (l_seq >= n_lines) continue;                                    // no sequence line at all
         bool process;
-        if (A.abund) process = 4 * r + 4 <= A.n_lines;                     // four lines exist (iseq2comem.c:567)
-        else process = (r == 0) || (4 * r + 4 <= A.n_nl);                  // read without touching EOF (:300-307)
+        if (A.abund) process = 4 * r + 4 <= n_lines;                       // four lines exist (iseq2comem.c:567)
+        else process = (r == 0) || (4 * r + 4 <= n_nl);                    // read without touching EOF (:300-307)
         if (!process) continue;
-        const uint64_t s0 = A.nlpos[l_seq - 1] + 1;                        // l_seq >= 1: previous line is terminated
-        const uint64_t s1 = l_seq < A.n_nl ? A.nlpos[l_seq] : A.ge;        // end of bases ('\n' position or text end)
+        const uint64_t s0 = NLP(l_seq - 1) + 1;                            // l_seq >= 1: previous line is terminated
+        const uint64_t s1 = l_seq < n_nl ? NLP(l_seq) : A.ge;              // end of bases ('\n' position or text end)
         uint64_t q0 = 0, qlen = 0;                                          // quality line incl. its '\n'
-        if (l_q < A.n_lines) {
-            q0 = A.nlpos[l_q - 1] + 1;
-            qlen = l_q < A.n_nl ? A.nlpos[l_q] + 1 - q0 : A.ge - q0;
+        if (l_q < n_lines) {
+            q0 = NLP(l_q - 1) + 1;
+            qlen = l_q < n_nl ? NLP(l_q) + 1 - q0 : A.ge - q0;
         }
         {   // every line of the record must fit the reference's fgets buffer, or its framing (and ours) is off
-            const uint64_t h0 = r == 0 ? A.gs : A.nlpos[4 * r - 1] + 1;
-            const uint64_t hlen = A.nlpos[4 * r] - h0;
-            const uint64_t plen = (l_seq + 1 < A.n_nl) ? A.nlpos[l_seq + 1] - (A.nlpos[l_seq] + 1) : 0;
+            const uint64_t h0 = r == 0 ? A.gs : NLP(4 * r - 1) + 1;
+            const uint64_t hlen = NLP(4 * r) - h0;
+            const uint64_t plen = (l_seq + 1 < n_nl) ? NLP(l_seq + 1) - (NLP(l_seq) + 1) : 0;
             if (s1 - s0 > A.line_cap || hlen > A.line_cap || plen > A.line_cap || qlen > (uint64_t)A.line_cap + 1) {
                 atomicOr(&A.gstatus[A.gid], 2);
                 continue;

@@ -143,3 +143,45 @@ def test_index_dist_match_reference_golden(gpu_ctx_l3k10):
         ref = g[f"distance_out.{tag}"].tobytes().decode()
         assert norm(mine) == norm(ref), tag
     job.close(); ix.close()
+
+
+def _tiny_reads_fastq(n: int, seed: int) -> np.ndarray:
+    """reads of 1 .. 6 bases with empty headers: ~3 bytes per line, so the single-pass line index outgrows its buffer
+    (one entry per 8 bytes of text) and the library has to fall back to the two-pass index"""
+    r = synth._stream(seed, 2 * n, salt=41)
+    parts = []
+    for i in range(n):
+        ln = 1 + int(r[2 * i] % np.uint64(6))
+        seq = bytes(b"ACGT"[int((r[2 * i + 1] >> np.uint64(2 * j)) & np.uint64(3))] for j in range(ln))
+        parts.append(b"@\n" + seq + b"\n+\n" + b"I" * ln + b"\n")
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+
+
+def test_fastq_line_index_paths_agree(ctx_l2k8, shuf_s5, oracle_mod, monkeypatch):
+    """single-pass line index (default), the two-pass index (KSSD_FASTQ_TWO_PASS) and the overflow fallback give the oracle's sets"""
+    files = _edge_files()
+    src = synth.random_bases(400_000, 311)
+    files["many_reads"] = synth.to_fastq(src, 12_000, 150, seed=312)               # > 100 blocks of the index: look-back across blocks
+    files["tiny_reads"] = _tiny_reads_fastq(30_000, 313)                           # index overflow -> two-pass fallback for the whole call
+    names = list(files)
+    orc = oracle_mod.Ctx(8, 5, 2, shuf_s5)
+    want = [np.sort(orc.fastq(files[n], 0, 1)[0]) for n in names]
+    for two_pass in (False, True):
+        if two_pass:
+            monkeypatch.setenv("KSSD_FASTQ_TWO_PASS", "1")
+        else:
+            monkeypatch.delenv("KSSD_FASTQ_TWO_PASS", raising=False)
+        sk = ctx_l2k8.sketch_fastq([files[n] for n in names], Q=0, M=1)
+        sets = sk.genome_sets()
+        for i, n in enumerate(names):
+            assert np.array_equal(sets[i][0], want[i]), (n, two_pass, len(sets[i][0]), len(want[i]))
+    # without the overflowing file the single-pass index serves every file
+    monkeypatch.delenv("KSSD_FASTQ_TWO_PASS", raising=False)
+    keep = [n for n in names if n != "tiny_reads"]
+    sk = ctx_l2k8.sketch_fastq([files[n] for n in keep], abundance=True)
+    for i, n in enumerate(keep):
+        ids, comp, ab = orc.fastq_abund(files[n])
+        o = np.argsort(ids, kind="stable")
+        lo, hi = int(sk.index[0][i]), int(sk.index[0][i + 1])
+        assert np.array_equal(sk.ids[0][lo:hi], ids[o]), n
+        assert np.array_equal(sk.abund[0][lo:hi], ab[o]), n
