@@ -458,15 +458,18 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
         if (ge == gs) continue;
         const uint64_t a0 = gs & ~15ull;
         if (single_pass && ge - a0 < 0xffffffffull) {
-            const uint64_t nblk = (ge - a0 + kNlBytesPerBlock - 1) / kNlBytesPerBlock;
+            const uint64_t nblk = (ge - a0 + kNlxBytesPerBlock - 1) / kNlxBytesPerBlock;
             const uint64_t lines_cap = std::max<uint64_t>((ge - a0) / 8, 4096);          // lines of 8 bytes on average: 10x the usual read
             CU(c->flags.ensure(nblk * 8 + 64));
             CU(c->minord.ensure(lines_cap * 4));
             unsigned long long *state = c->flags.as<unsigned long long>();
             NlIndexOut *io = reinterpret_cast<NlIndexOut *>(state + nblk);
             CU(cudaMemsetAsync(state, 0, nblk * 8 + sizeof(NlIndexOut), c->stream));
+            const bool dbg = getenv("KSSD_FASTQ_TIMING") != nullptr;      // per-kernel times of this path on stderr (profiles/fastq_scale.py)
+            if (dbg && getenv("KSSD_FASTQ_FLUSH")) { CU(c->keys2.ensure(256u << 20)); CU(cudaMemsetAsync(c->keys2.p, 1, 256u << 20, c->stream)); }
+            if (dbg) CU(cudaEventRecord(c->ev[2], c->stream));
             nl_index_kernel<<<(uint32_t)nblk, kNlBlock, 0, c->stream>>>(d_seq, gs, ge, a0, (uint32_t)nblk, state, io, c->minord.as<uint32_t>(), (uint32_t)lines_cap,
-                                                                          A.ticket);
+                                                                          A.ticket, dbg && getenv("KSSD_NLX_NOLB") ? 1 : 0);
             FastqArgs F{};
             F.seq = d_seq; F.seq_bytes = A.seq_bytes; F.gs = gs; F.ge = ge;
             F.nlpos32 = c->minord.as<uint32_t>(); F.pos_base = a0; F.idx = io;
@@ -476,8 +479,20 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
             F.line_cap = F.abund ? 4094u : 19998u;
             F.out_keys = A.out_keys; F.out_ords = A.out_ords; F.out_cap = A.out_cap; F.out_count = A.out_count; F.gstatus = A.gstatus;
             const uint64_t want = ((ge - gs) / 64 + kFastqThreads - 1) / kFastqThreads;   // records are not counted yet: >= 64 bytes each as a guess
+            if (dbg) CU(cudaEventRecord(c->ev[3], c->stream));
             sketch_fastq_kernel<<<(uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)c->sm_count), kFastqThreads, (kPfWords + kPf2Words) * 4, c->stream>>>(P, F);
             LAUNCHED(2);
+            if (dbg) {
+                cudaEvent_t e4;
+                CU(cudaEventCreate(&e4));
+                CU(cudaEventRecord(e4, c->stream));
+                CU(cudaEventSynchronize(e4));
+                float t_ix = 0, t_walk = 0;
+                cudaEventElapsedTime(&t_ix, c->ev[2], c->ev[3]);
+                cudaEventElapsedTime(&t_walk, c->ev[3], e4);
+                fprintf(stderr, "kssd fastq genome %d: line index %.3f ms, walk %.3f ms\n", g, t_ix, t_walk);
+                cudaEventDestroy(e4);
+            }
             continue;
         }
         const uint64_t nblk = (ge - a0 + kNlBytesPerBlock - 1) / kNlBytesPerBlock;

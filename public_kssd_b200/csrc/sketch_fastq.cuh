@@ -140,30 +140,71 @@ __global__ void __launch_bounds__(kNlBlock) nl_fill_kernel(const uint8_t *__rest
 // that blocks start in text order), finds its line ends, publishes their number, adds up what the blocks before it
 // published (aggregates, or an inclusive prefix as soon as one is there) and writes its positions -- 32-bit offsets
 // from a0, which is all a file below 4 GiB needs.  state[b]: bits 62-63 = 0 nothing yet / 1 aggregate / 2 inclusive
-// prefix, low 32 bits = the count.  If the index does not fit `cap` entries the overflow flag is raised and the host
+// prefix, low 32 bits = the count.  A block covers 128 KiB (512 bytes per thread in eight coalesced steps, the masks stay in registers
+// between the count and the write).  If the index does not fit `cap` entries the overflow flag is raised and the host
 // falls back to the two-pass index.
 constexpr unsigned long long kNlAgg = 1ull << 62, kNlPrefix = 2ull << 62;
-struct NlIndexOut { unsigned long long n_nl; uint32_t overflow; uint32_t ticket; };
+constexpr int kNlxPerThread = 512;                            // bytes per thread of the single-pass index: 8 masks of 64 bits
+constexpr int kNlxBytesPerBlock = kNlBlock * kNlxPerThread;   // 128 KiB per block: ~10^4 blocks per GB, so that a block's look-back
+                                                              // (one L2 round trip per 32 predecessors) keeps up with the text rate
+struct NlIndexOut { unsigned long long n_nl; uint32_t overflow, ticket, highbit, pad; };   // highbit: some byte of the file is >= 0x80
 
-__global__ void __launch_bounds__(kNlBlock) nl_index_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0, uint32_t nblk,
+__global__ void __launch_bounds__(kNlBlock, 4) nl_index_kernel(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t ge, uint64_t a0, uint32_t nblk,
                                                              unsigned long long *__restrict__ state, NlIndexOut *__restrict__ out,
-                                                             uint32_t *__restrict__ nlpos32, uint32_t cap, uint32_t *__restrict__ any_overflow)
+                                                             uint32_t *__restrict__ nlpos32, uint32_t cap, uint32_t *__restrict__ any_overflow, int dbg_no_lookback)
 {
     __shared__ uint32_t s_blk, s_prefix, wsum[kNlBlock / 32];
     if (threadIdx.x == 0) s_blk = atomicAdd(&out->ticket, 1u);
     __syncthreads();
     const uint32_t b = s_blk;
-    const uint64_t a = a0 + (uint64_t)b * kNlBytesPerBlock + (uint64_t)kNlBytesPerThread * threadIdx.x;
-    uint64_t m = line_mask64<false>(seq, a, gs, ge);
-    const uint32_t c = __popcll(m);
+    // a warp owns 16 contiguous KiB of the block's 128; in step k its lanes read 64 adjacent bytes each (2 KiB per warp and step,
+    // coalesced); line ends are numbered in text order: warp, then step, then lane
+    constexpr int kSteps = kNlxPerThread / 64;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = c;
+    const uint64_t a = a0 + (uint64_t)b * kNlxBytesPerBlock + (uint64_t)wid * (32 * kNlxPerThread) + 64ull * lane;
+    uint64_t m[kSteps];
+    uint32_t pre[kSteps];                                    // line ends of the warp before this lane's 64 bytes of step k
+    uint32_t wtot = 0;
+    const uint64_t blk0 = a0 + (uint64_t)b * kNlxBytesPerBlock;
+    uint32_t hb = 0;                                          // OR of every byte: a quality byte can only fail -Q <= 0 with its high bit set
+    if (blk0 >= gs && blk0 + kNlxBytesPerBlock <= ge) {       // a block inside the file: no guards, two steps of loads in flight at a time
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= (uint32_t)o) incl += t;
+        for (int k = 0; k < kSteps; k += 2) {
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = ldg_stream(reinterpret_cast<const uint4 *>(seq + a + 2048ull * (k + (j >> 2)) + 16ull * (j & 3)));
+#pragma unroll
+            for (int j = 0; j < 8; j++) hb |= v[j].x | v[j].y | v[j].z | v[j].w;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t m0 = eq_mask16(v[4 * h], 0x0a0a0a0au), m1 = eq_mask16(v[4 * h + 1], 0x0a0a0a0au);
+                const uint32_t m2 = eq_mask16(v[4 * h + 2], 0x0a0a0a0au), m3 = eq_mask16(v[4 * h + 3], 0x0a0a0a0au);
+                m[k + h] = (uint64_t)(m0 | (m1 << 16)) | ((uint64_t)(m2 | (m3 << 16)) << 32);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kSteps; k++) m[k] = line_mask64<false>(seq, a + 2048ull * k, gs, ge);
+        for (int k = 0; k < kSteps; k++)                      // (first and last block of a file only)
+            for (int j = 0; j < 64; j++) {
+                const uint64_t p = a + 2048ull * k + j;
+                if (p >= gs && p < ge) hb |= seq[p];
+            }
     }
-    if (lane == 31) wsum[wid] = incl;
+    if (__any_sync(kFull, (hb & 0x80808080u) != 0) && lane == 0) out->highbit = 1u;
+#pragma unroll
+    for (int k = 0; k < kSteps; k++) {
+        const uint32_t c = __popcll(m[k]);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        pre[k] = wtot + incl - c;
+        wtot += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) wsum[wid] = wtot;
     __syncthreads();
     uint32_t base = 0, total = 0;
 #pragma unroll
@@ -172,7 +213,7 @@ __global__ void __launch_bounds__(kNlBlock) nl_index_kernel(const uint8_t *__res
         volatile unsigned long long *st = state;
         if (lane == 0) { st[b] = (b == 0 ? kNlPrefix : kNlAgg) | total; __threadfence(); }
         uint32_t excl = 0;
-        if (b > 0) {
+        if (b > 0 && !dbg_no_lookback) {
             int64_t j = (int64_t)b - 1;                      // lane l looks at block j - l
             for (;;) {
                 const int64_t mine = j - lane;
@@ -195,12 +236,17 @@ __global__ void __launch_bounds__(kNlBlock) nl_index_kernel(const uint8_t *__res
         }
     }
     __syncthreads();
-    uint32_t o = s_prefix + base + incl - c;
-    while (m) {
-        const int i = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        if (o < cap) nlpos32[o] = (uint32_t)(a + i - a0);
-        o++;
+    const uint32_t o0 = s_prefix + base;
+#pragma unroll
+    for (int k = 0; k < kSteps; k++) {
+        uint64_t mk = m[k];
+        uint32_t o = o0 + pre[k];
+        while (mk) {
+            const int i = __ffsll((long long)mk) - 1;
+            mk &= mk - 1;
+            if (o < cap) nlpos32[o] = (uint32_t)(a + 2048ull * k + i - a0);
+            o++;
+        }
     }
 }
 
@@ -289,6 +335,9 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
     const uint64_t n_lines = idx32 ? n_nl + (A.seq[A.ge - 1] != '\n' ? 1u : 0u) : A.n_lines;
     const uint64_t n_records = idx32 ? (n_lines + 3) / 4 : A.n_records;
     auto NLP = [&](uint64_t i) -> uint64_t { return idx32 ? A.pos_base + A.nlpos32[i] : A.nlpos[i]; };
+    // -Q <= 0: a quality byte fails only with its high bit set; the single-pass index has looked at every byte of the file, and
+    // when none has it the quality lines are not read at all
+    const bool q_can_fail = A.Q > 0 || !idx32 || A.idx->highbit != 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records; r += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t l_seq = 4 * r + 1, l_q = 4 * r + 3;
         if (l_seq >= n_lines) continue;                                    // no sequence line at all
@@ -323,7 +372,7 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
             const uint64_t last16 = (A.seq_bytes - 1) & ~15ull;                       // last readable aligned chunk
             auto ld16 = [&](uint64_t addr) -> uint4 { return __ldg(reinterpret_cast<const uint4 *>(A.seq + (addr < last16 ? addr : last16))); };
             const uint64_t a0 = s0 & ~15ull;
-            const bool have_q = use_q && qlen > 0;
+            const bool have_q = use_q && qlen > 0 && q_can_fail;
             // quality bytes of the chunk at a: [q0 + (a - s0), +16) -- unaligned; the two aligned chunks covering it
             const uint64_t qa0 = have_q ? ((q0 - (s0 - a0)) & ~15ull) : 0;
             const uint32_t qsh = have_q ? (uint32_t)((q0 - (s0 - a0)) & 15) : 0;     // same for every chunk of the read

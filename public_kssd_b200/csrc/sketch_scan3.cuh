@@ -33,6 +33,7 @@
 // the general path for dirty iterations) is unchanged from sketch_scan.cuh; the general path here rolls its k-mer in
 // the same oldest-lowest representation so that it shares the filters and the resolver.
 #pragma once
+#include <type_traits>
 #include "sketch_scan32.cuh"
 
 namespace kssd {
@@ -216,16 +217,19 @@ __device__ __forceinline__ void queue_push3(const SketchParams &P, const ScanArg
     }
 }
 
-// Parked lanes first .. first+m-1, one per lane.  ST = 3: every block hit i (windows 3i-2 .. 3i) is settled by one read
-// of the block's table entry; ST = 1: the bitmap was exact, every hit is a member.  Members go to the candidate queue.
+// Parked lanes first .. first+m-1, one per lane; ONE block hit of every lane is settled per call.  ST = 3: block hit i
+// (windows 3i-2 .. 3i) by one read of the block's table entry; ST = 1: the bitmap was exact, the hit is a member.  Members go to
+// the candidate queue.  Lanes that still hold block hits (one in seven) are parked again, compacted at `first`, and meet the next
+// drain with every lane busy -- looping here until the last lane is done ran 2.4 rounds for 1.15 hits per lane.  Returns the new
+// number of parked lanes.
 #ifdef KSSD_DRAIN_NOINLINE
 #define KSSD_DRAIN_ATTR __noinline__
 #else
 #define KSSD_DRAIN_ATTR __forceinline__
 #endif
 template <int ST>
-__device__ KSSD_DRAIN_ATTR void drain3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, const LaneQ3 &lq, uint32_t first,
-                                       uint32_t m, uint32_t gid, uint64_t ord_base)
+__device__ KSSD_DRAIN_ATTR uint32_t drain3(const SketchParams &P, const ScanArgs &A, WarpQ3 &q, uint32_t &qn, LaneQ3 &lq, uint32_t first,
+                                           uint32_t m, uint32_t gid, uint64_t ord_base)
 {
     const uint32_t lane = lane_id();
     const uint32_t e = first + (lane < m ? lane : 0u);
@@ -233,64 +237,61 @@ __device__ KSSD_DRAIN_ATTR void drain3(const SketchParams &P, const ScanArgs &A,
     if (lane < m) { cand = lq.cand[e]; wm = lq.wmask[e]; F = lq.flags[e]; off = lq.off[e]; }
     if (ST == 1) cand &= wm;
     const uint32_t *ye = &lq.y[0][e];                     // word a of the entry: ye[a * kQueueCap]
-    // S(i) = the 16 bases from X position 3i-2 on (the three windows of block hit i start at its bases 2, 1, 0); the
-    // table entry of the NEXT hit is requested before the current one is looked at
+    // S(i) = the 16 bases from X position 3i-2 on (the three windows of block hit i start at its bases 2, 1, 0)
     auto span16 = [&](int i) -> uint32_t {
         const int o = 2 * (P.out + 3 * i) - 4;
         if (o < 0) return ye[0] << (-o);
         const uint32_t a = (uint32_t)o >> 5;
         return __funnelshift_r(ye[a * kQueueCap], a < 3 ? ye[(a + 1) * kQueueCap] : 0u, (uint32_t)o);
     };
+    uint32_t hits = 0;                                    // ST = 3: bit r <-> window 3i - r is a member
     int i = 0;
-    uint32_t S = 0;
-    unsigned long long mm = 0;
-    bool act = cand != 0;
-    if (act) {
+    if (cand) {
         i = __ffs(cand) - 1;
         cand &= cand - 1;
-        if (ST == 3) { S = span16(i); mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]); }
+        if (ST == 1) hits = 1u;
+        else {
+            const uint32_t S = span16(i);
+            const unsigned long long mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]);
+            const uint32_t m01 = (uint32_t)mm, m2 = (uint32_t)(mm >> 32);
+            uint32_t e0, e1, e2;                          // what each window holds outside the block, folded to 4 bits
+            if (P.s == 6) { e0 = (S >> 24) & 15u; e1 = ((S >> 2) & 3u) | ((S >> 22) & 12u); e2 = S & 15u; }
+            else { e0 = gtab_ext((S >> 4) & P.innermask, 0); e1 = gtab_ext((S >> 2) & P.innermask, 1); e2 = gtab_ext(S & P.innermask, 2); }
+            const int j0 = 3 * i;                         // windows j0, j0 - 1, j0 - 2 (own bases 0 .. 31 only)
+            const uint32_t okm = j0 < 32 ? (wm >> j0) & 1u : 0u;
+            const uint32_t ok1 = (j0 >= 1 && j0 < 33) ? (wm >> (j0 - 1)) & 1u : 0u;
+            const uint32_t ok2 = j0 >= 2 ? (wm >> (j0 - 2)) & 1u : 0u;
+            hits = (okm & (m01 >> e0)) | ((ok1 & (m01 >> (16 + e1))) << 1) | ((ok2 & (m2 >> e2)) << 2);
+        }
     }
-    while (__any_sync(kFull, act)) {
-        const bool act_n = cand != 0;
-        int i_n = 0;
-        uint32_t S_n = 0;
-        unsigned long long mm_n = 0;
-        if (act_n) {
-            i_n = __ffs(cand) - 1;
-            cand &= cand - 1;
-            if (ST == 3) { S_n = span16(i_n); mm_n = __ldg(&P.gtab[(S_n >> 4) & 0xfffffu]); }
+    while (__any_sync(kFull, hits != 0)) {
+        const bool has = hits != 0;
+        uint32_t j = 0;
+        uint64_t kmer = 0;
+        if (has) {
+            const int r = __ffs(hits) - 1;
+            hits &= hits - 1;
+            j = (uint32_t)(ST == 1 ? i : 3 * i - r);
+            const uint32_t a = (2u * j) >> 5;             // 0 or 1: the k-mer is Y bits [2j, 2j + 4k)
+            const uint32_t w0 = ye[a * kQueueCap], w1 = ye[(a + 1) * kQueueCap], w2 = ye[(a + 2) * kQueueCap];
+            kmer = ((((uint64_t)__funnelshift_r(w1, w2, 2u * j)) << 32) | __funnelshift_r(w0, w1, 2u * j)) & P.tupmask;
         }
-        uint32_t hits = 0;                                // ST = 3: bit r <-> window 3i - r is a member
-        if (act) {
-            if (ST == 1) hits = 1u;
-            else {
-                const uint32_t m01 = (uint32_t)mm, m2 = (uint32_t)(mm >> 32);
-                uint32_t e0, e1, e2;                      // what each window holds outside the block, folded to 4 bits
-                if (P.s == 6) { e0 = (S >> 24) & 15u; e1 = ((S >> 2) & 3u) | ((S >> 22) & 12u); e2 = S & 15u; }
-                else { e0 = gtab_ext((S >> 4) & P.innermask, 0); e1 = gtab_ext((S >> 2) & P.innermask, 1); e2 = gtab_ext(S & P.innermask, 2); }
-                const int j0 = 3 * i;                     // windows j0, j0 - 1, j0 - 2 (own bases 0 .. 31 only)
-                const uint32_t okm = j0 < 32 ? (wm >> j0) & 1u : 0u;
-                const uint32_t ok1 = (j0 >= 1 && j0 < 33) ? (wm >> (j0 - 1)) & 1u : 0u;
-                const uint32_t ok2 = j0 >= 2 ? (wm >> (j0 - 2)) & 1u : 0u;
-                hits = (okm & (m01 >> e0)) | ((ok1 & (m01 >> (16 + e1))) << 1) | ((ok2 & (m2 >> e2)) << 2);
-            }
-        }
-        while (__any_sync(kFull, hits != 0)) {
-            const bool has = hits != 0;
-            uint32_t j = 0;
-            uint64_t kmer = 0;
-            if (has) {
-                const int r = __ffs(hits) - 1;
-                hits &= hits - 1;
-                j = (uint32_t)(ST == 1 ? i : 3 * i - r);
-                const uint32_t a = (2u * j) >> 5;         // 0 or 1: the k-mer is Y bits [2j, 2j + 4k)
-                const uint32_t w0 = ye[a * kQueueCap], w1 = ye[(a + 1) * kQueueCap], w2 = ye[(a + 2) * kQueueCap];
-                kmer = ((((uint64_t)__funnelshift_r(w1, w2, 2u * j)) << 32) | __funnelshift_r(w0, w1, 2u * j)) & P.tupmask;
-            }
-            queue_push3(P, A, q, qn, has, kmer, ord_base + off, j, F, gid);
-        }
-        act = act_n; i = i_n; S = S_n; mm = mm_n;
+        queue_push3(P, A, q, qn, has, kmer, ord_base + off, j, F, gid);
     }
+    // lanes with block hits left: parked again, compacted at `first` (a lane only ever moves down: read, then write)
+    const uint32_t rem = __ballot_sync(kFull, cand != 0);
+    if (rem) {
+        uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+        if (cand) { y0 = ye[0]; y1 = ye[kQueueCap]; y2 = ye[2 * kQueueCap]; y3 = ye[3 * kQueueCap]; }
+        __syncwarp();
+        if (cand) {
+            const uint32_t d = first + __popc(rem & ((1u << lane) - 1u));
+            lq.y[0][d] = y0; lq.y[1][d] = y1; lq.y[2][d] = y2; lq.y[3][d] = y3;
+            lq.flags[d] = F; lq.wmask[d] = wm; lq.cand[d] = cand; lq.off[d] = off;
+        }
+        __syncwarp();
+    }
+    return first + __popc(rem);
 }
 
 // One 512-byte GENERAL iteration (16 bytes per lane): headers, N, IUPAC, anything -- exact per byte.  `cur` is already
@@ -485,7 +486,149 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     }
     bool at_eof = false;
 
+    // One CLEAN iteration from the three words of the classification on: squeeze, history, Y / X, the block probes, parking.
+    // FAST: a steady iteration with a saturated run and no header pending -- the bulk of every span -- where nothing of the
+    // span's edges applies (no masked halves for k >= 9, no cut lanes, no position filter, no run accounting).
+    auto clean_iter = [&](auto fast_tag, uint32_t it, uint32_t lane_off, uint32_t PA, uint32_t PB, uint32_t F, uint32_t n, uint32_t nA, bool steady,
+                          bool past_end) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        {
+            uint32_t fa = F & 0xffffu, fb = F >> 16;
+            if (!FAST || !BIG) {                             // (a steady lane with >= 2k-1 >= 17 bases has no half without one)
+                if (fa == 0xffffu) { fa = 0; PA = 0; }       // a half masked out whole (span start, genome end)
+                if (fb == 0xffffu) { fb = 0; PB = 0; }
+            }
+            for (;;) {      // squeeze the skipped bytes out of both halves; first round is branch-free
+                const uint32_t ia = fa & (0u - fa), ib = fb & (0u - fb);
+                const uint32_t la = ia * ia - 1u, lb = ib * ib - 1u;
+                PA = ((PA >> 2) & ~la) | (PA & la);
+                PB = ((PB >> 2) & ~lb) | (PB & lb);
+                fa = (fa ^ ia) >> 1;
+                fb = (fb ^ ib) >> 1;
+                if (!__any_sync(kFull, (fa | fb) != 0)) break;
+            }
+        }
+        // the lane's n bases, oldest lowest: PA | PB << 2 nA
+        const uint32_t Q0 = PA | __funnelshift_lc(0u, PB, 2 * nA), Q1 = __funnelshift_lc(PB, 0u, 2 * nA);
+        // what the next lane needs of them: the last 2k-1, again oldest lowest
+        uint32_t S0, S1;
+        {
+            const int d = 2 * ((int)n - (TL - 1));
+            if (FAST || steady || d >= 0) {
+                if (BIG) { S0 = __funnelshift_rc(Q0, Q1, d); S1 = __funnelshift_rc(Q1, 0u, d); }      // d <= 32
+                else { S0 = (uint32_t)((((uint64_t)Q1 << 32) | Q0) >> d); S1 = 0u; }                  // d <= 62, 2k-1 <= 15 bases left
+            } else {                                                                                  // a cut lane with fewer bases: they end at group 2k-2
+                const uint64_t s = (((uint64_t)Q1 << 32) | Q0) << (-d);
+                S0 = (uint32_t)s; S1 = (uint32_t)(s >> 32);
+            }
+        }
+        uint32_t H0 = __shfl_up_sync(kFull, S0, 1), H1 = BIG ? __shfl_up_sync(kFull, S1, 1) : 0u;
+        if (lane == 0) { H0 = cw0; H1 = cw1; }
+        // Y = history | own bases << 2(2k-1): the k-mer that ends at own base j is Y bits [2j, 2j + 4k)
+        uint32_t Y0, Y1, Y2, Y3;
+        if (BIG) {
+            Y0 = H0;
+            Y1 = H1 | (Q0 << hsh);
+            Y2 = __funnelshift_l(Q0, Q1, hsh);
+            Y3 = __funnelshift_lc(Q1, 0u, hsh);
+        } else {
+            Y0 = H0 | (Q0 << hsh);
+            Y1 = __funnelshift_l(Q0, Q1, hsh);
+            Y2 = __funnelshift_lc(Q1, 0u, hsh);
+            Y3 = 0u;
+        }
+        // X = Y >> 2 out: the central 2s-mer of that k-mer is X bits [2j, 2j + 4s)
+        const uint32_t X0 = __funnelshift_r(Y0, Y1, 2 * P.out), X1 = __funnelshift_r(Y1, Y2, 2 * P.out), X2 = __funnelshift_r(Y2, Y3, 2 * P.out);
+        auto xsh = [&](int k) -> uint32_t {      // X >> k for a constant k in [-2, 95]
+            return k < 0 ? (X0 << (-k)) : (k < 32 ? __funnelshift_r(X0, X1, k) : (k < 64 ? __funnelshift_r(X1, X2, k - 32) : (X2 >> (k - 64))));
+        };
+        uint32_t cand = 0;
+#pragma unroll
+        for (int i = NPROBE - 1; i >= 0; i--) {
+            const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (xsh(2 * ST * i - 2) & 0x1fffcu));
+            cand = __funnelshift_l(__funnelshift_l(0u, word, xsh(2 * ST * i + 15)), cand, 1);      // cand = cand << 1 | flag
+        }
+
+        uint32_t wm = low_mask((int)n);                          // windows (own bases) the stream position allows
+        if (!FAST && (since_break < kRunCap || past_end)) {
+            const uint32_t N = __reduce_add_sync(kFull, n);
+            if (since_break < (uint32_t)(TL - 1) || past_end) {
+                // start of a span / run-out past its end: filter by position inside the iteration
+                uint32_t incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= (uint32_t)o) incl += t;
+                }
+                const int o_l = (int)(incl - n);                     // bases before this lane
+                const int need = TL - 1 - (int)since_break - o_l;    // own base j ends a k-mer of this span iff j >= need
+                if (need > 0) wm &= ~low_mask(min(need, 32));
+                if (past_end) {
+                    uint32_t E;                                      // bases of this iteration before `end`
+                    const uint32_t after_end = sc.after_end;
+                    const int64_t rel = (int64_t)sc.end - (int64_t)(sc.chunk0 + ((uint64_t)it << 10));
+                    if (rel <= 0) E = 0;
+                    else {
+                        const int le = (int)(rel >> 5), be = (int)(rel & 31);      // bytes [0, be) of lane `le` lie before `end`
+                        E = __shfl_sync(kFull, (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(F & low_mask(be)), le);
+                    }
+                    // the k-mer's first base lies before `end` iff after_end + (o_l + j - E + 1) <= 2k-1
+                    const int keep = TL - 1 - (int)after_end + (int)E - o_l;      // j < keep
+                    if (keep < 32) wm &= low_mask(max(keep, 0));
+                    __syncwarp();
+                    if (lane == 0) sc.after_end = after_end + N - E;
+                    __syncwarp();
+                }
+            }
+            since_break = min(since_break + N, kRunCap);
+        }
+        cw0 = __shfl_sync(kFull, S0, 31);
+        if (BIG) cw1 = __shfl_sync(kFull, S1, 31);
+        const uint32_t hit = __ballot_sync(kFull, cand != 0);
+        if (hit) {
+            uint32_t ln = sc.ln;                                  // parked lanes of this warp (cold state: shared memory)
+            if (cand) {
+                const uint32_t i = ln + __popc(hit & ((1u << lane) - 1u));
+                lq.y[0][i] = Y0; lq.y[1][i] = Y1; lq.y[2][i] = Y2; lq.y[3][i] = Y3;
+                lq.flags[i] = F; lq.wmask[i] = wm; lq.cand[i] = cand; lq.off[i] = lane_off;
+            }
+            ln += __popc(hit);
+            __syncwarp();
+            if (ln >= 32) {
+                uint32_t qn = sc.qn;                              // candidates waiting in the warp's queue (cold state too)
+                do ln = drain3<ST>(P, A, q, qn, lq, ln - 32, 32, sc.gid, sc.chunk0 - sc.gs); while (ln >= 32);
+                if (lane == 0) sc.qn = qn;
+            }
+            if (lane == 0) sc.ln = ln;
+            __syncwarp();
+        }
+    };
+
     for (uint32_t it = 0;; it++) {
+#ifndef KSSD_SCAN_TMA
+        // ---- fast loop: steady iterations 1 .. n_steady-1 with a saturated run and no header pending.  A dirty iteration leaves
+        // the loop with its text still in `cur` and goes through the general iteration below as it is.
+        if (it - 1u < n_steady - 1u && n_steady && since_break >= kRunCap && !hdr) {
+            for (;;) {
+                uint32_t dacc = 0, PA, PB, F;
+                {
+                    uint32_t c0, c1, c2, c3, c4, c5, c6, c7, g0, g1, g2, g3;
+                    classify_lazy8(cur.lo.x, cur.lo.y, dacc, c0, c1, g0);
+                    classify_lazy8(cur.lo.z, cur.lo.w, dacc, c2, c3, g1);
+                    classify_lazy8(cur.hi.x, cur.hi.y, dacc, c4, c5, g2);
+                    classify_lazy8(cur.hi.z, cur.hi.w, dacc, c6, c7, g3);
+                    F = top_bytes4(g0, g1, g2, g3);
+                    PA = top_bytes4(c0, c1, c2, c3);
+                    PB = top_bytes4(c4, c5, c6, c7);
+                }
+                const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
+                if (!__all_sync(kFull, dacc == 0 && n >= (uint32_t)(TL - 1))) break;
+                cur = ldg_stream256(A.seq + sc.chunk0 + ((uint64_t)(it + 1) << 10) + 32 * lane);
+                clean_iter(std::true_type{}, it, (it << 10) + 32 * lane, PA, PB, F, n, nA, true, false);
+                if (++it >= n_steady) break;                      // the last steady iteration loads its successor guarded: below
+            }
+        }
+#endif
         const bool steady = (it - 1u) < n_steady;
         const uint32_t lane_off = (it << 10) + 32 * lane;
 
@@ -538,115 +681,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         const bool clean = __all_sync(kFull, lane_ok) && !hdr;
 
         if (clean) {
-            {
-                uint32_t fa = F & 0xffffu, fb = F >> 16;
-                if (fa == 0xffffu) { fa = 0; PA = 0; }           // a half masked out whole (span start, genome end)
-                if (fb == 0xffffu) { fb = 0; PB = 0; }
-                for (;;) {      // squeeze the skipped bytes out of both halves; first round is branch-free
-                    const uint32_t ia = fa & (0u - fa), ib = fb & (0u - fb);
-                    const uint32_t la = ia * ia - 1u, lb = ib * ib - 1u;
-                    PA = ((PA >> 2) & ~la) | (PA & la);
-                    PB = ((PB >> 2) & ~lb) | (PB & lb);
-                    fa = (fa ^ ia) >> 1;
-                    fb = (fb ^ ib) >> 1;
-                    if (!__any_sync(kFull, (fa | fb) != 0)) break;
-                }
-            }
-            // the lane's n bases, oldest lowest: PA | PB << 2 nA
-            const uint32_t Q0 = PA | __funnelshift_lc(0u, PB, 2 * nA), Q1 = __funnelshift_lc(PB, 0u, 2 * nA);
-            // what the next lane needs of them: the last 2k-1, again oldest lowest
-            uint32_t S0, S1;
-            {
-                const int d = 2 * ((int)n - (TL - 1));
-                if (steady || d >= 0) {
-                    if (BIG) { S0 = __funnelshift_rc(Q0, Q1, d); S1 = __funnelshift_rc(Q1, 0u, d); }      // d <= 32
-                    else { S0 = (uint32_t)((((uint64_t)Q1 << 32) | Q0) >> d); S1 = 0u; }                  // d <= 62, 2k-1 <= 15 bases left
-                } else {                                                                                  // a cut lane with fewer bases: they end at group 2k-2
-                    const uint64_t s = (((uint64_t)Q1 << 32) | Q0) << (-d);
-                    S0 = (uint32_t)s; S1 = (uint32_t)(s >> 32);
-                }
-            }
-            uint32_t H0 = __shfl_up_sync(kFull, S0, 1), H1 = BIG ? __shfl_up_sync(kFull, S1, 1) : 0u;
-            if (lane == 0) { H0 = cw0; H1 = cw1; }
-            // Y = history | own bases << 2(2k-1): the k-mer that ends at own base j is Y bits [2j, 2j + 4k)
-            uint32_t Y0, Y1, Y2, Y3;
-            if (BIG) {
-                Y0 = H0;
-                Y1 = H1 | (Q0 << hsh);
-                Y2 = __funnelshift_l(Q0, Q1, hsh);
-                Y3 = __funnelshift_lc(Q1, 0u, hsh);
-            } else {
-                Y0 = H0 | (Q0 << hsh);
-                Y1 = __funnelshift_l(Q0, Q1, hsh);
-                Y2 = __funnelshift_lc(Q1, 0u, hsh);
-                Y3 = 0u;
-            }
-            // X = Y >> 2 out: the central 2s-mer of that k-mer is X bits [2j, 2j + 4s)
-            const uint32_t X0 = __funnelshift_r(Y0, Y1, 2 * P.out), X1 = __funnelshift_r(Y1, Y2, 2 * P.out), X2 = __funnelshift_r(Y2, Y3, 2 * P.out);
-            auto xsh = [&](int k) -> uint32_t {      // X >> k for a constant k in [-2, 95]
-                return k < 0 ? (X0 << (-k)) : (k < 32 ? __funnelshift_r(X0, X1, k) : (k < 64 ? __funnelshift_r(X1, X2, k - 32) : (X2 >> (k - 64))));
-            };
-            uint32_t cand = 0;
-#pragma unroll
-            for (int i = NPROBE - 1; i >= 0; i--) {
-                const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(pf) + (xsh(2 * ST * i - 2) & 0x1fffcu));
-                cand = __funnelshift_l(__funnelshift_l(0u, word, xsh(2 * ST * i + 15)), cand, 1);      // cand = cand << 1 | flag
-            }
-
-            uint32_t wm = low_mask((int)n);                          // windows (own bases) the stream position allows
-            if (since_break < kRunCap || past_end) {
-                const uint32_t N = __reduce_add_sync(kFull, n);
-                if (since_break < (uint32_t)(TL - 1) || past_end) {
-                    // start of a span / run-out past its end: filter by position inside the iteration
-                    uint32_t incl = n;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                        if (lane >= (uint32_t)o) incl += t;
-                    }
-                    const int o_l = (int)(incl - n);                     // bases before this lane
-                    const int need = TL - 1 - (int)since_break - o_l;    // own base j ends a k-mer of this span iff j >= need
-                    if (need > 0) wm &= ~low_mask(min(need, 32));
-                    if (past_end) {
-                        uint32_t E;                                      // bases of this iteration before `end`
-                        const uint32_t after_end = sc.after_end;
-                        const int64_t rel = (int64_t)sc.end - (int64_t)(sc.chunk0 + ((uint64_t)it << 10));
-                        if (rel <= 0) E = 0;
-                        else {
-                            const int le = (int)(rel >> 5), be = (int)(rel & 31);      // bytes [0, be) of lane `le` lie before `end`
-                            E = __shfl_sync(kFull, (uint32_t)o_l + (uint32_t)be - (uint32_t)__popc(F & low_mask(be)), le);
-                        }
-                        // the k-mer's first base lies before `end` iff after_end + (o_l + j - E + 1) <= 2k-1
-                        const int keep = TL - 1 - (int)after_end + (int)E - o_l;      // j < keep
-                        if (keep < 32) wm &= low_mask(max(keep, 0));
-                        __syncwarp();
-                        if (lane == 0) sc.after_end = after_end + N - E;
-                        __syncwarp();
-                    }
-                }
-                since_break = min(since_break + N, kRunCap);
-            }
-            cw0 = __shfl_sync(kFull, S0, 31);
-            if (BIG) cw1 = __shfl_sync(kFull, S1, 31);
-            const uint32_t hit = __ballot_sync(kFull, cand != 0);
-            if (hit) {
-                uint32_t ln = sc.ln;                                  // parked lanes of this warp (cold state: shared memory)
-                if (cand) {
-                    const uint32_t i = ln + __popc(hit & ((1u << lane) - 1u));
-                    lq.y[0][i] = Y0; lq.y[1][i] = Y1; lq.y[2][i] = Y2; lq.y[3][i] = Y3;
-                    lq.flags[i] = F; lq.wmask[i] = wm; lq.cand[i] = cand; lq.off[i] = lane_off;
-                }
-                ln += __popc(hit);
-                __syncwarp();
-                if (ln >= 32) {
-                    uint32_t qn = sc.qn;                              // candidates waiting in the warp's queue (cold state too)
-                    drain3<ST>(P, A, q, qn, lq, ln - 32, 32, sc.gid, sc.chunk0 - sc.gs);
-                    if (lane == 0) sc.qn = qn;
-                    ln -= 32;
-                }
-                if (lane == 0) sc.ln = ln;
-                __syncwarp();
-            }
+            clean_iter(std::false_type{}, it, lane_off, PA, PB, F, n, nA, steady, past_end);
         } else {
             // two general 512-byte iterations with a 16-byte lane mapping (reloaded: L2 hits); the carry changes
             // representation on the way in and out
@@ -682,10 +717,13 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         }
     }
     {
-        const uint32_t ln = sc.ln;
+        uint32_t ln = sc.ln;
         if (ln) {
             uint32_t qn = sc.qn;
-            drain3<ST>(P, A, q, qn, lq, 0, ln, sc.gid, sc.chunk0 - sc.gs);
+            while (ln) {                                              // one block hit per parked lane and pass
+                const uint32_t m = ln < 32u ? ln : 32u;
+                ln = drain3<ST>(P, A, q, qn, lq, ln - m, m, sc.gid, sc.chunk0 - sc.gs);
+            }
             __syncwarp();
             if (lane == 0) sc.qn = qn;
             __syncwarp();

@@ -163,6 +163,8 @@ def test_fastq_line_index_paths_agree(ctx_l2k8, shuf_s5, oracle_mod, monkeypatch
     src = synth.random_bases(400_000, 311)
     files["many_reads"] = synth.to_fastq(src, 12_000, 150, seed=312)               # > 100 blocks of the index: look-back across blocks
     files["tiny_reads"] = _tiny_reads_fastq(30_000, 313)                           # index overflow -> two-pass fallback for the whole call
+    hb = synth.to_fastq(src, 3_000, 120, seed=314).tobytes().replace(b"<", b"\xbc")   # quality bytes with the high bit set: negative as
+    files["highbit_qual"] = np.frombuffer(hb, dtype=np.uint8)                      # signed char, they fail -Q 0 (the walk must read the quality lines)
     names = list(files)
     orc = oracle_mod.Ctx(8, 5, 2, shuf_s5)
     want = [np.sort(orc.fastq(files[n], 0, 1)[0]) for n in names]
@@ -178,6 +180,10 @@ def test_fastq_line_index_paths_agree(ctx_l2k8, shuf_s5, oracle_mod, monkeypatch
     # without the overflowing file the single-pass index serves every file
     monkeypatch.delenv("KSSD_FASTQ_TWO_PASS", raising=False)
     keep = [n for n in names if n != "tiny_reads"]
+    sk = ctx_l2k8.sketch_fastq([files[n] for n in keep], Q=0, M=1)
+    sets = sk.genome_sets()
+    for i, n in enumerate(keep):
+        assert np.array_equal(sets[i][0], want[names.index(n)]), n
     sk = ctx_l2k8.sketch_fastq([files[n] for n in keep], abundance=True)
     for i, n in enumerate(keep):
         ids, comp, ab = orc.fastq_abund(files[n])
