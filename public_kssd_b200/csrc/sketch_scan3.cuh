@@ -461,11 +461,12 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
     // stream state in registers; packed into a StreamState only around the out-of-line general iterations
     uint32_t cw0 = 0, cw1 = 0;                                   // the last 2k-1 bases of the stream, oldest lowest
     uint32_t since_break = 0, hdr = 0;
+    uint32_t ln = 0;                                             // parked lanes of this warp
     uint32_t n_steady;
     Bytes32 cur;
     {
         const uint64_t start = sc.start, end = sc.end, ge = sc.ge, chunk0 = start & ~127ull;
-        if (lane == 0) { sc.chunk0 = chunk0; sc.after_end = 0; sc.ln = 0; }
+        if (lane == 0) { sc.chunk0 = chunk0; sc.after_end = 0; }
         __syncwarp();
         // iterations 1 .. n_steady are "steady": wholly inside [start, min(end, ge)) -- no masking, no run-out logic
         const uint64_t lim = end < ge ? end : ge;
@@ -586,8 +587,14 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         if (BIG) cw1 = __shfl_sync(kFull, S1, 31);
         const uint32_t hit = __ballot_sync(kFull, cand != 0);
         if (hit) {
-            uint32_t ln = sc.ln;                                  // parked lanes of this warp (cold state: shared memory)
             if (cand) {
+#ifdef KSSD_SCAN_GTAB_PF
+                if (ST == 3 && FAST) {      // the table entry of the lane's first block hit: asked into L1 now, read by the drain an iteration or three later
+                    const uint32_t sh = 6u * (uint32_t)(__ffs(cand) - 1), a = sh >> 5;
+                    const uint32_t lo = a == 0 ? X0 : (a == 1 ? X1 : X2), hi = a == 0 ? X1 : (a == 1 ? X2 : 0u);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(P.gtab + (__funnelshift_r(lo, hi, sh) & 0xfffffu)));
+                }
+#endif
                 const uint32_t i = ln + __popc(hit & ((1u << lane) - 1u));
                 lq.y[0][i] = Y0; lq.y[1][i] = Y1; lq.y[2][i] = Y2; lq.y[3][i] = Y3;
                 lq.flags[i] = F; lq.wmask[i] = wm; lq.cand[i] = cand; lq.off[i] = lane_off;
@@ -598,9 +605,8 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 uint32_t qn = sc.qn;                              // candidates waiting in the warp's queue (cold state too)
                 do ln = drain3<ST>(P, A, q, qn, lq, ln - 32, 32, sc.gid, sc.chunk0 - sc.gs); while (ln >= 32);
                 if (lane == 0) sc.qn = qn;
+                __syncwarp();
             }
-            if (lane == 0) sc.ln = ln;
-            __syncwarp();
         }
     };
 
@@ -609,6 +615,7 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         // ---- fast loop: steady iterations 1 .. n_steady-1 with a saturated run and no header pending.  A dirty iteration leaves
         // the loop with its text still in `cur` and goes through the general iteration below as it is.
         if (it - 1u < n_steady - 1u && n_steady && since_break >= kRunCap && !hdr) {
+            const uint8_t *np = A.seq + sc.chunk0 + ((uint64_t)(it + 1) << 10) + 32 * lane;      // the lane's text of the next iteration
             for (;;) {
                 uint32_t dacc = 0, PA, PB, F;
                 {
@@ -623,7 +630,16 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
                 }
                 const uint32_t nA = 16 - __popc(F & 0xffffu), n = 32 - __popc(F);
                 if (!__all_sync(kFull, dacc == 0 && n >= (uint32_t)(TL - 1))) break;
-                cur = ldg_stream256(A.seq + sc.chunk0 + ((uint64_t)(it + 1) << 10) + 32 * lane);
+                cur = ldg_stream256(np);
+                np += 1024;
+#ifndef KSSD_SCAN_NO_L2PF
+                // an iteration takes ~1 us, about what a DRAM access takes under load: the text of the iteration after next is
+                // asked into L2 now (no register, no shared memory), so that the load above finds it there
+#ifndef KSSD_SCAN_PFDIST
+#define KSSD_SCAN_PFDIST 1
+#endif
+                if (it + 2 + KSSD_SCAN_PFDIST <= n_steady) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + 1024 * KSSD_SCAN_PFDIST));
+#endif
                 clean_iter(std::true_type{}, it, (it << 10) + 32 * lane, PA, PB, F, n, nA, true, false);
                 if (++it >= n_steady) break;                      // the last steady iteration loads its successor guarded: below
             }
@@ -717,7 +733,6 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
         }
     }
     {
-        uint32_t ln = sc.ln;
         if (ln) {
             uint32_t qn = sc.qn;
             while (ln) {                                              // one block hit per parked lane and pass
@@ -733,7 +748,12 @@ __device__ void scan_span3(const SketchParams &P, const ScanArgs &A, const uint3
 }
 
 template <int ST, bool BIG>
-__global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(const __grid_constant__ SketchParams P, const __grid_constant__ ScanArgs A, const uint32_t *__restrict__ pf_global)
+#ifdef KSSD_SCAN_MAXNREG
+__global__ void __maxnreg__(KSSD_SCAN_MAXNREG) sketch_fasta3_kernel(
+#else
+__global__ void __launch_bounds__(kScanThreads, 1) sketch_fasta3_kernel(
+#endif
+    const __grid_constant__ SketchParams P, const __grid_constant__ ScanArgs A, const uint32_t *__restrict__ pf_global)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
