@@ -233,26 +233,44 @@ __device__ KSSD_DRAIN_ATTR uint32_t drain3(const SketchParams &P, const ScanArgs
 {
     const uint32_t lane = lane_id();
     const uint32_t e = first + (lane < m ? lane : 0u);
-    uint32_t cand = 0, wm = 0, F = 0, off = 0;
-    if (lane < m) { cand = lq.cand[e]; wm = lq.wmask[e]; F = lq.flags[e]; off = lq.off[e]; }
+    uint32_t cand = 0, wm = 0, F = 0, off = 0, y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    if (lane < m) {
+        cand = lq.cand[e]; wm = lq.wmask[e]; F = lq.flags[e]; off = lq.off[e];
+        y0 = lq.y[0][e]; y1 = lq.y[1][e]; y2 = lq.y[2][e]; y3 = lq.y[3][e];
+    }
     if (ST == 1) cand &= wm;
-    const uint32_t *ye = &lq.y[0][e];                     // word a of the entry: ye[a * kQueueCap]
-    // S(i) = the 16 bases from X position 3i-2 on (the three windows of block hit i start at its bases 2, 1, 0)
-    auto span16 = [&](int i) -> uint32_t {
-        const int o = 2 * (P.out + 3 * i) - 4;
-        if (o < 0) return ye[0] << (-o);
-        const uint32_t a = (uint32_t)o >> 5;
-        return __funnelshift_r(ye[a * kQueueCap], a < 3 ? ye[(a + 1) * kQueueCap] : 0u, (uint32_t)o);
-    };
-    uint32_t hits = 0;                                    // ST = 3: bit r <-> window 3i - r is a member
+    auto yw = [&](uint32_t a) -> uint32_t { return a == 0 ? y0 : (a == 1 ? y1 : (a == 2 ? y2 : (a == 3 ? y3 : 0u))); };
+    // the lane's block hit i: S = the 16 bases from X position 3i-2 on (the three windows of the hit start at its bases 2, 1, 0);
+    // its table entry is requested first, the re-parking below runs under the read's latency
     int i = 0;
-    if (cand) {
+    uint32_t S = 0;
+    unsigned long long mm = 0;
+    const bool act = cand != 0;
+    if (act) {
         i = __ffs(cand) - 1;
         cand &= cand - 1;
+        if (ST == 3) {
+            const int o = 2 * (P.out + 3 * i) - 4;
+            if (o < 0) S = y0 << (-o);
+            else { const uint32_t a = (uint32_t)o >> 5; S = __funnelshift_r(yw(a), yw(a + 1), (uint32_t)o); }
+            mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]);
+        }
+    }
+    // lanes with block hits left: parked again, compacted at `first` (every lane holds its entry in registers by now)
+    const uint32_t rem = __ballot_sync(kFull, cand != 0);
+    if (rem) {
+        __syncwarp();                                     // (every lane's reads of its entry are done before a slot is rewritten)
+        if (cand) {
+            const uint32_t d = first + __popc(rem & ((1u << lane) - 1u));
+            lq.y[0][d] = y0; lq.y[1][d] = y1; lq.y[2][d] = y2; lq.y[3][d] = y3;
+            lq.flags[d] = F; lq.wmask[d] = wm; lq.cand[d] = cand; lq.off[d] = off;
+        }
+        __syncwarp();
+    }
+    uint32_t hits = 0;                                    // ST = 3: bit r <-> window 3i - r is a member
+    if (act) {
         if (ST == 1) hits = 1u;
         else {
-            const uint32_t S = span16(i);
-            const unsigned long long mm = __ldg(&P.gtab[(S >> 4) & 0xfffffu]);
             const uint32_t m01 = (uint32_t)mm, m2 = (uint32_t)(mm >> 32);
             uint32_t e0, e1, e2;                          // what each window holds outside the block, folded to 4 bits
             if (P.s == 6) { e0 = (S >> 24) & 15u; e1 = ((S >> 2) & 3u) | ((S >> 22) & 12u); e2 = S & 15u; }
@@ -273,23 +291,10 @@ __device__ KSSD_DRAIN_ATTR uint32_t drain3(const SketchParams &P, const ScanArgs
             hits &= hits - 1;
             j = (uint32_t)(ST == 1 ? i : 3 * i - r);
             const uint32_t a = (2u * j) >> 5;             // 0 or 1: the k-mer is Y bits [2j, 2j + 4k)
-            const uint32_t w0 = ye[a * kQueueCap], w1 = ye[(a + 1) * kQueueCap], w2 = ye[(a + 2) * kQueueCap];
+            const uint32_t w0 = a ? y1 : y0, w1 = a ? y2 : y1, w2 = a ? y3 : y2;
             kmer = ((((uint64_t)__funnelshift_r(w1, w2, 2u * j)) << 32) | __funnelshift_r(w0, w1, 2u * j)) & P.tupmask;
         }
         queue_push3(P, A, q, qn, has, kmer, ord_base + off, j, F, gid);
-    }
-    // lanes with block hits left: parked again, compacted at `first` (a lane only ever moves down: read, then write)
-    const uint32_t rem = __ballot_sync(kFull, cand != 0);
-    if (rem) {
-        uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
-        if (cand) { y0 = ye[0]; y1 = ye[kQueueCap]; y2 = ye[2 * kQueueCap]; y3 = ye[3 * kQueueCap]; }
-        __syncwarp();
-        if (cand) {
-            const uint32_t d = first + __popc(rem & ((1u << lane) - 1u));
-            lq.y[0][d] = y0; lq.y[1][d] = y1; lq.y[2][d] = y2; lq.y[3][d] = y3;
-            lq.flags[d] = F; lq.wmask[d] = wm; lq.cand[d] = cand; lq.off[d] = off;
-        }
-        __syncwarp();
     }
     return first + __popc(rem);
 }
