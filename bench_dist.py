@@ -309,6 +309,49 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
         ok = torch.tensor([1 if out.get("content_ok", True) else 0], device=dev, dtype=torch.int64)
         dist.broadcast(ok, 0)
 
+    # ---- Stage I -> Stage II exchange at this size (SURVEY.md s8e "Index: one exchange step"): every rank starts with the sketches of
+    # ITS genome block, as Stage I leaves them; one all-to-all of (code, gid) pairs routes every code to the rank that owns its
+    # code range, and the rank indexes what it received.  Not on the main line above (which replicates the index), but what a
+    # reference set beyond one GPU's memory would do.
+    if world > 1:
+        try:
+            g = parallel.genome_shard(n_ref, world, rank)
+            a, bnd = int(ref_index_host[g.start]), int(ref_index_host[g.stop])
+            loc_c = t_rc[a:bnd].contiguous()
+            loc_i = (t_ri[g.start:g.stop + 1] - t_ri[g.start]).contiguous()
+            ex_ms, ix_ms2, got_n = [], [], 0
+            for it in range(3):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                xc, xi = parallel.exchange_codes_by_range(loc_c, loc_i, g.start, n_ref, world, rank, code_bits=28, device=dev)
+                e1.record()
+                torch.cuda.synchronize()
+                xix = ctx.combco2mco_dev(xc.data_ptr(), xi.data_ptr(), n_ref, int(xc.numel()))
+                ix_ms2.append(ctx.last_ms(2))
+                xix.close()
+                barrier()
+                ex_ms.append(e0.elapsed_time(e1))
+                got_n = int(xc.numel())
+            lo_c, hi_c = parallel.code_range(rank, world, 28)
+            want_n = int(((t_rc >= lo_c) & (t_rc < hi_c)).sum().item())                      # codes of ALL genomes in this rank's range
+            # (sum of code * (gid + 1)) mod 2^63 of what arrived == the same sum over the whole reference filtered to the range
+            gid_all = torch.repeat_interleave(torch.arange(n_ref, device=dev, dtype=torch.int64), (t_ri[1:] - t_ri[:-1]))
+            keep = (t_rc >= lo_c) & (t_rc < hi_c)
+            want_sum = int((t_rc[keep].to(torch.int64) * (gid_all[keep] + 1)).sum().item())
+            gid_got = torch.repeat_interleave(torch.arange(n_ref, device=dev, dtype=torch.int64), (xi[1:] - xi[:-1]))
+            got_sum = int((xc.to(torch.int64) * (gid_got + 1)).sum().item())
+            tt = torch.tensor([min(ex_ms[1:]), min(ix_ms2[1:]), 1.0 if (got_n == want_n and got_sum == want_sum) else 0.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt[:2], op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt[2:], op=dist.ReduceOp.MIN)
+            out["exchange"] = {"ms": float(tt[0].item()), "index_ms_per_rank_after": float(tt[1].item()), "postings": n_codes,
+                               "bytes_sent_per_rank": int(8 * (bnd - a) * (world - 1) // world), "content_ok": bool(tt[2].item() == 1.0),
+                               "note": "exchange_codes_by_range: sketches sharded by genome -> (code, gid) pairs routed by code range with one NCCL all-to-all (8 B per "
+                                       "posting), max over ranks; content = count and a (code, gid) checksum of what each rank received against the whole reference "
+                                       "filtered to its range"}
+        except Exception as ex:
+            out["exchange"] = {"failed": str(ex)}
+
     # ---- the baselines at N > 1, one batch: index by CODE range + NCCL reduce-scatter of dense partial matrices (north
     # star), and the same placement with the count kernel adding into the owner's rows over peer memory
     if world > 1 and baselines:

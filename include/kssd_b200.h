@@ -288,6 +288,13 @@ void kssd_host_free(void *p);
 int kssd_set_union_host(kssd_ctx_t *ctx, const uint32_t *combco, uint64_t n_codes, int uniq, uint32_t *pan_out, uint64_t *n_out);
 int kssd_set_union_dev(kssd_ctx_t *ctx, const uint32_t *combco_dev, uint64_t n_codes, int uniq, uint32_t *pan_dev,
                        uint64_t pan_cap, uint64_t *n_out);
+/* kssd set -g <grouping file> (grouping_genomes, command_set.c:698-790): the pan sketch of every group of genomes.
+ * member_gids[group_index[g] .. group_index[g+1]) are the genomes of group g in the order the reference walks them (hostfmt.organize_taxf
+ * replays its taxon table).  Out: per group the DISTINCT codes of its members in the order of their first occurrence -- what the slot
+ * layout of the reference's per-group hash table depends on (hostfmt.group_slot_order turns it into the bytes of combco.<c>) -- and
+ * index_out[n_groups + 1].  codes_out holds up to the sum of the members' sketch sizes. */
+int kssd_set_group_host(kssd_ctx_t *ctx, const uint32_t *combco, const uint64_t *index, int n_genomes, const uint32_t *member_gids,
+                        const uint64_t *group_index, int n_groups, uint32_t *codes_out, uint64_t *index_out);
 int kssd_set_operate_host(kssd_ctx_t *ctx, const uint32_t *combco, const uint64_t *index, int n_genomes,
                           const uint32_t *pan, uint64_t n_pan, int intersect, uint32_t *combco_out, uint64_t *index_out);
 int kssd_set_operate_dev(kssd_ctx_t *ctx, const uint32_t *combco_dev, const uint64_t *index_dev, int n_genomes,

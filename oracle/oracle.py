@@ -276,6 +276,39 @@ def set_operate(combco: np.ndarray, index: np.ndarray, pan: np.ndarray, intersec
     return out[:int(oix[-1])].copy(), oix
 
 
+_PRIMER = (251, 509, 1021, 2039, 4093, 8191, 16381, 32749, 65521, 131071, 262139, 524287, 1048573, 2097143, 4194301, 8388593, 16777213,
+           33554393, 67108859, 134217689, 268435399, 536870909, 1073741789, 2147483647, 4294967291)
+
+
+def set_group(combco: np.ndarray, index: np.ndarray, groups):
+    """kssd set -g for one component (grouping_genomes, command_set.c:726-775): for every group (list of genome ids, in the
+    reference's order) every code of every member is inserted into an open-addressing table of primer[LOG2(1.5 * codes) - 7]
+    slots (0 = empty, so code 0 is lost); the table's non-empty slots are written in slot order.  Returns (combco, index)."""
+    codes = np.asarray(combco, dtype=np.uint32)
+    ix = np.asarray(index, dtype=np.uint64)
+    out, oix = [], [0]
+    for gids in groups:
+        hashsize = int(sum(int(ix[g + 1] - ix[g]) for g in gids))
+        x15 = int(hashsize * 1.5)
+        ind = x15.bit_length() - 1 if x15 > 0 else 0
+        H = _PRIMER[ind - 7] if ind > 7 else _PRIMER[0]
+        table = {}
+        for g in gids:
+            for key in codes[int(ix[g]):int(ix[g + 1])].tolist():
+                h1, h2 = key % H, 1 + key % (H - 1)
+                for x in range(H):
+                    y = ((h1 + ((x * h2) & 0xFFFFFFFF)) & 0xFFFFFFFF) % H
+                    if table.get(y, 0) == 0:
+                        table[y] = key
+                        break
+                    if table[y] == key:
+                        break
+        row = [table[k] for k in sorted(table) if table[k] != 0]
+        out.extend(row)
+        oix.append(len(out))
+    return np.array(out, dtype=np.uint32), np.array(oix, dtype=np.uint64)
+
+
 def composite(ref_codes, ref_index, qry_codes, qry_index, qry_abund, min_kmers: int = 6):
     """get_species_abundance (command_composite.c:389-547), numbers only.  Arguments are per-component lists (combco.<c>,
     combco.index.<c>, combco.<c>.a).  For every query, the references that share >= MIN_KM_S (6) k-mers with it, most

@@ -29,7 +29,7 @@ SYMBOLS = [
     "kssd_dist_counts_dev", "kssd_dist_create_sparse", "kssd_dist_sparse_add_dev", "kssd_dist_sparse_add_host", "kssd_dist_accumulate_peer", "kssd_dev_alloc", "kssd_dev_zero", "kssd_dev_free",
     "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_stats_async", "kssd_dist_stats_wait", "kssd_dist_fetch_stats", "kssd_dist_free",
     "kssd_format_distance_rows", "kssd_host_free",
-    "kssd_set_union_host", "kssd_set_union_dev", "kssd_set_operate_host", "kssd_set_operate_dev",
+    "kssd_set_union_host", "kssd_set_union_dev", "kssd_set_operate_host", "kssd_set_operate_dev", "kssd_set_group_host",
     "kssd_composite_host",
 ]
 
@@ -166,6 +166,7 @@ def lib() -> C.CDLL:
     L.kssd_set_union_dev.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, C.c_uint64, u64p]
     L.kssd_set_operate_host.argtypes = [vp, u32p, u64p, C.c_int, u32p, C.c_uint64, C.c_int, u32p, u64p]
     L.kssd_set_operate_dev.argtypes = [vp, vp, vp, C.c_int, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp]
+    L.kssd_set_group_host.argtypes = [vp, u32p, u64p, C.c_int, u32p, u64p, C.c_int, u32p, u64p]
     L.kssd_composite_host.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int,
                                       C.POINTER(vp), u64p]
     L.kssd_host_free.argtypes = [vp]

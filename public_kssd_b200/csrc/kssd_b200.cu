@@ -14,6 +14,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/kssd_b200.h"
@@ -2308,6 +2309,81 @@ extern "C" int kssd_set_operate_dev(kssd_ctx_t *c, const uint32_t *combco_dev, c
     LAUNCHED(6);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
+    return KSSD_OK;
+}
+
+extern "C" int kssd_set_group_host(kssd_ctx_t *c, const uint32_t *combco, const uint64_t *index, int n_genomes, const uint32_t *member_gids,
+                                   const uint64_t *group_index, int n_groups, uint32_t *codes_out, uint64_t *index_out)
+{
+    if (!c || !index || !group_index || !index_out || n_genomes < 0 || n_groups < 0) return fail(KSSD_E_INVAL, "kssd_set_group_host: bad argument");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n_codes = index[n_genomes], M = group_index[n_groups];
+    if (M && !member_gids) return fail(KSSD_E_INVAL, "kssd_set_group_host: null member list");
+    if (M >= 0xffffffffull) return fail(KSSD_E_INVAL, "kssd_set_group_host: too many group members");
+    // where every member's codes come from and go to (group-major, members in the given order)
+    std::vector<uint64_t> m_src(M + 1, 0), m_dst(M + 1, 0);
+    std::vector<uint32_t> m_group(std::max<uint64_t>(M, 1), 0);
+    for (int g = 0; g < n_groups; g++) {
+        if (group_index[g + 1] < group_index[g]) return fail(KSSD_E_INVAL, "kssd_set_group_host: group index not ascending");
+        for (uint64_t m = group_index[g]; m < group_index[g + 1]; m++) {
+            const uint32_t gid = member_gids[m];
+            if (gid >= (uint32_t)n_genomes) return fail(KSSD_E_INVAL, "kssd_set_group_host: member %u of group %d is not a genome of the sketch (%d genomes)", gid, g, n_genomes);
+            if (index[gid + 1] < index[gid] || index[gid + 1] > n_codes) return fail(KSSD_E_INVAL, "kssd_set_group_host: combco index not ascending");
+            m_src[m] = index[gid];
+            m_dst[m + 1] = m_dst[m] + (index[gid + 1] - index[gid]);
+            m_group[m] = (uint32_t)g;
+        }
+    }
+    const uint64_t T = m_dst[M];
+    if (T >= 0xffffffffull) return fail(KSSD_E_INVAL, "kssd_set_group_host: more than 2^32 member codes in one component");
+    for (int g = 0; g <= n_groups; g++) index_out[g] = 0;
+    if (T == 0) return KSSD_OK;
+    if (!combco || !codes_out) return fail(KSSD_E_INVAL, "kssd_set_group_host: null code buffer");
+    StreamScratch scr(c->stream);
+    bool ok = true;
+    auto galloc = [&](auto *&ptr, size_t bytes) -> bool { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(scr.alloc(bytes)); return ptr != nullptr; };
+    uint32_t *d_combco = nullptr, *d_mgroup = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_flags = nullptr, *d_excl = nullptr, *d_hpos = nullptr,
+             *d_hcode = nullptr, *d_hpos2 = nullptr, *d_hcode2 = nullptr;
+    uint64_t *d_msrc = nullptr, *d_mdst = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    if (!(ok &= galloc(d_combco, n_codes * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_msrc, (M + 1) * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_mdst, (M + 1) * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_mgroup, M * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
+    if (!(ok &= galloc(d_keys, T * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_keys2, T * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_pos, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_pos2, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
+    if (!(ok &= galloc(d_flags, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_excl, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
+    CU(cudaMemcpyAsync(d_combco, combco, n_codes * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_msrc, m_src.data(), (M + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_mdst, m_dst.data(), (M + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_mgroup, m_group.data(), M * 4, cudaMemcpyHostToDevice, c->stream));
+    group_gather_kernel<<<(uint32_t)((M * 32 + 255) / 256), 256, 0, c->stream>>>(d_combco, d_msrc, d_mdst, d_mgroup, (uint32_t)M, d_keys, d_pos);
+    int gbits = 1;
+    while ((1ll << gbits) < n_groups) gbits++;
+    size_t tmp = 0, tmp2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_keys, d_keys2, d_pos, d_pos2, T, 0, 32 + gbits, c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_flags, d_excl, T, c->stream);
+    CU(c->cubtmp.ensure(std::max(tmp, tmp2)));
+    CU(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, d_keys, d_keys2, d_pos, d_pos2, T, 0, 32 + gbits, c->stream));      // stable: the earliest position leads its run
+    const uint32_t nb = (uint32_t)((T + 255) / 256);
+    group_heads_kernel<<<nb, 256, 0, c->stream>>>(d_keys2, T, d_flags);
+    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp2, d_flags, d_excl, T, c->stream));
+    uint32_t last_e = 0, last_f = 0;
+    CU(cudaMemcpyAsync(&last_e, d_excl + (T - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&last_f, d_flags + (T - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t U = (uint64_t)last_e + last_f;                           // distinct (group, code) pairs
+    if (!(ok &= galloc(d_hpos, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_hcode, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_hpos2, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_hcode2, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
+    group_compact_kernel<<<nb, 256, 0, c->stream>>>(d_keys2, d_pos2, d_flags, d_excl, T, d_hpos, d_hcode);
+    tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_hpos, d_hpos2, d_hcode, d_hcode2, U, 0, 32, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(c->cubtmp.p, tmp, d_hpos, d_hpos2, d_hcode, d_hcode2, U, 0, 32, c->stream));          // back to the order of first occurrence
+    LAUNCHED(12);
+    std::vector<uint32_t> hpos(U);
+    CU(cudaMemcpyAsync(hpos.data(), d_hpos2, U * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(codes_out, d_hcode2, U * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    for (int g = 0; g <= n_groups; g++)                                      // a group's codes sit where its members' positions do
+        index_out[g] = (uint64_t)(std::lower_bound(hpos.begin(), hpos.end(), (uint32_t)std::min<uint64_t>(m_dst[group_index[g]], 0xffffffffull)) - hpos.begin());
+    index_out[n_groups] = U;
     return KSSD_OK;
 }
 

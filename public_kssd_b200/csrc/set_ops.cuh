@@ -105,4 +105,34 @@ __global__ void set_index_kernel(const uint64_t *__restrict__ index, int n_genom
     out_index[g] = i < n ? pos[i] : (n ? (uint64_t)pos[n - 1] + flags[n - 1] : 0ull);
 }
 
+
+// ---- kssd set -g (grouping_genomes, reference command_set.c:698-790): the sketches of a group's member genomes, walked in the
+// order the reference inserts them into the group's hash table; what the table ends up holding is the DISTINCT codes, and the
+// order they were first met is all its slot layout depends on.  Here: member m's codes go to positions m_dst[m] .. of one
+// group-major sequence as (group << 32 | code) keys with their position as the value; a stable radix sort groups equal
+// (group, code) pairs with the earliest position first, the run heads are kept and sorted back by position.
+__global__ void group_gather_kernel(const uint32_t *__restrict__ combco, const uint64_t *__restrict__ m_src, const uint64_t *__restrict__ m_dst,
+                                    const uint32_t *__restrict__ m_group, uint32_t n_members, unsigned long long *__restrict__ keys, uint32_t *__restrict__ pos)
+{
+    const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (m >= n_members) return;
+    const uint64_t s = m_src[m], d = m_dst[m], n = m_dst[m + 1] - d;
+    const unsigned long long g = (unsigned long long)m_group[m] << 32;
+    for (uint64_t i = lane; i < n; i += 32) { keys[d + i] = g | combco[s + i]; pos[d + i] = (uint32_t)(d + i); }
+}
+
+__global__ void group_heads_kernel(const unsigned long long *__restrict__ keys, uint64_t n, uint32_t *__restrict__ flags)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// heads only: (first position, code), compacted
+__global__ void group_compact_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ flags,
+                                     const uint32_t *__restrict__ excl, uint64_t n, uint32_t *__restrict__ h_pos, uint32_t *__restrict__ h_code)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) { h_pos[excl[i]] = pos[i]; h_code[excl[i]] = (uint32_t)keys[i]; }
+}
+
 }  // namespace kssd

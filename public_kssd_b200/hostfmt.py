@@ -222,3 +222,84 @@ def combine_queries(dirs, out) -> dict:
         f.write(np.ascontiguousarray(ct, dtype="<u4").tobytes())
         f.write(_names_block(names))
     return read_cofiles_stat(out)
+
+
+# ---- kssd set -g / -c: the host-only parts (grouping file, hash-slot order of a group's pan sketch, pan concatenation) ----
+PRIMER = (251, 509, 1021, 2039, 4093, 8191, 16381, 32749, 65521, 131071, 262139, 524287, 1048573, 2097143, 4194301, 8388593, 16777213,
+          33554393, 67108859, 134217689, 268435399, 536870909, 1073741789, 2147483647, 4294967291)      # global_basic.c:74
+
+
+def _next_prime(n: int) -> int:
+    """global_basic.c:389 (trial division up to (int)sqrt(n))."""
+    while True:
+        if all(n % j for j in range(2, int(np.sqrt(n)) + 1)):
+            return n
+        n += 1
+
+
+def organize_taxf(text: str):
+    """The reference's grouping file (organize_taxf, command_set.c:536-600): line i = "<taxid>[\t<taxname>]" for genome i.  Returns the
+    groups in the order the reference walks them -- the slot order of its taxon hash table (double hashing on the taxid, table size
+    nextPrime(lines / 0.6)) -- as dicts(taxid, taxname, gids); taxid 0 marks genomes that belong to no group (still listed: callers skip them)."""
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    ln = len(lines)
+    hs = _next_prime(int(ln / 0.6))
+    table = {}
+    for i, line in enumerate(lines):
+        parts = [p for p in line.split("\t") if p != ""]          # strtok skips empty fields
+        taxid = int(parts[0]) if parts else 0                       # (atoi of a number)
+        taxname = parts[1] if len(parts) > 1 else None
+        for n in range(hs):
+            hv = (taxid % hs + n * (1 + taxid % (hs - 1))) % hs
+            if hv not in table:
+                table[hv] = {"taxid": taxid, "taxname": taxname, "gids": [i]}
+                break
+            if table[hv]["taxid"] == taxid:
+                if table[hv]["taxname"] != taxname:
+                    raise ValueError(f"organize_taxf: taxid {taxid} has different taxnames in lines {table[hv]['gids'][0]} and {i}")
+                table[hv]["gids"].append(i)
+                break
+    return [table[k] for k in sorted(table)], ln
+
+
+def group_hashsize(n_member_codes: int) -> int:
+    """size of a group's hash table in grouping_genomes (command_set.c:735-737): primer[LOG2(codes * 1.5) - 7] (codes with repeats)."""
+    x = int(n_member_codes * 1.5)
+    ind = x.bit_length() - 1 if x > 0 else 0
+    return PRIMER[ind - 7] if ind > 7 else PRIMER[0]
+
+
+def group_slot_order(codes_first_occurrence: np.ndarray, n_member_codes: int) -> np.ndarray:
+    """A group's distinct codes in first-occurrence order (Context.set_group) -> the order grouping_genomes writes them: the slots of
+    its open-addressing table (HASH = (K % H + x (1 + K % (H - 1))) % H with 32-bit unsigned arithmetic, command_set.c:738-752).  A
+    code equal to 0 is the table's empty marker and is never written."""
+    H = group_hashsize(n_member_codes)
+    table = {}
+    for key in np.asarray(codes_first_occurrence, dtype=np.uint32).tolist():
+        if key == 0:
+            continue
+        h1, h2 = key % H, 1 + key % (H - 1)
+        for x in range(H):
+            y = ((h1 + ((x * h2) & 0xFFFFFFFF)) & 0xFFFFFFFF) % H
+            if y not in table:
+                table[y] = key
+                break
+            if table[y] == key:
+                break
+    return np.array([table[k] for k in sorted(table)], dtype=np.uint32)
+
+
+def group_names(groups) -> list:
+    """names grouping_genomes writes to cofiles.stat: "<taxid>_<taxname>" or "<taxid>" (command_set.c:794-799)."""
+    return [f"{g['taxid']}_{g['taxname']}" if g["taxname"] is not None else str(g["taxid"]) for g in groups if g["taxid"] != 0]
+
+
+def combine_pans(pans_per_input) -> tuple:
+    """`kssd set -c` (combin_pans, command_set.c:444-512) for one component: the pan.<c> / uniq_pan.<c> arrays of the inputs
+    concatenated into one combco.<c> with its combco.index.<c>; host-only in the reference too."""
+    arrs = [np.ascontiguousarray(p, dtype=np.uint32) for p in pans_per_input]
+    index = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    index[1:] = np.cumsum([a.size for a in arrs])
+    return (np.concatenate(arrs) if arrs else np.zeros(0, np.uint32)), index

@@ -270,6 +270,22 @@ class Context:
                                           int(intersect), ptr(out, C.c_uint32), ptr(oix, C.c_uint64)))
         return out[:int(oix[-1])].copy(), oix
 
+    def set_group(self, combco: np.ndarray, index: np.ndarray, groups: Sequence[Sequence[int]]):
+        """`kssd set -g <grouping file>` for one component (grouping_genomes): per group of genome ids the DISTINCT codes of its
+        members in the order of their first occurrence (members walked in the given order).  Returns (codes, index[n_groups + 1]);
+        hostfmt.group_slot_order turns a group's codes into the order the reference writes them."""
+        a = np.ascontiguousarray(combco, dtype=np.uint32)
+        ix = np.ascontiguousarray(index, dtype=np.uint64)
+        members = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.uint32) for g in groups]) if len(groups) else np.zeros(0, np.uint32))
+        gix = np.zeros(len(groups) + 1, dtype=np.uint64)
+        gix[1:] = np.cumsum([len(g) for g in groups])
+        total = int(sum(int(ix[int(g) + 1] - ix[int(g)]) for g in members)) if members.size and members.max(initial=0) < ix.size - 1 else a.size
+        out = np.empty(max(total, 1), dtype=np.uint32)
+        oix = np.empty(len(groups) + 1, dtype=np.uint64)
+        check(lib().kssd_set_group_host(self._h, ptr(a, C.c_uint32), ptr(ix, C.c_uint64), ix.size - 1, ptr(members, C.c_uint32), ptr(gix, C.c_uint64),
+                                        len(groups), ptr(out, C.c_uint32), ptr(oix, C.c_uint64)))
+        return out[:int(oix[-1])].copy(), oix
+
     # ---------------- kssd composite ----------------
     def composite(self, ref_indexes, qry_codes, qry_index, qry_abund, min_kmers: int = 0) -> np.ndarray:
         """`kssd composite -r <refs> -q <-A queries>` (get_species_abundance): per-component lists of the reference

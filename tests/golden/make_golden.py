@@ -265,3 +265,43 @@ def composite_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "composite":
     composite_golden()
+
+
+def setgroup_golden():
+    """`kssd set -g <grouping file>` (grouping_genomes): pan sketch per group of genomes, L3K10 and L3K11 (16 components)."""
+    O.build()
+    t6 = synth.make_shuf_table(6, cases.SHUF_SEED_S6)
+    fa = cases.fasta_inputs()
+    tax_lines = ["101\tcladeA", "202\tcladeB", "202\tcladeB", "0", "101\tcladeA", "7"]
+    for tag, (k, s, L) in {"setgroup_l3k10": (10, 6, 3), "setgroup_l3k11": (11, 6, 3)}.items():
+        rr = O.RefRun(k, s, L, t6, shuf_id=cases.SHUF_ID)
+        d = rr.dir / "in"
+        d.mkdir()
+        for n in ("g_dup", "h_anc", "i_mut1", "j_mut5", "a_plain80", "d_messy"):
+            (d / f"{n}.fasta").write_bytes(fa[n].tobytes())
+        sk = rr.sketch(d, "sk", p=1)
+        st = O.read_cofiles_stat(sk)
+        comp = st["comp_num"]
+        assert len(st["names"]) == len(tax_lines)
+        tax = rr.dir / "groups.tsv"
+        tax.write_text("\n".join(tax_lines) + "\n")
+        out = rr.dir / "set_g"
+        r = O.run_ref(["set", "-g", tax, "-o", out, sk], cwd=rr.dir)
+        assert r.returncode == 0, r.stderr
+        ost = O.read_cofiles_stat(out)
+        pack = {"comp_num": np.int32(comp), "names": np.array([Path(n).name.rsplit(".", 1)[0] for n in st["names"]]), "tax": np.array(tax_lines),
+                "g.ctx_ct": ost["ctx_ct"], "g.all_ctx_ct": np.uint64(ost["all_ctx_ct"]), "g.names": np.array([str(n) for n in ost["names"]]),
+                "g.infile_num": np.int32(len(ost["names"]))}
+        for c in range(comp):
+            codes, ix, _ = O.read_combco(sk, c)
+            pack[f"in.{c}"] = codes
+            pack[f"in.index.{c}"] = ix
+            pack[f"g.{c}"] = np.fromfile(out / f"combco.{c}", dtype="<u4")
+            pack[f"g.index.{c}"] = np.fromfile(out / f"combco.index.{c}", dtype="<u8")
+        np.savez_compressed(OUT / f"{tag}.npz", **pack)
+        print(tag, "components", comp, "groups", len(ost["names"]), "group codes", sum(len(pack[f'g.{c}']) for c in range(comp)), list(pack["g.names"]))
+        rr.cleanup()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "setgroup":
+    setgroup_golden()

@@ -262,3 +262,27 @@ def test_slot_order_replay_matches_reference(oracle_mod, tables):
     ctx = oracle_mod.Ctx(k, s, L, tab)
     replay = hostfmt.slot_order(ids, occ, ctx.hashsize)
     assert np.array_equal(replay, g["f_short_lines.0"])
+
+
+@pytest.mark.parametrize("tag", ["setgroup_l3k10", "setgroup_l3k11"])
+def test_set_grouping_oracle_matches_reference_golden(oracle_mod, tag):
+    """kssd set -g: the oracle's restatement of grouping_genomes and the grouping-file replay (hostfmt.organize_taxf) against the
+    files the unmodified reference wrote."""
+    from public_kssd_b200 import hostfmt
+    g = np.load(GOLD / f"{tag}.npz", allow_pickle=False)
+    groups_all, n_lines = hostfmt.organize_taxf("\n".join(str(t) for t in g["tax"]) + "\n")
+    groups = [x["gids"] for x in groups_all if x["taxid"] != 0]
+    assert hostfmt.group_names(groups_all) == [str(n) for n in g["g.names"]]
+    total = 0
+    for c in range(int(g["comp_num"])):
+        codes, ix = oracle_mod.set_group(g[f"in.{c}"], g[f"in.index.{c}"], groups)
+        assert np.array_equal(codes, g[f"g.{c}"]) and np.array_equal(ix, g[f"g.index.{c}"]), (tag, c)
+        total += codes.size
+    assert total == int(g["g.all_ctx_ct"])
+
+
+def test_combine_pans_is_concatenation():
+    from public_kssd_b200 import hostfmt
+    a, b = np.array([3, 9, 12], np.uint32), np.array([], np.uint32)
+    codes, ix = hostfmt.combine_pans([a, b, a[:1]])
+    assert codes.tolist() == [3, 9, 12, 3] and ix.tolist() == [0, 3, 3, 4]
