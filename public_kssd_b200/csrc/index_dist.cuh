@@ -19,6 +19,36 @@ __global__ void mark_genome_starts_kernel(const uint64_t *__restrict__ index, in
     if (a < b) gid[a] = (uint32_t)j;
 }
 
+// The same in one pass and without the scan: a warp takes 1024 consecutive posting positions, finds the genome of the first one by a
+// binary search of the (L2-resident) index and walks on from there; every lane also checks its codes against the component's code
+// space (a code beyond it has no place in the index: flag, KSSD_E_INVAL).  4 B read + 4 B written per posting.
+__global__ void tag_gids_kernel(const uint64_t *__restrict__ index, int n_genomes, uint64_t n, const uint32_t *__restrict__ codes, uint64_t space,
+                                uint32_t *__restrict__ gid, uint32_t *__restrict__ flag)
+{
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base = w << 10;
+    if (base >= n) return;
+    uint32_t lo = 0, hi = (uint32_t)n_genomes;                // index[lo] <= base < index[hi] for a well-formed index
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (index[mid] <= base) lo = mid; else hi = mid;
+    }
+    uint32_t g = lo;
+    bool bad = false;
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) {
+        const uint64_t i = base + 32u * j + lane;
+        if (i >= n) break;
+        while (g + 1 < (uint32_t)n_genomes && index[g + 1] <= i) g++;
+        gid[i] = g;
+        bad |= codes[i] >= space;
+    }
+    if (bad) atomicOr(flag, 1u);
+}
+
+// run heads -> CSR by head flags + scan + scatter: three passes; kept for components beyond 2^31 postings (the run-length encode that
+// replaced it counts with an int)
 __global__ void head_flags_kernel(const uint32_t *__restrict__ codes, uint64_t n, uint32_t *__restrict__ flags)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

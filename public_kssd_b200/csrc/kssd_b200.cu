@@ -1183,7 +1183,26 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
     // d_sorted_codes: n_postings codes ascending (scratch), ix->d_gids already in (code, gid) order
     const uint64_t n = ix->n_postings;
     uint32_t nuniq = 0;
-    if (n) {
+    size_t rle_tmp = 0;
+    const bool big = n >= 0x7fffffffull;
+    if (n && !big) {
+        // unique codes and their run lengths in ONE pass over the sorted codes (run-length encode with a look-back scan inside), into
+        // scratch that can hold the worst case; the exact-size arrays are filled below
+        CU(c->flags.ensure(n * 4));                           // unique codes (scratch)
+        CU(c->pos.ensure(n * 4));                             // run lengths (scratch)
+        CU(c->misc.ensure(16));
+        cub::DeviceRunLengthEncode::Encode(nullptr, rle_tmp, d_sorted_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), c->misc.as<uint32_t>(), (int)n, c->stream);
+        CU(c->cubtmp.ensure(rle_tmp));
+        CU(cub::DeviceRunLengthEncode::Encode(c->cubtmp.p, rle_tmp, d_sorted_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), c->misc.as<uint32_t>(), (int)n,
+                                              c->stream));
+        LAUNCHED(2);
+        CU(cudaMemcpyAsync(&nuniq, c->misc.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        bool bad = false;
+        const int vrc = validation_failed(c, &bad);               // (synchronises)
+        if (vrc) return vrc;
+        if (bad) return fail(KSSD_E_INVAL, "index: a code or genome id lies outside the component's space / the genome count (mismatched or corrupt input)");
+    }
+    if (big) {                                                // head flags + scan + scatter (three passes)
         CU(c->flags.ensure(n * 4));
         CU(c->pos.ensure(n * 4));
         const uint32_t nb = (uint32_t)((n + 255) / 256);
@@ -1205,10 +1224,16 @@ static int index_finish(kssd_ctx *c, kssd_index *ix, uint32_t *d_sorted_codes)
     ix->n_unique = nuniq;
     CU(cudaMallocAsync(&ix->d_ucodes, std::max<size_t>(nuniq, 1) * 4, c->stream));
     CU(cudaMallocAsync(&ix->d_uoff, ((size_t)nuniq + 1) * 4, c->stream));
-    if (n) {
-        csr_scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(d_sorted_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n,
-                                                                               ix->d_ucodes, ix->d_uoff);
+    if (big) {
+        csr_scatter_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(d_sorted_codes, c->flags.as<uint32_t>(), c->pos.as<uint32_t>(), n, ix->d_ucodes, ix->d_uoff);
         LAUNCHED(1);
+    } else if (nuniq) {
+        CU(cudaMemcpyAsync(ix->d_ucodes, c->flags.p, (size_t)nuniq * 4, cudaMemcpyDeviceToDevice, c->stream));
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->pos.as<uint32_t>(), ix->d_uoff, nuniq, c->stream);
+        CU(c->cubtmp.ensure(std::max(tmp, rle_tmp)));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, c->pos.as<uint32_t>(), ix->d_uoff, nuniq, c->stream));
+        LAUNCHED(2);
     }
     const uint32_t n32 = (uint32_t)n;
     CU(cudaMemcpyAsync(ix->d_uoff + nuniq, &n32, 4, cudaMemcpyHostToDevice, c->stream));
@@ -1237,16 +1262,13 @@ extern "C" int kssd_index_build_dev(kssd_ctx_t *c, const uint32_t *combco_dev, c
     CU(cudaMallocAsync(&ix->d_gids, std::max<size_t>(n_codes, 1) * 4, c->stream));
     uint32_t *d_sorted = nullptr;
     if (n_codes) {
-        validate_below(c, combco_dev, n_codes, ix->space);        // a code outside 16^COMPONENT_SZ has no place in the index
         CU(c->keys.ensure(n_codes * 4));     // gid tags (unsorted)
         CU(c->keys2.ensure(n_codes * 4));    // sorted codes
-        CU(cudaMemsetAsync(c->keys.p, 0, n_codes * 4, c->stream));
-        mark_genome_starts_kernel<<<(n_genomes + 255) / 256, 256, 0, c->stream>>>(cbdcoindex_dev, n_genomes, c->keys.as<uint32_t>());
+        // gid of every posting position + the check that no code lies outside 16^COMPONENT_SZ, one pass
+        tag_gids_kernel<<<(uint32_t)((((n_codes + 1023) >> 10) * 32 + 255) / 256), 256, 0, c->stream>>>(cbdcoindex_dev, n_genomes, n_codes, combco_dev, ix->space,
+                                                                                                      c->keys.as<uint32_t>(), c->d_flag);
+        LAUNCHED(1);
         size_t tmp = 0;
-        cub::DeviceScan::InclusiveScan(nullptr, tmp, c->keys.as<uint32_t>(), c->keys.as<uint32_t>(), cub::Max(), n_codes, c->stream);
-        CU(c->cubtmp.ensure(tmp));
-        CU(cub::DeviceScan::InclusiveScan(c->cubtmp.p, tmp, c->keys.as<uint32_t>(), c->keys.as<uint32_t>(), cub::Max(), n_codes, c->stream));
-        LAUNCHED(3);
         tmp = 0;
         const int bits = 4 * std::min(c->info.component_sz, c->info.k - c->info.drlevel);
         cub::DeviceRadixSort::SortPairs(nullptr, tmp, combco_dev, c->keys2.as<uint32_t>(), c->keys.as<uint32_t>(), ix->d_gids, n_codes, 0, bits,

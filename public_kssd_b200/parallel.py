@@ -99,7 +99,8 @@ def exchange_codes_by_range(codes, index, gid_lo: int, n_genomes: int, world: in
     gids = torch.repeat_interleave(torch.arange(gid_lo, gid_lo + n_local, device=dev, dtype=torch.int32), counts)
     bounds = torch.tensor([code_range(r, world, code_bits)[0] for r in range(1, world)], device=dev, dtype=torch.int32)
     dest = torch.bucketize(c, bounds, right=True)                       # owner rank of every code
-    order = torch.sort(dest, stable=True).indices
+    # stable order by owner: a one-byte key is ONE radix pass (the int64 ranks bucketize returns would be eight)
+    order = torch.sort(dest.to(torch.uint8) if world <= 256 else dest, stable=True).indices
     send_counts = torch.bincount(dest, minlength=world)
     recv_counts = torch.empty_like(send_counts)
     if world > 1:
