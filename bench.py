@@ -589,7 +589,7 @@ def main():
     if rank == 0:
         line = {"metric": "sketch_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-                "data": "synthetic", "config": config, "clocks": clk,
+                "data": "synthetic", "config": config, "clocks": clk, "library": capi.library_provenance(),
                 "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": float(te.item()) * 1e3, "matches_device_path": same,
                         "h2d_copy_alone_ms": h2d_ms, "h2d_aggregate_gb_per_s": world * nbytes / (h2d_ms * 1e-3) / 1e9,

@@ -83,6 +83,29 @@ def build_library(force: bool = False) -> Path:
     return LIB_PATH
 
 
+def sources_digest() -> str:
+    """sha256 (first 16 hex digits) over the library's sources: csrc/*.cu, *.cuh, the Makefile and the C-ABI header."""
+    import hashlib
+    src = PKG_DIR / "csrc"
+    h = hashlib.sha256()
+    for f in sorted(list(src.glob("*.cu")) + list(src.glob("*.cuh")) + [src / "Makefile", PKG_DIR.parent / "include" / "kssd_b200.h"]):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def library_provenance() -> dict:
+    """What a bench line says about the binary it ran: the .so's own digest, when it was built, and whether it is newer than every
+    source it was built from (build() rebuilds it otherwise)."""
+    import hashlib
+    src = PKG_DIR / "csrc"
+    newest = max(p.stat().st_mtime for p in list(src.glob("*.cu")) + list(src.glob("*.cuh")) + [PKG_DIR.parent / "include" / "kssd_b200.h"])
+    st = LIB_PATH.stat()
+    return {"path": str(LIB_PATH.relative_to(PKG_DIR.parent)), "sha256_16": hashlib.sha256(LIB_PATH.read_bytes()).hexdigest()[:16], "bytes": st.st_size,
+            "built_unix": int(st.st_mtime), "newer_than_sources": bool(st.st_mtime >= newest), "sources_sha256_16": sources_digest(),
+            "flags": "nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a (csrc/Makefile)", "version": lib().kssd_version().decode()}
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
