@@ -21,6 +21,7 @@
 #include "index_dist.cuh"
 #include "sketch_scan3.cuh"
 #include "sketch_fastq.cuh"
+#include "sketch_fastq3.cuh"
 #include "sketch_buckets.cuh"
 #include "set_ops.cuh"
 #include "composite.cuh"
@@ -454,6 +455,10 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
 {
     const SketchParams &P = c->P;
     CU(cudaFuncSetAttribute(sketch_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kPfWords + kPf2Words) * 4)));
+    CU(cudaFuncSetAttribute(sketch_fastq3_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFq3SmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fastq3_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFq3SmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fastq3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFq3SmemBytes));
+    CU(cudaFuncSetAttribute(sketch_fastq3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFq3SmemBytes));
     for (int g = 0; g < n_genomes; g++) {
         const uint64_t gs = goff[g], ge = gs + glen[g];
         if (ge == gs) continue;
@@ -481,6 +486,20 @@ static int fastq_run(kssd_ctx *c, const uint8_t *d_seq, const uint64_t *goff, co
             F.out_keys = A.out_keys; F.out_ords = A.out_ords; F.out_cap = A.out_cap; F.out_count = A.out_count; F.gstatus = A.gstatus;
             const uint64_t want = ((ge - gs) / 64 + kFastqThreads - 1) / kFastqThreads;   // records are not counted yet: >= 64 bytes each as a guess
             if (dbg) CU(cudaEventRecord(c->ev[3], c->stream));
+            // the warp walk (block prefilter, lazy codes) whenever the qualities cannot matter: -A, or -Q <= 0 and no byte >= 0x80 in the
+            // file -- the second condition is known on the device only, so both kernels are queued and one of them returns at once
+            const bool warp_walk = (F.abund || Q <= 0) && !getenv("KSSD_FASTQ_THREAD_WALK");
+            if (warp_walk) {
+                ScanArgs A3 = A;
+                A3.strict_window = 1;
+                const bool big = 2 * (P.TL - 1) >= 32;
+                F.warp_walk = 1;
+                if (c->scan_stride == 3 && big) sketch_fastq3_kernel<3, true><<<c->sm_count, kScanThreads, kFq3SmemBytes, c->stream>>>(P, A3, F, c->d_prefilter3);
+                else if (c->scan_stride == 3) sketch_fastq3_kernel<3, false><<<c->sm_count, kScanThreads, kFq3SmemBytes, c->stream>>>(P, A3, F, c->d_prefilter3);
+                else if (big) sketch_fastq3_kernel<1, true><<<c->sm_count, kScanThreads, kFq3SmemBytes, c->stream>>>(P, A3, F, c->d_prefilter3);
+                else sketch_fastq3_kernel<1, false><<<c->sm_count, kScanThreads, kFq3SmemBytes, c->stream>>>(P, A3, F, c->d_prefilter3);
+                LAUNCHED(1);
+            }
             sketch_fastq_kernel<<<(uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)c->sm_count), kFastqThreads, (kPfWords + kPf2Words) * 4, c->stream>>>(P, F);
             LAUNCHED(2);
             if (dbg) {

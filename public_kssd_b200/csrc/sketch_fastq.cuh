@@ -258,6 +258,7 @@ struct FastqArgs {
     const uint32_t *nlpos32;     // or (single-pass index): 32-bit offsets from pos_base, the counts read from *idx on the device
     uint64_t pos_base;
     const NlIndexOut *idx;
+    int warp_walk;               // 1: sketch_fastq3_kernel walks this file unless a quality byte can fail (then this kernel does)
     uint64_t n_nl;               // newline-terminated lines
     uint64_t n_lines;            // n_nl + 1 if an unterminated tail line exists
     uint64_t n_records;          // ceil(n_lines / 4)
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(kFastqThreads, 1) sketch_fastq_kernel(const Sk
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *pf = reinterpret_cast<uint32_t *>(smem_raw);
+    if (A.nlpos32 && A.warp_walk && (A.abund || A.Q <= -128 || !A.idx->highbit)) return;      // sketch_fastq3_kernel has walked this file
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.prefilter);
         uint4 *dst = reinterpret_cast<uint4 *>(pf);

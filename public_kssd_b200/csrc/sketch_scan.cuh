@@ -64,6 +64,7 @@ struct ScanArgs {
     uint32_t *bcnt;              // occurrences per bucket (may exceed the capacity: then *boverflow is set)
     uint32_t *boverflow;
     uint32_t n_genomes;
+    int strict_window;           // FASTQ reads: the final check wants the 2k BYTES ending at the position to be letters (no line ends inside)
 };
 
 struct WarpQueue {

@@ -136,6 +136,17 @@ __device__ __forceinline__ bool verify_window(const uint8_t *__restrict__ seq, u
     }
 }
 
+// FASTQ reads (sketch_fastq3.cuh): the 2k bytes ending at absolute offset p are all of ACGTacgt, none before the file's first byte
+__device__ __forceinline__ bool verify_window_strict(const uint8_t *__restrict__ seq, uint64_t gs, uint64_t p, int TL)
+{
+    if (p - gs + 1 < (uint64_t)TL) return false;
+    for (int i = 0; i < TL; i++) {
+        const uint32_t l = __ldg(seq + p - i) | 0x20u;
+        if (!(l == 'a' || l == 'c' || l == 'g' || l == 't')) return false;
+    }
+    return true;
+}
+
 // exact resolution of queued candidates (scan representation), up to 32 at a time.  Out of line: three call sites,
 // a few thousand calls per launch -- the clean loop should not carry this code in its instruction-cache footprint.
 __device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, const WarpQ3 &q, uint32_t first, uint32_t m)
@@ -148,7 +159,9 @@ __device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, 
         const uint64_t y = ((uint64_t)q.hi[first + lane] << 32) | q.lo[first + lane];
         // byte of the occurrence's last base: the lane's offset plus the (j+1)-th byte of the lane without a skip flag
         const uint32_t oh = q.ordhi[first + lane];
-        ordv = (((uint64_t)(oh & 0x07ffffffu) << 32) | q.ordlo[first + lane]) + __fns(~q.f[first + lane], 0, (int)(oh >> 27) + 1);
+        uint64_t lane_ord = ((uint64_t)(oh & 0x07ffffffu) << 32) | q.ordlo[first + lane];       // 59 bits, two's complement: a lane may start
+        if (lane_ord >> 58) lane_ord |= ~((1ull << 59) - 1ull);                                    // a few bytes before its genome does
+        ordv = lane_ord + __fns(~q.f[first + lane], 0, (int)(oh >> 27) + 1);
         gid = q.gid[first + lane];
         const uint64_t gs = A.goff[gid];
         const uint64_t yf = y ^ ((y >> 1) & 0x5555555555555555ull);       // raw -> A0 C1 G2 T3
@@ -167,7 +180,7 @@ __device__ __noinline__ void resolve3(const SketchParams &P, const ScanArgs &A, 
         if (found) {
             const uint64_t dr = (((u & P.undomask) + ((u & P.outmask) << (4 * P.s))) >> (4 * P.L)) + pf;
             key = ((dr & P.comp_mask) << 56) | ((uint64_t)gid << 28) | (dr >> P.comp_code_bits);
-            found = verify_window(A.seq, gs, gs + ordv, P.TL);
+            found = A.strict_window ? verify_window_strict(A.seq, gs, gs + ordv, P.TL) : verify_window(A.seq, gs, gs + ordv, P.TL);
             if (found && A.drop_zero && dr == 0) { found = false; atomicAdd(&A.zero_count[gid], 1u); }
         }
     }
