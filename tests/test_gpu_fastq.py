@@ -191,3 +191,48 @@ def test_fastq_line_index_paths_agree(ctx_l2k8, shuf_s5, oracle_mod, monkeypatch
         lo, hi = int(sk.index[0][i]), int(sk.index[0][i + 1])
         assert np.array_equal(sk.ids[0][lo:hi], ids[o]), n
         assert np.array_equal(sk.abund[0][lo:hi], ab[o]), n
+
+
+def _mixed_length_fastq(n: int, seed: int) -> np.ndarray:
+    """reads of 1 .. 400 bases in random order (the lanes of the warp walk get reads of different piece counts), a few N, lower case,
+    headers of different lengths so that the sequence lines start at every alignment"""
+    src = synth.random_bases(50_000, seed)
+    r = synth._stream(seed, 3 * n, salt=43)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    parts = []
+    for i in range(n):
+        ln = 1 + int(r[3 * i] % np.uint64(400))
+        st = int(r[3 * i + 1] % np.uint64(src.size - ln))
+        seq = acgt[src[st:st + ln]].copy()
+        f = int(r[3 * i + 2])
+        if f & 7 == 0 and ln > 30:
+            seq[ln // 2] = ord("N")
+        if f & 24 == 8:
+            seq[: ln // 3] |= 0x20
+        parts.append(b"@r" + b"x" * ((f >> 8) % 37) + b"\n" + seq.tobytes() + b"\n+\n" + b"I" * ln + b"\n")
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("abund", [False, True])
+def test_fastq_mixed_read_lengths(ctx_l2k8, shuf_s5, oracle_mod, abund, monkeypatch):
+    """warp walk (lane per read, rounds of pieces) on reads of every length and alignment, against the oracle and the thread walk"""
+    files = [_mixed_length_fastq(5000, 321), _mixed_length_fastq(77, 322)[:-1]]
+    orc = oracle_mod.Ctx(8, 5, 2, shuf_s5)
+    res = {}
+    for walk in ("warp", "thread"):
+        if walk == "thread":
+            monkeypatch.setenv("KSSD_FASTQ_THREAD_WALK", "1")
+        else:
+            monkeypatch.delenv("KSSD_FASTQ_THREAD_WALK", raising=False)
+        res[walk] = ctx_l2k8.sketch_fastq(files, Q=0, M=1, abundance=abund)
+    for i, f in enumerate(files):
+        for walk, sk in res.items():
+            lo, hi = int(sk.index[0][i]), int(sk.index[0][i + 1])
+            if abund:
+                ids, comp, ab = orc.fastq_abund(f)
+                o = np.argsort(ids, kind="stable")
+                assert np.array_equal(sk.ids[0][lo:hi], ids[o]), (walk, i)
+                assert np.array_equal(sk.abund[0][lo:hi], ab[o]), (walk, i)
+            else:
+                ids, comp = orc.fastq(f, 0, 1)
+                assert np.array_equal(sk.ids[0][lo:hi], np.sort(ids)), (walk, i, hi - lo, len(ids))
