@@ -106,3 +106,26 @@ def test_multi_config_parity(oracle_mod):
                     assert np.array_equal(sets[i][c], np.sort(ids[comp == c])), (k, s, L, i, c)
         finally:
             ctx.close()
+
+
+def test_genomes_at_16_byte_starts_give_the_same_sketch(gpu_ctx_l3k10):
+    """The C-ABI asks for genome starts at multiples of 16 only: a genome that starts in the middle of a 32-byte lane / a 128-byte chunk
+    must give the ids AND the first-occurrence offsets of the 128-aligned layout (lane offsets below the genome start are negative)."""
+    from public_kssd_b200 import capi, kssd
+    gens = [synth.to_fasta(synth.random_bases(40_000 + 37 * i, 500 + i), f"g{i}", 60 + i) for i in range(7)]
+    gens.append(synth.messy_fasta(60_000, 9))
+    want = gpu_ctx_l3k10.sketch(gens)
+    buf, goff, glen = kssd.pack_genomes(gens, align=16)
+    assert any(int(o) % 32 for o in goff)
+    h = gpu_ctx_l3k10.sketch_raw(buf, buf.size, goff, glen)
+    got = gpu_ctx_l3k10.fetch_sketch(h, len(gens), want_ord=True)
+    assert np.array_equal(got.index[0], want.index[0]) and np.array_equal(got.ids[0], want.ids[0])
+    assert np.array_equal(got.ord[0], want.ord[0])
+    # FASTQ through the same layout (warp walk: pieces that start before the file does)
+    src = synth.random_bases(30_000, 77)
+    fq = [synth.to_fastq(src, 400 + 3 * i, 100 + i, seed=600 + i) for i in range(5)]
+    w = gpu_ctx_l3k10.sketch_fastq(fq, Q=0, M=1)
+    buf, goff, glen = kssd.pack_genomes(fq, align=16)
+    h = gpu_ctx_l3k10.sketch_raw(buf, buf.size, goff, glen, mode=capi.MODE_FASTQ, Q=0, M=1)
+    g = gpu_ctx_l3k10.fetch_sketch(h, len(fq), want_ord=True)
+    assert np.array_equal(g.index[0], w.index[0]) and np.array_equal(g.ids[0], w.ids[0]) and np.array_equal(g.ord[0], w.ord[0])
