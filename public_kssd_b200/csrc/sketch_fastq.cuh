@@ -162,11 +162,23 @@ __global__ void __launch_bounds__(kNlBlock, 4) nl_index_kernel(const uint8_t *__
     constexpr int kSteps = kNlxPerThread / 64;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint64_t a = a0 + (uint64_t)b * kNlxBytesPerBlock + (uint64_t)wid * (32 * kNlxPerThread) + 64ull * lane;
-    uint64_t m[kSteps];
+    // line ends of the thread's 16 groups of 32 bytes, one word per group in WORD-MAJOR bit order: bit 8j + k <-> byte j of word k of the
+    // group, i.e. text position 4k + j.  That order costs one shift and a third of an OR per word to build (the exact 0x80-per-matching-
+    // byte flags of the eight words, shifted by 7 - k and ORed) where the text-order gather cost a multiply, a shift and an OR; counting
+    // does not care, and the few words that hold a line end are put into text order when the positions are written.
+    uint32_t W[2 * kSteps];
     uint32_t pre[kSteps];                                    // line ends of the warp before this lane's 64 bytes of step k
     uint32_t wtot = 0;
     const uint64_t blk0 = a0 + (uint64_t)b * kNlxBytesPerBlock;
     uint32_t hb = 0;                                          // OR of every byte: a quality byte can only fail -Q <= 0 with its high bit set
+    auto zflags = [](uint32_t w) -> uint32_t {                // 0x80 in every byte of w that equals '\n' (exact)
+        const uint32_t x = w ^ 0x0a0a0a0au;
+        return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    };
+    auto group_word = [&](const uint4 &lo, const uint4 &hi) -> uint32_t {
+        return (zflags(lo.x) >> 7) | (zflags(lo.y) >> 6) | (zflags(lo.z) >> 5) | (zflags(lo.w) >> 4) | (zflags(hi.x) >> 3) | (zflags(hi.y) >> 2) |
+               (zflags(hi.z) >> 1) | zflags(hi.w);
+    };
     if (blk0 >= gs && blk0 + kNlxBytesPerBlock <= ge) {       // a block inside the file: no guards, two steps of loads in flight at a time
 #pragma unroll
         for (int k = 0; k < kSteps; k += 2) {
@@ -177,15 +189,23 @@ __global__ void __launch_bounds__(kNlBlock, 4) nl_index_kernel(const uint8_t *__
             for (int j = 0; j < 8; j++) hb |= v[j].x | v[j].y | v[j].z | v[j].w;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const uint32_t m0 = eq_mask16(v[4 * h], 0x0a0a0a0au), m1 = eq_mask16(v[4 * h + 1], 0x0a0a0a0au);
-                const uint32_t m2 = eq_mask16(v[4 * h + 2], 0x0a0a0a0au), m3 = eq_mask16(v[4 * h + 3], 0x0a0a0a0au);
-                m[k + h] = (uint64_t)(m0 | (m1 << 16)) | ((uint64_t)(m2 | (m3 << 16)) << 32);
+                W[2 * (k + h)] = group_word(v[4 * h], v[4 * h + 1]);
+                W[2 * (k + h) + 1] = group_word(v[4 * h + 2], v[4 * h + 3]);
             }
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kSteps; k++) m[k] = line_mask64<false>(seq, a + 2048ull * k, gs, ge);
-        for (int k = 0; k < kSteps; k++)                      // (first and last block of a file only)
+        for (int k = 0; k < kSteps; k++) {                    // (first and last block of a file only: text-order masks, re-ordered bit by bit)
+            const uint64_t m = line_mask64<false>(seq, a + 2048ull * k, gs, ge);
+            uint32_t w2[2] = {0u, 0u};
+            for (uint64_t t = m; t; t &= t - 1) {
+                const int i = __ffsll((long long)t) - 1, g = i >> 5, q = i & 31;
+                w2[g] |= 1u << (8 * (q & 3) + (q >> 2));
+            }
+            W[2 * k] = w2[0];
+            W[2 * k + 1] = w2[1];
+        }
+        for (int k = 0; k < kSteps; k++)
             for (int j = 0; j < 64; j++) {
                 const uint64_t p = a + 2048ull * k + j;
                 if (p >= gs && p < ge) hb |= seq[p];
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(kNlBlock, 4) nl_index_kernel(const uint8_t *__
     if (__any_sync(kFull, (hb & 0x80808080u) != 0) && lane == 0) out->highbit = 1u;
 #pragma unroll
     for (int k = 0; k < kSteps; k++) {
-        const uint32_t c = __popcll(m[k]);
+        const uint32_t c = __popc(W[2 * k]) + __popc(W[2 * k + 1]);
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -239,13 +259,21 @@ __global__ void __launch_bounds__(kNlBlock, 4) nl_index_kernel(const uint8_t *__
     const uint32_t o0 = s_prefix + base;
 #pragma unroll
     for (int k = 0; k < kSteps; k++) {
-        uint64_t mk = m[k];
         uint32_t o = o0 + pre[k];
-        while (mk) {
-            const int i = __ffsll((long long)mk) - 1;
-            mk &= mk - 1;
-            if (o < cap) nlpos32[o] = (uint32_t)(a + 2048ull * k + i - a0);
-            o++;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t w = W[2 * k + h];
+            if (!w) continue;
+            uint32_t T = 0;                                   // the group's line ends in text order
+            for (; w; w &= w - 1) {
+                const int bb = __ffs(w) - 1;
+                T |= 1u << (4 * (bb & 7) + (bb >> 3));
+            }
+            for (; T; T &= T - 1) {
+                const int i = __ffs(T) - 1;
+                if (o < cap) nlpos32[o] = (uint32_t)(a + 2048ull * k + 32u * h + i - a0);
+                o++;
+            }
         }
     }
 }
