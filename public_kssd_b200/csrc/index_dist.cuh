@@ -734,6 +734,10 @@ __global__ void __launch_bounds__(C::kThreads) dist_sparse_kernel(const SparseCo
     extern __shared__ __align__(16) uint32_t sparse_sm[];
     uint32_t *keys = sparse_sm, *vals = keys + C::kSlots, *lstart = vals + (PACKED ? 0 : C::kSlots), *lpre = lstart + C::kTile,
              *bitmap = lpre + C::kTile + 1;                  // PACKED: no vals array, the descriptors start right after the keys
+    // touched refs in the words before a word, inside its thread's run of words: kept in the list descriptors' space, which is free once
+    // the walk is over (when it fits: R <= 16 (2 kTile + 1) references; else the emission sums the run's words itself)
+    uint16_t *wpfx = reinterpret_cast<uint16_t *>(lstart);
+    const bool use_pfx = ((n_ref + 31) / 32) * 2 <= (2 * C::kTile + 1) * 4;
     const uint32_t cmask = PACKED ? ((1u << cb) - 1u) : 0u;
     __shared__ uint32_t distinct, tbase[C::kThreads];
     __shared__ uint2 wsum[C::kThreads / 32];
@@ -784,7 +788,7 @@ __global__ void __launch_bounds__(C::kThreads) dist_sparse_kernel(const SparseCo
         while (((uint32_t)C::kThreads << per_log) < bw) per_log++;
         const uint32_t w0 = min(threadIdx.x << per_log, bw), w1 = min(w0 + (1u << per_log), bw);
         uint32_t cnt = 0;
-        for (uint32_t w = w0; w < w1; w++) cnt += __popc(bitmap[w]);
+        for (uint32_t w = w0; w < w1; w++) { if (use_pfx) wpfx[w] = (uint16_t)cnt; cnt += __popc(bitmap[w]); }      // (a run is < 2^16 refs)
         uint2 tot2;
         const uint32_t off = sparse_block_scan<C>(make_uint2(cnt, 0u), wsum, &tot2).x;
         const uint32_t total = tot2.x;
@@ -803,7 +807,8 @@ __global__ void __launch_bounds__(C::kThreads) dist_sparse_kernel(const SparseCo
                 const uint32_t r = PACKED ? e >> cb : e;
                 const uint32_t w = r >> 5, owner = w >> per_log;
                 uint32_t rank = tbase[owner] + __popc(bitmap[w] & ((1u << (r & 31)) - 1u));
-                for (uint32_t x = owner << per_log; x < w; x++) rank += __popc(bitmap[x]);
+                if (use_pfx) rank += wpfx[w];
+                else for (uint32_t x = owner << per_log; x < w; x++) rank += __popc(bitmap[x]);
                 SparseHit h;
                 h.q = q; h.r = r; h.shared = PACKED ? e & cmask : vals[sidx];
                 hits[base + rank] = h;
