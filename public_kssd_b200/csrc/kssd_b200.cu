@@ -334,6 +334,7 @@ extern "C" int kssd_ctx_sync(const kssd_ctx_t *c)
 {
     if (!c) return fail(KSSD_E_INVAL, "kssd_ctx_sync: null");
     CU(cudaStreamSynchronize(c->stream));
+    if (c->stream2) CU(cudaStreamSynchronize(c->stream2));      // the rows passes of queued searches (kssd_dist_stats_async)
     return KSSD_OK;
 }
 extern "C" float kssd_ctx_last_ms(const kssd_ctx_t *cc, int which)
