@@ -293,16 +293,26 @@ def run(ctx, world: int, rank: int, dev, peak_gbs: float, n_ref: int = N_REF, n_
                                "note": "bytes = 4 Nq (codes) + 16 Nq (two offsets per lookup) + 4 P (postings) + 4 Q R (matrix written once), SURVEY.md s8d"}
             # end to end: host query buffers in, statistics rows on the host out (sparse job)
             qc_h, qi_h = tq.cpu().numpy().view(np.uint32), ti.cpu().numpy().view(np.uint64)
-            e2e = []
+            from public_kssd_b200 import capi as _capi
+            row_b = _capi.STAT_ROW_DTYPE.itemsize
+            pin_q = torch.from_numpy(qc_h.view(np.int32).copy()).pin_memory()              # the caller's buffers: pinned, allocated once
+            pin_rows = torch.empty(len(want) * row_b + 4096, dtype=torch.uint8, pin_memory=True)
+            qc_p = pin_q.numpy().view(np.uint32)
+            e2e, n_rows = [], 0
             for _ in range(3):
                 t1 = time.perf_counter()
                 sj = kssd.DistJob(ctx, qsz0, ref_sizes, sparse=True)
-                sj.accumulate(full, qc_h, qi_h)
-                rows_h = sj.stats(skip_zero=1, cmprsn_num=cm)
+                sj.accumulate(full, qc_p, qi_h)
+                n_rows = int(sj.stats(skip_zero=1, fetch=False, cmprsn_num=cm))
+                assert n_rows * row_b <= pin_rows.numel()
+                sj.fetch_stats_into(pin_rows.data_ptr())
                 sj.close()
                 e2e.append(time.perf_counter() - t1)
+            rows_h = pin_rows.numpy()[: n_rows * row_b].view(_capi.STAT_ROW_DTYPE)
+            same_rows = bool(n_rows == len(want) and rows_h.tobytes() == want.tobytes())
             out["e2e"] = {"value": n_qry * n_ref / min(e2e), "unit": "pairs/s", "ms": min(e2e) * 1e3, "h2d_bytes": int(qc_h.nbytes + qi_h.nbytes + qsz0.nbytes),
-                          "d2h_bytes": int(rows_h.nbytes), "note": "kssd_dist_create_sparse + add_host + stats + fetch_stats: query sketches from host memory, rows back"}
+                          "d2h_bytes": int(n_rows * row_b), "rows_equal_dense_job": same_rows,
+                          "note": "kssd_dist_create_sparse + add_host + stats + fetch_stats: query sketches from pinned host memory, all statistics rows back into pinned host memory"}
         dj.close()
         full.close()
     if world > 1:

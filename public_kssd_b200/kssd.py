@@ -418,6 +418,11 @@ class DistJob:
         check(lib().kssd_dist_fetch_stats(self._h, rows.ctypes.data_as(C.c_void_p)))
         return rows
 
+    def fetch_stats_into(self, host_ptr: int) -> None:
+        """copy the rows of the last stats() / stats_wait() into caller-owned host memory (n_rows * 88 bytes; pinned memory makes it
+        a single DMA at link speed)"""
+        check(lib().kssd_dist_fetch_stats(self._h, C.c_void_p(host_ptr)))
+
     def stats_async(self, metric: int = 0, correction: int = 0, kmerlen: int | None = None, dim_rd_len: int | None = None,
                     dthreshold: float = 1.0, n_neighbors: int = 0, skip_zero: int = 0, cmprsn_num: int = 0):
         """Queue the whole sparse search (count + list + statistics) without waiting for the GPU; stats_wait() returns the row
