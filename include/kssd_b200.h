@@ -240,9 +240,11 @@ typedef struct kssd_stat_row {
  * copy) and kssd_dist_stats counts, filters and lists in one kernel: shared counts live in a per-query shared-memory
  * hash table, work is proportional to the postings touched instead of Q x R.  Rows are identical to the dense job's.
  * Queries that touch more than 6144 references do not fit the shared-memory table: they are counted through a small
- * dense sub-job (n_over x R) and merged back in print order.  If the options do print zero cells (-N, -D >= 1 without
- * skip_zero, --correction, empty sketches whose cells are NaN), most queries overflow, or counts are fetched, the whole
- * job falls back to the matrix transparently. */
+ * dense sub-job (n_over x R) and merged back in print order.  -N never lists a reference that shares nothing
+ * (command_dist.c:1212-1227 inserts on metric > 0 only), so its best n are picked from the cells the kernel touched
+ * (topn_sparse_kernel); if some query overflowed the table, -N goes through the matrix.  If the options do print zero
+ * cells (-D >= 1 without skip_zero, --correction, empty sketches whose cells are NaN), most queries overflow, or
+ * counts are fetched, the whole job falls back to the matrix transparently. */
 int kssd_dist_create_sparse(kssd_ctx_t *ctx, int n_qry, int n_ref, const uint32_t *qry_ctx_ct,
                             const uint32_t *ref_ctx_ct, kssd_dist_t **out);
 int kssd_dist_sparse_add_dev(kssd_dist_t *d, const kssd_index_t *ref_ix, const uint32_t *qcodes_dev,

@@ -930,4 +930,68 @@ __global__ void __launch_bounds__(256) topn_kernel(const StatParams S, const uin
     if (threadIdx.x == 0) row_counts[q] = nout;
 }
 
+
+// -N on the sparse job: a reference that shares nothing with the query has metric 0 and is never listed, so the best n are among the
+// cells the sparse count kernel touched -- the query's run of the hit list (ascending reference order) instead of a row of R cells.
+// Same insertion rule as topn_kernel.
+__global__ void __launch_bounds__(256) topn_sparse_kernel(const StatParams S, const SparseHit *__restrict__ hits, const unsigned long long *__restrict__ q_pos,
+                                                          const uint32_t *__restrict__ q_cnt, const uint32_t *__restrict__ qsz, const uint32_t *__restrict__ rsz,
+                                                          int nmax, uint32_t *__restrict__ row_counts, StatRow *__restrict__ rows)
+{
+    const uint32_t q = blockIdx.x;
+    const uint32_t Y = qsz[q], cnt = q_cnt[q];
+    const SparseHit *hq = hits + q_pos[q];
+    __shared__ double best_m[256];
+    __shared__ int best_i[256];
+    __shared__ double last_m;
+    __shared__ int last_r;
+    __shared__ uint32_t nout;
+    if (threadIdx.x == 0) { last_m = 1e300; last_r = -1; nout = 0; }
+    __syncthreads();
+    for (int it = 0; it < nmax; it++) {
+        double bm = 0.0;
+        int bi = -1, br = -1;
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t r = hq[i].r, X = rsz[r], I = hq[i].shared;
+            const double m = S.metric == 1 ? (double)I / (double)(X < Y ? X : Y) : (double)I / (double)(X + Y - I);
+            const bool after = (m < last_m) || (m == last_m && (int)r > last_r);
+            if (!(m > 0.0) || !after) continue;
+            if (bi < 0 || m > bm || (m == bm && (int)r < br)) { bm = m; bi = (int)i; br = (int)r; }
+        }
+        best_m[threadIdx.x] = bm;
+        best_i[threadIdx.x] = bi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            int r = -1, sel = -1;
+            for (int t = 0; t < (int)blockDim.x; t++) {
+                if (best_i[t] < 0) continue;
+                const int rt = (int)hq[best_i[t]].r;
+                if (sel < 0 || best_m[t] > m || (best_m[t] == m && rt < r)) { m = best_m[t]; r = rt; sel = best_i[t]; }
+            }
+            last_m = m;
+            last_r = r;
+            if (sel >= 0) {
+                StatRow row;
+                if (stat_row(S, rsz[r], Y, hq[sel].shared, row)) {
+                    row.qry = q; row.ref = (uint32_t)r;
+                    rows[(uint64_t)q * nmax + nout] = row;
+                    nout++;
+                }
+            }
+        }
+        __syncthreads();
+        if (last_r < 0) break;
+    }
+    if (threadIdx.x == 0) row_counts[q] = nout;
+}
+
+// the listed rows of every query (up to nmax each, at q * nmax) -> one query-major list
+__global__ void topn_gather_kernel(const StatRow *__restrict__ tmp, const uint32_t *__restrict__ row_counts, const uint64_t *__restrict__ row_off, int nmax,
+                                   StatRow *__restrict__ rows)
+{
+    const uint32_t q = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < row_counts[q]; i += blockDim.x) rows[row_off[q] + i] = tmp[(uint64_t)q * nmax + i];
+}
+
 }  // namespace kssd

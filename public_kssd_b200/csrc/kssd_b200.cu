@@ -1733,6 +1733,27 @@ extern "C" int kssd_dist_fetch_counts(const kssd_dist_t *d, uint32_t *ct_out)
 
 extern "C" const uint32_t *kssd_dist_counts_dev(const kssd_dist_t *d) { return d ? d->d_ct : nullptr; }
 
+// -N: the rows topn_*_kernel listed (row counts in `counts`, up to N per query at q * N in tmp_rows) -> d->d_rows, query-major
+static int topn_collect(kssd_ctx *c, kssd_dist *d, const StatRow *tmp_rows, int N, uint32_t *counts /* n_qry + 1 words */, uint64_t *total_out)
+{
+    CU(c->pos.ensure(((size_t)d->n_qry + 1) * 8));
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, counts, c->pos.as<uint64_t>(), d->n_qry + 1, c->stream);
+    CU(c->cubtmp.ensure(tmp));
+    CU(cudaMemsetAsync(counts + d->n_qry, 0, 4, c->stream));
+    CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, counts, c->pos.as<uint64_t>(), d->n_qry + 1, c->stream));
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, c->pos.as<uint64_t>() + d->n_qry, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
+    topn_gather_kernel<<<d->n_qry, 64, 0, c->stream>>>(tmp_rows, counts, c->pos.as<uint64_t>(), N, d->d_rows);
+    LAUNCHED(3);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    *total_out = total;
+    return KSSD_OK;
+}
+
 extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
 {
     if (!d || !o) return fail(KSSD_E_INVAL, "kssd_dist_stats: null");
@@ -1774,8 +1795,10 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
             const size_t slots = nar ? SparseNarrow::kSlots : SparseWide::kSlots, tile = nar ? SparseNarrow::kTile : SparseWide::kTile;
             return ((packed ? 1ull : 2ull) * slots + 2ull * tile + 1 + bw) * 4;
         };
-        if (no_zero_rows && smem_of(false) <= 200u * 1024u) {
-            const bool trivial = S.dthreshold >= 1.0;
+        // -N: a reference that shares nothing is never listed, so the best n of a query are among the cells the sparse kernel touches
+        const bool topn_sparse = o->n_neighbors > 0 && !getenv("KSSD_TOPN_DENSE");
+        if ((no_zero_rows || topn_sparse) && smem_of(false) <= 200u * 1024u) {
+            const bool trivial = topn_sparse || S.dthreshold >= 1.0;      // (-N lists first and applies the keep rule to what it listed)
             const int nc = (int)d->comps.size();
             CU(cudaEventRecord(c->ev[0], c->stream));
             CU(c->flags.ensure((size_t)d->n_qry * 4));                 // q_cnt
@@ -1786,7 +1809,7 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
             if (nc) CU(cudaMemcpyAsync(mb + 16, d->comps.data(), sizeof(SparseComp) * nc, cudaMemcpyHostToDevice, c->stream));
             uint64_t total = 0, cap = std::max<uint64_t>(1ull << 22, (uint64_t)d->n_qry * 1024);
             uint32_t n_over = 0, bad_extent = 0;
-            CU(c->ords2.ensure((size_t)d->n_qry * 4));                 // queries that overflow the table
+            CU(c->ords2.ensure(((size_t)d->n_qry + 1) * 4));           // queries that overflow the table (-N: rows listed per query)
             for (int attempt = 0;; attempt++) {
                 if (cap > 0xffffffffull) return fail(KSSD_E_NOMEM, "kssd_dist_stats: more than 2^32 rows pass the filter; tighten -D");
                 CU(c->keys.ensure(cap * sizeof(SparseHit)));
@@ -1825,7 +1848,27 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
                 if (attempt > 0) return fail(KSSD_E_NOMEM, "kssd_dist_stats: hit list overflow");
                 cap = total;
             }
-            if ((uint64_t)n_over * 2 <= (uint64_t)d->n_qry) {
+            if (topn_sparse && n_over == 0) {
+                float count_ms = 0;
+                CU(cudaEventElapsedTime(&count_ms, c->ev[0], c->ev[2]));
+                c->last_ms[3] = count_ms;
+                const int N = o->n_neighbors;
+                StatRow *tmp_rows = nullptr;
+                CU(cudaMallocAsync(&tmp_rows, (size_t)d->n_qry * N * sizeof(StatRow), c->stream));
+                topn_sparse_kernel<<<d->n_qry, 256, 0, c->stream>>>(S, c->keys.as<SparseHit>(), c->counts.as<unsigned long long>(), c->flags.as<uint32_t>(), d->d_qsz,
+                                                                    d->d_rsz, N, c->ords2.as<uint32_t>(), tmp_rows);
+                LAUNCHED(1);
+                uint64_t listed = 0;
+                const int grc = topn_collect(c, d, tmp_rows, N, c->ords2.as<uint32_t>(), &listed);
+                cudaFreeAsync(tmp_rows, c->stream);
+                if (grc) return grc;
+                d->n_rows = listed;
+                CU(cudaEventRecord(c->ev[1], c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]));
+                return (int64_t)d->n_rows;
+            }
+            if (!topn_sparse && (uint64_t)n_over * 2 <= (uint64_t)d->n_qry) {
                 float count_ms = 0;
                 CU(cudaEventElapsedTime(&count_ms, c->ev[0], c->ev[2]));             // counting + listing
                 c->last_ms[3] = count_ms;
@@ -1944,21 +1987,14 @@ extern "C" int64_t kssd_dist_stats(kssd_dist_t *d, const kssd_stat_opts_t *o)
         const int N = o->n_neighbors;
         StatRow *tmp_rows = nullptr;
         CU(cudaMallocAsync(&tmp_rows, (size_t)d->n_qry * N * sizeof(StatRow), c->stream));
-        CU(c->flags.ensure((size_t)d->n_qry * 4));
+        CU(c->flags.ensure(((size_t)d->n_qry + 1) * 4));
         topn_kernel<<<d->n_qry, 256, 0, c->stream>>>(S, d->d_ct, d->d_qsz, d->d_rsz, (uint32_t)d->n_ref, N, c->flags.as<uint32_t>(), tmp_rows);
         LAUNCHED(1);
-        std::vector<uint32_t> rc(d->n_qry);
-        CU(cudaMemcpyAsync(rc.data(), c->flags.p, (size_t)d->n_qry * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
         uint64_t total = 0;
-        for (auto v : rc) total += v;
-        CU(cudaMallocAsync(&d->d_rows, std::max<uint64_t>(total, 1) * sizeof(StatRow), c->stream));
-        uint64_t o2 = 0;
-        for (int q = 0; q < d->n_qry; q++) {
-            if (rc[q]) CU(cudaMemcpyAsync(d->d_rows + o2, tmp_rows + (size_t)q * N, (size_t)rc[q] * sizeof(StatRow), cudaMemcpyDeviceToDevice, c->stream));
-            o2 += rc[q];
+        {
+            const int grc = topn_collect(c, d, tmp_rows, N, c->flags.as<uint32_t>(), &total);
+            if (grc) { cudaFreeAsync(tmp_rows, c->stream); return grc; }
         }
-        CU(cudaStreamSynchronize(c->stream));
         cudaFreeAsync(tmp_rows, c->stream);
         d->n_rows = total;
     } else if (S.dthreshold >= 1.0 && !o->skip_zero) {

@@ -161,10 +161,12 @@ def test_topn_neighbors(gpu_ctx_l3k10, oracle_mod):
 
 
 @pytest.mark.parametrize("opts", [dict(skip_zero=1), dict(dthreshold=0.05), dict(metric=1, dthreshold=0.2), dict(metric=1, skip_zero=1, correction=1),
-                                  dict(dthreshold=1.0), dict(n_neighbors=3), dict(dthreshold=0.3, correction=1)])
+                                  dict(dthreshold=1.0), dict(n_neighbors=3), dict(dthreshold=0.3, correction=1),
+                                  dict(n_neighbors=20, metric=1), dict(n_neighbors=7, dthreshold=0.1, correction=1)])
 def test_sparse_job_rows_identical_to_dense(gpu_ctx_l3k10, opts):
-    """kssd_dist_create_sparse: fused count + filter + listing without the Q x R matrix gives byte-identical rows; options
-    that print zero-shared cells (-D >= 1, -N, --correction with -D) fall back to the matrix transparently."""
+    """kssd_dist_create_sparse: fused count + filter + listing without the Q x R matrix gives byte-identical rows; -N picks
+    its rows from the cells the sparse kernel touched (a reference sharing nothing is never listed); options that print
+    zero-shared cells (-D >= 1, --correction with -D) fall back to the matrix transparently."""
     from public_kssd_b200 import kssd
     rc, ri = synth.synth_sketches(700, 400, seed=8, cluster_size=25)
     qc, qi = synth.synth_sketches(67, 400, seed=8, cluster_size=5)
@@ -224,7 +226,7 @@ def test_sparse_job_many_refs_per_query_falls_back(gpu_ctx_l3k10):
     dense.close(); sp.close(); ix.close()
 
 
-@pytest.mark.parametrize("opts", [dict(skip_zero=1), dict(dthreshold=0.4), dict(metric=1, dthreshold=0.3)])
+@pytest.mark.parametrize("opts", [dict(skip_zero=1), dict(dthreshold=0.4), dict(metric=1, dthreshold=0.3), dict(n_neighbors=5)])
 def test_sparse_job_heavy_queries_take_the_dense_sub_job(gpu_ctx_l3k10, opts):
     """Queries that touch more references than the shared-memory table holds are counted through a small dense sub-job
     and merged back in print order; the others stay sparse.  Rows identical to the all-dense job."""
@@ -246,7 +248,7 @@ def test_sparse_job_heavy_queries_take_the_dense_sub_job(gpu_ctx_l3k10, opts):
     sp = kssd.DistJob(gpu_ctx_l3k10, qsz, rsz, sparse=True)
     sp.accumulate(ix, qc, qi)
     got = sp.stats(**opts)
-    assert len(want) > 2 * n_ref - 100 or "dthreshold" in opts
+    assert len(want) > 2 * n_ref - 100 or "dthreshold" in opts or "n_neighbors" in opts
     assert got.tobytes() == want.tobytes()
     got2 = sp.stats(**opts)                                   # the job is reusable
     assert got2.tobytes() == want.tobytes()
@@ -278,7 +280,7 @@ def test_sparse_job_multi_component(shuf_l3k10):
         ctx.close()
 
 
-@pytest.mark.parametrize("sparse,opts", [(False, dict()), (False, dict(metric=1, dthreshold=0.3)), (True, dict(skip_zero=1)), (False, dict(n_neighbors=4))])
+@pytest.mark.parametrize("sparse,opts", [(False, dict()), (False, dict(metric=1, dthreshold=0.3)), (True, dict(skip_zero=1)), (False, dict(n_neighbors=4)), (True, dict(n_neighbors=4))])
 def test_query_batches_equal_one_job(gpu_ctx_l3k10, sparse, opts):
     """The reference's num_cof_batch loop (command_dist.c:731-734, :763-790): searching the queries a batch at a time gives the
     rows and the counts of one job, FDR column included (cmprsn_num is the whole search's)."""
