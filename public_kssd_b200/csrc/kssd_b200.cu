@@ -2418,15 +2418,15 @@ extern "C" int kssd_set_group_host(kssd_ctx_t *c, const uint32_t *combco, const 
     if (T == 0) return KSSD_OK;
     if (!combco || !codes_out) return fail(KSSD_E_INVAL, "kssd_set_group_host: null code buffer");
     StreamScratch scr(c->stream);
-    bool ok = true;
     auto galloc = [&](auto *&ptr, size_t bytes) -> bool { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(scr.alloc(bytes)); return ptr != nullptr; };
+#define GALLOC(ptr, bytes) do { if (!galloc(ptr, bytes)) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); } while (0)
     uint32_t *d_combco = nullptr, *d_mgroup = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_flags = nullptr, *d_excl = nullptr, *d_hpos = nullptr,
              *d_hcode = nullptr, *d_hpos2 = nullptr, *d_hcode2 = nullptr;
     uint64_t *d_msrc = nullptr, *d_mdst = nullptr;
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
-    if (!(ok &= galloc(d_combco, n_codes * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_msrc, (M + 1) * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_mdst, (M + 1) * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_mgroup, M * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
-    if (!(ok &= galloc(d_keys, T * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_keys2, T * 8))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_pos, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_pos2, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
-    if (!(ok &= galloc(d_flags, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_excl, T * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
+    GALLOC(d_combco, n_codes * 4); GALLOC(d_msrc, (M + 1) * 8); GALLOC(d_mdst, (M + 1) * 8); GALLOC(d_mgroup, M * 4);
+    GALLOC(d_keys, T * 8); GALLOC(d_keys2, T * 8); GALLOC(d_pos, T * 4); GALLOC(d_pos2, T * 4);
+    GALLOC(d_flags, T * 4); GALLOC(d_excl, T * 4);
     CU(cudaMemcpyAsync(d_combco, combco, n_codes * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_msrc, m_src.data(), (M + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_mdst, m_dst.data(), (M + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -2447,7 +2447,7 @@ extern "C" int kssd_set_group_host(kssd_ctx_t *c, const uint32_t *combco, const 
     CU(cudaMemcpyAsync(&last_f, d_flags + (T - 1), 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const uint64_t U = (uint64_t)last_e + last_f;                           // distinct (group, code) pairs
-    if (!(ok &= galloc(d_hpos, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_hcode, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_hpos2, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory"); if (!(ok &= galloc(d_hcode2, U * 4))) return fail(KSSD_E_NOMEM, "kssd_set_group_host: out of device memory");
+    GALLOC(d_hpos, U * 4); GALLOC(d_hcode, U * 4); GALLOC(d_hpos2, U * 4); GALLOC(d_hcode2, U * 4);
     group_compact_kernel<<<nb, 256, 0, c->stream>>>(d_keys2, d_pos2, d_flags, d_excl, T, d_hpos, d_hcode);
     tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_hpos, d_hpos2, d_hcode, d_hcode2, U, 0, 32, c->stream);
@@ -2463,6 +2463,7 @@ extern "C" int kssd_set_group_host(kssd_ctx_t *c, const uint32_t *combco, const 
         index_out[g] = (uint64_t)(std::lower_bound(hpos.begin(), hpos.end(), (uint32_t)std::min<uint64_t>(m_dst[group_index[g]], 0xffffffffull)) - hpos.begin());
     index_out[n_groups] = U;
     return KSSD_OK;
+#undef GALLOC
 }
 
 extern "C" int kssd_set_operate_host(kssd_ctx_t *c, const uint32_t *combco, const uint64_t *index, int n_genomes, const uint32_t *pan, uint64_t n_pan,
