@@ -438,21 +438,31 @@ def main():
                 dist_info["shared_total"] = int(ct.sum(dtype=np.uint64))
                 dist_info["diag_ok"] = bool(np.array_equal(np.diag(ct), sizes))
                 dist_info["rows"] = int(nrows)
-                # end to end like the reference's Stage III: statistics rows to the host + the distance.out text
+                # end to end like the reference's Stage III: statistics + the distance.out text on the host.  Main line: the GPU writes
+                # the text from the rows on the device (kssd_dist_format_text); beside it the rows fetched and formatted by the host threads
+                names = [f"g{i}.fna" for i in range(args.genomes)]
+                name_block = hostfmt._names_block(names)
+                for rep in range(2):
+                    t0 = time.perf_counter()
+                    job.stats(fetch=False)
+                    text = job.distance_out_view(name_block, name_block, 0, 2)
+                    dist_info["text_s"] = time.perf_counter() - t0
+                dist_info["text_kernels_ms"] = ctx.last_ms(5)
                 t0 = time.perf_counter()
                 rows_host = job.stats()
-                names = [f"g{i}.fna" for i in range(args.genomes)]
-                text = hostfmt.format_distance_out(rows_host, names, names, 0, 2)
-                dist_info["text_s"] = time.perf_counter() - t0
+                text_host = hostfmt.format_distance_out(rows_host, names, names, 0, 2)
+                dist_info["text_host_formatter_s"] = time.perf_counter() - t0
                 dist_info["text_bytes"] = len(text)
-                del text, rows_host
+                dist_info["text_gpu_equals_host"] = bool(bytes(text) == text_host)
+                del text, text_host, rows_host
             job.close(); ix.close()
         d_ct, d_st, d_ix = float(np.min(ct_ms)), float(np.min(st_ms)), float(np.min(ix_ms))
         dist_bytes = 4 * n_codes + 8 * n_codes + 4 * dist_info.get("shared_total", 0) + 4 * pairs
         dist_info.update({"metric": "dist_pairs_per_s", "pairs": pairs, "pairs_per_s": pairs / ((d_ct + d_st) * 1e-3), "count_ms": d_ct,
                           "stats_ms": d_st, "index_ms": d_ix,
                           "pairs_per_s_incl_text": pairs / ((d_ct) * 1e-3 + dist_info.get("text_s", 0.0)),
-                          "text_note": "text_s = statistics kernel + D2H of the rows + native multi-threaded distance.out formatting (host)",
+                          "text_note": "text_s = statistics kernel + distance.out written by the GPU (fmt_exact.cuh: glibc's %.6lf / %E in integer arithmetic) + D2H of the text into the context's pinned buffer; "
+                                       "text_host_formatter_s = statistics + D2H of the rows + snprintf on every host thread",
                           "stats_rows": "all Q*R rows (Jaccard, MashD, P-value, FDR, CIs), fp64",
                           "roofline": {"bound": "hbm", "achieved": dist_bytes / (d_ct * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": dist_bytes / (d_ct * 1e-3) / 1e9 / peak, "traffic": None,

@@ -276,6 +276,24 @@ void kssd_dist_free(kssd_dist_t *d);
 int kssd_format_distance_rows(const kssd_stat_row_t *rows, size_t n_rows, const char *qry_names, const char *ref_names,
                               size_t name_stride, int metric, int outfields, int with_header, int n_threads,
                               char **text_out, size_t *text_len);
+/* The same text produced on the GPU from the rows kssd_dist_stats left on the device (the rows never travel: the host
+ * receives distance.out's bytes).  "%.6lf" and "%E" are evaluated with integer arithmetic that reproduces glibc's
+ * correctly rounded output (csrc/fmt_exact.cuh); a value that arithmetic cannot decide (within 2^-47 of a rounding tie,
+ * |x| >= 2^40 under "%.6lf") sends the whole call through kssd_format_distance_rows instead, so the bytes are the same
+ * either way.  Names as above: n_qry and n_ref records of `name_stride` bytes.  Free the text with kssd_host_free. */
+int kssd_dist_format_text(kssd_dist_t *d, const char *qry_names, const char *ref_names, size_t name_stride, int metric,
+                          int outfields, int with_header, char **text_out, size_t *text_len);
+/* ... into pinned host memory owned by the context (one DMA at link speed, no allocation once the buffer has grown):
+ * *text stays valid until the next kssd_dist_text call on this context or kssd_ctx_destroy; do not free it. */
+int kssd_dist_text(kssd_dist_t *d, const char *qry_names, const char *ref_names, size_t name_stride, int metric,
+                   int outfields, int with_header, const char **text, size_t *text_len);
+/* ... and for rows that are on the host (they are copied to the device first): n_qry / n_ref = the number of name records */
+int kssd_format_distance_rows_gpu(kssd_ctx_t *ctx, const kssd_stat_row_t *rows, size_t n_rows, int n_qry, int n_ref,
+                                  const char *qry_names, const char *ref_names, size_t name_stride, int metric,
+                                  int outfields, int with_header, char **text_out, size_t *text_len);
+/* diagnostic, host only: the integer formatter against snprintf("%.6lf") / snprintf("%E") on 5 n + 25 values; returns
+ * the number of differing strings (0 expected), *handed_back (may be NULL) = values the formatter declined. */
+int64_t kssd_format_selftest(uint64_t n, uint64_t seed, uint64_t *handed_back);
 void kssd_host_free(void *p);
 
 /* ------------------------------------------------------------------------------------------ *
@@ -322,7 +340,7 @@ int kssd_composite_host(kssd_ctx_t *ctx, int n_comp, const kssd_index_t *const *
 
 /* device time (ms, CUDA events on the context stream) of the last scan / index / count / stats
  * kernel sequence issued through this context; which = 0 sketch scan, 1 sketch total,
- * 2 index build, 3 dist counts, 4 dist stats */
+ * 2 index build, 3 dist counts, 4 dist stats, 5 distance.out text kernels */
 float kssd_ctx_last_ms(const kssd_ctx_t *ctx, int which);
 
 #ifdef __cplusplus

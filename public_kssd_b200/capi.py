@@ -28,7 +28,7 @@ SYMBOLS = [
     "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
     "kssd_dist_counts_dev", "kssd_dist_create_sparse", "kssd_dist_sparse_add_dev", "kssd_dist_sparse_add_host", "kssd_dist_accumulate_peer", "kssd_dev_alloc", "kssd_dev_zero", "kssd_dev_free",
     "kssd_ipc_export", "kssd_ipc_open", "kssd_ipc_close", "kssd_dist_stats", "kssd_dist_stats_async", "kssd_dist_stats_wait", "kssd_dist_fetch_stats", "kssd_dist_free",
-    "kssd_format_distance_rows", "kssd_host_free",
+    "kssd_format_distance_rows", "kssd_dist_format_text", "kssd_dist_text", "kssd_format_distance_rows_gpu", "kssd_format_selftest", "kssd_host_free",
     "kssd_set_union_host", "kssd_set_union_dev", "kssd_set_operate_host", "kssd_set_operate_dev", "kssd_set_group_host",
     "kssd_composite_host",
 ]
@@ -75,7 +75,7 @@ _lib = None
 def build_library(force: bool = False) -> Path:
     """nvcc-compile the library in-tree for sm_100a (cross-compiles without a GPU)."""
     src = PKG_DIR / "csrc"
-    newest = max(p.stat().st_mtime for p in list(src.glob("*.cu")) + list(src.glob("*.cuh")) + [PKG_DIR.parent / "include" / "kssd_b200.h"])
+    newest = max(p.stat().st_mtime for p in list(src.glob("*.cu")) + list(src.glob("*.cuh")) + list(src.glob("*.inc")) + [PKG_DIR.parent / "include" / "kssd_b200.h"])
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
         r = subprocess.run(["make", "-C", str(src)], capture_output=True, text=True)
         if r.returncode != 0:
@@ -88,7 +88,7 @@ def sources_digest() -> str:
     import hashlib
     src = PKG_DIR / "csrc"
     h = hashlib.sha256()
-    for f in sorted(list(src.glob("*.cu")) + list(src.glob("*.cuh")) + [src / "Makefile", PKG_DIR.parent / "include" / "kssd_b200.h"]):
+    for f in sorted(list(src.glob("*.cu")) + list(src.glob("*.cuh")) + list(src.glob("*.inc")) + [src / "Makefile", PKG_DIR.parent / "include" / "kssd_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
     return h.hexdigest()[:16]
@@ -99,7 +99,7 @@ def library_provenance() -> dict:
     source it was built from (build() rebuilds it otherwise)."""
     import hashlib
     src = PKG_DIR / "csrc"
-    newest = max(p.stat().st_mtime for p in list(src.glob("*.cu")) + list(src.glob("*.cuh")) + [PKG_DIR.parent / "include" / "kssd_b200.h"])
+    newest = max(p.stat().st_mtime for p in list(src.glob("*.cu")) + list(src.glob("*.cuh")) + list(src.glob("*.inc")) + [PKG_DIR.parent / "include" / "kssd_b200.h"])
     st = LIB_PATH.stat()
     return {"path": str(LIB_PATH.relative_to(PKG_DIR.parent)), "sha256_16": hashlib.sha256(LIB_PATH.read_bytes()).hexdigest()[:16], "bytes": st.st_size,
             "built_unix": int(st.st_mtime), "newer_than_sources": bool(st.st_mtime >= newest), "sources_sha256_16": sources_digest(),
@@ -185,6 +185,12 @@ def lib() -> C.CDLL:
     L.kssd_dist_free.restype = None
     L.kssd_format_distance_rows.argtypes = [vp, C.c_size_t, C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.kssd_dist_format_text.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.kssd_dist_text.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.kssd_format_distance_rows_gpu.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                                C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.kssd_format_selftest.argtypes = [C.c_uint64, C.c_uint64, u64p]
+    L.kssd_format_selftest.restype = C.c_int64
     L.kssd_set_union_host.argtypes = [vp, u32p, C.c_uint64, C.c_int, u32p, u64p]
     L.kssd_set_union_dev.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, C.c_uint64, u64p]
     L.kssd_set_operate_host.argtypes = [vp, u32p, u64p, C.c_int, u32p, C.c_uint64, C.c_int, u32p, u64p]

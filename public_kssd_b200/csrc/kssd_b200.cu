@@ -25,6 +25,7 @@
 #include "sketch_buckets.cuh"
 #include "set_ops.cuh"
 #include "composite.cuh"
+#include "dist_text.cuh"
 
 using namespace kssd;
 
@@ -123,8 +124,10 @@ struct kssd_ctx {
     bool plan_buckets = false;
     uint32_t plan_bucket_total = 0, plan_bucket_maxcap = 0;
     DevBuf bplan, bwork;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float last_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // [4], [5]: the distance.out text kernels
+    float last_ms[6] = {0, 0, 0, 0, 0, 0};
+    char *h_text = nullptr;                      // pinned: the text of kssd_dist_text (grow-only)
+    size_t h_text_cap = 0;
     bool stats_ms_pending = false;               // last_ms[4] of a sparse search: read off ev[2] .. ev[1] on demand
     bool total_ms_pending = false;               // last_ms[1] of a bucket-mode sketch: read off ev[0] .. ev[2] on demand
     // Sketch-size arrays of reference sets already on the device (Stage III): the reference's query-batch loop
@@ -310,6 +313,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
     for (auto &e : c->size_sets) cudaFree(e.dev);
     if (c->async_page) cudaFreeHost(c->async_page);
+    if (c->h_text) cudaFreeHost(c->h_text);
     for (cudaEvent_t e : c->async_events) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->async_counted) if (e) cudaEventDestroy(e);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -340,7 +344,7 @@ extern "C" int kssd_ctx_sync(const kssd_ctx_t *c)
 extern "C" float kssd_ctx_last_ms(const kssd_ctx_t *cc, int which)
 {
     kssd_ctx *c = const_cast<kssd_ctx *>(cc);
-    if (!c || which < 0 || which >= 5) return -1.f;
+    if (!c || which < 0 || which >= 6) return -1.f;
     if (which == 4 && c->stats_ms_pending) {
         cudaSetDevice(c->device);
         if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[2], c->ev[1]);
@@ -2267,6 +2271,178 @@ extern "C" int kssd_format_distance_rows(const kssd_stat_row_t *rows, size_t n_r
     *text_out = buf;
     *text_len = off;
     return KSSD_OK;
+}
+
+// distance.out straight from rows on the device: lengths, scan, lines (dist_text.cuh); the host only adds the header.
+// If the integer formatter handed a value back, the rows are fetched and formatted by kssd_format_distance_rows instead.
+// `pinned`: the text goes to the context's pinned buffer (*text_out points into it) instead of a malloc'd one.
+static int format_text_dev(kssd_ctx *c, const StatRow *d_rows, uint64_t n, int n_qry, int n_ref, const char *qry_names, const char *ref_names,
+                           size_t name_stride, int metric, int outfields, int with_header, bool pinned, char **text_out, size_t *text_len)
+{
+    std::string head;
+    if (with_header) {
+        head = "Qry\tRef\tShared_k|Ref_s|Qry_s";
+        for (int i = 0; i <= outfields; i++) { head += "\t"; head += kDistHeader[metric][i]; }
+        head += "\n";
+    }
+    uint64_t total = 0;
+    uint32_t handed[2] = {0, 0};
+    StreamScratch scr(c->stream);
+    char *d_text = nullptr;
+    if (n) {
+        const size_t qb = (size_t)n_qry * name_stride, rb = (size_t)n_ref * name_stride;
+        char *d_qn = static_cast<char *>(scr.alloc(qb)), *d_rn = static_cast<char *>(scr.alloc(rb));
+        uint16_t *d_ql = static_cast<uint16_t *>(scr.alloc((size_t)n_qry * 2)), *d_rl = static_cast<uint16_t *>(scr.alloc((size_t)n_ref * 2));
+        uint32_t *d_len = static_cast<uint32_t *>(scr.alloc((n + 1) * 4)), *d_handed = static_cast<uint32_t *>(scr.alloc(8));
+        uint64_t *d_off = static_cast<uint64_t *>(scr.alloc((n + 1) * 8));
+        if (!d_qn || !d_rn || !d_ql || !d_rl || !d_len || !d_handed || !d_off) return fail(KSSD_E_NOMEM, "distance.out text: out of device memory");
+        CU(cudaMemcpyAsync(d_qn, qry_names, qb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_rn, ref_names, rb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync(d_handed, 0, 8, c->stream));
+        CU(cudaMemsetAsync(d_len + n, 0, 4, c->stream));
+        CU(cudaEventRecord(c->ev[4], c->stream));
+        name_len_kernel<<<(uint32_t)((n_qry + 255) / 256), 256, 0, c->stream>>>(d_qn, name_stride, (uint32_t)n_qry, d_ql);
+        name_len_kernel<<<(uint32_t)((n_ref + 255) / 256), 256, 0, c->stream>>>(d_rn, name_stride, (uint32_t)n_ref, d_rl);
+        const uint32_t nb = (uint32_t)((n + kTextThreads - 1) / kTextThreads);
+        dist_text_len_kernel<<<nb, kTextThreads, 0, c->stream>>>(d_rows, n, (uint32_t)n_qry, (uint32_t)n_ref, d_ql, d_rl, outfields, d_len, d_handed);
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_len, d_off, n + 1, c->stream);
+        CU(c->cubtmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp, d_len, d_off, n + 1, c->stream));
+        CU(cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(handed, d_handed, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        LAUNCHED(5);
+        if (handed[1]) return fail(KSSD_E_INVAL, "distance.out text: a row names a query or reference outside the name lists");
+        if (handed[0] || getenv("KSSD_TEXT_ON_HOST")) {      // (env: tests of this branch)
+            std::vector<kssd_stat_row_t> rows(n);
+            CU(cudaMemcpyAsync(rows.data(), d_rows, n * sizeof(StatRow), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            char *t = nullptr;
+            size_t tl = 0;
+            const int rc = kssd_format_distance_rows(rows.data(), n, qry_names, ref_names, name_stride, metric, outfields, with_header, 0, &t, &tl);
+            if (rc || !pinned) { *text_out = t; *text_len = tl; return rc; }
+            if (tl + 1 > c->h_text_cap) {
+                if (c->h_text) cudaFreeHost(c->h_text);
+                c->h_text = nullptr; c->h_text_cap = 0;
+                if (cudaMallocHost(&c->h_text, tl + 1) != cudaSuccess) { free(t); return fail(KSSD_E_NOMEM, "distance.out text: out of pinned host memory"); }
+                c->h_text_cap = tl + 1;
+            }
+            memcpy(c->h_text, t, tl + 1);
+            free(t);
+            *text_out = c->h_text; *text_len = tl;
+            return KSSD_OK;
+        }
+        d_text = static_cast<char *>(scr.alloc(std::max<uint64_t>(total, 1)));
+        if (!d_text) return fail(KSSD_E_NOMEM, "distance.out text: out of device memory");
+        dist_text_write_kernel<<<nb, kTextThreads, 0, c->stream>>>(d_rows, n, d_qn, d_rn, name_stride, d_ql, d_rl, outfields, d_off, d_text);
+        LAUNCHED(1);
+        CU(cudaEventRecord(c->ev[5], c->stream));
+    }
+    const size_t need = head.size() + total + 1;
+    char *buf = nullptr;
+    if (pinned) {
+        if (need > c->h_text_cap) {
+            if (c->h_text) cudaFreeHost(c->h_text);
+            c->h_text = nullptr; c->h_text_cap = 0;
+            const size_t cap = need + need / 4;
+            if (cudaMallocHost(&c->h_text, cap) != cudaSuccess) return fail(KSSD_E_NOMEM, "distance.out text: out of pinned host memory");
+            c->h_text_cap = cap;
+        }
+        buf = c->h_text;
+    } else buf = (char *)malloc(need);
+    if (!buf) return fail(KSSD_E_NOMEM, "distance.out text: out of host memory");
+    memcpy(buf, head.data(), head.size());
+    if (total) {
+        const cudaError_t e = cudaMemcpyAsync(buf + head.size(), d_text, total, cudaMemcpyDeviceToHost, c->stream);
+        const cudaError_t e2 = e == cudaSuccess ? cudaStreamSynchronize(c->stream) : e;
+        if (e2 != cudaSuccess) { if (!pinned) free(buf); return fail(KSSD_E_CUDA, "distance.out text: %s", cudaGetErrorString(e2)); }
+        cudaEventElapsedTime(&c->last_ms[5], c->ev[4], c->ev[5]);
+    }
+    buf[head.size() + total] = 0;
+    *text_out = buf;
+    *text_len = head.size() + total;
+    return KSSD_OK;
+}
+
+extern "C" int kssd_dist_format_text(kssd_dist_t *d, const char *qry_names, const char *ref_names, size_t name_stride, int metric, int outfields,
+                                     int with_header, char **text_out, size_t *text_len)
+{
+    if (!d || !text_out || !text_len || metric < 0 || metric > 1 || outfields < 0 || outfields > 2 || name_stride == 0 || name_stride > 65535)
+        return fail(KSSD_E_INVAL, "kssd_dist_format_text: bad argument");
+    if (d->async_pending) return fail(KSSD_E_INVAL, "kssd_dist_format_text: call kssd_dist_stats_wait first");
+    if (d->n_rows && (!qry_names || !ref_names || !d->d_rows)) return fail(KSSD_E_INVAL, "kssd_dist_format_text: no rows (kssd_dist_stats first) or null names");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    return format_text_dev(c, d->d_rows, d->n_rows, d->n_qry, d->n_ref, qry_names, ref_names, name_stride, metric, outfields, with_header, false, text_out, text_len);
+}
+
+extern "C" int kssd_dist_text(kssd_dist_t *d, const char *qry_names, const char *ref_names, size_t name_stride, int metric, int outfields, int with_header,
+                              const char **text, size_t *text_len)
+{
+    if (!d || !text || !text_len || metric < 0 || metric > 1 || outfields < 0 || outfields > 2 || name_stride == 0 || name_stride > 65535)
+        return fail(KSSD_E_INVAL, "kssd_dist_text: bad argument");
+    if (d->async_pending) return fail(KSSD_E_INVAL, "kssd_dist_text: call kssd_dist_stats_wait first");
+    if (d->n_rows && (!qry_names || !ref_names || !d->d_rows)) return fail(KSSD_E_INVAL, "kssd_dist_text: no rows (kssd_dist_stats first) or null names");
+    kssd_ctx *c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    char *t = nullptr;
+    const int rc = format_text_dev(c, d->d_rows, d->n_rows, d->n_qry, d->n_ref, qry_names, ref_names, name_stride, metric, outfields, with_header, true, &t, text_len);
+    *text = t;
+    return rc;
+}
+
+extern "C" int kssd_format_distance_rows_gpu(kssd_ctx_t *c, const kssd_stat_row_t *rows, size_t n_rows, int n_qry, int n_ref, const char *qry_names,
+                                             const char *ref_names, size_t name_stride, int metric, int outfields, int with_header, char **text_out,
+                                             size_t *text_len)
+{
+    if (!c || !text_out || !text_len || metric < 0 || metric > 1 || outfields < 0 || outfields > 2 || name_stride == 0 || name_stride > 65535 || n_qry < 0 ||
+        n_ref < 0 || (n_rows && (!rows || !qry_names || !ref_names)))
+        return fail(KSSD_E_INVAL, "kssd_format_distance_rows_gpu: bad argument");
+    CU(cudaSetDevice(c->device));
+    StreamScratch scr(c->stream);
+    StatRow *d_rows = nullptr;
+    if (n_rows) {
+        d_rows = static_cast<StatRow *>(scr.alloc(n_rows * sizeof(StatRow)));
+        if (!d_rows) return fail(KSSD_E_NOMEM, "kssd_format_distance_rows_gpu: out of device memory");
+        CU(cudaMemcpyAsync(d_rows, rows, n_rows * sizeof(StatRow), cudaMemcpyHostToDevice, c->stream));
+    }
+    return format_text_dev(c, d_rows, n_rows, n_qry, n_ref, qry_names, ref_names, name_stride, metric, outfields, with_header, false, text_out, text_len);
+}
+
+// The integer formatter of fmt_exact.cuh against snprintf on the host: n values per family (any bit pattern, metric-like decimals,
+// dyadic fractions where exact ties live, e^-x), returns the number of differing strings; *handed_back counts the values
+// the formatter declined.  No GPU involved: the CPU test suite calls it.
+extern "C" int64_t kssd_format_selftest(uint64_t n, uint64_t seed, uint64_t *handed_back)
+{
+    uint64_t st = seed * 0x9e3779b97f4a7c15ull + 0x2545f4914f6cdd1dull, handed = 0;
+    auto next = [&]() -> uint64_t { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st * 0x2545f4914f6cdd1dull; };
+    int64_t bad = 0;
+    auto check = [&](double x) {
+        char a[64], b[64];
+        int l = fmt::put_f6(a, x);
+        if (l < 0) handed++;
+        else { a[l] = 0; snprintf(b, sizeof b, "%.6lf", x); bad += strcmp(a, b) != 0; }
+        l = fmt::put_e6(a, x);
+        if (l < 0) handed++;
+        else { a[l] = 0; snprintf(b, sizeof b, "%E", x); bad += strcmp(a, b) != 0; }
+    };
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t bits = next();
+        double x;
+        memcpy(&x, &bits, 8);
+        check(x);
+        check((double)(next() % 2000001) / 1000000.0 - 0.5);
+        check(ldexp((double)(next() >> 11), -(int)(next() % 120)));
+        check(((double)(next() % 20000000) + 0.5) / 8.0);
+        check(exp(-(double)(next() % 700000) / 1000.0));
+    }
+    const double special[] = {0.0, -0.0, 1.0, 0.5, 1e-7, 5e-7, 0.0000015, 0.0000025, 9.9999995, 999999.95, 9999999.5, 99999995.0, 1e22, 1e23, 5e-324,
+                              2.2250738585072014e-308, 1.7976931348623157e308, NAN, -NAN, INFINITY, -INFINITY, 1e12, 1099511627775.5, 8388608.5, 0.1};
+    for (double x : special) check(x);
+    if (handed_back) *handed_back = handed;
+    return bad;
 }
 
 extern "C" void kssd_host_free(void *p) { free(p); }

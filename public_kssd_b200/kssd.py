@@ -423,6 +423,32 @@ class DistJob:
         a single DMA at link speed)"""
         check(lib().kssd_dist_fetch_stats(self._h, C.c_void_p(host_ptr)))
 
+    def distance_out(self, qry_names, ref_names, metric: int = 0, outfields: int = 2, header: bool = True) -> bytes:
+        """distance.out of the last stats(fetch=False) / stats_wait(), formatted on the GPU (kssd_dist_format_text): header + one line
+        per row, byte-identical to dist_print_nobin / output_ctrl (command_dist.c:1188-1195, 1267-1285).  Names: lists of str, or the
+        256-byte name blocks of cofiles.stat / mcofiles.stat as bytes."""
+        from . import hostfmt
+        qn = qry_names if isinstance(qry_names, (bytes, bytearray)) else hostfmt._names_block(qry_names)
+        rn = ref_names if isinstance(ref_names, (bytes, bytearray)) else hostfmt._names_block(ref_names)
+        text, n = C.c_void_p(), C.c_size_t()
+        check(lib().kssd_dist_format_text(self._h, bytes(qn), bytes(rn), 256, metric, outfields, int(header), C.byref(text), C.byref(n)))
+        try:
+            return C.string_at(text, n.value)
+        finally:
+            lib().kssd_host_free(text)
+
+    def distance_out_view(self, qry_names, ref_names, metric: int = 0, outfields: int = 2, header: bool = True) -> memoryview:
+        """distance_out() without a copy: a view of the context's pinned text buffer (kssd_dist_text), valid until the next call on
+        this context -- write it to the file, or bytes() it."""
+        from . import hostfmt
+        qn = qry_names if isinstance(qry_names, (bytes, bytearray)) else hostfmt._names_block(qry_names)
+        rn = ref_names if isinstance(ref_names, (bytes, bytearray)) else hostfmt._names_block(ref_names)
+        text, n = C.c_void_p(), C.c_size_t()
+        check(lib().kssd_dist_text(self._h, bytes(qn), bytes(rn), 256, metric, outfields, int(header), C.byref(text), C.byref(n)))
+        if n.value == 0:
+            return memoryview(b"")
+        return memoryview((C.c_char * n.value).from_address(text.value)).cast("B")
+
     def stats_async(self, metric: int = 0, correction: int = 0, kmerlen: int | None = None, dim_rd_len: int | None = None,
                     dthreshold: float = 1.0, n_neighbors: int = 0, skip_zero: int = 0, cmprsn_num: int = 0):
         """Queue the whole sparse search (count + list + statistics) without waiting for the GPU; stats_wait() returns the row

@@ -142,6 +142,7 @@ def test_index_dist_match_reference_golden(gpu_ctx_l3k10):
         mine = hostfmt.distance_out_header(metric, outfields) + hostfmt.format_stat_rows(rows, qn, rn, metric, outfields)
         ref = g[f"distance_out.{tag}"].tobytes().decode()
         assert norm(mine) == norm(ref), tag
+        assert job.distance_out(qn, rn, metric, outfields).decode() == mine, tag          # the same text written by the GPU
     job.close(); ix.close()
 
 

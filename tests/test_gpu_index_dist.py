@@ -182,6 +182,11 @@ def test_sparse_job_rows_identical_to_dense(gpu_ctx_l3k10, opts):
     sp.accumulate(ix, qc, qi)
     got = sp.stats(**opts)
     assert len(want) > 0 and got.tobytes() == want.tobytes()
+    # distance.out written by the GPU from the rows on the device == the host formatter on the fetched rows
+    from public_kssd_b200 import hostfmt
+    qn, rn = [f"q{i}.fa" for i in range(len(qsz))], [f"dir/r{i}.fna" for i in range(len(rsz))]
+    assert sp.distance_out(qn, rn, opts.get("metric", 0), 2) == hostfmt.format_distance_out(got, qn, rn, opts.get("metric", 0), 2)
+    assert bytes(sp.distance_out_view(qn, rn, opts.get("metric", 0), 1)) == hostfmt.format_distance_out(got, qn, rn, opts.get("metric", 0), 1)
     assert np.array_equal(sp.counts(), dense.counts())          # counts on request: the matrix is built then
     dense.close(); sp.close(); ix.close()
 
