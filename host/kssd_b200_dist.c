@@ -291,17 +291,14 @@ static int cmd_dist(int argc, char **argv)
     kssd_stat_opts_t so = {metric, correction, mh.kmerlen, mh.dim_rd_len, dthr, nn, 0, 0};
     const int64_t nrows = kssd_dist_stats(job, &so);
     if (nrows < 0) die("kssd_dist_stats");
-    kssd_stat_row_t *rows = malloc(nrows > 0 ? (size_t)nrows * sizeof *rows : sizeof *rows);
-    if (kssd_dist_fetch_stats(job, rows)) die("kssd_dist_fetch_stats");
-    char *text;
+    const char *text;                                        /* written by the GPU into the context's pinned buffer: the rows stay on the device */
     size_t len;
-    if (kssd_format_distance_rows(rows, (size_t)nrows, q.names, ref_names, PATHLEN, metric, outfields, 1, 0, &text, &len)) die("kssd_format_distance_rows");
+    if (kssd_dist_text(job, q.names, ref_names, PATHLEN, metric, outfields, 1, &text, &len)) die("kssd_dist_text");
     spill(outdir, "distance.out", -1, "", text, len);                                                /* dist_print_nobin */
     printf("%d x %d pairs, %lld rows\n", q.h.infile_num, mh.infile_num, (long long)nrows);
-    kssd_host_free(text);
     kssd_dist_free(job);
     kssd_ctx_destroy(ctx);
-    free(rows); free(ct); free(mraw); free(q.raw);
+    free(ct); free(mraw); free(q.raw);
     return 0;
 }
 
