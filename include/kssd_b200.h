@@ -133,7 +133,12 @@ void kssd_sketch_free(kssd_sketch_t *s);
  * plain files straight into pinned staging memory and inflate .gz files with zlib; batches of about batch_bytes are
  * copied and sketched on the context stream while the readers fill the second staging buffer.  The result is what
  * kssd_sketch_fetch would give for all files in input order (combco.<c>, combco.index.<c>, combco.<c>.a).
- * n_threads <= 0: all hardware threads; batch_bytes 0: 1 GiB.  Modes: every KSSD_MODE_* but BYREAD. */
+ * n_threads <= 0: all hardware threads; batch_bytes 0: 1 GiB.  Modes: every KSSD_MODE_* but BYREAD.
+ * With 64 or more .gz files in the call (KSSD_GZ_GPU=1 / 0 forces / forbids it) the files are copied to the device as
+ * they are and inflated THERE, one file per thread (csrc/inflate.cuh; ISIZE and CRC-32 of every member checked): the
+ * compressed bytes cross PCIe and the host cores only read.  Batches are then sized by decoded bytes (8 GiB, or
+ * KSSD_GZ_BATCH_BYTES) and batch_bytes is ignored.  A file that does not decode into its ISIZE bytes (several gzip
+ * members, damage) sends the whole call through zlib on the host, which reports damage as before. */
 typedef struct kssd_stage1 kssd_stage1_t;
 int kssd_stage1_files(kssd_ctx_t *ctx, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts,
                       int n_threads, size_t batch_bytes, kssd_stage1_t **out);
@@ -145,6 +150,11 @@ int kssd_stage1_fetch(const kssd_stage1_t *s, int comp, uint32_t *ids, uint64_t 
 int kssd_stage1_status(const kssd_stage1_t *s, int32_t *status_out /* n_files */);
 /* average busy seconds per reader thread, seconds inside GPU calls, wall seconds, decoded bytes, batches */
 int kssd_stage1_timing(const kssd_stage1_t *s, double *read_s, double *gpu_s, double *total_s, uint64_t *bytes, int *batches);
+/* whether the .gz files were inflated on the GPU, and the seconds of H2D + inflate (part of gpu_s) */
+int kssd_stage1_gz_info(const kssd_stage1_t *s, int *on_gpu, double *gz_gpu_s);
+/* diagnostic, host only: the GPU's gzip decoder run on the host (0, or -1 header / -2 data / -3 output full /
+ * -4 truncated / -5 CRC / -6 ISIZE); the CPU test suite checks it against zlib */
+int kssd_gunzip_host(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
 void kssd_stage1_free(kssd_stage1_t *s);
 
 /* ------------------------------------------------------------------------------------------ *

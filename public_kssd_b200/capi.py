@@ -22,7 +22,7 @@ SYMBOLS = [
     "kssd_ctx_create", "kssd_ctx_destroy", "kssd_ctx_info", "kssd_ctx_stream", "kssd_ctx_sync", "kssd_ctx_last_ms",
     "kssd_sketch_batch_host", "kssd_sketch_batch_dev", "kssd_sketch_count", "kssd_sketch_status", "kssd_sketch_fetch",
     "kssd_sketch_dev_ptrs", "kssd_sketch_stats", "kssd_sketch_free", "kssd_sketch_read_counts", "kssd_sketch_fetch_read_index",
-    "kssd_stage1_files", "kssd_stage1_files_ex", "kssd_stage1_count", "kssd_stage1_fetch", "kssd_stage1_status", "kssd_stage1_timing", "kssd_stage1_free",
+    "kssd_stage1_files", "kssd_stage1_files_ex", "kssd_stage1_count", "kssd_stage1_fetch", "kssd_stage1_status", "kssd_stage1_timing", "kssd_stage1_gz_info", "kssd_gunzip_host", "kssd_stage1_free",
     "kssd_index_build_host", "kssd_index_build_dev", "kssd_index_sizes", "kssd_index_fetch", "kssd_index_fetch_dense",
     "kssd_index_from_dense_host", "kssd_index_free",
     "kssd_dist_create", "kssd_dist_create_ext", "kssd_dist_accumulate_host", "kssd_dist_accumulate_dev", "kssd_dist_fetch_counts",
@@ -143,6 +143,8 @@ def lib() -> C.CDLL:
     L.kssd_stage1_fetch.argtypes = [vp, C.c_int, u32p, u64p, u16p]
     L.kssd_stage1_status.argtypes = [vp, i32p]
     L.kssd_stage1_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    L.kssd_stage1_gz_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.kssd_gunzip_host.argtypes = [C.c_char_p, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.kssd_stage1_free.argtypes = [vp]
     L.kssd_stage1_free.restype = None
     L.kssd_sketch_dev_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]

@@ -115,6 +115,7 @@ struct kssd_ctx {
     DevBuf seq, meta, plan, keys, ords, keys2, ords2, flags, pos, runs, keep, counts, minord, cubtmp, misc;
     uint8_t *stag[2] = {nullptr, nullptr};       // pinned staging buffers of kssd_stage1_files
     uint64_t stag_cap[2] = {0, 0};
+    DevBuf gzin, gztext;                         // .gz batches decoded on the GPU: compressed bytes, decoded text (stage1_files.cuh)
     // cached span plan of the last batch layout
     bool plan_valid = false;
     uint64_t plan_key = 0;
@@ -308,7 +309,7 @@ extern "C" void kssd_ctx_destroy(kssd_ctx_t *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf *b : {&c->seq, &c->meta, &c->plan, &c->keys, &c->ords, &c->keys2, &c->ords2, &c->flags, &c->pos, &c->runs, &c->keep, &c->bplan, &c->bwork, &c->counts, &c->minord,
-                      &c->cubtmp, &c->misc})
+                      &c->cubtmp, &c->misc, &c->gzin, &c->gztext})
         b->release();
     for (int b = 0; b < 2; b++) if (c->stag[b]) cudaFreeHost(c->stag[b]);
     for (auto &e : c->size_sets) cudaFree(e.dev);

@@ -12,12 +12,17 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
+
 #include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
+
+#include "inflate.cuh"
 
 struct kssd_stage1 {
     int n_files = 0, n_comp = 1;
@@ -26,7 +31,8 @@ struct kssd_stage1 {
     std::vector<std::vector<uint64_t>> index;    // per component, n_files + 1
     std::vector<int32_t> status;                 // per file: 0 / KSSD_E_*
     std::vector<uint64_t> file_bytes;            // decoded size of every file
-    double read_s = 0, gpu_s = 0, total_s = 0;
+    double read_s = 0, gpu_s = 0, total_s = 0, gz_gpu_s = 0;      // gz_gpu_s: H2D of the compressed bytes + inflate on the GPU (part of gpu_s)
+    bool gz_on_gpu = false;
     uint64_t bytes = 0;
     int batches = 0;
 };
@@ -176,6 +182,186 @@ static bool inflate_file(const char *path, uint8_t **out, uint64_t *size)
     return true;
 }
 
+// the sketch of one batch appended to the call's result, files in batch order
+static int append_results(kssd_stage1 *R, kssd_sketch_t *sk, const std::vector<int> &files, int mode)
+{
+    const int nf = (int)files.size();
+    std::vector<uint64_t> ix(nf + 1);
+    int rc = KSSD_OK;
+    for (int cc = 0; cc < R->n_comp && rc == KSSD_OK; cc++) {
+        const int64_t n = kssd_sketch_count(sk, cc);
+        const size_t base = R->ids[cc].size();
+        R->ids[cc].resize(base + (size_t)n);
+        const bool ab = mode == KSSD_MODE_FASTQ_ABUND;
+        if (ab) R->abund[cc].resize(base + (size_t)n);
+        rc = kssd_sketch_fetch(sk, cc, n ? R->ids[cc].data() + base : nullptr, ix.data(), ab && n ? R->abund[cc].data() + base : nullptr, nullptr);
+        const uint64_t off = R->index[cc].back();
+        for (int f = 0; f < nf; f++) R->index[cc].push_back(off + ix[f + 1]);
+    }
+    std::vector<int32_t> stt(nf);
+    if (rc == KSSD_OK) rc = kssd_sketch_status(sk, stt.data());
+    for (int f = 0; f < nf; f++) R->status[files[f]] = stt[f];
+    return rc;
+}
+
+// ---- .gz decoded on the GPU (inflate.cuh) -------------------------------------------------------------------------------
+// The files of a batch are read as they are (compressed) into the pinned staging buffer and copied to the device; one thread per
+// file inflates into the batch's text buffer (every file's decoded size is its gzip ISIZE), plain files of the batch are copied
+// device to device, and the batch is sketched where it lies.  A batch is sized by DECODED bytes (8 GiB unless
+// KSSD_GZ_BATCH_BYTES says otherwise): the decoder's parallelism is the number of files in flight.  Any file the kernel cannot
+// finish in its ISIZE bytes (several gzip members, corrupt data, CRC mismatch) sets *fall_back: the caller redoes the call with
+// zlib on the host, which also produces the error message if the file is really broken.
+struct GzFile { bool gz = false; uint64_t csize = 0, dsize = 0; };
+
+static bool gz_isize(const char *path, uint64_t fsize, uint64_t *isize)
+{
+    if (fsize < 18) return false;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    unsigned char t[4];
+    const bool ok = pread(fd, t, 4, (off_t)(fsize - 4)) == 4;
+    close(fd);
+    *isize = (uint64_t)t[0] | ((uint64_t)t[1] << 8) | ((uint64_t)t[2] << 16) | ((uint64_t)t[3] << 24);
+    return ok;
+}
+
+static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts, int nt, const std::vector<GzFile> &F,
+                      kssd_stage1 *R, bool *fall_back)
+{
+    const int mode = opts ? opts->mode : KSSD_MODE_FASTA;
+    const char *eb = getenv("KSSD_GZ_BATCH_BYTES");
+    const uint64_t cap_dec = eb ? std::max<uint64_t>(strtoull(eb, nullptr, 10), 1u << 20) : (8ull << 30);
+    const bool check_crc = !getenv("KSSD_GZ_NOCRC");
+    std::vector<std::pair<int, int>> batches;
+    {
+        uint64_t acc = 0;
+        int lo = 0;
+        for (int i = 0; i < n_files; i++) {
+            const uint64_t need = (F[i].dsize + 15) & ~15ull;
+            if (i > lo && acc + need > cap_dec) { batches.push_back({lo, i}); lo = i; acc = 0; }
+            acc += need;
+        }
+        batches.push_back({lo, n_files});
+    }
+    auto staged = [&](int i) { return (F[i].csize + 31) & ~15ull; };      // >= 16 zero bytes behind every file
+    auto ensure_staging = [&](int b, uint64_t bytes) -> bool {
+        if (bytes <= c->stag_cap[b]) return true;
+        if (c->stag[b]) cudaFreeHost(c->stag[b]);
+        c->stag[b] = nullptr;
+        c->stag_cap[b] = 0;
+        if (cudaHostAlloc((void **)&c->stag[b], bytes, cudaHostAllocDefault) != cudaSuccess) return false;
+        c->stag_cap[b] = bytes;
+        return true;
+    };
+    double read_busy = 0;
+    std::mutex m;
+    // reads batch k into staging buffer k & 1 on nt threads; joined by the returned thread
+    std::vector<char> read_ok(batches.size(), 1);
+    auto start_read = [&](size_t k) -> std::thread {
+        return std::thread([&, k] {
+            const int lo = batches[k].first, hi = batches[k].second;
+            uint64_t bytes = 0;
+            std::vector<uint64_t> soff(hi - lo);
+            for (int i = lo; i < hi; i++) { soff[i - lo] = bytes; bytes += staged(i); }
+            if (!ensure_staging((int)(k & 1), bytes + 4096)) { read_ok[k] = 0; return; }
+            uint8_t *base = c->stag[k & 1];
+            std::atomic<int> next{lo};
+            std::atomic<bool> ok{true};
+            std::vector<std::thread> th;
+            const int workers = std::max(1, std::min(nt, hi - lo));
+            for (int w = 0; w < workers; w++)
+                th.emplace_back([&] {
+                    const auto t0 = clk::now();
+                    for (;;) {
+                        const int i = next.fetch_add(1);
+                        if (i >= hi) break;
+                        uint8_t *dst = base + soff[i - lo];
+                        if (!read_plain(paths[i], dst, F[i].csize)) ok = false;
+                        memset(dst + F[i].csize, 0, staged(i) - F[i].csize);
+                    }
+                    std::lock_guard<std::mutex> l(m);
+                    read_busy += secs(t0, clk::now());
+                });
+            for (auto &t : th) t.join();
+            if (!ok) read_ok[k] = 0;
+        });
+    };
+    std::thread rd = start_read(0);
+    for (size_t k = 0; k < batches.size(); k++) {
+        if (rd.joinable()) rd.join();
+        if (!read_ok[k]) return fail(KSSD_E_INVAL, "kssd_stage1_files: cannot read a file of batch %zu", k);
+        if (k + 1 < batches.size()) rd = start_read(k + 1);
+        struct Joiner { std::thread *t; bool armed; ~Joiner() { if (armed && t->joinable()) t->join(); } } joiner{&rd, k + 1 < batches.size()};
+        const auto t0 = clk::now();
+        const int lo = batches[k].first, hi = batches[k].second, n = hi - lo;
+        std::vector<uint64_t> soff(n), goff(n), glen(n);
+        uint64_t sbytes = 0, tbytes = 0;
+        for (int i = lo; i < hi; i++) {
+            soff[i - lo] = sbytes; sbytes += staged(i);
+            goff[i - lo] = tbytes; glen[i - lo] = F[i].dsize; tbytes += (F[i].dsize + 15) & ~15ull;
+        }
+        CU(c->gzin.ensure(sbytes + 64));
+        CU(c->gztext.ensure(tbytes + 1024));
+        uint8_t *d_in = c->gzin.as<uint8_t>(), *d_text = c->gztext.as<uint8_t>();
+        CU(cudaMemcpyAsync(d_in, c->stag[k & 1], sbytes, cudaMemcpyHostToDevice, c->stream));
+        std::vector<int> order;                           // gz files, largest first: the ticket order
+        for (int i = lo; i < hi; i++) {
+            if (F[i].gz) order.push_back(i);
+            else if (F[i].dsize) CU(cudaMemcpyAsync(d_text + goff[i - lo], d_in + soff[i - lo], F[i].dsize, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return F[a].csize != F[b].csize ? F[a].csize > F[b].csize : a < b; });
+        const uint32_t nj = (uint32_t)order.size();
+        std::vector<kssd::gz::Job> jobs(nj);
+        for (uint32_t j = 0; j < nj; j++) {
+            const int i = order[j];
+            jobs[j].in_off = soff[i - lo]; jobs[j].in_len = F[i].csize; jobs[j].out_off = goff[i - lo]; jobs[j].out_cap = F[i].dsize;
+        }
+        StreamScratch scr(c->stream);
+        std::vector<kssd::gz::Result> res(nj);
+        uint64_t *d_goff = static_cast<uint64_t *>(scr.alloc((size_t)n * 8)), *d_glen = static_cast<uint64_t *>(scr.alloc((size_t)n * 8));
+        if (!d_goff || !d_glen) return fail(KSSD_E_NOMEM, "kssd_stage1_files: out of device memory");
+        CU(cudaMemcpyAsync(d_goff, goff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_glen, glen.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        if (nj) {
+            kssd::gz::Job *d_jobs = static_cast<kssd::gz::Job *>(scr.alloc((size_t)nj * sizeof(kssd::gz::Job)));
+            kssd::gz::Result *d_res = static_cast<kssd::gz::Result *>(scr.alloc((size_t)nj * sizeof(kssd::gz::Result)));
+            uint32_t *d_ticket = static_cast<uint32_t *>(scr.alloc(4));
+            if (!d_jobs || !d_res || !d_ticket) return fail(KSSD_E_NOMEM, "kssd_stage1_files: out of device memory");
+            CU(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(kssd::gz::Job), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemsetAsync(d_ticket, 0, 4, c->stream));
+            // one file per warp while the SMs have room for the warps (32 CTAs each), then more lanes per warp
+            const uint32_t max_ctas = (uint32_t)c->sm_count * 32u;
+            const uint32_t active = std::min<uint32_t>(32u, (nj + max_ctas - 1) / max_ctas);
+            const uint32_t grid = std::min<uint32_t>(max_ctas, (nj + active - 1) / active);
+            const size_t smem = 1024 + (size_t)active * sizeof(kssd::gz::Tables);
+            CU(cudaFuncSetAttribute(kssd::gz::gunzip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kssd::gz::gunzip_kernel<<<grid, 32, smem, c->stream>>>(d_in, d_text, d_jobs, d_res, nj, active, d_ticket, check_crc ? 1 : 0);
+            LAUNCHED(1);
+            CU(cudaMemcpyAsync(res.data(), d_res, (size_t)nj * sizeof(kssd::gz::Result), cudaMemcpyDeviceToHost, c->stream));
+        }
+        kssd::gz::pad_text_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(d_text, d_goff, d_glen, (uint32_t)n);
+        LAUNCHED(1);
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        for (uint32_t j = 0; j < nj; j++)
+            if (res[j].status != kssd::gz::kOk || res[j].out_len != F[order[j]].dsize) { *fall_back = true; return KSSD_OK; }
+        R->gz_gpu_s += secs(t0, clk::now());
+        kssd_sketch_t *sk = nullptr;
+        int rc = kssd_sketch_batch_dev(c, d_text, tbytes, goff.data(), glen.data(), n, opts, &sk);
+        if (rc != KSSD_OK) return rc;
+        std::vector<int> files(n);
+        for (int i = 0; i < n; i++) files[i] = lo + i;
+        rc = append_results(R, sk, files, mode);
+        kssd_sketch_free(sk);
+        if (rc != KSSD_OK) return rc;
+        for (int i = lo; i < hi; i++) { R->file_bytes[i] = F[i].dsize; R->bytes += F[i].dsize; }
+        R->gpu_s += secs(t0, clk::now());
+        R->batches++;
+    }
+    R->read_s = read_busy / nt;
+    return KSSD_OK;
+}
+
 }  // namespace stage1
 
 extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int n_files, const kssd_sketch_opts_t *opts, int n_threads,
@@ -241,6 +427,40 @@ extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int
     R->status.assign(n_files, 0);
     R->file_bytes.assign(n_files, 0);
 
+    // enough .gz files to keep the GPU's decoder busy (or KSSD_GZ_GPU=1): compressed bytes cross PCIe, inflate runs on the device
+    {
+        int n_gz = 0;
+        for (int i = 0; i < n_files; i++) n_gz += tasks[i].gz ? 1 : 0;
+        const char *eg = getenv("KSSD_GZ_GPU");
+        bool use = !(pipecmd && pipecmd[0]) && n_gz > 0 && (eg ? atoi(eg) != 0 : n_gz >= 64);
+        std::vector<GzFile> F(n_files);
+        for (int i = 0; i < n_files && use; i++) {
+            struct stat st;
+            stat(paths[i], &st);
+            F[i].gz = tasks[i].gz;
+            F[i].csize = (uint64_t)st.st_size;
+            F[i].dsize = F[i].csize;
+            // (a compressed file much larger than its ISIZE: more than 4 GiB of text, or several members -- zlib's business)
+            if (F[i].gz && (!gz_isize(paths[i], F[i].csize, &F[i].dsize) || F[i].dsize > (1ull << 30) || F[i].csize > F[i].dsize + F[i].dsize / 1000 + 1024)) use = false;
+        }
+        if (use) {
+            bool fall_back = false;
+            const int rc = run_gz_gpu(c, paths, n_files, opts, nt, F, R, &fall_back);
+            if (rc != KSSD_OK) { delete R; return rc; }
+            if (!fall_back) {
+                R->gz_on_gpu = true;
+                R->total_s = secs(t_start, clk::now());
+                *out = R;
+                return KSSD_OK;
+            }
+            // some file did not decode into its ISIZE bytes: start over with zlib on the host
+            for (int cc = 0; cc < R->n_comp; cc++) { R->ids[cc].clear(); R->abund[cc].clear(); R->index[cc].assign(1, 0); }
+            R->status.assign(n_files, 0);
+            R->file_bytes.assign(n_files, 0);
+            R->bytes = 0; R->batches = 0; R->gpu_s = 0; R->read_s = 0; R->gz_gpu_s = 0;
+        }
+    }
+
     std::mutex m;
     std::condition_variable cv;
     uint64_t inflight_priv = 0;                       // bytes of inflated-but-unplaced data (back-pressure on the gz decoders)
@@ -270,21 +490,7 @@ extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int
                 kssd_sketch_t *sk = nullptr;
                 rc = kssd_sketch_batch_host(c, stag[b.staging], b.bytes, b.goff.data(), b.glen.data(), (int)b.files.size(), opts, &sk);
                 if (rc == KSSD_OK) {
-                    const int nf = (int)b.files.size();
-                    std::vector<uint64_t> ix(nf + 1);
-                    for (int cc = 0; cc < R->n_comp && rc == KSSD_OK; cc++) {
-                        const int64_t n = kssd_sketch_count(sk, cc);
-                        const size_t base = R->ids[cc].size();
-                        R->ids[cc].resize(base + (size_t)n);
-                        const bool ab = mode == KSSD_MODE_FASTQ_ABUND;
-                        if (ab) R->abund[cc].resize(base + (size_t)n);
-                        rc = kssd_sketch_fetch(sk, cc, n ? R->ids[cc].data() + base : nullptr, ix.data(), ab && n ? R->abund[cc].data() + base : nullptr, nullptr);
-                        const uint64_t off = R->index[cc].back();
-                        for (int f = 0; f < nf; f++) R->index[cc].push_back(off + ix[f + 1]);
-                    }
-                    std::vector<int32_t> stt(nf);
-                    if (rc == KSSD_OK) rc = kssd_sketch_status(sk, stt.data());
-                    for (int f = 0; f < nf; f++) R->status[b.files[f]] = stt[f];
+                    rc = append_results(R, sk, b.files, mode);
                     kssd_sketch_free(sk);
                 }
                 if (rc != KSSD_OK) gpu_err = kssd_last_error();
@@ -457,6 +663,28 @@ extern "C" int kssd_stage1_timing(const kssd_stage1_t *s, double *read_s, double
     if (bytes) *bytes = s->bytes;
     if (batches) *batches = s->batches;
     return KSSD_OK;
+}
+
+extern "C" int kssd_stage1_gz_info(const kssd_stage1_t *s, int *on_gpu, double *gz_gpu_s)
+{
+    if (!s) return fail(KSSD_E_INVAL, "kssd_stage1_gz_info: null");
+    if (on_gpu) *on_gpu = s->gz_on_gpu ? 1 : 0;
+    if (gz_gpu_s) *gz_gpu_s = s->gz_gpu_s;
+    return KSSD_OK;
+}
+
+// the GPU's gzip decoder (inflate.cuh) run on the host, for the CPU test suite: 0 or one of its negative codes
+extern "C" int kssd_gunzip_host(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len)
+{
+    if (!in || !out_len || (cap && !out)) return fail(KSSD_E_INVAL, "kssd_gunzip_host: null");
+    static uint32_t crc_tab[256];
+    static std::once_flag once;
+    std::call_once(once, [] { kssd::gz::crc32_table(crc_tab, 0, 1); });
+    std::unique_ptr<kssd::gz::Tables> T(new kssd::gz::Tables);
+    uint64_t len = 0;
+    const int rc = kssd::gz::gunzip(in, n, out, cap, *T, crc_tab, &len);
+    *out_len = (size_t)len;
+    return rc;
 }
 
 extern "C" void kssd_stage1_free(kssd_stage1_t *s) { delete s; }

@@ -213,12 +213,15 @@ class Context:
             check(lib().kssd_stage1_status(h, ptr(status, C.c_int32)))
             rs, gs, ts, nb, nbat = C.c_double(), C.c_double(), C.c_double(), C.c_uint64(), C.c_int()
             check(lib().kssd_stage1_timing(h, C.byref(rs), C.byref(gs), C.byref(ts), C.byref(nb), C.byref(nbat)))
+            gz_gpu, gz_s = C.c_int(), C.c_double()
+            check(lib().kssd_stage1_gz_info(h, C.byref(gz_gpu), C.byref(gz_s)))
         finally:
             lib().kssd_stage1_free(h)
         sk = Sketch(ids, index, abund, [None] * self.component_num, status, 0, 0.0, 0.0)
         if strict:
             self._raise_status(sk)
-        return sk, dict(read_s=rs.value, gpu_s=gs.value, total_s=ts.value, bytes=int(nb.value), batches=int(nbat.value))
+        return sk, dict(read_s=rs.value, gpu_s=gs.value, total_s=ts.value, bytes=int(nb.value), batches=int(nbat.value),
+                        gz_on_gpu=bool(gz_gpu.value), gz_gpu_s=gz_s.value)
 
     def reads2mco(self, files: Sequence[bytes | np.ndarray], strict: bool = True):
         """`kssd dist --byread` (reference reads2mco, iseq2comem.c:78-186) for every file of FASTA-formatted reads in the

@@ -107,3 +107,70 @@ def test_unreadable_file_fails_loudly(gpu_ctx_l3k10, tmp_path):
             gpu_ctx_l3k10.sketch_files(order, batch_bytes=150_000)
     sk, _ = gpu_ctx_l3k10.sketch_files([good, good])          # the context is still usable
     assert len(sk.ids[0]) > 0
+
+
+def _many_fasta(n_files, seed):
+    files = {}
+    for i in range(n_files):
+        src = synth.random_bases(20_000 + 3_000 * (i % 7), seed + i)
+        half = src.size // 2
+        files[f"g{i:03d}"] = np.concatenate([synth.to_fasta(src[:half], f"contig_{i}_a", width=60 if i % 2 else 80),
+                                             synth.to_fasta(src[half:], f"contig_{i}_b", width=70)])
+    return files
+
+
+def test_gz_inflated_on_the_gpu(gpu_ctx_l3k10, tmp_path, monkeypatch):
+    """.gz files copied to the device as they are and inflated there (csrc/inflate.cuh, one file per thread): same sketch as zlib on
+    the host and as the batch API on the decoded bytes; plain files may sit in the same batch; 70 files switch it on by themselves;
+    small batches (KSSD_GZ_BATCH_BYTES); a two-member file and a damaged one go through the host path (which reports the damage)."""
+    from public_kssd_b200 import kssd
+    files = _many_fasta(70, 100)
+    files["zz_empty"] = np.frombuffer(b"", dtype=np.uint8)
+    names = sorted(files)
+    paths = []
+    for i, n in enumerate(names):
+        raw = files[n].tobytes()
+        if i % 9 == 4:
+            p = tmp_path / f"{n}.fa"
+            p.write_bytes(raw)
+        else:
+            p = tmp_path / f"{n}.fa.gz"
+            with gzip.open(p, "wb", compresslevel=[1, 6, 9][i % 3]) as f:
+                f.write(raw)
+        paths.append(p)
+    want = gpu_ctx_l3k10.sketch([files[n] for n in names])
+    monkeypatch.setenv("KSSD_GZ_GPU", "0")
+    host, th = gpu_ctx_l3k10.sketch_files(paths, threads=4)
+    assert not th["gz_on_gpu"]
+    monkeypatch.delenv("KSSD_GZ_GPU")
+    for batch in (None, "1048576"):
+        if batch:
+            monkeypatch.setenv("KSSD_GZ_BATCH_BYTES", batch)
+        sk, t = gpu_ctx_l3k10.sketch_files(paths, threads=4)
+        assert t["gz_on_gpu"] and t["bytes"] == sum(v.size for v in files.values()) and (t["batches"] == 1 if not batch else t["batches"] >= 3)
+        for got in (sk, host):
+            assert np.array_equal(got.index[0], want.index[0]) and np.array_equal(got.ids[0], want.ids[0])
+    monkeypatch.delenv("KSSD_GZ_BATCH_BYTES")
+    # forced on for a handful of files
+    monkeypatch.setenv("KSSD_GZ_GPU", "1")
+    few = [p for p in paths if p.suffix == ".gz"][:5]
+    sk5, t5 = gpu_ctx_l3k10.sketch_files(few, threads=2)
+    assert t5["gz_on_gpu"]
+    idx = [paths.index(p) for p in few]
+    for j, i in enumerate(idx):
+        assert np.array_equal(sk5.ids[0][int(sk5.index[0][j]):int(sk5.index[0][j + 1])], want.ids[0][int(want.index[0][i]):int(want.index[0][i + 1])])
+    # two gzip members in one file: ISIZE is the last member's -> the call falls back to zlib, same result as the decoded bytes
+    two = tmp_path / "two_members.fa.gz"
+    a, b = files[names[0]].tobytes(), files[names[1]].tobytes()
+    two.write_bytes(gzip.compress(a, 6) + gzip.compress(b, 1))
+    sk2, t2 = gpu_ctx_l3k10.sketch_files([two] + few, threads=2)
+    assert not t2["gz_on_gpu"]
+    w2 = gpu_ctx_l3k10.sketch([np.frombuffer(a + b, dtype=np.uint8)])
+    assert np.array_equal(sk2.ids[0][:int(sk2.index[0][1])], w2.ids[0])
+    # damage inside the stream: an error either way, never a sketch of garbage
+    dmg = bytearray(few[0].read_bytes())
+    dmg[len(dmg) // 2] ^= 0x5a
+    bad = tmp_path / "damaged.fa.gz"
+    bad.write_bytes(bytes(dmg))
+    with pytest.raises(kssd.KssdError):
+        gpu_ctx_l3k10.sketch_files([bad] + few, threads=2)
