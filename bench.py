@@ -216,10 +216,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the reference arm: the unmodified CPU kssd on the box's host cores
 # ------------------------------------------------------------------------------------------------
-def files_leg(ctx, host_np, goff, glen, genome_len, ids_e2e, ix_e2e, n_plain=200, n_gz=400):
+def files_leg(ctx, host_np, goff, glen, genome_len, ids_e2e, ix_e2e, n_plain=200, n_gz=1000):
     """End to end the way a user runs it: Stage I from FILES (kssd_stage1_files: host threads read into pinned staging, H2D, scan,
     results back).  Plain FASTA and gzip (level 1, the format of the reference's own fixtures) on tmpfs; gzip twice: inflated by
-    zlib on the host cores (KSSD_GZ_GPU=0) and inflated on the GPU, one file per thread (the library's choice from 64 files on).
+    zlib on the host cores (KSSD_GZ_GPU=0) and inflated on the GPU, one file per thread (the library's choice from 640 files on).
     The ids must equal the resident path's."""
     import zlib
     from concurrent.futures import ThreadPoolExecutor

@@ -1,13 +1,21 @@
 // gzip / DEFLATE (RFC 1952 / 1951) decoding, one compressed file per thread -- what the reference gets from popen("zcat -fc")
 // (iseq2comem.c:187-200, :283-290).  A batch of Stage I is hundreds of independent .gz genomes: decoding them on the GPU lets the
 // compressed bytes cross PCIe (3-4x fewer) and takes inflate off the host cores.  A single stream is serial (every symbol's
-// position depends on the one before), so the parallelism is over files; `stage1_files.cuh` picks this path when a batch holds
-// enough of them and leaves large single files to zlib on the host.
+// position depends on the one before), so the parallelism is over files; `stage1_files.cuh` picks this path when a call holds
+// enough of them and leaves the others to zlib on the host.
 //
-// Decoder: 64-bit bit buffer refilled by bytes; literal/length codes through a 10-bit lookup table (codes of DNA text are 2-9 bits),
-// distance codes through an 8-bit one, longer codes by the canonical count/symbol walk; tables live in memory the caller provides
-// (shared memory on the GPU).  Members are decoded one after another (multi-member files, `cat a.gz b.gz`); every member's ISIZE and
-// CRC-32 are checked.  The same code compiles for the host, where the CPU test suite runs it against zlib.
+// What one thread does per symbol is therefore what counts:
+//   * the bit buffer (64 bits) is refilled 32 bits at a time from aligned words, the next word requested one refill ahead;
+//   * literal/length codes go through an 11-bit table whose entries hold up to TWO literals, or a length code's base and
+//     extra-bit count; distance codes through an 8-bit table of base / extra bits; longer codes by the canonical count/symbol walk;
+//   * the last 8 KiB of output are mirrored in a ring next to the tables (shared memory): `gzip -1` codes random DNA as nothing
+//     but 3-6 byte matches a few dozen bytes back, and a match served from the ring costs a shared-memory read instead of an L2
+//     round trip that the in-order thread would have to sit out; farther matches read the output itself;
+//   * output bytes are collected in a register and stored eight at a time;
+//   * offsets inside a file are 32-bit (a file decodes to < 4 GiB here; the caller sends larger ones to zlib).
+// Tables live in memory the caller provides (shared memory on the GPU).  Members are decoded one after another (multi-member
+// files, `cat a.gz b.gz`); every member's ISIZE and CRC-32 (slicing-by-8) are checked.  The same code compiles for the host, where
+// the CPU test suite runs it against zlib.  The input must be readable kInPad bytes past its end (zeros), the output 8-byte aligned.
 #pragma once
 #include <cstdint>
 
@@ -22,34 +30,87 @@ namespace gz {
 
 enum : int { kOk = 0, kBadHeader = -1, kBadData = -2, kOutputFull = -3, kTruncated = -4, kBadCrc = -5, kBadSize = -6 };
 
-constexpr int kLRoot = 10, kDRoot = 8;
+constexpr int kLRoot = 11, kDRoot = 8;
+constexpr uint32_t kInPad = 16;       // readable zero bytes behind the compressed data
 
+static const uint32_t h_crc8[2048] = {
+#include "crc32_slice8.inc"
+};
+#ifdef __CUDACC__
+__device__ const uint32_t d_crc8[2048] = {
+#include "crc32_slice8.inc"
+};
+#endif
+
+constexpr uint32_t kWin = 8192;       // bytes of output mirrored in the ring
+
+// build() leaves symbol | code length << 16 in an entry (0: the code is longer than the root -> canonical walk); then
+//   literal/length table: literals   lit0 | lit1 << 8 | bits consumed << 16 | n << 24 (n = 1, 2)
+//                         length     base | extra-bit count << 9 | code length << 16 | kLen
+//                         end of block                              code length << 16 | kEob      (symbols 286, 287: kBad)
+//   distance table:       base | extra-bit count << 15 | code length << 19                        (symbols 30, 31: kBad)
+constexpr uint32_t kLen = 1u << 31, kEob = 1u << 30, kBad = 1u << 29;
 struct Tables {
-    uint16_t lfast[1 << kLRoot];      // (symbol << 4) | length, 0 = longer than the root
-    uint16_t dfast[1 << kDRoot];
+    uint32_t lfast[1 << kLRoot];
+    uint32_t dfast[1 << kDRoot];
     uint16_t lcount[16], dcount[16];  // canonical walk: codes per length, symbols in code order
     uint16_t lsym[288], dsym[32];
+    uint8_t win[kWin];
 };
+
+#define KSSD_GZ_CONST_TABLES(Q)                                                                                                                      \
+    Q const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258}; \
+    Q const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};                              \
+    Q const uint16_t dbase[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,                               \
+                                  193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};                            \
+    Q const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+namespace host_tab { KSSD_GZ_CONST_TABLES(static) }
+#ifdef __CUDACC__
+namespace dev_tab { KSSD_GZ_CONST_TABLES(__device__) }
+#endif
+#ifdef __CUDA_ARCH__
+namespace tab = dev_tab;
+#else
+namespace tab = host_tab;
+#endif
 
 struct Bits {
-    const uint8_t *p;
-    uint64_t pos, end;
+    const uint32_t *wp, *wend;        // next aligned word to request; first word that is not inside the padded input (zeros from there on)
+    uint32_t nextw;                   // the word requested last (not in bb yet)
     uint64_t bb;
     int bc;
+    uint64_t loaded;                  // bytes of the file that went into bb so far (position = loaded - bc / 8)
 };
 
-KGZ void refill(Bits &b)
+KGZ void bits_open(Bits &b, const uint8_t *in, uint64_t pos, uint64_t n)
 {
-    while (b.bc <= 56) {
-        const uint64_t byte = b.pos < b.end ? b.p[b.pos] : 0u;      // zeros past the end; the caller checks pos against end
-        b.pos++;
-        b.bb |= byte << b.bc;
+    b.wend = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(in + n + kInPad) & ~(uintptr_t)3);
+    b.bb = 0;
+    b.bc = 0;
+    b.loaded = pos;
+    while ((reinterpret_cast<uintptr_t>(in + b.loaded) & 3u) != 0) {
+        b.bb |= (uint64_t)in[b.loaded] << b.bc;
         b.bc += 8;
+        b.loaded++;
+    }
+    b.wp = reinterpret_cast<const uint32_t *>(in + b.loaded);
+    b.nextw = b.wp < b.wend ? *b.wp : 0u;
+    b.wp++;
+}
+KGZ void refill(Bits &b)                                  // afterwards bc > 32
+{
+    if (b.bc <= 32) {
+        b.bb |= (uint64_t)b.nextw << b.bc;
+        b.bc += 32;
+        b.loaded += 4;
+        b.nextw = b.wp < b.wend ? *b.wp : 0u;      // (a damaged stream that runs past the end reads zeros until its output is full)
+        b.wp++;
     }
 }
-KGZ uint32_t take(Bits &b, int n)      // n <= 32, bits are there
+KGZ uint64_t bits_pos(const Bits &b) { return b.loaded - (uint64_t)(b.bc >> 3); }      // first byte not consumed whole
+KGZ uint32_t take(Bits &b, int n)                         // n <= 16, bits are there
 {
-    const uint32_t v = (uint32_t)(b.bb & ((1ull << n) - 1ull));
+    const uint32_t v = (uint32_t)b.bb & ((1u << n) - 1u);
     b.bb >>= n;
     b.bc -= n;
     return v;
@@ -62,9 +123,10 @@ KGZ uint32_t reverse_bits(uint32_t v, int n)
     return r;
 }
 
-// canonical Huffman tables from code lengths; false: over-subscribed, or incomplete with more than one code (the fixed distance
-// code of RFC 1951 3.2.6 is incomplete by definition: `fixed`)
-KGZ bool build(const uint8_t *len, int n, uint16_t *count, uint16_t *sym, uint16_t *fast, int root, bool fixed = false)
+// canonical Huffman code from code lengths: count / sym for the walk, and for every code of at most `root` bits the entries
+// fast[reversed code + k * 2^len] = symbol | len << 16.  false: over-subscribed, or incomplete with more than one code (the fixed
+// distance code of RFC 1951 3.2.6 is incomplete by definition: `fixed`).
+KGZ bool build(const uint8_t *len, int n, uint16_t *count, uint16_t *sym, uint32_t *fast, int root, bool fixed)
 {
     for (int i = 0; i < 16; i++) count[i] = 0;
     for (int i = 0; i < n; i++) count[len[i]]++;
@@ -82,34 +144,55 @@ KGZ bool build(const uint8_t *len, int n, uint16_t *count, uint16_t *sym, uint16
     for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
     uint32_t code = 0;
     next[0] = 0;
-    for (int l = 1; l < 16; l++) {
-        code = (code + count[l - 1]) << 1;
-        if (l == 1) code = 0;
+    for (int l = 1; l < 16; l++) {                        // first code of length l
+        code = l == 1 ? 0u : (code + count[l - 1]) << 1;
         next[l] = (uint16_t)code;
     }
-    // (next[l] = first code of length l: code_1 = 0, code_l = (code_{l-1} + count_{l-1}) << 1)
     for (int s = 0; s < n; s++) {
         const int l = len[s];
         if (!l) continue;
         sym[offs[l]++] = (uint16_t)s;
         const uint32_t c = next[l]++;
         if (l <= root) {
-            const uint32_t r = reverse_bits(c, l);
-            for (uint32_t k = r; k < (1u << root); k += 1u << l) fast[k] = (uint16_t)((s << 4) | l);
+            const uint32_t e = (uint32_t)s | ((uint32_t)l << 16);
+            for (uint32_t k = reverse_bits(c, l); k < (1u << root); k += 1u << l) fast[k] = e;
         }
     }
     return true;
 }
 
-// one symbol; -1: invalid code
-KGZ int decode(Bits &b, const uint16_t *fast, int root, const uint16_t *count, const uint16_t *sym)
+// literal/length table into its final form; two literals per entry where the bits of the index hold two whole literal codes
+// (descending: the entry read for the second literal is not converted yet)
+KGZ void finish_litlen(uint32_t *fast)
 {
-    const uint32_t e = fast[b.bb & ((1u << root) - 1u)];
-    if (e & 15u) {
-        b.bb >>= (e & 15u);
-        b.bc -= (int)(e & 15u);
-        return (int)(e >> 4);
+    for (int i = (1 << kLRoot) - 1; i >= 0; i--) {
+        const uint32_t e = fast[i], l1 = (e >> 16) & 31u, s1 = e & 0x1ffu;
+        if (l1 == 0) continue;
+        uint32_t f;
+        if (s1 < 256u) {
+            f = s1 | (l1 << 16) | (1u << 24);
+            if (l1 < (uint32_t)kLRoot) {
+                const uint32_t e2 = fast[i >> l1], l2 = (e2 >> 16) & 31u, s2 = e2 & 0x1ffu;
+                if ((e2 >> 24) == 0 && l2 != 0 && s2 < 256u && l1 + l2 <= (uint32_t)kLRoot) f = s1 | (s2 << 8) | ((l1 + l2) << 16) | (2u << 24);
+            }
+        } else if (s1 == 256u) f = (l1 << 16) | kEob;
+        else if (s1 < 286u) f = tab::lbase[s1 - 257u] | ((uint32_t)tab::lext[s1 - 257u] << 9) | (l1 << 16) | kLen;
+        else f = (l1 << 16) | kBad;
+        fast[i] = f;
     }
+}
+KGZ void finish_dist(uint32_t *fast)
+{
+    for (int i = 0; i < (1 << kDRoot); i++) {
+        const uint32_t e = fast[i], l = (e >> 16) & 31u, s = e & 0x1ffu;
+        if (l == 0) continue;
+        fast[i] = s < 30u ? tab::dbase[s] | ((uint32_t)tab::dext[s] << 15) | (l << 19) : kBad;
+    }
+}
+
+// a symbol by the canonical walk (any code length); -1: invalid code
+KGZ int decode_walk(Bits &b, const uint16_t *count, const uint16_t *sym)
+{
     int code = 0, first = 0, index = 0;
     uint64_t bits = b.bb;
     for (int l = 1; l <= 15; l++) {
@@ -128,45 +211,75 @@ KGZ int decode(Bits &b, const uint16_t *fast, int root, const uint16_t *count, c
     }
     return -1;
 }
-
-KGZ uint32_t crc32_bytes(const uint32_t *tab, uint32_t crc, const uint8_t *p, uint64_t n)      // tab: the 256-entry table of 0xEDB88320
+KGZ int decode_small(Bits &b, const uint32_t *fast, int root, const uint16_t *count, const uint16_t *sym)      // tables as build() leaves them
 {
-    crc = ~crc;
-    for (uint64_t i = 0; i < n; i++) crc = tab[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
-    return ~crc;
+    const uint32_t e = fast[(uint32_t)b.bb & ((1u << root) - 1u)], l = e >> 16;
+    if (l) {
+        b.bb >>= l;
+        b.bc -= (int)l;
+        return (int)(e & 0xffffu);
+    }
+    return decode_walk(b, count, sym);
 }
-KGZ void crc32_table(uint32_t *tab, int first, int step)
+
+// the output of one file: bytes are mirrored in the ring and collected in `acc` until eight can be stored at once
+struct Out {
+    uint8_t *base;                    // 8-byte aligned
+    uint32_t o;
+    uint64_t acc;                     // bytes [o & ~7, o)
+};
+KGZ void put(Out &w, uint8_t *win, uint32_t c)
 {
-    for (int i = first; i < 256; i += step) {
-        uint32_t c = (uint32_t)i;
-        for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-        tab[i] = c;
+    win[w.o & (kWin - 1u)] = (uint8_t)c;
+    w.acc |= (uint64_t)c << (8u * (w.o & 7u));
+    w.o++;
+    if ((w.o & 7u) == 0) {
+        *reinterpret_cast<uint64_t *>(w.base + (w.o - 8u)) = w.acc;
+        w.acc = 0;
     }
 }
-
-// one raw DEFLATE stream from b into out[o ..]; returns kOk with o advanced
-KGZ int inflate_stream(Bits &b, Tables &T, uint8_t *out, uint64_t &o, uint64_t cap)
+KGZ void flush_partial(const Out &w)                      // the bytes still in acc, bytewise (acc stays: the next put goes on)
 {
-    const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-    const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (uint32_t k = 0; k < (w.o & 7u); k++) w.base[(w.o & ~7u) + k] = (uint8_t)(w.acc >> (8u * k));
+}
+
+// CRC-32 of p[0 .. n), p + `skew` 8-byte aligned for some skew < 8 handled bytewise first; t: the slicing-by-8 tables
+KGZ uint32_t crc32_slice8(const uint32_t *t, const uint8_t *p, uint32_t n)
+{
+    uint32_t crc = 0xffffffffu, i = 0;
+    for (; i < n && (reinterpret_cast<uintptr_t>(p + i) & 7u); i++) crc = t[(crc ^ p[i]) & 255u] ^ (crc >> 8);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p + i);
+    for (; i + 8 <= n; i += 8, w += 2) {
+        const uint32_t lo = w[0] ^ crc, hi = w[1];
+        crc = t[7 * 256 + (lo & 255u)] ^ t[6 * 256 + ((lo >> 8) & 255u)] ^ t[5 * 256 + ((lo >> 16) & 255u)] ^ t[4 * 256 + (lo >> 24)] ^
+              t[3 * 256 + (hi & 255u)] ^ t[2 * 256 + ((hi >> 8) & 255u)] ^ t[1 * 256 + ((hi >> 16) & 255u)] ^ t[hi >> 24];
+    }
+    for (; i < n; i++) crc = t[(crc ^ p[i]) & 255u] ^ (crc >> 8);
+    return ~crc;
+}
+
+// one raw DEFLATE stream from b; returns kOk with w advanced.  `end`: size of the compressed file.
+KGZ int inflate_stream(Bits &b, uint64_t end, Tables &T, Out &w, uint32_t cap)
+{
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-    const uint64_t start = o;
+    const uint32_t start = w.o;
     for (;;) {
         refill(b);
         const uint32_t last = take(b, 1), type = take(b, 2);
         if (type == 0) {
             take(b, b.bc & 7);                            // to the byte boundary
             refill(b);
-            const uint32_t n = take(b, 16), nn = take(b, 16);
+            const uint32_t n = take(b, 16);
+            refill(b);
+            const uint32_t nn = take(b, 16);
             if ((n ^ 0xffffu) != nn) return kBadData;
-            if (o + n > cap) return kOutputFull;
+            if (n > cap - w.o) return kOutputFull;
             for (uint32_t i = 0; i < n; i++) {
-                if (b.bc < 8) refill(b);
-                out[o++] = (uint8_t)take(b, 8);
+                refill(b);
+                put(w, T.win, take(b, 8));
+                if ((i & 1023u) == 0 && bits_pos(b) > end) return kTruncated;
             }
-            if (b.pos - (uint64_t)(b.bc >> 3) > b.end) return kTruncated;
+            if (bits_pos(b) > end) return kTruncated;
         } else if (type == 1 || type == 2) {
             uint8_t lens[320];
             int nlen, ndist;
@@ -184,17 +297,16 @@ KGZ int inflate_stream(Bits &b, Tables &T, uint8_t *out, uint64_t &o, uint64_t c
                 if (nlen > 286 || ndist > 30) return kBadData;
                 uint8_t cl[19];
                 for (int i = 0; i < 19; i++) cl[i] = 0;
-                refill(b);
                 for (int i = 0; i < ncode; i++) {
-                    if (b.bc < 3) refill(b);
+                    refill(b);
                     cl[order[i]] = (uint8_t)take(b, 3);
                 }
                 // the code-length code goes through the distance tables' memory (7-bit codes, 19 symbols)
-                if (!build(cl, 19, T.dcount, T.dsym, T.dfast, 7)) return kBadData;
+                if (!build(cl, 19, T.dcount, T.dsym, T.dfast, 7, false)) return kBadData;
                 int i = 0;
                 while (i < nlen + ndist) {
                     refill(b);
-                    const int s = decode(b, T.dfast, 7, T.dcount, T.dsym);
+                    const int s = decode_small(b, T.dfast, 7, T.dcount, T.dsym);
                     if (s < 0) return kBadData;
                     if (s < 16) lens[i++] = (uint8_t)s;
                     else {
@@ -208,46 +320,90 @@ KGZ int inflate_stream(Bits &b, Tables &T, uint8_t *out, uint64_t &o, uint64_t c
                         if (i + rep > nlen + ndist) return kBadData;
                         while (rep--) lens[i++] = (uint8_t)v;
                     }
-                    if (b.pos > b.end + 8) return kTruncated;
                 }
+                if (bits_pos(b) > end) return kTruncated;
                 if (lens[256] == 0) return kBadData;      // no end-of-block code
             }
-            if (!build(lens, nlen, T.lcount, T.lsym, T.lfast, kLRoot)) return kBadData;
+            if (!build(lens, nlen, T.lcount, T.lsym, T.lfast, kLRoot, false)) return kBadData;
             if (!build(lens + nlen, ndist, T.dcount, T.dsym, T.dfast, kDRoot, type == 1)) return kBadData;
+            finish_litlen(T.lfast);
+            finish_dist(T.dfast);
+            uint32_t guard = 0;
             for (;;) {
-                if (b.bc < 48) refill(b);
-                const int s = decode(b, T.lfast, kLRoot, T.lcount, T.lsym);
-                if (s < 256) {
+                refill(b);                                // > 32 bits: a literal/length code and its extra bits (15 + 5)
+                uint32_t e = T.lfast[(uint32_t)b.bb & ((1u << kLRoot) - 1u)];
+                if (e == 0) {                             // a code longer than the root: the walk, then the entry the table would have held
+                    const int s = decode_walk(b, T.lcount, T.lsym);
                     if (s < 0) return kBadData;
-                    if (o >= cap) return kOutputFull;
-                    out[o++] = (uint8_t)s;
+                    if (s < 256) e = (uint32_t)s | (1u << 24);
+                    else if (s == 256) e = kEob;
+                    else if (s < 286) e = tab::lbase[s - 257] | ((uint32_t)tab::lext[s - 257] << 9) | kLen;
+                    else e = kBad;
+                } else {
+                    const uint32_t l = (e >> 16) & 31u;
+                    b.bb >>= l;
+                    b.bc -= (int)l;
+                }
+                if (e & kLen) {
+                    const uint32_t len = (e & 0x1ffu) + take(b, (int)((e >> 9) & 7u));
+                    refill(b);                            // a distance code and its extra bits (15 + 13)
+                    uint32_t d = T.dfast[(uint32_t)b.bb & ((1u << kDRoot) - 1u)];
+                    if (d == 0) {
+                        const int ds = decode_walk(b, T.dcount, T.dsym);
+                        if (ds < 0 || ds >= 30) return kBadData;
+                        d = tab::dbase[ds] | ((uint32_t)tab::dext[ds] << 15);
+                    } else {
+                        if (d & kBad) return kBadData;
+                        const uint32_t l = (d >> 19) & 15u;
+                        b.bb >>= l;
+                        b.bc -= (int)l;
+                    }
+                    const uint32_t dist = (d & 0x7fffu) + take(b, (int)((d >> 15) & 15u));
+                    if (dist > w.o - start) return kBadData;      // (a member never reaches back into the one before)
+                    if (len > cap - w.o) return kOutputFull;
+                    uint32_t i = 0;
+                    if (dist <= kWin) {                   // from the ring (read before the slot is rewritten when dist == kWin)
+                        if (dist >= 4u)
+                            for (; i + 4 <= len; i += 4) {
+                                const uint32_t p = w.o - dist;
+                                const uint32_t c0 = T.win[p & (kWin - 1u)], c1 = T.win[(p + 1u) & (kWin - 1u)], c2 = T.win[(p + 2u) & (kWin - 1u)],
+                                               c3 = T.win[(p + 3u) & (kWin - 1u)];
+                                put(w, T.win, c0); put(w, T.win, c1); put(w, T.win, c2); put(w, T.win, c3);
+                            }
+                        for (; i < len; i++) put(w, T.win, T.win[(w.o - dist) & (kWin - 1u)]);
+                    } else {                              // from the output itself: all of it is stored (dist > 8 KiB, len <= 258)
+                        for (; i + 4 <= len; i += 4) {
+                            const uint8_t *src = w.base + (w.o - dist);
+                            const uint32_t c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
+                            put(w, T.win, c0); put(w, T.win, c1); put(w, T.win, c2); put(w, T.win, c3);
+                        }
+                        for (; i < len; i++) put(w, T.win, w.base[w.o - dist]);
+                    }
+                    if ((++guard & 255u) == 0 && bits_pos(b) > end) return kTruncated;
                     continue;
                 }
-                if (s == 256) break;
-                const int li = s - 257;
-                if (li >= 29) return kBadData;
-                const uint32_t len = lbase[li] + take(b, lext[li]);
-                const int ds = decode(b, T.dfast, kDRoot, T.dcount, T.dsym);
-                if (ds < 0 || ds >= 30) return kBadData;
-                const uint64_t dist = dbase[ds] + take(b, dext[ds]);
-                if (dist > o - start) return kBadData;    // (a member never reaches back into the one before)
-                if (o + len > cap) return kOutputFull;
-                const uint8_t *src = out + o - dist;
-                uint8_t *dst = out + o;
-                for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
-                o += len;
-                if (b.pos > b.end + 8) return kTruncated;
+                const uint32_t nl = (e >> 24) & 3u;
+                if (nl) {                                 // one or two literals
+                    if (cap - w.o < nl) return kOutputFull;
+                    put(w, T.win, e & 0xffu);
+                    if (nl == 2u) put(w, T.win, (e >> 8) & 0xffu);
+                    continue;
+                }
+                if (e & kEob) break;
+                return kBadData;
             }
-            if (b.pos - (uint64_t)(b.bc >> 3) > b.end) return kTruncated;
+            if (bits_pos(b) > end) return kTruncated;
         } else return kBadData;
         if (last) return kOk;
     }
 }
 
-// a whole .gz file (one or more members) -> out; *out_len = decoded bytes
-KGZ int gunzip(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, Tables &T, const uint32_t *crc_tab, uint64_t *out_len)
+// a whole .gz file (one or more members) -> out; *out_len = decoded bytes.  in[n .. n + kInPad) must be readable.
+KGZ int gunzip(const uint8_t *in, uint64_t n, uint8_t *out, uint32_t cap, Tables &T, const uint32_t *crc_tab, uint32_t *out_len)
 {
-    uint64_t pos = 0, o = 0;
+    uint64_t pos = 0;
+    Out w;
+    w.base = out; w.o = 0; w.acc = 0;
     int members = 0;
     while (pos < n) {
         if (n - pos < 18 || in[pos] != 0x1f || in[pos + 1] != 0x8b || in[pos + 2] != 8) {
@@ -269,20 +425,21 @@ KGZ int gunzip(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, Tables
         if (flg & 2u) pos += 2;
         if (pos >= n) return kTruncated;
         Bits b;
-        b.p = in; b.pos = pos; b.end = n; b.bb = 0; b.bc = 0;
-        const uint64_t o0 = o;
-        const int rc = inflate_stream(b, T, out, o, cap);
+        bits_open(b, in, pos, n);
+        const uint32_t o0 = w.o;
+        const int rc = inflate_stream(b, n, T, w, cap);
         if (rc != kOk) return rc;
-        pos = b.pos - (uint64_t)(b.bc >> 3);              // bytes still whole in the bit buffer were not consumed
+        flush_partial(w);
+        pos = bits_pos(b);
         if (pos + 8 > n) return kTruncated;
         const uint32_t crc = (uint32_t)in[pos] | ((uint32_t)in[pos + 1] << 8) | ((uint32_t)in[pos + 2] << 16) | ((uint32_t)in[pos + 3] << 24);
         const uint32_t isz = (uint32_t)in[pos + 4] | ((uint32_t)in[pos + 5] << 8) | ((uint32_t)in[pos + 6] << 16) | ((uint32_t)in[pos + 7] << 24);
         pos += 8;
-        if ((uint32_t)(o - o0) != isz) return kBadSize;
-        if (crc_tab && crc32_bytes(crc_tab, 0, out + o0, o - o0) != crc) return kBadCrc;
+        if (w.o - o0 != isz) return kBadSize;
+        if (crc_tab && crc32_slice8(crc_tab, out + o0, w.o - o0) != crc) return kBadCrc;
         members++;
     }
-    *out_len = o;
+    *out_len = w.o;
     return members ? kOk : kBadHeader;
 }
 
@@ -292,22 +449,19 @@ struct Result { uint64_t out_len; int32_t status, pad; };
 #ifdef __CUDACC__
 // One file per thread, pulled by ticket (the host orders the jobs largest first).  A CTA is one warp of which the first
 // `active` lanes decode: a stream is latency-bound (table lookup -> shift -> next lookup), so a batch of a few hundred files is
-// spread one per warp over every SM, and only a batch of many thousands packs 32 files into a warp.  Tables in shared memory.
+// spread one per warp over every SM, and only a batch of many thousands packs several files into a warp.  Tables in shared memory.
 __global__ void __launch_bounds__(32) gunzip_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const Job *__restrict__ jobs,
                                                     Result *__restrict__ res, uint32_t n, uint32_t active, uint32_t *__restrict__ ticket, int check_crc)
 {
     extern __shared__ __align__(16) uint8_t gz_smem[];
-    uint32_t *crc_tab = reinterpret_cast<uint32_t *>(gz_smem);
-    crc32_table(crc_tab, (int)threadIdx.x, 32);
-    __syncwarp();
     if (threadIdx.x >= active) return;
-    Tables &T = *(reinterpret_cast<Tables *>(gz_smem + 1024) + threadIdx.x);
+    Tables &T = *(reinterpret_cast<Tables *>(gz_smem) + threadIdx.x);
     for (;;) {
         const uint32_t i = atomicAdd(ticket, 1u);
         if (i >= n) return;
         const Job j = jobs[i];
-        uint64_t len = 0;
-        const int rc = gunzip(in + j.in_off, j.in_len, out + j.out_off, j.out_cap, T, check_crc ? crc_tab : nullptr, &len);
+        uint32_t len = 0;
+        const int rc = gunzip(in + j.in_off, j.in_len, out + j.out_off, (uint32_t)j.out_cap, T, check_crc ? d_crc8 : nullptr, &len);
         Result r;
         r.out_len = len; r.status = rc; r.pad = 0;
         res[i] = r;

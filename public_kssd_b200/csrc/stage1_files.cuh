@@ -329,11 +329,13 @@ static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, cons
             if (!d_jobs || !d_res || !d_ticket) return fail(KSSD_E_NOMEM, "kssd_stage1_files: out of device memory");
             CU(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(kssd::gz::Job), cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemsetAsync(d_ticket, 0, 4, c->stream));
-            // one file per warp while the SMs have room for the warps (32 CTAs each), then more lanes per warp
-            const uint32_t max_ctas = (uint32_t)c->sm_count * 32u;
-            const uint32_t active = std::min<uint32_t>(32u, (nj + max_ctas - 1) / max_ctas);
+            // one file per warp while the SMs have room for the warps' tables and rings (12 per SM), then more lanes per warp;
+            // whatever does not fit at once is pulled by ticket as threads finish
+            const uint32_t per_sm = (uint32_t)((227u * 1024u) / (sizeof(kssd::gz::Tables) + 1024u));
+            const uint32_t max_ctas = (uint32_t)c->sm_count * per_sm;
+            const uint32_t active = std::min<uint32_t>(per_sm, (nj + max_ctas - 1) / max_ctas);
             const uint32_t grid = std::min<uint32_t>(max_ctas, (nj + active - 1) / active);
-            const size_t smem = 1024 + (size_t)active * sizeof(kssd::gz::Tables);
+            const size_t smem = (size_t)active * sizeof(kssd::gz::Tables);
             CU(cudaFuncSetAttribute(kssd::gz::gunzip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kssd::gz::gunzip_kernel<<<grid, 32, smem, c->stream>>>(d_in, d_text, d_jobs, d_res, nj, active, d_ticket, check_crc ? 1 : 0);
             LAUNCHED(1);
@@ -427,12 +429,14 @@ extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int
     R->status.assign(n_files, 0);
     R->file_bytes.assign(n_files, 0);
 
-    // enough .gz files to keep the GPU's decoder busy (or KSSD_GZ_GPU=1): compressed bytes cross PCIe, inflate runs on the device
+    // enough .gz files to keep the GPU's decoder busy (or KSSD_GZ_GPU=1): compressed bytes cross PCIe, inflate runs on the device.
+    // One stream takes the GPU thread ~0.13 s per MB of text however many run beside it (up to ~1,800 at once), the host's cores
+    // inflate ~4 GB/s together: measured break-even at about 600 files of 5 MB (profiles/r2_gz_summary.md)
     {
         int n_gz = 0;
         for (int i = 0; i < n_files; i++) n_gz += tasks[i].gz ? 1 : 0;
         const char *eg = getenv("KSSD_GZ_GPU");
-        bool use = !(pipecmd && pipecmd[0]) && n_gz > 0 && (eg ? atoi(eg) != 0 : n_gz >= 64);
+        bool use = !(pipecmd && pipecmd[0]) && n_gz > 0 && (eg ? atoi(eg) != 0 : n_gz >= 640);
         std::vector<GzFile> F(n_files);
         for (int i = 0; i < n_files && use; i++) {
             struct stat st;
@@ -677,12 +681,14 @@ extern "C" int kssd_stage1_gz_info(const kssd_stage1_t *s, int *on_gpu, double *
 extern "C" int kssd_gunzip_host(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len)
 {
     if (!in || !out_len || (cap && !out)) return fail(KSSD_E_INVAL, "kssd_gunzip_host: null");
-    static uint32_t crc_tab[256];
-    static std::once_flag once;
-    std::call_once(once, [] { kssd::gz::crc32_table(crc_tab, 0, 1); });
+    if (cap > 0xffffffffull) return fail(KSSD_E_INVAL, "kssd_gunzip_host: output larger than 4 GiB");
+    std::vector<uint8_t> padded(n + kssd::gz::kInPad, 0);             // the decoder reads whole words: zeros behind the data
+    memcpy(padded.data(), in, n);
+    std::vector<uint64_t> aligned((cap + 7) / 8 + 1);                  // and checks the CRC from an 8-byte aligned text
     std::unique_ptr<kssd::gz::Tables> T(new kssd::gz::Tables);
-    uint64_t len = 0;
-    const int rc = kssd::gz::gunzip(in, n, out, cap, *T, crc_tab, &len);
+    uint32_t len = 0;
+    const int rc = kssd::gz::gunzip(padded.data(), n, reinterpret_cast<uint8_t *>(aligned.data()), (uint32_t)cap, *T, kssd::gz::h_crc8, &len);
+    if (rc == 0 && len) memcpy(out, aligned.data(), len);
     *out_len = (size_t)len;
     return rc;
 }

@@ -121,10 +121,10 @@ def _many_fasta(n_files, seed):
 
 def test_gz_inflated_on_the_gpu(gpu_ctx_l3k10, tmp_path, monkeypatch):
     """.gz files copied to the device as they are and inflated there (csrc/inflate.cuh, one file per thread): same sketch as zlib on
-    the host and as the batch API on the decoded bytes; plain files may sit in the same batch; 70 files switch it on by themselves;
+    the host and as the batch API on the decoded bytes; plain files may sit in the same batch; a handful of files;
     small batches (KSSD_GZ_BATCH_BYTES); a two-member file and a damaged one go through the host path (which reports the damage)."""
     from public_kssd_b200 import kssd
-    files = _many_fasta(70, 100)
+    files = _many_fasta(80, 100)
     files["zz_empty"] = np.frombuffer(b"", dtype=np.uint8)
     names = sorted(files)
     paths = []
@@ -139,20 +139,17 @@ def test_gz_inflated_on_the_gpu(gpu_ctx_l3k10, tmp_path, monkeypatch):
                 f.write(raw)
         paths.append(p)
     want = gpu_ctx_l3k10.sketch([files[n] for n in names])
-    monkeypatch.setenv("KSSD_GZ_GPU", "0")
-    host, th = gpu_ctx_l3k10.sketch_files(paths, threads=4)
+    host, th = gpu_ctx_l3k10.sketch_files(paths, threads=4)      # 72 .gz files: below the library's threshold (640), zlib on the host
     assert not th["gz_on_gpu"]
-    monkeypatch.delenv("KSSD_GZ_GPU")
-    for batch in (None, "1048576"):
+    monkeypatch.setenv("KSSD_GZ_GPU", "1")
+    for batch in (None, "1048576"):      # (KSSD_GZ_BATCH_BYTES has a floor of 1 MiB: about 2 MB of text -> 2 batches)
         if batch:
             monkeypatch.setenv("KSSD_GZ_BATCH_BYTES", batch)
         sk, t = gpu_ctx_l3k10.sketch_files(paths, threads=4)
-        assert t["gz_on_gpu"] and t["bytes"] == sum(v.size for v in files.values()) and (t["batches"] == 1 if not batch else t["batches"] >= 3)
+        assert t["gz_on_gpu"] and t["bytes"] == sum(v.size for v in files.values()) and (t["batches"] == 1 if not batch else t["batches"] >= 2)
         for got in (sk, host):
             assert np.array_equal(got.index[0], want.index[0]) and np.array_equal(got.ids[0], want.ids[0])
     monkeypatch.delenv("KSSD_GZ_BATCH_BYTES")
-    # forced on for a handful of files
-    monkeypatch.setenv("KSSD_GZ_GPU", "1")
     few = [p for p in paths if p.suffix == ".gz"][:5]
     sk5, t5 = gpu_ctx_l3k10.sketch_files(few, threads=2)
     assert t5["gz_on_gpu"]
@@ -174,3 +171,16 @@ def test_gz_inflated_on_the_gpu(gpu_ctx_l3k10, tmp_path, monkeypatch):
     bad.write_bytes(bytes(dmg))
     with pytest.raises(kssd.KssdError):
         gpu_ctx_l3k10.sketch_files([bad] + few, threads=2)
+
+
+def test_many_gz_files_switch_the_gpu_decoder_on(gpu_ctx_l3k10, tmp_path):
+    """640 or more .gz files in one call: the library inflates on the GPU without being told to."""
+    datas, paths = [], []
+    for i in range(650):
+        d = synth.to_fasta(synth.random_bases(400 + i % 50, 7000 + i), f"s{i}", width=70)
+        p = tmp_path / f"s{i:04d}.fa.gz"
+        p.write_bytes(gzip.compress(d.tobytes(), 1))
+        datas.append(d); paths.append(p)
+    sk, t = gpu_ctx_l3k10.sketch_files(paths, threads=4)
+    want = gpu_ctx_l3k10.sketch(datas)
+    assert t["gz_on_gpu"] and np.array_equal(sk.index[0], want.index[0]) and np.array_equal(sk.ids[0], want.ids[0])
