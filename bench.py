@@ -260,7 +260,7 @@ def files_leg(ctx, host_np, goff, glen, genome_len, ids_e2e, ix_e2e, n_plain=200
             on_disk = int(sum(f.stat().st_size for f in paths))
             out[name] = {"value": bp / best["total_s"] / 1e9, "unit": "Gbp/s", "files": n, "text_bytes": best["bytes"], "bytes_on_disk": on_disk,
                          "total_s": best["total_s"], "read_s": best["read_s"], "gpu_s": best["gpu_s"], "text_gb_per_s": best["bytes"] / best["total_s"] / 1e9,
-                         "batches": best["batches"], "batch_bytes": best_bb or ("default (1 GiB)" if not best.get("gz_on_gpu") else "8 GiB decoded"),
+                         "batches": best["batches"], "batch_bytes": best_bb or ("default (1 GiB)" if not best.get("gz_on_gpu") else "16 GiB decoded"),
                          "matches_device_path": same}
             if name != "plain":
                 out[name].update({"inflate": "GPU (csrc/inflate.cuh, one file per thread)" if best.get("gz_on_gpu") else "zlib on the host cores",

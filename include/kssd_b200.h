@@ -136,7 +136,7 @@ void kssd_sketch_free(kssd_sketch_t *s);
  * n_threads <= 0: all hardware threads; batch_bytes 0: 1 GiB.  Modes: every KSSD_MODE_* but BYREAD.
  * With 640 or more .gz files in the call (KSSD_GZ_GPU=1 / 0 forces / forbids it) the files are copied to the device as
  * they are and inflated THERE, one file per thread (csrc/inflate.cuh; ISIZE and CRC-32 of every member checked): the
- * compressed bytes cross PCIe and the host cores only read.  Batches are then sized by decoded bytes (8 GiB, or
+ * compressed bytes cross PCIe and the host cores only read.  Batches are then sized by decoded bytes (16 GiB, or
  * KSSD_GZ_BATCH_BYTES) and batch_bytes is ignored.  A file that does not decode into its ISIZE bytes (several gzip
  * members, damage) sends the whole call through zlib on the host, which reports damage as before. */
 typedef struct kssd_stage1 kssd_stage1_t;

@@ -21,13 +21,14 @@ try:
     paths = [m[0] for m in made]
     on_disk = sum(p.stat().st_size for p in paths)
     print(f"{n_max} files, {sum(m[1] for m in made)/1e9:.2f} GB of text, {on_disk/1e9:.2f} GB on disk", flush=True)
-    for n in (64, 200, 400, n_max):
+    sizes = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else sorted(set([64, 200, 400, 1000, 2000, n_max]))
+    for n in sizes:
         if n > n_max: continue
         res = {}
         for mode in ("0", "1"):
             os.environ["KSSD_GZ_GPU"] = mode
             best = None
-            for rep in range(3):
+            for rep in range(2 if n > 1000 else 3):
                 sk, t = ctx.sketch_files(paths[:n])
                 if best is None or t["total_s"] < best["total_s"]: best = t
             res[mode] = (best, sk.ids[0].copy())

@@ -6,16 +6,17 @@
 //
 // What one thread does per symbol is therefore what counts:
 //   * the bit buffer (64 bits) is refilled 32 bits at a time from aligned words, the next word requested one refill ahead;
-//   * literal/length codes go through an 11-bit table whose entries hold up to TWO literals, or a length code's base and
+//   * literal/length codes go through a 10-bit table whose entries hold up to TWO literals, or a length code's base and
 //     extra-bit count; distance codes through an 8-bit table of base / extra bits; longer codes by the canonical count/symbol walk;
-//   * the last 8 KiB of output are mirrored in a ring next to the tables (shared memory): `gzip -1` codes random DNA as nothing
-//     but 3-6 byte matches a few dozen bytes back, and a match served from the ring costs a shared-memory read instead of an L2
-//     round trip that the in-order thread would have to sit out; farther matches read the output itself;
-//   * output bytes are collected in a register and stored eight at a time;
+//   * match bytes are loaded in groups before they are stored (independent loads; an overlapping match stays bytewise);
 //   * offsets inside a file are 32-bit (a file decodes to < 4 GiB here; the caller sends larger ones to zlib).
+// Measured (B200, `gzip -1` of random DNA = nothing but 3-6 byte matches): ~1,000 cycles per match however the copy is done -- a ring
+// of the last 8 KiB in shared memory, eight-byte stores from a register, base / extra bits folded into the table entries each left
+// the 0.66-0.68 s per 5 MB file where it was: one thread issues a dependent instruction every ~10 cycles, and two files in one
+// warp take turns (divergence).  What does scale is the number of WARPS, so the tables are kept small (5.8 KB: 32 streams per SM).
 // Tables live in memory the caller provides (shared memory on the GPU).  Members are decoded one after another (multi-member
 // files, `cat a.gz b.gz`); every member's ISIZE and CRC-32 (slicing-by-8) are checked.  The same code compiles for the host, where
-// the CPU test suite runs it against zlib.  The input must be readable kInPad bytes past its end (zeros), the output 8-byte aligned.
+// the CPU test suite runs it against zlib.  The input must be readable kInPad bytes past its end (zeros).
 #pragma once
 #include <cstdint>
 
@@ -30,7 +31,7 @@ namespace gz {
 
 enum : int { kOk = 0, kBadHeader = -1, kBadData = -2, kOutputFull = -3, kTruncated = -4, kBadCrc = -5, kBadSize = -6 };
 
-constexpr int kLRoot = 11, kDRoot = 8;
+constexpr int kLRoot = 10, kDRoot = 8;
 constexpr uint32_t kInPad = 16;       // readable zero bytes behind the compressed data
 
 static const uint32_t h_crc8[2048] = {
@@ -41,8 +42,6 @@ __device__ const uint32_t d_crc8[2048] = {
 #include "crc32_slice8.inc"
 };
 #endif
-
-constexpr uint32_t kWin = 8192;       // bytes of output mirrored in the ring
 
 // build() leaves symbol | code length << 16 in an entry (0: the code is longer than the root -> canonical walk); then
 //   literal/length table: literals   lit0 | lit1 << 8 | bits consumed << 16 | n << 24 (n = 1, 2)
@@ -55,7 +54,6 @@ struct Tables {
     uint32_t dfast[1 << kDRoot];
     uint16_t lcount[16], dcount[16];  // canonical walk: codes per length, symbols in code order
     uint16_t lsym[288], dsym[32];
-    uint8_t win[kWin];
 };
 
 #define KSSD_GZ_CONST_TABLES(Q)                                                                                                                      \
@@ -114,6 +112,30 @@ KGZ uint32_t take(Bits &b, int n)                         // n <= 16, bits are t
     b.bb >>= n;
     b.bc -= n;
     return v;
+}
+
+KGZ uint32_t bfe(uint32_t v, uint32_t pos, uint32_t n)      // n bits of v from bit pos on (pos + n <= 32)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(n));
+    return r;
+#else
+    return (v >> pos) & (uint32_t)((1ull << n) - 1ull);
+#endif
+}
+KGZ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)      // bits sh .. sh + 31 of hi:lo, sh < 32
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+KGZ void drop(Bits &b, uint32_t n)
+{
+    b.bb >>= n;
+    b.bc -= (int)n;
 }
 
 KGZ uint32_t reverse_bits(uint32_t v, int n)
@@ -222,28 +244,14 @@ KGZ int decode_small(Bits &b, const uint32_t *fast, int root, const uint16_t *co
     return decode_walk(b, count, sym);
 }
 
-// the output of one file: bytes are mirrored in the ring and collected in `acc` until eight can be stored at once
+// the output of one file
 struct Out {
-    uint8_t *base;                    // 8-byte aligned
+    uint8_t *base;
     uint32_t o;
-    uint64_t acc;                     // bytes [o & ~7, o)
 };
-KGZ void put(Out &w, uint8_t *win, uint32_t c)
-{
-    win[w.o & (kWin - 1u)] = (uint8_t)c;
-    w.acc |= (uint64_t)c << (8u * (w.o & 7u));
-    w.o++;
-    if ((w.o & 7u) == 0) {
-        *reinterpret_cast<uint64_t *>(w.base + (w.o - 8u)) = w.acc;
-        w.acc = 0;
-    }
-}
-KGZ void flush_partial(const Out &w)                      // the bytes still in acc, bytewise (acc stays: the next put goes on)
-{
-    for (uint32_t k = 0; k < (w.o & 7u); k++) w.base[(w.o & ~7u) + k] = (uint8_t)(w.acc >> (8u * k));
-}
+KGZ void put(Out &w, uint32_t c) { w.base[w.o++] = (uint8_t)c; }
 
-// CRC-32 of p[0 .. n), p + `skew` 8-byte aligned for some skew < 8 handled bytewise first; t: the slicing-by-8 tables
+// CRC-32 of p[0 .. n): bytes up to the first 8-byte boundary one by one, then eight at a time; t: the slicing-by-8 tables
 KGZ uint32_t crc32_slice8(const uint32_t *t, const uint8_t *p, uint32_t n)
 {
     uint32_t crc = 0xffffffffu, i = 0;
@@ -276,7 +284,7 @@ KGZ int inflate_stream(Bits &b, uint64_t end, Tables &T, Out &w, uint32_t cap)
             if (n > cap - w.o) return kOutputFull;
             for (uint32_t i = 0; i < n; i++) {
                 refill(b);
-                put(w, T.win, take(b, 8));
+                put(w, take(b, 8));
                 if ((i & 1023u) == 0 && bits_pos(b) > end) return kTruncated;
             }
             if (bits_pos(b) > end) return kTruncated;
@@ -331,66 +339,74 @@ KGZ int inflate_stream(Bits &b, uint64_t end, Tables &T, Out &w, uint32_t cap)
             uint32_t guard = 0;
             for (;;) {
                 refill(b);                                // > 32 bits: a literal/length code and its extra bits (15 + 5)
-                uint32_t e = T.lfast[(uint32_t)b.bb & ((1u << kLRoot) - 1u)];
-                if (e == 0) {                             // a code longer than the root: the walk, then the entry the table would have held
-                    const int s = decode_walk(b, T.lcount, T.lsym);
-                    if (s < 0) return kBadData;
-                    if (s < 256) e = (uint32_t)s | (1u << 24);
-                    else if (s == 256) e = kEob;
-                    else if (s < 286) e = tab::lbase[s - 257] | ((uint32_t)tab::lext[s - 257] << 9) | kLen;
-                    else e = kBad;
-                } else {
-                    const uint32_t l = (e >> 16) & 31u;
-                    b.bb >>= l;
-                    b.bc -= (int)l;
-                }
+                uint32_t lo = (uint32_t)b.bb;
+                const uint32_t e = T.lfast[lo & ((1u << kLRoot) - 1u)];
+                uint32_t len = 0;
                 if (e & kLen) {
-                    const uint32_t len = (e & 0x1ffu) + take(b, (int)((e >> 9) & 7u));
-                    refill(b);                            // a distance code and its extra bits (15 + 13)
-                    uint32_t d = T.dfast[(uint32_t)b.bb & ((1u << kDRoot) - 1u)];
-                    if (d == 0) {
-                        const int ds = decode_walk(b, T.dcount, T.dsym);
-                        if (ds < 0 || ds >= 30) return kBadData;
-                        d = tab::dbase[ds] | ((uint32_t)tab::dext[ds] << 15);
-                    } else {
-                        if (d & kBad) return kBadData;
-                        const uint32_t l = (d >> 19) & 15u;
-                        b.bb >>= l;
-                        b.bc -= (int)l;
+                    const uint32_t cl = (e >> 16) & 31u, xb = (e >> 9) & 7u;
+                    len = (e & 0x1ffu) + bfe(lo, cl, xb);
+                    drop(b, cl + xb);
+                } else if (e != 0) {
+                    drop(b, (e >> 16) & 31u);
+                    const uint32_t nl = (e >> 24) & 3u;
+                    if (nl) {                             // one or two literals
+                        if (cap - w.o < nl) return kOutputFull;
+                        put(w, e & 0xffu);
+                        if (nl == 2u) put(w, (e >> 8) & 0xffu);
+                        continue;
                     }
-                    const uint32_t dist = (d & 0x7fffu) + take(b, (int)((d >> 15) & 15u));
-                    if (dist > w.o - start) return kBadData;      // (a member never reaches back into the one before)
-                    if (len > cap - w.o) return kOutputFull;
-                    uint32_t i = 0;
-                    if (dist <= kWin) {                   // from the ring (read before the slot is rewritten when dist == kWin)
-                        if (dist >= 4u)
-                            for (; i + 4 <= len; i += 4) {
-                                const uint32_t p = w.o - dist;
-                                const uint32_t c0 = T.win[p & (kWin - 1u)], c1 = T.win[(p + 1u) & (kWin - 1u)], c2 = T.win[(p + 2u) & (kWin - 1u)],
-                                               c3 = T.win[(p + 3u) & (kWin - 1u)];
-                                put(w, T.win, c0); put(w, T.win, c1); put(w, T.win, c2); put(w, T.win, c3);
-                            }
-                        for (; i < len; i++) put(w, T.win, T.win[(w.o - dist) & (kWin - 1u)]);
-                    } else {                              // from the output itself: all of it is stored (dist > 8 KiB, len <= 258)
-                        for (; i + 4 <= len; i += 4) {
-                            const uint8_t *src = w.base + (w.o - dist);
-                            const uint32_t c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
-                            put(w, T.win, c0); put(w, T.win, c1); put(w, T.win, c2); put(w, T.win, c3);
-                        }
-                        for (; i < len; i++) put(w, T.win, w.base[w.o - dist]);
+                    if (e & kEob) break;
+                    return kBadData;
+                } else {                                  // a code longer than the root
+                    const int s = decode_walk(b, T.lcount, T.lsym);
+                    if (s < 0 || s >= 286) return kBadData;
+                    if (s < 256) {
+                        if (cap == w.o) return kOutputFull;
+                        put(w, (uint32_t)s);
+                        continue;
                     }
-                    if ((++guard & 255u) == 0 && bits_pos(b) > end) return kTruncated;
-                    continue;
+                    if (s == 256) break;
+                    len = tab::lbase[s - 257] + take(b, tab::lext[s - 257]);
                 }
-                const uint32_t nl = (e >> 24) & 3u;
-                if (nl) {                                 // one or two literals
-                    if (cap - w.o < nl) return kOutputFull;
-                    put(w, T.win, e & 0xffu);
-                    if (nl == 2u) put(w, T.win, (e >> 8) & 0xffu);
-                    continue;
+                refill(b);                                // a distance code and its extra bits (15 + 13)
+                lo = (uint32_t)b.bb;
+                const uint32_t d = T.dfast[lo & ((1u << kDRoot) - 1u)];
+                uint32_t dist;
+                if (d != 0) {
+                    if (d & kBad) return kBadData;
+                    const uint32_t dl = (d >> 19) & 15u, xd = (d >> 15) & 15u;
+                    dist = (d & 0x7fffu) + bfe(lo, dl, xd);
+                    drop(b, dl + xd);
+                } else {
+                    const int ds = decode_walk(b, T.dcount, T.dsym);
+                    if (ds < 0 || ds >= 30) return kBadData;
+                    dist = tab::dbase[ds] + take(b, tab::dext[ds]);
                 }
-                if (e & kEob) break;
-                return kBadData;
+                if (dist > w.o - start) return kBadData;  // (a member never reaches back into the one before)
+                if (len > cap - w.o) return kOutputFull;
+                const uint8_t *src = w.base + (w.o - dist);
+                uint8_t *dst = w.base + w.o;
+                uint32_t i = 0;
+                if (dist >= 8u) {
+                    for (; i + 8 <= len; i += 8) {
+                        const uint8_t c0 = src[i], c1 = src[i + 1], c2 = src[i + 2], c3 = src[i + 3], c4 = src[i + 4], c5 = src[i + 5], c6 = src[i + 6], c7 = src[i + 7];
+                        dst[i] = c0; dst[i + 1] = c1; dst[i + 2] = c2; dst[i + 3] = c3; dst[i + 4] = c4; dst[i + 5] = c5; dst[i + 6] = c6; dst[i + 7] = c7;
+                    }
+                    if (i + 4 <= len) {
+                        const uint8_t c0 = src[i], c1 = src[i + 1], c2 = src[i + 2], c3 = src[i + 3];
+                        dst[i] = c0; dst[i + 1] = c1; dst[i + 2] = c2; dst[i + 3] = c3;
+                        i += 4;
+                    }
+                    if (i < len) {                        // 1 .. 3 left
+                        const uint8_t c0 = src[i], c1 = i + 1 < len ? src[i + 1] : (uint8_t)0, c2 = i + 2 < len ? src[i + 2] : (uint8_t)0;
+                        dst[i] = c0;
+                        if (i + 1 < len) dst[i + 1] = c1;
+                        if (i + 2 < len) dst[i + 2] = c2;
+                    }
+                } else
+                    for (; i < len; i++) dst[i] = src[i];
+                w.o += len;
+                if ((++guard & 255u) == 0 && bits_pos(b) > end) return kTruncated;
             }
             if (bits_pos(b) > end) return kTruncated;
         } else return kBadData;
@@ -403,7 +419,7 @@ KGZ int gunzip(const uint8_t *in, uint64_t n, uint8_t *out, uint32_t cap, Tables
 {
     uint64_t pos = 0;
     Out w;
-    w.base = out; w.o = 0; w.acc = 0;
+    w.base = out; w.o = 0;
     int members = 0;
     while (pos < n) {
         if (n - pos < 18 || in[pos] != 0x1f || in[pos + 1] != 0x8b || in[pos + 2] != 8) {
@@ -429,7 +445,6 @@ KGZ int gunzip(const uint8_t *in, uint64_t n, uint8_t *out, uint32_t cap, Tables
         const uint32_t o0 = w.o;
         const int rc = inflate_stream(b, n, T, w, cap);
         if (rc != kOk) return rc;
-        flush_partial(w);
         pos = bits_pos(b);
         if (pos + 8 > n) return kTruncated;
         const uint32_t crc = (uint32_t)in[pos] | ((uint32_t)in[pos + 1] << 8) | ((uint32_t)in[pos + 2] << 16) | ((uint32_t)in[pos + 3] << 24);

@@ -207,8 +207,8 @@ static int append_results(kssd_stage1 *R, kssd_sketch_t *sk, const std::vector<i
 // ---- .gz decoded on the GPU (inflate.cuh) -------------------------------------------------------------------------------
 // The files of a batch are read as they are (compressed) into the pinned staging buffer and copied to the device; one thread per
 // file inflates into the batch's text buffer (every file's decoded size is its gzip ISIZE), plain files of the batch are copied
-// device to device, and the batch is sketched where it lies.  A batch is sized by DECODED bytes (8 GiB unless
-// KSSD_GZ_BATCH_BYTES says otherwise): the decoder's parallelism is the number of files in flight.  Any file the kernel cannot
+// device to device, and the batch is sketched where it lies.  A batch is sized by DECODED bytes (16 GiB unless
+// KSSD_GZ_BATCH_BYTES says otherwise, the batches of a call equal in size): the decoder's parallelism is the number of files in flight.  Any file the kernel cannot
 // finish in its ISIZE bytes (several gzip members, corrupt data, CRC mismatch) sets *fall_back: the caller redoes the call with
 // zlib on the host, which also produces the error message if the file is really broken.
 struct GzFile { bool gz = false; uint64_t csize = 0, dsize = 0; };
@@ -230,15 +230,19 @@ static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, cons
 {
     const int mode = opts ? opts->mode : KSSD_MODE_FASTA;
     const char *eb = getenv("KSSD_GZ_BATCH_BYTES");
-    const uint64_t cap_dec = eb ? std::max<uint64_t>(strtoull(eb, nullptr, 10), 1u << 20) : (8ull << 30);
+    const uint64_t cap_dec = eb ? std::max<uint64_t>(strtoull(eb, nullptr, 10), 1u << 20) : (16ull << 30);
     const bool check_crc = !getenv("KSSD_GZ_NOCRC");
     std::vector<std::pair<int, int>> batches;
     {
+        // batches of equal decoded size (a short last batch would leave most of the GPU's decoder threads idle for a whole pass)
+        uint64_t total = 0;
+        for (int i = 0; i < n_files; i++) total += (F[i].dsize + 15) & ~15ull;
+        const uint64_t nb = std::max<uint64_t>(1, (total + cap_dec - 1) / cap_dec), per = (total + nb - 1) / nb;
         uint64_t acc = 0;
         int lo = 0;
         for (int i = 0; i < n_files; i++) {
             const uint64_t need = (F[i].dsize + 15) & ~15ull;
-            if (i > lo && acc + need > cap_dec) { batches.push_back({lo, i}); lo = i; acc = 0; }
+            if (i > lo && (acc + need > cap_dec || acc >= per)) { batches.push_back({lo, i}); lo = i; acc = 0; }
             acc += need;
         }
         batches.push_back({lo, n_files});
@@ -329,12 +333,11 @@ static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, cons
             if (!d_jobs || !d_res || !d_ticket) return fail(KSSD_E_NOMEM, "kssd_stage1_files: out of device memory");
             CU(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(kssd::gz::Job), cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemsetAsync(d_ticket, 0, 4, c->stream));
-            // one file per warp while the SMs have room for the warps' tables and rings (12 per SM), then more lanes per warp;
-            // whatever does not fit at once is pulled by ticket as threads finish
-            const uint32_t per_sm = (uint32_t)((227u * 1024u) / (sizeof(kssd::gz::Tables) + 1024u));
-            const uint32_t max_ctas = (uint32_t)c->sm_count * per_sm;
-            const uint32_t active = std::min<uint32_t>(per_sm, (nj + max_ctas - 1) / max_ctas);
-            const uint32_t grid = std::min<uint32_t>(max_ctas, (nj + active - 1) / active);
+            // one file per warp (two files in a warp would only take turns); as many warps as the SMs hold (32 each), the rest of
+            // the files pulled by ticket as warps finish
+            const uint32_t per_sm = std::min<uint32_t>(32u, (uint32_t)((227u * 1024u) / (sizeof(kssd::gz::Tables) + 1024u)));
+            const uint32_t active = 1;
+            const uint32_t grid = std::min<uint32_t>((uint32_t)c->sm_count * per_sm, nj);
             const size_t smem = (size_t)active * sizeof(kssd::gz::Tables);
             CU(cudaFuncSetAttribute(kssd::gz::gunzip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kssd::gz::gunzip_kernel<<<grid, 32, smem, c->stream>>>(d_in, d_text, d_jobs, d_res, nj, active, d_ticket, check_crc ? 1 : 0);
