@@ -238,12 +238,13 @@ static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, cons
         uint64_t total = 0;
         for (int i = 0; i < n_files; i++) total += (F[i].dsize + 15) & ~15ull;
         const uint64_t nb = std::max<uint64_t>(1, (total + cap_dec - 1) / cap_dec), per = (total + nb - 1) / nb;
-        uint64_t acc = 0;
+        uint64_t acc = 0, left = total;                   // left: bytes of the files not placed yet
         int lo = 0;
         for (int i = 0; i < n_files; i++) {
             const uint64_t need = (F[i].dsize + 15) & ~15ull;
-            if (i > lo && (acc + need > cap_dec || acc >= per)) { batches.push_back({lo, i}); lo = i; acc = 0; }
+            if (i > lo && (acc + need > cap_dec || (acc >= per && left > 0))) { batches.push_back({lo, i}); lo = i; acc = 0; }
             acc += need;
+            left -= need;
         }
         batches.push_back({lo, n_files});
     }
