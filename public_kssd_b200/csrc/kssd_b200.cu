@@ -2290,6 +2290,7 @@ static int format_text_dev(kssd_ctx *c, const StatRow *d_rows, uint64_t n, int n
     uint32_t handed[2] = {0, 0};
     StreamScratch scr(c->stream);
     char *d_text = nullptr;
+    if (n && (n_qry <= 0 || n_ref <= 0)) return fail(KSSD_E_INVAL, "distance.out text: rows without names");
     if (n) {
         const size_t qb = (size_t)n_qry * name_stride, rb = (size_t)n_ref * name_stride;
         char *d_qn = static_cast<char *>(scr.alloc(qb)), *d_rn = static_cast<char *>(scr.alloc(rb));
