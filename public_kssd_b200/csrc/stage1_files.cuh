@@ -305,8 +305,13 @@ static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, cons
             soff[i - lo] = sbytes; sbytes += staged(i);
             goff[i - lo] = tbytes; glen[i - lo] = F[i].dsize; tbytes += (F[i].dsize + 15) & ~15ull;
         }
-        CU(c->gzin.ensure(sbytes + 64));
-        CU(c->gztext.ensure(tbytes + 1024));
+        if (c->gzin.ensure(sbytes + 64) != cudaSuccess || c->gztext.ensure(tbytes + 1024) != cudaSuccess) {
+            cudaGetLastError();                           // no room for the batch on the device: the host path needs far less
+            c->gzin.release();
+            c->gztext.release();
+            *fall_back = true;
+            return KSSD_OK;
+        }
         uint8_t *d_in = c->gzin.as<uint8_t>(), *d_text = c->gztext.as<uint8_t>();
         CU(cudaMemcpyAsync(d_in, c->stag[k & 1], sbytes, cudaMemcpyHostToDevice, c->stream));
         std::vector<int> order;                           // gz files, largest first: the ticket order
@@ -454,6 +459,7 @@ extern "C" int kssd_stage1_files_ex(kssd_ctx_t *c, const char *const *paths, int
         if (use) {
             bool fall_back = false;
             const int rc = run_gz_gpu(c, paths, n_files, opts, nt, F, R, &fall_back);
+            if (c->gztext.cap > (1ull << 30)) { c->gzin.release(); c->gztext.release(); }      // (a big batch's buffers are not kept: Stage II / III want the memory)
             if (rc != KSSD_OK) { delete R; return rc; }
             if (!fall_back) {
                 R->gz_on_gpu = true;
