@@ -264,6 +264,7 @@ static int run_gz_gpu(kssd_ctx_t *c, const char *const *paths, int n_files, cons
     std::vector<char> read_ok(batches.size(), 1);
     auto start_read = [&](size_t k) -> std::thread {
         return std::thread([&, k] {
+            cudaSetDevice(c->device);                     // (this thread may pin the staging buffer: on the context's device, not on device 0)
             const int lo = batches[k].first, hi = batches[k].second;
             uint64_t bytes = 0;
             std::vector<uint64_t> soff(hi - lo);
