@@ -67,3 +67,33 @@ def test_header_fields_members_and_damage(tmp_path):
     bad[-6] ^= 1                                                           # the stored CRC itself
     assert _gunzip(bytes(bad), len(a))[0] == -5
     assert _gunzip(b"not a gzip file at all....", 100)[0] == -1
+
+
+def test_decoder_on_random_mixtures():
+    """200 buffers of random structure (alphabet size, repeat density, run lengths, size 0 .. 300 KB), random level / strategy /
+    window size: the decoder returns exactly what zlib compressed, and never accepts a buffer with a flipped bit as the original."""
+    rng = np.random.default_rng(2024)
+    for case in range(200):
+        n = int(rng.integers(0, 300_000)) if case % 5 else int(rng.integers(0, 64))
+        alpha = int(rng.choice([2, 4, 5, 20, 256]))
+        data = rng.integers(0, alpha, n, dtype=np.uint8) + (65 if alpha < 200 else 0)
+        for _ in range(int(rng.integers(0, 30))):               # repeats at random distances (short and beyond 8 KiB)
+            if n < 100:
+                break
+            ln = int(rng.integers(3, min(400, n // 2)))
+            src = int(rng.integers(0, n - ln))
+            dst = int(rng.integers(0, n - ln))
+            data[dst:dst + ln] = data[src:src + ln].copy()
+        if case % 7 == 0 and n > 10:
+            data[: n // 2] = data[0]                           # a long run
+        raw = data.astype(np.uint8).tobytes()
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, 16 + int(rng.integers(9, 16)), int(rng.integers(1, 10)),
+                              int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED])))
+        z = co.compress(raw) + co.flush()
+        rc, out = _gunzip(z, len(raw))
+        assert rc == 0 and out == raw, case
+        if len(z) > 30:
+            bad = bytearray(z)
+            bad[int(rng.integers(10, len(z) - 8))] ^= 1 << int(rng.integers(0, 8))
+            rc, out = _gunzip(bytes(bad), len(raw))
+            assert rc != 0 or out == raw, case                 # (a flip inside the header's mtime / OS bytes changes nothing)
