@@ -6,6 +6,8 @@
 // read) or inflate .gz files with zlib into a private buffer that is copied to its place once its size is known.  A
 // batch is closed when the next file would not fit; a GPU thread copies it to the device and sketches it while the
 // readers fill the second staging buffer.  Results of all batches are appended in file order.
+// A call with 640 or more .gz files takes the other road (run_gz_gpu below): the files go to the device as they are and are
+// inflated there, one file per warp (inflate.cuh).
 #pragma once
 #include <fcntl.h>
 #include <sys/stat.h>
